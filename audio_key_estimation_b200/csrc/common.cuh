@@ -1,0 +1,83 @@
+// common.cuh -- shared host/device helpers for libake_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+
+#include "../../include/ake_b200.h"
+
+namespace ake {
+
+// ---- error plumbing -------------------------------------------------------------------------
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+void set_last_error(const std::string& msg);
+int64_t& launch_counter();
+
+[[noreturn]] inline void fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  throw Error(code, buf);
+}
+
+#define AKE_CUDA(expr)                                                                          \
+  do {                                                                                          \
+    cudaError_t e__ = (expr);                                                                   \
+    if (e__ != cudaSuccess)                                                                     \
+      ::ake::fail(AKE_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+// Call after every kernel launch: counts the launch and surfaces launch-configuration errors.
+#define AKE_LAUNCHED()                                                                          \
+  do {                                                                                          \
+    ++::ake::launch_counter();                                                                  \
+    AKE_CUDA(cudaGetLastError());                                                               \
+  } while (0)
+
+// Wrap every extern "C" body: exceptions never cross the ABI.
+template <class F>
+inline int guarded(F&& f) {
+  try {
+    f();
+    return AKE_OK;
+  } catch (const Error& e) {
+    set_last_error(e.what());
+    return e.code;
+  } catch (const std::exception& e) {
+    set_last_error(e.what());
+    return AKE_ERR_INVALID;
+  }
+}
+
+inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Bump allocator over the caller's workspace (256-byte aligned slices).
+struct Arena {
+  char* base;
+  size_t cap, off = 0;
+  Arena(void* b, size_t c) : base(static_cast<char*>(b)), cap(c) {}
+  template <class T>
+  T* take(size_t n) {
+    size_t bytes = align_up(n * sizeof(T), 256);
+    if (base && off + bytes > cap) fail(AKE_ERR_WORKSPACE, "workspace too small: need > %zu, have %zu", off + bytes, cap);
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += bytes;
+    return p;
+  }
+};
+
+constexpr float kLeakySlope = 0.01f;  // nn.LeakyReLU() default (models.py:197,234,315)
+constexpr float kBnEps = 1e-5f;       // nn.BatchNorm2d default
+
+}  // namespace ake

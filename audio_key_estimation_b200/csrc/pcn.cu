@@ -1,0 +1,652 @@
+// pcn.cu -- PitchClassNet plan + forward orchestration + C ABI (see include/ake_b200.h).
+//
+// Architecture facts restated from the reference (cited per item):
+//   channel plan            models.py:266-308, 694-710
+//   layer 0 / layer >= 1    models.py:359-369 / 370-396
+//   heads                   models.py:713-742
+//   masked mean + sigmoid   models.py:754-804
+#include <cmath>
+#include <algorithm>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "pcn_kernels.cuh"
+
+namespace ake {
+
+thread_local std::string g_last_error;
+thread_local int64_t g_launches = 0;
+void set_last_error(const std::string& msg) { g_last_error = msg; }
+int64_t& launch_counter() { return g_launches; }
+
+struct TensorInfo {
+  std::string name;
+  int ndim;
+  int64_t shape[4];
+  int64_t off, numel;
+};
+
+struct BnSite {
+  int C;
+  int64_t gamma, beta, mean, var;  // offsets into the flat parameter buffer
+  int stat_off;                    // channel offset into the concatenated BN-statistics output
+};
+
+struct Conv {
+  int Cout, Cin, KH, KW;
+  bool transposed = false;  // ConvTranspose2d weight layout (Cin, Cout, KH, KW)
+  int64_t w_off, b_off;
+  int bn = -1;              // index into bn sites, -1: none
+  int cout_pad = 0;
+  int64_t packed_off = 0;   // into packed weights
+  int ss_off = 0;           // into the scale/shift tables
+};
+
+struct LayerPlan {
+  int prev_p = 0, prev_pc = 0, out_p = 0, out_pc = 0;
+  int sem = -1, up = -1;
+  std::vector<int> p2p, pc2pc;
+};
+
+}  // namespace ake
+
+using namespace ake;
+
+struct ake_pcn {
+  ake_pcn_config cfg;
+  std::vector<TensorInfo> tensors;
+  std::vector<BnSite> bns;
+  std::vector<Conv> convs;
+  std::vector<LayerPlan> layers;
+  std::vector<int> tonic_head, key_head, genre_head;
+  int64_t n_params = 0, n_packed = 0;
+  int n_ss = 0, n_bn_ch = 0;
+  // device state owned by the plan (small: weights only)
+  float* d_params = nullptr;   // flat fp32 copy of the state_dict
+  float* d_packed = nullptr;   // repacked conv weights
+  float* d_ss_eval = nullptr;  // [scale | shift] eval-mode epilogues, n_ss each
+  float* d_ss_raw = nullptr;   // [1 | bias] raw epilogues
+  bool has_params = false;
+  std::map<std::string, std::pair<const float*, int64_t>> taps;
+};
+
+namespace ake {
+
+static int64_t add_tensor(ake_pcn* p, const std::string& name, std::initializer_list<int64_t> shape) {
+  TensorInfo t;
+  t.name = name;
+  t.ndim = (int)shape.size();
+  t.numel = 1;
+  int i = 0;
+  for (auto s : shape) t.shape[i++] = s, t.numel *= s;
+  for (; i < 4; ++i) t.shape[i] = 1;
+  t.off = p->n_params;
+  p->n_params += t.numel;
+  p->tensors.push_back(t);
+  return t.off;
+}
+
+static int add_bn(ake_pcn* p, const std::string& prefix, int C) {
+  BnSite b;
+  b.C = C;
+  b.gamma = add_tensor(p, prefix + ".weight", {C});
+  b.beta = add_tensor(p, prefix + ".bias", {C});
+  b.mean = add_tensor(p, prefix + ".running_mean", {C});
+  b.var = add_tensor(p, prefix + ".running_var", {C});
+  b.stat_off = p->n_bn_ch;
+  p->n_bn_ch += C;
+  p->bns.push_back(b);
+  return (int)p->bns.size() - 1;
+}
+
+static int add_conv(ake_pcn* p, const std::string& wname, int Cout, int Cin, int KH, int KW, int co_tile,
+                    bool transposed = false) {
+  Conv c;
+  c.Cout = Cout, c.Cin = Cin, c.KH = KH, c.KW = KW, c.transposed = transposed;
+  if (transposed)
+    c.w_off = add_tensor(p, wname + ".weight", {Cin, Cout, KH, KW});
+  else
+    c.w_off = add_tensor(p, wname + ".weight", {Cout, Cin, KH, KW});
+  c.b_off = add_tensor(p, wname + ".bias", {Cout});
+  c.cout_pad = cdiv(Cout, co_tile) * co_tile;
+  c.packed_off = p->n_packed;
+  if (!transposed) p->n_packed += (int64_t)Cin * KH * KW * c.cout_pad;
+  c.ss_off = p->n_ss;
+  p->n_ss += Cout;
+  p->convs.push_back(c);
+  return (int)p->convs.size() - 1;
+}
+
+static int co_tile_for(int Cout) { return Cout >= 8 ? 8 : (Cout >= 4 ? 4 : 1); }
+
+static void build_plan(ake_pcn* p) {
+  const ake_pcn_config& c = p->cfg;
+  if (c.resblock || c.denseblock || c.stay_sixth || c.only_semitones || c.p2pc_conv || c.pc2p_mem || c.local)
+    fail(AKE_ERR_UNSUPPORTED,
+         "resblock/denseblock/stay_sixth/only_semitones/p2pc_conv/pc2p_mem/local are outside the B200 hot path");
+  if (c.pitch_classes != 12) fail(AKE_ERR_INVALID, "pitch_classes must be 12 (models.py:171)");
+  if (c.pitches <= 0 || c.pitches % 36) fail(AKE_ERR_INVALID, "pitches must be a positive multiple of 36");
+  if (c.kernel_size != 7) fail(AKE_ERR_UNSUPPORTED, "kernel_size %d: only 7 is built", c.kernel_size);
+  if (c.time_pool_size != 2) fail(AKE_ERR_UNSUPPORTED, "time_pool_size %d: only 2 is built", c.time_pool_size);
+  if (c.num_layers < 1 || c.num_layers > 3) fail(AKE_ERR_UNSUPPORTED, "num_layers %d: 1..3 are built", c.num_layers);
+  if (c.conv_layers < 1 || c.n_filters < 1 || c.head_layers < 1) fail(AKE_ERR_INVALID, "bad layer counts");
+  const int k = c.kernel_size, nf = c.n_filters;
+
+  for (int L = 0; L < c.num_layers; ++L) {
+    LayerPlan lp;
+    const std::string pre = "model." + std::to_string(L) + ".";
+    if (L == 0) {
+      lp.out_p = 1, lp.out_pc = nf;  // models.py:298-300 (pc2pc built with num_filters, :320)
+      lp.sem = add_conv(p, pre + "pool_semi", 1, 1, 3, 3, 1);
+      p->convs[lp.sem].bn = add_bn(p, pre + "pool_semi_b", 1);
+      for (int i = 0; i < c.conv_layers; ++i) {
+        const std::string s = pre + "pc2pc.layer." + std::to_string(3 * i);
+        int id = add_conv(p, s + ".conv2d", nf, i == 0 ? 1 : nf, 12, k, co_tile_for(nf));
+        p->convs[id].bn = add_bn(p, pre + "pc2pc.layer." + std::to_string(3 * i + 1), nf);
+        lp.pc2pc.push_back(id);
+      }
+    } else {
+      // models.py:285-308
+      if (L == 1) lp.prev_p = 1, lp.prev_pc = nf, lp.out_p = 2 * nf, lp.out_pc = 2 * lp.out_p;
+      else {
+        lp.prev_p = (2 * nf) * (int)std::pow(4.0, L - 2);
+        lp.prev_pc = 2 * lp.prev_p;
+        lp.out_p = 4 * lp.prev_p, lp.out_pc = 4 * lp.prev_pc;
+      }
+      lp.up = add_conv(p, pre + "up_sixth", lp.prev_pc, lp.prev_pc, 3, 1, 1, /*transposed=*/true);
+      p->convs[lp.up].bn = add_bn(p, pre + "up_sixth_b", lp.prev_pc);
+      for (int i = 0; i < c.conv_layers; ++i) {
+        const std::string s = pre + "p2p.layer." + std::to_string(3 * i);
+        int id = add_conv(p, s, lp.out_p, i == 0 ? lp.prev_p + lp.prev_pc : lp.out_p, k, k, 8);
+        p->convs[id].bn = add_bn(p, pre + "p2p.layer." + std::to_string(3 * i + 1), lp.out_p);
+        lp.p2p.push_back(id);
+      }
+      lp.sem = add_conv(p, pre + "pool_semi", lp.out_p, lp.out_p, 3, 3, 8);
+      p->convs[lp.sem].bn = add_bn(p, pre + "pool_semi_b", lp.out_p);
+      for (int i = 0; i < c.conv_layers; ++i) {
+        const std::string s = pre + "pc2pc.layer." + std::to_string(3 * i);
+        int id = add_conv(p, s + ".conv2d", lp.out_pc, i == 0 ? lp.out_p + lp.prev_pc : lp.out_pc, 12, k, 8);
+        p->convs[id].bn = add_bn(p, pre + "pc2pc.layer." + std::to_string(3 * i + 1), lp.out_pc);
+        lp.pc2pc.push_back(id);
+      }
+    }
+    p->layers.push_back(lp);
+  }
+  // heads (models.py:713-742); registration order tonic, key, genre (models.py:739-742)
+  const int final_ch = p->layers.back().out_pc;
+  auto build_head = [&](const std::string& name, bool equivariant, std::vector<int>& ids) {
+    int fc = final_ch;
+    for (int i = 0; i < c.head_layers; ++i) {
+      const std::string s = name + "." + std::to_string(3 * i);
+      if (i == c.head_layers - 1) {
+        ids.push_back(add_conv(p, equivariant ? s + ".conv2d" : s, 1, fc, equivariant ? 12 : 2, k, 1));
+      } else {
+        const int oc = i == 0 ? 2 * fc : fc;
+        int id = add_conv(p, equivariant ? s + ".conv2d" : s, oc, fc, equivariant ? 12 : 1, k, 8);
+        p->convs[id].bn = add_bn(p, name + "." + std::to_string(3 * i + 1), oc);
+        ids.push_back(id);
+        fc = oc;
+      }
+    }
+  };
+  build_head("tonic_classifier", true, p->tonic_head);
+  build_head("key_classifier", true, p->key_head);
+  if (c.genre) build_head("genre_classifier", false, p->genre_head);
+}
+
+// ------------------------------------------------------------------------------ kernel launch helpers
+struct View {  // (B, C, R, T) contiguous fp32
+  float* p = nullptr;
+  int C = 0, R = 0, T = 0;
+  long long bstride() const { return (long long)C * R * T; }
+  long long numel(int B) const { return bstride() * B; }
+};
+
+struct ConvGeom {
+  int KH, KW, SR;
+  int rows_v, row_circ, row_off, pad_t, time_circ;
+  int rows_out, T_out;
+  int pool_t = 0;
+};
+
+template <int KH, int KW, int SR, int RB, int CO_T, int RT>
+static void launch_conv_t(ConvArgs a, int B, int max_tg, cudaStream_t st) {
+  constexpr int RIN = (RB - 1) * SR + KH;
+  const int groups = cdiv(a.T_out, RT);
+  const int n_tiles = cdiv(groups, max_tg);
+  a.tgroups = cdiv(groups, n_tiles);
+  const int TBW = a.tgroups * RT + KW - 1;
+  if (TBW > 96) fail(AKE_ERR_INVALID, "internal: time tile too wide");
+  int xp = (TBW + 3) / 4 * 4;
+  while (xp % 32 != 12 && xp % 32 != 4 && xp % 32 != 20 && xp % 32 != 28) xp += 4;  // odd multiple of 4: conflict-free float4 rows
+  a.xp = xp;
+  a.n_row_tiles = cdiv(a.rows_out, RB);
+  const int threads = cdiv(RB * a.tgroups, 32) * 32;
+  const size_t smem = sizeof(float) * ((size_t)kConvCI * RIN * xp + (size_t)kConvCI * KH * KW * CO_T);
+  auto kern = conv_rows_kernel<KH, KW, SR, RB, CO_T, RT>;
+  static size_t configured = 0;
+  if (smem > configured) {
+    AKE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  dim3 grid(n_tiles, a.n_row_tiles * (a.cout_pad / CO_T), B);
+  kern<<<grid, threads, smem, st>>>(a);
+  AKE_LAUNCHED();
+}
+
+static void launch_conv(const ConvArgs& a, const ConvGeom& g, int co_tile, int B, cudaStream_t st) {
+  // (KH, KW, SR) families: equivariant 12x7, pitch 7x7, semitone 3x3/3, genre 1x7 and 2x7
+  if (g.KH == 12 && g.KW == 7 && g.SR == 1) {
+    if (co_tile == 8) return launch_conv_t<12, 7, 1, 12, 8, 4>(a, B, 8, st);
+    if (co_tile == 4) return launch_conv_t<12, 7, 1, 12, 4, 4>(a, B, 8, st);
+    if (co_tile == 1) return launch_conv_t<12, 7, 1, 12, 1, 4>(a, B, 8, st);
+  } else if (g.KH == 7 && g.KW == 7 && g.SR == 1) {
+    if (co_tile == 8) return launch_conv_t<7, 7, 1, 32, 8, 8>(a, B, 4, st);
+  } else if (g.KH == 3 && g.KW == 3 && g.SR == 3) {
+    if (co_tile == 8) return launch_conv_t<3, 3, 3, 32, 8, 8>(a, B, 4, st);
+    if (co_tile == 1) return launch_conv_t<3, 3, 3, 32, 1, 8>(a, B, 4, st);
+  } else if (g.KH == 1 && g.KW == 7 && g.SR == 1) {
+    if (co_tile == 8) return launch_conv_t<1, 7, 1, 12, 8, 4>(a, B, 8, st);
+  } else if (g.KH == 2 && g.KW == 7 && g.SR == 1) {
+    if (co_tile == 1) return launch_conv_t<2, 7, 1, 12, 1, 4>(a, B, 8, st);
+  }
+  fail(AKE_ERR_UNSUPPORTED, "no conv kernel for KH=%d KW=%d SR=%d co_tile=%d", g.KH, g.KW, g.SR, co_tile);
+}
+
+static int ew_blocks(long long n) { return (int)std::min<long long>(cdiv64(n, 256), 148LL * 16); }
+
+struct Fwd {
+  ake_pcn* p;
+  int B, T;
+  bool train, dry;
+  cudaStream_t st;
+  Arena arena;
+  const int* seq_len;
+  float* bn_stats_out;
+  double* d_stats = nullptr;  // train: per conv channel (sum, sumsq)
+  float* d_ss_train = nullptr;
+
+  Fwd(ake_pcn* p_, int B_, int T_, bool train_, void* ws, size_t ws_bytes, cudaStream_t st_)
+      : p(p_), B(B_), T(T_), train(train_), dry(ws == nullptr), st(st_), arena(ws, ws_bytes) {}
+
+  View alloc(int C, int R, int Tn) {
+    View v;
+    v.C = C, v.R = R, v.T = Tn;
+    v.p = arena.take<float>((size_t)B * C * R * Tn);
+    return v;
+  }
+  void tap(const std::string& name, const View& v, int C = -1) {
+    if (!dry) p->taps[name] = {v.p, (int64_t)B * (C < 0 ? v.C : C) * v.R * v.T};
+  }
+  const float* scale_of(const Conv& c, bool raw) const { return (raw ? p->d_ss_raw : p->d_ss_eval) + c.ss_off; }
+  const float* shift_of(const Conv& c, bool raw) const {
+    return (raw ? p->d_ss_raw : p->d_ss_eval) + p->n_ss + c.ss_off;
+  }
+
+  // Batch statistics of channels [coff, coff+C) of `v`, then scale/shift for the train-mode epilogue.
+  void train_bn(const Conv& c, const View& v, int coff) {
+    const BnSite& bn = p->bns[c.bn];
+    double* stats = d_stats + 2 * c.ss_off;
+    if (dry) return;
+    const int rt = v.R * v.T;
+    dim3 grid(std::max(1, std::min(64, (int)cdiv64((long long)B * rt, 4096))), c.Cout);
+    bn_stats_kernel<<<grid, 256, 0, st>>>(v.p, B, v.C, coff, rt, stats);
+    AKE_LAUNCHED();
+    bn_finalize_kernel<<<cdiv(c.Cout, 64), 64, 0, st>>>(stats, (double)B * rt, p->d_params + bn.gamma,
+                                                         p->d_params + bn.beta, c.Cout, d_ss_train + c.ss_off,
+                                                         d_ss_train + p->n_ss + c.ss_off,
+                                                         bn_stats_out ? bn_stats_out + 2 * bn.stat_off : nullptr);
+    AKE_LAUNCHED();
+  }
+
+  // One row convolution + BatchNorm + LeakyReLU (+ fused time pool).  Returns nothing; writes `out`.
+  void conv(int id, const View& in0, const View* in1, const ConvGeom& g, View& out, int out_coff, bool act) {
+    const Conv& c = p->convs[id];
+    const bool has_bn = c.bn >= 0;
+    const bool raw = train && has_bn;
+    if (dry) return;
+    ConvArgs a{};
+    a.in0 = in0.p, a.c0 = in0.C, a.rows0 = in0.R, a.bs0 = in0.bstride();
+    if (in1) a.in1 = in1->p, a.c1 = in1->C, a.rows1 = in1->R, a.bs1 = in1->bstride();
+    else a.in1 = in0.p, a.c1 = 0, a.rows1 = 1, a.bs1 = 0;
+    a.T_in = in0.T;
+    a.rows_v = g.rows_v, a.row_circ = g.row_circ, a.row_off = g.row_off, a.pad_t = g.pad_t, a.time_circ = g.time_circ;
+    a.rows_out = g.rows_out, a.T_out = g.T_out;
+    a.Cin = c.Cin, a.Cout = c.Cout;
+    if (a.c0 + a.c1 != c.Cin) fail(AKE_ERR_INVALID, "internal: conv %d channel mismatch %d+%d vs %d", id, a.c0, a.c1, c.Cin);
+    a.w = p->d_packed + c.packed_off, a.cout_pad = c.cout_pad;
+    a.scale = scale_of(c, raw), a.shift = shift_of(c, raw);
+    a.act = raw ? 0 : (act ? 1 : 0);
+    a.out = out.p, a.obs = out.bstride(), a.ocs = (long long)out.R * out.T, a.out_coff = out_coff;
+    a.pool_t = raw ? 0 : g.pool_t;
+    a.T_store = out.T;
+    const int co_tile = c.cout_pad % 8 == 0 ? 8 : (c.cout_pad % 4 == 0 ? 4 : 1);
+    launch_conv(a, g, co_tile, B, st);
+  }
+
+  void affine_act(const Conv& c, View& v, int coff) {
+    if (dry) return;
+    const long long n = (long long)B * c.Cout * v.R * v.T;
+    affine_act_kernel<<<ew_blocks(n), 256, 0, st>>>(v.p, B, v.C, coff, c.Cout, v.R * v.T, d_ss_train + c.ss_off,
+                                                   d_ss_train + p->n_ss + c.ss_off, 1);
+    AKE_LAUNCHED();
+  }
+
+  // conv + BN + act writing channels [coff, coff+Cout) of `out` (same T), both BN modes.
+  void conv_bn_act(int id, const View& in0, const View* in1, const ConvGeom& g, View& out, int coff) {
+    conv(id, in0, in1, g, out, coff, true);
+    if (train) {
+      train_bn(p->convs[id], out, coff);
+      affine_act(p->convs[id], out, coff);
+    }
+  }
+
+  void run(const float* mel, float* key_out, float* tonic_out, float* genre_out);
+};
+
+void Fwd::run(const float* mel, float* key_out, float* tonic_out, float* genre_out) {
+  const ake_pcn_config& cfg = p->cfg;
+  const int P = cfg.pitches, S = P / 3, k = cfg.kernel_size;
+  if (!dry) p->taps.clear();
+  if (train) {
+    d_stats = arena.take<double>(2 * (size_t)p->n_ss);
+    d_ss_train = arena.take<float>(2 * (size_t)p->n_ss);
+    if (!dry) AKE_CUDA(cudaMemsetAsync(d_stats, 0, sizeof(double) * 2 * p->n_ss, st));
+  }
+  const ConvGeom g_sem{3, 3, 3, P, 0, 0, 1, 1, S, 0};
+  auto g_equiv = [&](int Tn, bool same) { return ConvGeom{12, k, 1, 12, 1, 0, same ? k / 2 : 0, 0, 12, same ? Tn : Tn - k + 1}; };
+
+  View p_in;  // current pitch-wise features
+  p_in.p = const_cast<float*>(mel), p_in.C = 1, p_in.R = P, p_in.T = T;
+  View pc;    // current pitch-class features
+  int Tn = T;
+
+  auto semitone_pool = [&](int L, const View& src, View& dst_cat, int coff) {
+    // pool_semi conv + BN + act (models.py:361-363 / 386-388), then Pitch2PitchClassPool (:368 / :389)
+    const LayerPlan& lp = p->layers[L];
+    const Conv& c = p->convs[lp.sem];
+    View semi = alloc(c.Cout, S, Tn);
+    ConvGeom g = g_sem;
+    g.T_out = Tn;
+    conv(lp.sem, src, nullptr, g, semi, 0, true);
+    const long long n = (long long)B * c.Cout * 12 * Tn;
+    if (train) train_bn(c, semi, 0);
+    if (!dry) {
+      octmax_kernel<<<ew_blocks(n), 256, 0, st>>>(semi.p, B, c.Cout, S, Tn, train ? d_ss_train + c.ss_off : nullptr,
+                                                 train ? d_ss_train + p->n_ss + c.ss_off : nullptr, train ? 1 : 0,
+                                                 dst_cat.p, dst_cat.C, coff);
+      AKE_LAUNCHED();
+    }
+    tap("l" + std::to_string(L) + (train ? ".semi_raw" : ".semi"), semi);
+  };
+
+  for (int L = 0; L < cfg.num_layers; ++L) {
+    const LayerPlan& lp = p->layers[L];
+    const std::string ln = "l" + std::to_string(L);
+    View cat;  // input of the pc2pc stack
+    if (L == 0) {
+      cat = alloc(1, 12, Tn);
+      semitone_pool(0, p_in, cat, 0);
+      tap("l0.pool", cat);
+    } else {
+      // up_sixth ConvTranspose + BN + act (models.py:372-374); tiled to all pitches by the conv loader (:378)
+      const Conv& cu = p->convs[lp.up];
+      View up = alloc(lp.prev_pc, 36, Tn);
+      if (!dry) {
+        const bool raw = train;
+        const long long n = up.numel(B);
+        upsixth_kernel<<<ew_blocks(n), 256, 0, st>>>(pc.p, p->d_params + cu.w_off, scale_of(cu, raw), shift_of(cu, raw),
+                                                    raw ? 0 : 1, up.p, B, lp.prev_pc, Tn);
+        AKE_LAUNCHED();
+      }
+      if (train) {
+        train_bn(cu, up, 0);
+        affine_act(cu, up, 0);
+      }
+      tap(ln + ".up", up);
+      // Pitch2Pitch stack (models.py:384): circular in pitch and time
+      ConvGeom gp{k, k, 1, P, 1, -(k / 2), k / 2, 1, P, Tn};
+      View a = alloc(lp.out_p, P, Tn), b2 = alloc(lp.out_p, P, Tn);
+      View* src = nullptr;
+      View* dst = &a;
+      for (size_t i = 0; i < lp.p2p.size(); ++i) {
+        if (i == 0) conv_bn_act(lp.p2p[i], p_in, &up, gp, *dst, 0);
+        else conv_bn_act(lp.p2p[i], *src, nullptr, gp, *dst, 0);
+        tap(ln + ".p2p" + std::to_string(i), *dst);
+        src = dst;
+        dst = (dst == &a) ? &b2 : &a;
+      }
+      View p_feat = *src;
+      // concat [pc, pc2] (models.py:392): previous pc is copied in, pool_semi result written beside it
+      cat = alloc(lp.prev_pc + lp.out_p, 12, Tn);
+      if (!dry)
+        AKE_CUDA(cudaMemcpy2DAsync(cat.p, sizeof(float) * cat.bstride(), pc.p, sizeof(float) * pc.bstride(),
+                                   sizeof(float) * pc.bstride(), B, cudaMemcpyDeviceToDevice, st));
+      semitone_pool(L, p_feat, cat, lp.prev_pc);
+      tap(ln + ".cat", cat);
+      // time pooling of the pitch-wise features is only needed if another layer follows (models.py:395)
+      if (L + 1 < cfg.num_layers) {
+        View pp = alloc(lp.out_p, P, Tn / 2);
+        if (!dry) {
+          timepool_kernel<<<ew_blocks(pp.numel(B)), 256, 0, st>>>(p_feat.p, B, lp.out_p, P, Tn, nullptr, nullptr, 0, pp.p);
+          AKE_LAUNCHED();
+        }
+        p_in = pp;
+      }
+    }
+    // PitchClass2PitchClass stack (models.py:369 / 393), zero padding in time
+    View a = alloc(lp.out_pc, 12, Tn), b2 = alloc(lp.out_pc, 12, Tn);
+    View* src = &cat;
+    View* dst = &a;
+    for (size_t i = 0; i < lp.pc2pc.size(); ++i) {
+      const bool last = i + 1 == lp.pc2pc.size();
+      ConvGeom g = g_equiv(Tn, true);
+      if (last && L > 0) {
+        // fuse time_pool_pc (models.py:396) into the last conv's epilogue (eval) or the BN apply (train)
+        View pooled = alloc(lp.out_pc, 12, Tn / 2);
+        const Conv& c = p->convs[lp.pc2pc[i]];
+        if (!train) {
+          g.pool_t = 1;
+          conv(lp.pc2pc[i], *src, nullptr, g, pooled, 0, true);
+        } else {
+          conv(lp.pc2pc[i], *src, nullptr, g, *dst, 0, true);
+          train_bn(c, *dst, 0);
+          if (!dry) {
+            timepool_kernel<<<ew_blocks(pooled.numel(B)), 256, 0, st>>>(dst->p, B, lp.out_pc, 12, Tn, d_ss_train + c.ss_off,
+                                                                       d_ss_train + p->n_ss + c.ss_off, 1, pooled.p);
+            AKE_LAUNCHED();
+          }
+        }
+        pc = pooled;
+        Tn /= 2;
+      } else {
+        conv_bn_act(lp.pc2pc[i], *src, nullptr, g, *dst, 0);
+        tap(ln + ".pc2pc" + std::to_string(i), *dst);
+        pc = *dst;
+        src = dst;
+        dst = (dst == &a) ? &b2 : &a;
+      }
+    }
+  }
+  tap("pc_final", pc);
+
+  // heads (models.py:750-753)
+  auto head = [&](const std::vector<int>& ids, bool equivariant, const char* name) -> View {
+    View x = pc;
+    int Th = Tn;
+    for (size_t i = 0; i < ids.size(); ++i) {
+      const Conv& c = p->convs[ids[i]];
+      const bool last = i + 1 == ids.size();
+      ConvGeom g;
+      if (equivariant) g = g_equiv(Th, false);
+      else g = ConvGeom{c.KH, k, 1, 12, 0, 0, 0, 0, 12 - c.KH + 1, Th - k + 1};
+      View y = alloc(c.Cout, g.rows_out, g.T_out);
+      if (last) conv(ids[i], x, nullptr, g, y, 0, false);
+      else conv_bn_act(ids[i], x, nullptr, g, y, 0);
+      x = y;
+      Th = g.T_out;
+    }
+    tap(name, x);
+    return x;
+  };
+  View tonic_f = head(p->tonic_head, true, "tonic_frames");
+  View key_f = head(p->key_head, true, "key_frames");
+  View genre_f;
+  if (cfg.genre) genre_f = head(p->genre_head, false, "genre_frames");
+  if (tonic_f.T <= 0) fail(AKE_ERR_INVALID, "T=%d is too short: the heads need more than %d frames after pooling", T,
+                           (k - 1) * cfg.head_layers);
+  if (!dry) {
+    int pool_div = 1;
+    for (int i = 0; i < cfg.num_layers - 1; ++i) pool_div *= cfg.time_pool_size;
+    const int rows = cfg.genre ? 35 : 24;
+    head_reduce_kernel<<<cdiv(B * rows * 32, 256), 256, 0, st>>>(key_f.p, tonic_f.p, cfg.genre ? genre_f.p : nullptr, B,
+                                                                tonic_f.T, seq_len, pool_div, (k - 1) * cfg.head_layers,
+                                                                cfg.max_pool, key_out, tonic_out, genre_out);
+    AKE_LAUNCHED();
+  }
+}
+
+static void upload_params(ake_pcn* p, const float* flat_dev, int64_t n, cudaStream_t st) {
+  if (n != p->n_params) fail(AKE_ERR_INVALID, "expected %lld parameter floats, got %lld", (long long)p->n_params, (long long)n);
+  if (!p->d_params) {
+    AKE_CUDA(cudaMalloc(&p->d_params, sizeof(float) * p->n_params));
+    AKE_CUDA(cudaMalloc(&p->d_packed, sizeof(float) * std::max<int64_t>(p->n_packed, 1)));
+    AKE_CUDA(cudaMalloc(&p->d_ss_eval, sizeof(float) * 2 * p->n_ss));
+    AKE_CUDA(cudaMalloc(&p->d_ss_raw, sizeof(float) * 2 * p->n_ss));
+  }
+  AKE_CUDA(cudaMemcpyAsync(p->d_params, flat_dev, sizeof(float) * n, cudaMemcpyDeviceToDevice, st));
+  for (const Conv& c : p->convs) {
+    if (!c.transposed) {
+      const int nn = c.Cin * c.KH * c.KW * c.cout_pad;
+      pack_conv_kernel<<<cdiv(nn, 256), 256, 0, st>>>(p->d_params + c.w_off, c.Cout, c.Cin, c.KH * c.KW, c.cout_pad,
+                                                     p->d_packed + c.packed_off);
+      AKE_LAUNCHED();
+    }
+    const BnSite* bn = c.bn >= 0 ? &p->bns[c.bn] : nullptr;
+    fold_bn_kernel<<<cdiv(c.Cout, 64), 64, 0, st>>>(
+        p->d_params + c.b_off, bn ? p->d_params + bn->gamma : nullptr, bn ? p->d_params + bn->beta : nullptr,
+        bn ? p->d_params + bn->mean : nullptr, bn ? p->d_params + bn->var : nullptr, c.Cout, p->d_ss_eval + c.ss_off,
+        p->d_ss_eval + p->n_ss + c.ss_off, p->d_ss_raw + c.ss_off, p->d_ss_raw + p->n_ss + c.ss_off);
+    AKE_LAUNCHED();
+  }
+  p->has_params = true;
+}
+
+}  // namespace ake
+
+// =============================================================================== extern "C"
+extern "C" {
+
+int ake_abi_version(void) { return AKE_ABI_VERSION; }
+const char* ake_last_error(void) { return g_last_error.c_str(); }
+int64_t ake_launch_count(int reset) {
+  int64_t v = g_launches;
+  if (reset) g_launches = 0;
+  return v;
+}
+
+int ake_pcn_create(const ake_pcn_config* cfg, ake_pcn** out) {
+  return guarded([&] {
+    if (!cfg || !out) fail(AKE_ERR_INVALID, "null argument");
+    ake_pcn* p = new ake_pcn();
+    p->cfg = *cfg;
+    try {
+      build_plan(p);
+    } catch (...) {
+      delete p;
+      throw;
+    }
+    *out = p;
+  });
+}
+
+void ake_pcn_destroy(ake_pcn* p) {
+  if (!p) return;
+  cudaFree(p->d_params);
+  cudaFree(p->d_packed);
+  cudaFree(p->d_ss_eval);
+  cudaFree(p->d_ss_raw);
+  delete p;
+}
+
+int ake_pcn_num_tensors(const ake_pcn* p) { return p ? (int)p->tensors.size() : AKE_ERR_INVALID; }
+const char* ake_pcn_tensor_name(const ake_pcn* p, int i) {
+  return (p && i >= 0 && i < (int)p->tensors.size()) ? p->tensors[i].name.c_str() : nullptr;
+}
+int ake_pcn_tensor_shape(const ake_pcn* p, int i, int64_t shape4[4]) {
+  if (!p || i < 0 || i >= (int)p->tensors.size()) return AKE_ERR_INVALID;
+  for (int k = 0; k < 4; ++k) shape4[k] = p->tensors[i].shape[k];
+  return p->tensors[i].ndim;
+}
+int64_t ake_pcn_param_floats(const ake_pcn* p) { return p ? p->n_params : AKE_ERR_INVALID; }
+int ake_pcn_bn_channels(const ake_pcn* p) { return p ? p->n_bn_ch : AKE_ERR_INVALID; }
+int ake_pcn_get_config(const ake_pcn* p, ake_pcn_config* out) {
+  if (!p || !out) return AKE_ERR_INVALID;
+  *out = p->cfg;
+  return AKE_OK;
+}
+
+int ake_pcn_set_params_f32(ake_pcn* p, const float* flat_dev, int64_t n, void* stream) {
+  return guarded([&] {
+    if (!p || !flat_dev) fail(AKE_ERR_INVALID, "null argument");
+    upload_params(p, flat_dev, n, static_cast<cudaStream_t>(stream));
+  });
+}
+
+size_t ake_pcn_workspace_bytes(const ake_pcn* p, int B, int T, int bn_mode) {
+  if (!p || B <= 0 || T <= 0) return 0;
+  try {
+    Fwd f(const_cast<ake_pcn*>(p), B, T, bn_mode != 0, nullptr, 0, nullptr);
+    f.seq_len = nullptr, f.bn_stats_out = nullptr;
+    f.run(nullptr, nullptr, nullptr, nullptr);
+    return f.arena.off + 256;
+  } catch (const std::exception& e) {
+    set_last_error(e.what());
+    return 0;
+  }
+}
+
+int ake_pcn_forward_f32(ake_pcn* p, const float* mel_dev, int B, int T, const int32_t* seq_len_dev, int bn_mode,
+                        float* key_out_dev, float* tonic_out_dev, float* genre_out_dev, float* bn_stats_out_dev,
+                        void* ws_dev, size_t ws_bytes, void* stream) {
+  return guarded([&] {
+    if (!p || !mel_dev || !key_out_dev || !tonic_out_dev || !ws_dev) fail(AKE_ERR_INVALID, "null argument");
+    if (p->cfg.genre && !genre_out_dev) fail(AKE_ERR_INVALID, "genre head enabled but genre_out_dev is NULL");
+    if (B <= 0 || T <= 0) fail(AKE_ERR_INVALID, "B and T must be positive (got %d, %d)", B, T);
+    if (!p->has_params) fail(AKE_ERR_INVALID, "ake_pcn_set_params_f32 has not been called");
+    Fwd f(p, B, T, bn_mode != 0, ws_dev, ws_bytes, static_cast<cudaStream_t>(stream));
+    f.seq_len = seq_len_dev, f.bn_stats_out = bn_stats_out_dev;
+    f.run(mel_dev, key_out_dev, tonic_out_dev, p->cfg.genre ? genre_out_dev : nullptr);
+  });
+}
+
+int64_t ake_pcn_get_tap(const ake_pcn* p, const char* name, float* out_dev, int64_t cap, void* stream) {
+  int64_t n = AKE_ERR_INVALID;
+  int rc = guarded([&] {
+    if (!p || !name) fail(AKE_ERR_INVALID, "null argument");
+    auto it = p->taps.find(name);
+    if (it == p->taps.end()) fail(AKE_ERR_INVALID, "no tap named '%s' in the last forward", name);
+    n = it->second.second;
+    if (out_dev) {
+      if (cap < n) fail(AKE_ERR_INVALID, "tap '%s' needs %lld floats", name, (long long)n);
+      AKE_CUDA(cudaMemcpyAsync(out_dev, it->second.first, sizeof(float) * n, cudaMemcpyDeviceToDevice,
+                               static_cast<cudaStream_t>(stream)));
+    }
+  });
+  return rc == AKE_OK ? n : rc;
+}
+
+int ake_decode_f32(const float* key_out_dev, const float* tonic_out_dev, const float* genre_out_dev, int B,
+                   int32_t* key_id_dev, int32_t* tonic_id_dev, int32_t* genre_id_dev, void* stream) {
+  return guarded([&] {
+    if (B <= 0) fail(AKE_ERR_INVALID, "B must be positive");
+    if ((key_id_dev && !key_out_dev) || (tonic_id_dev && !tonic_out_dev)) fail(AKE_ERR_INVALID, "null argument");
+    decode_kernel<<<cdiv(B, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(key_out_dev, tonic_out_dev, genre_out_dev, B,
+                                                                            key_id_dev, tonic_id_dev, genre_id_dev);
+    AKE_LAUNCHED();
+  });
+}
+
+}  // extern "C"

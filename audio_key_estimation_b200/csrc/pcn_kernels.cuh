@@ -1,0 +1,448 @@
+// pcn_kernels.cuh -- fp32 CUDA-core kernels of the PitchClassNet forward (sm_100a).
+//
+// Every convolution of the network is an instance of
+// one "row convolution":
+//   out[co, r, t] = sum_{ci, dr<KH, dt<KW} W[co,ci,dr,dt] * x[ci, rowmap(r*SR + off + dr), tmap(t - pad + dt)]
+// with circular or zero row/time maps.  conv_rows_kernel stages an input tile (8 input channels at a
+// time) plus the matching weight slice in shared memory and lets every thread own a CO_T x RT register
+// tile of outputs (CO_T output channels of RT consecutive frames of one row), so the inner loop is
+// pure FFMA fed by 128-bit shared-memory loads (weights are warp-uniform -> broadcast).
+//
+// Bit-exact transposition equivariance (SURVEY.md hard part 6): every output element accumulates its
+// K = Cin*KH*KW products in the same order (ci, dr, dt ascending) with the same instructions no matter
+// which row it is; rows only enter through load addresses (mod rows); no atomics are used.
+#pragma once
+#include "common.cuh"
+
+namespace ake {
+
+struct ConvArgs {
+  const float* in0;  // channels [0, c0)
+  const float* in1;  // channels [c0, c0 + c1) -- rows tiled modulo rows1 (PitchClass2Pitch, models.py:135-143)
+  int c0, c1;
+  int rows0, rows1;    // physical rows per channel
+  long long bs0, bs1;  // batch strides (floats)
+  int T_in;
+  int rows_v;     // logical input rows
+  int row_circ;   // 1: rows wrap, 0: rows outside read as zero
+  int row_off;    // input row of (out row 0, tap 0)
+  int pad_t;      // input frame of (out frame 0, tap 0) is -pad_t
+  int time_circ;  // 1: frames wrap (padding_mode="circular"), 0: zero padding / valid
+  int rows_out, T_out;
+  int Cin, Cout;
+  const float* w;  // packed [Cin][KH][KW][cout_pad]
+  int cout_pad;
+  const float* scale;  // epilogue y = act(acc * scale[c] + shift[c])
+  const float* shift;
+  int act;
+  float* out;
+  long long obs, ocs;  // output batch / channel strides (floats)
+  int out_coff;        // channel offset in the output tensor (free torch.cat, models.py:383,392)
+  int T_store;         // stored frames per row (T_out, or T_out/2 with pool_t)
+  int pool_t;          // fuse MaxPool2d((1,2)) (models.py:349-350)
+  int n_row_tiles;
+  int tgroups;  // time groups per block: block covers tgroups*RT output frames
+  int xp;       // shared-memory row pitch (floats, multiple of 4, >= tgroups*RT + KW - 1)
+};
+
+constexpr int kConvCI = 8;  // input channels staged per shared-memory pass
+
+__device__ __forceinline__ float leaky(float v) { return v > 0.f ? v : kLeakySlope * v; }
+
+template <int KH, int KW, int SR, int RB, int CO_T, int RT>
+__global__ void __launch_bounds__(256) conv_rows_kernel(const ConvArgs a) {
+  constexpr int RIN = (RB - 1) * SR + KH;  // input rows a row tile touches
+  constexpr int NX = RT + KW - 1;          // input frames a thread touches per (ci, dr)
+  static_assert(NX % 2 == 0 && RT % 2 == 0, "vector loads need even windows");
+  extern __shared__ float4 smem4[];
+  float* xs = reinterpret_cast<float*>(smem4);  // [kConvCI][RIN][XP]
+  const int XP = a.xp;
+  float* wsm = xs + kConvCI * RIN * XP;         // [kConvCI][KH][KW][CO_T]
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const int TB = a.tgroups * RT;
+  const int TBW = TB + KW - 1;
+  const int row_tile = blockIdx.y % a.n_row_tiles;
+  const int cob = blockIdx.y / a.n_row_tiles;
+  const int b = blockIdx.z;
+  const int t0 = blockIdx.x * TB;
+  const int out_row0 = row_tile * RB;
+  const bool active = tid < RB * a.tgroups;
+  const int r = tid % RB, tg = tid / RB;
+
+  // frame index of each shared-memory column this lane fills (-1 = zero)
+  int tm[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    int j = lane + 32 * k;
+    int t = t0 - a.pad_t + j;
+    if (a.time_circ) {
+      t %= a.T_in;
+      if (t < 0) t += a.T_in;
+    } else if (t < 0 || t >= a.T_in) {
+      t = -1;
+    }
+    tm[k] = (j < TBW) ? t : -2;  // -2: column not present
+  }
+
+  float acc[CO_T][RT];
+#pragma unroll
+  for (int c = 0; c < CO_T; ++c)
+#pragma unroll
+    for (int j = 0; j < RT; ++j) acc[c][j] = 0.f;
+
+  for (int cbase = 0; cbase < a.Cin; cbase += kConvCI) {
+    const int nci = min(kConvCI, a.Cin - cbase);
+    __syncthreads();
+    // ---- stage the input tile: one warp per (channel, row) line
+    for (int line = warp; line < nci * RIN; line += nwarps) {
+      const int ci = line / RIN, row = line - ci * RIN;
+      int v = out_row0 * SR + a.row_off + row;
+      const float* src = nullptr;
+      if (a.row_circ) {
+        v %= a.rows_v;
+        if (v < 0) v += a.rows_v;
+      }
+      if (v >= 0 && v < a.rows_v) {
+        const int ch = cbase + ci;
+        src = (ch < a.c0) ? a.in0 + b * a.bs0 + (long long)(ch * a.rows0 + v) * a.T_in
+                          : a.in1 + b * a.bs1 + (long long)((ch - a.c0) * a.rows1 + v % a.rows1) * a.T_in;
+      }
+      float* dst = xs + (ci * RIN + row) * XP;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        if (tm[k] != -2) dst[lane + 32 * k] = (src != nullptr && tm[k] >= 0) ? __ldg(src + tm[k]) : 0.f;
+      }
+    }
+    // ---- stage the weight slice [nci][KH][KW][CO_T]
+    {
+      const float* wsrc = a.w + (long long)cbase * KH * KW * a.cout_pad + cob * CO_T;
+      for (int i = tid; i < nci * KH * KW * CO_T; i += blockDim.x) {
+        const int k = i / CO_T, co = i - k * CO_T;
+        wsm[i] = __ldg(wsrc + (long long)k * a.cout_pad + co);
+      }
+    }
+    __syncthreads();
+    if (active) {
+      for (int ci = 0; ci < nci; ++ci) {
+#pragma unroll 1
+        for (int dr = 0; dr < KH; ++dr) {
+          const float* xr = xs + (ci * RIN + r * SR + dr) * XP + tg * RT;
+          float x[NX];
+#pragma unroll
+          for (int q = 0; q < NX / 4; ++q) {
+            const float4 v4 = *reinterpret_cast<const float4*>(xr + 4 * q);
+            x[4 * q] = v4.x, x[4 * q + 1] = v4.y, x[4 * q + 2] = v4.z, x[4 * q + 3] = v4.w;
+          }
+          if (NX % 4) {
+            const float2 v2 = *reinterpret_cast<const float2*>(xr + (NX / 4) * 4);
+            x[NX - 2] = v2.x, x[NX - 1] = v2.y;
+          }
+          const float* wr = wsm + (ci * KH + dr) * KW * CO_T;
+#pragma unroll
+          for (int dt = 0; dt < KW; ++dt) {
+            float wv[CO_T];
+            if constexpr (CO_T % 4 == 0) {
+#pragma unroll
+              for (int q = 0; q < CO_T / 4; ++q) {
+                const float4 w4 = *reinterpret_cast<const float4*>(wr + dt * CO_T + 4 * q);
+                wv[4 * q] = w4.x, wv[4 * q + 1] = w4.y, wv[4 * q + 2] = w4.z, wv[4 * q + 3] = w4.w;
+              }
+            } else {
+#pragma unroll
+              for (int c = 0; c < CO_T; ++c) wv[c] = wr[dt * CO_T + c];
+            }
+#pragma unroll
+            for (int c = 0; c < CO_T; ++c)
+#pragma unroll
+              for (int j = 0; j < RT; ++j) acc[c][j] = fmaf(wv[c], x[j + dt], acc[c][j]);
+          }
+        }
+      }
+    }
+  }
+
+  const int out_row = out_row0 + r;
+  if (!active || out_row >= a.rows_out) return;
+#pragma unroll
+  for (int c = 0; c < CO_T; ++c) {
+    const int ch = cob * CO_T + c;
+    if (ch >= a.Cout) break;
+    const float s = a.scale[ch], h = a.shift[ch];
+    float* op = a.out + b * a.obs + (a.out_coff + ch) * a.ocs + (long long)out_row * a.T_store;
+    if (!a.pool_t) {
+#pragma unroll
+      for (int j = 0; j < RT; ++j) {
+        const int t = t0 + tg * RT + j;
+        if (t < a.T_out) {
+          float v = fmaf(acc[c][j], s, h);
+          op[t] = a.act ? leaky(v) : v;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < RT / 2; ++j) {
+        const int u = (t0 + tg * RT) / 2 + j;
+        if (2 * u + 1 < a.T_out) {
+          float v0 = fmaf(acc[c][2 * j], s, h), v1 = fmaf(acc[c][2 * j + 1], s, h);
+          if (a.act) v0 = leaky(v0), v1 = leaky(v1);
+          op[u] = fmaxf(v0, v1);
+        }
+      }
+    }
+  }
+}
+
+// ---- ConvTranspose2d(C,C,(3,1),stride=(3,1)) (+affine+act): models.py:325-327 ------------------
+// out[b,co,3c+r,t] = act(scale[co] * sum_ci W[ci,co,r] * pc[b,ci,c,t] + shift[co]);  W is (Cin,Cout,3,1).
+__global__ void upsixth_kernel(const float* __restrict__ pc, const float* __restrict__ w,
+                               const float* __restrict__ scale, const float* __restrict__ shift, int act,
+                               float* __restrict__ out, int B, int C, int T) {
+  const long long n = (long long)B * C * 36 * T;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int t = i % T;
+    long long q = i / T;
+    const int row = q % 36;
+    q /= 36;
+    const int co = q % C;
+    const int b = q / C;
+    const int c = row / 3, r = row - 3 * c;
+    float acc = 0.f;
+    for (int ci = 0; ci < C; ++ci)
+      acc = fmaf(__ldg(w + (ci * C + co) * 3 + r), __ldg(pc + (((long long)b * C + ci) * 12 + c) * T + t), acc);
+    float v = fmaf(acc, scale[co], shift[co]);
+    out[i] = act ? leaky(v) : v;
+  }
+}
+
+// ---- Pitch2PitchClassPool (models.py:82-106): pc[c] = max_o x[c + 12 o], optional affine+act first ----
+__global__ void octmax_kernel(const float* __restrict__ in, int B, int C, int R, int T, const float* __restrict__ scale,
+                              const float* __restrict__ shift, int affine_act, float* __restrict__ out, int C_total,
+                              int coff) {
+  const long long n = (long long)B * C * 12 * T;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int t = i % T;
+    long long q = i / T;
+    const int pc = q % 12;
+    q /= 12;
+    const int c = q % C;
+    const int b = q / C;
+    const float* src = in + (((long long)b * C + c) * R) * T + t;
+    float s = 1.f, h = 0.f;
+    if (affine_act) s = scale[c], h = shift[c];
+    float m = -INFINITY;
+    for (int row = pc; row < R; row += 12) {
+      float v = __ldg(src + (long long)row * T);
+      if (affine_act) v = leaky(fmaf(v, s, h));
+      m = fmaxf(m, v);
+    }
+    out[(((long long)b * C_total + coff + c) * 12 + pc) * T + t] = m;
+  }
+}
+
+// ---- train-mode BatchNorm pieces (batch statistics over (B, rows, T) per channel) ---------------
+// stats[2c] += sum, stats[2c+1] += sum of squares (double); in is (B, C_total, R, T) viewed at channel coff + c.
+__global__ void bn_stats_kernel(const float* __restrict__ in, int B, int C_total, int coff, int RT_elems,
+                                double* __restrict__ stats) {
+  const int c = blockIdx.y;
+  const long long n = (long long)B * RT_elems;
+  double s = 0.0, ss = 0.0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / RT_elems, e = i - b * RT_elems;
+    const double v = (double)__ldg(in + ((b * C_total + coff + c) * (long long)RT_elems) + e);
+    s += v;
+    ss += v * v;
+  }
+  __shared__ double sh[2][32];
+  for (int o = 16; o; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  }
+  if ((threadIdx.x & 31) == 0) sh[0][threadIdx.x >> 5] = s, sh[1][threadIdx.x >> 5] = ss;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int nw = blockDim.x >> 5;
+    s = threadIdx.x < nw ? sh[0][threadIdx.x] : 0.0;
+    ss = threadIdx.x < nw ? sh[1][threadIdx.x] : 0.0;
+    for (int o = 16; o; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    }
+    if (threadIdx.x == 0) {
+      atomicAdd(stats + 2 * c, s);
+      atomicAdd(stats + 2 * c + 1, ss);
+    }
+  }
+}
+
+// scale = gamma / sqrt(var + eps), shift = beta - mean * scale (the conv bias is already inside the raw values)
+__global__ void bn_finalize_kernel(const double* __restrict__ stats, double count, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, int C, float* __restrict__ scale,
+                                   float* __restrict__ shift, float* __restrict__ stats_out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double mean = stats[2 * c] / count;
+  double var = stats[2 * c + 1] / count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const double s = (double)gamma[c] / sqrt(var + (double)kBnEps);
+  scale[c] = (float)s;
+  shift[c] = (float)((double)beta[c] - mean * s);
+  if (stats_out) stats_out[c] = (float)mean, stats_out[C + c] = (float)var;
+}
+
+// in-place y = act(x*scale[c] + shift[c]) over channels [coff, coff+C) of a (B, C_total, R*T) tensor
+__global__ void affine_act_kernel(float* __restrict__ x, int B, int C_total, int coff, int C, int RT_elems,
+                                  const float* __restrict__ scale, const float* __restrict__ shift, int act) {
+  const long long n = (long long)B * C * RT_elems;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long e = i % RT_elems;
+    long long q = i / RT_elems;
+    const int c = q % C;
+    const long long b = q / C;
+    float* p = x + ((b * C_total + coff + c) * (long long)RT_elems) + e;
+    float v = fmaf(*p, scale[c], shift[c]);
+    *p = act ? leaky(v) : v;
+  }
+}
+
+// MaxPool2d((1,2)) with optional affine+act first: (B,C,R,T) -> (B,C,R,T/2)
+__global__ void timepool_kernel(const float* __restrict__ in, int B, int C, int R, int T, const float* __restrict__ scale,
+                                const float* __restrict__ shift, int affine_act, float* __restrict__ out) {
+  const int T2 = T / 2;
+  const long long n = (long long)B * C * R * T2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int u = i % T2;
+    const long long line = i / T2;
+    const int c = (line / R) % C;
+    float v0 = __ldg(in + line * T + 2 * u), v1 = __ldg(in + line * T + 2 * u + 1);
+    if (affine_act) {
+      v0 = leaky(fmaf(v0, scale[c], shift[c]));
+      v1 = leaky(fmaf(v1, scale[c], shift[c]));
+    }
+    out[i] = fmaxf(v0, v1);
+  }
+}
+
+// ---- masked temporal mean / max + sigmoid (models.py:754-804) -----------------------------------
+// One warp per output element (clip, head row).  frames: key (B,12,Th), tonic (B,12,Th), genre (B,11,Th).
+// Fixed summation order (lane-strided partial sums, then a shuffle tree) independent of the row index.
+__global__ void head_reduce_kernel(const float* __restrict__ key_f, const float* __restrict__ tonic_f,
+                                   const float* __restrict__ genre_f, int B, int Th, const int* __restrict__ seq_len,
+                                   int pool_div, int head_shrink, int max_pool, float* __restrict__ key_out,
+                                   float* __restrict__ tonic_out, float* __restrict__ genre_out) {
+  const int rows_per_clip = genre_f ? 35 : 24;
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (gw >= B * rows_per_clip) return;
+  const int b = gw / rows_per_clip, rr = gw - b * rows_per_clip;
+  const float* src;
+  float* dst;
+  int is_key = 0;
+  if (rr < 12) {
+    src = key_f + ((long long)b * 12 + rr) * Th, dst = key_out + b * 12 + rr, is_key = 1;
+  } else if (rr < 24) {
+    src = tonic_f + ((long long)b * 12 + rr - 12) * Th, dst = tonic_out + b * 12 + rr - 12;
+  } else {
+    src = genre_f + ((long long)b * 11 + rr - 24) * Th, dst = genre_out + b * 11 + rr - 24;
+  }
+  int n = Th;
+  bool use_max = max_pool != 0;
+  if (seq_len) {
+    // actual_seq_length = floor(seq / pool^(L-1)) - (k-1)*head_layers  (models.py:757-760); slicing clamps to Th
+    n = min(Th, seq_len[b] / pool_div - head_shrink);
+    use_max = max_pool && b == 0;  // reference quirk: max_pool honoured for sample 0 only (models.py:765-785)
+  }
+  float v;
+  if (n <= 0) {
+    v = use_max ? -INFINITY : __int_as_float(0x7fc00000);  // empty slice: torch.mean -> nan
+  } else if (use_max) {
+    float m = -INFINITY;
+    for (int t = lane; t < n; t += 32) m = fmaxf(m, __ldg(src + t));
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    v = m;
+  } else {
+    float s = 0.f;
+    for (int t = lane; t < n; t += 32) s += __ldg(src + t);
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    v = s / (float)n;
+  }
+  if (is_key) v = 1.f / (1.f + expf(-v));
+  if (lane == 0) *dst = v;
+}
+
+// ---- key / tonic / genre decode (models.py:1083-1085, 1096, 923) --------------------------------
+__constant__ unsigned short kKeySignatureBits[21] = {
+    // bit (11 - pc) set when pitch class pc belongs to the signature; rows of utils/key_signatures.py:19-42
+    0x5AB, 0x56B, 0xD6A, 0xD5A, 0xB5A, 0xB56, 0xAD6, 0xAD5, 0xAB5, 0x6B5, 0x6AD,
+    0x5AD, 0x5AB, 0x56B, 0xD6A, 0x6B5, 0x5AD, 0x6AD, 0xB5A, 0xD5A, 0xB56};
+
+__global__ void decode_kernel(const float* __restrict__ key_out, const float* __restrict__ tonic_out,
+                              const float* __restrict__ genre_out, int B, int* __restrict__ key_id,
+                              int* __restrict__ tonic_id, int* __restrict__ genre_id) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  if (key_id) {
+    float k[12], nk = 0.f;
+    for (int i = 0; i < 12; ++i) k[i] = key_out[b * 12 + i], nk = fmaf(k[i], k[i], nk);
+    const float inv = 1.f / (fmaxf(sqrtf(nk), 1e-8f) * sqrtf(7.f));
+    int best = 0;
+    float bv = -INFINITY;
+    for (int r = 0; r < 21; ++r) {
+      float d = 0.f;
+      for (int i = 0; i < 12; ++i)
+        if ((kKeySignatureBits[r] >> (11 - i)) & 1) d += k[i];
+      d *= inv;
+      if (d > bv) bv = d, best = r;  // strict '>' keeps the first maximum, as torch.argmax does
+    }
+    key_id[b] = best;
+  }
+  if (tonic_id) {
+    int best = 0;
+    for (int i = 1; i < 12; ++i)
+      if (tonic_out[b * 12 + i] > tonic_out[b * 12 + best]) best = i;
+    tonic_id[b] = best;
+  }
+  if (genre_id) {
+    int best = -1;
+    if (genre_out) {
+      best = 0;
+      for (int i = 1; i < 11; ++i)
+        if (genre_out[b * 11 + i] > genre_out[b * 11 + best]) best = i;
+    }
+    genre_id[b] = best;
+  }
+}
+
+// ---- parameter preparation ---------------------------------------------------------------------
+// Repack a (Cout,Cin,KH,KW) conv weight to [Cin][KH][KW][cout_pad] (zero padded output channels).
+__global__ void pack_conv_kernel(const float* __restrict__ w, int Cout, int Cin, int KHW, int cout_pad,
+                                 float* __restrict__ dst) {
+  const int n = Cin * KHW * cout_pad;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int co = i % cout_pad, k = i / cout_pad;  // k = ci*KHW + tap
+    dst[i] = co < Cout ? w[(long long)co * Cin * KHW + k] : 0.f;
+  }
+}
+
+// Eval-mode epilogue (BatchNorm folded on running statistics) and the raw epilogue (bias only).
+__global__ void fold_bn_kernel(const float* __restrict__ bias, const float* __restrict__ gamma,
+                               const float* __restrict__ beta, const float* __restrict__ mean,
+                               const float* __restrict__ var, int C, float* __restrict__ scale_eval,
+                               float* __restrict__ shift_eval, float* __restrict__ scale_raw,
+                               float* __restrict__ shift_raw) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double bb = bias ? (double)bias[c] : 0.0;
+  scale_raw[c] = 1.f;
+  shift_raw[c] = (float)bb;
+  if (gamma) {
+    const double s = (double)gamma[c] / sqrt((double)var[c] + (double)kBnEps);
+    scale_eval[c] = (float)s;
+    shift_eval[c] = (float)((bb - (double)mean[c]) * s + (double)beta[c]);
+  } else {
+    scale_eval[c] = 1.f;
+    shift_eval[c] = (float)bb;
+  }
+}
+
+}  // namespace ake

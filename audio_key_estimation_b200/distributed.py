@@ -1,0 +1,98 @@
+"""Batch sharding of clips across the GPUs of one box.
+
+Clips are independent in eval mode (BatchNorm uses running statistics), so the batch is split
+into contiguous clip ranges, one process per GPU, with NO collective on the data path; the only
+exchange is one all-gather of the (clips, 35) result rows -- 12 key probabilities, 12 tonic
+logits, 11 genre logits -- and, optionally, one all-reduce of a few metric counters.  The
+reference itself is single-GPU (train_model.py:86,116); this layer is new.
+
+Works with the ``nccl`` backend on CUDA tensors (production) and with ``gloo`` on CPU tensors
+(host-logic tests, tests/test_distributed_cpu.py).
+"""
+from __future__ import annotations
+
+import os
+from typing import List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+ROW = 35  # 12 key + 12 tonic + 11 genre
+
+
+def shard_range(n_clips: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous [lo, hi) clip range of ``rank``; the first ``n_clips % world`` ranks hold one extra clip."""
+    if world <= 0 or not 0 <= rank < world or n_clips < 0:
+        raise ValueError("bad shard arguments")
+    base, extra = divmod(n_clips, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def shard_counts(n_clips: int, world: int) -> List[int]:
+    return [shard_range(n_clips, r, world)[1] - shard_range(n_clips, r, world)[0] for r in range(world)]
+
+
+def init_from_env(backend: Optional[str] = None) -> Tuple[int, int, int]:
+    """(rank, local_rank, world) from torchrun's environment; initialises the process group if world > 1."""
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29511")
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        kwargs = {}
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+            kwargs["device_id"] = torch.device("cuda", local)
+        dist.init_process_group(backend=backend, rank=rank, world_size=world, **kwargs)
+    return rank, local, world
+
+
+def pack_rows(key: torch.Tensor, tonic: torch.Tensor, genre: Optional[torch.Tensor]) -> torch.Tensor:
+    """(n, 35) fp32 rows [key | tonic | genre-or-zeros]."""
+    n = key.shape[0]
+    rows = torch.zeros((n, ROW), dtype=torch.float32, device=key.device)
+    rows[:, :12] = key
+    rows[:, 12:24] = tonic
+    if genre is not None:
+        rows[:, 24:] = genre
+    return rows
+
+
+def unpack_rows(rows: torch.Tensor, genre: bool):
+    out = (rows[:, :12], rows[:, 12:24])
+    return out + ((rows[:, 24:],) if genre else ())
+
+
+def gather_rows(local_rows: torch.Tensor, n_clips: int, group=None) -> torch.Tensor:
+    """All ranks receive the (n_clips, 35) table in clip order.  One collective (all_gather_into_tensor on
+    equal-size padded shards: NCCL's fast path; ragged tails are trimmed afterwards)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        if local_rows.shape[0] != n_clips:
+            raise ValueError("single process must hold every clip")
+        return local_rows
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    counts = shard_counts(n_clips, world)
+    if local_rows.shape[0] != counts[rank]:
+        raise ValueError(f"rank {rank} holds {local_rows.shape[0]} rows, expected {counts[rank]}")
+    width = local_rows.shape[1]
+    cmax = max(counts)
+    send = local_rows
+    if counts[rank] != cmax:
+        send = torch.zeros((cmax, width), dtype=local_rows.dtype, device=local_rows.device)
+        send[: counts[rank]] = local_rows
+    recv = torch.empty((world * cmax, width), dtype=local_rows.dtype, device=local_rows.device)
+    dist.all_gather_into_tensor(recv, send.contiguous(), group=group)
+    if all(c == cmax for c in counts):
+        return recv
+    return torch.cat([recv[r * cmax: r * cmax + counts[r]] for r in range(world)], dim=0)
+
+
+def reduce_counters(counters: torch.Tensor, group=None) -> torch.Tensor:
+    """Sum a small vector of metric counters over ranks (in place)."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(counters, op=dist.ReduceOp.SUM, group=group)
+    return counters

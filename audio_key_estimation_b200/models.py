@@ -1,0 +1,282 @@
+"""``PitchClassNet`` -- drop-in for the reference's ``models.PitchClassNet`` forward path.
+
+Same constructor arguments, same ``state_dict`` key names/shapes, same ``forward(mel, seq_length)``
+contract and output tuple as models.py:651-817 (call sites train_model.py:105, eval.py:98,
+equivariance_test.py:178), but the forward pass is one call into libake_b200.so
+(``ake_pcn_forward_f32``, include/ake_b200.h) running hand-written sm_100a kernels.  There is no
+PyTorch/CPU fallback: CPU tensors, missing CUDA library and unsupported architecture switches
+all raise.
+
+Differences a maintainer should know (also in INTEGRATION.md):
+* arithmetic is fp32 on the device (the reference runs cuDNN float64); inputs of any float dtype
+  are accepted and the outputs are returned in the input's dtype (``general_step`` feeds
+  ``key_out`` to ``BCELoss`` against ``.double()`` labels, models.py:823, 878);
+* forward only: outputs carry no autograd graph (the training step is SURVEY.md section 8 a-15,
+  "config 5", not built yet) -- calling it under ``torch.enable_grad()`` with parameters that
+  require grad works but returns detached tensors;
+* ``net.modules()`` works (the reference shadows it with a list, models.py:673).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Optional, Tuple
+
+import torch
+from torch import nn
+
+from . import _lib
+from ._lib import PcnConfig, check
+
+_UNSUPPORTED_FLAGS = ("resblock", "denseblock", "stay_sixth", "only_semitones", "p2pc_conv", "pc2p_mem", "local")
+
+
+class _Workspace:
+    """Grow-only device scratch buffer per (device, tag)."""
+
+    _bufs: dict = {}
+
+    @classmethod
+    def get(cls, device: torch.device, nbytes: int, tag: str = "pcn") -> torch.Tensor:
+        key = (device.index if device.index is not None else torch.cuda.current_device(), tag)
+        buf = cls._bufs.get(key)
+        if buf is None or buf.numel() < nbytes:
+            buf = None
+            cls._bufs.pop(key, None)
+            buf = torch.empty(int(nbytes * 1.05) + 256, dtype=torch.uint8, device=device)
+            cls._bufs[key] = buf
+        return buf
+
+
+def _opt_get(opt, name, default):
+    return getattr(opt, name, default) if opt is not None else default
+
+
+class _Node(nn.Module):
+    """Name-only container so parameters appear under the reference's dotted state_dict keys."""
+
+
+class PitchClassNet(nn.Module):
+    """Reference signature: models.py:653.  ``opt`` carries the train_model.py:160-242 flags."""
+
+    def __init__(self, pitches, pitch_classes, num_layers, kernel_size, opt=None, window_size=23, batch_size=4,
+                 train_set=None, val_set=None):
+        super().__init__()
+        if opt is None:
+            # the reference dereferences opt.conv_layers unconditionally (models.py:662) -> AttributeError
+            raise AttributeError("'NoneType' object has no attribute 'conv_layers'")
+        self.pitches, self.pitch_classes = int(pitches), int(pitch_classes)
+        self.num_layers, self.kernel_size = int(num_layers), int(kernel_size)
+        self.batch_size, self.window_size, self.opt = batch_size, window_size, opt
+        self.conv_layers, self.n_filters = int(opt.conv_layers), int(opt.n_filters)
+        self.resblock, self.denseblock = bool(_opt_get(opt, "resblock", False)), bool(_opt_get(opt, "denseblock", False))
+        self.best_mirex_score = 0
+        self.data = {"train": train_set, "val": val_set}
+
+        cfg = PcnConfig(
+            pitches=self.pitches, pitch_classes=self.pitch_classes, num_layers=self.num_layers,
+            kernel_size=self.kernel_size, conv_layers=self.conv_layers, n_filters=self.n_filters,
+            head_layers=int(_opt_get(opt, "head_layers", 2)), time_pool_size=int(_opt_get(opt, "time_pool_size", 2)),
+            genre=int(bool(_opt_get(opt, "genre", False))), max_pool=int(bool(_opt_get(opt, "max_pool", False))),
+            **{f: int(bool(_opt_get(opt, f, False))) for f in _UNSUPPORTED_FLAGS})
+        self._cfg = cfg
+        self._genre = bool(cfg.genre)
+        lib = _lib.lib()
+        handle = C.c_void_p()
+        check(lib.ake_pcn_create(C.byref(cfg), C.byref(handle)))  # NotImplementedError for unsupported switches
+        self._plan = handle
+        self._plan_device: Optional[torch.device] = None
+        self._param_key = None
+
+        # ---- parameters / buffers under the reference's names
+        self._tensor_names = []
+        n = lib.ake_pcn_num_tensors(handle)
+        shape4 = (C.c_int64 * 4)()
+        for i in range(n):
+            name = lib.ake_pcn_tensor_name(handle, i).decode()
+            nd = lib.ake_pcn_tensor_shape(handle, i, C.byref(shape4))
+            shape = tuple(int(shape4[k]) for k in range(nd))
+            self._tensor_names.append(name)
+            self._register(name, shape)
+        self._bn_sites = [nm[: -len(".running_mean")] for nm in self._tensor_names if nm.endswith(".running_mean")]
+        self._bn_channels = [self._lookup(s + ".running_mean").numel() for s in self._bn_sites]
+        self.sig = nn.Sigmoid()
+
+    # -------------------------------------------------------------------------------- module tree
+    def _register(self, name: str, shape) -> None:
+        parts = name.split(".")
+        node = self
+        for p in parts[:-1]:
+            if p not in node._modules:
+                node.add_module(p, _Node())
+            node = node._modules[p]
+        leaf = parts[-1]
+        if leaf in ("running_mean", "running_var"):
+            init = torch.zeros(shape) if leaf == "running_mean" else torch.ones(shape)
+            node.register_buffer(leaf, init)
+            if leaf == "running_var":
+                node.register_buffer("num_batches_tracked", torch.tensor(0, dtype=torch.long))
+            return
+        is_bn = len(shape) == 1 and not hasattr(node, "weight") and leaf == "weight"
+        if len(shape) == 4:
+            # torch default conv init: kaiming_uniform(a=sqrt(5)) == U(-1/sqrt(fan_in), 1/sqrt(fan_in));
+            # train_model.py:14-17 defines weights_init but never applies it.
+            fan_in = shape[1] * shape[2] * shape[3]
+            node._ake_fan_in = fan_in
+            t = torch.empty(shape).uniform_(-1.0 / math.sqrt(fan_in), 1.0 / math.sqrt(fan_in))
+        elif is_bn:
+            t = torch.ones(shape)
+        elif leaf == "bias" and hasattr(node, "_ake_fan_in"):
+            b = 1.0 / math.sqrt(node._ake_fan_in)
+            t = torch.empty(shape).uniform_(-b, b)
+        else:
+            t = torch.zeros(shape)  # BatchNorm bias
+        node.register_parameter(leaf, nn.Parameter(t))
+
+    def _lookup(self, name: str) -> torch.Tensor:
+        node = self
+        parts = name.split(".")
+        for p in parts[:-1]:
+            node = node._modules[p]
+        leaf = parts[-1]
+        return node._parameters[leaf] if leaf in node._parameters else node._buffers[leaf]
+
+    def __del__(self):
+        try:
+            if getattr(self, "_plan", None):
+                _lib.lib().ake_pcn_destroy(self._plan)
+                self._plan = None
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------------------- parameters
+    def _sync_params(self, device: torch.device, stream_ptr: int) -> None:
+        tensors = [self._lookup(n) for n in self._tensor_names]
+        key = (str(device),) + tuple((t.data_ptr(), t._version) for t in tensors)
+        if key == self._param_key:
+            return
+        for t in tensors:
+            if t.device != device:
+                raise RuntimeError(f"PitchClassNet parameters live on {t.device} but the input is on {device}; "
+                                   "move the module with .cuda()/.to(device) (there is no CPU path)")
+        flat = torch.cat([t.detach().reshape(-1).to(torch.float32) for t in tensors])
+        lib = _lib.lib()
+        check(lib.ake_pcn_set_params_f32(self._plan, flat.data_ptr(), flat.numel(), stream_ptr))
+        self._param_key = key
+
+    # ---------------------------------------------------------------------------------- forward
+    def forward(self, mel: torch.Tensor, seq_length=None) -> Tuple[torch.Tensor, ...]:
+        """models.py:747-817.  mel (B,1,pitches,T); seq_length None | int tensor (B,) | (1,1)."""
+        if _opt_get(self.opt, "local", False):
+            raise NotImplementedError("opt.local sliding-window heads are outside the B200 hot path")
+        if not isinstance(mel, torch.Tensor) or mel.dim() != 4 or mel.shape[1] != 1 or mel.shape[2] != self.pitches:
+            raise ValueError(f"mel must be (B, 1, {self.pitches}, T), got {tuple(getattr(mel, 'shape', ()))}")
+        if not mel.is_cuda:
+            raise RuntimeError("PitchClassNet (B200) runs on CUDA tensors only; there is no CPU fallback")
+        if not mel.is_floating_point():
+            raise ValueError("mel must be a floating-point tensor")
+        lib = _lib.lib()
+        device, out_dtype = mel.device, mel.dtype
+        B, T = int(mel.shape[0]), int(mel.shape[3])
+        with torch.cuda.device(device):
+            stream = torch.cuda.current_stream(device).cuda_stream
+            self._sync_params(device, stream)
+            x = mel.detach().to(torch.float32).contiguous()
+            seq = None
+            if seq_length is not None:
+                seq = torch.as_tensor(seq_length).reshape(-1)
+                if seq.numel() == 1 and B > 1:
+                    seq = seq.expand(B)
+                if seq.numel() != B:
+                    raise ValueError(f"seq_length has {seq.numel()} entries for a batch of {B}")
+                seq = seq.to(device=device, dtype=torch.int32).contiguous()
+            train = bool(self.training)
+            ws_bytes = lib.ake_pcn_workspace_bytes(self._plan, B, T, int(train))
+            if ws_bytes == 0:
+                check(_lib.AKE_ERR_INVALID)
+            ws = _Workspace.get(device, ws_bytes)
+            key = torch.empty((B, 12), dtype=torch.float32, device=device)
+            tonic = torch.empty((B, 12), dtype=torch.float32, device=device)
+            genre = torch.empty((B, 11), dtype=torch.float32, device=device) if self._genre else None
+            stats = None
+            if train:
+                stats = torch.empty(2 * sum(self._bn_channels), dtype=torch.float32, device=device)
+            check(lib.ake_pcn_forward_f32(
+                self._plan, x.data_ptr(), B, T, seq.data_ptr() if seq is not None else None, int(train),
+                key.data_ptr(), tonic.data_ptr(), genre.data_ptr() if genre is not None else None,
+                stats.data_ptr() if stats is not None else None, ws.data_ptr(), ws.numel(), stream))
+            if train:
+                self._update_running_stats(stats, B, T)
+        outs = (key, tonic) + ((genre,) if self._genre else ())
+        return tuple(o.to(out_dtype) for o in outs)
+
+    def _bn_counts(self, B: int, T: int):
+        """Elements per channel each BN site normalises over (B * rows * frames), in site order."""
+        counts = []
+        S = self.pitches // 3
+        k, hl = self.kernel_size, int(_opt_get(self.opt, "head_layers", 2))
+        Tn = T
+        for name in self._bn_sites:
+            if name.startswith("model."):
+                L = int(name.split(".")[1])
+                Tl = T // (2 ** max(L - 1, 0)) if L > 0 else T
+                if ".pool_semi_b" in name:
+                    counts.append(B * S * Tl)
+                elif ".up_sixth_b" in name:
+                    counts.append(B * 36 * Tl)
+                elif ".p2p." in name:
+                    counts.append(B * self.pitches * Tl)
+                else:
+                    counts.append(B * 12 * Tl)
+                Tn = Tl // 2 if L > 0 else Tl
+            else:
+                i = int(name.split(".")[1]) // 3  # head conv index this BN follows
+                counts.append(B * 12 * (Tn - (k - 1) * (i + 1)))
+        return counts
+
+    @torch.no_grad()
+    def _update_running_stats(self, stats: torch.Tensor, B: int, T: int) -> None:
+        """nn.BatchNorm2d train-mode buffer update (momentum 0.1, unbiased variance)."""
+        off = 0
+        for site, Cn, n in zip(self._bn_sites, self._bn_channels, self._bn_counts(B, T)):
+            mean, var = stats[off: off + Cn], stats[off + Cn: off + 2 * Cn]
+            off += 2 * Cn
+            rm, rv = self._lookup(site + ".running_mean"), self._lookup(site + ".running_var")
+            nb = self._lookup(site + ".num_batches_tracked")
+            unbiased = var * (n / max(n - 1, 1))
+            rm.mul_(0.9).add_(mean.to(rm.dtype), alpha=0.1)
+            rv.mul_(0.9).add_(unbiased.to(rv.dtype), alpha=0.1)
+            nb.add_(1)
+
+    # ---------------------------------------------------------------------- parity/debug helpers
+    def tap(self, name: str) -> torch.Tensor:
+        """Flat fp32 copy of a named intermediate of the last forward (oracle/pcn_port.py tap names)."""
+        lib = _lib.lib()
+        n = lib.ake_pcn_get_tap(self._plan, name.encode(), None, 0, None)
+        if n < 0:
+            check(int(n))
+        dev = self._lookup(self._tensor_names[0]).device
+        out = torch.empty(int(n), dtype=torch.float32, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        n2 = lib.ake_pcn_get_tap(self._plan, name.encode(), out.data_ptr(), out.numel(), stream)
+        if n2 < 0:
+            check(int(n2))
+        return out
+
+
+def decode(key_out: torch.Tensor, tonic_out: torch.Tensor, genre_out: Optional[torch.Tensor] = None):
+    """argmax key signature / tonic / genre ids on the device (models.py:1083-1085, 1096, 923)."""
+    if not key_out.is_cuda:
+        raise RuntimeError("decode runs on CUDA tensors only")
+    lib = _lib.lib()
+    B = key_out.shape[0]
+    dev = key_out.device
+    k = key_out.detach().to(torch.float32).contiguous()
+    t = tonic_out.detach().to(torch.float32).contiguous()
+    g = genre_out.detach().to(torch.float32).contiguous() if genre_out is not None else None
+    ids = torch.empty((3, B), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        check(lib.ake_decode_f32(k.data_ptr(), t.data_ptr(), g.data_ptr() if g is not None else None, B,
+                                 ids[0].data_ptr(), ids[1].data_ptr(), ids[2].data_ptr(), stream))
+    return (ids[0], ids[1]) + ((ids[2],) if g is not None else ())

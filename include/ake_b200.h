@@ -1,0 +1,152 @@
+/* ake_b200.h -- C ABI of the B200-native Audio-Key-Estimation hot path.
+ *
+ * One shared library (libake_b200.so, built from audio_key_estimation_b200/csrc
+ * with nvcc for sm_100a) exports exactly the entry points below.  They replace,
+ * for the reference repository flo-stilz/Audio-Key-Estimation:
+ *
+ *   ake_cqt_*      librosa.cqt(...) + abs + log(1+x) + reshape at
+ *                  KeyDataset.py:485-509 (same call at equivariance_test.py:155-170)
+ *   ake_pcn_*      PitchClassNet.__init__ / forward, models.py:651-817
+ *                  (layers models.py:22-399), state_dict contract eval.py:113-115
+ *   ake_decode_*   the argmax key / tonic / genre rule, models.py:1083-1085,1096,923
+ *   ake_estimate_* the two stages chained for host buffers (the loop eval.py:118-129
+ *                  drives through KeyDataset + trainer.validate)
+ *
+ * Conventions: plain C types only; every pointer named *_dev is a CUDA device
+ * pointer owned by the caller (PyTorch allocates them), *_host is host memory;
+ * `stream` is a cudaStream_t passed as void*; calls are asynchronous on that
+ * stream unless stated; the return value is 0 on success or a negative AKE_ERR_*
+ * code, with a thread-local message available from ake_last_error().  Plans
+ * hold no mutable global state: different plans may be driven from different
+ * host threads / streams.  There is no CPU fallback: every compute entry point
+ * launches CUDA kernels or fails.
+ */
+#ifndef AKE_B200_H
+#define AKE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AKE_ABI_VERSION 1
+
+#define AKE_OK 0
+#define AKE_ERR_INVALID (-1)      /* bad argument / shape (the reference asserts: models.py:43-44,101,356-357) */
+#define AKE_ERR_UNSUPPORTED (-2)  /* option combination outside the hot path */
+#define AKE_ERR_CUDA (-3)         /* CUDA runtime error */
+#define AKE_ERR_WORKSPACE (-4)    /* caller workspace too small */
+
+typedef struct ake_pcn ake_pcn; /* PitchClassNet plan: architecture + device weights */
+typedef struct ake_cqt ake_cqt; /* CQT plan: decimator taps + dense time-domain filter bank */
+
+int ake_abi_version(void);
+const char* ake_last_error(void);
+/* Number of kernels this library launched from the calling thread since the last reset. */
+int64_t ake_launch_count(int reset);
+
+/* ---------------------------------------------------------------- PitchClassNet */
+
+/* Mirrors the fields PitchClassNet.__init__/forward read from `opt`
+ * (models.py:260-350, 662-742, 766-794) plus the positional ctor arguments
+ * (models.py:653).  Booleans are 0/1. */
+typedef struct ake_pcn_config {
+  int32_t pitches;        /* ctor arg; 36*octaves: 288 (train_model.py:93-94) or 360 (equivariance_test.py:176) */
+  int32_t pitch_classes;  /* ctor arg; must be 12 (models.py:171,208 hard-code it) */
+  int32_t num_layers;     /* opt.num_layers, default 2 */
+  int32_t kernel_size;    /* opt.kernel_size, default 7 */
+  int32_t conv_layers;    /* opt.conv_layers, default 3 */
+  int32_t n_filters;      /* opt.n_filters, default 4 */
+  int32_t head_layers;    /* opt.head_layers, default 2 */
+  int32_t time_pool_size; /* opt.time_pool_size, default 2 */
+  int32_t genre;          /* opt.genre */
+  int32_t max_pool;       /* opt.max_pool */
+  /* architecture switches that are NOT on the hot path: any non-zero -> AKE_ERR_UNSUPPORTED */
+  int32_t resblock, denseblock, stay_sixth, only_semitones, p2pc_conv, pc2p_mem, local;
+} ake_pcn_config;
+
+int ake_pcn_create(const ake_pcn_config* cfg, ake_pcn** out);
+void ake_pcn_destroy(ake_pcn* plan);
+
+/* The float tensors of the reference state_dict, in state_dict order, WITHOUT the int64
+ * `num_batches_tracked` entries.  ake_pcn_set_params_f32 takes them concatenated in this order. */
+int ake_pcn_num_tensors(const ake_pcn* plan);
+const char* ake_pcn_tensor_name(const ake_pcn* plan, int i);
+int ake_pcn_tensor_shape(const ake_pcn* plan, int i, int64_t shape4[4]); /* returns ndim */
+int64_t ake_pcn_param_floats(const ake_pcn* plan);
+int ake_pcn_set_params_f32(ake_pcn* plan, const float* flat_dev, int64_t n_floats, void* stream);
+
+/* bn_mode: 0 = eval (running statistics, eval.py:116); 1 = train (batch statistics,
+ * equivariance_test.py:178 leaves the model in train mode). */
+size_t ake_pcn_workspace_bytes(const ake_pcn* plan, int B, int T, int bn_mode);
+
+/* forward(mel, seq_length) of models.py:747-817.
+ *   mel_dev      (B,1,pitches,T) fp32, contiguous
+ *   seq_len_dev  int32[B] valid frames per clip, or NULL (= seq_length None: plain mean over all frames)
+ *   key_out_dev  (B,12) sigmoid probabilities; tonic_out_dev (B,12) logits;
+ *   genre_out_dev (B,11) logits, required iff cfg.genre
+ *   bn_stats_out_dev  optional (train mode): for every BatchNorm site in state_dict order, C batch means
+ *                     followed by C biased batch variances (so the caller can update running buffers) */
+int ake_pcn_forward_f32(ake_pcn* plan, const float* mel_dev, int B, int T, const int32_t* seq_len_dev,
+                        int bn_mode, float* key_out_dev, float* tonic_out_dev, float* genre_out_dev,
+                        float* bn_stats_out_dev, void* ws_dev, size_t ws_bytes, void* stream);
+int ake_pcn_bn_channels(const ake_pcn* plan); /* total channels over all BN sites */
+int ake_pcn_get_config(const ake_pcn* plan, ake_pcn_config* out);
+
+/* Debug/parity taps: copy a named intermediate of the LAST forward out of the workspace.
+ * Names follow oracle/pcn_port.py taps ("l0.semi", "l1.p2p2", "pc_final", "key_frames", ...).
+ * Returns the number of floats (negative error); `out_dev` may be NULL to query the size. */
+int64_t ake_pcn_get_tap(const ake_pcn* plan, const char* name, float* out_dev, int64_t cap, void* stream);
+
+/* argmax key signature (cosine similarity against the 21x12 table of utils/key_signatures.py:19-42),
+ * argmax tonic, argmax genre (genre_out_dev / genre_id_dev may be NULL). */
+int ake_decode_f32(const float* key_out_dev, const float* tonic_out_dev, const float* genre_out_dev, int B,
+                   int32_t* key_id_dev, int32_t* tonic_id_dev, int32_t* genre_id_dev, void* stream);
+
+/* ---------------------------------------------------------------- constant-Q front-end */
+
+/* librosa.cqt(y, sr, hop_length, fmin, n_bins, bins_per_octave, filter_scale, sparsity) with the other
+ * arguments at their librosa-0.9.2 defaults (tuning 0, norm 1, hann, scale True, pad_mode 'constant',
+ * res_type None -> kaiser_fast).  fmin <= 0 selects C1.  Fails (AKE_ERR_INVALID) where librosa 0.9.2
+ * raises ParameterError (hop not a multiple of 2^(n_octaves-1), top filter above Nyquist) and
+ * (AKE_ERR_UNSUPPORTED) where its recursion would early-downsample or switch resampler. */
+int ake_cqt_create(double sr, int hop_length, int n_bins, int bins_per_octave, double fmin, double filter_scale,
+                   double sparsity, ake_cqt** out);
+void ake_cqt_destroy(ake_cqt* plan);
+int ake_cqt_n_fft(const ake_cqt* plan);
+int ake_cqt_n_bins(const ake_cqt* plan);
+int ake_cqt_frames(const ake_cqt* plan, int64_t n_samples); /* frames librosa returns for a clip of that length */
+/* The dense real time-domain bank the kernels contract with: (2*bins_per_octave, n_fft) fp32, row 2k = Re, 2k+1 = Im. */
+int ake_cqt_get_bank(const ake_cqt* plan, float* bank_host, int64_t cap_floats);
+int ake_cqt_get_decimator(const ake_cqt* plan, float* taps_host, int cap); /* returns #taps of the half filter (32) */
+size_t ake_cqt_workspace_bytes(const ake_cqt* plan, int B, int64_t n_max);
+
+#define AKE_CQT_LOGMAG 0  /* log(1+|C|): what KeyDataset.py:497-499 feeds the network */
+#define AKE_CQT_COMPLEX 1 /* raw complex64 C (interleaved re,im): what librosa.cqt returns */
+
+/* audio_dev: B clips, clip b at audio_dev + b*stride, lengths_host[b] valid samples (NULL: all n_max).
+ * out_dev: mode LOGMAG (B,1,n_bins,T_max) fp32 zero-padded beyond each clip's frames (KeyDataset.py:242-254);
+ *          mode COMPLEX (B,n_bins,T_max,2) fp32.
+ * seq_len_out_dev: optional int32[B] frames per clip (the `seq_length` batch field, KeyDataset.py:254). */
+int ake_cqt_run_f32(ake_cqt* plan, const float* audio_dev, int64_t stride, const int64_t* lengths_host, int B,
+                    int64_t n_max, int mode, float* out_dev, int T_max, int32_t* seq_len_out_dev, void* ws_dev,
+                    size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------- host-buffer pipeline */
+
+size_t ake_estimate_workspace_bytes(const ake_cqt* cqt, const ake_pcn* pcn, int B, int64_t n_max);
+/* Host audio in -> host predictions out: H2D copy, CQT, forward (eval mode), decode, D2H copy, stream sync.
+ * audio_host should be page-locked for full PCIe speed.  Outputs: key (B,12), tonic (B,12), genre (B,11 or NULL),
+ * ids int32 (3,B) = key signature ids, tonic ids, genre ids (-1 without genre head); any output may be NULL
+ * (genre_out_host must be NULL when the plan has no genre head). */
+int ake_estimate_host_f32(ake_cqt* cqt, ake_pcn* pcn, const float* audio_host, int64_t stride,
+                          const int64_t* lengths_host, int B, int64_t n_max, float* key_out_host,
+                          float* tonic_out_host, float* genre_out_host, int32_t* ids_host, void* ws_dev,
+                          size_t ws_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AKE_B200_H */

@@ -1,0 +1,61 @@
+"""World-size-2 gloo test of the multi-GPU host logic (shard -> local rows -> all-gather -> same table on every rank)."""
+import os
+import socket
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n_clips, genre, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    from audio_key_estimation_b200 import distributed as akd
+    r, _, w = akd.init_from_env("gloo")
+    assert (r, w) == (rank, world)
+    lo, hi = akd.shard_range(n_clips, rank, world)
+    ids = torch.arange(lo, hi, dtype=torch.float32)
+    # stand-in "predictions" that encode the clip id so ordering errors are visible
+    key = ids[:, None] + torch.arange(12)[None] / 100
+    tonic = -ids[:, None] + torch.arange(12)[None] / 100
+    gen = ids[:, None] * 2 + torch.arange(11)[None] / 100 if genre else None
+    table = akd.gather_rows(akd.pack_rows(key, tonic, gen), n_clips)
+    counters = akd.reduce_counters(torch.tensor([hi - lo, 1], dtype=torch.int64))
+    out = akd.unpack_rows(table, genre)
+    q.put((rank, table.clone(), counters.clone(), len(out)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_clips,genre", [(8, True), (7, False), (1, True)])
+def test_shard_gather_world2(n_clips, genre):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n_clips, genre, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    ids = torch.arange(n_clips, dtype=torch.float32)
+    for rank, table, counters, n_out in results:
+        assert table.shape == (n_clips, 35)
+        assert torch.allclose(table[:, 0], ids) and torch.allclose(table[:, 12], -ids)
+        assert torch.allclose(table[:, 24], ids * 2 if genre else torch.zeros(n_clips))
+        assert counters.tolist() == [n_clips, 2]
+        assert n_out == (3 if genre else 2)

@@ -1,0 +1,89 @@
+"""Host-side mirror of the reference interface (no GPU needed): constructor, state_dict contract,
+error behaviour, synthetic generators, shard arithmetic."""
+import numpy as np
+import pytest
+import torch
+
+import audio_key_estimation_b200 as ake
+from audio_key_estimation_b200 import distributed as akd, synth
+from conftest import golden_state_dict
+
+
+def test_state_dict_contract_strict_load():
+    for genre in (False, True):
+        net = ake.PitchClassNet(288, 12, 2, 7, opt=ake.default_opt(genre=genre), window_size=592, batch_size=8,
+                                train_set=None, val_set=None)
+        ref = golden_state_dict(genre)
+        assert list(net.state_dict()) == list(ref)
+        for k, v in net.state_dict().items():
+            assert tuple(v.shape) == tuple(ref[k].shape) and v.dtype == ref[k].dtype, k
+        net.load_state_dict(ref, strict=True)   # eval.py:113-115
+        assert torch.equal(net.state_dict()["model.1.p2p.layer.3.weight"], ref["model.1.p2p.layer.3.weight"])
+        assert sum(p.numel() for p in net.parameters()) == (167031 if genre else 162902)
+        net.double()                            # train_model.py:105 calls .double() on the module
+        assert net.state_dict()["key_classifier.0.conv2d.weight"].dtype == torch.float64
+        assert len(list(net.modules())) > 10
+
+
+def test_default_init_matches_torch_defaults():
+    torch.manual_seed(0)
+    net = ake.PitchClassNet(288, 12, 2, 7, opt=ake.default_opt())
+    sd = net.state_dict()
+    w = sd["model.1.p2p.layer.0.weight"]
+    bound = 1 / np.sqrt(5 * 49)
+    assert w.abs().max() <= bound and w.abs().max() > 0.9 * bound
+    assert torch.all(sd["model.1.p2p.layer.1.weight"] == 1) and torch.all(sd["model.1.p2p.layer.1.bias"] == 0)
+    assert torch.all(sd["model.1.p2p.layer.1.running_var"] == 1) and sd["model.1.p2p.layer.1.num_batches_tracked"] == 0
+
+
+def test_constructor_errors_mirror_reference():
+    with pytest.raises(AttributeError):
+        ake.PitchClassNet(288, 12, 2, 7)  # opt=None: models.py:662 dereferences it
+    for flag in ("resblock", "denseblock", "stay_sixth", "only_semitones", "p2pc_conv", "pc2p_mem", "local"):
+        with pytest.raises(NotImplementedError):
+            ake.PitchClassNet(288, 12, 2, 7, opt=ake.default_opt(**{flag: True}))
+    with pytest.raises(ValueError):
+        ake.PitchClassNet(288, 10, 2, 7, opt=ake.default_opt())
+
+
+def test_no_cpu_fallback():
+    net = ake.PitchClassNet(288, 12, 2, 7, opt=ake.default_opt())
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        net(torch.zeros(1, 1, 288, 64), None)
+    with pytest.raises(ValueError):
+        net(torch.zeros(1, 288, 64), None)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ake.cqt(torch.zeros(48000), sr=48000, hop_length=9600, n_bins=288, bins_per_octave=36)
+    with pytest.raises(ValueError):
+        ake.CQTPlan(44100, 8820, 288, 36)  # librosa 0.9.2 raises ParameterError for this hop
+
+
+def test_bn_counts():
+    net = ake.PitchClassNet(288, 12, 2, 7, opt=ake.default_opt(genre=True))
+    counts = dict(zip(net._bn_sites, net._bn_counts(3, 61)))
+    assert counts["model.0.pool_semi_b"] == 3 * 96 * 61
+    assert counts["model.1.up_sixth_b"] == 3 * 36 * 61
+    assert counts["model.1.p2p.layer.7"] == 3 * 288 * 61
+    assert counts["model.1.pc2pc.layer.1"] == 3 * 12 * 61
+    assert counts["key_classifier.1"] == 3 * 12 * (30 - 6)
+    assert counts["genre_classifier.1"] == 3 * 12 * (30 - 6)
+
+
+def test_synth_is_deterministic_and_tonal():
+    a = synth.synth_clip(5, 48000, 48000)
+    b = synth.synth_clip(5, 48000, 48000)
+    assert torch.equal(a, b) and a.dtype == torch.float32 and a.abs().max() <= 1.0
+    assert not torch.equal(a, synth.synth_clip(6, 48000, 48000))
+    pat = synth.custom_cqt_pattern(360, 592)
+    assert pat.shape == (360, 592) and pat[50, 330] == 20 and pat[120, 30] == 1  # equivariance_test.py:266-277
+
+
+def test_shard_ranges():
+    for n, w in ((256, 8), (10, 4), (3, 8), (0, 2), (16384, 8)):
+        ranges = [akd.shard_range(n, r, w) for r in range(w)]
+        assert ranges[0][0] == 0 and ranges[-1][1] == n
+        assert all(ranges[i][1] == ranges[i + 1][0] for i in range(w - 1))
+        assert max(b - a for a, b in ranges) - min(b - a for a, b in ranges) <= 1
+        assert akd.shard_counts(n, w) == [b - a for a, b in ranges]
+    with pytest.raises(ValueError):
+        akd.shard_range(4, 2, 2)

@@ -1,0 +1,101 @@
+"""oracle.cqt_port (PARITY UNPINNED: no librosa here, no CQT fixture in the reference): anchored on
+analytic known-answer tests, structural properties and a committed regression fixture."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from oracle import cqt_port as cp
+
+SR, HOP = 48000, 9600
+
+
+def test_decimator_taps_properties():
+    h = cp.decimator_taps()
+    assert h.shape == (63,)
+    np.testing.assert_allclose(h, h[::-1], atol=0)           # linear phase
+    assert abs(h[31] - 0.5 * 0.85) < 1e-15                   # centre tap = ratio * rolloff
+    assert abs(h.sum() - 1.0) < 1e-4                         # unit DC gain
+    # stop band: a tone above the new Nyquist is attenuated by > 60 dB, a low tone passes
+    n = np.arange(8192)
+    for f, lo, hi in ((1.0 / 16, 0.99, 1.01), (0.42, 0.0, 1e-3)):
+        y = cp.resample_half(np.sin(2 * np.pi * f * n)) * np.sqrt(0.5)
+        amp = np.abs(y[200:-200]).max()
+        assert lo <= amp <= hi, (f, amp)
+
+
+def test_resample_half_length_and_tail():
+    for n in (1000, 1001):
+        y = cp.resample_half(np.ones(n))
+        assert y.shape[0] == (n + 1) // 2
+        if n % 2:
+            assert y[-1] == 0.0  # librosa fix_length pads resampy's int(n/2) samples with a zero
+
+
+def test_frames_and_hop_rule():
+    assert cp.n_frames(SR * 30, HOP, 8) == 151
+    assert cp.n_frames(SR * 240, HOP, 8) == 1201
+    with pytest.raises(cp.ParameterError):
+        cp.cqt(np.zeros(44100), sr=44100, hop_length=8820, n_bins=288, bins_per_octave=36)  # 8820 = 2^2 * 2205
+
+
+@pytest.mark.parametrize("bin_", [36, 100, 199, 280])
+def test_pure_tone_known_answer(bin_):
+    """A*sin at a bin centre: peak at that bin, |C| ~ A/2 * sqrt(filter length)."""
+    n = SR * 4
+    f0 = cp.C1_HZ * 2 ** (bin_ / 36)
+    y = 0.3 * np.sin(2 * np.pi * f0 * np.arange(n) / SR)
+    Cq = np.abs(cp.cqt(y, SR, HOP, None, 288, 36))
+    col = Cq[:, 10]
+    assert col.argmax() == bin_
+    expect = 0.5 * 0.3 * np.sqrt(cp.constant_q_lengths(SR, cp.C1_HZ, 288, 36)[bin_])
+    assert abs(col.max() / expect - 1) < 2e-3
+
+
+def test_linearity_and_float32_mode():
+    rng = np.random.default_rng(0)
+    a, b = rng.standard_normal(SR), rng.standard_normal(SR)
+    Ca, Cb, Cab = (cp.cqt(v, SR, HOP, None, 288, 36) for v in (a, b, 2 * a - 3 * b))
+    np.testing.assert_allclose(Cab, 2 * Ca - 3 * Cb, atol=1e-9)
+    C32 = cp.cqt(a.astype(np.float32), SR, HOP, None, 288, 36, dtype=np.float32)
+    assert C32.dtype == np.complex64
+    assert np.abs(C32 - Ca).max() < 2e-4 * np.abs(Ca).max()
+
+
+def test_time_domain_bank_equals_fft_basis():
+    """The dense real bank the CUDA kernels contract with == librosa's sparse FFT basis (host tables only)."""
+    from audio_key_estimation_b200 import _lib
+    L = _lib.lib()
+    h = C.c_void_p()
+    assert L.ake_cqt_create(float(SR), HOP, 288, 36, 0.0, 1.0, 0.01, C.byref(h)) == 0
+    try:
+        n_fft = L.ake_cqt_n_fft(h)
+        assert n_fft == 1024
+        bank = np.zeros((72, n_fft), np.float32)
+        assert L.ake_cqt_get_bank(h, bank.ctypes.data, bank.size) == 0
+        fb, n2 = cp.cqt_filter_fft(float(SR), float(cp.C1_HZ * 2 ** 7), 36, 36, 1.0, 0.01)
+        assert n2 == n_fft
+        f, n = np.arange(n_fft // 2 + 1), np.arange(n_fft)
+        K = fb.astype(np.complex128) @ np.exp(-2j * np.pi * np.outer(f, n) / n_fft)
+        assert np.abs(K.real - bank[0::2]).max() < 1e-6 and np.abs(K.imag - bank[1::2]).max() < 1e-6
+        taps = (C.c_float * 32)()
+        assert L.ake_cqt_get_decimator(h, taps, 32) == 32
+        np.testing.assert_allclose(np.array(taps[:]), cp.decimator_taps()[31:], atol=1e-7)
+        for n_samp in (0, 1, 9599, 9600, SR * 30, SR * 30 + 1, 12345677):
+            assert L.ake_cqt_frames(h, n_samp) == cp.n_frames(n_samp, HOP, 8)
+    finally:
+        L.ake_cqt_destroy(h)
+
+
+def test_regression_fixture():
+    from audio_key_estimation_b200 import synth
+    g = load_golden("cqt_port.npz")
+    y = synth.synth_clip(int(g["clip_id"]), int(g["n_samples"]), SR).numpy()
+    np.testing.assert_array_equal(y[:64], g["audio_head"])
+    Cq = cp.cqt(y, SR, HOP, None, 288, 36)
+    np.testing.assert_allclose(Cq.real, g["C_re"], atol=2e-5)
+    np.testing.assert_allclose(Cq.imag, g["C_im"], atol=2e-5)
+    mel = cp.cqt_logmag(y, SR)
+    assert mel.shape == (1, 288, 16) and mel.dtype == np.float64
+    np.testing.assert_allclose(mel[0], g["logmag"], atol=2e-5)
