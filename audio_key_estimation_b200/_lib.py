@@ -31,6 +31,8 @@ _SIGNATURES = {
     "ake_abi_version": (C.c_int, []),
     "ake_last_error": (C.c_char_p, []),
     "ake_launch_count": (C.c_int64, [C.c_int]),
+    "ake_profile_enable": (C.c_int, [C.c_int]),
+    "ake_profile_collect": (C.c_int, [_P, C.c_int, _P, _P, C.c_int]),
     "ake_pcn_create": (C.c_int, [C.POINTER(PcnConfig), C.POINTER(_P)]),
     "ake_pcn_destroy": (None, [_P]),
     "ake_pcn_num_tensors": (C.c_int, [_P]),
@@ -87,6 +89,22 @@ def lib() -> C.CDLL:
                 raise RuntimeError("libake_b200.so ABI version mismatch")
             _lib = handle
     return _lib
+
+
+def profile_enable(on: bool) -> None:
+    check(lib().ake_profile_enable(int(on)))
+
+
+def profile_collect() -> dict:
+    """{tag: (milliseconds, kernel launches)} accumulated since the last collect (synchronises)."""
+    cap, stride = 64, 48
+    tags = C.create_string_buffer(cap * stride)
+    ms = (C.c_double * cap)()
+    launches = (C.c_int64 * cap)()
+    n = lib().ake_profile_collect(tags, stride, ms, launches, cap)
+    if n < 0:
+        check(n)
+    return {tags.raw[i * stride:(i + 1) * stride].split(b"\0", 1)[0].decode(): (ms[i], int(launches[i])) for i in range(n)}
 
 
 class AkeError(RuntimeError):

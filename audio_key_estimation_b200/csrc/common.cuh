@@ -77,6 +77,25 @@ struct Arena {
   }
 };
 
+// ---- optional per-section device timing (ake_profile_enable / ake_profile_collect) -----------
+// When enabled, a ProfScope records a CUDA event pair on the launch stream around the kernels of one
+// tagged section; the events are resolved and summed per tag by ake_profile_collect().  Disabled (the
+// default) it costs one relaxed atomic load.
+bool profile_enabled();
+void profile_record(const char* tag, cudaStream_t st, bool begin, int n_launches);
+struct ProfScope {
+  const char* tag;
+  cudaStream_t st;
+  bool on;
+  int64_t launches0;
+  ProfScope(const char* t, cudaStream_t s) : tag(t), st(s), on(profile_enabled()), launches0(launch_counter()) {
+    if (on) profile_record(tag, st, true, 0);
+  }
+  ~ProfScope() {
+    if (on) profile_record(tag, st, false, (int)(launch_counter() - launches0));
+  }
+};
+
 constexpr float kLeakySlope = 0.01f;  // nn.LeakyReLU() default (models.py:197,234,315)
 constexpr float kBnEps = 1e-5f;       // nn.BatchNorm2d default
 

@@ -269,9 +269,9 @@ __global__ void cqt_bank_kernel(const float* __restrict__ sig, long long sig_str
   __shared__ int s_T[kBankRows];            // 1: real frame, 0: batch padding (t >= frames of the clip), -1: no row
   const int tid = threadIdx.x;
   const long long m0 = (long long)blockIdx.x * kBankRows;
-  if (tid < kBankRows) {
-    const long long m = m0 + tid;
-    s_T[tid] = -1, s_base[tid] = 0, s_first[tid] = 0, s_len[tid] = 0;
+  for (int row = tid; row < kBankRows; row += blockDim.x) {
+    const long long m = m0 + row;
+    s_T[row] = -1, s_base[row] = 0, s_first[row] = 0, s_len[row] = 0;
     if (m < (long long)B * T_max) {
       const int b = m / T_max, t = m % T_max;
       const long long n0 = lengths ? lengths[b] : n_uniform;
@@ -280,10 +280,10 @@ __global__ void cqt_bank_kernel(const float* __restrict__ sig, long long sig_str
         const long long ti = 1 + ((n0 + (1LL << i) - 1) >> i) / (hop0 >> i);
         T = (T < 0 || ti < T) ? ti : T;
       }
-      s_T[tid] = t < T ? 1 : 0;
-      s_base[tid] = b * sig_stride;
-      s_first[tid] = (long long)t * hop_i - n_fft / 2;
-      s_len[tid] = (n0 + (1LL << octave) - 1) >> octave;
+      s_T[row] = t < T ? 1 : 0;
+      s_base[row] = b * sig_stride;
+      s_first[row] = (long long)t * hop_i - n_fft / 2;
+      s_len[row] = (n0 + (1LL << octave) - 1) >> octave;
     }
   }
   __syncthreads();
@@ -393,6 +393,7 @@ static void run_cqt(ake_cqt* p, const float* audio, long long stride, const int6
   w.level[0] = const_cast<float*>(audio);
   w.stride[0] = stride;
   for (int i = 1; i < p->n_oct; ++i) {
+    ProfScope prof("cqt.decimate", st);
     const long long n_out = len_at(n_max, i);
     dim3 grid((unsigned)cdiv64(n_out, kDecOutPerBlock), B);
     decimate2_kernel<<<grid, kDecThreads, 0, st>>>(w.level[i - 1], w.stride[i - 1], w.level[i], w.stride[i], d_len, n_max, i);
@@ -400,6 +401,7 @@ static void run_cqt(ake_cqt* p, const float* audio, long long stride, const int6
   }
   const long long rows = (long long)B * T_max;
   for (int i = 0; i < p->n_oct; ++i) {
+    ProfScope prof("cqt.bank", st);
     if (2 * p->bpo == 72) {
       cqt_bank_kernel<72><<<(unsigned)cdiv64(rows, kBankRows), 4 * 18, 0, st>>>(
           w.level[i], w.stride[i], d_len, n_max, i, p->hop >> i, p->n_fft, p->d_bank, p->d_scale, B, T_max, p->n_oct, p->hop,
@@ -479,6 +481,7 @@ int ake_cqt_run_f32(ake_cqt* p, const float* audio_dev, int64_t stride, const in
     if (!p || !audio_dev || !out_dev || !ws_dev) fail(AKE_ERR_INVALID, "null argument");
     if (B <= 0 || n_max <= 0 || stride < n_max || T_max <= 0) fail(AKE_ERR_INVALID, "bad sizes");
     if (mode != AKE_CQT_LOGMAG && mode != AKE_CQT_COMPLEX) fail(AKE_ERR_INVALID, "bad mode");
+    ProfScope prof("cqt.total", static_cast<cudaStream_t>(stream));
     run_cqt(p, audio_dev, stride, lengths_host, B, n_max, mode, out_dev, T_max, seq_len_out_dev, ws_dev, ws_bytes,
             static_cast<cudaStream_t>(stream));
   });

@@ -8,7 +8,9 @@
 #include <cmath>
 #include <algorithm>
 #include <cstring>
+#include <atomic>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -20,6 +22,52 @@ thread_local std::string g_last_error;
 thread_local int64_t g_launches = 0;
 void set_last_error(const std::string& msg) { g_last_error = msg; }
 int64_t& launch_counter() { return g_launches; }
+
+// ---- section profiler ---------------------------------------------------------------------------
+namespace {
+struct ProfEntry {
+  std::string tag;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int launches = 0;
+};
+std::atomic<bool> g_prof_on{false};
+std::mutex g_prof_mu;
+std::vector<ProfEntry> g_prof_entries;
+std::vector<cudaEvent_t> g_prof_pool;
+thread_local std::vector<size_t> g_prof_open;  // indices of sections opened by this thread
+
+cudaEvent_t prof_event() {
+  if (!g_prof_pool.empty()) {
+    cudaEvent_t e = g_prof_pool.back();
+    g_prof_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+  return e;
+}
+}  // namespace
+
+bool profile_enabled() { return g_prof_on.load(std::memory_order_relaxed); }
+
+void profile_record(const char* tag, cudaStream_t st, bool begin, int n_launches) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (begin) {
+    ProfEntry e;
+    e.tag = tag;
+    e.ev0 = prof_event(), e.ev1 = prof_event();
+    if (e.ev0) cudaEventRecord(e.ev0, st);
+    g_prof_entries.push_back(e);
+    g_prof_open.push_back(g_prof_entries.size() - 1);
+  } else if (!g_prof_open.empty()) {
+    const size_t i = g_prof_open.back();
+    g_prof_open.pop_back();
+    if (i < g_prof_entries.size()) {
+      if (g_prof_entries[i].ev1) cudaEventRecord(g_prof_entries[i].ev1, st);
+      g_prof_entries[i].launches = n_launches;
+    }
+  }
+}
 
 struct TensorInfo {
   std::string name;
@@ -307,6 +355,7 @@ struct Fwd {
     const bool has_bn = c.bn >= 0;
     const bool raw = train && has_bn;
     if (dry) return;
+    ProfScope prof(g.KH == 7 ? "pcn.p2p" : (g.SR == 3 ? "pcn.semitone" : (g.rows_v == 12 && g.row_circ ? "pcn.equiv" : "pcn.genre")), st);
     ConvArgs a{};
     a.in0 = in0.p, a.c0 = in0.C, a.rows0 = in0.R, a.bs0 = in0.bstride();
     if (in1) a.in1 = in1->p, a.c1 = in1->C, a.rows1 = in1->R, a.bs1 = in1->bstride();
@@ -547,6 +596,52 @@ int64_t ake_launch_count(int reset) {
   return v;
 }
 
+int ake_profile_enable(int on) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof_on.store(on != 0);
+  if (!on) {
+    for (auto& e : g_prof_entries) {
+      if (e.ev0) g_prof_pool.push_back(e.ev0);
+      if (e.ev1) g_prof_pool.push_back(e.ev1);
+    }
+    g_prof_entries.clear();
+  }
+  return AKE_OK;
+}
+
+int ake_profile_collect(char* tags_out, int tag_stride, double* ms_out, int64_t* launches_out, int cap) {
+  int n_tags = 0;
+  int rc = guarded([&] {
+    if (!tags_out || !ms_out || !launches_out || tag_stride < 8 || cap <= 0) fail(AKE_ERR_INVALID, "bad arguments");
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    std::vector<std::string> tags;
+    std::vector<double> ms;
+    std::vector<int64_t> launches;
+    for (auto& e : g_prof_entries) {
+      float t = 0.f;
+      if (e.ev0 && e.ev1) {
+        AKE_CUDA(cudaEventSynchronize(e.ev1));
+        AKE_CUDA(cudaEventElapsedTime(&t, e.ev0, e.ev1));
+      }
+      size_t k = 0;
+      for (; k < tags.size(); ++k)
+        if (tags[k] == e.tag) break;
+      if (k == tags.size()) tags.push_back(e.tag), ms.push_back(0.0), launches.push_back(0);
+      ms[k] += t, launches[k] += e.launches;
+      if (e.ev0) g_prof_pool.push_back(e.ev0);
+      if (e.ev1) g_prof_pool.push_back(e.ev1);
+    }
+    g_prof_entries.clear();
+    if ((int)tags.size() > cap) fail(AKE_ERR_INVALID, "need room for %zu tags", tags.size());
+    for (size_t k = 0; k < tags.size(); ++k) {
+      snprintf(tags_out + k * tag_stride, tag_stride, "%s", tags[k].c_str());
+      ms_out[k] = ms[k], launches_out[k] = launches[k];
+    }
+    n_tags = (int)tags.size();
+  });
+  return rc == AKE_OK ? n_tags : rc;
+}
+
 int ake_pcn_create(const ake_pcn_config* cfg, ake_pcn** out) {
   return guarded([&] {
     if (!cfg || !out) fail(AKE_ERR_INVALID, "null argument");
@@ -616,6 +711,7 @@ int ake_pcn_forward_f32(ake_pcn* p, const float* mel_dev, int B, int T, const in
     if (p->cfg.genre && !genre_out_dev) fail(AKE_ERR_INVALID, "genre head enabled but genre_out_dev is NULL");
     if (B <= 0 || T <= 0) fail(AKE_ERR_INVALID, "B and T must be positive (got %d, %d)", B, T);
     if (!p->has_params) fail(AKE_ERR_INVALID, "ake_pcn_set_params_f32 has not been called");
+    ProfScope prof("pcn.total", static_cast<cudaStream_t>(stream));
     Fwd f(p, B, T, bn_mode != 0, ws_dev, ws_bytes, static_cast<cudaStream_t>(stream));
     f.seq_len = seq_len_dev, f.bn_stats_out = bn_stats_out_dev;
     f.run(mel_dev, key_out_dev, tonic_out_dev, p->cfg.genre ? genre_out_dev : nullptr);

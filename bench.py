@@ -1,0 +1,355 @@
+"""bench.py -- clips/s of the CQT + PitchClassNet forward hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (CUDA path through the C ABI)
+    python bench.py --impl reference --gpus N --steps K ...  # the CPU oracle port on the host cores
+
+A step = one pass of the hot path (CQT -> PitchClassNet forward -> argmax decode) over one batch
+of synthetic clips per GPU.  Workload (BASELINE.json configs[1]): 256 mono fp32 clips per GPU,
+48 kHz x 30 s (1,440,000 samples, hop 9600 -> 151 frames, 288 bins), PitchClassNet at the
+train_model.py defaults (+ genre head), seeded weights with randomised BatchNorm statistics
+(tests/golden/weights_seed0.npz).  `value`: inputs resident in HBM; `e2e`: pinned HOST audio in,
+host predictions out through ake_estimate_host_f32 (H2D + D2H inside the timed region).
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+SR, SECONDS_STD, FRAMES, OCTAVES = 48000, 30, 5, 8
+METRIC = "clips/s CQT+PitchClassNet fwd"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="clips per GPU per step")
+    ap.add_argument("--seconds", type=float, default=SECONDS_STD, help="clip duration")
+    ap.add_argument("--no-genre", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            d = json.load(fh)
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+def golden_weights(genre: bool):
+    import numpy as np
+    import torch
+    w = np.load(os.path.join(ROOT, "tests", "golden", "weights_seed0.npz"))
+    return {k: torch.from_numpy(w[k]) for k in w.files if genre or not k.startswith("genre_classifier.")}
+
+
+# ------------------------------------------------------------------------------------ clock sampling
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons while the timed region runs (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.th.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])), mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------ CPU oracle arm
+def cpu_oracle_step(clips, sd64, genre, pool):
+    """One reference-side step on the host: oracle CQT per clip (thread pool, as KeyDataset.py:127 preloads)
+    then the float64 forward (the reference's dtype, train_model.py:105) + argmax decode."""
+    import numpy as np
+    import torch
+    from oracle import cqt_port, pcn_port
+    mels = list(pool.map(lambda c: cqt_port.cqt_logmag(c, SR, FRAMES, OCTAVES, dtype=np.float32), clips))
+    T = max(m.shape[-1] for m in mels)
+    x = torch.from_numpy(np.stack([np.pad(m, ((0, 0), (0, 0), (0, T - m.shape[-1]))) for m in mels]))
+    with torch.no_grad():
+        out = pcn_port.pcn_forward(sd64, x, torch.tensor([m.shape[-1] for m in mels]))
+        ids = pcn_port.decode(*out)
+    return out, ids
+
+
+def time_cpu_oracle(n_clips, n_samples, steps, warmup, genre):
+    import concurrent.futures as cf
+    import torch
+    from audio_key_estimation_b200 import synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd64 = {k: v.double() for k, v in golden_weights(genre).items() if v.is_floating_point()}
+    clips = [synth.synth_clip(i, n_samples, SR).numpy() for i in range(n_clips)]
+    with cf.ThreadPoolExecutor(max_workers=cores) as pool:
+        for _ in range(warmup):
+            cpu_oracle_step(clips, sd64, genre, pool)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            cpu_oracle_step(clips, sd64, genre, pool)
+        dt = time.perf_counter() - t0
+    return n_clips * steps / dt, dt / steps, cores
+
+
+def run_reference(args):
+    """--impl reference: the CPU implementation of the path on the host cores.  The reference is pure Python
+    (models.py + librosa) and cannot travel to the GPU box, so this times the oracle port (kind "port")."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_samples = int(round(args.seconds * SR))
+    genre = not args.no_genre
+    # calibrate: size the per-step sample so the whole run stays within ~150 s
+    t0 = time.perf_counter()
+    time_cpu_oracle(1, n_samples, 1, 0, genre)
+    t_clip = time.perf_counter() - t0
+    cores = os.cpu_count() or 1
+    budget = 150.0 / max(1, args.steps + args.warmup)
+    n_clips = int(max(1, min(args.batch, 8, budget / max(t_clip / min(cores, 8), 1e-3))))
+    value, step_s, cores = time_cpu_oracle(n_clips, n_samples, args.steps, args.warmup, genre)
+    sample = f"{n_clips} clips/step of the b200 arm's workload ({args.seconds:g} s @ {SR} Hz), oracle CQT (numpy fp32, thread pool) + float64 forward (torch CPU)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, genre),
+        "cpu_baseline": {"value": value, "unit": "clips/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, genre):
+    n_samples = int(round(args.seconds * SR))
+    return {"workload": f"configs[1]: {args.batch} synthetic mono clips per GPU, {args.seconds:g} s @ {SR} Hz "
+                        f"({n_samples} samples, hop {SR // FRAMES}, {1 + n_samples // (SR // FRAMES)} frames x {36 * OCTAVES} bins), "
+                        f"CQT + PitchClassNet(288,12,2,7) train_model.py defaults{' + genre head' if genre else ''} + decode, eval-mode BN",
+            "clips_per_gpu": args.batch, "global_batch": args.batch * args.gpus, "clip_seconds": args.seconds, "sr": SR,
+            "l2_policy": "inputs larger than L2 (audio batch >> 126 MB), no flush", "parallelism": f"dp{args.gpus} (batch sharded, logit all-gather)"}
+
+
+# ------------------------------------------------------------------------------------ B200 arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    import audio_key_estimation_b200 as ake
+    from audio_key_estimation_b200 import _lib, distributed as akd, synth
+    from oracle import pcn_port  # MAC counting only (bench bookkeeping), never on the timed path
+
+    rank, local, world = akd.init_from_env("nccl")
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torchrun for --gpus > 1 (python -m torch.distributed.run --nproc-per-node N bench.py ...)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    genre = not args.no_genre
+    peaks = load_peaks()
+    B, n_samples = args.batch, int(round(args.seconds * SR))
+
+    net = ake.PitchClassNet(36 * OCTAVES, 12, 2, 7, opt=ake.default_opt(genre=genre))
+    sd = golden_weights(genre)
+    net.load_state_dict(sd, strict=True)
+    net = net.to(dev).eval()
+    est = ake.KeyEstimator(net, SR, FRAMES)
+    T = est.frames(n_samples)
+
+    lo, _ = akd.shard_range(B * world, rank, world)
+    audio = torch.empty((B, n_samples), dtype=torch.float32, device=dev)
+    synth.synth_batch(lo, B, n_samples, SR, device=dev, out=audio)
+    torch.cuda.synchronize()
+
+    def device_step():
+        out = est.estimate_device(audio)
+        ids = ake.decode(*out)
+        rows = akd.pack_rows(out[0], out[1], out[2] if genre else None)
+        table = akd.gather_rows(rows, B * world) if world > 1 else rows
+        return table, ids
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    # ---- device-resident throughput ("value")
+    for _ in range(max(args.warmup, 3)):
+        device_step()
+    barrier()
+    lib = _lib.lib()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    _lib.profile_enable(True)
+    lib.ake_launch_count(1)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        table, ids = device_step()
+    ev1.record()
+    barrier()
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+    launches = int(lib.ake_launch_count(1))
+    prof = _lib.profile_collect()
+    _lib.profile_enable(False)
+    clocks = sampler.stop() if rank == 0 else None
+    value = B * world * args.steps / (ms_total * 1e-3)
+
+    # ---- end to end through the C ABI with host buffers ("e2e")
+    e2e = None
+    if not args.no_e2e:
+        host_audio = torch.empty((B, n_samples), dtype=torch.float32).pin_memory()
+        host_audio.copy_(audio)
+        out_bufs = None
+        for _ in range(2):
+            out_bufs = est.estimate_host(host_audio, out=out_bufs)
+        barrier()
+        t0 = time.perf_counter()
+        ev0.record()
+        for _ in range(args.steps):
+            out_bufs = est.estimate_host(host_audio, out=out_bufs)
+            if world > 1:
+                rows = akd.pack_rows(out_bufs["key"], out_bufs["tonic"], out_bufs["genre"]).to(dev)
+                akd.gather_rows(rows, B * world)
+        ev1.record()
+        torch.cuda.synchronize()
+        wall_ms = (time.perf_counter() - t0) * 1e3  # estimate_host ends with a stream sync: wall ~ device time
+        ms_e2e = max_over_ranks(max(ev0.elapsed_time(ev1), wall_ms))
+        d2h = sum(v.numel() * v.element_size() for v in out_bufs.values() if v is not None)
+        e2e = {"value": B * world * args.steps / (ms_e2e * 1e-3), "unit": "clips/s",
+               "h2d_bytes_per_step": int(host_audio.numel() * 4), "d2h_bytes_per_step": int(d2h),
+               "ms_per_step": ms_e2e / args.steps, "api": "KeyEstimator.estimate_host -> ake_estimate_host_f32 (pinned host audio)"}
+        # parity guard: host-buffer path == device-resident path
+        for j, dev_ids in enumerate(ids):
+            if not torch.equal(out_bufs["ids"][j].to(dev), dev_ids):
+                raise SystemExit("e2e ids differ from the device-resident path")
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline bookkeeping (algorithmic work per step per GPU)
+    sd_f = {k: v for k, v in sd.items() if v.is_floating_point()}
+    macs_clip = pcn_port.count_macs(sd_f, 36 * OCTAVES, T)
+    p2p_macs_clip = 288 * T * 8 * (5 + 8 + 8) * 49
+    cqt_bytes_clip = 4 * n_samples + 4 * 288 * T
+    steps = args.steps
+
+    def sec(tag):
+        ms, n = prof.get(tag, (0.0, 0))
+        return ms / steps, n // steps if steps else 0
+
+    p2p_ms, p2p_n = sec("pcn.p2p")
+    pcn_ms, _ = sec("pcn.total")
+    cqt_ms, _ = sec("cqt.total")
+    dec_ms, dec_n = sec("cqt.decimate")
+    bank_ms, bank_n = sec("cqt.bank")
+    p2p_tflops = 2.0 * p2p_macs_clip * B / (p2p_ms * 1e-3) / 1e12 if p2p_ms else None
+    roofline = {
+        "kernel": "pcn.p2p: 3 x Conv2d 7x7 circular (pitch,time) + BN + LeakyReLU (64.6% of the forward's MACs)",
+        "bound": "tensor", "achieved": p2p_tflops, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+        "frac": (p2p_tflops / peaks["bf16_tflops_sustained"]) if p2p_tflops else None, "traffic": None,
+        "peak_source": f"{peaks['source']} bf16 dense, sustained (kernel timed inside a long step)",
+        "launches_per_step": p2p_n, "ms_per_step": p2p_ms,
+        "algorithmic_flops_per_step": 2.0 * p2p_macs_clip * B,
+    }
+    stages = {
+        "cqt": {"ms_per_step": cqt_ms, "bound": "hbm", "algorithmic_bytes_per_clip": cqt_bytes_clip,
+                "achieved_gbs": (cqt_bytes_clip * B / (cqt_ms * 1e-3) / 1e9) if cqt_ms else None, "peak_gbs": peaks["hbm_gbs"],
+                "frac": (cqt_bytes_clip * B / (cqt_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]) if cqt_ms else None,
+                "decimate_ms": dec_ms, "bank_ms": bank_ms},
+        "pcn": {"ms_per_step": pcn_ms, "bound": "tensor", "algorithmic_macs_per_clip": macs_clip,
+                "achieved_tflops": (2.0 * macs_clip * B / (pcn_ms * 1e-3) / 1e12) if pcn_ms else None,
+                "peak_tflops": peaks["bf16_tflops_sustained"],
+                "frac": (2.0 * macs_clip * B / (pcn_ms * 1e-3) / 1e12 / peaks["bf16_tflops_sustained"]) if pcn_ms else None,
+                "sections_ms": {k: v[0] / steps for k, v in prof.items() if k.startswith("pcn.") and k != "pcn.total"}},
+    }
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        n_cpu = 4
+        cv, cstep, cores = time_cpu_oracle(n_cpu, n_samples, 2, 1, genre)
+        cpu_baseline = {"value": cv, "unit": "clips/s", "cores": cores, "kind": "port",
+                        "sample": f"{n_cpu} clips x 2 steps of the same workload: oracle CQT (numpy fp32, thread pool) + float64 forward (torch CPU, {cores} threads)"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": workload_config(args, genre),
+        "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "stages": stages,
+        "cpu_baseline": cpu_baseline,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -47,6 +47,14 @@ const char* ake_last_error(void);
 /* Number of kernels this library launched from the calling thread since the last reset. */
 int64_t ake_launch_count(int reset);
 
+/* Optional device timing of the library's kernel sections (used by bench.py for the roofline line).
+ * While enabled, each section ("cqt.decimate", "cqt.bank", "pcn.p2p", "pcn.equiv", "pcn.semitone", ...)
+ * records a CUDA event pair on its launch stream.  ake_profile_collect synchronises on those events, sums
+ * milliseconds and kernel launches per tag into the caller's arrays (tags_out: cap strings of tag_stride
+ * bytes), clears the log and returns the number of tags (negative error). */
+int ake_profile_enable(int on);
+int ake_profile_collect(char* tags_out, int tag_stride, double* ms_out, int64_t* launches_out, int cap);
+
 /* ---------------------------------------------------------------- PitchClassNet */
 
 /* Mirrors the fields PitchClassNet.__init__/forward read from `opt`

@@ -1,0 +1,85 @@
+"""GPU parity of the constant-Q front-end (through the C ABI) against oracle.cqt_port.
+CQT parity is UNPINNED (librosa is not available; see oracle/cqt_port.py): the yardstick is this
+repo's float64 restatement.  Tolerance: |C| error <= 2e-4 of max |C| (fp32 arithmetic through a
+7-deep decimator cascade), log-magnitude max-abs <= 5e-4."""
+import numpy as np
+import pytest
+import torch
+
+import audio_key_estimation_b200 as ake
+from audio_key_estimation_b200 import synth
+from conftest import load_golden
+from oracle import cqt_port as cp
+
+pytestmark = pytest.mark.gpu
+SR, HOP = 48000, 9600
+
+
+def test_complex_cqt_matches_oracle():
+    y = synth.synth_clip(3, SR * 5 + 123, SR)
+    want = cp.cqt(y.numpy(), SR, HOP, None, 288, 36)
+    got = ake.cqt(y.cuda(), sr=SR, hop_length=HOP, n_bins=288, bins_per_octave=36)
+    assert got.dtype == torch.complex64 and tuple(got.shape) == want.shape
+    err = np.abs(got.cpu().numpy() - want).max()
+    assert err <= 2e-4 * np.abs(want).max(), err
+
+
+def test_fixture_and_logmag():
+    g = load_golden("cqt_port.npz")
+    y = synth.synth_clip(int(g["clip_id"]), int(g["n_samples"]), SR)
+    mel, seq = ake.cqt_logmag(y[None].cuda(), SR)
+    assert tuple(mel.shape) == (1, 1, 288, 16) and seq.tolist() == [16]
+    assert np.abs(mel[0, 0].cpu().numpy() - g["logmag"]).max() <= 5e-4
+
+
+def test_ragged_batch_padding_and_seq_length():
+    """KeyDataset.py:242-254: clips are zero-padded in time to the longest one; seq_length keeps the true frames."""
+    lens = [SR * 4, SR * 3 + 4801, 9599, SR * 4 - 1]
+    clips = [synth.synth_clip(20 + i, n, SR) for i, n in enumerate(lens)]
+    mel, seq = ake.cqt_logmag([c.cuda() for c in clips], SR)
+    T = [cp.n_frames(n, HOP, 8) for n in lens]
+    assert seq.tolist() == T and mel.shape[-1] == max(T)
+    for i, c in enumerate(clips):
+        want = cp.cqt_logmag(c.numpy(), SR)[0]
+        got = mel[i, 0].cpu().numpy()
+        assert np.abs(got[:, : T[i]] - want).max() <= 5e-4
+        assert not got[:, T[i]:].any()
+
+
+def test_pure_tone_and_linearity_on_device():
+    n = SR * 4
+    t = torch.arange(n, dtype=torch.float64) / SR
+    f0 = cp.C1_HZ * 2 ** (150 / 36)
+    a = (0.3 * torch.sin(2 * np.pi * f0 * t)).float().cuda()
+    Ca = ake.cqt(a, sr=SR, hop_length=HOP, n_bins=288, bins_per_octave=36)
+    col = Ca[:, 10].abs()
+    assert int(col.argmax()) == 150
+    expect = 0.5 * 0.3 * np.sqrt(cp.constant_q_lengths(SR, cp.C1_HZ, 288, 36)[150])
+    assert abs(float(col.max()) / expect - 1) < 2e-3
+    b = synth.synth_clip(1, n, SR).cuda()
+    Cb = ake.cqt(b, sr=SR, hop_length=HOP, n_bins=288, bins_per_octave=36)
+    Cab = ake.cqt(0.5 * a - 0.25 * b, sr=SR, hop_length=HOP, n_bins=288, bins_per_octave=36)
+    assert (Cab - (0.5 * Ca - 0.25 * Cb)).abs().max() <= 2e-4 * Cb.abs().max()
+
+
+def test_full_size_properties():
+    """BASELINE config sizes (30 s clips): frame count, batch independence, determinism."""
+    n = SR * 30
+    batch = synth.synth_batch(0, 4, n, SR).cuda()
+    mel, seq = ake.cqt_logmag(batch, SR)
+    assert tuple(mel.shape) == (4, 1, 288, 151) and seq.tolist() == [151] * 4
+    mel2, _ = ake.cqt_logmag(batch, SR)
+    assert torch.equal(mel, mel2)
+    single, _ = ake.cqt_logmag(batch[2:3].clone(), SR)
+    assert torch.equal(single[0], mel[2])
+    want = cp.cqt_logmag(batch[1].cpu().numpy(), SR)[0]
+    assert np.abs(mel[1, 0].cpu().numpy() - want).max() <= 5e-4
+
+
+def test_other_bank_shapes_and_errors():
+    y = synth.synth_clip(9, 22050 * 3, 22050).cuda()
+    got = ake.cqt(y, sr=22050, hop_length=512, n_bins=84, bins_per_octave=12)   # librosa's own defaults
+    want = cp.cqt(y.cpu().numpy(), 22050, 512, None, 84, 12)
+    assert np.abs(got.cpu().numpy() - want).max() <= 2e-4 * np.abs(want).max()
+    with pytest.raises(ValueError):
+        ake.cqt(y, sr=44100, hop_length=8820, n_bins=288, bins_per_octave=36)

@@ -1,0 +1,177 @@
+"""GPU parity of the PitchClassNet forward (through the C ABI) against the reference goldens and
+the pinned oracle port.  Tolerance (north_star): logits max-abs <= 1e-3 relative to max |logit|;
+the fp32 kernels are held to 2e-5 here."""
+import numpy as np
+import pytest
+import torch
+
+import audio_key_estimation_b200 as ake
+from audio_key_estimation_b200 import _lib, synth
+from conftest import float_state_dict, golden_state_dict
+from oracle import pcn_port
+
+pytestmark = pytest.mark.gpu
+REL_TOL = 2e-5   # measured fp32-vs-fp64 noise of the reference itself is ~1e-6
+
+
+def _net(genre=False, pitches=288, train=False, **opt):
+    net = ake.PitchClassNet(pitches, 12, opt.get("num_layers", 2), 7, opt=ake.default_opt(genre=genre, **opt))
+    return net
+
+
+def _golden_net(genre, pitches=288):
+    net = _net(genre, pitches)
+    net.load_state_dict(golden_state_dict(genre), strict=True)
+    return net.cuda().eval()
+
+
+def _close(got, want, tol=REL_TOL):
+    want = np.asarray(want, dtype=np.float64)
+    got = got.detach().double().cpu().numpy()
+    assert got.shape == want.shape
+    err = np.abs(got - want).max()
+    assert err <= tol * max(1.0, np.abs(want).max()), f"max-abs error {err:.3e}"
+
+
+@pytest.mark.parametrize("tag", ["default", "genre"])
+def test_forward_matches_reference_golden(fwd_golden, tag):
+    g = fwd_golden
+    net = _golden_net(tag == "genre")
+    launches0 = _lib.lib().ake_launch_count(1)
+    x = torch.from_numpy(g["mel"])[:, None].cuda()
+    seq = torch.from_numpy(g["seq_length"]).cuda()
+    for stag, sl in (("seq", seq), ("noseq", None)):
+        res = net(x, sl)
+        assert len(res) == (3 if tag == "genre" else 2)
+        for name, r in zip(("key", "tonic", "genre"), res):
+            assert r.dtype == torch.float32 and r.is_cuda
+            _close(r, g[f"{tag}.eval.{stag}.{name}"])
+    assert _lib.lib().ake_launch_count(0) > 10   # the CUDA path ran (no fallback exists)
+    _close(net.tap("pc_final").reshape(g[f"{tag}.eval.pc_final"].shape), g[f"{tag}.eval.pc_final"], 5e-5)
+    # float64 in -> float64 out (train_model.py:105 runs the model in double)
+    res = net.double()(x.double(), seq)
+    assert all(r.dtype == torch.float64 for r in res)
+    _close(res[1], g[f"{tag}.eval.seq.tonic"])
+    # seq_length on the host, int64, shape (B,1): same result
+    res = net(x.double(), torch.from_numpy(g["seq_length"]).reshape(-1, 1))
+    _close(res[0], g[f"{tag}.eval.seq.key"])
+
+
+def test_max_pool_quirk(fwd_golden):
+    g = fwd_golden
+    net = _net(True, max_pool=True)
+    net.load_state_dict(golden_state_dict(True))
+    net = net.cuda().eval()
+    res = net(torch.from_numpy(g["mel"])[:, None].cuda(), torch.from_numpy(g["seq_length"]).cuda())
+    for name, r in zip(("key", "tonic", "genre"), res):
+        _close(r, g[f"genre.eval.seq_maxpool.{name}"])
+
+
+def test_train_mode_batch_statistics(fwd_golden):
+    g = fwd_golden
+    net = _net(True)
+    net.load_state_dict(golden_state_dict(True))
+    net = net.cuda().train()
+    res = net(torch.from_numpy(g["mel"])[:, None].cuda(), torch.from_numpy(g["seq_length"]).cuda())
+    for name, r in zip(("key", "tonic", "genre"), res):
+        _close(r, g[f"genre.train.seq.{name}"], 1e-4)
+    sd = net.state_dict()
+    for k in g.files:
+        if k.startswith("genre.train.buf."):
+            _close(sd[k[len("genre.train.buf."):]], g[k], 1e-4)
+    assert int(sd["model.1.p2p.layer.7.num_batches_tracked"]) == 1
+
+
+@pytest.mark.parametrize("cfg,B,T", [
+    (dict(), 5, 151), (dict(genre=True), 2, 1201), (dict(), 1, 26), (dict(genre=True), 3, 33),
+    (dict(num_layers=1), 2, 40), (dict(num_layers=3, n_filters=2), 2, 64), (dict(conv_layers=2, head_layers=3), 2, 80),
+    (dict(n_filters=8), 1, 48)])
+def test_layer_by_layer_against_oracle(cfg, B, T):
+    """Every tapped intermediate + outputs vs oracle.pcn_port (float64) on random features, ragged lengths."""
+    torch.manual_seed(7)
+    genre = cfg.get("genre", False)
+    net = _net(**cfg)
+    sd = synth.randomise_state_dict(net.state_dict(), seed=11)
+    net.load_state_dict(sd)
+    net = net.cuda().eval()
+    x = (torch.rand(B, 1, 288, T) * 3.5)
+    seq = torch.randint(max(T - 20, T // 2 * 2 - 1), T + 1, (B,))
+    seq[0] = T
+    got = net(x.cuda(), seq.cuda())
+    sd64 = {k: v.double() for k, v in float_state_dict(sd).items()}
+    taps = {}
+    want = pcn_port.pcn_forward(sd64, x.double(), seq, taps=taps)
+    checked = 0
+    for name, ref in taps.items():
+        try:
+            t = net.tap(name)
+        except ValueError:
+            continue
+        _close(t.reshape(ref.shape), ref.numpy(), 5e-5)
+        checked += 1
+    assert checked >= 4
+    for r, w in zip(got, want):
+        _close(r, w.numpy())
+    assert len(got) == len(want) == (3 if genre else 2)
+
+
+def test_seq_length_edge_cases():
+    net = _golden_net(False)
+    x = torch.rand(2, 1, 288, 40).cuda()
+    # shortest valid clip: floor(26/2) - 12 = 1 frame
+    k, t = net(x[:, :, :, :26], None)
+    assert torch.isfinite(k).all() and torch.isfinite(t).all()
+    with pytest.raises(ValueError):
+        net(x[:, :, :, :24], None)            # heads have no valid frame
+    with pytest.raises(ValueError):
+        net(x, torch.tensor([40, 40, 40]))    # wrong number of lengths
+    # a clip whose masked length is 0 averages an empty slice -> nan, exactly as torch.mean does in the reference
+    k, t = net(x, torch.tensor([40, 24]).cuda())
+    assert torch.isfinite(k[0]).all() and torch.isnan(t[1]).all()
+
+
+@pytest.mark.parametrize("inp", ["pattern", "padded_cqt"])
+def test_equivariance_config3(eq_golden, inp):
+    """equivariance_test.py:172-205: shift the CQT by 3*s bins, expect outputs rolled by s.
+    Eval mode: bit-exact roll (as the reference, see test_oracle_pcn); train mode: <= 1e-6."""
+    if inp == "pattern":
+        pat = synth.custom_cqt_pattern(360, 592, with_border=False).float()
+    else:
+        m = torch.from_numpy(eq_golden["padded_cqt.input288"])
+        pad = torch.zeros(36, m.shape[1])
+        pat = torch.cat([pad, m, pad])
+    net = _golden_net(False, pitches=360)
+    shifts = [int(s) for s in eq_golden["shifts"]]
+    for mode in ("eval", "train"):
+        net.train(mode == "train")
+        keys, tonics = [], []
+        for s in shifts:
+            m = torch.zeros_like(pat)
+            if s >= 0:
+                m[3 * s:] = pat[: 360 - 3 * s]
+            else:
+                m[: 360 + 3 * s] = pat[-3 * s:]
+            k, t = net(m.reshape(1, 1, 360, -1).cuda(), torch.tensor(m.shape[1]).reshape(1, 1).cuda())
+            keys.append(k[0].cpu()), tonics.append(t[0].cpu())
+        for rows, head in ((keys, "key"), (tonics, "tonic")):
+            want = eq_golden[f"{inp}.{mode}.{head}"]
+            for i, s in enumerate(shifts):
+                if mode == "eval":
+                    assert torch.equal(rows[i], torch.roll(rows[0], s)), (head, s)
+                else:
+                    assert (rows[i] - torch.roll(rows[0], s)).abs().max() <= 1e-6, (head, s)
+                _close(rows[i], want[i], 1e-4 if mode == "train" else REL_TOL)
+
+
+def test_decode_matches_oracle():
+    torch.manual_seed(3)
+    key, tonic, genre = torch.rand(257, 12), torch.randn(257, 12), torch.randn(257, 11)
+    ids = ake.decode(key.cuda(), tonic.cuda(), genre.cuda())
+    want = pcn_port.decode(key.double(), tonic.double(), genre.double())
+    margin = torch.nn.functional.cosine_similarity(key.double()[:, None], pcn_port.key_signature_map(torch.float64)[None], dim=2)
+    top2 = margin.topk(2, dim=1).values
+    safe = (top2[:, 0] - top2[:, 1]) > 1e-6   # the table holds duplicate rows (enharmonic signatures): first index wins
+    assert torch.equal(ids[0].cpu().long()[safe], want[0][safe])
+    assert torch.equal(ids[1].cpu().long(), want[1]) and torch.equal(ids[2].cpu().long(), want[2])
+    dup = pcn_port.key_signature_map()[[12]] * 0.9 + 0.05   # rows 0 and 12 are identical -> argmax returns 0
+    assert int(ake.decode(dup.cuda(), tonic[:1].cuda())[0][0]) == 0
