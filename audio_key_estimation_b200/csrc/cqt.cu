@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "umma.cuh"
 
 namespace ake {
 
@@ -21,6 +22,11 @@ constexpr int kHalfTaps = 32;          // h[0..31]; full filter has 63 taps (|j|
 constexpr double kPi = 3.14159265358979323846;
 constexpr double kHannBandwidth = 1.50018310546875;  // librosa.filters.WINDOW_BANDWIDTHS['hann']
 constexpr double kBwFastest = 0.85;                   // resampy kaiser_fast rolloff (librosa.audio.BW_FASTEST)
+// tensor-core filter bank (cqt_bank_umma_kernel)
+constexpr int kUKB = 64;        // samples of K per pipeline stage (4 MMA k-steps of 16)
+constexpr int kUStages = 2;
+constexpr float kXScale = 8.f;  // audio is scaled into fp16's comfortable range; the bank by kBankScale
+constexpr float kBankScale = 16.f;
 
 __constant__ float c_dec_taps[kHalfTaps];  // h[|j|] * sqrt(2), identical for every plan (kaiser_fast is fixed)
 
@@ -62,8 +68,11 @@ struct ake_cqt {
   std::vector<double> dec_half;    // kaiser_fast half filter (without the sqrt(2) gain)
   std::vector<float> bank;         // (2*bpo, n_fft): row 2k = Re K_k, 2k+1 = Im K_k
   std::vector<float> out_scale;    // (n_oct, bpo): sqrt(2^i) / sqrt(length of the full-rate bin)
-  float* d_bank = nullptr;
   float* d_scale = nullptr;
+  // tensor-core path: fp16 (hi | lo) image of the bank in the shared-memory operand layout, one block per 64 samples of K
+  __half* d_bank_img = nullptr;
+  float* d_scale_umma = nullptr;
+  int npad = 0;  // filters per MMA (2*bpo rounded up to 16), 0: tensor-core path not available for this shape
 };
 
 namespace ake {
@@ -171,14 +180,35 @@ static void build_cqt(ake_cqt* p) {
 
 // Device copies are made lazily so that plan creation (and the bank / tap getters) need no GPU.
 static void ensure_device(ake_cqt* p) {
-  if (p->d_bank) return;
+  if (p->d_scale) return;
   float taps[kHalfTaps];
   for (int m = 0; m < kHalfTaps; ++m) taps[m] = (float)(p->dec_half[m] * std::sqrt(2.0));  // resample(scale=True): / sqrt(1/2)
   AKE_CUDA(cudaMemcpyToSymbol(c_dec_taps, taps, sizeof taps));
   AKE_CUDA(cudaMalloc(&p->d_scale, sizeof(float) * p->out_scale.size()));
   AKE_CUDA(cudaMemcpy(p->d_scale, p->out_scale.data(), sizeof(float) * p->out_scale.size(), cudaMemcpyHostToDevice));
-  AKE_CUDA(cudaMalloc(&p->d_bank, sizeof(float) * p->bank.size()));
-  AKE_CUDA(cudaMemcpy(p->d_bank, p->bank.data(), sizeof(float) * p->bank.size(), cudaMemcpyHostToDevice));
+  // tensor-core operand image: per 64-sample block of K, 8 chunks x (2*npad) rows x 8 halves; rows [0,npad) = hi, [npad,2npad) = lo
+  const int nf = 2 * p->bpo;
+  const int npad = (nf + 15) / 16 * 16;
+  if ((npad == 80 || npad == 32) && p->n_fft % kUKB == 0) {
+    p->npad = npad;
+    const int n_kb = p->n_fft / kUKB;
+    std::vector<__half> img((size_t)n_kb * 8 * 2 * npad * 8, __float2half(0.f));
+    for (int f = 0; f < nf; ++f)
+      for (int k = 0; k < p->n_fft; ++k) {
+        const float v = p->bank[(size_t)f * p->n_fft + k] * kBankScale;
+        const __half hi = __float2half_rn(v);
+        const __half lo = __float2half_rn(v - __half2float(hi));
+        const size_t blk = (size_t)(k / kUKB) * 8 * 2 * npad * 8, c = (k % kUKB) / 8, e = k % 8;
+        img[blk + (c * 2 * npad + f) * 8 + e] = hi;
+        img[blk + (c * 2 * npad + npad + f) * 8 + e] = lo;
+      }
+    AKE_CUDA(cudaMalloc(&p->d_bank_img, sizeof(__half) * img.size()));
+    AKE_CUDA(cudaMemcpy(p->d_bank_img, img.data(), sizeof(__half) * img.size(), cudaMemcpyHostToDevice));
+    std::vector<float> sc(p->out_scale);
+    for (float& v : sc) v /= (kXScale * kBankScale);
+    AKE_CUDA(cudaMalloc(&p->d_scale_umma, sizeof(float) * sc.size()));
+    AKE_CUDA(cudaMemcpy(p->d_scale_umma, sc.data(), sizeof(float) * sc.size(), cudaMemcpyHostToDevice));
+  }
 }
 
 static inline long long len_at(long long n0, int i) { return (n0 + (1LL << i) - 1) >> i; }  // ceil(n0 / 2^i)
@@ -250,102 +280,158 @@ __global__ void __launch_bounds__(kDecThreads) decimate2_kernel(const float* __r
   }
 }
 
-// Filter-bank contraction + magnitude / scale / log1p epilogue for one octave.
-//   rows m = (clip, frame) flattened, 32 per block; 72 = 2*36 real filters; K = n_fft in chunks of 32.
-// Thread tile: 8 frames x 4 filters (two complex bins), 72 threads per block (4 frame groups x 18 bin pairs).
-constexpr int kBankRows = 32, kBankBK = 32, kBankPitchA = 36;
+// ---- tensor-core filter bank (tcgen05): one CTA = 128 frames of one octave x all filters x all of K ----------------
+//   D[frame, n] = sum_k x[frame, k] * K[n, k],  x ~= xh + xl, K ~= Kh + Kl (fp16 pairs, fp32 accumulation in TMEM)
+//   MMA 1: A = xh, B = [Kh | Kl]  (N = 2*NPAD)  -> columns [0,NPAD) += xh*Kh, [NPAD,2*NPAD) += xh*Kl
+//   MMA 2: A = xl, B =  Kh        (N =   NPAD)  -> columns [0,NPAD) += xl*Kh
+// Warps 0-3: stage frames (fp32 -> fp16 hi/lo, operand layout of umma.cuh) and run the |.|, scale, log1p epilogue out
+// of TMEM; warp 4 lane 0 issues the MMAs; the bank block of each stage arrives by one bulk async copy.
 
-template <int NF2 /* 2*bpo real filters, multiple of 4 */>
-__global__ void cqt_bank_kernel(const float* __restrict__ sig, long long sig_stride, const long long* __restrict__ lengths,
-                                long long n_uniform, int octave, int hop_i, int n_fft, const float* __restrict__ bank,
-                                const float* __restrict__ scale, int B, int T_max, int n_oct, int hop0, int n_bins, int mode,
-                                float* __restrict__ out) {
-  constexpr int NTB = NF2 / 4;  // threads along filters
-  __shared__ __align__(16) float As[kBankBK][kBankPitchA];  // [k][row]
-  __shared__ __align__(16) float Bs[kBankBK][NF2];          // [k][filter]
-  __shared__ long long s_base[kBankRows];   // offset of the clip's sample 0 inside `sig`
-  __shared__ long long s_first[kBankRows];  // clip-relative index of the frame's sample k = 0 (negative at the left edge)
-  __shared__ long long s_len[kBankRows];    // valid samples of this clip at this octave
-  __shared__ int s_T[kBankRows];            // 1: real frame, 0: batch padding (t >= frames of the clip), -1: no row
-  const int tid = threadIdx.x;
-  const long long m0 = (long long)blockIdx.x * kBankRows;
-  for (int row = tid; row < kBankRows; row += blockDim.x) {
-    const long long m = m0 + row;
-    s_T[row] = -1, s_base[row] = 0, s_first[row] = 0, s_len[row] = 0;
-    if (m < (long long)B * T_max) {
-      const int b = m / T_max, t = m % T_max;
-      const long long n0 = lengths ? lengths[b] : n_uniform;
-      long long T = -1;
-      for (int i = 0; i < n_oct; ++i) {
-        const long long ti = 1 + ((n0 + (1LL << i) - 1) >> i) / (hop0 >> i);
-        T = (T < 0 || ti < T) ? ti : T;
-      }
-      s_T[row] = t < T ? 1 : 0;
-      s_base[row] = b * sig_stride;
-      s_first[row] = (long long)t * hop_i - n_fft / 2;
-      s_len[row] = (n0 + (1LL << octave) - 1) >> octave;
-    }
+struct BankArgs {
+  const float* level[16];
+  long long stride[16];
+  const long long* lengths;
+  long long n_uniform;
+  int n_oct, hop0, n_fft, B, T_max, n_bins, bpo, mode;
+  const __half* bank_img;
+  const float* scale;
+  float* out;
+};
+
+template <int NPAD>
+__global__ void __launch_bounds__(160) cqt_bank_umma_kernel(const BankArgs a) {
+  using namespace umma;
+  constexpr uint32_t A_HALF = 128 * kUKB * 2;                // 16 KB: 8 chunks x 128 rows x 16 B
+  constexpr uint32_t B_BYTES = (kUKB / 8) * 2 * NPAD * 16;   // 8 chunks x 2*NPAD rows x 16 B
+  constexpr uint32_t STAGE = 2 * A_HALF + B_BYTES;
+  constexpr uint32_t TMEM_COLS = (2 * NPAD <= 64) ? 64 : ((2 * NPAD <= 128) ? 128 : 256);
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t full_bar[kUStages], empty_bar[kUStages], done_bar;
+  __shared__ uint32_t tmem_slot;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int octave = blockIdx.y;
+  const long long m0 = (long long)blockIdx.x * 128;
+  const int n_kb = a.n_fft / kUKB;
+
+  if (warp == 4) tmem_alloc(&tmem_slot, TMEM_COLS);
+  if (tid == 0) {
+    for (int s = 0; s < kUStages; ++s) mbar_init(&full_bar[s], 128), mbar_init(&empty_bar[s], 1);
+    mbar_init(&done_bar, 1);
+    mbar_init_fence();
   }
+  fence_before_sync();
   __syncthreads();
-  const int fg = tid / NTB, bg = tid % NTB;  // frame group (8 frames), filter group (4 filters)
-  float acc[8][4];
-#pragma unroll
-  for (int i = 0; i < 8; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  fence_after_sync();
+  const uint32_t tmem = tmem_slot;
 
-  for (int k0 = 0; k0 < n_fft; k0 += kBankBK) {
-    __syncthreads();
-    for (int i = tid; i < kBankRows * kBankBK; i += blockDim.x) {
-      const int row = i / kBankBK, kk = i % kBankBK;
-      float v = 0.f;
-      if (s_T[row] == 1) {
-        const long long idx = s_first[row] + k0 + kk;  // centred frame, zero padded (pad_mode='constant')
-        if (idx >= 0 && idx < s_len[row]) v = __ldg(sig + s_base[row] + idx);
+  if (warp < 4) {
+    // ---------------------------------------------------------------- producer: frame row `tid`
+    const long long m = m0 + tid;
+    const bool in_range = m < (long long)a.B * a.T_max;
+    const int b = in_range ? (int)(m / a.T_max) : 0, t = in_range ? (int)(m % a.T_max) : 0;
+    const long long n0 = a.lengths ? a.lengths[b] : a.n_uniform;
+    long long T = -1;
+    for (int i = 0; i < a.n_oct; ++i) {
+      const long long ti = 1 + ((n0 + (1LL << i) - 1) >> i) / (a.hop0 >> i);
+      T = (T < 0 || ti < T) ? ti : T;
+    }
+    const bool real_frame = in_range && t < T;
+    const long long len = (n0 + (1LL << octave) - 1) >> octave;
+    const float* src = a.level[octave] + (long long)b * a.stride[octave];
+    const long long first = (long long)t * (a.hop0 >> octave) - a.n_fft / 2;  // centred frame, zero padded (pad_mode='constant')
+
+    for (int kb = 0; kb < n_kb; ++kb) {
+      const int s = kb % kUStages;
+      const uint32_t phase = (kb / kUStages) & 1;
+      mbar_wait(&empty_bar[s], phase ^ 1);
+      uint8_t* stage = smem + (size_t)s * STAGE;
+      if (tid == 0) {
+        mbar_arrive_expect_tx(&full_bar[s], B_BYTES);
+        bulk_g2s(stage + 2 * A_HALF, reinterpret_cast<const uint8_t*>(a.bank_img) + (size_t)kb * B_BYTES, B_BYTES, &full_bar[s]);
       }
-      As[kk][row] = v;
-    }
-    for (int i = tid; i < kBankBK * NF2; i += blockDim.x) {
-      const int kk = i / NF2, f = i % NF2;
-      Bs[kk][f] = __ldg(bank + (long long)f * n_fft + k0 + kk);
-    }
-    __syncthreads();
-#pragma unroll 8
-    for (int kk = 0; kk < kBankBK; ++kk) {
-      const float4 a0 = *reinterpret_cast<const float4*>(&As[kk][fg * 8]);
-      const float4 a1 = *reinterpret_cast<const float4*>(&As[kk][fg * 8 + 4]);
-      const float4 w = *reinterpret_cast<const float4*>(&Bs[kk][bg * 4]);
-      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-      const float wv[4] = {w.x, w.y, w.z, w.w};
+      const long long i0 = first + (long long)kb * kUKB;
+      float x[kUKB];
+      const float* p = src + i0;
+      if (real_frame && i0 >= 0 && i0 + kUKB <= len && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
-    }
-  }
-  // epilogue
-  const int bpo = NF2 / 2;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int row = fg * 8 + i;
-    if (s_T[row] < 0) continue;
-    const long long m = m0 + row;
-    const int b = m / T_max, t = m % T_max;
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const int k = bg * 2 + j;
-      const int bin = n_bins - bpo * (octave + 1) + k;
-      const float s = scale[octave * bpo + k];
-      float re = acc[i][2 * j] * s, im = acc[i][2 * j + 1] * s;
-      if (s_T[row] == 0) re = 0.f, im = 0.f;  // beyond the clip's frames: batch padding is zero (KeyDataset.py:242-254)
-      if (mode == AKE_CQT_LOGMAG) {
-        out[((long long)b * n_bins + bin) * T_max + t] = log1pf(sqrtf(re * re + im * im));
+        for (int q = 0; q < kUKB / 4; ++q) {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(p) + q);
+          x[4 * q] = v.x, x[4 * q + 1] = v.y, x[4 * q + 2] = v.z, x[4 * q + 3] = v.w;
+        }
       } else {
-        float2* o2 = reinterpret_cast<float2*>(out) + ((long long)b * n_bins + bin) * T_max + t;
-        *o2 = make_float2(re, im);
+#pragma unroll
+        for (int q = 0; q < kUKB; ++q) {
+          const long long i = i0 + q;
+          x[q] = (real_frame && i >= 0 && i < len) ? __ldg(src + i) : 0.f;
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < kUKB / 8; ++c) {
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          __half h0, l0, h1, l1;
+          split_f16(x[8 * c + 2 * e] * kXScale, h0, l0);
+          split_f16(x[8 * c + 2 * e + 1] * kXScale, h1, l1);
+          hi[e] = pack_h2(h0, h1), lo[e] = pack_h2(l0, l1);
+        }
+        *reinterpret_cast<uint4*>(stage + c * 2048 + tid * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(stage + A_HALF + c * 2048 + tid * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      }
+      fence_proxy_async();
+      if (tid != 0) mbar_arrive(&full_bar[s]);
+    }
+    // ---------------------------------------------------------------- epilogue: TMEM lane `tid` = frame row `tid`
+    mbar_wait(&done_bar, 0);
+    fence_after_sync();
+    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+    const int bpo = a.bpo;
+#pragma unroll 1
+    for (int c0 = 0; c0 < NPAD; c0 += 16) {
+      float u[16], w[16];
+      tmem_ld16(lane_base + c0, u);
+      tmem_ld16(lane_base + NPAD + c0, w);
+      if (!in_range) continue;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int k = c0 / 2 + j;
+        if (k >= bpo) break;
+        const int bin = a.n_bins - bpo * (octave + 1) + k;
+        const float sc = a.scale[octave * bpo + k];
+        float re = (u[2 * j] + w[2 * j]) * sc, im = (u[2 * j + 1] + w[2 * j + 1]) * sc;
+        if (!real_frame) re = 0.f, im = 0.f;  // beyond the clip's frames: batch padding is zero (KeyDataset.py:242-254)
+        if (a.mode == AKE_CQT_LOGMAG) {
+          a.out[((long long)b * a.n_bins + bin) * a.T_max + t] = log1pf(sqrtf(re * re + im * im));
+        } else {
+          reinterpret_cast<float2*>(a.out)[((long long)b * a.n_bins + bin) * a.T_max + t] = make_float2(re, im);
+        }
       }
     }
+    (void)lane;
+  } else if (lane == 0) {
+    // ---------------------------------------------------------------- MMA issuer
+    constexpr uint64_t A_DESC = desc_hi(128 * 16);       // chunk stride 2 KB (128 rows x 16 B)
+    constexpr uint64_t B_DESC = desc_hi(2 * NPAD * 16);  // chunk stride = 2*NPAD rows x 16 B
+    constexpr uint32_t IDESC_WIDE = idesc_f16(2 * NPAD), IDESC_NARROW = idesc_f16(NPAD);
+    for (int kb = 0; kb < n_kb; ++kb) {
+      const int s = kb % kUStages;
+      mbar_wait(&full_bar[s], (kb / kUStages) & 1);
+      fence_after_sync();
+      const uint32_t base = smem_u32(smem + (size_t)s * STAGE);
+#pragma unroll
+      for (int j = 0; j < kUKB / 16; ++j) {
+        const uint64_t bd = make_desc(B_DESC, base + 2 * A_HALF + j * (2 * 2 * NPAD * 16));
+        mma_f16(tmem, make_desc(A_DESC, base + j * 4096), bd, IDESC_WIDE, (kb | j) ? 1u : 0u);
+        mma_f16(tmem, make_desc(A_DESC, base + A_HALF + j * 4096), bd, IDESC_NARROW, 1u);
+      }
+      commit(&empty_bar[s]);
+    }
+    commit(&done_bar);
   }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem, TMEM_COLS);
 }
 
 __global__ void cqt_seqlen_kernel(const long long* __restrict__ lengths, long long n_uniform, int B, int n_oct, int hop0,
@@ -400,20 +486,35 @@ static void run_cqt(ake_cqt* p, const float* audio, long long stride, const int6
     AKE_LAUNCHED();
   }
   const long long rows = (long long)B * T_max;
-  for (int i = 0; i < p->n_oct; ++i) {
+  if (p->npad) {
+    // tensor cores: every octave in one launch (grid.y = octave)
     ProfScope prof("cqt.bank", st);
-    if (2 * p->bpo == 72) {
-      cqt_bank_kernel<72><<<(unsigned)cdiv64(rows, kBankRows), 4 * 18, 0, st>>>(
-          w.level[i], w.stride[i], d_len, n_max, i, p->hop >> i, p->n_fft, p->d_bank, p->d_scale, B, T_max, p->n_oct, p->hop,
-          p->n_bins, mode, out);
-    } else if (2 * p->bpo == 24) {
-      cqt_bank_kernel<24><<<(unsigned)cdiv64(rows, kBankRows), 4 * 6, 0, st>>>(
-          w.level[i], w.stride[i], d_len, n_max, i, p->hop >> i, p->n_fft, p->d_bank, p->d_scale, B, T_max, p->n_oct, p->hop,
-          p->n_bins, mode, out);
+    BankArgs ba{};
+    for (int i = 0; i < p->n_oct; ++i) ba.level[i] = w.level[i], ba.stride[i] = w.stride[i];
+    ba.lengths = d_len, ba.n_uniform = n_max, ba.n_oct = p->n_oct, ba.hop0 = p->hop, ba.n_fft = p->n_fft, ba.B = B, ba.T_max = T_max;
+    ba.n_bins = p->n_bins, ba.bpo = p->bpo, ba.mode = mode, ba.bank_img = p->d_bank_img, ba.scale = p->d_scale_umma, ba.out = out;
+    dim3 grid((unsigned)cdiv64(rows, 128), p->n_oct);
+    if (p->npad == 80) {
+      constexpr size_t smem = kUStages * (2 * 128 * kUKB * 2 + (kUKB / 8) * 2 * 80 * 16);
+      static bool configured = false;
+      if (!configured) {
+        AKE_CUDA(cudaFuncSetAttribute(cqt_bank_umma_kernel<80>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+      }
+      cqt_bank_umma_kernel<80><<<grid, 160, smem, st>>>(ba);
     } else {
-      fail(AKE_ERR_UNSUPPORTED, "bins_per_octave %d: 36 and 12 are built", p->bpo);
+      constexpr size_t smem = kUStages * (2 * 128 * kUKB * 2 + (kUKB / 8) * 2 * 32 * 16);
+      static bool configured = false;
+      if (!configured) {
+        AKE_CUDA(cudaFuncSetAttribute(cqt_bank_umma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+      }
+      cqt_bank_umma_kernel<32><<<grid, 160, smem, st>>>(ba);
     }
     AKE_LAUNCHED();
+  } else {
+    fail(AKE_ERR_UNSUPPORTED, "bins_per_octave %d / n_fft %d: the filter-bank kernel is built for 36 and 12 bins per octave, n_fft %% 64 == 0",
+         p->bpo, p->n_fft);
   }
   if (seq_len_out) {
     cqt_seqlen_kernel<<<cdiv(B, 128), 128, 0, st>>>(d_len, n_max, B, p->n_oct, p->hop, T_max, seq_len_out);
@@ -444,8 +545,9 @@ int ake_cqt_create(double sr, int hop_length, int n_bins, int bins_per_octave, d
 
 void ake_cqt_destroy(ake_cqt* p) {
   if (!p) return;
-  if (p->d_bank) cudaFree(p->d_bank);
   if (p->d_scale) cudaFree(p->d_scale);
+  if (p->d_bank_img) cudaFree(p->d_bank_img);
+  if (p->d_scale_umma) cudaFree(p->d_scale_umma);
   delete p;
 }
 

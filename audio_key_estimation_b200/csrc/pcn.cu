@@ -326,7 +326,11 @@ struct Fwd {
     return v;
   }
   void tap(const std::string& name, const View& v, int C = -1) {
-    if (!dry) p->taps[name] = {v.p, (int64_t)B * (C < 0 ? v.C : C) * v.R * v.T};
+    if (dry) return;
+    // ping-pong buffers are reused: a newer tap on the same storage invalidates the older one
+    for (auto it = p->taps.begin(); it != p->taps.end();)
+      it = (it->second.first == v.p) ? p->taps.erase(it) : std::next(it);
+    p->taps[name] = {v.p, (int64_t)B * (C < 0 ? v.C : C) * v.R * v.T};
   }
   const float* scale_of(const Conv& c, bool raw) const { return (raw ? p->d_ss_raw : p->d_ss_eval) + c.ss_off; }
   const float* shift_of(const Conv& c, bool raw) const {
