@@ -6,6 +6,7 @@
 //   heads                   models.py:713-742
 //   masked mean + sigmoid   models.py:754-804
 #include <cmath>
+#include <cstdlib>
 #include <algorithm>
 #include <cstring>
 #include <atomic>
@@ -15,6 +16,7 @@
 #include <vector>
 
 #include "pcn_kernels.cuh"
+#include "pcn_umma.cuh"
 
 namespace ake {
 
@@ -117,6 +119,10 @@ struct ake_pcn {
   float* d_ss_eval = nullptr;  // [scale | shift] eval-mode epilogues, n_ss each
   float* d_ss_raw = nullptr;   // [1 | bias] raw epilogues
   bool has_params = false;
+  // tensor-core path (eval mode, default channel plan): fp16 hi/lo operand images of the 7x7 convolutions
+  bool umma = false;
+  __half* d_wimg = nullptr;         // one kP2PWBytes image per Pitch2Pitch conv, in conv-id order of `umma_convs`
+  std::vector<int> umma_convs;
   std::map<std::string, std::pair<const float*, int64_t>> taps;
 };
 
@@ -239,6 +245,12 @@ static void build_plan(ake_pcn* p) {
       }
     }
   };
+  {
+    // Tensor-core path: the Pitch2Pitch stack of layer 1 at the train_model.py channel plan (1 + 4 -> 8 -> 8 channels).
+    const char* off = getenv("AKE_DISABLE_UMMA");
+    p->umma = !(off && off[0] == '1') && c.num_layers == 2 && nf == 4 && k == 7;
+    if (p->umma) p->umma_convs = p->layers[1].p2p;
+  }
   build_head("tonic_classifier", true, p->tonic_head);
   build_head("key_classifier", true, p->key_head);
   if (c.genre) build_head("genre_classifier", false, p->genre_head);
@@ -444,6 +456,56 @@ void Fwd::run(const float* mel, float* key_out, float* tonic_out, float* genre_o
       semitone_pool(0, p_in, cat, 0);
       tap("l0.pool", cat);
     } else {
+      const bool fast = p->umma && !train && L == 1 && Tn >= 7;
+      View p_feat;
+      cat = alloc(lp.prev_pc + lp.out_p, 12, Tn);
+      if (!dry)  // concat [pc, pc2] (models.py:392): previous pc is copied in, the pool_semi result is written beside it
+        AKE_CUDA(cudaMemcpy2DAsync(cat.p, sizeof(float) * cat.bstride(), pc.p, sizeof(float) * pc.bstride(),
+                                   sizeof(float) * pc.bstride(), B, cudaMemcpyDeviceToDevice, st));
+      if (fast) {
+        // ---- tensor-core path: chunk-plane activations (pcn_umma.cuh), up_sixth fused into the first operand build
+        const int Wd = Tn + 6;
+        const size_t plane_halves = (size_t)B * (P + 6) * Wd * 8;
+        __half* x[2][2];
+        for (int i = 0; i < 2; ++i)
+          for (int j = 0; j < 2; ++j) x[i][j] = arena.take<__half>(plane_halves);
+        const Conv& cu = p->convs[lp.up];
+        if (!dry) {
+          ProfScope prof("pcn.prep", st);
+          PrepArgs pa{p_in.p, pc.p, p->d_params + cu.w_off, scale_of(cu, false), shift_of(cu, false), x[0][0], x[0][1], B, P, Tn, Wd};
+          p2p_prep_kernel<<<ew_blocks((long long)B * (P + 6) * Wd), 256, 0, st>>>(pa);
+          AKE_LAUNCHED();
+        }
+        const int n_tt = cdiv(Tn, kP2PMaxTB), TB = cdiv(Tn, n_tt);
+        const size_t smem = p2p_smem_bytes(TB + 6);
+        int cur = 0;
+        for (size_t i = 0; i < lp.p2p.size(); ++i) {
+          const Conv& c = p->convs[lp.p2p[i]];
+          if (!dry) {
+            ProfScope prof("pcn.p2p", st);
+            static size_t configured = 0;
+            if (smem > configured) {
+              AKE_CUDA(cudaFuncSetAttribute(p2p_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+              configured = smem;
+            }
+            P2PArgs a{x[cur][0], x[cur][1], x[cur ^ 1][0], x[cur ^ 1][1],
+                      reinterpret_cast<const __half*>(reinterpret_cast<const uint8_t*>(p->d_wimg) + i * kP2PWBytes),
+                      scale_of(c, false), shift_of(c, false), P, Tn, Wd, TB, cdiv(Tn, TB)};
+            dim3 grid(cdiv(P, kP2PRows) * cdiv(Tn, TB), B);
+            p2p_umma_kernel<<<grid, 160, smem, st>>>(a);
+            AKE_LAUNCHED();
+          }
+          cur ^= 1;
+        }
+        const Conv& cs = p->convs[lp.sem];
+        if (!dry) {
+          ProfScope prof("pcn.semitone", st);
+          SemiArgs sa{x[cur][0], x[cur][1], p->d_params + cs.w_off, scale_of(cs, false), shift_of(cs, false), cat.p, B, P, Tn, Wd,
+                      cat.C, lp.prev_pc};
+          semitone_pool_chunks_kernel<<<dim3(cdiv(Tn, 128), 12, B), 128, 0, st>>>(sa);
+          AKE_LAUNCHED();
+        }
+      } else {
       // up_sixth ConvTranspose + BN + act (models.py:372-374); tiled to all pitches by the conv loader (:378)
       const Conv& cu = p->convs[lp.up];
       View up = alloc(lp.prev_pc, 36, Tn);
@@ -471,13 +533,9 @@ void Fwd::run(const float* mel, float* key_out, float* tonic_out, float* genre_o
         src = dst;
         dst = (dst == &a) ? &b2 : &a;
       }
-      View p_feat = *src;
-      // concat [pc, pc2] (models.py:392): previous pc is copied in, pool_semi result written beside it
-      cat = alloc(lp.prev_pc + lp.out_p, 12, Tn);
-      if (!dry)
-        AKE_CUDA(cudaMemcpy2DAsync(cat.p, sizeof(float) * cat.bstride(), pc.p, sizeof(float) * pc.bstride(),
-                                   sizeof(float) * pc.bstride(), B, cudaMemcpyDeviceToDevice, st));
+      p_feat = *src;
       semitone_pool(L, p_feat, cat, lp.prev_pc);
+      }
       tap(ln + ".cat", cat);
       // time pooling of the pitch-wise features is only needed if another layer follows (models.py:395)
       if (L + 1 < cfg.num_layers) {
@@ -584,6 +642,15 @@ static void upload_params(ake_pcn* p, const float* flat_dev, int64_t n, cudaStre
         p->d_ss_eval + p->n_ss + c.ss_off, p->d_ss_raw + c.ss_off, p->d_ss_raw + p->n_ss + c.ss_off);
     AKE_LAUNCHED();
   }
+  if (p->umma) {
+    if (!p->d_wimg) AKE_CUDA(cudaMalloc(&p->d_wimg, (size_t)kP2PWBytes * p->umma_convs.size()));
+    for (size_t i = 0; i < p->umma_convs.size(); ++i) {
+      const Conv& c = p->convs[p->umma_convs[i]];
+      p2p_pack_weights_kernel<<<14, 256, 0, st>>>(p->d_params + c.w_off, c.Cout, c.Cin,
+                                                   reinterpret_cast<__half*>(reinterpret_cast<uint8_t*>(p->d_wimg) + i * kP2PWBytes));
+      AKE_LAUNCHED();
+    }
+  }
   p->has_params = true;
 }
 
@@ -667,6 +734,7 @@ void ake_pcn_destroy(ake_pcn* p) {
   cudaFree(p->d_packed);
   cudaFree(p->d_ss_eval);
   cudaFree(p->d_ss_raw);
+  cudaFree(p->d_wimg);
   delete p;
 }
 

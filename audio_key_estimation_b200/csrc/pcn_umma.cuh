@@ -1,0 +1,355 @@
+// pcn_umma.cuh -- tensor-core (tcgen05) kernels of the PitchClassNet forward, eval mode, default channel plan.
+//
+// Activation layout ("chunk planes"): a tensor of 8*G channels over a (rows x cols) grid is stored as
+//   plane[b][g][row][col][8 channels] in fp16, twice: a `hi` plane and a `lo` plane with  x ~= hi + lo  (22 bits).
+// One position of one channel group is 16 bytes = one K chunk of the MMA operand layout of umma.cuh, so a tile of the
+// tensor copied verbatim into shared memory IS a valid A operand, and a convolution tap (dp, dt) is the same operand
+// started (dp * pitch + dt) * 16 bytes further on ("shift-GEMM": no im2col, no register traffic).  Circular padding
+// (padding_mode="circular", models.py:230-232) is materialised as halo rows / columns by the producing kernel.
+//
+// Pitch2Pitch 7x7 circular convolution (models.py:228-234; 64.6 % of the forward's MACs):
+//   out[a] = sum_{dp<7} sum_{dt<7} X[a + dp*Wt + dt] . W[dp][dt]        (a = flattened anchor, 8 -> 8 channels)
+// is issued as 7 row taps x 2 MMAs per 128 anchors:
+//   K = 16 : chunk 0 = X[a' + dp*Wt], chunk 1 = X[a' + dp*Wt + 1]                 (LBO = 16 B: two time taps)
+//   N = 64 : 4 "phases" f (time taps 2f, 2f+1) x 8 output channels x {W_hi, W_lo}   (MMA 1, A = X_hi)
+//   N = 32 : the W_hi half only                                                     (MMA 2, A = X_lo)
+// and the epilogue adds the phases back together one row apart:  out[a] = sum_f D_f[a + 2f]  (fixed order, so every
+// output is accumulated identically whatever its pitch -> transposition equivariance stays bit exact).
+#pragma once
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace ake {
+
+constexpr float kWScale = 64.f;     // conv weights are scaled into fp16's normal range; folded back in the epilogue
+constexpr int kP2PStride = 122;     // anchors produced per 128-row MMA block (6 rows feed the phase shifts)
+constexpr int kP2PRows = 8;         // pitch rows per CTA tile
+constexpr int kP2PMaxTB = 160;      // frames per CTA tile (upper bound)
+
+__device__ __forceinline__ float leaky_f(float v) { return v > 0.f ? v : kLeakySlope * v; }
+
+__device__ __forceinline__ void store_split8(__half* hi_dst, __half* lo_dst, const float (&v)[8]) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    __half h0, l0, h1, l1;
+    umma::split_f16(v[2 * e], h0, l0);
+    umma::split_f16(v[2 * e + 1], h1, l1);
+    h[e] = umma::pack_h2(h0, h1), l[e] = umma::pack_h2(l0, l1);
+  }
+  *reinterpret_cast<uint4*>(hi_dst) = make_uint4(h[0], h[1], h[2], h[3]);
+  *reinterpret_cast<uint4*>(lo_dst) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// ---- layer >= 1 input: cat[p (1 ch), tile(up_sixth(pc)) (4 ch)] -> chunk planes with circular halos ---------------
+// models.py:372-383: ConvTranspose2d(4,4,(3,1),stride (3,1)) + BN + LeakyReLU on pc, tiled x8 along pitch
+// (PitchClass2Pitch, :135-143), concatenated behind the raw CQT channel.  One thread per halo'd position.
+struct PrepArgs {
+  const float* mel;   // (B,1,P,T)
+  const float* pc;    // (B,4,12,T)
+  const float* w_up;  // (4 ci, 4 co, 3, 1)
+  const float* scale; // 4 (eval-mode BN folded, bias included)
+  const float* shift;
+  __half* out_hi;
+  __half* out_lo;
+  int B, P, T, Wd;
+};
+
+__global__ void __launch_bounds__(256) p2p_prep_kernel(const PrepArgs a) {
+  __shared__ float w[48], sc[4], sh[4];
+  if (threadIdx.x < 48) w[threadIdx.x] = a.w_up[threadIdx.x];
+  if (threadIdx.x < 4) sc[threadIdx.x] = a.scale[threadIdx.x], sh[threadIdx.x] = a.shift[threadIdx.x];
+  __syncthreads();
+  const int rows = a.P + 6;
+  const long long n = (long long)a.B * rows * a.Wd;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int col = i % a.Wd;
+    const long long q = i / a.Wd;
+    const int row = q % rows, b = q / rows;
+    int p = row - 3, t = col - 3;
+    p += (p < 0) ? a.P : 0, p -= (p >= a.P) ? a.P : 0;
+    t += (t < 0) ? a.T : 0, t -= (t >= a.T) ? a.T : 0;
+    float v[8];
+    v[0] = __ldg(a.mel + ((long long)b * a.P + p) * a.T + t);
+    const int p36 = p % 36, c = p36 / 3, r = p36 - 3 * c;
+    float x[4];
+#pragma unroll
+    for (int ci = 0; ci < 4; ++ci) x[ci] = __ldg(a.pc + (((long long)b * 4 + ci) * 12 + c) * a.T + t);
+#pragma unroll
+    for (int co = 0; co < 4; ++co) {
+      float acc = 0.f;
+#pragma unroll
+      for (int ci = 0; ci < 4; ++ci) acc = fmaf(w[(ci * 4 + co) * 3 + r], x[ci], acc);
+      v[1 + co] = leaky_f(fmaf(acc, sc[co], sh[co]));
+    }
+    v[5] = v[6] = v[7] = 0.f;
+    store_split8(a.out_hi + i * 8, a.out_lo + i * 8, v);
+  }
+}
+
+// ---- weight image for the 7x7 convolution: [dp 7][chunk 2][n 64][ci 8] fp16 ---------------------------------------
+// n < 32: W_hi of (phase f = n / 8, co = n % 8), time tap dt = 2 f + chunk (zero for dt = 7); n >= 32: W_lo.
+__global__ void p2p_pack_weights_kernel(const float* __restrict__ w, int Cout, int Cin, __half* __restrict__ img) {
+  const int n_items = 7 * 2 * 32 * 8;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_items; i += gridDim.x * blockDim.x) {
+    const int ci = i % 8, n = (i / 8) % 32, c = (i / 256) % 2, dp = i / 512;
+    const int f = n / 8, co = n % 8, dt = 2 * f + c;
+    float v = 0.f;
+    if (dt < 7 && ci < Cin && co < Cout) v = w[(((long long)co * Cin + ci) * 7 + dp) * 7 + dt] * kWScale;
+    const __half hi = __float2half_rn(v);
+    const __half lo = __float2half_rn(v - __half2float(hi));
+    img[((dp * 2 + c) * 64 + n) * 8 + ci] = hi;
+    img[((dp * 2 + c) * 64 + 32 + n) * 8 + ci] = lo;
+  }
+}
+
+struct P2PArgs {
+  const __half* in_hi;
+  const __half* in_lo;   // [B][P+6][Wd][8]
+  __half* out_hi;
+  __half* out_lo;        // same geometry
+  const __half* wimg;    // p2p_pack_weights_kernel image (14336 B)
+  const float* scale;    // 8: eval-mode BN scale (the 1/kWScale factor is applied in the kernel)
+  const float* shift;    // 8
+  int P, T, Wd;          // Wd = T + 6
+  int TB, n_ttiles;      // frames per tile, tiles along time
+};
+
+constexpr uint32_t kP2PWBytes = 7 * 2 * 64 * 16;
+
+__host__ __device__ inline uint32_t p2p_plane_positions(int Wt) { return (uint32_t)((kP2PRows + 6) * Wt + 136); }
+__host__ __device__ inline size_t p2p_smem_bytes(int Wt) {
+  return (size_t)2 * p2p_plane_positions(Wt) * 16 + kP2PWBytes + 6 * 128 * 16;
+}
+
+__global__ void __launch_bounds__(160) p2p_umma_kernel(const P2PArgs a) {
+  using namespace umma;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t tile_bar, acc_full[2], acc_empty[2];
+  __shared__ uint32_t tmem_slot;
+  __shared__ float s_scale[8], s_shift[8];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ttile = blockIdx.x % a.n_ttiles, rtile = blockIdx.x / a.n_ttiles, b = blockIdx.y;
+  const int p0 = rtile * kP2PRows, t0 = ttile * a.TB;
+  const int PB = min(kP2PRows, a.P - p0);           // valid output rows of this tile
+  const int TBv = min(a.TB, a.T - t0);              // valid output frames
+  const int Wt = a.TB + 6;                          // tile pitch (positions per staged row)
+  const int n_anchor = PB * Wt;
+  const int n_mb = (n_anchor + kP2PStride - 1) / kP2PStride;
+  const uint32_t plane = p2p_plane_positions(Wt) * 16;
+  uint8_t* s_hi = smem;
+  uint8_t* s_lo = smem + plane;
+  uint8_t* s_w = smem + 2 * plane;
+  float4* s_ex = reinterpret_cast<float4*>(smem + 2 * plane + kP2PWBytes);  // [(phase-1)*2 + half][128 rows]
+
+  if (warp == 4) tmem_alloc(&tmem_slot, 128);
+  if (tid == 0) {
+    mbar_init(&tile_bar, 1);
+    mbar_init(&acc_full[0], 1), mbar_init(&acc_full[1], 1);
+    mbar_init(&acc_empty[0], 128), mbar_init(&acc_empty[1], 128);
+    mbar_init_fence();
+  }
+  if (tid < 8) s_scale[tid] = a.scale[tid] * (1.f / kWScale), s_shift[tid] = a.shift[tid];
+  {
+    // Zero what the bulk copies will not write (tail padding, the column gap of a narrow last time tile): the MMAs
+    // read it under zero weights (time tap 7) and in discarded rows, and 0 * NaN would poison a valid output.
+    const int cols_in = min(Wt, a.Wd - t0);
+    const uint32_t loaded = (uint32_t)(PB + 6) * Wt, total = p2p_plane_positions(Wt);
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    for (uint32_t i = loaded + tid; i < total; i += blockDim.x)
+      reinterpret_cast<uint4*>(s_hi)[i] = z, reinterpret_cast<uint4*>(s_lo)[i] = z;
+    if (cols_in < Wt) {
+      const int gap = Wt - cols_in;
+      for (int i = tid; i < (PB + 6) * gap; i += blockDim.x) {
+        const uint32_t q = (uint32_t)(i / gap) * Wt + cols_in + i % gap;
+        reinterpret_cast<uint4*>(s_hi)[q] = z, reinterpret_cast<uint4*>(s_lo)[q] = z;
+      }
+    }
+    fence_proxy_async();
+  }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+
+  if (warp == 4) {
+    // ------------------------------------------------------------ loader + MMA issuer
+    const int rows_in = PB + 6;
+    const int cols_in = min(Wt, a.Wd - t0);  // the last time tile may be narrower than Wt
+    const uint32_t row_bytes = (uint32_t)cols_in * 16;
+    if (lane == 0) mbar_arrive_expect_tx(&tile_bar, kP2PWBytes + 2u * rows_in * row_bytes);
+    __syncwarp();
+    if (lane == 0) bulk_g2s(s_w, a.wimg, kP2PWBytes, &tile_bar);
+    for (int rr = lane; rr < rows_in; rr += 32) {
+      const long long src = (((long long)b * (a.P + 6) + p0 + rr) * a.Wd + t0) * 8;
+      bulk_g2s(s_hi + (size_t)rr * Wt * 16, a.in_hi + src, row_bytes, &tile_bar);
+      bulk_g2s(s_lo + (size_t)rr * Wt * 16, a.in_lo + src, row_bytes, &tile_bar);
+    }
+    if (lane == 0) {
+      mbar_wait(&tile_bar, 0);
+      constexpr uint64_t A_DESC = desc_hi(16);        // chunk 1 = next position (next time frame)
+      constexpr uint64_t B_DESC = desc_hi(64 * 16);   // chunk stride: 64 rows x 16 B
+      constexpr uint32_t IDESC64 = idesc_f16(64), IDESC32 = idesc_f16(32);
+      const uint32_t hi0 = smem_u32(s_hi), lo0 = smem_u32(s_lo), w0 = smem_u32(s_w);
+      for (int m = 0; m < n_mb; ++m) {
+        const int buf = m & 1;
+        mbar_wait(&acc_empty[buf], ((m >> 1) & 1) ^ 1);
+        fence_after_sync();
+        const uint32_t d = tmem + buf * 64;
+        const uint32_t a_off = (uint32_t)(m * kP2PStride) * 16;
+#pragma unroll
+        for (int dp = 0; dp < 7; ++dp) {
+          const uint32_t off = a_off + (uint32_t)(dp * Wt) * 16;
+          const uint64_t bd = make_desc(B_DESC, w0 + dp * 2048);
+          mma_f16(d, make_desc(A_DESC, hi0 + off), bd, IDESC64, dp ? 1u : 0u);
+          mma_f16(d, make_desc(A_DESC, lo0 + off), bd, IDESC32, 1u);
+        }
+        commit(&acc_full[buf]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue: thread = TMEM lane = anchor row
+    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+    for (int m = 0; m < n_mb; ++m) {
+      const int buf = m & 1;
+      mbar_wait(&acc_full[buf], (m >> 1) & 1);
+      fence_after_sync();
+      float v[4][8];
+      {
+        float u[16], w[16];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          tmem_ld16(lane_base + buf * 64 + h * 16, u);
+          tmem_ld16(lane_base + buf * 64 + 32 + h * 16, w);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[2 * h + j / 8][j % 8] = u[j] + w[j];
+        }
+      }
+      fence_before_sync();
+      mbar_arrive(&acc_empty[buf]);  // accumulator drained: the issuer may start block m + 2
+      float4* ex = s_ex;
+#pragma unroll
+      for (int f = 1; f < 4; ++f) {
+        ex[((f - 1) * 2 + 0) * 128 + tid] = make_float4(v[f][0], v[f][1], v[f][2], v[f][3]);
+        ex[((f - 1) * 2 + 1) * 128 + tid] = make_float4(v[f][4], v[f][5], v[f][6], v[f][7]);
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int anchor = m * kP2PStride + tid;
+      if (tid < kP2PStride && anchor < n_anchor) {
+        const int pl = anchor / Wt, tl = anchor - pl * Wt;
+        if (tl < TBv) {
+          float o[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) o[c] = v[0][c];
+#pragma unroll
+          for (int f = 1; f < 4; ++f) {
+            const float4 x0 = ex[((f - 1) * 2 + 0) * 128 + tid + 2 * f];
+            const float4 x1 = ex[((f - 1) * 2 + 1) * 128 + tid + 2 * f];
+            o[0] += x0.x, o[1] += x0.y, o[2] += x0.z, o[3] += x0.w;
+            o[4] += x1.x, o[5] += x1.y, o[6] += x1.z, o[7] += x1.w;
+          }
+#pragma unroll
+          for (int c = 0; c < 8; ++c) o[c] = leaky_f(fmaf(o[c], s_scale[c], s_shift[c]));
+          uint32_t h[4], l[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            __half h0, l0, h1, l1;
+            split_f16(o[2 * e], h0, l0);
+            split_f16(o[2 * e + 1], h1, l1);
+            h[e] = pack_h2(h0, h1), l[e] = pack_h2(l0, l1);
+          }
+          const uint4 hv = make_uint4(h[0], h[1], h[2], h[3]), lv = make_uint4(l[0], l[1], l[2], l[3]);
+          const int p = p0 + pl, t = t0 + tl;
+          // home position + circular halo copies (rows p +- P, columns t +- T)
+          const int row2 = (p < 3) ? p + 3 + a.P : ((p >= a.P - 3) ? p + 3 - a.P : -1);
+          const int col2 = (t < 3) ? t + 3 + a.T : ((t >= a.T - 3) ? t + 3 - a.T : -1);
+          const long long base = (long long)b * (a.P + 6);
+          const long long q00 = ((base + p + 3) * a.Wd + t + 3) * 8;
+          *reinterpret_cast<uint4*>(a.out_hi + q00) = hv, *reinterpret_cast<uint4*>(a.out_lo + q00) = lv;
+          if (col2 >= 0) {
+            const long long q = ((base + p + 3) * a.Wd + col2) * 8;
+            *reinterpret_cast<uint4*>(a.out_hi + q) = hv, *reinterpret_cast<uint4*>(a.out_lo + q) = lv;
+          }
+          if (row2 >= 0) {
+            const long long q = ((base + row2) * a.Wd + t + 3) * 8;
+            *reinterpret_cast<uint4*>(a.out_hi + q) = hv, *reinterpret_cast<uint4*>(a.out_lo + q) = lv;
+            if (col2 >= 0) {
+              const long long q2 = ((base + row2) * a.Wd + col2) * 8;
+              *reinterpret_cast<uint4*>(a.out_hi + q2) = hv, *reinterpret_cast<uint4*>(a.out_lo + q2) = lv;
+            }
+          }
+        }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // the exchange buffer is reused by the next block
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem, 128);
+}
+
+// ---- pool_semi conv (3x3, stride (3,1), time-circular) + BN + LeakyReLU + octave max pool, from chunk planes ------
+// models.py:337-339, 386-389: s[co, j, t] = act(bn(sum_{ci,dp<3,dt<3} W x[ci, 3j+dp, (t+dt-1) mod T])), pc[co,c,t] = max_o s[co, c+12o, t].
+// One thread per (c, t); writes channels [coff, coff+8) of the (B, C_total, 12, T) fp32 concat tensor (models.py:392).
+struct SemiArgs {
+  const __half* in_hi;
+  const __half* in_lo;  // [B][P+6][Wd][8]
+  const float* w;       // (8 co, 8 ci, 3, 3)
+  const float* scale;
+  const float* shift;
+  float* out;           // (B, C_total, 12, T)
+  int B, P, T, Wd, C_total, coff;
+};
+
+__global__ void __launch_bounds__(128) semitone_pool_chunks_kernel(const SemiArgs a) {
+  __shared__ float w[8 * 8 * 9];  // [dp][dt][ci][co]
+  __shared__ float sc[8], sh[8];
+  for (int i = threadIdx.x; i < 576; i += blockDim.x) {
+    const int co = i % 8, ci = (i / 8) % 8, tap = i / 64;
+    w[i] = a.w[(co * 8 + ci) * 9 + tap];
+  }
+  if (threadIdx.x < 8) sc[threadIdx.x] = a.scale[threadIdx.x], sh[threadIdx.x] = a.shift[threadIdx.x];
+  __syncthreads();
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = blockIdx.y, b = blockIdx.z;
+  if (t >= a.T) return;
+  const int n_oct = a.P / 36;
+  float best[8];
+#pragma unroll
+  for (int co = 0; co < 8; ++co) best[co] = -INFINITY;
+  for (int o = 0; o < n_oct; ++o) {
+    float acc[8];
+#pragma unroll
+    for (int co = 0; co < 8; ++co) acc[co] = 0.f;
+    const int row0 = 3 * (c + 12 * o) + 3;  // halo'd row of tap dp = 0
+#pragma unroll
+    for (int dp = 0; dp < 3; ++dp) {
+#pragma unroll
+      for (int dt = 0; dt < 3; ++dt) {
+        const long long q = (((long long)b * (a.P + 6) + row0 + dp) * a.Wd + t + 2 + dt) * 8;  // column (t + dt - 1) + 3
+        const uint4 hv = __ldg(reinterpret_cast<const uint4*>(a.in_hi + q));
+        const uint4 lv = __ldg(reinterpret_cast<const uint4*>(a.in_lo + q));
+        const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w}, lw[4] = {lv.x, lv.y, lv.z, lv.w};
+        float x[8];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[e]));
+          const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lw[e]));
+          x[2 * e] = hf.x + lf.x, x[2 * e + 1] = hf.y + lf.y;
+        }
+        const float* wt = w + (dp * 3 + dt) * 64;
+#pragma unroll
+        for (int ci = 0; ci < 8; ++ci)
+#pragma unroll
+          for (int co = 0; co < 8; ++co) acc[co] = fmaf(wt[ci * 8 + co], x[ci], acc[co]);
+      }
+    }
+#pragma unroll
+    for (int co = 0; co < 8; ++co) best[co] = fmaxf(best[co], leaky_f(fmaf(acc[co], sc[co], sh[co])));
+  }
+#pragma unroll
+  for (int co = 0; co < 8; ++co) a.out[(((long long)b * a.C_total + a.coff + co) * 12 + c) * a.T + t] = best[co];
+}
+
+}  // namespace ake

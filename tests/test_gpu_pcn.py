@@ -175,3 +175,32 @@ def test_decode_matches_oracle():
     assert torch.equal(ids[1].cpu().long(), want[1]) and torch.equal(ids[2].cpu().long(), want[2])
     dup = pcn_port.key_signature_map()[[12]] * 0.9 + 0.05   # rows 0 and 12 are identical -> argmax returns 0
     assert int(ake.decode(dup.cuda(), tonic[:1].cuda())[0][0]) == 0
+
+
+def test_tensor_core_and_cuda_core_paths_agree(monkeypatch, fwd_golden):
+    """The tcgen05 path (fp16 hi/lo split operands) and the fp32 CUDA-core path are two implementations of the
+    same layers: both must sit within tolerance of the reference, and of each other."""
+    g = fwd_golden
+    x = torch.from_numpy(g["mel"])[:, None].cuda()
+    seq = torch.from_numpy(g["seq_length"]).cuda()
+    fast = _golden_net(True)
+    monkeypatch.setenv("AKE_DISABLE_UMMA", "1")
+    slow = _golden_net(True)
+    monkeypatch.delenv("AKE_DISABLE_UMMA")
+    lib = _lib.lib()
+    _lib.profile_enable(True)
+    out_fast = fast(x, seq)
+    tags_fast = set(_lib.profile_collect())
+    out_slow = slow(x, seq)
+    tags_slow = set(_lib.profile_collect())
+    _lib.profile_enable(False)
+    assert "pcn.prep" in tags_fast and "pcn.prep" not in tags_slow   # the two plans really took different paths
+    for a, b, name in zip(out_fast, out_slow, ("key", "tonic", "genre")):
+        assert (a - b).abs().max().item() <= 2e-5
+        _close(a, g[f"genre.eval.seq.{name}"])
+        _close(b, g[f"genre.eval.seq.{name}"])
+    # long clips exercise the time-tiled variant of the tensor-core kernel (T > 160 frames per tile)
+    torch.manual_seed(5)
+    xl = (torch.rand(2, 1, 288, 401) * 3).cuda()
+    for a, b in zip(fast(xl, None), slow(xl, None)):
+        assert (a - b).abs().max().item() <= 2e-5
