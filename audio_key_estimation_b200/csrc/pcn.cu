@@ -123,6 +123,10 @@ struct ake_pcn {
   bool umma = false;
   __half* d_wimg = nullptr;         // one kP2PWBytes image per Pitch2Pitch conv, in conv-id order of `umma_convs`
   std::vector<int> umma_convs;
+  __half* d_wimg_pc = nullptr;      // equivariant convs of the layer-1 PitchClass2PitchClass stack (98,304 B each)
+  __half* d_wimg_heads = nullptr;   // first conv of the tonic and key heads, fused along N (344,064 B)
+  float* d_ss_heads = nullptr;      // [scale 64 | shift 64] of that fused conv (tonic channels first)
+  bool umma_heads = false;
   std::map<std::string, std::pair<const float*, int64_t>> taps;
 };
 
@@ -253,6 +257,7 @@ static void build_plan(ake_pcn* p) {
   }
   build_head("tonic_classifier", true, p->tonic_head);
   build_head("key_classifier", true, p->key_head);
+  p->umma_heads = p->umma && c.head_layers == 2;  // 16 -> 32 (BN, act) -> 1: the first conv runs on tensor cores
   if (c.genre) build_head("genre_classifier", false, p->genre_head);
 }
 
@@ -325,6 +330,9 @@ struct Fwd {
   Arena arena;
   const int* seq_len;
   float* bn_stats_out;
+  __half* umma_pc_hi = nullptr;  // tensor-core path: final pitch-class features as chunk planes [B][2][23][T/2][8]
+  __half* umma_pc_lo = nullptr;
+  bool umma_pc_ready = false;
   double* d_stats = nullptr;  // train: per conv channel (sum, sumsq)
   float* d_ss_train = nullptr;
 
@@ -458,10 +466,12 @@ void Fwd::run(const float* mel, float* key_out, float* tonic_out, float* genre_o
     } else {
       const bool fast = p->umma && !train && L == 1 && Tn >= 7;
       View p_feat;
-      cat = alloc(lp.prev_pc + lp.out_p, 12, Tn);
-      if (!dry)  // concat [pc, pc2] (models.py:392): previous pc is copied in, the pool_semi result is written beside it
-        AKE_CUDA(cudaMemcpy2DAsync(cat.p, sizeof(float) * cat.bstride(), pc.p, sizeof(float) * pc.bstride(),
-                                   sizeof(float) * pc.bstride(), B, cudaMemcpyDeviceToDevice, st));
+      if (!fast) {
+        cat = alloc(lp.prev_pc + lp.out_p, 12, Tn);
+        if (!dry)  // concat [pc, pc2] (models.py:392): previous pc is copied in, the pool_semi result is written beside it
+          AKE_CUDA(cudaMemcpy2DAsync(cat.p, sizeof(float) * cat.bstride(), pc.p, sizeof(float) * pc.bstride(),
+                                     sizeof(float) * pc.bstride(), B, cudaMemcpyDeviceToDevice, st));
+      }
       if (fast) {
         // ---- tensor-core path: chunk-plane activations (pcn_umma.cuh), up_sixth fused into the first operand build
         const int Wd = Tn + 6;
@@ -498,13 +508,64 @@ void Fwd::run(const float* mel, float* key_out, float* tonic_out, float* genre_o
           cur ^= 1;
         }
         const Conv& cs = p->convs[lp.sem];
+        // concat [pc, pool_semi(p)] as 16-channel chunk planes (wrap rows + zero halo columns) for the equivariant convs
+        const size_t eq_halves = (size_t)B * 2 * 23 * Wd * 8;
+        __half* e[3][2];
+        for (int i = 0; i < 3; ++i)
+          for (int j = 0; j < 2; ++j) e[i][j] = arena.take<__half>(eq_halves);
         if (!dry) {
           ProfScope prof("pcn.semitone", st);
-          SemiArgs sa{x[cur][0], x[cur][1], p->d_params + cs.w_off, scale_of(cs, false), shift_of(cs, false), cat.p, B, P, Tn, Wd,
-                      cat.C, lp.prev_pc};
-          semitone_pool_chunks_kernel<<<dim3(cdiv(Tn, 128), 12, B), 128, 0, st>>>(sa);
+          SemiArgs sa{x[cur][0], x[cur][1], p->d_params + cs.w_off, scale_of(cs, false), shift_of(cs, false), pc.p,
+                      e[0][0], e[0][1], B, P, Tn, Wd};
+          semitone_pool_chunks_kernel<<<dim3(cdiv(Wd, 128), 12, B), 128, 0, st>>>(sa);
           AKE_LAUNCHED();
         }
+        // PitchClass2PitchClass stack (models.py:393) on tensor cores; MaxPool2d((1,2)) fused into the last conv
+        const int Th = Tn / 2;
+        View pooled = alloc(lp.out_pc, 12, Th);
+        umma_pc_hi = arena.take<__half>((size_t)B * 2 * 23 * Th * 8);
+        umma_pc_lo = arena.take<__half>((size_t)B * 2 * 23 * Th * 8);
+        if (!dry) {
+          ProfScope prof("pcn.equiv", st);
+          // the "same" padding of the following conv = zero halo columns of its input planes
+          for (int i = 1; i < 3; ++i)
+            for (int j = 0; j < 2; ++j) AKE_CUDA(cudaMemsetAsync(e[i][j], 0, sizeof(__half) * eq_halves, st));
+          const int n_tt = cdiv(Tn, 32), TBe = (cdiv(Tn, n_tt) + 1) / 2 * 2;
+          const size_t smem_e = equiv_smem_bytes(TBe + 6);
+          static size_t conf0 = 0, conf1 = 0;
+          if (smem_e > conf0) {
+            AKE_CUDA(cudaFuncSetAttribute(equiv_umma_kernel<16, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e));
+            conf0 = smem_e;
+          }
+          if (smem_e > conf1) {
+            AKE_CUDA(cudaFuncSetAttribute(equiv_umma_kernel<16, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e));
+            conf1 = smem_e;
+          }
+          constexpr size_t kPcImg = 48 * 2048;
+          int ce = 0;
+          for (size_t i = 0; i < lp.pc2pc.size(); ++i) {
+            const Conv& c = p->convs[lp.pc2pc[i]];
+            const bool last = i + 1 == lp.pc2pc.size();
+            const int nxt = last ? ce : (ce == 1 ? 2 : 1);
+            EquivArgs ea{};
+            ea.in_hi = e[ce][0], ea.in_lo = e[ce][1], ea.Wd_in = Wd, ea.T_out = Tn, ea.TB = TBe, ea.n_ttiles = cdiv(Tn, TBe);
+            ea.wimg = reinterpret_cast<const __half*>(reinterpret_cast<const uint8_t*>(p->d_wimg_pc) + i * kPcImg);
+            ea.scale = scale_of(c, false), ea.shift = shift_of(c, false);
+            dim3 grid(ea.n_ttiles, B);
+            if (!last) {
+              ea.out_hi = e[nxt][0], ea.out_lo = e[nxt][1], ea.Wd_out = Wd, ea.col_off = 3;
+              equiv_umma_kernel<16, 2, 0><<<grid, 192, smem_e, st>>>(ea);
+            } else {
+              ea.out_hi = umma_pc_hi, ea.out_lo = umma_pc_lo, ea.Wd_out = Th, ea.col_off = 0, ea.out_f32 = pooled.p;
+              equiv_umma_kernel<16, 2, 1><<<grid, 192, smem_e, st>>>(ea);
+            }
+            AKE_LAUNCHED();
+            ce = nxt;
+          }
+        }
+        pc = pooled;
+        Tn = Th;
+        umma_pc_ready = true;
       } else {
       // up_sixth ConvTranspose + BN + act (models.py:372-374); tiled to all pitches by the conv loader (:378)
       const Conv& cu = p->convs[lp.up];
@@ -535,8 +596,8 @@ void Fwd::run(const float* mel, float* key_out, float* tonic_out, float* genre_o
       }
       p_feat = *src;
       semitone_pool(L, p_feat, cat, lp.prev_pc);
-      }
       tap(ln + ".cat", cat);
+      }
       // time pooling of the pitch-wise features is only needed if another layer follows (models.py:395)
       if (L + 1 < cfg.num_layers) {
         View pp = alloc(lp.out_p, P, Tn / 2);
@@ -547,6 +608,7 @@ void Fwd::run(const float* mel, float* key_out, float* tonic_out, float* genre_o
         p_in = pp;
       }
     }
+    if (umma_pc_ready && L == 1) continue;
     // PitchClass2PitchClass stack (models.py:369 / 393), zero padding in time
     View a = alloc(lp.out_pc, 12, Tn), b2 = alloc(lp.out_pc, 12, Tn);
     View* src = &cat;
@@ -602,8 +664,41 @@ void Fwd::run(const float* mel, float* key_out, float* tonic_out, float* genre_o
     tap(name, x);
     return x;
   };
-  View tonic_f = head(p->tonic_head, true, "tonic_frames");
-  View key_f = head(p->key_head, true, "key_frames");
+  View tonic_f, key_f;
+  if (umma_pc_ready && p->umma_heads && Tn >= 13) {
+    // first conv of both heads in one tensor-core pass (16 -> 32 | 32, valid in time), then the 32 -> 1 convs
+    const int T1 = Tn - (k - 1);
+    View th = alloc(32, 12, T1), kh = alloc(32, 12, T1);
+    if (!dry) {
+      ProfScope prof("pcn.equiv", st);
+      const int n_tt = cdiv(T1, 32), TBe = (cdiv(T1, n_tt) + 1) / 2 * 2;
+      const size_t smem_e = equiv_smem_bytes(TBe + 6);
+      static size_t conf = 0;
+      if (smem_e > conf) {
+        AKE_CUDA(cudaFuncSetAttribute(equiv_umma_kernel<64, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e));
+        conf = smem_e;
+      }
+      EquivArgs ea{};
+      ea.in_hi = umma_pc_hi, ea.in_lo = umma_pc_lo, ea.Wd_in = Tn, ea.T_out = T1, ea.TB = TBe, ea.n_ttiles = cdiv(T1, TBe);
+      ea.wimg = p->d_wimg_heads, ea.scale = p->d_ss_heads, ea.shift = p->d_ss_heads + 64;
+      ea.out_f32 = th.p, ea.out_f32_b = kh.p;
+      equiv_umma_kernel<64, 1, 2><<<dim3(ea.n_ttiles, B), 192, smem_e, st>>>(ea);
+      AKE_LAUNCHED();
+    }
+    auto tail = [&](const std::vector<int>& ids, const View& h1, const char* name) -> View {
+      const Conv& c = p->convs[ids[1]];
+      ConvGeom g = g_equiv(T1, false);
+      View y = alloc(c.Cout, 12, g.T_out);
+      conv(ids[1], h1, nullptr, g, y, 0, false);
+      tap(name, y);
+      return y;
+    };
+    tonic_f = tail(p->tonic_head, th, "tonic_frames");
+    key_f = tail(p->key_head, kh, "key_frames");
+  } else {
+    tonic_f = head(p->tonic_head, true, "tonic_frames");
+    key_f = head(p->key_head, true, "key_frames");
+  }
   View genre_f;
   if (cfg.genre) genre_f = head(p->genre_head, false, "genre_frames");
   if (tonic_f.T <= 0) fail(AKE_ERR_INVALID, "T=%d is too short: the heads need more than %d frames after pooling", T,
@@ -649,6 +744,31 @@ static void upload_params(ake_pcn* p, const float* flat_dev, int64_t n, cudaStre
       p2p_pack_weights_kernel<<<14, 256, 0, st>>>(p->d_params + c.w_off, c.Cout, c.Cin,
                                                    reinterpret_cast<__half*>(reinterpret_cast<uint8_t*>(p->d_wimg) + i * kP2PWBytes));
       AKE_LAUNCHED();
+    }
+    const std::vector<int>& pcs = p->layers[1].pc2pc;
+    constexpr size_t kPcImg = 48 * 2048;
+    if (!p->d_wimg_pc) AKE_CUDA(cudaMalloc(&p->d_wimg_pc, kPcImg * pcs.size()));
+    for (size_t i = 0; i < pcs.size(); ++i) {
+      const Conv& c = p->convs[pcs[i]];
+      equiv_pack_weights_kernel<<<96, 256, 0, st>>>(p->d_params + c.w_off, p->d_params + c.w_off, 16, 16, c.Cin, 2,
+                                                     reinterpret_cast<__half*>(reinterpret_cast<uint8_t*>(p->d_wimg_pc) + i * kPcImg));
+      AKE_LAUNCHED();
+    }
+    if (p->umma_heads) {
+      const Conv& ct = p->convs[p->tonic_head[0]];
+      const Conv& ck = p->convs[p->key_head[0]];
+      if (!p->d_wimg_heads) {
+        AKE_CUDA(cudaMalloc(&p->d_wimg_heads, (size_t)84 * 4096));
+        AKE_CUDA(cudaMalloc(&p->d_ss_heads, sizeof(float) * 128));
+      }
+      equiv_pack_weights_kernel<<<168, 256, 0, st>>>(p->d_params + ct.w_off, p->d_params + ck.w_off, 32, 64, 16, 1, p->d_wimg_heads);
+      AKE_LAUNCHED();
+      const Conv* hc[2] = {&ct, &ck};
+      for (int h = 0; h < 2; ++h) {
+        AKE_CUDA(cudaMemcpyAsync(p->d_ss_heads + 32 * h, p->d_ss_eval + hc[h]->ss_off, sizeof(float) * 32, cudaMemcpyDeviceToDevice, st));
+        AKE_CUDA(cudaMemcpyAsync(p->d_ss_heads + 64 + 32 * h, p->d_ss_eval + p->n_ss + hc[h]->ss_off, sizeof(float) * 32,
+                                 cudaMemcpyDeviceToDevice, st));
+      }
     }
   }
   p->has_params = true;
@@ -735,6 +855,9 @@ void ake_pcn_destroy(ake_pcn* p) {
   cudaFree(p->d_ss_eval);
   cudaFree(p->d_ss_raw);
   cudaFree(p->d_wimg);
+  cudaFree(p->d_wimg_pc);
+  cudaFree(p->d_wimg_heads);
+  cudaFree(p->d_ss_heads);
   delete p;
 }
 

@@ -291,15 +291,19 @@ __global__ void __launch_bounds__(160) p2p_umma_kernel(const P2PArgs a) {
 
 // ---- pool_semi conv (3x3, stride (3,1), time-circular) + BN + LeakyReLU + octave max pool, from chunk planes ------
 // models.py:337-339, 386-389: s[co, j, t] = act(bn(sum_{ci,dp<3,dt<3} W x[ci, 3j+dp, (t+dt-1) mod T])), pc[co,c,t] = max_o s[co, c+12o, t].
-// One thread per (c, t); writes channels [coff, coff+8) of the (B, C_total, 12, T) fp32 concat tensor (models.py:392).
+// One thread per (c, column).  The result is concatenated behind the previous pitch-class features (models.py:392) and
+// written as 16-channel chunk planes [B][2][23][T+6][8] for the equivariant convolutions: channels [pc (4) | pooled (8) |
+// zero (4)], wrap rows 12..22 = rows 0..10 (models.py:27-28), zero halo columns (the "same" padding of models.py:45-47).
 struct SemiArgs {
   const __half* in_hi;
   const __half* in_lo;  // [B][P+6][Wd][8]
   const float* w;       // (8 co, 8 ci, 3, 3)
   const float* scale;
   const float* shift;
-  float* out;           // (B, C_total, 12, T)
-  int B, P, T, Wd, C_total, coff;
+  const float* pc_prev; // (B, 4, 12, T) fp32
+  __half* out_hi;
+  __half* out_lo;       // [B][2][23][Wd][8]
+  int B, P, T, Wd;
 };
 
 __global__ void __launch_bounds__(128) semitone_pool_chunks_kernel(const SemiArgs a) {
@@ -311,45 +315,347 @@ __global__ void __launch_bounds__(128) semitone_pool_chunks_kernel(const SemiArg
   }
   if (threadIdx.x < 8) sc[threadIdx.x] = a.scale[threadIdx.x], sh[threadIdx.x] = a.shift[threadIdx.x];
   __syncthreads();
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
   const int c = blockIdx.y, b = blockIdx.z;
-  if (t >= a.T) return;
-  const int n_oct = a.P / 36;
-  float best[8];
+  if (col >= a.Wd) return;
+  const int t = col - 3;
+  float g0[8], g1[8];
 #pragma unroll
-  for (int co = 0; co < 8; ++co) best[co] = -INFINITY;
-  for (int o = 0; o < n_oct; ++o) {
-    float acc[8];
+  for (int e = 0; e < 8; ++e) g0[e] = 0.f, g1[e] = 0.f;
+  if (t >= 0 && t < a.T) {
+    const int n_oct = a.P / 36;
+    float best[8];
 #pragma unroll
-    for (int co = 0; co < 8; ++co) acc[co] = 0.f;
-    const int row0 = 3 * (c + 12 * o) + 3;  // halo'd row of tap dp = 0
+    for (int co = 0; co < 8; ++co) best[co] = -INFINITY;
+    for (int o = 0; o < n_oct; ++o) {
+      float acc[8];
 #pragma unroll
-    for (int dp = 0; dp < 3; ++dp) {
+      for (int co = 0; co < 8; ++co) acc[co] = 0.f;
+      const int row0 = 3 * (c + 12 * o) + 3;  // halo'd row of tap dp = 0
 #pragma unroll
-      for (int dt = 0; dt < 3; ++dt) {
-        const long long q = (((long long)b * (a.P + 6) + row0 + dp) * a.Wd + t + 2 + dt) * 8;  // column (t + dt - 1) + 3
-        const uint4 hv = __ldg(reinterpret_cast<const uint4*>(a.in_hi + q));
-        const uint4 lv = __ldg(reinterpret_cast<const uint4*>(a.in_lo + q));
-        const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w}, lw[4] = {lv.x, lv.y, lv.z, lv.w};
-        float x[8];
+      for (int dp = 0; dp < 3; ++dp) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[e]));
-          const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lw[e]));
-          x[2 * e] = hf.x + lf.x, x[2 * e + 1] = hf.y + lf.y;
+        for (int dt = 0; dt < 3; ++dt) {
+          const long long q = (((long long)b * (a.P + 6) + row0 + dp) * a.Wd + t + 2 + dt) * 8;  // column (t + dt - 1) + 3
+          const uint4 hv = __ldg(reinterpret_cast<const uint4*>(a.in_hi + q));
+          const uint4 lv = __ldg(reinterpret_cast<const uint4*>(a.in_lo + q));
+          const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w}, lw[4] = {lv.x, lv.y, lv.z, lv.w};
+          float x[8];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[e]));
+            const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lw[e]));
+            x[2 * e] = hf.x + lf.x, x[2 * e + 1] = hf.y + lf.y;
+          }
+          const float* wt = w + (dp * 3 + dt) * 64;
+#pragma unroll
+          for (int ci = 0; ci < 8; ++ci)
+#pragma unroll
+            for (int co = 0; co < 8; ++co) acc[co] = fmaf(wt[ci * 8 + co], x[ci], acc[co]);
         }
-        const float* wt = w + (dp * 3 + dt) * 64;
-#pragma unroll
-        for (int ci = 0; ci < 8; ++ci)
-#pragma unroll
-          for (int co = 0; co < 8; ++co) acc[co] = fmaf(wt[ci * 8 + co], x[ci], acc[co]);
       }
+#pragma unroll
+      for (int co = 0; co < 8; ++co) best[co] = fmaxf(best[co], leaky_f(fmaf(acc[co], sc[co], sh[co])));
     }
 #pragma unroll
-    for (int co = 0; co < 8; ++co) best[co] = fmaxf(best[co], leaky_f(fmaf(acc[co], sc[co], sh[co])));
-  }
+    for (int ci = 0; ci < 4; ++ci) g0[ci] = __ldg(a.pc_prev + (((long long)b * 4 + ci) * 12 + c) * a.T + t);
 #pragma unroll
-  for (int co = 0; co < 8; ++co) a.out[(((long long)b * a.C_total + a.coff + co) * 12 + c) * a.T + t] = best[co];
+    for (int e = 0; e < 4; ++e) g0[4 + e] = best[e], g1[e] = best[4 + e];
+  }
+  const long long q0 = ((((long long)b * 2 + 0) * 23 + c) * a.Wd + col) * 8, q1 = ((((long long)b * 2 + 1) * 23 + c) * a.Wd + col) * 8;
+  store_split8(a.out_hi + q0, a.out_lo + q0, g0);
+  store_split8(a.out_hi + q1, a.out_lo + q1, g1);
+  if (c < 11) {
+    const long long w0 = q0 + (long long)12 * a.Wd * 8, w1 = q1 + (long long)12 * a.Wd * 8;
+    store_split8(a.out_hi + w0, a.out_lo + w0, g0);
+    store_split8(a.out_hi + w1, a.out_lo + w1, g1);
+  }
+}
+
+// ---- equivariant pitch-class convolution (models.py:22-51) on tensor cores -----------------------------------------
+//   out[co, c, t] = sum_{ci<16, dp<12, dt<7} W[co,ci,dp,dt] x[ci, (c+dp) mod 12, t + dt - pad]
+// Input: 16-channel chunk planes [B][2 groups][23 rows][Wd][8] (rows 12..22 wrap, zero halo columns for "same" layers).
+// K = 16 = the two channel groups of ONE position (LBO = group plane), anchors a = c*Wt + tl as in the 7x7 kernel.
+//   PH = 2 (NCO = 16, the PitchClass2PitchClass stack): two time taps per start as N-phases, out[a] = D_0[a] + D_1[a+1];
+//   PH = 1 (NCO = 64, both classifier heads' first conv in one pass): one tap per start.
+// The weights (84 taps x 16 ci x NCO x {hi,lo}) do not fit beside the tile: they stream through a 2 x 16 KB ring.
+// EPI 0: BN + LeakyReLU -> chunk planes (next layer);  EPI 1: + MaxPool2d((1,2)) (models.py:349-350, 396) -> chunk planes
+// without halos + fp32 (B,16,12,T/2);  EPI 2: BN + LeakyReLU -> fp32 (B,32,12,T_out) for each head.
+struct EquivArgs {
+  const __half* in_hi;
+  const __half* in_lo;
+  int Wd_in, T_out, TB, n_ttiles;
+  const __half* wimg;
+  const float* scale;
+  const float* shift;
+  __half* out_hi;
+  __half* out_lo;
+  int Wd_out, col_off;
+  float* out_f32;
+  float* out_f32_b;
+};
+
+constexpr uint32_t kEqStageBytes = 16384;
+constexpr int kEqWStages = 2;
+
+__host__ __device__ inline uint32_t equiv_group_positions(int Wt) { return (uint32_t)(23 * Wt + 136); }
+__host__ __device__ inline size_t equiv_smem_bytes(int Wt) {
+  return (size_t)4 * equiv_group_positions(Wt) * 16 + kEqWStages * kEqStageBytes + 2 * 4 * 128 * 16;
+}
+
+// Weight image: [start j][chunk g 2][n N1][ci 8] fp16; N1 = 2 * NCO * PH: rows [0, N1/2) = W_hi of (phase f = n / NCO,
+// co = n % NCO), rows [N1/2, N1) = W_lo.  PH = 2: j = dp*4 + s/2, time tap dt = s + f (zero for dt = 7); PH = 1: j = dp*7 + dt.
+// Output channels [0, split) come from w0 (Cout0 = split), [split, NCO) from w1.
+__global__ void equiv_pack_weights_kernel(const float* __restrict__ w0, const float* __restrict__ w1, int split, int NCO, int Cin, int PH,
+                                          __half* __restrict__ img) {
+  const int N2 = NCO * PH, NS = 12 * (PH == 2 ? 4 : 7);
+  const int n_items = NS * 2 * N2 * 8;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_items; i += gridDim.x * blockDim.x) {
+    const int e = i % 8, n = (i / 8) % N2, g = (i / (8 * N2)) % 2, j = i / (16 * N2);
+    const int f = n / NCO, co = n % NCO, ci = g * 8 + e;
+    const int dp = PH == 2 ? j / 4 : j / 7, dt = PH == 2 ? 2 * (j % 4) + f : j % 7;
+    float v = 0.f;
+    if (dt < 7 && ci < Cin) {
+      const float* w = co < split ? w0 : w1;
+      const int cc = co < split ? co : co - split;
+      v = w[(((long long)cc * Cin + ci) * 12 + dp) * 7 + dt] * kWScale;
+    }
+    const __half hi = __float2half_rn(v);
+    const __half lo = __float2half_rn(v - __half2float(hi));
+    const long long base = ((long long)(j * 2 + g) * 2 * N2) * 8;
+    img[base + (long long)n * 8 + e] = hi;
+    img[base + (long long)(N2 + n) * 8 + e] = lo;
+  }
+}
+
+template <int NCO, int PH, int EPI>
+__global__ void __launch_bounds__(192) equiv_umma_kernel(const EquivArgs a) {
+  using namespace umma;
+  constexpr int N2 = NCO * PH, N1 = 2 * N2;
+  constexpr int ACC = N1;                        // TMEM columns per accumulator (one 128-anchor block)
+  constexpr int NACC = ACC <= 64 ? 2 : 1;        // blocks sharing one pass over the weight stream
+  constexpr int NS = 12 * (PH == 2 ? 4 : 7);     // MMA starts per block
+  constexpr uint32_t START_BYTES = 32u * N1;
+  constexpr int SPS = kEqStageBytes / START_BYTES;
+  constexpr int NSTG = NS / SPS;
+  static_assert(NS % SPS == 0, "stages must tile the tap list");
+  constexpr int STRIDE = PH == 2 ? (EPI == 1 ? 126 : 127) : 128;
+
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t tile_bar, w_full[kEqWStages], w_empty[kEqWStages], acc_full[2], acc_empty[2];
+  __shared__ uint32_t tmem_slot;
+  __shared__ float s_scale[NCO], s_shift[NCO];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.y, t0 = blockIdx.x * a.TB;
+  const int TBv = min(a.TB, a.T_out - t0);
+  const int Wt = a.TB + 6;
+  const int cols_in = min(Wt, a.Wd_in - t0);
+  const uint32_t GPpos = equiv_group_positions(Wt), GP = GPpos * 16;
+  const int n_anchor = 12 * Wt;
+  const int n_mb = (n_anchor + STRIDE - 1) / STRIDE, n_grp = (n_mb + NACC - 1) / NACC;
+  uint8_t* s_hi = smem;             // [g 2][GP]
+  uint8_t* s_lo = smem + 2 * GP;
+  uint8_t* s_w = smem + 4 * GP;
+  float4* s_ex = reinterpret_cast<float4*>(smem + 4 * GP + kEqWStages * kEqStageBytes);  // 2 x [4][128]
+
+  if (warp == 4) tmem_alloc(&tmem_slot, 256);
+  if (tid == 0) {
+    mbar_init(&tile_bar, 1);
+    for (int s = 0; s < kEqWStages; ++s) mbar_init(&w_full[s], 1), mbar_init(&w_empty[s], 1);
+    mbar_init(&acc_full[0], 1), mbar_init(&acc_full[1], 1);
+    mbar_init(&acc_empty[0], 128), mbar_init(&acc_empty[1], 128);
+    mbar_init_fence();
+  }
+  for (int i = tid; i < NCO; i += blockDim.x) s_scale[i] = a.scale[i] * (1.f / kWScale), s_shift[i] = a.shift[i];
+  {
+    // zero what the bulk copies leave untouched (see p2p_umma_kernel)
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    const int gap = Wt - cols_in;
+    for (int pl = 0; pl < 4; ++pl) {
+      uint4* base = reinterpret_cast<uint4*>(smem + (size_t)pl * GP);
+      for (uint32_t i = 23u * Wt + tid; i < GPpos; i += blockDim.x) base[i] = z;
+      if (gap > 0)
+        for (int i = tid; i < 23 * gap; i += blockDim.x) base[(uint32_t)(i / gap) * Wt + cols_in + i % gap] = z;
+    }
+    fence_proxy_async();
+  }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+
+  if (warp == 4) {
+    // ------------------------------------------------------------ loader: activation tile, then the weight stream
+    const uint32_t row_bytes = (uint32_t)cols_in * 16;
+    if (lane == 0) mbar_arrive_expect_tx(&tile_bar, 4u * 23u * row_bytes);
+    __syncwarp();
+    for (int idx = lane; idx < 46; idx += 32) {
+      const int g = idx / 23, r = idx - g * 23;
+      const long long src = ((((long long)b * 2 + g) * 23 + r) * a.Wd_in + t0) * 8;
+      bulk_g2s(s_hi + (size_t)g * GP + (size_t)r * Wt * 16, a.in_hi + src, row_bytes, &tile_bar);
+      bulk_g2s(s_lo + (size_t)g * GP + (size_t)r * Wt * 16, a.in_lo + src, row_bytes, &tile_bar);
+    }
+    if (lane == 0) {
+      const int n_it = n_grp * NSTG;
+      for (int it = 0; it < n_it; ++it) {
+        const int s = it % kEqWStages;
+        mbar_wait(&w_empty[s], ((it / kEqWStages) & 1) ^ 1);
+        mbar_arrive_expect_tx(&w_full[s], kEqStageBytes);
+        bulk_g2s(s_w + (size_t)s * kEqStageBytes, reinterpret_cast<const uint8_t*>(a.wimg) + (size_t)(it % NSTG) * kEqStageBytes,
+                 kEqStageBytes, &w_full[s]);
+      }
+    }
+  } else if (warp == 5) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      mbar_wait(&tile_bar, 0);
+      const uint64_t A_DESC = desc_hi(GP);  // chunk 1 = the other channel group of the same position
+      constexpr uint64_t B_DESC = desc_hi(N1 * 16);
+      constexpr uint32_t IDESC1 = idesc_f16(N1), IDESC2 = idesc_f16(N2);
+      const uint32_t hi0 = smem_u32(s_hi), lo0 = smem_u32(s_lo), w0 = smem_u32(s_w);
+      int it = 0;
+      for (int grp = 0; grp < n_grp; ++grp) {
+        const int gb = grp & 1;
+        mbar_wait(&acc_empty[gb], ((grp >> 1) & 1) ^ 1);
+        fence_after_sync();
+        for (int stg = 0; stg < NSTG; ++stg, ++it) {
+          const int s = it % kEqWStages;
+          mbar_wait(&w_full[s], (it / kEqWStages) & 1);
+          fence_after_sync();
+#pragma unroll
+          for (int u = 0; u < SPS; ++u) {
+            const int j = stg * SPS + u;
+            const int dp = PH == 2 ? j / 4 : j / 7, sft = PH == 2 ? 2 * (j % 4) : j % 7;
+            const uint64_t bd = make_desc(B_DESC, w0 + s * kEqStageBytes + u * START_BYTES);
+#pragma unroll
+            for (int acc = 0; acc < NACC; ++acc) {
+              const int m = grp * NACC + acc;
+              if (m < n_mb) {
+                const uint32_t off = (uint32_t)(m * STRIDE + dp * Wt + sft) * 16;
+                const uint32_t d = tmem + gb * (NACC * ACC) + acc * ACC;
+                mma_f16(d, make_desc(A_DESC, hi0 + off), bd, IDESC1, j ? 1u : 0u);
+                mma_f16(d, make_desc(A_DESC, lo0 + off), bd, IDESC2, 1u);
+              }
+            }
+          }
+          commit(&w_empty[s]);
+        }
+        commit(&acc_full[gb]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue: thread = TMEM lane = anchor row
+    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+    float4* exA = s_ex;
+    float4* exB = s_ex + 4 * 128;
+    for (int grp = 0; grp < n_grp; ++grp) {
+      const int gb = grp & 1;
+      mbar_wait(&acc_full[gb], (grp >> 1) & 1);
+      fence_after_sync();
+      for (int acc = 0; acc < NACC; ++acc) {
+        const int m = grp * NACC + acc;
+        if (m >= n_mb) break;
+        const uint32_t d = lane_base + gb * (NACC * ACC) + acc * ACC;
+        const int anchor = m * STRIDE + tid;
+        const int c = anchor / Wt, tl = anchor - c * Wt;
+        const int t = t0 + tl;
+        if constexpr (PH == 2) {
+          // NCO == 16: D_0 = cols [0,16) + [32,48), D_1 = cols [16,32) + [48,64)
+          float o[16], d1[16];
+          {
+            float u[16], w[16];
+            tmem_ld16(d, u), tmem_ld16(d + 32, w);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) o[j] = u[j] + w[j];
+            tmem_ld16(d + 16, u), tmem_ld16(d + 48, w);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) d1[j] = u[j] + w[j];
+          }
+          float4* ex = (EPI == 0) ? (m & 1 ? exB : exA) : exA;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) ex[q * 128 + tid] = make_float4(d1[4 * q], d1[4 * q + 1], d1[4 * q + 2], d1[4 * q + 3]);
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (tid < 127) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float4 x = ex[q * 128 + tid + 1];
+              o[4 * q] += x.x, o[4 * q + 1] += x.y, o[4 * q + 2] += x.z, o[4 * q + 3] += x.w;
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) o[j] = leaky_f(fmaf(o[j], s_scale[j], s_shift[j]));
+          if constexpr (EPI == 0) {
+            if (tid < STRIDE && anchor < n_anchor && tl < TBv) {
+              float g0[8], g1[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) g0[e] = o[e], g1[e] = o[8 + e];
+              const long long q0 = ((((long long)b * 2 + 0) * 23 + c) * a.Wd_out + t + a.col_off) * 8;
+              const long long q1 = ((((long long)b * 2 + 1) * 23 + c) * a.Wd_out + t + a.col_off) * 8;
+              store_split8(a.out_hi + q0, a.out_lo + q0, g0);
+              store_split8(a.out_hi + q1, a.out_lo + q1, g1);
+              if (c < 11) {
+                const long long wr = (long long)12 * a.Wd_out * 8;
+                store_split8(a.out_hi + q0 + wr, a.out_lo + q0 + wr, g0);
+                store_split8(a.out_hi + q1 + wr, a.out_lo + q1 + wr, g1);
+              }
+            }
+          } else {
+            // fused MaxPool2d((1,2)): frames (2u, 2u+1) sit in adjacent rows (t0 and TB are even)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) exB[q * 128 + tid] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            const int Th = a.T_out / 2;
+            if (tid < STRIDE && anchor < n_anchor && tl < TBv && (t & 1) == 0 && (t >> 1) < Th) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float4 x = exB[q * 128 + tid + 1];
+                o[4 * q] = fmaxf(o[4 * q], x.x), o[4 * q + 1] = fmaxf(o[4 * q + 1], x.y);
+                o[4 * q + 2] = fmaxf(o[4 * q + 2], x.z), o[4 * q + 3] = fmaxf(o[4 * q + 3], x.w);
+              }
+              const int uo = t >> 1;
+              float g0[8], g1[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) g0[e] = o[e], g1[e] = o[8 + e];
+              const long long q0 = ((((long long)b * 2 + 0) * 23 + c) * a.Wd_out + uo + a.col_off) * 8;
+              const long long q1 = ((((long long)b * 2 + 1) * 23 + c) * a.Wd_out + uo + a.col_off) * 8;
+              store_split8(a.out_hi + q0, a.out_lo + q0, g0);
+              store_split8(a.out_hi + q1, a.out_lo + q1, g1);
+              if (c < 11) {
+                const long long wr = (long long)12 * a.Wd_out * 8;
+                store_split8(a.out_hi + q0 + wr, a.out_lo + q0 + wr, g0);
+                store_split8(a.out_hi + q1 + wr, a.out_lo + q1 + wr, g1);
+              }
+#pragma unroll
+              for (int j = 0; j < 16; ++j) a.out_f32[(((long long)b * 16 + j) * 12 + c) * Th + uo] = o[j];
+            }
+          }
+        } else {
+          // PH == 1, NCO == 64: out = cols [0,64) + [64,128); heads: channels [0,32) tonic, [32,64) key (EPI 2)
+          const bool valid = anchor < n_anchor && tl < TBv;
+#pragma unroll
+          for (int h = 0; h < NCO / 16; ++h) {
+            float u[16], w[16];
+            tmem_ld16(d + h * 16, u), tmem_ld16(d + N2 + h * 16, w);
+            if (valid) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const int co = h * 16 + j;
+                const float y = leaky_f(fmaf(u[j] + w[j], s_scale[co], s_shift[co]));
+                float* dst = co < 32 ? a.out_f32 : a.out_f32_b;
+                dst[(((long long)b * 32 + (co & 31)) * 12 + c) * a.T_out + t] = y;
+              }
+            }
+          }
+        }
+      }
+      fence_before_sync();
+      mbar_arrive(&acc_empty[gb]);
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem, 256);
 }
 
 }  // namespace ake
