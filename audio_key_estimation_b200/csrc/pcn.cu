@@ -664,7 +664,8 @@ void Fwd::run(const float* mel, float* key_out, float* tonic_out, float* genre_o
     tap(name, x);
     return x;
   };
-  View tonic_f, key_f;
+  View tonic_f, key_f, genre_f;
+  bool heads_done = false;
   if (umma_pc_ready && p->umma_heads && Tn >= 13) {
     // first conv of both heads in one tensor-core pass (16 -> 32 | 32, valid in time), then the 32 -> 1 convs
     const int T1 = Tn - (k - 1);
@@ -685,22 +686,43 @@ void Fwd::run(const float* mel, float* key_out, float* tonic_out, float* genre_o
       equiv_umma_kernel<64, 1, 2><<<dim3(ea.n_ttiles, B), 192, smem_e, st>>>(ea);
       AKE_LAUNCHED();
     }
-    auto tail = [&](const std::vector<int>& ids, const View& h1, const char* name) -> View {
-      const Conv& c = p->convs[ids[1]];
-      ConvGeom g = g_equiv(T1, false);
-      View y = alloc(c.Cout, 12, g.T_out);
-      conv(ids[1], h1, nullptr, g, y, 0, false);
-      tap(name, y);
-      return y;
-    };
-    tonic_f = tail(p->tonic_head, th, "tonic_frames");
-    key_f = tail(p->key_head, kh, "key_frames");
+    // last conv of every head (32 -> 1) in one launch; the genre head's first conv (1 x 7, not equivariant) stays generic
+    View gh;
+    if (cfg.genre) {
+      const Conv& cg = p->convs[p->genre_head[0]];
+      ConvGeom gg{cg.KH, k, 1, 12, 0, 0, 0, 0, 12 - cg.KH + 1, T1};
+      gh = alloc(cg.Cout, gg.rows_out, T1);
+      conv_bn_act(p->genre_head[0], pc, nullptr, gg, gh, 0);
+    }
+    const int Tf = T1 - (k - 1);
+    tonic_f = alloc(1, 12, Tf), key_f = alloc(1, 12, Tf);
+    if (cfg.genre) genre_f = alloc(1, 11, Tf);
+    if (!dry && Tf > 0) {
+      ProfScope prof("pcn.heads", st);
+      HeadTailArgs ha{};
+      const Conv* hc[3] = {&p->convs[p->tonic_head[1]], &p->convs[p->key_head[1]], cfg.genre ? &p->convs[p->genre_head[1]] : nullptr};
+      const float* hx[3] = {th.p, kh.p, gh.p};
+      float* ho[3] = {tonic_f.p, key_f.p, genre_f.p};
+      const int nh = cfg.genre ? 3 : 2;
+      for (int h = 0; h < nh; ++h)
+        ha.x[h] = hx[h], ha.w[h] = p->d_params + hc[h]->w_off, ha.bias[h] = p->d_params + hc[h]->b_off, ha.out[h] = ho[h], ha.KH[h] = hc[h]->KH;
+      ha.T1 = T1, ha.Cin = 32;
+      const size_t smem_h = sizeof(float) * ((size_t)32 * 12 * 8 + (size_t)kHeadCi * 23 * kHeadTP);
+      static size_t conf_h = 0;
+      if (smem_h > conf_h) {
+        AKE_CUDA(cudaFuncSetAttribute(head_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_h));
+        conf_h = smem_h;
+      }
+      head_tail_kernel<<<dim3(B, nh, cdiv(Tf, kHeadTile)), 128, smem_h, st>>>(ha);
+      AKE_LAUNCHED();
+    }
+    tap("tonic_frames", tonic_f), tap("key_frames", key_f);
+    heads_done = true;
   } else {
     tonic_f = head(p->tonic_head, true, "tonic_frames");
     key_f = head(p->key_head, true, "key_frames");
   }
-  View genre_f;
-  if (cfg.genre) genre_f = head(p->genre_head, false, "genre_frames");
+  if (cfg.genre && !heads_done) genre_f = head(p->genre_head, false, "genre_frames");
   if (tonic_f.T <= 0) fail(AKE_ERR_INVALID, "T=%d is too short: the heads need more than %d frames after pooling", T,
                            (k - 1) * cfg.head_layers);
   if (!dry) {

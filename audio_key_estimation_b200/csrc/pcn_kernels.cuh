@@ -194,6 +194,81 @@ __global__ void __launch_bounds__(256) conv_rows_kernel(const ConvArgs a) {
   }
 }
 
+// ---- last convolution of the classifier heads (models.py:716-733): 32 -> 1 channel, valid in time ----------------
+// tonic / key: EquivariantPitchClassConvolutionSimple(32 -> 1, 12 x 7, pitch classes wrap); genre: Conv2d(32, 1, (2, 7))
+// (11 rows, no wrap).  A one-output-channel conv starves the tiled kernel above (no weight reuse across channels), so
+// each thread here owns 8 consecutive frames of one output row and walks (ci, dp) with the frame window in registers.
+// grid (B, heads, time tiles of kHeadTile frames), 128 threads.  No BatchNorm / activation follows (the per-frame
+// logits go to the masked mean).
+struct HeadTailArgs {
+  const float* x[3];     // (B, 32, 12, T1) per head
+  const float* w[3];     // (1, 32, KH, 7)
+  const float* bias[3];  // 1
+  float* out[3];         // (B, 1, rows_out, T1 - 6)
+  int KH[3];
+  int T1, Cin;
+};
+
+constexpr int kHeadCi = 4;     // input channels staged per pass
+constexpr int kHeadTile = 80;  // output frames per block (10 strips of 8)
+constexpr int kHeadTP = 96;    // staged row pitch: tile + 6 taps + strip overhang, multiple of 4
+
+__global__ void __launch_bounds__(128) head_tail_kernel(const HeadTailArgs a) {
+  extern __shared__ __align__(16) float hsm[];
+  const int h = blockIdx.y, b = blockIdx.x;
+  const int KH = a.KH[h], rows_out = 12 - (KH == 12 ? 0 : KH - 1), rows_in = KH == 12 ? 23 : 12;
+  const int T1 = a.T1, Tf = T1 - 6;
+  const int tb = blockIdx.z * kHeadTile;       // first output frame of this tile
+  constexpr int TP = kHeadTP;
+  float* ws = hsm;                             // [Cin][KH][8]
+  float* xs = hsm + a.Cin * KH * 8;            // [kHeadCi][rows_in][TP]
+  for (int i = threadIdx.x; i < a.Cin * KH * 8; i += blockDim.x) {
+    const int dt = i % 8, k = i / 8;
+    ws[i] = dt < 7 ? __ldg(a.w[h] + (long long)k * 7 + dt) : 0.f;
+  }
+  const int strips = (min(kHeadTile, Tf - tb) + 7) / 8;
+  const bool active = threadIdx.x < rows_out * strips;
+  const int c = threadIdx.x / strips, t0 = (threadIdx.x - c * strips) * 8;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  const float* xb = a.x[h] + (long long)b * a.Cin * 12 * T1;
+  for (int c0 = 0; c0 < a.Cin; c0 += kHeadCi) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < kHeadCi * rows_in * TP; i += blockDim.x) {
+      const int t = i % TP, r = (i / TP) % rows_in, ci = i / (TP * rows_in);
+      xs[i] = tb + t < T1 ? __ldg(xb + ((long long)(c0 + ci) * 12 + (r % 12)) * T1 + tb + t) : 0.f;
+    }
+    __syncthreads();
+    if (active) {
+      for (int ci = 0; ci < kHeadCi; ++ci) {
+        for (int dp = 0; dp < KH; ++dp) {
+          const float* xr = xs + (ci * rows_in + c + dp) * TP + t0;
+          float x[16];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 v = *reinterpret_cast<const float4*>(xr + 4 * q);
+            x[4 * q] = v.x, x[4 * q + 1] = v.y, x[4 * q + 2] = v.z, x[4 * q + 3] = v.w;
+          }
+          const float* wr = ws + ((c0 + ci) * KH + dp) * 8;
+          const float4 w0 = *reinterpret_cast<const float4*>(wr), w1 = *reinterpret_cast<const float4*>(wr + 4);
+          const float wv[7] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z};
+#pragma unroll
+          for (int dt = 0; dt < 7; ++dt)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = fmaf(wv[dt], x[j + dt], acc[j]);
+        }
+      }
+    }
+  }
+  if (!active) return;
+  const float bias = __ldg(a.bias[h]);
+  float* dst = a.out[h] + ((long long)b * rows_out + c) * Tf;
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    if (tb + t0 + j < Tf) dst[tb + t0 + j] = acc[j] + bias;
+}
+
 // ---- ConvTranspose2d(C,C,(3,1),stride=(3,1)) (+affine+act): models.py:325-327 ------------------
 // out[b,co,3c+r,t] = act(scale[co] * sum_ci W[ci,co,r] * pc[b,ci,c,t] + shift[co]);  W is (Cin,Cout,3,1).
 __global__ void upsixth_kernel(const float* __restrict__ pc, const float* __restrict__ w,
