@@ -27,8 +27,8 @@ constexpr int kUKB = 64;        // samples of K per pipeline stage (4 MMA k-step
 constexpr int kUStages = 2;
 constexpr float kXScale = 8.f;  // audio is scaled into fp16's comfortable range; the bank by kBankScale
 constexpr float kBankScale = 16.f;
+constexpr float kDecScale = 16.f;  // decimator taps are scaled into fp16's normal range too
 
-__constant__ float c_dec_taps[kHalfTaps];  // h[|j|] * sqrt(2), identical for every plan (kaiser_fast is fixed)
 
 static double bessel_i0(double x) {
   double sum = 1.0, term = 1.0;
@@ -71,6 +71,7 @@ struct ake_cqt {
   float* d_scale = nullptr;
   // tensor-core path: fp16 (hi | lo) image of the bank in the shared-memory operand layout, one block per 64 samples of K
   __half* d_bank_img = nullptr;
+  __half* d_dec_img = nullptr;   // Toeplitz image of the 63-tap decimator (cascade_umma_kernel)
   float* d_scale_umma = nullptr;
   int npad = 0;  // filters per MMA (2*bpo rounded up to 16), 0: tensor-core path not available for this shape
 };
@@ -181,9 +182,24 @@ static void build_cqt(ake_cqt* p) {
 // Device copies are made lazily so that plan creation (and the bank / tap getters) need no GPU.
 static void ensure_device(ake_cqt* p) {
   if (p->d_scale) return;
-  float taps[kHalfTaps];
-  for (int m = 0; m < kHalfTaps; ++m) taps[m] = (float)(p->dec_half[m] * std::sqrt(2.0));  // resample(scale=True): / sqrt(1/2)
-  AKE_CUDA(cudaMemcpyToSymbol(c_dec_taps, taps, sizeof taps));
+  {
+    // Toeplitz operand of the decimator (cascade_umma_kernel): H[n][k] = sqrt(2) h[|k - 2n - 32|], fp16 hi | lo.
+    // (sqrt(2): resample(scale=True) divides by sqrt(ratio).)
+    std::vector<__half> img((size_t)16 * 64 * 8, __float2half(0.f));
+    for (int n = 0; n < 32; ++n)
+      for (int k = 0; k < 128; ++k) {
+        const int m = std::abs(k - 2 * n - 32);
+        if (m >= kHalfTaps) continue;
+        const float v = (float)(p->dec_half[m] * std::sqrt(2.0) * kDecScale);
+        const __half hi = __float2half_rn(v);
+        const __half lo = __float2half_rn(v - __half2float(hi));
+        const size_t c = k / 8, e = k % 8;
+        img[(c * 64 + n) * 8 + e] = hi;
+        img[(c * 64 + 32 + n) * 8 + e] = lo;
+      }
+    AKE_CUDA(cudaMalloc(&p->d_dec_img, sizeof(__half) * img.size()));
+    AKE_CUDA(cudaMemcpy(p->d_dec_img, img.data(), sizeof(__half) * img.size(), cudaMemcpyHostToDevice));
+  }
   AKE_CUDA(cudaMalloc(&p->d_scale, sizeof(float) * p->out_scale.size()));
   AKE_CUDA(cudaMemcpy(p->d_scale, p->out_scale.data(), sizeof(float) * p->out_scale.size(), cudaMemcpyHostToDevice));
   // tensor-core operand image: per 64-sample block of K, 8 chunks x (2*npad) rows x 8 halves; rows [0,npad) = hi, [npad,2npad) = lo
@@ -223,61 +239,226 @@ static int frames_for(const ake_cqt* p, long long n) {
 }
 
 // ------------------------------------------------------------------------------------------ kernels
-// One octave step of the resampling cascade: out[t] = sqrt(2) * sum_{|j|<=31} h[|j|] * in[2t + j], zero extended,
-// for t < floor(n_in/2); librosa pads the result to ceil(n_in/2) samples with a zero.
-// Block: 256 threads x 8 outputs.  The input span is de-interleaved into even/odd phases in shared memory so
-// each thread reads two contiguous windows with 128-bit loads and runs 504 FFMAs from registers.
-constexpr int kDecOutPerThread = 8;
-constexpr int kDecThreads = 256;
-constexpr int kDecOutPerBlock = kDecOutPerThread * kDecThreads;
+// ---- resampling cascade on tensor cores (tcgen05) -------------------------------------------------------------------
+// One octave step is  out[t] = sqrt(2) * sum_{|j|<=31} h[|j|] * in[2t + j]  (zero extended) for t < floor(n_in/2);
+// librosa pads the result to ceil(n_in/2) samples with a zero.  As a GEMM: a "row" is 64 consecutive input samples and
+// yields 32 outputs,
+//     D[r, n] = sum_{k<128} X[r, k] * H[n, k],   X[r, k] = in[base + 64 r + k],   H[n, k] = h[|k - 2n - 32|]   (Toeplitz)
+// with X ~= Xh + Xl and H ~= Hh + Hl in fp16 (fp32 accumulation in TMEM, ~22 significant bits as in the filter bank):
+//     MMA 1: A = Xh, B = [Hh | Hl] (N = 64);   MMA 2: A = Xl, B = Hh (N = 32);   out[r, n] = D[r, n] + D[r, 32 + n].
+// Shared-memory operand ("transposed chunk planes"): the 16-byte chunk q (samples 8q .. 8q+7) of the tile's input span
+// lives at  plane[q % 8] + (q / 8) * 16,  so operand row r = 64 samples is one 16-byte slot per plane, chunks 0..7 of a
+// row are the 8 planes (LBO = plane pitch) and chunks 8..15 the same planes one row further (start address + 16 B).
+// One CTA tile fuses TWO octave steps: 129 input rows -> 128 rows of level p+1 (4096 samples, kept in shared memory as
+// the next operand and written to global memory) -> 63 rows of level p+2 (2016 samples).  Each tile recomputes a halo of
+// 32 + 2*32 input samples per side (2.4 %) instead of exchanging state with its neighbours.  Persistent CTAs, 3 per SM.
+constexpr int kCasRows2 = 63;                       // level p+2 rows (of 32 outputs) per tile
+constexpr int kCasOwn2 = kCasRows2 * 32;            // 2016 level p+2 outputs owned by a tile
+constexpr int kCasOwn1 = 2 * kCasOwn2;              // 4032 level p+1 outputs owned by a tile (rows 1..126 of 128)
+constexpr int kCasP0Rows = 129, kCasP1Rows = 65;    // plane rows (16 B each) of the level p / level p+1 operands
+constexpr uint32_t kCasLBO0 = kCasP0Rows * 16, kCasLBO1 = kCasP1Rows * 16;  // odd multiples of 16 B: conflict-free scatter
+constexpr uint32_t kCasP0Bytes = 8 * kCasLBO0, kCasP1Bytes = 8 * kCasLBO1;
+constexpr uint32_t kCasImgBytes = 16 * 64 * 16;     // Toeplitz image: [chunk 16][n 64 = Hh 32 | Hl 32][8 halves]
+constexpr uint32_t kCasSmem = 2 * kCasP1Bytes + 2 * kCasP0Bytes + kCasImgBytes;
 
-__global__ void __launch_bounds__(kDecThreads) decimate2_kernel(const float* __restrict__ in, long long in_stride,
-                                                                  float* __restrict__ out, long long out_stride,
-                                                                  const long long* __restrict__ lengths, long long n_uniform,
-                                                                  int level /* input is level-1 */) {
-  constexpr int SPAN = kDecOutPerBlock + 32;  // phase samples m in [t0-16, t0+OUT+16)
-  __shared__ __align__(16) float se[SPAN];
-  __shared__ __align__(16) float so[SPAN];
-  const int b = blockIdx.y;
-  const long long n0 = lengths ? lengths[b] : n_uniform;
-  const long long n_in = (n0 + (1LL << (level - 1)) - 1) >> (level - 1);
-  const long long n_half = n_in >> 1, n_out = (n_in + 1) >> 1;
-  const long long t0 = (long long)blockIdx.x * kDecOutPerBlock;
-  if (t0 >= n_out) return;
-  const float* src = in + b * in_stride;
-  for (int i = threadIdx.x; i < SPAN; i += kDecThreads) {
-    const long long m = t0 - 16 + i;
-    const long long s = 2 * m;
-    se[i] = (s >= 0 && s < n_in) ? __ldg(src + s) : 0.f;
-    so[i] = (s + 1 >= 0 && s + 1 < n_in) ? __ldg(src + s + 1) : 0.f;
+struct CascadeArgs {
+  const float* in;      // level p, clip b at in + b * in_stride
+  long long in_stride;
+  float* out1;          // level p+1
+  long long stride1;
+  float* out2;          // level p+2 (unused when n_levels == 1)
+  long long stride2;
+  const long long* lengths;  // full-rate samples per clip, or NULL (= n_uniform)
+  long long n_uniform;
+  int level_in, n_levels, tiles_per_clip, n_tiles;
+  const __half* img;
+};
+
+__device__ __forceinline__ void cas_store_split8(uint8_t* hi_dst, uint8_t* lo_dst, const float (&v)[8], float scale) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    __half h0, l0, h1, l1;
+    umma::split_f16(v[2 * e] * scale, h0, l0);
+    umma::split_f16(v[2 * e + 1] * scale, h1, l1);
+    h[e] = umma::pack_h2(h0, h1), l[e] = umma::pack_h2(l0, l1);
   }
+  *reinterpret_cast<uint4*>(hi_dst) = make_uint4(h[0], h[1], h[2], h[3]);
+  *reinterpret_cast<uint4*>(lo_dst) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+__global__ void __launch_bounds__(128) cascade_umma_kernel(const CascadeArgs a) {
+  using namespace umma;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t img_bar, mma_bar;
+  __shared__ uint32_t tmem_slot;
+  // Order matters: the level p+1 MMA runs M = 128 over 63 useful rows; its surplus rows read on into the next buffer,
+  // which must hold finite fp16 data (their products only reach accumulator rows that are never read back).
+  uint8_t* p1h = smem;
+  uint8_t* p1l = smem + kCasP1Bytes;
+  uint8_t* p0h = smem + 2 * kCasP1Bytes;
+  uint8_t* p0l = p0h + kCasP0Bytes;
+  uint8_t* img = p0l + kCasP0Bytes;
+  const int tid = threadIdx.x, warp = tid >> 5;
+
+  if (warp == 0) tmem_alloc(&tmem_slot, 64);
+  if (tid == 0) {
+    mbar_init(&img_bar, 1), mbar_init(&mma_bar, 1);
+    mbar_init_fence();
+  }
+  for (uint32_t i = tid; i < (2 * kCasP1Bytes + 2 * kCasP0Bytes) / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async();
+  fence_before_sync();
   __syncthreads();
-  const int lt = threadIdx.x * kDecOutPerThread;  // local output index; phase index of output t is lt + 16
-  float xe[kDecOutPerThread + 32], xo[kDecOutPerThread + 32];
-#pragma unroll
-  for (int q = 0; q < (kDecOutPerThread + 32) / 4; ++q) {
-    const float4 a = *reinterpret_cast<const float4*>(se + lt + 4 * q);
-    const float4 c = *reinterpret_cast<const float4*>(so + lt + 4 * q);
-    xe[4 * q] = a.x, xe[4 * q + 1] = a.y, xe[4 * q + 2] = a.z, xe[4 * q + 3] = a.w;
-    xo[4 * q] = c.x, xo[4 * q + 1] = c.y, xo[4 * q + 2] = c.z, xo[4 * q + 3] = c.w;
+  fence_after_sync();
+  if (tid == 0) {
+    mbar_arrive_expect_tx(&img_bar, kCasImgBytes);
+    bulk_g2s(img, a.img, kCasImgBytes, &img_bar);
   }
-  float acc[kDecOutPerThread];
+  const uint32_t tmem = tmem_slot;
+  const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+  uint32_t phase = 0;
+  bool img_ready = false;
+  constexpr float kInvD = 1.f / (kXScale * kDecScale);  // accumulator -> sample
+  constexpr float kToX = 1.f / kDecScale;               // accumulator -> kXScale * sample (the next operand)
+
+  auto issue_level = [&](uint32_t hi0, uint32_t lo0, uint32_t lbo) {
+    const uint64_t a_desc = desc_hi(lbo);
+    constexpr uint64_t B_DESC = desc_hi(64 * 16);
+    constexpr uint32_t IDESC64 = idesc_f16(64), IDESC32 = idesc_f16(32);
+    const uint32_t w0 = smem_u32(img);
 #pragma unroll
-  for (int r = 0; r < kDecOutPerThread; ++r) {
-    // output t = t0 + lt + r sits at phase index r + 16: even taps j = 2e -> xe[r+16+e], odd j = 2o+1 -> xo[r+16+o]
-    float s = c_dec_taps[0] * xe[r + 16];
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t off = (uint32_t)((2 * j) & 7) * lbo + (j >= 4 ? 16u : 0u);  // chunks 8..15 = planes 0..7, one row on
+      const uint64_t bd = make_desc(B_DESC, w0 + (uint32_t)j * 2048);
+      mma_f16(tmem, make_desc(a_desc, hi0 + off), bd, IDESC64, j ? 1u : 0u);
+      mma_f16(tmem, make_desc(a_desc, lo0 + off), bd, IDESC32, 1u);
+    }
+    commit(&mma_bar);
+  };
+
+  for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+    const int b = tile / a.tiles_per_clip, t = tile - b * a.tiles_per_clip;
+    const long long n0 = a.lengths ? a.lengths[b] : a.n_uniform;
+    const long long n_p = (n0 + (1LL << a.level_in) - 1) >> a.level_in;
+    const long long n_half1 = n_p >> 1, n1 = (n_p + 1) >> 1, n_half2 = n1 >> 1, n2 = (n1 + 1) >> 1;
+    const long long own1 = (long long)kCasOwn1 * t;          // first level p+1 output this tile owns
+    if (own1 >= n1) continue;                                 // beyond this clip's data (ragged batch): nothing to write
+    const long long o_lo2 = (long long)kCasOwn2 * t, o_lo1 = own1 - 32, base0 = 2 * o_lo1 - 32;
+
+    // ---- stage the input span: fp32 -> fp16 hi/lo, scattered into the transposed chunk planes
+    const float* src = a.in + (long long)b * a.in_stride;
+    const bool aligned = (reinterpret_cast<uintptr_t>(src) & 15) == 0;
 #pragma unroll
-    for (int e = 1; e <= 15; ++e) s = fmaf(c_dec_taps[2 * e], xe[r + 16 + e] + xe[r + 16 - e], s);
+    for (int half = 0; half < 2; ++half) {
+      constexpr int PER = 5;
+      float x[PER][8];
 #pragma unroll
-    for (int o = 0; o <= 15; ++o) s = fmaf(c_dec_taps[2 * o + 1], xo[r + 16 + o] + xo[r + 15 - o], s);
-    acc[r] = s;
+      for (int i = 0; i < PER; ++i) {
+        const int q = tid + 128 * (half * PER + i);
+        const long long g = base0 + 8LL * q;
+        if (q < kCasP0Rows * 8 && aligned && g >= 0 && g + 8 <= n_p) {
+          const float4 v0 = __ldg(reinterpret_cast<const float4*>(src + g)), v1 = __ldg(reinterpret_cast<const float4*>(src + g) + 1);
+          x[i][0] = v0.x, x[i][1] = v0.y, x[i][2] = v0.z, x[i][3] = v0.w, x[i][4] = v1.x, x[i][5] = v1.y, x[i][6] = v1.z, x[i][7] = v1.w;
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) x[i][e] = (q < kCasP0Rows * 8 && g + e >= 0 && g + e < n_p) ? __ldg(src + g + e) : 0.f;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < PER; ++i) {
+        const int q = tid + 128 * (half * PER + i);
+        if (q < kCasP0Rows * 8) {
+          const uint32_t off = (uint32_t)(q & 7) * kCasLBO0 + (uint32_t)(q >> 3) * 16;
+          cas_store_split8(p0h + off, p0l + off, x[i], kXScale);
+        }
+      }
+    }
+    fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+      if (!img_ready) mbar_wait(&img_bar, 0), img_ready = true;
+      fence_after_sync();
+      issue_level(smem_u32(p0h), smem_u32(p0l), kCasLBO0);
+    }
+    mbar_wait(&mma_bar, phase);
+    phase ^= 1;
+    fence_after_sync();
+
+    // ---- level p+1: thread = accumulator lane = row of 32 outputs
+    {
+      float o[32];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float u[16], w[16];
+        tmem_ld16(lane_base + h * 16, u);
+        tmem_ld16(lane_base + 32 + h * 16, w);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) o[h * 16 + j] = u[j] + w[j];
+      }
+      const long long i1 = o_lo1 + 32LL * tid;
+#pragma unroll
+      for (int n = 0; n < 32; ++n) o[n] = (i1 + n >= 0 && i1 + n < n_half1) ? o[n] : 0.f;  // samples that do not exist are zero
+      if (tid >= 1 && tid <= 126 && i1 < n1) {
+        float4* dst = reinterpret_cast<float4*>(a.out1 + (long long)b * a.stride1 + i1);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) dst[q] = make_float4(o[4 * q] * kInvD, o[4 * q + 1] * kInvD, o[4 * q + 2] * kInvD, o[4 * q + 3] * kInvD);
+      }
+      if (a.n_levels == 2) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float v[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = o[8 * i + e];
+          const uint32_t off = (uint32_t)(4 * (tid & 1) + i) * kCasLBO1 + (uint32_t)(tid >> 1) * 16;
+          cas_store_split8(p1h + off, p1l + off, v, kToX);
+        }
+      }
+    }
+    if (a.n_levels == 2) {
+      fence_before_sync();
+      fence_proxy_async();
+      __syncthreads();
+      if (tid == 0) {
+        fence_after_sync();
+        issue_level(smem_u32(p1h), smem_u32(p1l), kCasLBO1);
+      }
+      mbar_wait(&mma_bar, phase);
+      phase ^= 1;
+      fence_after_sync();
+      if (warp < 2) {  // rows 0..62 live in warps 0 and 1 (tcgen05.ld is warp-collective: no per-thread predicate here)
+        float o[32];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          float u[16], w[16];
+          tmem_ld16(lane_base + h * 16, u);
+          tmem_ld16(lane_base + 32 + h * 16, w);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) o[h * 16 + j] = u[j] + w[j];
+        }
+        const long long i2 = o_lo2 + 32LL * tid;
+        if (tid < kCasRows2 && i2 < n2) {
+          float4* dst = reinterpret_cast<float4*>(a.out2 + (long long)b * a.stride2 + i2);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            float4 v;
+            v.x = (i2 + 4 * q + 0 < n_half2) ? o[4 * q + 0] * kInvD : 0.f;
+            v.y = (i2 + 4 * q + 1 < n_half2) ? o[4 * q + 1] * kInvD : 0.f;
+            v.z = (i2 + 4 * q + 2 < n_half2) ? o[4 * q + 2] * kInvD : 0.f;
+            v.w = (i2 + 4 * q + 3 < n_half2) ? o[4 * q + 3] * kInvD : 0.f;
+            dst[q] = v;
+          }
+        }
+      }
+    }
+    fence_before_sync();
+    __syncthreads();  // accumulator drained and operands consumed: the next tile may overwrite both
+    fence_after_sync();
   }
-  float* dst = out + b * out_stride;
-#pragma unroll
-  for (int r = 0; r < kDecOutPerThread; ++r) {
-    const long long t = t0 + lt + r;
-    if (t < n_out) dst[t] = t < n_half ? acc[r] : 0.f;
-  }
+  if (tid == 0 && !img_ready) mbar_wait(&img_bar, 0);  // never leave with a bulk copy in flight
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 64);
 }
 
 // ---- tensor-core filter bank (tcgen05): one CTA = 128 frames of one octave x all filters x all of K ----------------
@@ -457,7 +638,7 @@ static CqtWs carve(const ake_cqt* p, Arena& ar, int B, long long n_max) {
   CqtWs w{};
   w.d_len = ar.take<long long>(B);
   for (int i = 1; i < p->n_oct; ++i) {
-    w.stride[i] = (long long)align_up((size_t)len_at(n_max, i), 4);
+    w.stride[i] = (long long)align_up((size_t)len_at(n_max, i), 32);  // the cascade kernel stores whole rows of 32 samples
     w.level[i] = ar.take<float>((size_t)B * w.stride[i]);
   }
   return w;
@@ -478,12 +659,32 @@ static void run_cqt(ake_cqt* p, const float* audio, long long stride, const int6
   }
   w.level[0] = const_cast<float*>(audio);
   w.stride[0] = stride;
-  for (int i = 1; i < p->n_oct; ++i) {
+  if (p->n_oct > 1) {
+    // resampling cascade: two octave steps per pass (level p -> p+1, p+2), persistent CTAs, 3 per SM
     ProfScope prof("cqt.decimate", st);
-    const long long n_out = len_at(n_max, i);
-    dim3 grid((unsigned)cdiv64(n_out, kDecOutPerBlock), B);
-    decimate2_kernel<<<grid, kDecThreads, 0, st>>>(w.level[i - 1], w.stride[i - 1], w.level[i], w.stride[i], d_len, n_max, i);
-    AKE_LAUNCHED();
+    static bool configured = false;
+    static int n_sm = 0;
+    if (!configured) {
+      AKE_CUDA(cudaFuncSetAttribute(cascade_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCasSmem));
+      int dev = 0;
+      AKE_CUDA(cudaGetDevice(&dev));
+      AKE_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+      configured = true;
+    }
+    for (int lv = 0; lv < p->n_oct - 1; lv += 2) {
+      CascadeArgs ca{};
+      ca.in = w.level[lv], ca.in_stride = w.stride[lv];
+      ca.out1 = w.level[lv + 1], ca.stride1 = w.stride[lv + 1];
+      ca.n_levels = std::min(2, p->n_oct - 1 - lv);
+      if (ca.n_levels == 2) ca.out2 = w.level[lv + 2], ca.stride2 = w.stride[lv + 2];
+      ca.lengths = d_len, ca.n_uniform = n_max, ca.level_in = lv;
+      ca.tiles_per_clip = (int)cdiv64(len_at(n_max, lv + 1), kCasOwn1);
+      ca.n_tiles = ca.tiles_per_clip * B;
+      ca.img = p->d_dec_img;
+      const int grid = std::min(ca.n_tiles, 3 * n_sm);
+      cascade_umma_kernel<<<grid, 128, kCasSmem, st>>>(ca);
+      AKE_LAUNCHED();
+    }
   }
   const long long rows = (long long)B * T_max;
   if (p->npad) {
@@ -547,6 +748,7 @@ void ake_cqt_destroy(ake_cqt* p) {
   if (!p) return;
   if (p->d_scale) cudaFree(p->d_scale);
   if (p->d_bank_img) cudaFree(p->d_bank_img);
+  if (p->d_dec_img) cudaFree(p->d_dec_img);
   if (p->d_scale_umma) cudaFree(p->d_scale_umma);
   delete p;
 }
