@@ -251,7 +251,8 @@ static int frames_for(const ake_cqt* p, long long n) {
 // row are the 8 planes (LBO = plane pitch) and chunks 8..15 the same planes one row further (start address + 16 B).
 // One CTA tile fuses TWO octave steps: 129 input rows -> 128 rows of level p+1 (4096 samples, kept in shared memory as
 // the next operand and written to global memory) -> 63 rows of level p+2 (2016 samples).  Each tile recomputes a halo of
-// 32 + 2*32 input samples per side (2.4 %) instead of exchanging state with its neighbours.  Persistent CTAs, 3 per SM.
+// 32 + 2*32 input samples per side (2.4 %) instead of exchanging state with its neighbours.  Persistent CTAs, 2 per SM; the next tile's
+// span is landed in shared memory by cp.async while the current tile runs its MMAs and epilogues.
 constexpr int kCasRows2 = 63;                       // level p+2 rows (of 32 outputs) per tile
 constexpr int kCasOwn2 = kCasRows2 * 32;            // 2016 level p+2 outputs owned by a tile
 constexpr int kCasOwn1 = 2 * kCasOwn2;              // 4032 level p+1 outputs owned by a tile (rows 1..126 of 128)
@@ -277,36 +278,47 @@ struct CascadeArgs {
 __device__ __forceinline__ void cas_store_split8(uint8_t* hi_dst, uint8_t* lo_dst, const float (&v)[8], float scale) {
   uint32_t h[4], l[4];
 #pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    __half h0, l0, h1, l1;
-    umma::split_f16(v[2 * e] * scale, h0, l0);
-    umma::split_f16(v[2 * e + 1] * scale, h1, l1);
-    h[e] = umma::pack_h2(h0, h1), l[e] = umma::pack_h2(l0, l1);
-  }
+  for (int e = 0; e < 4; ++e) umma::split_f16x2(v[2 * e] * scale, v[2 * e + 1] * scale, h[e], l[e]);
   *reinterpret_cast<uint4*>(hi_dst) = make_uint4(h[0], h[1], h[2], h[3]);
   *reinterpret_cast<uint4*>(lo_dst) = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
-__global__ void __launch_bounds__(128) cascade_umma_kernel(const CascadeArgs a) {
+constexpr int kCasThreads = 256;  // warps w and w+4 share accumulator lanes 32 (w % 4) ..: each takes 16 of a row's 32 outputs
+constexpr int kCasChunks = kCasP0Rows * 8;                 // 1032 chunks of 8 samples per tile span
+constexpr int kCasPer = (kCasChunks + kCasThreads - 1) / kCasThreads;  // chunks per thread (the last round holds 8)
+constexpr uint32_t kCasStageBytes = kCasChunks * 32;       // fp32 landing buffer of the next tile's span (cp.async)
+constexpr uint32_t kCasSmemTotal = kCasSmem + kCasStageBytes;
+
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(umma::smem_u32(dst_smem)), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* dst_smem, const void* src, int src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(umma::smem_u32(dst_smem)), "l"(src), "r"(src_bytes) : "memory");
+}
+
+__global__ void __launch_bounds__(kCasThreads, 2) cascade_umma_kernel(const CascadeArgs a) {
   using namespace umma;
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t img_bar, mma_bar;
   __shared__ uint32_t tmem_slot;
-  // Order matters: the level p+1 MMA runs M = 128 over 63 useful rows; its surplus rows read on into the next buffer,
+  // Order matters: the level p+2 MMA runs M = 128 over 63 useful rows; its surplus rows read on into the next buffer,
   // which must hold finite fp16 data (their products only reach accumulator rows that are never read back).
   uint8_t* p1h = smem;
   uint8_t* p1l = smem + kCasP1Bytes;
   uint8_t* p0h = smem + 2 * kCasP1Bytes;
   uint8_t* p0l = p0h + kCasP0Bytes;
   uint8_t* img = p0l + kCasP0Bytes;
-  const int tid = threadIdx.x, warp = tid >> 5;
+  float* stage = reinterpret_cast<float*>(img + kCasImgBytes);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row = 32 * (warp & 3) + lane;  // accumulator lane = row of 32 outputs
+  const int hf = warp >> 2;                // which 16 of them this thread handles
 
   if (warp == 0) tmem_alloc(&tmem_slot, 64);
   if (tid == 0) {
     mbar_init(&img_bar, 1), mbar_init(&mma_bar, 1);
     mbar_init_fence();
   }
-  for (uint32_t i = tid; i < (2 * kCasP1Bytes + 2 * kCasP0Bytes) / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  for (uint32_t i = tid; i < (2 * kCasP1Bytes + 2 * kCasP0Bytes) / 16; i += kCasThreads) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
   fence_proxy_async();
   fence_before_sync();
   __syncthreads();
@@ -316,7 +328,7 @@ __global__ void __launch_bounds__(128) cascade_umma_kernel(const CascadeArgs a) 
     bulk_g2s(img, a.img, kCasImgBytes, &img_bar);
   }
   const uint32_t tmem = tmem_slot;
-  const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+  const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16) + 16 * hf;
   uint32_t phase = 0;
   bool img_ready = false;
   constexpr float kInvD = 1.f / (kXScale * kDecScale);  // accumulator -> sample
@@ -336,43 +348,87 @@ __global__ void __launch_bounds__(128) cascade_umma_kernel(const CascadeArgs a) 
     }
     commit(&mma_bar);
   };
-
-  for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-    const int b = tile / a.tiles_per_clip, t = tile - b * a.tiles_per_clip;
+  // this thread's 16 accumulator columns: out[n] = D[n] + D[32 + n]
+  auto read_acc = [&](float (&o)[16]) {
+    float w[16];
+    tmem_ld16(lane_base, o);
+    tmem_ld16(lane_base + 32, w);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) o[j] += w[j];
+  };
+  auto clip_len = [&](int b) {  // samples of level p in clip b
     const long long n0 = a.lengths ? a.lengths[b] : a.n_uniform;
-    const long long n_p = (n0 + (1LL << a.level_in) - 1) >> a.level_in;
-    const long long n_half1 = n_p >> 1, n1 = (n_p + 1) >> 1, n_half2 = n1 >> 1, n2 = (n1 + 1) >> 1;
-    const long long own1 = (long long)kCasOwn1 * t;          // first level p+1 output this tile owns
-    if (own1 >= n1) continue;                                 // beyond this clip's data (ragged batch): nothing to write
-    const long long o_lo2 = (long long)kCasOwn2 * t, o_lo1 = own1 - 32, base0 = 2 * o_lo1 - 32;
-
-    // ---- stage the input span: fp32 -> fp16 hi/lo, scattered into the transposed chunk planes
-    const float* src = a.in + (long long)b * a.in_stride;
+    return (n0 + (1LL << a.level_in) - 1) >> a.level_in;
+  };
+  // first tile at or after `tile` (in this CTA's stride) that has data; tiles beyond a short clip's end write nothing
+  auto next_tile = [&](int tile) {
+    for (; tile < a.n_tiles; tile += gridDim.x) {
+      const int b = tile / a.tiles_per_clip, t = tile - b * a.tiles_per_clip;
+      if ((long long)kCasOwn1 * t < ((clip_len(b) + 1) >> 1)) break;
+    }
+    return tile;
+  };
+  // Each thread lands the chunks it will itself convert, so only its own cp.async group orders the reuse of the stage.
+  auto prefetch = [&](int tile) {
+    const int b = tile / a.tiles_per_clip, t = tile - b * a.tiles_per_clip;
+    const long long n_p = clip_len(b);
+    const long long base0 = 2 * ((long long)kCasOwn1 * t - 32) - 32;
+    const float* clip = a.in + (long long)b * a.in_stride;
+    const float* src = clip + base0;
     const bool aligned = (reinterpret_cast<uintptr_t>(src) & 15) == 0;
+    const int vlo = (int)max(0LL, -base0), vhi = (int)min((long long)kCasChunks * 8, n_p - base0);  // existing samples of the span
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      constexpr int PER = 5;
-      float x[PER][8];
+    for (int i = 0; i < kCasPer; ++i) {
+      const int q = tid + kCasThreads * i, s0 = 8 * q;
+      if (q >= kCasChunks) break;
+      if (aligned) {
 #pragma unroll
-      for (int i = 0; i < PER; ++i) {
-        const int q = tid + 128 * (half * PER + i);
-        const long long g = base0 + 8LL * q;
-        if (q < kCasP0Rows * 8 && aligned && g >= 0 && g + 8 <= n_p) {
-          const float4 v0 = __ldg(reinterpret_cast<const float4*>(src + g)), v1 = __ldg(reinterpret_cast<const float4*>(src + g) + 1);
+        for (int h = 0; h < 2; ++h) {
+          const int s = s0 + 4 * h;
+          const int n_ok = s < vlo ? 0 : max(0, min(4, vhi - s));
+          cp_async16(stage + s, n_ok ? src + s : clip, 4 * n_ok);
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const bool ok = s0 + e >= vlo && s0 + e < vhi;
+          cp_async4(stage + s0 + e, ok ? src + s0 + e : clip, ok ? 4 : 0);
+        }
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  int tile = next_tile(blockIdx.x);
+  if (tile < a.n_tiles) prefetch(tile);
+  while (tile < a.n_tiles) {
+    const int b = tile / a.tiles_per_clip, t = tile - b * a.tiles_per_clip;
+    const long long n_p = clip_len(b);
+    const long long n_half1 = n_p >> 1, n1 = (n_p + 1) >> 1, n_half2 = n1 >> 1, n2 = (n1 + 1) >> 1;
+    const long long o_lo2 = (long long)kCasOwn2 * t, o_lo1 = (long long)kCasOwn1 * t - 32;
+    const int nxt = next_tile(tile + gridDim.x);
+
+    // ---- stage -> registers, start the next tile's copies, then fp32 -> fp16 hi/lo into the transposed chunk planes
+    {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      float x[kCasPer][8];
+#pragma unroll
+      for (int i = 0; i < kCasPer; ++i) {
+        const int q = tid + kCasThreads * i;
+        if (q < kCasChunks) {
+          const float4 v0 = *reinterpret_cast<const float4*>(stage + 8 * q), v1 = *reinterpret_cast<const float4*>(stage + 8 * q + 4);
           x[i][0] = v0.x, x[i][1] = v0.y, x[i][2] = v0.z, x[i][3] = v0.w, x[i][4] = v1.x, x[i][5] = v1.y, x[i][6] = v1.z, x[i][7] = v1.w;
-        } else {
-#pragma unroll
-          for (int e = 0; e < 8; ++e) x[i][e] = (q < kCasP0Rows * 8 && g + e >= 0 && g + e < n_p) ? __ldg(src + g + e) : 0.f;
         }
       }
 #pragma unroll
-      for (int i = 0; i < PER; ++i) {
-        const int q = tid + 128 * (half * PER + i);
-        if (q < kCasP0Rows * 8) {
+      for (int i = 0; i < kCasPer; ++i) {
+        const int q = tid + kCasThreads * i;
+        if (q < kCasChunks) {
           const uint32_t off = (uint32_t)(q & 7) * kCasLBO0 + (uint32_t)(q >> 3) * 16;
           cas_store_split8(p0h + off, p0l + off, x[i], kXScale);
         }
       }
+      if (nxt < a.n_tiles) prefetch(nxt);  // after this thread's reads of the stage have been consumed
     }
     fence_proxy_async();
     __syncthreads();
@@ -385,32 +441,27 @@ __global__ void __launch_bounds__(128) cascade_umma_kernel(const CascadeArgs a) 
     phase ^= 1;
     fence_after_sync();
 
-    // ---- level p+1: thread = accumulator lane = row of 32 outputs
+    // ---- level p+1
     {
-      float o[32];
+      float o[16];
+      read_acc(o);
+      const long long i1 = o_lo1 + 32LL * row + 16 * hf;  // level p+1 index of o[0]
+      // samples that do not exist (index < 0 or >= floor(n_p / 2)) are zero
+      const int zlo = (int)min(16LL, max(0LL, -i1)), zhi = (int)min(16LL, max(0LL, n_half1 - i1));
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        float u[16], w[16];
-        tmem_ld16(lane_base + h * 16, u);
-        tmem_ld16(lane_base + 32 + h * 16, w);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) o[h * 16 + j] = u[j] + w[j];
-      }
-      const long long i1 = o_lo1 + 32LL * tid;
-#pragma unroll
-      for (int n = 0; n < 32; ++n) o[n] = (i1 + n >= 0 && i1 + n < n_half1) ? o[n] : 0.f;  // samples that do not exist are zero
-      if (tid >= 1 && tid <= 126 && i1 < n1) {
+      for (int n = 0; n < 16; ++n) o[n] = (n >= zlo && n < zhi) ? o[n] : 0.f;
+      if (row >= 1 && row <= 126 && i1 < n1) {  // rows 0 and 127 are the halo the next level needs
         float4* dst = reinterpret_cast<float4*>(a.out1 + (long long)b * a.stride1 + i1);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) dst[q] = make_float4(o[4 * q] * kInvD, o[4 * q + 1] * kInvD, o[4 * q + 2] * kInvD, o[4 * q + 3] * kInvD);
+        for (int q = 0; q < 4; ++q) dst[q] = make_float4(o[4 * q] * kInvD, o[4 * q + 1] * kInvD, o[4 * q + 2] * kInvD, o[4 * q + 3] * kInvD);
       }
       if (a.n_levels == 2) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < 2; ++i) {
           float v[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) v[e] = o[8 * i + e];
-          const uint32_t off = (uint32_t)(4 * (tid & 1) + i) * kCasLBO1 + (uint32_t)(tid >> 1) * 16;
+          const uint32_t off = (uint32_t)(4 * (row & 1) + 2 * hf + i) * kCasLBO1 + (uint32_t)(row >> 1) * 16;
           cas_store_split8(p1h + off, p1l + off, v, kToX);
         }
       }
@@ -426,26 +477,20 @@ __global__ void __launch_bounds__(128) cascade_umma_kernel(const CascadeArgs a) 
       mbar_wait(&mma_bar, phase);
       phase ^= 1;
       fence_after_sync();
-      if (warp < 2) {  // rows 0..62 live in warps 0 and 1 (tcgen05.ld is warp-collective: no per-thread predicate here)
-        float o[32];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          float u[16], w[16];
-          tmem_ld16(lane_base + h * 16, u);
-          tmem_ld16(lane_base + 32 + h * 16, w);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) o[h * 16 + j] = u[j] + w[j];
-        }
-        const long long i2 = o_lo2 + 32LL * tid;
-        if (tid < kCasRows2 && i2 < n2) {
+      if ((warp & 3) < 2) {  // rows 0..62 live in accumulator lanes 0..63 (tcgen05.ld is warp-collective: no per-thread predicate)
+        float o[16];
+        read_acc(o);
+        const long long i2 = o_lo2 + 32LL * row + 16 * hf;
+        if (row < kCasRows2 && i2 < n2) {
+          const int zhi = (int)min(16LL, max(0LL, n_half2 - i2));
           float4* dst = reinterpret_cast<float4*>(a.out2 + (long long)b * a.stride2 + i2);
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
+          for (int q = 0; q < 4; ++q) {
             float4 v;
-            v.x = (i2 + 4 * q + 0 < n_half2) ? o[4 * q + 0] * kInvD : 0.f;
-            v.y = (i2 + 4 * q + 1 < n_half2) ? o[4 * q + 1] * kInvD : 0.f;
-            v.z = (i2 + 4 * q + 2 < n_half2) ? o[4 * q + 2] * kInvD : 0.f;
-            v.w = (i2 + 4 * q + 3 < n_half2) ? o[4 * q + 3] * kInvD : 0.f;
+            v.x = (4 * q + 0 < zhi) ? o[4 * q + 0] * kInvD : 0.f;
+            v.y = (4 * q + 1 < zhi) ? o[4 * q + 1] * kInvD : 0.f;
+            v.z = (4 * q + 2 < zhi) ? o[4 * q + 2] * kInvD : 0.f;
+            v.w = (4 * q + 3 < zhi) ? o[4 * q + 3] * kInvD : 0.f;
             dst[q] = v;
           }
         }
@@ -454,6 +499,7 @@ __global__ void __launch_bounds__(128) cascade_umma_kernel(const CascadeArgs a) 
     fence_before_sync();
     __syncthreads();  // accumulator drained and operands consumed: the next tile may overwrite both
     fence_after_sync();
+    tile = nxt;
   }
   if (tid == 0 && !img_ready) mbar_wait(&img_bar, 0);  // never leave with a bulk copy in flight
   fence_before_sync();
@@ -551,12 +597,7 @@ __global__ void __launch_bounds__(160) cqt_bank_umma_kernel(const BankArgs a) {
       for (int c = 0; c < kUKB / 8; ++c) {
         uint32_t hi[4], lo[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          __half h0, l0, h1, l1;
-          split_f16(x[8 * c + 2 * e] * kXScale, h0, l0);
-          split_f16(x[8 * c + 2 * e + 1] * kXScale, h1, l1);
-          hi[e] = pack_h2(h0, h1), lo[e] = pack_h2(l0, l1);
-        }
+        for (int e = 0; e < 4; ++e) split_f16x2(x[8 * c + 2 * e] * kXScale, x[8 * c + 2 * e + 1] * kXScale, hi[e], lo[e]);
         *reinterpret_cast<uint4*>(stage + c * 2048 + tid * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
         *reinterpret_cast<uint4*>(stage + A_HALF + c * 2048 + tid * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
       }
@@ -665,7 +706,7 @@ static void run_cqt(ake_cqt* p, const float* audio, long long stride, const int6
     static bool configured = false;
     static int n_sm = 0;
     if (!configured) {
-      AKE_CUDA(cudaFuncSetAttribute(cascade_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCasSmem));
+      AKE_CUDA(cudaFuncSetAttribute(cascade_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCasSmemTotal));
       int dev = 0;
       AKE_CUDA(cudaGetDevice(&dev));
       AKE_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
@@ -681,8 +722,8 @@ static void run_cqt(ake_cqt* p, const float* audio, long long stride, const int6
       ca.tiles_per_clip = (int)cdiv64(len_at(n_max, lv + 1), kCasOwn1);
       ca.n_tiles = ca.tiles_per_clip * B;
       ca.img = p->d_dec_img;
-      const int grid = std::min(ca.n_tiles, 3 * n_sm);
-      cascade_umma_kernel<<<grid, 128, kCasSmem, st>>>(ca);
+      const int grid = std::min(ca.n_tiles, 2 * n_sm);
+      cascade_umma_kernel<<<grid, kCasThreads, kCasSmemTotal, st>>>(ca);
       AKE_LAUNCHED();
     }
   }

@@ -31,12 +31,7 @@ __device__ __forceinline__ float leaky_f(float v) { return v > 0.f ? v : kLeakyS
 __device__ __forceinline__ void store_split8(__half* hi_dst, __half* lo_dst, const float (&v)[8]) {
   uint32_t h[4], l[4];
 #pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    __half h0, l0, h1, l1;
-    umma::split_f16(v[2 * e], h0, l0);
-    umma::split_f16(v[2 * e + 1], h1, l1);
-    h[e] = umma::pack_h2(h0, h1), l[e] = umma::pack_h2(l0, l1);
-  }
+  for (int e = 0; e < 4; ++e) umma::split_f16x2(v[2 * e], v[2 * e + 1], h[e], l[e]);
   *reinterpret_cast<uint4*>(hi_dst) = make_uint4(h[0], h[1], h[2], h[3]);
   *reinterpret_cast<uint4*>(lo_dst) = make_uint4(l[0], l[1], l[2], l[3]);
 }
@@ -253,12 +248,7 @@ __global__ void __launch_bounds__(160) p2p_umma_kernel(const P2PArgs a) {
           for (int c = 0; c < 8; ++c) o[c] = leaky_f(fmaf(o[c], s_scale[c], s_shift[c]));
           uint32_t h[4], l[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            __half h0, l0, h1, l1;
-            split_f16(o[2 * e], h0, l0);
-            split_f16(o[2 * e + 1], h1, l1);
-            h[e] = pack_h2(h0, h1), l[e] = pack_h2(l0, l1);
-          }
+          for (int e = 0; e < 4; ++e) split_f16x2(o[2 * e], o[2 * e + 1], h[e], l[e]);
           const uint4 hv = make_uint4(h[0], h[1], h[2], h[3]), lv = make_uint4(l[0], l[1], l[2], l[3]);
           const int p = p0 + pl, t = t0 + tl;
           // home position + circular halo copies (rows p +- P, columns t +- T)
