@@ -275,31 +275,68 @@ struct CascadeArgs {
   const __half* img;
 };
 
+// fp32x2 packed arithmetic (sm_100: FMUL2 / FADD2) halves the scale / residual instructions of the hi/lo split
+__device__ __forceinline__ uint64_t f2_pack(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t f2_sub(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+// (a, b) -> fp16 pairs hi, lo with a ~= hi + lo
+__device__ __forceinline__ void cas_split2(uint64_t x, uint32_t& hi, uint32_t& lo) {
+  float x0, x1;
+  f2_unpack(x, x0, x1);
+  const __half2 h = __floats2half2_rn(x0, x1);
+  const float2 hf = __half22float2(h);
+  float d0, d1;
+  f2_unpack(f2_sub(x, f2_pack(hf.x, hf.y)), d0, d1);
+  const __half2 l = __floats2half2_rn(d0, d1);
+  hi = *reinterpret_cast<const uint32_t*>(&h), lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+template <bool SCALE>
 __device__ __forceinline__ void cas_store_split8(uint8_t* hi_dst, uint8_t* lo_dst, const float (&v)[8], float scale) {
   uint32_t h[4], l[4];
+  const uint64_t ss = f2_pack(scale, scale);
 #pragma unroll
-  for (int e = 0; e < 4; ++e) umma::split_f16x2(v[2 * e] * scale, v[2 * e + 1] * scale, h[e], l[e]);
+  for (int e = 0; e < 4; ++e) {
+    uint64_t x = f2_pack(v[2 * e], v[2 * e + 1]);
+    if (SCALE) x = f2_mul(x, ss);
+    cas_split2(x, h[e], l[e]);
+  }
   *reinterpret_cast<uint4*>(hi_dst) = make_uint4(h[0], h[1], h[2], h[3]);
   *reinterpret_cast<uint4*>(lo_dst) = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
 constexpr int kCasThreads = 256;  // warps w and w+4 share accumulator lanes 32 (w % 4) ..: each takes 16 of a row's 32 outputs
 constexpr int kCasChunks = kCasP0Rows * 8;                 // 1032 chunks of 8 samples per tile span
+constexpr int kCasSpan = kCasChunks * 8;                   // 8256 input samples per tile
 constexpr int kCasPer = (kCasChunks + kCasThreads - 1) / kCasThreads;  // chunks per thread (the last round holds 8)
-constexpr uint32_t kCasStageBytes = kCasChunks * 32;       // fp32 landing buffer of the next tile's span (cp.async)
-constexpr uint32_t kCasSmemTotal = kCasSmem + kCasStageBytes;
+constexpr int kCasPer4 = (2 * kCasChunks + kCasThreads - 1) / kCasThreads;  // float4s per thread
+constexpr uint32_t kCasStageBytes = kCasSpan * 4;          // fp32 landing buffer of the next tile's span (bulk async copy)
+constexpr int kCasTPitch = 36;                             // floats per row of the store-transposition buffers (144 B: conflict-free)
+constexpr uint32_t kCasT2Bytes = kCasRows2 * kCasTPitch * 4;  // level p+2 outputs on their way to coalesced global stores
+constexpr uint32_t kCasSmemTotal = kCasSmem + kCasStageBytes + kCasT2Bytes;
+static_assert(128 * kCasTPitch * 4 <= 2 * kCasP0Bytes, "the level p+1 transposition buffer aliases the level-p planes");
 
-__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src, int src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(umma::smem_u32(dst_smem)), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async4(void* dst_smem, const void* src, int src_bytes) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(umma::smem_u32(dst_smem)), "l"(src), "r"(src_bytes) : "memory");
-}
-
+// Software pipeline of one persistent CTA (two per SM), tile i, next tile j:
+//   wait MMA1(i) -> epilogue 1(i): level p+1 to global memory and, as fp16 hi/lo planes, to shared memory
+//   issue MMA2(i)                     | meanwhile: convert the landed span of tile j into the level-p planes
+//   issue MMA1(j), start the bulk copy of the tile after j | meanwhile: wait MMA2(i) -> epilogue 2(i): level p+2 to global memory
+// Levels 1 and 2 accumulate in separate TMEM columns so MMA1(j) can overlap epilogue 2(i).
 __global__ void __launch_bounds__(kCasThreads, 2) cascade_umma_kernel(const CascadeArgs a) {
   using namespace umma;
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ __align__(8) uint64_t img_bar, mma_bar;
+  __shared__ __align__(8) uint64_t img_bar, bar1, bar2, stage_bar;
   __shared__ uint32_t tmem_slot;
   // Order matters: the level p+2 MMA runs M = 128 over 63 useful rows; its surplus rows read on into the next buffer,
   // which must hold finite fp16 data (their products only reach accumulator rows that are never read back).
@@ -309,13 +346,16 @@ __global__ void __launch_bounds__(kCasThreads, 2) cascade_umma_kernel(const Casc
   uint8_t* p0l = p0h + kCasP0Bytes;
   uint8_t* img = p0l + kCasP0Bytes;
   float* stage = reinterpret_cast<float*>(img + kCasImgBytes);
+  float* tbuf2 = reinterpret_cast<float*>(img + kCasImgBytes + kCasStageBytes);
+  float* tbuf1 = reinterpret_cast<float*>(p0h);  // free between MMA1 of a tile and the conversion of the next one
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row = 32 * (warp & 3) + lane;  // accumulator lane = row of 32 outputs
   const int hf = warp >> 2;                // which 16 of them this thread handles
+  const bool two = a.n_levels == 2;
 
-  if (warp == 0) tmem_alloc(&tmem_slot, 64);
+  if (warp == 0) tmem_alloc(&tmem_slot, 128);
   if (tid == 0) {
-    mbar_init(&img_bar, 1), mbar_init(&mma_bar, 1);
+    mbar_init(&img_bar, 1), mbar_init(&bar1, 1), mbar_init(&bar2, 1), mbar_init(&stage_bar, 1);
     mbar_init_fence();
   }
   for (uint32_t i = tid; i < (2 * kCasP1Bytes + 2 * kCasP0Bytes) / 16; i += kCasThreads) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
@@ -329,12 +369,12 @@ __global__ void __launch_bounds__(kCasThreads, 2) cascade_umma_kernel(const Casc
   }
   const uint32_t tmem = tmem_slot;
   const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16) + 16 * hf;
-  uint32_t phase = 0;
-  bool img_ready = false;
-  constexpr float kInvD = 1.f / (kXScale * kDecScale);  // accumulator -> sample
-  constexpr float kToX = 1.f / kDecScale;               // accumulator -> kXScale * sample (the next operand)
+  uint32_t ph1 = 0, ph2 = 0, phs = 0;
+  // accumulator -> sample: level p+1 carries kXScale * kDecScale, level p+2 one more kDecScale (the level p+1 operand is the
+  // raw accumulator: no rescaling between the two steps)
+  constexpr float kInv1 = 1.f / (kXScale * kDecScale), kInv2 = kInv1 / kDecScale;
 
-  auto issue_level = [&](uint32_t hi0, uint32_t lo0, uint32_t lbo) {
+  auto issue_level = [&](uint32_t d, uint32_t hi0, uint32_t lo0, uint32_t lbo, uint64_t* bar) {
     const uint64_t a_desc = desc_hi(lbo);
     constexpr uint64_t B_DESC = desc_hi(64 * 16);
     constexpr uint32_t IDESC64 = idesc_f16(64), IDESC32 = idesc_f16(32);
@@ -343,16 +383,16 @@ __global__ void __launch_bounds__(kCasThreads, 2) cascade_umma_kernel(const Casc
     for (int j = 0; j < 8; ++j) {
       const uint32_t off = (uint32_t)((2 * j) & 7) * lbo + (j >= 4 ? 16u : 0u);  // chunks 8..15 = planes 0..7, one row on
       const uint64_t bd = make_desc(B_DESC, w0 + (uint32_t)j * 2048);
-      mma_f16(tmem, make_desc(a_desc, hi0 + off), bd, IDESC64, j ? 1u : 0u);
-      mma_f16(tmem, make_desc(a_desc, lo0 + off), bd, IDESC32, 1u);
+      mma_f16(d, make_desc(a_desc, hi0 + off), bd, IDESC64, j ? 1u : 0u);
+      mma_f16(d, make_desc(a_desc, lo0 + off), bd, IDESC32, 1u);
     }
-    commit(&mma_bar);
+    commit(bar);
   };
   // this thread's 16 accumulator columns: out[n] = D[n] + D[32 + n]
-  auto read_acc = [&](float (&o)[16]) {
+  auto read_acc = [&](uint32_t col0, float (&o)[16]) {
     float w[16];
-    tmem_ld16(lane_base, o);
-    tmem_ld16(lane_base + 32, w);
+    tmem_ld16(lane_base + col0, o);
+    tmem_ld16(lane_base + col0 + 32, w);
 #pragma unroll
     for (int j = 0; j < 16; ++j) o[j] += w[j];
   };
@@ -368,39 +408,92 @@ __global__ void __launch_bounds__(kCasThreads, 2) cascade_umma_kernel(const Casc
     }
     return tile;
   };
-  // Each thread lands the chunks it will itself convert, so only its own cp.async group orders the reuse of the stage.
-  auto prefetch = [&](int tile) {
+  struct Span {
+    const float* src;  // first sample of the span (may lie before the clip: zero extension)
+    int vlo, vhi;      // samples [vlo, vhi) of the span exist
+    bool bulk;         // 16-byte aligned: landed by one bulk async copy
+  };
+  auto span_of = [&](int tile) {
     const int b = tile / a.tiles_per_clip, t = tile - b * a.tiles_per_clip;
-    const long long n_p = clip_len(b);
     const long long base0 = 2 * ((long long)kCasOwn1 * t - 32) - 32;
-    const float* clip = a.in + (long long)b * a.in_stride;
-    const float* src = clip + base0;
-    const bool aligned = (reinterpret_cast<uintptr_t>(src) & 15) == 0;
-    const int vlo = (int)max(0LL, -base0), vhi = (int)min((long long)kCasChunks * 8, n_p - base0);  // existing samples of the span
-#pragma unroll
-    for (int i = 0; i < kCasPer; ++i) {
-      const int q = tid + kCasThreads * i, s0 = 8 * q;
-      if (q >= kCasChunks) break;
-      if (aligned) {
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int s = s0 + 4 * h;
-          const int n_ok = s < vlo ? 0 : max(0, min(4, vhi - s));
-          cp_async16(stage + s, n_ok ? src + s : clip, 4 * n_ok);
-        }
-      } else {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const bool ok = s0 + e >= vlo && s0 + e < vhi;
-          cp_async4(stage + s0 + e, ok ? src + s0 + e : clip, ok ? 4 : 0);
+    Span s;
+    s.src = a.in + (long long)b * a.in_stride + base0;
+    s.vlo = (int)max(0LL, -base0), s.vhi = (int)min((long long)kCasSpan, clip_len(b) - base0);
+    s.bulk = (reinterpret_cast<uintptr_t>(s.src) & 15) == 0;
+    return s;
+  };
+  // Start landing a tile's span in the stage (call when no thread reads the stage any more).  Aligned clips: thread 0 sends
+  // one bulk copy of the existing samples (whole float4s) and patches the <= 3 tail samples; otherwise every thread fetches
+  // the chunks it will convert itself.  Samples outside [vlo, vhi) are masked at conversion time, not written here.
+  auto start_stage = [&](int tile) {
+    const Span s = span_of(tile);
+    if (s.bulk) {
+      if (tid == 0) {
+        const int n4 = (s.vhi - s.vlo) & ~3;
+        for (int i = s.vlo + n4; i < s.vhi; ++i) stage[i] = __ldg(s.src + i);
+        if (n4 > 0) {
+          mbar_arrive_expect_tx(&stage_bar, (uint32_t)n4 * 4);
+          bulk_g2s(stage + s.vlo, s.src + s.vlo, (uint32_t)n4 * 4, &stage_bar);
+        } else {
+          mbar_arrive(&stage_bar);
         }
       }
+    } else {
+      for (int i = 0; i < kCasPer; ++i) {
+        const int q = tid + kCasThreads * i;
+        if (q < kCasChunks)
+          for (int e = 0; e < 8; ++e)
+            if (8 * q + e >= s.vlo && 8 * q + e < s.vhi) stage[8 * q + e] = __ldg(s.src + 8 * q + e);
+      }
+      if (tid == 0) mbar_arrive(&stage_bar);
     }
-    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  // stage -> level-p operand planes (fp16 hi/lo, transposed chunk planes)
+  auto convert = [&](int tile) {
+    const Span s = span_of(tile);
+    mbar_wait(&stage_bar, phs);
+    phs ^= 1;
+    const bool interior = s.vlo == 0 && s.vhi == kCasSpan;
+    const uint64_t ss = f2_pack(kXScale, kXScale);
+    // one float4 per thread and round: consecutive lanes read consecutive 16 B of the stage and write 8-byte halves of the
+    // operand chunks (both conflict-free)
+#pragma unroll
+    for (int i = 0; i < kCasPer4; ++i) {
+      const int f = tid + kCasThreads * i;
+      if (f < 2 * kCasChunks) {
+        const float4 v = *reinterpret_cast<const float4*>(stage + 4 * f);
+        float x[4] = {v.x, v.y, v.z, v.w};
+        if (!interior) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) x[e] = (4 * f + e >= s.vlo && 4 * f + e < s.vhi) ? x[e] : 0.f;
+        }
+        uint32_t h[2], l[2];
+        cas_split2(f2_mul(f2_pack(x[0], x[1]), ss), h[0], l[0]);
+        cas_split2(f2_mul(f2_pack(x[2], x[3]), ss), h[1], l[1]);
+        const int q = f >> 1;
+        const uint32_t off = (uint32_t)(q & 7) * kCasLBO0 + (uint32_t)(q >> 3) * 16 + (uint32_t)(f & 1) * 8;
+        *reinterpret_cast<uint2*>(p0h + off) = make_uint2(h[0], h[1]);
+        *reinterpret_cast<uint2*>(p0l + off) = make_uint2(l[0], l[1]);
+      }
+    }
   };
 
   int tile = next_tile(blockIdx.x);
-  if (tile < a.n_tiles) prefetch(tile);
+  if (tile < a.n_tiles) {
+    start_stage(tile);
+    convert(tile);
+    fence_proxy_async();
+    __syncthreads();
+    const int nxt = next_tile(tile + gridDim.x);
+    if (nxt < a.n_tiles) start_stage(nxt);
+    if (tid == 0) {
+      mbar_wait(&img_bar, 0);
+      fence_after_sync();
+      issue_level(tmem, smem_u32(p0h), smem_u32(p0l), kCasLBO0, &bar1);
+    }
+  } else if (tid == 0) {
+    mbar_wait(&img_bar, 0);  // never leave with a bulk copy in flight
+  }
   while (tile < a.n_tiles) {
     const int b = tile / a.tiles_per_clip, t = tile - b * a.tiles_per_clip;
     const long long n_p = clip_len(b);
@@ -408,103 +501,109 @@ __global__ void __launch_bounds__(kCasThreads, 2) cascade_umma_kernel(const Casc
     const long long o_lo2 = (long long)kCasOwn2 * t, o_lo1 = (long long)kCasOwn1 * t - 32;
     const int nxt = next_tile(tile + gridDim.x);
 
-    // ---- stage -> registers, start the next tile's copies, then fp32 -> fp16 hi/lo into the transposed chunk planes
-    {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-      float x[kCasPer][8];
-#pragma unroll
-      for (int i = 0; i < kCasPer; ++i) {
-        const int q = tid + kCasThreads * i;
-        if (q < kCasChunks) {
-          const float4 v0 = *reinterpret_cast<const float4*>(stage + 8 * q), v1 = *reinterpret_cast<const float4*>(stage + 8 * q + 4);
-          x[i][0] = v0.x, x[i][1] = v0.y, x[i][2] = v0.z, x[i][3] = v0.w, x[i][4] = v1.x, x[i][5] = v1.y, x[i][6] = v1.z, x[i][7] = v1.w;
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < kCasPer; ++i) {
-        const int q = tid + kCasThreads * i;
-        if (q < kCasChunks) {
-          const uint32_t off = (uint32_t)(q & 7) * kCasLBO0 + (uint32_t)(q >> 3) * 16;
-          cas_store_split8(p0h + off, p0l + off, x[i], kXScale);
-        }
-      }
-      if (nxt < a.n_tiles) prefetch(nxt);  // after this thread's reads of the stage have been consumed
-    }
-    fence_proxy_async();
-    __syncthreads();
-    if (tid == 0) {
-      if (!img_ready) mbar_wait(&img_bar, 0), img_ready = true;
-      fence_after_sync();
-      issue_level(smem_u32(p0h), smem_u32(p0l), kCasLBO0);
-    }
-    mbar_wait(&mma_bar, phase);
-    phase ^= 1;
-    fence_after_sync();
-
     // ---- level p+1
+    mbar_wait(&bar1, ph1);
+    ph1 ^= 1;
+    fence_after_sync();
     {
       float o[16];
-      read_acc(o);
+      read_acc(0, o);
       const long long i1 = o_lo1 + 32LL * row + 16 * hf;  // level p+1 index of o[0]
-      // samples that do not exist (index < 0 or >= floor(n_p / 2)) are zero
-      const int zlo = (int)min(16LL, max(0LL, -i1)), zhi = (int)min(16LL, max(0LL, n_half1 - i1));
+      if (o_lo1 < 0 || o_lo1 + 128 * 32 > n_half1) {
+        // samples that do not exist (index < 0 or >= floor(n_p / 2)) are zero
+        const int zlo = (int)min(16LL, max(0LL, -i1)), zhi = (int)min(16LL, max(0LL, n_half1 - i1));
 #pragma unroll
-      for (int n = 0; n < 16; ++n) o[n] = (n >= zlo && n < zhi) ? o[n] : 0.f;
-      if (row >= 1 && row <= 126 && i1 < n1) {  // rows 0 and 127 are the halo the next level needs
-        float4* dst = reinterpret_cast<float4*>(a.out1 + (long long)b * a.stride1 + i1);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) dst[q] = make_float4(o[4 * q] * kInvD, o[4 * q + 1] * kInvD, o[4 * q + 2] * kInvD, o[4 * q + 3] * kInvD);
+        for (int n = 0; n < 16; ++n) o[n] = (n >= zlo && n < zhi) ? o[n] : 0.f;
       }
-      if (a.n_levels == 2) {
+      // fp32 outputs go through shared memory so that the global stores are row-contiguous (a thread owns a row: storing
+      // straight from registers would touch 32 different lines per instruction)
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        *reinterpret_cast<float4*>(tbuf1 + row * kCasTPitch + 16 * hf + 4 * q) =
+            make_float4(o[4 * q] * kInv1, o[4 * q + 1] * kInv1, o[4 * q + 2] * kInv1, o[4 * q + 3] * kInv1);
+      if (two) {
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
           float v[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) v[e] = o[8 * i + e];
           const uint32_t off = (uint32_t)(4 * (row & 1) + 2 * hf + i) * kCasLBO1 + (uint32_t)(row >> 1) * 16;
-          cas_store_split8(p1h + off, p1l + off, v, kToX);
-        }
-      }
-    }
-    if (a.n_levels == 2) {
-      fence_before_sync();
-      fence_proxy_async();
-      __syncthreads();
-      if (tid == 0) {
-        fence_after_sync();
-        issue_level(smem_u32(p1h), smem_u32(p1l), kCasLBO1);
-      }
-      mbar_wait(&mma_bar, phase);
-      phase ^= 1;
-      fence_after_sync();
-      if ((warp & 3) < 2) {  // rows 0..62 live in accumulator lanes 0..63 (tcgen05.ld is warp-collective: no per-thread predicate)
-        float o[16];
-        read_acc(o);
-        const long long i2 = o_lo2 + 32LL * row + 16 * hf;
-        if (row < kCasRows2 && i2 < n2) {
-          const int zhi = (int)min(16LL, max(0LL, n_half2 - i2));
-          float4* dst = reinterpret_cast<float4*>(a.out2 + (long long)b * a.stride2 + i2);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            float4 v;
-            v.x = (4 * q + 0 < zhi) ? o[4 * q + 0] * kInvD : 0.f;
-            v.y = (4 * q + 1 < zhi) ? o[4 * q + 1] * kInvD : 0.f;
-            v.z = (4 * q + 2 < zhi) ? o[4 * q + 2] * kInvD : 0.f;
-            v.w = (4 * q + 3 < zhi) ? o[4 * q + 3] * kInvD : 0.f;
-            dst[q] = v;
-          }
+          cas_store_split8<false>(p1h + off, p1l + off, v, 1.f);
         }
       }
     }
     fence_before_sync();
-    __syncthreads();  // accumulator drained and operands consumed: the next tile may overwrite both
-    fence_after_sync();
+    fence_proxy_async();
+    __syncthreads();
+    if (two && tid == 0) {
+      fence_after_sync();
+      issue_level(tmem + 64, smem_u32(p1h), smem_u32(p1l), kCasLBO1, &bar2);
+    }
+    {
+      // rows 1..126 are owned (0 and 127 are the halo the next level needs): 1008 float4s, 8 per row
+      float* dst = a.out1 + (long long)b * a.stride1 + o_lo1;
+      const long long lim = n1 - o_lo1;  // row-local indices < lim exist (the buffers are padded to whole rows of 32)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int idx = tid + kCasThreads * i;
+        const int r = 1 + (idx >> 3), c4 = idx & 7;
+        if (idx < 126 * 8 && 32LL * r < lim)
+          *reinterpret_cast<float4*>(dst + 32 * r + 4 * c4) = *reinterpret_cast<const float4*>(tbuf1 + r * kCasTPitch + 4 * c4);
+      }
+    }
+    __syncthreads();  // tbuf1 aliases the level-p planes the conversion below overwrites
+    // ---- next tile's operand while MMA2 runs (the level-p planes are free: MMA1 of this tile has completed)
+    if (nxt < a.n_tiles) convert(nxt);
+    fence_proxy_async();
+    __syncthreads();
+    if (nxt < a.n_tiles) {
+      const int nxt2 = next_tile(nxt + gridDim.x);
+      if (nxt2 < a.n_tiles) start_stage(nxt2);  // every thread has consumed the stage
+      if (tid == 0) {
+        fence_after_sync();
+        issue_level(tmem, smem_u32(p0h), smem_u32(p0l), kCasLBO0, &bar1);
+      }
+    }
+    // ---- level p+2 (overlaps MMA1 of the next tile)
+    if (two) {
+      mbar_wait(&bar2, ph2);
+      ph2 ^= 1;
+      fence_after_sync();
+      if ((warp & 3) < 2) {  // rows 0..62 live in accumulator lanes 0..63 (tcgen05.ld is warp-collective: no per-thread predicate)
+        float o[16];
+        read_acc(64, o);
+        const long long i2 = o_lo2 + 32LL * row + 16 * hf;
+        const int zhi = (int)min(16LL, max(0LL, n_half2 - i2));
+        if (row < kCasRows2) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float4 v;
+            v.x = (4 * q + 0 < zhi) ? o[4 * q + 0] * kInv2 : 0.f;
+            v.y = (4 * q + 1 < zhi) ? o[4 * q + 1] * kInv2 : 0.f;
+            v.z = (4 * q + 2 < zhi) ? o[4 * q + 2] * kInv2 : 0.f;
+            v.w = (4 * q + 3 < zhi) ? o[4 * q + 3] * kInv2 : 0.f;
+            *reinterpret_cast<float4*>(tbuf2 + row * kCasTPitch + 16 * hf + 4 * q) = v;
+          }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // warps 0, 1, 4, 5
+        float* dst = a.out2 + (long long)b * a.stride2 + o_lo2;
+        const long long lim = n2 - o_lo2;
+        const int t128 = (warp >> 2) * 64 + (warp & 1) * 32 + lane;  // 0..127 over the four warps
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int idx = t128 + 128 * i;
+          const int r = idx >> 3, c4 = idx & 7;
+          if (idx < kCasRows2 * 8 && 32LL * r < lim)
+            *reinterpret_cast<float4*>(dst + 32 * r + 4 * c4) = *reinterpret_cast<const float4*>(tbuf2 + r * kCasTPitch + 4 * c4);
+        }
+      }
+      fence_before_sync();  // ordered before the next MMA2 by the barrier that precedes its issue
+    }
     tile = nxt;
   }
-  if (tid == 0 && !img_ready) mbar_wait(&img_bar, 0);  // never leave with a bulk copy in flight
   fence_before_sync();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, 64);
+  if (warp == 0) tmem_dealloc(tmem, 128);
 }
 
 // ---- tensor-core filter bank (tcgen05): one CTA = 128 frames of one octave x all filters x all of K ----------------
