@@ -624,16 +624,21 @@ struct BankArgs {
   float* out;
 };
 
+constexpr uint32_t kBankLBO = 129 * 16;                  // chunk pitch of the frame operand: odd multiple of 16 B (conflict-free 8-byte scatter)
+constexpr uint32_t kBankAHalf = (kUKB / 8) * kBankLBO;   // one of {hi, lo}: 8 chunks x 128 rows x 16 B (+ pad)
+
 template <int NPAD>
 __global__ void __launch_bounds__(160) cqt_bank_umma_kernel(const BankArgs a) {
   using namespace umma;
-  constexpr uint32_t A_HALF = 128 * kUKB * 2;                // 16 KB: 8 chunks x 128 rows x 16 B
+  constexpr uint32_t A_HALF = kBankAHalf;
   constexpr uint32_t B_BYTES = (kUKB / 8) * 2 * NPAD * 16;   // 8 chunks x 2*NPAD rows x 16 B
   constexpr uint32_t STAGE = 2 * A_HALF + B_BYTES;
   constexpr uint32_t TMEM_COLS = (2 * NPAD <= 64) ? 64 : ((2 * NPAD <= 128) ? 128 : 256);
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t full_bar[kUStages], empty_bar[kUStages], done_bar;
   __shared__ uint32_t tmem_slot;
+  __shared__ long long s_g0[128];   // index (into the octave's level array) of the first sample of frame row r
+  __shared__ int2 s_valid[128];     // samples [x, y) of that frame exist (the rest is the zero padding of centred frames)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int octave = blockIdx.y;
@@ -646,27 +651,39 @@ __global__ void __launch_bounds__(160) cqt_bank_umma_kernel(const BankArgs a) {
     mbar_init(&done_bar, 1);
     mbar_init_fence();
   }
-  fence_before_sync();
-  __syncthreads();
-  fence_after_sync();
-  const uint32_t tmem = tmem_slot;
-
+  // ---- frame row `tid`: which clip / frame, where its samples live
+  bool in_range = false, real_frame = false;
+  int b = 0, t = 0;
   if (warp < 4) {
-    // ---------------------------------------------------------------- producer: frame row `tid`
     const long long m = m0 + tid;
-    const bool in_range = m < (long long)a.B * a.T_max;
-    const int b = in_range ? (int)(m / a.T_max) : 0, t = in_range ? (int)(m % a.T_max) : 0;
+    in_range = m < (long long)a.B * a.T_max;
+    b = in_range ? (int)(m / a.T_max) : 0, t = in_range ? (int)(m % a.T_max) : 0;
     const long long n0 = a.lengths ? a.lengths[b] : a.n_uniform;
     long long T = -1;
     for (int i = 0; i < a.n_oct; ++i) {
       const long long ti = 1 + ((n0 + (1LL << i) - 1) >> i) / (a.hop0 >> i);
       T = (T < 0 || ti < T) ? ti : T;
     }
-    const bool real_frame = in_range && t < T;
+    real_frame = in_range && t < T;
     const long long len = (n0 + (1LL << octave) - 1) >> octave;
-    const float* src = a.level[octave] + (long long)b * a.stride[octave];
     const long long first = (long long)t * (a.hop0 >> octave) - a.n_fft / 2;  // centred frame, zero padded (pad_mode='constant')
+    s_g0[tid] = (long long)b * a.stride[octave] + first;
+    s_valid[tid] = real_frame ? make_int2((int)max(0LL, -first), (int)max(0LL, min((long long)a.n_fft, len - first))) : make_int2(0, 0);
+  }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_slot;
 
+  if (warp < 4) {
+    // ---------------------------------------------------------------- producer
+    // A warp stages 32 frame rows; one instruction covers two rows x 64 samples: lanes 0-15 read the 16 float4s of one row,
+    // lanes 16-31 those of the next (coalesced 256-byte runs), convert to fp16 hi/lo and scatter 8-byte halves of the
+    // operand chunks (chunk c of row r at c * kBankLBO + r * 16).
+    const float* level = a.level[octave];
+    const bool base_aligned = (reinterpret_cast<uintptr_t>(level) & 15) == 0;
+    const int f = lane & 15;
+    const uint64_t ss = f2_pack(kXScale, kXScale);
     for (int kb = 0; kb < n_kb; ++kb) {
       const int s = kb % kUStages;
       const uint32_t phase = (kb / kUStages) & 1;
@@ -676,29 +693,31 @@ __global__ void __launch_bounds__(160) cqt_bank_umma_kernel(const BankArgs a) {
         mbar_arrive_expect_tx(&full_bar[s], B_BYTES);
         bulk_g2s(stage + 2 * A_HALF, reinterpret_cast<const uint8_t*>(a.bank_img) + (size_t)kb * B_BYTES, B_BYTES, &full_bar[s]);
       }
-      const long long i0 = first + (long long)kb * kUKB;
-      float x[kUKB];
-      const float* p = src + i0;
-      if (real_frame && i0 >= 0 && i0 + kUKB <= len && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {
+      const int i0 = kb * kUKB + 4 * f;  // frame-local index of this lane's first sample
+      // all 16 loads are issued before the first conversion consumes one (the branch below must not serialise them)
+      float x[16][4];
 #pragma unroll
-        for (int q = 0; q < kUKB / 4; ++q) {
-          const float4 v = __ldg(reinterpret_cast<const float4*>(p) + q);
-          x[4 * q] = v.x, x[4 * q + 1] = v.y, x[4 * q + 2] = v.z, x[4 * q + 3] = v.w;
-        }
-      } else {
+      for (int it = 0; it < 16; ++it) {
+        const int r = warp * 32 + 2 * it + (lane >> 4);
+        const long long g = s_g0[r] + i0;
+        const int2 v = s_valid[r];
+        if (i0 >= v.x && i0 + 4 <= v.y && base_aligned && (g & 3) == 0) {
+          const float4 q = __ldg(reinterpret_cast<const float4*>(level + g));
+          x[it][0] = q.x, x[it][1] = q.y, x[it][2] = q.z, x[it][3] = q.w;
+        } else {
 #pragma unroll
-        for (int q = 0; q < kUKB; ++q) {
-          const long long i = i0 + q;
-          x[q] = (real_frame && i >= 0 && i < len) ? __ldg(src + i) : 0.f;
+          for (int e = 0; e < 4; ++e) x[it][e] = (i0 + e >= v.x && i0 + e < v.y) ? __ldg(level + g + e) : 0.f;
         }
       }
 #pragma unroll
-      for (int c = 0; c < kUKB / 8; ++c) {
-        uint32_t hi[4], lo[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) split_f16x2(x[8 * c + 2 * e] * kXScale, x[8 * c + 2 * e + 1] * kXScale, hi[e], lo[e]);
-        *reinterpret_cast<uint4*>(stage + c * 2048 + tid * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<uint4*>(stage + A_HALF + c * 2048 + tid * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      for (int it = 0; it < 16; ++it) {
+        const int r = warp * 32 + 2 * it + (lane >> 4);
+        uint32_t h0, l0, h1, l1;
+        cas_split2(f2_mul(f2_pack(x[it][0], x[it][1]), ss), h0, l0);
+        cas_split2(f2_mul(f2_pack(x[it][2], x[it][3]), ss), h1, l1);
+        const uint32_t off = (uint32_t)(f >> 1) * kBankLBO + (uint32_t)r * 16 + (uint32_t)(f & 1) * 8;
+        *reinterpret_cast<uint2*>(stage + off) = make_uint2(h0, h1);
+        *reinterpret_cast<uint2*>(stage + A_HALF + off) = make_uint2(l0, l1);
       }
       fence_proxy_async();
       if (tid != 0) mbar_arrive(&full_bar[s]);
@@ -729,10 +748,9 @@ __global__ void __launch_bounds__(160) cqt_bank_umma_kernel(const BankArgs a) {
         }
       }
     }
-    (void)lane;
   } else if (lane == 0) {
     // ---------------------------------------------------------------- MMA issuer
-    constexpr uint64_t A_DESC = desc_hi(128 * 16);       // chunk stride 2 KB (128 rows x 16 B)
+    constexpr uint64_t A_DESC = desc_hi(kBankLBO);
     constexpr uint64_t B_DESC = desc_hi(2 * NPAD * 16);  // chunk stride = 2*NPAD rows x 16 B
     constexpr uint32_t IDESC_WIDE = idesc_f16(2 * NPAD), IDESC_NARROW = idesc_f16(NPAD);
     for (int kb = 0; kb < n_kb; ++kb) {
@@ -743,8 +761,8 @@ __global__ void __launch_bounds__(160) cqt_bank_umma_kernel(const BankArgs a) {
 #pragma unroll
       for (int j = 0; j < kUKB / 16; ++j) {
         const uint64_t bd = make_desc(B_DESC, base + 2 * A_HALF + j * (2 * 2 * NPAD * 16));
-        mma_f16(tmem, make_desc(A_DESC, base + j * 4096), bd, IDESC_WIDE, (kb | j) ? 1u : 0u);
-        mma_f16(tmem, make_desc(A_DESC, base + A_HALF + j * 4096), bd, IDESC_NARROW, 1u);
+        mma_f16(tmem, make_desc(A_DESC, base + j * 2 * kBankLBO), bd, IDESC_WIDE, (kb | j) ? 1u : 0u);
+        mma_f16(tmem, make_desc(A_DESC, base + A_HALF + j * 2 * kBankLBO), bd, IDESC_NARROW, 1u);
       }
       commit(&empty_bar[s]);
     }
@@ -836,7 +854,7 @@ static void run_cqt(ake_cqt* p, const float* audio, long long stride, const int6
     ba.n_bins = p->n_bins, ba.bpo = p->bpo, ba.mode = mode, ba.bank_img = p->d_bank_img, ba.scale = p->d_scale_umma, ba.out = out;
     dim3 grid((unsigned)cdiv64(rows, 128), p->n_oct);
     if (p->npad == 80) {
-      constexpr size_t smem = kUStages * (2 * 128 * kUKB * 2 + (kUKB / 8) * 2 * 80 * 16);
+      constexpr size_t smem = kUStages * (2 * kBankAHalf + (kUKB / 8) * 2 * 80 * 16);
       static bool configured = false;
       if (!configured) {
         AKE_CUDA(cudaFuncSetAttribute(cqt_bank_umma_kernel<80>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -844,7 +862,7 @@ static void run_cqt(ake_cqt* p, const float* audio, long long stride, const int6
       }
       cqt_bank_umma_kernel<80><<<grid, 160, smem, st>>>(ba);
     } else {
-      constexpr size_t smem = kUStages * (2 * 128 * kUKB * 2 + (kUKB / 8) * 2 * 32 * 16);
+      constexpr size_t smem = kUStages * (2 * kBankAHalf + (kUKB / 8) * 2 * 32 * 16);
       static bool configured = false;
       if (!configured) {
         AKE_CUDA(cudaFuncSetAttribute(cqt_bank_umma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -461,7 +461,20 @@ void Fwd::run(const float* mel, float* key_out, float* tonic_out, float* genre_o
     View cat;  // input of the pc2pc stack
     if (L == 0) {
       cat = alloc(1, 12, Tn);
-      semitone_pool(0, p_in, cat, 0);
+      if (!train && p->convs[lp.sem].Cout == 1) {
+        // eval mode: conv + BN + act + octave pool in one pass over the log-CQT
+        const Conv& c = p->convs[lp.sem];
+        View semi = alloc(1, S, Tn);
+        if (!dry) {
+          ProfScope prof("pcn.semitone", st);
+          l0_semitone_pool_kernel<<<dim3(cdiv(Tn, 128), 12, B), 128, 0, st>>>(p_in.p, p->d_params + c.w_off, scale_of(c, false),
+                                                                            shift_of(c, false), semi.p, cat.p, P, Tn, 1, 0);
+          AKE_LAUNCHED();
+        }
+        tap("l0.semi", semi);
+      } else {
+        semitone_pool(0, p_in, cat, 0);
+      }
       tap("l0.pool", cat);
     } else {
       const bool fast = p->umma && !train && L == 1 && Tn >= 7;

@@ -316,6 +316,40 @@ __global__ void octmax_kernel(const float* __restrict__ in, int B, int C, int R,
   }
 }
 
+// ---- layer 0 in one pass (eval mode): pool_semi Conv2d(1,1,3,stride (3,1),time-circular) + BN + LeakyReLU (models.py:313-315,
+// 361-363) and Pitch2PitchClassPool (models.py:368) straight from the log-CQT.  One thread per (pitch class, frame): it walks
+// the octaves, so every semitone is accumulated by the same instruction sequence (transposition equivariance stays bit exact).
+// grid (frames / 128, 12, B).  `semi` (B,1,S,T) keeps the pre-pool map for the parity taps.
+__global__ void __launch_bounds__(128) l0_semitone_pool_kernel(const float* __restrict__ mel, const float* __restrict__ w,
+                                                                const float* __restrict__ scale, const float* __restrict__ shift,
+                                                                float* __restrict__ semi, float* __restrict__ pc, int P, int T,
+                                                                int C_total, int coff) {
+  const int t = blockIdx.x * 128 + threadIdx.x, c = blockIdx.y, b = blockIdx.z;
+  if (t >= T) return;
+  const int tm = t == 0 ? T - 1 : t - 1, tp = t == T - 1 ? 0 : t + 1;
+  float k[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) k[i] = __ldg(w + i);
+  const float sc = __ldg(scale), sh = __ldg(shift);
+  const int S = P / 3;
+  float best = -INFINITY;
+  for (int j = c; j < S; j += 12) {
+    const float* r0 = mel + ((long long)b * P + 3 * j) * T;
+    float acc = 0.f;
+#pragma unroll
+    for (int dp = 0; dp < 3; ++dp) {
+      const float* r = r0 + (long long)dp * T;
+      acc = fmaf(k[dp * 3 + 0], __ldg(r + tm), acc);
+      acc = fmaf(k[dp * 3 + 1], __ldg(r + t), acc);
+      acc = fmaf(k[dp * 3 + 2], __ldg(r + tp), acc);
+    }
+    const float v = leaky(fmaf(acc, sc, sh));
+    semi[((long long)b * S + j) * T + t] = v;
+    best = fmaxf(best, v);
+  }
+  pc[(((long long)b * C_total + coff) * 12 + c) * T + t] = best;
+}
+
 // ---- train-mode BatchNorm pieces (batch statistics over (B, rows, T) per channel) ---------------
 // stats[2c] += sum, stats[2c+1] += sum of squares (double); in is (B, C_total, R, T) viewed at channel coff + c.
 __global__ void bn_stats_kernel(const float* __restrict__ in, int B, int C_total, int coff, int RT_elems,
