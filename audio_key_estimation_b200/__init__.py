@@ -8,5 +8,6 @@ from .models import PitchClassNet, decode  # noqa: F401
 from .cqt import CQTPlan, cqt, cqt_logmag  # noqa: F401
 from .pipeline import KeyEstimator  # noqa: F401
 from .options import default_opt  # noqa: F401
+from .training import TrainStep, criterion  # noqa: F401
 
-__all__ = ["PitchClassNet", "decode", "CQTPlan", "cqt", "cqt_logmag", "KeyEstimator", "default_opt"]
+__all__ = ["PitchClassNet", "decode", "CQTPlan", "cqt", "cqt_logmag", "KeyEstimator", "default_opt", "TrainStep", "criterion"]

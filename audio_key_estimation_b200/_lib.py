@@ -43,6 +43,8 @@ _SIGNATURES = {
     "ake_pcn_workspace_bytes": (C.c_size_t, [_P, C.c_int, C.c_int, C.c_int]),
     "ake_pcn_forward_f32": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, C.c_int, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "ake_pcn_bn_channels": (C.c_int, [_P]),
+    "ake_pcn_backward_f32": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, _P, C.c_size_t, _P]),
+    "ake_loss_f32": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_float, C.c_float, C.c_float, _P, _P, _P, _P, _P]),
     "ake_pcn_get_config": (C.c_int, [_P, C.POINTER(PcnConfig)]),
     "ake_pcn_get_tap": (C.c_int64, [_P, C.c_char_p, _P, C.c_int64, _P]),
     "ake_decode_f32": (C.c_int, [_P, _P, _P, C.c_int, _P, _P, _P, _P]),

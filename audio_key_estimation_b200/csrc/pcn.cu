@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "pcn_kernels.cuh"
+#include "pcn_train_kernels.cuh"
 #include "pcn_umma.cuh"
 
 namespace ake {
@@ -94,6 +95,8 @@ struct Conv {
   int ss_off = 0;           // into the scale/shift tables
 };
 
+struct TrainTape;
+
 struct LayerPlan {
   int prev_p = 0, prev_pc = 0, out_p = 0, out_pc = 0;
   int sem = -1, up = -1;
@@ -128,6 +131,7 @@ struct ake_pcn {
   float* d_ss_heads = nullptr;      // [scale 64 | shift 64] of that fused conv (tonic channels first)
   bool umma_heads = false;
   std::map<std::string, std::pair<const float*, int64_t>> taps;
+  struct ake::TrainTape* tape = nullptr;  // activations kept by the last bn_mode = 2 forward (pcn_train.cuh)
 };
 
 namespace ake {
@@ -309,13 +313,18 @@ static void launch_conv(const ConvArgs& a, const ConvGeom& g, int co_tile, int B
     if (co_tile == 1) return launch_conv_t<12, 7, 1, 12, 1, 4>(a, B, 8, st);
   } else if (g.KH == 7 && g.KW == 7 && g.SR == 1) {
     if (co_tile == 8) return launch_conv_t<7, 7, 1, 32, 8, 8>(a, B, 4, st);
+    if (co_tile == 4) return launch_conv_t<7, 7, 1, 32, 4, 8>(a, B, 4, st);
+    if (co_tile == 1) return launch_conv_t<7, 7, 1, 32, 1, 8>(a, B, 4, st);
   } else if (g.KH == 3 && g.KW == 3 && g.SR == 3) {
     if (co_tile == 8) return launch_conv_t<3, 3, 3, 32, 8, 8>(a, B, 4, st);
     if (co_tile == 1) return launch_conv_t<3, 3, 3, 32, 1, 8>(a, B, 4, st);
   } else if (g.KH == 1 && g.KW == 7 && g.SR == 1) {
     if (co_tile == 8) return launch_conv_t<1, 7, 1, 12, 8, 4>(a, B, 8, st);
+    if (co_tile == 4) return launch_conv_t<1, 7, 1, 12, 4, 4>(a, B, 8, st);
+    if (co_tile == 1) return launch_conv_t<1, 7, 1, 12, 1, 4>(a, B, 8, st);
   } else if (g.KH == 2 && g.KW == 7 && g.SR == 1) {
     if (co_tile == 1) return launch_conv_t<2, 7, 1, 12, 1, 4>(a, B, 8, st);
+    if (co_tile == 8) return launch_conv_t<2, 7, 1, 12, 8, 4>(a, B, 8, st);
   }
   fail(AKE_ERR_UNSUPPORTED, "no conv kernel for KH=%d KW=%d SR=%d co_tile=%d", g.KH, g.KW, g.SR, co_tile);
 }
@@ -417,6 +426,9 @@ struct Fwd {
   }
 
   void run(const float* mel, float* key_out, float* tonic_out, float* genre_out);
+  // training step (pcn_train.cuh): forward that keeps every activation, and the backward pass over them
+  void run_keep(const float* mel, float* key_out, float* tonic_out, float* genre_out, TrainTape& tape);
+  void backward_keep(const TrainTape& tape, const float* d_key, const float* d_tonic, const float* d_genre, float* grads);
 };
 
 void Fwd::run(const float* mel, float* key_out, float* tonic_out, float* genre_out) {
@@ -749,6 +761,10 @@ void Fwd::run(const float* mel, float* key_out, float* tonic_out, float* genre_o
   }
 }
 
+}  // namespace ake
+#include "pcn_train.cuh"
+namespace ake {
+
 static void upload_params(ake_pcn* p, const float* flat_dev, int64_t n, cudaStream_t st) {
   if (n != p->n_params) fail(AKE_ERR_INVALID, "expected %lld parameter floats, got %lld", (long long)p->n_params, (long long)n);
   if (!p->d_params) {
@@ -893,6 +909,7 @@ void ake_pcn_destroy(ake_pcn* p) {
   cudaFree(p->d_wimg_pc);
   cudaFree(p->d_wimg_heads);
   cudaFree(p->d_ss_heads);
+  delete p->tape;
   delete p;
 }
 
@@ -925,7 +942,13 @@ size_t ake_pcn_workspace_bytes(const ake_pcn* p, int B, int T, int bn_mode) {
   try {
     Fwd f(const_cast<ake_pcn*>(p), B, T, bn_mode != 0, nullptr, 0, nullptr);
     f.seq_len = nullptr, f.bn_stats_out = nullptr;
-    f.run(nullptr, nullptr, nullptr, nullptr);
+    if (bn_mode == 2) {
+      TrainTape tape;
+      f.run_keep(nullptr, nullptr, nullptr, nullptr, tape);
+      f.backward_keep(tape, nullptr, nullptr, nullptr, nullptr);
+    } else {
+      f.run(nullptr, nullptr, nullptr, nullptr);
+    }
     return f.arena.off + 256;
   } catch (const std::exception& e) {
     set_last_error(e.what());
@@ -944,7 +967,47 @@ int ake_pcn_forward_f32(ake_pcn* p, const float* mel_dev, int B, int T, const in
     ProfScope prof("pcn.total", static_cast<cudaStream_t>(stream));
     Fwd f(p, B, T, bn_mode != 0, ws_dev, ws_bytes, static_cast<cudaStream_t>(stream));
     f.seq_len = seq_len_dev, f.bn_stats_out = bn_stats_out_dev;
-    f.run(mel_dev, key_out_dev, tonic_out_dev, p->cfg.genre ? genre_out_dev : nullptr);
+    if (bn_mode == 2) {
+      if (!p->tape) p->tape = new TrainTape();
+      p->tape->valid = false;
+      f.run_keep(mel_dev, key_out_dev, tonic_out_dev, p->cfg.genre ? genre_out_dev : nullptr, *p->tape);
+      p->tape->ws = ws_dev;
+    } else {
+      f.run(mel_dev, key_out_dev, tonic_out_dev, p->cfg.genre ? genre_out_dev : nullptr);
+    }
+  });
+}
+
+int ake_pcn_backward_f32(ake_pcn* p, const float* d_key_out_dev, const float* d_tonic_out_dev, const float* d_genre_out_dev,
+                         float* grads_out_dev, int64_t n_floats, void* ws_dev, size_t ws_bytes, void* stream) {
+  return guarded([&] {
+    if (!p || !grads_out_dev || !ws_dev) fail(AKE_ERR_INVALID, "null argument");
+    if (!d_key_out_dev && !d_tonic_out_dev && !d_genre_out_dev) fail(AKE_ERR_INVALID, "no output gradient given");
+    if (n_floats != p->n_params) fail(AKE_ERR_INVALID, "grads_out_dev must hold %lld floats", (long long)p->n_params);
+    if (!p->tape || !p->tape->valid) fail(AKE_ERR_INVALID, "no kept forward: call ake_pcn_forward_f32 with bn_mode = 2 first");
+    if (p->tape->ws != ws_dev) fail(AKE_ERR_INVALID, "the backward pass needs the workspace of the kept forward");
+    ProfScope prof("pcn.backward", static_cast<cudaStream_t>(stream));
+    Fwd f(p, p->tape->B, p->tape->T, true, ws_dev, ws_bytes, static_cast<cudaStream_t>(stream));
+    f.arena.off = p->tape->ws_off;
+    f.seq_len = p->tape->seq_len, f.bn_stats_out = nullptr;
+    f.backward_keep(*p->tape, d_key_out_dev, d_tonic_out_dev, d_genre_out_dev, grads_out_dev);
+    p->tape->valid = false;  // the backward pass reuses nothing: one backward per kept forward
+  });
+}
+
+int ake_loss_f32(const float* key_out_dev, const float* tonic_out_dev, const float* genre_out_dev, const float* key_labels_dev,
+                 const int32_t* tonic_idx_dev, const int32_t* genre_idx_dev, int B, float key_weight, float tonic_weight,
+                 float genre_weight, float* loss_out_dev, float* d_key_out_dev, float* d_tonic_out_dev, float* d_genre_out_dev,
+                 void* stream) {
+  return guarded([&] {
+    if (!key_out_dev || !tonic_out_dev || !key_labels_dev || !tonic_idx_dev || !loss_out_dev || !d_key_out_dev || !d_tonic_out_dev)
+      fail(AKE_ERR_INVALID, "null argument");
+    if (genre_out_dev && !d_genre_out_dev) fail(AKE_ERR_INVALID, "d_genre_out_dev is required with a genre head");
+    if (B <= 0) fail(AKE_ERR_INVALID, "B must be positive");
+    loss_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(key_out_dev, tonic_out_dev, genre_out_dev, key_labels_dev, tonic_idx_dev,
+                                                                 genre_idx_dev, B, key_weight, tonic_weight, genre_weight, loss_out_dev,
+                                                                 d_key_out_dev, d_tonic_out_dev, d_genre_out_dev);
+    AKE_LAUNCHED();
   });
 }
 

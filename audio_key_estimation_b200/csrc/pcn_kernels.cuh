@@ -43,6 +43,7 @@ struct ConvArgs {
   int n_row_tiles;
   int tgroups;  // time groups per block: block covers tgroups*RT output frames
   int xp;       // shared-memory row pitch (floats, multiple of 4, >= tgroups*RT + KW - 1)
+  int accum;    // add to the stored values instead of overwriting them (data gradients with several consumers)
 };
 
 constexpr int kConvCI = 8;  // input channels staged per shared-memory pass
@@ -177,7 +178,8 @@ __global__ void __launch_bounds__(256) conv_rows_kernel(const ConvArgs a) {
         const int t = t0 + tg * RT + j;
         if (t < a.T_out) {
           float v = fmaf(acc[c][j], s, h);
-          op[t] = a.act ? leaky(v) : v;
+          v = a.act ? leaky(v) : v;
+          op[t] = a.accum ? op[t] + v : v;
         }
       }
     } else {

@@ -1,0 +1,457 @@
+// pcn_train_kernels.cuh -- backward kernels of the PitchClassNet training step (BASELINE config 5; SURVEY.md section 8
+// a-15): gradients of models.py:352-399, 713-817 with train-mode BatchNorm, fp32 CUDA cores.
+//
+//   data gradient of a stride-1 row convolution  = the forward conv_rows_kernel run on dY with flipped, transposed weights
+//   weight gradient                               = conv_wgrad_kernel (below), fp32 atomics into the flat gradient buffer
+//   BatchNorm + LeakyReLU backward                = bn_bwd_reduce_kernel + bn_bwd_apply_kernel (two passes per site)
+//   pools / up-sampling / masked mean             = one small kernel each
+// The gradient buffer has the layout of the flat parameter buffer (ake_pcn_set_params_f32), so a data-parallel job
+// all-reduces it as ONE bucket.
+#pragma once
+#include "pcn_kernels.cuh"
+
+namespace ake {
+
+// a = leaky(z * scale[c] + shift[c]), out of place (z is kept for the backward pass).  z, a: (B, C, RT).
+__global__ void bn_act_out_kernel(const float* __restrict__ z, float* __restrict__ a, int B, int C, int RT,
+                                  const float* __restrict__ scale, const float* __restrict__ shift) {
+  const long long n = (long long)B * C * RT;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (i / RT) % C;
+    a[i] = leaky(fmaf(z[i], scale[c], shift[c]));
+  }
+}
+
+// Weights of the data-gradient convolution: dst[co][KH-1-dr][KW-1-dt][ci (padded)] = w[co][ci][dr][dt]
+// (the forward packing [Cin'][KH][KW][cout_pad'] with Cin' = Cout, Cout' = Cin, taps flipped).
+__global__ void pack_conv_dgrad_kernel(const float* __restrict__ w, int Cout, int Cin, int KH, int KW, int cin_pad,
+                                       float* __restrict__ dst) {
+  const int n = Cout * KH * KW * cin_pad;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int ci = i % cin_pad;
+    int q = i / cin_pad;
+    const int dt = q % KW;
+    q /= KW;
+    const int dr = q % KH, co = q / KH;
+    dst[i] = ci < Cin ? w[(((long long)co * Cin + ci) * KH + (KH - 1 - dr)) * KW + (KW - 1 - dt)] : 0.f;
+  }
+}
+
+// ---- weight gradient of a row convolution ---------------------------------------------------------------------------
+//   dW[co, ci, dr, dt] = sum_{b, r, t} dZ[b, co, r, t] * x[b, ci, rowmap(r*SR + off + dr), tmap(t - pad + dt)]
+// grid (row tiles, Cin, B); a block walks the frames of its (clip, input channel, row tile) in tiles of 16, keeps
+// KW accumulators per (co, dr) pair in registers and adds them to the gradient buffer once at the end.
+struct WgradArgs {
+  const float* in0;
+  const float* in1;
+  int c0, c1, rows0, rows1;
+  long long bs0, bs1;
+  int T_in, rows_v, row_circ, row_off, pad_t, time_circ;
+  int rows_out, T_out, Cin, Cout;
+  const float* dz;  // (B, Cout, rows_out, T_out)
+  float* dw;        // (Cout, Cin, KH, KW), accumulated
+};
+
+constexpr int kWgTB = 16;
+
+template <int KH, int KW, int SR, int RB>
+__global__ void __launch_bounds__(256) conv_wgrad_kernel(const WgradArgs a) {
+  constexpr int RIN = (RB - 1) * SR + KH;
+  constexpr int XW = kWgTB + KW - 1;
+  constexpr int XP = (XW + 3) / 4 * 4;
+  extern __shared__ float4 smem4[];
+  float* xs = reinterpret_cast<float*>(smem4);  // [RIN][XP]
+  float* gs = xs + RIN * XP;                    // [Cout][RB][kWgTB]
+  const int tid = threadIdx.x;
+  const int row_tile = blockIdx.x, ci = blockIdx.y, b = blockIdx.z;
+  const int out_row0 = row_tile * RB;
+  const int n_pairs = a.Cout * KH;
+  float acc[2][KW];
+#pragma unroll
+  for (int p = 0; p < 2; ++p)
+#pragma unroll
+    for (int d = 0; d < KW; ++d) acc[p][d] = 0.f;
+
+  for (int t0 = 0; t0 < a.T_out; t0 += kWgTB) {
+    __syncthreads();
+    for (int i = tid; i < RIN * XP; i += blockDim.x) {
+      const int row = i / XP, j = i - row * XP;
+      int v = out_row0 * SR + a.row_off + row;
+      if (a.row_circ) {
+        v %= a.rows_v;
+        if (v < 0) v += a.rows_v;
+      }
+      int t = t0 - a.pad_t + j;
+      if (a.time_circ) {
+        t %= a.T_in;
+        if (t < 0) t += a.T_in;
+      }
+      float val = 0.f;
+      if (j < XW && v >= 0 && v < a.rows_v && t >= 0 && t < a.T_in) {
+        const float* src = (ci < a.c0) ? a.in0 + b * a.bs0 + (long long)(ci * a.rows0 + v) * a.T_in
+                                       : a.in1 + b * a.bs1 + (long long)((ci - a.c0) * a.rows1 + v % a.rows1) * a.T_in;
+        val = __ldg(src + t);
+      }
+      xs[i] = val;
+    }
+    for (int i = tid; i < a.Cout * RB * kWgTB; i += blockDim.x) {
+      const int j = i % kWgTB, r = (i / kWgTB) % RB, co = i / (kWgTB * RB);
+      const int orow = out_row0 + r, t = t0 + j;
+      gs[i] = (orow < a.rows_out && t < a.T_out) ? __ldg(a.dz + (((long long)b * a.Cout + co) * a.rows_out + orow) * a.T_out + t) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int pp = 0; pp < 2; ++pp) {
+      const int p = tid + 256 * pp;
+      if (p < n_pairs) {
+        const int co = p / KH, dr = p - co * KH;
+#pragma unroll 1
+        for (int r = 0; r < RB; ++r) {
+          const float* xr = xs + (r * SR + dr) * XP;
+          const float* gr = gs + (co * RB + r) * kWgTB;
+          float x[XP], g[kWgTB];
+#pragma unroll
+          for (int q = 0; q < XP / 4; ++q) {
+            const float4 v4 = *reinterpret_cast<const float4*>(xr + 4 * q);
+            x[4 * q] = v4.x, x[4 * q + 1] = v4.y, x[4 * q + 2] = v4.z, x[4 * q + 3] = v4.w;
+          }
+#pragma unroll
+          for (int q = 0; q < kWgTB / 4; ++q) {
+            const float4 v4 = *reinterpret_cast<const float4*>(gr + 4 * q);
+            g[4 * q] = v4.x, g[4 * q + 1] = v4.y, g[4 * q + 2] = v4.z, g[4 * q + 3] = v4.w;
+          }
+#pragma unroll
+          for (int j = 0; j < kWgTB; ++j)
+#pragma unroll
+            for (int d = 0; d < KW; ++d) acc[pp][d] = fmaf(g[j], x[j + d], acc[pp][d]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int pp = 0; pp < 2; ++pp) {
+    const int p = tid + 256 * pp;
+    if (p < n_pairs) {
+      const int co = p / KH, dr = p - co * KH;
+      float* dst = a.dw + (((long long)co * a.Cin + ci) * KH + dr) * KW;
+#pragma unroll
+      for (int d = 0; d < KW; ++d) atomicAdd(dst + d, acc[pp][d]);
+    }
+  }
+}
+
+// out[c] += sum over (B, RT) of x[b, c, :]   (bias gradients).  grid (chunks, C)
+__global__ void channel_sum_kernel(const float* __restrict__ x, int B, int C, int RT, float* __restrict__ out) {
+  const int c = blockIdx.y;
+  const long long n = (long long)B * RT;
+  float s = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / RT, e = i - b * RT;
+    s += x[(b * C + c) * (long long)RT + e];
+  }
+  __shared__ float sh[32];
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    s = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.f;
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0) atomicAdd(out + c, s);
+  }
+}
+
+// ---- BatchNorm (batch statistics) + LeakyReLU backward ----------------------------------------------------------------
+//   y = z*scale + shift, xhat = (z - mean)*invstd, a = leaky(y);  dyh = da * (y > 0 ? 1 : slope)
+//   dbeta = sum dyh, dgamma = sum dyh*xhat, dz = scale * (dyh - dbeta/N - xhat*dgamma/N)
+// pass 1: sums[2c] += sum dyh, sums[2c+1] += sum dyh*xhat (double).  grid (chunks, C)
+__global__ void bn_bwd_reduce_kernel(const float* __restrict__ z, const float* __restrict__ da, int B, int C, int RT,
+                                     const float* __restrict__ scale, const float* __restrict__ shift,
+                                     const float* __restrict__ mean, const float* __restrict__ invstd,
+                                     double* __restrict__ sums) {
+  const int c = blockIdx.y;
+  const long long n = (long long)B * RT;
+  const float sc = scale[c], sh_ = shift[c], mu = mean[c], is = invstd[c];
+  double s1 = 0.0, s2 = 0.0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / RT, e = i - b * RT;
+    const long long idx = (b * C + c) * (long long)RT + e;
+    const float zz = z[idx];
+    const float y = fmaf(zz, sc, sh_);
+    const float g = da[idx] * (y > 0.f ? 1.f : kLeakySlope);
+    s1 += g, s2 += g * ((zz - mu) * is);
+  }
+  __shared__ double sh[2][32];
+  for (int o = 16; o; o >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  }
+  if ((threadIdx.x & 31) == 0) sh[0][threadIdx.x >> 5] = s1, sh[1][threadIdx.x >> 5] = s2;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int nw = blockDim.x >> 5;
+    s1 = threadIdx.x < nw ? sh[0][threadIdx.x] : 0.0;
+    s2 = threadIdx.x < nw ? sh[1][threadIdx.x] : 0.0;
+    for (int o = 16; o; o >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    if (threadIdx.x == 0) {
+      atomicAdd(sums + 2 * c, s1);
+      atomicAdd(sums + 2 * c + 1, s2);
+    }
+  }
+}
+
+// pass 2: dz; block 0 also writes dgamma / dbeta.
+__global__ void bn_bwd_apply_kernel(const float* __restrict__ z, const float* __restrict__ da, float* __restrict__ dz, int B,
+                                    int C, int RT, const float* __restrict__ scale, const float* __restrict__ shift,
+                                    const float* __restrict__ mean, const float* __restrict__ invstd,
+                                    const double* __restrict__ sums, double count, float* __restrict__ dgamma,
+                                    float* __restrict__ dbeta) {
+  if (blockIdx.x == 0 && threadIdx.x < C) {
+    dbeta[threadIdx.x] = (float)sums[2 * threadIdx.x];
+    dgamma[threadIdx.x] = (float)sums[2 * threadIdx.x + 1];
+  }
+  const long long n = (long long)B * C * RT;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (i / RT) % C;
+    const float sc = scale[c], mu = mean[c], is = invstd[c];
+    const float zz = z[i];
+    const float y = fmaf(zz, sc, shift[c]);
+    const float g = da[i] * (y > 0.f ? 1.f : kLeakySlope);
+    const float xh = (zz - mu) * is;
+    const float m1 = (float)(sums[2 * c] / count), m2 = (float)(sums[2 * c + 1] / count);
+    dz[i] = sc * (g - m1 - xh * m2);
+  }
+}
+
+// ---- pools ------------------------------------------------------------------------------------------------------------
+// Pitch2PitchClassPool backward (models.py:82-106): the gradient of pc[c] goes to the first maximal octave of
+// a = leaky(z*scale + shift) (recomputed).  z, da: (B, C, R, T); dcat: (B, C_total, 12, T) read at channel coff + c.
+__global__ void octmax_bwd_kernel(const float* __restrict__ z, int B, int C, int R, int T, const float* __restrict__ scale,
+                                  const float* __restrict__ shift, const float* __restrict__ dcat, int C_total, int coff,
+                                  float* __restrict__ da) {
+  const long long n = (long long)B * C * 12 * T;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int t = i % T;
+    long long q = i / T;
+    const int pc = q % 12;
+    q /= 12;
+    const int c = q % C;
+    const int b = q / C;
+    const long long base = (((long long)b * C + c) * R) * T + t;
+    const float s = scale[c], h = shift[c];
+    float m = -INFINITY;
+    int best = pc;
+    for (int row = pc; row < R; row += 12) {
+      const float v = leaky(fmaf(z[base + (long long)row * T], s, h));
+      if (v > m) m = v, best = row;
+    }
+    const float g = dcat[(((long long)b * C_total + coff + c) * 12 + pc) * T + t];
+    for (int row = pc; row < R; row += 12) da[base + (long long)row * T] = row == best ? g : 0.f;
+  }
+}
+
+// MaxPool2d((1,2)) backward with the affine + activation recomputed: z, da (B*C*R lines of T), dpooled lines of T/2.
+__global__ void timepool_bwd_kernel(const float* __restrict__ z, int B, int C, int R, int T, const float* __restrict__ scale,
+                                    const float* __restrict__ shift, const float* __restrict__ dpooled,
+                                    float* __restrict__ da) {
+  const int T2 = T / 2;
+  const long long n = (long long)B * C * R * T2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int u = i % T2;
+    const long long line = i / T2;
+    const int c = (line / R) % C;
+    const float v0 = leaky(fmaf(z[line * T + 2 * u], scale[c], shift[c]));
+    const float v1 = leaky(fmaf(z[line * T + 2 * u + 1], scale[c], shift[c]));
+    const float g = dpooled[i];
+    da[line * T + 2 * u] = v1 > v0 ? 0.f : g;
+    da[line * T + 2 * u + 1] = v1 > v0 ? g : 0.f;
+    if ((T & 1) && u == T2 - 1) da[line * T + T - 1] = 0.f;
+  }
+}
+
+// ---- ConvTranspose2d(C,C,(3,1),stride (3,1)) backward (models.py:325): out[co,3c+r] = b + sum_ci W[ci,co,r] pc[ci,c] ----
+//   dpc[b,ci,c,t] += sum_{co,r} W[ci,co,r] dz[b,co,3c+r,t];  dW[ci,co,r] += sum_{b,c,t} pc[b,ci,c,t] dz[b,co,3c+r,t]
+// One thread per (b, c, t); C <= 8.  The weight gradient is reduced over the warp before the atomics.
+__global__ void upsixth_bwd_kernel(const float* __restrict__ pc, const float* __restrict__ w, const float* __restrict__ dz,
+                                   int B, int C, int T, float* __restrict__ dpc, float* __restrict__ dw) {
+  const long long n = (long long)B * 12 * T;
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const bool ok = i < n;
+  const int t = ok ? (int)(i % T) : 0;
+  const int c = ok ? (int)((i / T) % 12) : 0;
+  const int b = ok ? (int)(i / ((long long)T * 12)) : 0;
+  float x[8], g[8][3];
+  for (int ci = 0; ci < C; ++ci) x[ci] = ok ? pc[(((long long)b * C + ci) * 12 + c) * T + t] : 0.f;
+  for (int co = 0; co < C; ++co)
+    for (int r = 0; r < 3; ++r) g[co][r] = ok ? dz[(((long long)b * C + co) * 36 + 3 * c + r) * T + t] : 0.f;
+  for (int ci = 0; ci < C; ++ci) {
+    float d = 0.f;
+    for (int co = 0; co < C; ++co)
+      for (int r = 0; r < 3; ++r) {
+        d = fmaf(__ldg(w + (ci * C + co) * 3 + r), g[co][r], d);
+        float p = x[ci] * g[co][r];
+        for (int o = 16; o; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+        if ((threadIdx.x & 31) == 0) atomicAdd(dw + (ci * C + co) * 3 + r, p);
+      }
+    if (ok) dpc[(((long long)b * C + ci) * 12 + c) * T + t] += d;
+  }
+}
+
+// ---- semitone conv (3x3, stride (3,1), time-circular) data gradient (models.py:337) ------------------------------------
+//   dx[b,ci,3s+dp,t] = sum_{co,dt} W[co,ci,dp,dt] dz[b,co,s,(t - dt + 1) mod T]
+__global__ void semitone_dgrad_kernel(const float* __restrict__ dz, const float* __restrict__ w, int B, int Cin, int Cout,
+                                      int P, int T, float* __restrict__ dx) {
+  const long long n = (long long)B * Cin * P * T;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int t = i % T;
+    long long q = i / T;
+    const int p = q % P;
+    q /= P;
+    const int ci = q % Cin;
+    const int b = q / Cin;
+    const int s = p / 3, dp = p - 3 * s, S = P / 3;
+    float acc = 0.f;
+    for (int co = 0; co < Cout; ++co) {
+      const float* g = dz + (((long long)b * Cout + co) * S + s) * T;
+      const float* wk = w + ((co * Cin + ci) * 3 + dp) * 3;
+#pragma unroll
+      for (int dt = 0; dt < 3; ++dt) {
+        int tt = t - dt + 1;
+        tt += tt < 0 ? T : 0, tt -= tt >= T ? T : 0;
+        acc = fmaf(__ldg(wk + dt), g[tt], acc);
+      }
+    }
+    dx[i] = acc;
+  }
+}
+
+// PitchClass2Pitch backward (models.py:135-143): du[b,c,r36,t] = sum_o dx[b, coff + c, r36 + 36 o, t]
+__global__ void tile_sum_kernel(const float* __restrict__ dx, int B, int C_total, int coff, int C, int P, int T,
+                                float* __restrict__ du) {
+  const long long n = (long long)B * C * 36 * T;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int t = i % T;
+    long long q = i / T;
+    const int r = q % 36;
+    q /= 36;
+    const int c = q % C;
+    const int b = q / C;
+    float s = 0.f;
+    for (int row = r; row < P; row += 36) s += dx[(((long long)b * C_total + coff + c) * P + row) * T + t];
+    du[i] = s;
+  }
+}
+
+// dst[b, c, :] (+)= src[b, soff + c, :]   for c < C
+__global__ void copy_channels_kernel(const float* __restrict__ src, int Cs, int soff, float* __restrict__ dst, int Cd, int doff,
+                                     int B, int C, int RT, int accumulate) {
+  const long long n = (long long)B * C * RT;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long e = i % RT;
+    long long q = i / RT;
+    const int c = q % C;
+    const long long b = q / C;
+    const float v = src[(b * Cs + soff + c) * RT + e];
+    float* d = dst + (b * Cd + doff + c) * RT + e;
+    *d = accumulate ? *d + v : v;
+  }
+}
+
+// ---- masked temporal mean (+ sigmoid) backward (models.py:754-804) ------------------------------------------------------
+// d_frames[b, row, t] = d_out[b, row] * (sigmoid' for the key head) / n_b for t < n_b, else 0.
+__global__ void head_reduce_bwd_kernel(const float* __restrict__ d_key_out, const float* __restrict__ d_tonic_out,
+                                       const float* __restrict__ d_genre_out, const float* __restrict__ key_out, int B, int Th,
+                                       const int* __restrict__ seq_len, int pool_div, int head_shrink, float* __restrict__ d_key_f,
+                                       float* __restrict__ d_tonic_f, float* __restrict__ d_genre_f) {
+  const int rows_per_clip = d_genre_f ? 35 : 24;
+  const long long n = (long long)B * rows_per_clip * Th;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int t = i % Th;
+    const int rr = (i / Th) % rows_per_clip, b = i / ((long long)Th * rows_per_clip);
+    int len = Th;
+    if (seq_len) len = min(Th, seq_len[b] / pool_div - head_shrink);
+    float g;
+    float* dst;
+    if (rr < 12) {
+      const float p = key_out[b * 12 + rr];
+      g = (d_key_out ? d_key_out[b * 12 + rr] : 0.f) * p * (1.f - p);
+      dst = d_key_f + ((long long)b * 12 + rr) * Th + t;
+    } else if (rr < 24) {
+      g = d_tonic_out ? d_tonic_out[b * 12 + rr - 12] : 0.f;
+      dst = d_tonic_f + ((long long)b * 12 + rr - 12) * Th + t;
+    } else {
+      g = d_genre_out ? d_genre_out[b * 11 + rr - 24] : 0.f;
+      dst = d_genre_f + ((long long)b * 11 + rr - 24) * Th + t;
+    }
+    *dst = (len > 0 && t < len) ? g / (float)len : 0.f;
+  }
+}
+
+// ---- training objective (models.py:855-896, global key estimation) -----------------------------------------------------
+//   loss = key_weight * BCELoss(key_out, key_labels) + tonic_weight * CE(tonic_out, tonic_idx)
+//        + genre_weight * CE(genre_out[mask], genre_idx[mask])          (mask: genre_idx >= 0; skipped when empty)
+// One block.  loss_out[4] = {total, bce, tonic, genre}; the gradients w.r.t. the three outputs are written too.
+__global__ void loss_kernel(const float* __restrict__ key_out, const float* __restrict__ tonic_out, const float* __restrict__ genre_out,
+                            const float* __restrict__ key_labels, const int* __restrict__ tonic_idx, const int* __restrict__ genre_idx,
+                            int B, float key_weight, float tonic_weight, float genre_weight, float* __restrict__ loss_out,
+                            float* __restrict__ d_key, float* __restrict__ d_tonic, float* __restrict__ d_genre) {
+  __shared__ float red[3][32];
+  __shared__ int s_nm;
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    int nm = 0;
+    if (genre_out && genre_idx)
+      for (int b = 0; b < B; ++b) nm += genre_idx[b] >= 0;
+    s_nm = nm;
+  }
+  __syncthreads();
+  const int nm = s_nm;
+  float bce = 0.f, ce_t = 0.f, ce_g = 0.f;
+  for (int i = tid; i < B * 12; i += blockDim.x) {
+    const float p = key_out[i], y = key_labels[i];
+    bce -= y * fmaxf(logf(p), -100.f) + (1.f - y) * fmaxf(log1pf(-p), -100.f);  // nn.BCELoss clamps the logs at -100
+    d_key[i] = key_weight * (p - y) / fmaxf((1.f - p) * p, 1e-12f) / (float)(B * 12);
+  }
+  for (int b = tid; b < B; b += blockDim.x) {
+    {
+      const float* x = tonic_out + b * 12;
+      float m = x[0];
+      for (int i = 1; i < 12; ++i) m = fmaxf(m, x[i]);
+      float s = 0.f;
+      for (int i = 0; i < 12; ++i) s += expf(x[i] - m);
+      const float lse = m + logf(s);
+      ce_t += lse - x[tonic_idx[b]];
+      for (int i = 0; i < 12; ++i) d_tonic[b * 12 + i] = tonic_weight * (expf(x[i] - lse) - (i == tonic_idx[b] ? 1.f : 0.f)) / (float)B;
+    }
+    if (genre_out) {
+      const float* x = genre_out + b * 11;
+      const bool on = genre_idx && genre_idx[b] >= 0 && nm > 0;
+      float m = x[0];
+      for (int i = 1; i < 11; ++i) m = fmaxf(m, x[i]);
+      float s = 0.f;
+      for (int i = 0; i < 11; ++i) s += expf(x[i] - m);
+      const float lse = m + logf(s);
+      if (on) ce_g += lse - x[genre_idx[b]];
+      for (int i = 0; i < 11; ++i)
+        d_genre[b * 11 + i] = on ? genre_weight * (expf(x[i] - lse) - (i == genre_idx[b] ? 1.f : 0.f)) / (float)nm : 0.f;
+    }
+  }
+  for (int o = 16; o; o >>= 1) {
+    bce += __shfl_xor_sync(0xffffffffu, bce, o);
+    ce_t += __shfl_xor_sync(0xffffffffu, ce_t, o);
+    ce_g += __shfl_xor_sync(0xffffffffu, ce_g, o);
+  }
+  if ((tid & 31) == 0) red[0][tid >> 5] = bce, red[1][tid >> 5] = ce_t, red[2][tid >> 5] = ce_g;
+  __syncthreads();
+  if (tid == 0) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) a0 += red[0][w], a1 += red[1][w], a2 += red[2][w];
+    a0 /= (float)(B * 12), a1 /= (float)B, a2 = nm > 0 ? a2 / (float)nm : 0.f;
+    loss_out[1] = a0, loss_out[2] = a1, loss_out[3] = a2;
+    loss_out[0] = key_weight * a0 + tonic_weight * a1 + (nm > 0 ? genre_weight * a2 : 0.f);
+  }
+}
+
+}  // namespace ake

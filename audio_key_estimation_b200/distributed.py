@@ -96,3 +96,13 @@ def reduce_counters(counters: torch.Tensor, group=None) -> torch.Tensor:
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(counters, op=dist.ReduceOp.SUM, group=group)
     return counters
+
+
+def allreduce_gradients(flat_grads: torch.Tensor, group=None) -> torch.Tensor:
+    """Average the flat gradient buffer of training.TrainStep over the ranks, in place: ONE all-reduce of
+    162,902 (167,031 with the genre head) fp32 values per step -- latency-bound on NVLink/NVSwitch, so a single
+    bucket (no per-tensor launches).  BatchNorm statistics stay per rank (plain DDP semantics)."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(flat_grads, op=dist.ReduceOp.SUM, group=group)
+        flat_grads.div_(dist.get_world_size(group))
+    return flat_grads

@@ -11,9 +11,11 @@ Differences a maintainer should know (also in INTEGRATION.md):
 * arithmetic is fp32 on the device (the reference runs cuDNN float64); inputs of any float dtype
   are accepted and the outputs are returned in the input's dtype (``general_step`` feeds
   ``key_out`` to ``BCELoss`` against ``.double()`` labels, models.py:823, 878);
-* forward only: outputs carry no autograd graph (the training step is SURVEY.md section 8 a-15,
-  "config 5", not built yet) -- calling it under ``torch.enable_grad()`` with parameters that
-  require grad works but returns detached tensors;
+* training (train_model.py:122, models.py:952-961): in ``.train()`` mode with grad enabled the forward
+  runs through ``ake_pcn_forward_f32(bn_mode=2)`` and ``loss.backward()`` through
+  ``ake_pcn_backward_f32`` (a ``torch.autograd.Function``), for the train_model.py default
+  architecture (num_layers 2, head_layers 2, ``max_pool`` off); ``training.TrainStep`` is the fused
+  forward + loss + backward call;
 * ``net.modules()`` works (the reference shadows it with a list, models.py:673).
 """
 from __future__ import annotations
@@ -54,6 +56,49 @@ def _opt_get(opt, name, default):
 
 class _Node(nn.Module):
     """Name-only container so parameters appear under the reference's dotted state_dict keys."""
+
+
+class _KeptForward(torch.autograd.Function):
+    """Train-mode forward that keeps its activations (bn_mode 2) + backward through ake_pcn_backward_f32."""
+
+    @staticmethod
+    def forward(ctx, net, x, seq, *params):
+        lib = _lib.lib()
+        device = x.device
+        B, T = int(x.shape[0]), int(x.shape[3])
+        with torch.cuda.device(device):
+            stream = torch.cuda.current_stream(device).cuda_stream
+            ws_bytes = lib.ake_pcn_workspace_bytes(net._plan, B, T, 2)
+            if ws_bytes == 0:
+                check(_lib.AKE_ERR_UNSUPPORTED if b"built for" in (lib.ake_last_error() or b"") else _lib.AKE_ERR_INVALID)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)  # private: it must survive until backward
+            key = torch.empty((B, 12), dtype=torch.float32, device=device)
+            tonic = torch.empty((B, 12), dtype=torch.float32, device=device)
+            genre = torch.empty((B, 11), dtype=torch.float32, device=device) if net._genre else None
+            stats = torch.empty(2 * sum(net._bn_channels), dtype=torch.float32, device=device)
+            check(lib.ake_pcn_forward_f32(
+                net._plan, x.data_ptr(), B, T, seq.data_ptr() if seq is not None else None, 2, key.data_ptr(),
+                tonic.data_ptr(), genre.data_ptr() if genre is not None else None, stats.data_ptr(), ws.data_ptr(),
+                ws.numel(), stream))
+        net._update_running_stats(stats, B, T)
+        ctx.net, ctx.ws, ctx.keep = net, ws, (x, seq, key)
+        ctx.n_params = len(params)
+        return (key, tonic, genre) if genre is not None else (key, tonic)
+
+    @staticmethod
+    def backward(ctx, *douts):
+        net, ws = ctx.net, ctx.ws
+        lib = _lib.lib()
+        device = ws.device
+        d = [g.contiguous().to(torch.float32) if g is not None else None for g in douts]
+        while len(d) < 3:
+            d.append(None)
+        with torch.cuda.device(device):
+            stream = torch.cuda.current_stream(device).cuda_stream
+            flat = torch.empty(lib.ake_pcn_param_floats(net._plan), dtype=torch.float32, device=device)
+            check(lib.ake_pcn_backward_f32(net._plan, *(g.data_ptr() if g is not None else None for g in d), flat.data_ptr(),
+                                           flat.numel(), ws.data_ptr(), ws.numel(), stream))
+        return (None, None, None) + tuple(net._split_flat_grads(flat))
 
 
 class PitchClassNet(nn.Module):
@@ -191,6 +236,9 @@ class PitchClassNet(nn.Module):
                     raise ValueError(f"seq_length has {seq.numel()} entries for a batch of {B}")
                 seq = seq.to(device=device, dtype=torch.int32).contiguous()
             train = bool(self.training)
+            if train and torch.is_grad_enabled() and any(p.requires_grad for p in self._grad_params()):
+                outs = _KeptForward.apply(self, x, seq, *self._grad_params())
+                return tuple(o.to(out_dtype) for o in outs)
             ws_bytes = lib.ake_pcn_workspace_bytes(self._plan, B, T, int(train))
             if ws_bytes == 0:
                 check(_lib.AKE_ERR_INVALID)
@@ -209,6 +257,21 @@ class PitchClassNet(nn.Module):
                 self._update_running_stats(stats, B, T)
         outs = (key, tonic) + ((genre,) if self._genre else ())
         return tuple(o.to(out_dtype) for o in outs)
+
+    # ------------------------------------------------------------------------------- gradients
+    def _grad_params(self):
+        """The nn.Parameters in flat-buffer order (running statistics are buffers and carry no gradient)."""
+        return [t for t in (self._lookup(n) for n in self._tensor_names) if isinstance(t, nn.Parameter)]
+
+    def _split_flat_grads(self, flat: torch.Tensor):
+        """Views of the flat gradient buffer (layout of ake_pcn_set_params_f32), one per nn.Parameter."""
+        out, off = [], 0
+        for n in self._tensor_names:
+            t = self._lookup(n)
+            if isinstance(t, nn.Parameter):
+                out.append(flat[off: off + t.numel()].view(t.shape).to(t.dtype))
+            off += t.numel()
+        return out
 
     def _bn_counts(self, B: int, T: int):
         """Elements per channel each BN site normalises over (B * rows * frames), in site order."""

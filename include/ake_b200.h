@@ -87,7 +87,9 @@ int64_t ake_pcn_param_floats(const ake_pcn* plan);
 int ake_pcn_set_params_f32(ake_pcn* plan, const float* flat_dev, int64_t n_floats, void* stream);
 
 /* bn_mode: 0 = eval (running statistics, eval.py:116); 1 = train (batch statistics,
- * equivariance_test.py:178 leaves the model in train mode). */
+ * equivariance_test.py:178 leaves the model in train mode); 2 = train, and keep every activation in the
+ * workspace for ake_pcn_backward_f32 (the training step of train_model.py:122 / models.py:952-961; built for
+ * num_layers = 2, head_layers = 2, max_pool off -- AKE_ERR_UNSUPPORTED otherwise). */
 size_t ake_pcn_workspace_bytes(const ake_pcn* plan, int B, int T, int bn_mode);
 
 /* forward(mel, seq_length) of models.py:747-817.
@@ -101,6 +103,25 @@ int ake_pcn_forward_f32(ake_pcn* plan, const float* mel_dev, int B, int T, const
                         int bn_mode, float* key_out_dev, float* tonic_out_dev, float* genre_out_dev,
                         float* bn_stats_out_dev, void* ws_dev, size_t ws_bytes, void* stream);
 int ake_pcn_bn_channels(const ake_pcn* plan); /* total channels over all BN sites */
+
+/* Backward pass of the last bn_mode = 2 forward (what loss.backward() runs through models.py:747-817 in the
+ * reference).  d_*_out_dev: gradients of the loss w.r.t. key_out (B,12, AFTER the sigmoid), tonic_out (B,12) and
+ * genre_out (B,11); NULL = zero.  grads_out_dev receives ake_pcn_param_floats() floats in the layout of
+ * ake_pcn_set_params_f32 (entries of the running-statistics buffers are zero), so a data-parallel job all-reduces it
+ * as one bucket.  ws_dev must be the workspace that forward used, untouched since (size: ake_pcn_workspace_bytes with
+ * bn_mode 2).  One backward per kept forward. */
+int ake_pcn_backward_f32(ake_pcn* plan, const float* d_key_out_dev, const float* d_tonic_out_dev,
+                         const float* d_genre_out_dev, float* grads_out_dev, int64_t n_floats, void* ws_dev,
+                         size_t ws_bytes, void* stream);
+
+/* The training objective of models.py:855-896 (global key estimation) and its gradient w.r.t. the network outputs:
+ *   loss = key_weight * BCELoss(key_out, key_labels) + tonic_weight * CrossEntropy(tonic_out, tonic_idx)
+ *        + genre_weight * CrossEntropy(genre_out[mask], genre_idx[mask]),  mask = genre_idx >= 0 (models.py:836-840).
+ * loss_out_dev[4] = {total, bce, tonic, genre}.  genre_out_dev / genre_idx_dev / d_genre_out_dev may be NULL. */
+int ake_loss_f32(const float* key_out_dev, const float* tonic_out_dev, const float* genre_out_dev,
+                 const float* key_labels_dev, const int32_t* tonic_idx_dev, const int32_t* genre_idx_dev, int B,
+                 float key_weight, float tonic_weight, float genre_weight, float* loss_out_dev, float* d_key_out_dev,
+                 float* d_tonic_out_dev, float* d_genre_out_dev, void* stream);
 int ake_pcn_get_config(const ake_pcn* plan, ake_pcn_config* out);
 
 /* Debug/parity taps: copy a named intermediate of the LAST forward out of the workspace.

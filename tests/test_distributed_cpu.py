@@ -59,3 +59,33 @@ def test_shard_gather_world2(n_clips, genre):
         assert torch.allclose(table[:, 24], ids * 2 if genre else torch.zeros(n_clips))
         assert counters.tolist() == [n_clips, 2]
         assert n_out == (3 if genre else 2)
+
+
+def _grad_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    from audio_key_estimation_b200 import distributed as akd
+    akd.init_from_env("gloo")
+    flat = torch.full((167031,), float(rank + 1))  # the flat gradient bucket of the genre architecture
+    flat[rank] = 10.0
+    akd.allreduce_gradients(flat)
+    q.put((rank, flat[:3].clone(), float(flat[100])))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gradient_bucket_allreduce_world2():
+    """Config 5's only collective: ONE averaged all-reduce of the flat gradient buffer."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_grad_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, head, mid in results:
+        assert head.tolist() == [6.0, 5.5, 1.5] and mid == 1.5

@@ -1,0 +1,90 @@
+"""GPU parity of the training step (BASELINE config 5) against the reference's own
+general_step + loss.backward() frozen in tests/golden/train_step.npz.
+Tolerance: loss 1e-5 relative; every parameter gradient max-abs <= 2e-3 of that tensor's max |grad| (+1e-6):
+fp32 arithmetic with atomically accumulated weight gradients against a float64 reference."""
+import numpy as np
+import pytest
+import torch
+
+import audio_key_estimation_b200 as ake
+from audio_key_estimation_b200 import distributed as akd
+from conftest import golden_state_dict, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(genre, fwd_golden):
+    g = load_golden("train_step.npz")
+    net = ake.PitchClassNet(288, 12, 2, 7, opt=ake.default_opt(genre=genre))
+    net.load_state_dict(golden_state_dict(genre), strict=True)
+    net = net.cuda().train()
+    mel = torch.from_numpy(fwd_golden["mel"])[:, None].cuda()
+    seq = torch.from_numpy(fwd_golden["seq_length"]).cuda()
+    B = mel.shape[0]
+    key_labels = torch.from_numpy(g["key_labels"]).cuda()
+    tonic_1h = torch.nn.functional.one_hot(torch.from_numpy(g["tonic_idx"]), 12).cuda()
+    gi = torch.from_numpy(g["genre_idx"])
+    genre_1h = torch.zeros(B, 11, dtype=torch.long)
+    genre_1h[gi >= 0, gi[gi >= 0]] = 1
+    return g, net, mel, seq, key_labels, tonic_1h, genre_1h.cuda()
+
+
+def _check_grads(net, g, tag, tol=2e-3):
+    worst = 0.0
+    n = 0
+    # conv biases in front of a train-mode BatchNorm have an exactly-zero gradient (reference: ~1e-15): the floor is set by
+    # fp32 cancellation relative to the largest gradient of the network
+    floor = 1e-5 * max(np.abs(g[k]).max() for k in g.files if k.startswith(f"{tag}.grad."))
+    for name, prm in net.named_parameters():
+        ref = g[f"{tag}.grad.{name}"]
+        got = prm.grad.detach().cpu().numpy()
+        assert got.shape == ref.shape, name
+        err = np.abs(got - ref).max()
+        scale = np.abs(ref).max()
+        assert err <= tol * scale + floor, f"{name}: max-abs error {err:.3e} vs max |grad| {scale:.3e}"
+        worst = max(worst, err / (scale + 1e-12))
+        n += 1
+    return n, worst
+
+
+@pytest.mark.parametrize("tag", ["default", "genre"])
+def test_fused_train_step_matches_reference(tag, fwd_golden):
+    genre = tag == "genre"
+    g, net, mel, seq, key_labels, tonic_1h, genre_1h = _setup(genre, fwd_golden)
+    step = ake.TrainStep(net)
+    res = step.step(mel, seq, key_labels, tonic_1h, genre_1h if genre else None)
+    want = float(g[f"{tag}.loss"])
+    assert abs(res["loss"].item() - want) <= 1e-5 * abs(want)
+    n, worst = _check_grads(net, g, tag)
+    assert n == (66 if genre else 60)
+    # the flat buffer is what a data-parallel job all-reduces; world size 1 leaves it untouched
+    before = step.flat_grads.clone()
+    akd.allreduce_gradients(step.flat_grads)
+    assert torch.equal(before, step.flat_grads)
+    # running statistics were updated like nn.BatchNorm2d does in train mode
+    assert int(net.model._modules["0"].pool_semi_b.num_batches_tracked) == 1
+
+
+def test_autograd_path_matches_reference(fwd_golden):
+    """forward() in train mode + torch loss + loss.backward(): the route the reference's Lightning loop takes."""
+    g, net, mel, seq, key_labels, tonic_1h, genre_1h = _setup(True, fwd_golden)
+    out = net(mel.double(), seq)
+    assert out[0].dtype == torch.float64 and out[0].requires_grad
+    loss = ake.criterion(out, key_labels.double(), tonic_1h, genre_1h, net.opt)
+    assert abs(loss.item() - float(g["genre.loss"])) <= 1e-5 * abs(float(g["genre.loss"]))
+    loss.backward()
+    _check_grads(net, g, "genre")
+    # an optimizer step with the reference's settings (models.py:1017-1027) runs on those gradients
+    opt = torch.optim.Adam(net.parameters(), lr=3e-4, betas=(0.9, 0.999))
+    w0 = net.model._modules["1"].p2p.layer._modules["0"].weight.detach().clone()
+    opt.step()
+    assert not torch.equal(w0, net.model._modules["1"].p2p.layer._modules["0"].weight)
+    out2 = net(mel, seq)  # the changed parameters are re-uploaded
+    assert torch.isfinite(out2[0]).all()
+
+
+def test_unsupported_training_configs_fail_loudly(fwd_golden):
+    net = ake.PitchClassNet(288, 12, 2, 7, opt=ake.default_opt(max_pool=True)).cuda().train()
+    mel = torch.from_numpy(fwd_golden["mel"])[:, None].cuda()
+    with pytest.raises((NotImplementedError, ValueError)):
+        net(mel, None)
