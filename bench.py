@@ -41,6 +41,9 @@ def parse_args():
     ap.add_argument("--no-genre", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--train", action="store_true",
+                    help="BASELINE configs[4] instead of the headline metric: training step (fwd + loss + bwd, batch 8 per GPU, "
+                         "train-mode BN) with ONE flat gradient all-reduce over NCCL; prints its own JSON line")
     return ap.parse_args()
 
 
@@ -343,9 +346,96 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def run_train(args):
+    """configs[4]: PitchClassNet training step (train_model.py defaults + genre head, batch 8 clips of 151 frames per GPU):
+    kept-activation forward + loss + CUDA backward, then one all-reduce of the flat gradient bucket.  With
+    --impl reference: the oracle port (float64 torch-CPU autograd, the reference's dtype) on the host cores."""
+    import numpy as np
+    import torch
+    B, T = 8, 1 + SECONDS_STD * SR // (SR // FRAMES)
+    rng = np.random.default_rng(0)
+    mel = torch.from_numpy(np.log1p(rng.gamma(1.0, 1.0, (B, 1, 36 * OCTAVES, T))).astype(np.float32))
+    key_labels = torch.from_numpy((rng.random((B, 12)) < 0.6).astype(np.float32))
+    tonic_1h = torch.nn.functional.one_hot(torch.from_numpy(rng.integers(0, 12, B)), 12)
+    genre_1h = torch.nn.functional.one_hot(torch.from_numpy(rng.integers(0, 11, B)), 11)
+    seq = torch.full((B,), T, dtype=torch.int64)
+    sd = golden_weights(True)
+    if args.impl == "reference":
+        if int(os.environ.get("RANK", "0")) != 0:
+            return
+        from audio_key_estimation_b200 import training
+        from oracle import pcn_port
+        torch.set_num_threads(os.cpu_count() or 1)
+        sd64 = {k: v.double().requires_grad_("running_" not in k) for k, v in sd.items() if v.is_floating_point()}
+        def step():
+            for v in sd64.values():
+                v.grad = None
+            out = pcn_port.pcn_forward(sd64, mel.double(), seq, train=True)
+            training.criterion(out, key_labels.double(), tonic_1h, genre_1h).backward()
+        for _ in range(args.warmup):
+            step()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step()
+        dt = (time.perf_counter() - t0) / args.steps
+        print(json.dumps({"impl": "reference", "metric": "clips/s PitchClassNet training step (fwd+loss+bwd)", "value": B / dt, "unit": "clips/s",
+                          "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+                          "dtype": "f64", "data": "synthetic", "config": {"workload": f"configs[4]: batch {B} x {T} frames, oracle port autograd, {os.cpu_count()} host threads"},
+                          "cpu_baseline": {"value": B / dt, "unit": "clips/s", "cores": os.cpu_count(), "kind": "port", "sample": "whole step"}}), flush=True)
+        return
+    import torch.distributed as dist
+    import audio_key_estimation_b200 as ake
+    from audio_key_estimation_b200 import _lib, distributed as akd
+    rank, local, world = akd.init_from_env("nccl")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    net = ake.PitchClassNet(36 * OCTAVES, 12, 2, 7, opt=ake.default_opt(genre=True))
+    net.load_state_dict(sd, strict=True)
+    net = net.to(dev).train()
+    ts = ake.TrainStep(net)
+    mel, seq, key_labels, tonic_1h, genre_1h = (t.to(dev) for t in (mel, seq, key_labels, tonic_1h, genre_1h))
+
+    def step():
+        res = ts.step(mel, seq, key_labels, tonic_1h, genre_1h, assign_grads=False)
+        akd.allreduce_gradients(ts.flat_grads)
+        return res
+    for _ in range(max(args.warmup, 3)):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    _lib.lib().ake_launch_count(1)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        res = step()
+    ev1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    launches = int(_lib.lib().ake_launch_count(1))
+    if rank == 0:
+        print(json.dumps({"metric": "clips/s PitchClassNet training step (fwd+loss+bwd+grad all-reduce)", "value": B * world * args.steps / (ms * 1e-3),
+                          "unit": "clips/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+                          "higher_is_better": True, "scaling": "weak", "dtype": "f32", "data": "synthetic", "gpu_launches": launches,
+                          "loss": float(res["loss"]),
+                          "config": {"workload": f"configs[4]: batch {B} clips x {T} frames per GPU, train-mode BN, defaults + genre head, "
+                                                 f"{ts.flat_grads.numel()} fp32 gradients all-reduced as one bucket", "parallelism": f"ddp{world}"}}), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     args = parse_args()
-    if args.impl == "reference":
+    if args.train:
+        run_train(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_b200(args)
