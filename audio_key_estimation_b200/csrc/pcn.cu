@@ -129,6 +129,8 @@ struct ake_pcn {
   __half* d_wimg_pc = nullptr;      // equivariant convs of the layer-1 PitchClass2PitchClass stack (98,304 B each)
   __half* d_wimg_heads = nullptr;   // first conv of the tonic and key heads, fused along N (344,064 B)
   float* d_ss_heads = nullptr;      // [scale 64 | shift 64] of that fused conv (tonic channels first)
+  __half* d_wimg_genre = nullptr;   // first conv of the genre head (1 x 7, 16 -> 32): one 16 KB stage
+  __half* d_wimg_tail = nullptr;    // last conv of the tonic / key / genre heads (head_tail_umma_kernel), 12 KB each
   bool umma_heads = false;
   std::map<std::string, std::pair<const float*, int64_t>> taps;
   struct ake::TrainTape* tape = nullptr;  // activations kept by the last bn_mode = 2 forward (pcn_train.cuh)
@@ -693,52 +695,65 @@ void Fwd::run(const float* mel, float* key_out, float* tonic_out, float* genre_o
   bool heads_done = false;
   if (umma_pc_ready && p->umma_heads && Tn >= 13) {
     // first conv of both heads in one tensor-core pass (16 -> 32 | 32, valid in time), then the 32 -> 1 convs
-    const int T1 = Tn - (k - 1);
-    View th = alloc(32, 12, T1), kh = alloc(32, 12, T1);
+    const int T1 = Tn - (k - 1), Tf = T1 - (k - 1);
+    // first conv of the tonic / key heads (N = 64 channels) and of the genre head (1 x 7) -> fp16 chunk planes
+    const size_t hk_halves = (size_t)B * 8 * 23 * T1 * 8, g_halves = (size_t)B * 4 * 12 * T1 * 8;
+    __half* hk_hi = arena.take<__half>(hk_halves);
+    __half* hk_lo = arena.take<__half>(hk_halves);
+    __half* g_hi = cfg.genre ? arena.take<__half>(g_halves) : nullptr;
+    __half* g_lo = cfg.genre ? arena.take<__half>(g_halves) : nullptr;
     if (!dry) {
       ProfScope prof("pcn.equiv", st);
       const int n_tt = cdiv(T1, 32), TBe = (cdiv(T1, n_tt) + 1) / 2 * 2;
       const size_t smem_e = equiv_smem_bytes(TBe + 6);
-      static size_t conf = 0;
+      static size_t conf = 0, confg = 0;
       if (smem_e > conf) {
-        AKE_CUDA(cudaFuncSetAttribute(equiv_umma_kernel<64, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e));
+        AKE_CUDA(cudaFuncSetAttribute(equiv_umma_kernel<64, 1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e));
         conf = smem_e;
       }
       EquivArgs ea{};
       ea.in_hi = umma_pc_hi, ea.in_lo = umma_pc_lo, ea.Wd_in = Tn, ea.T_out = T1, ea.TB = TBe, ea.n_ttiles = cdiv(T1, TBe);
       ea.wimg = p->d_wimg_heads, ea.scale = p->d_ss_heads, ea.shift = p->d_ss_heads + 64;
-      ea.out_f32 = th.p, ea.out_f32_b = kh.p;
-      equiv_umma_kernel<64, 1, 2><<<dim3(ea.n_ttiles, B), 192, smem_e, st>>>(ea);
+      ea.out_hi = hk_hi, ea.out_lo = hk_lo, ea.out_rows = 23;
+      equiv_umma_kernel<64, 1, 3><<<dim3(ea.n_ttiles, B), 192, smem_e, st>>>(ea);
       AKE_LAUNCHED();
+      if (cfg.genre) {
+        if (smem_e > confg) {
+          AKE_CUDA(cudaFuncSetAttribute(equiv_umma_kernel<32, 1, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e));
+          confg = smem_e;
+        }
+        const Conv& cg = p->convs[p->genre_head[0]];
+        ea.wimg = p->d_wimg_genre, ea.scale = scale_of(cg, false), ea.shift = shift_of(cg, false);
+        ea.out_hi = g_hi, ea.out_lo = g_lo, ea.out_rows = 12;
+        equiv_umma_kernel<32, 1, 3, 1><<<dim3(ea.n_ttiles, B), 192, smem_e, st>>>(ea);
+        AKE_LAUNCHED();
+      }
     }
-    // last conv of every head (32 -> 1) in one launch; the genre head's first conv (1 x 7, not equivariant) stays generic
-    View gh;
-    if (cfg.genre) {
-      const Conv& cg = p->convs[p->genre_head[0]];
-      ConvGeom gg{cg.KH, k, 1, 12, 0, 0, 0, 0, 12 - cg.KH + 1, T1};
-      gh = alloc(cg.Cout, gg.rows_out, T1);
-      conv_bn_act(p->genre_head[0], pc, nullptr, gg, gh, 0);
-    }
-    const int Tf = T1 - (k - 1);
+    // last conv of every head (32 -> 1) in one tensor-core launch
     tonic_f = alloc(1, 12, Tf), key_f = alloc(1, 12, Tf);
     if (cfg.genre) genre_f = alloc(1, 11, Tf);
     if (!dry && Tf > 0) {
       ProfScope prof("pcn.heads", st);
-      HeadTailArgs ha{};
-      const Conv* hc[3] = {&p->convs[p->tonic_head[1]], &p->convs[p->key_head[1]], cfg.genre ? &p->convs[p->genre_head[1]] : nullptr};
-      const float* hx[3] = {th.p, kh.p, gh.p};
-      float* ho[3] = {tonic_f.p, key_f.p, genre_f.p};
+      HeadUmmaArgs ha{};
       const int nh = cfg.genre ? 3 : 2;
-      for (int h = 0; h < nh; ++h)
-        ha.x[h] = hx[h], ha.w[h] = p->d_params + hc[h]->w_off, ha.bias[h] = p->d_params + hc[h]->b_off, ha.out[h] = ho[h], ha.KH[h] = hc[h]->KH;
-      ha.T1 = T1, ha.Cin = 32;
-      const size_t smem_h = sizeof(float) * ((size_t)32 * 12 * 8 + (size_t)kHeadCi * 23 * kHeadTP);
+      const Conv* hc[3] = {&p->convs[p->tonic_head[1]], &p->convs[p->key_head[1]], cfg.genre ? &p->convs[p->genre_head[1]] : nullptr};
+      float* ho[3] = {tonic_f.p, key_f.p, genre_f.p};
+      for (int h = 0; h < nh; ++h) {
+        const bool eq = h < 2;
+        ha.in_hi[h] = eq ? hk_hi : g_hi, ha.in_lo[h] = eq ? hk_lo : g_lo;
+        ha.G_total[h] = eq ? 8 : 4, ha.g0[h] = h == 1 ? 4 : 0, ha.R[h] = eq ? 23 : 12, ha.KH[h] = hc[h]->KH, ha.rows_out[h] = eq ? 12 : 11;
+        ha.wimg[h] = reinterpret_cast<const __half*>(reinterpret_cast<const uint8_t*>(p->d_wimg_tail) + (size_t)h * 24 * 512);
+        ha.bias[h] = p->d_params + hc[h]->b_off, ha.out[h] = ho[h];
+      }
+      const int n_tt = cdiv(Tf, 20);
+      ha.T1 = T1, ha.Tf = Tf, ha.TB = cdiv(Tf, n_tt), ha.n_ttiles = cdiv(Tf, ha.TB);
+      const size_t smem_h = head_tail_smem_bytes(ha.TB + 6);
       static size_t conf_h = 0;
       if (smem_h > conf_h) {
-        AKE_CUDA(cudaFuncSetAttribute(head_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_h));
+        AKE_CUDA(cudaFuncSetAttribute(head_tail_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_h));
         conf_h = smem_h;
       }
-      head_tail_kernel<<<dim3(B, nh, cdiv(Tf, kHeadTile)), 128, smem_h, st>>>(ha);
+      head_tail_umma_kernel<<<dim3(ha.n_ttiles, nh, B), 160, smem_h, st>>>(ha);
       AKE_LAUNCHED();
     }
     tap("tonic_frames", tonic_f), tap("key_frames", key_f);
@@ -814,6 +829,26 @@ static void upload_params(ake_pcn* p, const float* flat_dev, int64_t n, cudaStre
       }
       equiv_pack_weights_kernel<<<168, 256, 0, st>>>(p->d_params + ct.w_off, p->d_params + ck.w_off, 32, 64, 16, 1, p->d_wimg_heads);
       AKE_LAUNCHED();
+      if (!p->d_wimg_tail) {
+        AKE_CUDA(cudaMalloc(&p->d_wimg_tail, (size_t)3 * 24 * 512));
+        AKE_CUDA(cudaMalloc(&p->d_wimg_genre, (size_t)16384));
+      }
+      AKE_CUDA(cudaMemsetAsync(p->d_wimg_tail, 0, (size_t)3 * 24 * 512, st));
+      {
+        const Conv* tc[3] = {&p->convs[p->tonic_head[1]], &p->convs[p->key_head[1]], p->cfg.genre ? &p->convs[p->genre_head[1]] : nullptr};
+        for (int h = 0; h < 3; ++h) {
+          if (!tc[h]) continue;
+          if (tc[h]->Cin != 32) fail(AKE_ERR_UNSUPPORTED, "internal: head tail expects 32 input channels");
+          head_tail_pack_kernel<<<cdiv(tc[h]->KH * 256, 256), 256, 0, st>>>(
+              p->d_params + tc[h]->w_off, tc[h]->KH, reinterpret_cast<__half*>(reinterpret_cast<uint8_t*>(p->d_wimg_tail) + (size_t)h * 24 * 512));
+          AKE_LAUNCHED();
+        }
+        if (p->cfg.genre) {
+          const Conv& cg = p->convs[p->genre_head[0]];
+          equiv_pack_weights_kernel<<<16, 256, 0, st>>>(p->d_params + cg.w_off, p->d_params + cg.w_off, 32, 32, 16, 1, p->d_wimg_genre, 1);
+          AKE_LAUNCHED();
+        }
+      }
       const Conv* hc[2] = {&ct, &ck};
       for (int h = 0; h < 2; ++h) {
         AKE_CUDA(cudaMemcpyAsync(p->d_ss_heads + 32 * h, p->d_ss_eval + hc[h]->ss_off, sizeof(float) * 32, cudaMemcpyDeviceToDevice, st));
@@ -909,6 +944,8 @@ void ake_pcn_destroy(ake_pcn* p) {
   cudaFree(p->d_wimg_pc);
   cudaFree(p->d_wimg_heads);
   cudaFree(p->d_ss_heads);
+  cudaFree(p->d_wimg_genre);
+  cudaFree(p->d_wimg_tail);
   delete p->tape;
   delete p;
 }

@@ -383,6 +383,7 @@ struct EquivArgs {
   int Wd_out, col_off;
   float* out_f32;
   float* out_f32_b;
+  int out_rows;   // EPI 3: rows per group of the output planes (23: wrapped pitch classes, 12: plain rows)
 };
 
 constexpr uint32_t kEqStageBytes = 16384;
@@ -397,18 +398,19 @@ __host__ __device__ inline size_t equiv_smem_bytes(int Wt) {
 // co = n % NCO), rows [N1/2, N1) = W_lo.  PH = 2: j = dp*4 + s/2, time tap dt = s + f (zero for dt = 7); PH = 1: j = dp*7 + dt.
 // Output channels [0, split) come from w0 (Cout0 = split), [split, NCO) from w1.
 __global__ void equiv_pack_weights_kernel(const float* __restrict__ w0, const float* __restrict__ w1, int split, int NCO, int Cin, int PH,
-                                          __half* __restrict__ img) {
-  const int N2 = NCO * PH, NS = 12 * (PH == 2 ? 4 : 7);
+                                          __half* __restrict__ img, int KH = 12) {
+  // KH = 1 (the genre head's Conv2d(16, 32, (1, 7)), models.py:724): 7 taps + one all-zero start, PH = 1
+  const int N2 = NCO * PH, NS = KH == 12 ? 12 * (PH == 2 ? 4 : 7) : 8;
   const int n_items = NS * 2 * N2 * 8;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_items; i += gridDim.x * blockDim.x) {
     const int e = i % 8, n = (i / 8) % N2, g = (i / (8 * N2)) % 2, j = i / (16 * N2);
     const int f = n / NCO, co = n % NCO, ci = g * 8 + e;
-    const int dp = PH == 2 ? j / 4 : j / 7, dt = PH == 2 ? 2 * (j % 4) + f : j % 7;
+    const int dp = KH == 12 ? (PH == 2 ? j / 4 : j / 7) : 0, dt = KH == 12 ? (PH == 2 ? 2 * (j % 4) + f : j % 7) : j;
     float v = 0.f;
     if (dt < 7 && ci < Cin) {
       const float* w = co < split ? w0 : w1;
       const int cc = co < split ? co : co - split;
-      v = w[(((long long)cc * Cin + ci) * 12 + dp) * 7 + dt] * kWScale;
+      v = w[(((long long)cc * Cin + ci) * KH + dp) * 7 + dt] * kWScale;
     }
     const __half hi = __float2half_rn(v);
     const __half lo = __float2half_rn(v - __half2float(hi));
@@ -418,13 +420,14 @@ __global__ void equiv_pack_weights_kernel(const float* __restrict__ w0, const fl
   }
 }
 
-template <int NCO, int PH, int EPI>
+template <int NCO, int PH, int EPI, int KHT = 12>
 __global__ void __launch_bounds__(192) equiv_umma_kernel(const EquivArgs a) {
   using namespace umma;
   constexpr int N2 = NCO * PH, N1 = 2 * N2;
   constexpr int ACC = N1;                        // TMEM columns per accumulator (one 128-anchor block)
   constexpr int NACC = ACC <= 64 ? 2 : 1;        // blocks sharing one pass over the weight stream
-  constexpr int NS = 12 * (PH == 2 ? 4 : 7);     // MMA starts per block
+  constexpr int NS = KHT == 12 ? 12 * (PH == 2 ? 4 : 7) : 8;  // MMA starts per block (KHT = 1: 7 taps + a zero-weight start)
+  static_assert(KHT == 12 || (KHT == 1 && PH == 1), "row taps: 12 (equivariant) or 1");
   constexpr uint32_t START_BYTES = 32u * N1;
   constexpr int SPS = kEqStageBytes / START_BYTES;
   constexpr int NSTG = NS / SPS;
@@ -516,7 +519,7 @@ __global__ void __launch_bounds__(192) equiv_umma_kernel(const EquivArgs a) {
 #pragma unroll
           for (int u = 0; u < SPS; ++u) {
             const int j = stg * SPS + u;
-            const int dp = PH == 2 ? j / 4 : j / 7, sft = PH == 2 ? 2 * (j % 4) : j % 7;
+            const int dp = KHT == 12 ? (PH == 2 ? j / 4 : j / 7) : 0, sft = KHT == 12 ? (PH == 2 ? 2 * (j % 4) : j % 7) : j;
             const uint64_t bd = make_desc(B_DESC, w0 + s * kEqStageBytes + u * START_BYTES);
 #pragma unroll
             for (int acc = 0; acc < NACC; ++acc) {
@@ -627,6 +630,27 @@ __global__ void __launch_bounds__(192) equiv_umma_kernel(const EquivArgs a) {
           for (int h = 0; h < NCO / 16; ++h) {
             float u[16], w[16];
             tmem_ld16(d + h * 16, u), tmem_ld16(d + N2 + h * 16, w);
+            if constexpr (EPI == 3) {
+              // BN + LeakyReLU -> chunk planes [B][NCO / 8 groups][out_rows][T_out][8] for the tensor-core head tails
+              if (valid) {
+                float g0[8], g1[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  g0[j] = leaky_f(fmaf(u[j] + w[j], s_scale[h * 16 + j], s_shift[h * 16 + j]));
+                  g1[j] = leaky_f(fmaf(u[8 + j] + w[8 + j], s_scale[h * 16 + 8 + j], s_shift[h * 16 + 8 + j]));
+                }
+                const long long q0 = ((((long long)b * (NCO / 8) + 2 * h) * a.out_rows + c) * a.T_out + t) * 8;
+                const long long q1 = q0 + (long long)a.out_rows * a.T_out * 8;
+                store_split8(a.out_hi + q0, a.out_lo + q0, g0);
+                store_split8(a.out_hi + q1, a.out_lo + q1, g1);
+                if (a.out_rows == 23 && c < 11) {
+                  const long long wr = (long long)12 * a.T_out * 8;
+                  store_split8(a.out_hi + q0 + wr, a.out_lo + q0 + wr, g0);
+                  store_split8(a.out_hi + q1 + wr, a.out_lo + q1 + wr, g1);
+                }
+              }
+              continue;
+            }
             if (valid) {
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
@@ -646,6 +670,162 @@ __global__ void __launch_bounds__(192) equiv_umma_kernel(const EquivArgs a) {
   fence_before_sync();
   __syncthreads();
   if (warp == 4) tmem_dealloc(tmem, 256);
+}
+
+// ---- last convolution of the classifier heads on tensor cores (models.py:716-733: 32 -> 1 channel, valid in time) -----
+//   out[c, t] = bias + sum_{ci<32, dp<KH, dt<7} W[ci, dp, dt] x[ci, c + dp, t + dt]     (rows wrap for tonic / key: 23-row planes)
+// One output channel would leave the MMA's N idle, so the 7 time taps are the N-phases:
+//   D_f[a] = sum_{ci, dp} W[ci, dp, f] x[ci, a + dp * Wt],   out[a] = sum_f D_f[a + f]       (a = c * Wt + tl, as in the 7x7 kernel)
+// K = 16 = two channel groups of one position (LBO = group plane), two K-halves per row tap; N = 16 = 8 phases x {W_hi, W_lo};
+// both the x_hi and the x_lo MMA use the full [W_hi | W_lo] operand (N = 16 is the minimum: the extra x_lo * W_lo term is free).
+// Input: chunk planes [B][G_total][R][T1][8] written by equiv_umma_kernel EPI 3.  grid (time tiles, heads, B).
+struct HeadUmmaArgs {
+  const __half* in_hi[3];
+  const __half* in_lo[3];
+  int G_total[3], g0[3], R[3], KH[3], rows_out[3];
+  const __half* wimg[3];  // [KH * 2 starts][chunk 2][n 16][ci 8]
+  const float* bias[3];
+  float* out[3];          // (B, 1, rows_out, Tf)
+  int T1, Tf, TB, n_ttiles;
+};
+
+constexpr int kHtStride = 122;  // anchors produced per 128-row block (6 rows feed the phase shifts)
+
+__host__ __device__ inline uint32_t head_tail_group_positions(int Wt) { return (uint32_t)(23 * Wt + 136); }
+__host__ __device__ inline size_t head_tail_smem_bytes(int Wt) {
+  return (size_t)8 * head_tail_group_positions(Wt) * 16 + 24 * 512 + 6 * 128 * 4;
+}
+
+// W (1, 32, KH, 7) -> operand image: start j = dp * 2 + kh covers channels [16 kh, 16 kh + 16); n < 8: W_hi of time tap n
+// (zero for n = 7), n >= 8: W_lo.
+__global__ void head_tail_pack_kernel(const float* __restrict__ w, int KH, __half* __restrict__ img) {
+  const int n_items = KH * 2 * 2 * 8 * 8;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_items; i += gridDim.x * blockDim.x) {
+    const int e = i % 8, f = (i / 8) % 8, g = (i / 64) % 2, j = i / 128;
+    const int dp = j / 2, kh = j % 2, ci = kh * 16 + g * 8 + e;
+    const float v = f < 7 ? w[((long long)ci * KH + dp) * 7 + f] * kWScale : 0.f;
+    const __half hi = __float2half_rn(v);
+    const __half lo = __float2half_rn(v - __half2float(hi));
+    img[((j * 2 + g) * 16 + f) * 8 + e] = hi;
+    img[((j * 2 + g) * 16 + 8 + f) * 8 + e] = lo;
+  }
+}
+
+__global__ void __launch_bounds__(160) head_tail_umma_kernel(const HeadUmmaArgs a) {
+  using namespace umma;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t tile_bar, acc_full[2], acc_empty[2];
+  __shared__ uint32_t tmem_slot;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int h = blockIdx.y, b = blockIdx.z, t0 = blockIdx.x * a.TB;
+  const int KH = a.KH[h], R = a.R[h], rows_out = a.rows_out[h];
+  const int TBv = min(a.TB, a.Tf - t0);
+  const int Wt = a.TB + 6;
+  const int cols_in = min(Wt, a.T1 - t0);
+  const int rows_in = rows_out + KH - 1;  // 23 (wrapped) or 12
+  const uint32_t GPpos = head_tail_group_positions(Wt), GP = GPpos * 16;
+  const int n_anchor = rows_out * Wt;
+  const int n_mb = (n_anchor + kHtStride - 1) / kHtStride;
+  uint8_t* s_hi = smem;            // [g 4][GP]
+  uint8_t* s_lo = smem + 4 * GP;
+  uint8_t* s_w = smem + 8 * GP;    // 24 starts x 512 B
+  float* s_ex = reinterpret_cast<float*>(smem + 8 * GP + 24 * 512);  // [6 phases][128]
+
+  if (warp == 4) tmem_alloc(&tmem_slot, 32);
+  if (tid == 0) {
+    mbar_init(&tile_bar, 1);
+    mbar_init(&acc_full[0], 1), mbar_init(&acc_full[1], 1);
+    mbar_init(&acc_empty[0], 128), mbar_init(&acc_empty[1], 128);
+    mbar_init_fence();
+  }
+  {
+    // zero what the bulk copies leave untouched (rows beyond rows_in, the tail padding, the column gap of a narrow last tile)
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    const int gap = Wt - cols_in;
+    for (int pl = 0; pl < 8; ++pl) {
+      uint4* base = reinterpret_cast<uint4*>(smem + (size_t)pl * GP);
+      for (uint32_t i = (uint32_t)rows_in * Wt + tid; i < GPpos; i += blockDim.x) base[i] = z;
+      if (gap > 0)
+        for (int i = tid; i < rows_in * gap; i += blockDim.x) base[(uint32_t)(i / gap) * Wt + cols_in + i % gap] = z;
+    }
+    fence_proxy_async();
+  }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+
+  if (warp == 4) {
+    // ------------------------------------------------------------ loader + MMA issuer
+    const uint32_t row_bytes = (uint32_t)cols_in * 16;
+    const uint32_t w_bytes = (uint32_t)KH * 2 * 512;
+    if (lane == 0) mbar_arrive_expect_tx(&tile_bar, w_bytes + 8u * rows_in * row_bytes);
+    __syncwarp();
+    if (lane == 0) bulk_g2s(s_w, a.wimg[h], w_bytes, &tile_bar);
+    for (int idx = lane; idx < 4 * rows_in; idx += 32) {
+      const int g = idx / rows_in, r = idx - g * rows_in;
+      const long long src = ((((long long)b * a.G_total[h] + a.g0[h] + g) * R + r) * a.T1 + t0) * 8;
+      bulk_g2s(s_hi + (size_t)g * GP + (size_t)r * Wt * 16, a.in_hi[h] + src, row_bytes, &tile_bar);
+      bulk_g2s(s_lo + (size_t)g * GP + (size_t)r * Wt * 16, a.in_lo[h] + src, row_bytes, &tile_bar);
+    }
+    if (lane == 0) {
+      mbar_wait(&tile_bar, 0);
+      const uint64_t A_DESC = desc_hi(GP);          // chunk 1 = the next channel group of the same position
+      constexpr uint64_t B_DESC = desc_hi(16 * 16);  // chunk stride: 16 rows x 16 B
+      constexpr uint32_t IDESC = idesc_f16(16);
+      const uint32_t hi0 = smem_u32(s_hi), lo0 = smem_u32(s_lo), w0 = smem_u32(s_w);
+      for (int m = 0; m < n_mb; ++m) {
+        const int buf = m & 1;
+        mbar_wait(&acc_empty[buf], ((m >> 1) & 1) ^ 1);
+        fence_after_sync();
+        const uint32_t d = tmem + buf * 16;
+        for (int dp = 0; dp < KH; ++dp) {
+#pragma unroll
+          for (int kh = 0; kh < 2; ++kh) {
+            const uint32_t off = (uint32_t)(m * kHtStride + dp * Wt) * 16 + (uint32_t)(2 * kh) * GP;
+            const uint64_t bd = make_desc(B_DESC, w0 + (uint32_t)(dp * 2 + kh) * 512);
+            mma_f16(d, make_desc(A_DESC, hi0 + off), bd, IDESC, (dp | kh) ? 1u : 0u);
+            mma_f16(d, make_desc(A_DESC, lo0 + off), bd, IDESC, 1u);
+          }
+        }
+        commit(&acc_full[buf]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue: thread = TMEM lane = anchor row
+    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+    const float bias = __ldg(a.bias[h]);
+    for (int m = 0; m < n_mb; ++m) {
+      const int buf = m & 1;
+      mbar_wait(&acc_full[buf], (m >> 1) & 1);
+      fence_after_sync();
+      float u[16];
+      tmem_ld16(lane_base + buf * 16, u);
+      fence_before_sync();
+      mbar_arrive(&acc_empty[buf]);
+      float v[7];
+#pragma unroll
+      for (int f = 0; f < 7; ++f) v[f] = u[f] + u[8 + f];
+#pragma unroll
+      for (int f = 1; f < 7; ++f) s_ex[(f - 1) * 128 + tid] = v[f];
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int anchor = m * kHtStride + tid;
+      if (tid < kHtStride && anchor < n_anchor) {
+        const int c = anchor / Wt, tl = anchor - c * Wt;
+        if (tl < TBv) {
+          float o = v[0];
+#pragma unroll
+          for (int f = 1; f < 7; ++f) o += s_ex[(f - 1) * 128 + tid + f];
+          a.out[h][((long long)b * rows_out + c) * a.Tf + t0 + tl] = fmaf(o, 1.f / kWScale, bias);
+        }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem, 32);
 }
 
 }  // namespace ake
