@@ -529,7 +529,7 @@ void Fwd::run(const float* mel, float* key_out, float* tonic_out, float* genre_o
                       reinterpret_cast<const __half*>(reinterpret_cast<const uint8_t*>(p->d_wimg) + i * kP2PWBytes),
                       scale_of(c, false), shift_of(c, false), P, Tn, Wd, TB, cdiv(Tn, TB)};
             dim3 grid(cdiv(P, kP2PRows) * cdiv(Tn, TB), B);
-            p2p_umma_kernel<<<grid, 160, smem, st>>>(a);
+            p2p_umma_kernel<<<grid, kP2PThreads, smem, st>>>(a);
             AKE_LAUNCHED();
           }
           cur ^= 1;

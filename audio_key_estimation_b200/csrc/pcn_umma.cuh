@@ -9,12 +9,13 @@
 //
 // Pitch2Pitch 7x7 circular convolution (models.py:228-234; 64.6 % of the forward's MACs):
 //   out[a] = sum_{dp<7} sum_{dt<7} X[a + dp*Wt + dt] . W[dp][dt]        (a = flattened anchor, 8 -> 8 channels)
-// is issued as 7 row taps x 2 MMAs per 128 anchors:
-//   K = 16 : chunk 0 = X[a' + dp*Wt], chunk 1 = X[a' + dp*Wt + 1]                 (LBO = 16 B: two time taps)
-//   N = 64 : 4 "phases" f (time taps 2f, 2f+1) x 8 output channels x {W_hi, W_lo}   (MMA 1, A = X_hi)
-//   N = 32 : the W_hi half only                                                     (MMA 2, A = X_lo)
-// and the epilogue adds the phases back together one row apart:  out[a] = sum_f D_f[a + 2f]  (fixed order, so every
+// is issued as ONE MMA per row tap and 128 anchors:
+//   K = 16 : chunk 0 = X_hi[a' + dp*Wt], chunk 1 = X_lo[a' + dp*Wt]            (LBO = distance between the hi and lo planes)
+//   N = 112: 7 "phases" f (time tap dt = f) x 8 output channels x {W_hi, W_lo}   (both K chunks meet the same weights)
+// and the epilogue adds the phases back together one row apart:  out[a] = sum_f D_f[a + f]  (fixed order, so every
 // output is accumulated identically whatever its pitch -> transposition equivariance stays bit exact).
+// Cost model (tools/umma_rate.cu): 7 x max(56, 32 + 28) = 420 cycles per 122 anchors, against 7 x (48 + 40) = 616 for the
+// earlier two-MMA form (time-tap pairs in K, x_hi and x_lo in separate MMAs).
 #pragma once
 #include "common.cuh"
 #include "umma.cuh"
@@ -25,6 +26,8 @@ constexpr float kWScale = 64.f;     // conv weights are scaled into fp16's norma
 constexpr int kP2PStride = 122;     // anchors produced per 128-row MMA block (6 rows feed the phase shifts)
 constexpr int kP2PRows = 8;         // pitch rows per CTA tile
 constexpr int kP2PMaxTB = 160;      // frames per CTA tile (upper bound)
+constexpr int kP2PPubFloats = 4 * 6 * 6 * 8;  // per epilogue group: [warp 4][phase 6][lane 6][co 8] boundary values
+constexpr int kP2PThreads = 288;    // 2 epilogue groups of 4 warps + the loader / MMA-issuer warp
 
 __device__ __forceinline__ float leaky_f(float v) { return v > 0.f ? v : kLeakySlope * v; }
 
@@ -82,19 +85,22 @@ __global__ void __launch_bounds__(256) p2p_prep_kernel(const PrepArgs a) {
   }
 }
 
-// ---- weight image for the 7x7 convolution: [dp 7][chunk 2][n 64][ci 8] fp16 ---------------------------------------
-// n < 32: W_hi of (phase f = n / 8, co = n % 8), time tap dt = 2 f + chunk (zero for dt = 7); n >= 32: W_lo.
+// ---- weight image for the 7x7 convolution: [dp 7][chunk 2][n 112][ci 8] fp16 ------------------------------------------
+// n < 56: W_hi of (time tap f = n / 8, co = n % 8); n >= 56: W_lo.  Both chunks (x_hi, x_lo) hold the same weights.
 __global__ void p2p_pack_weights_kernel(const float* __restrict__ w, int Cout, int Cin, __half* __restrict__ img) {
-  const int n_items = 7 * 2 * 32 * 8;
+  const int n_items = 7 * 56 * 8;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_items; i += gridDim.x * blockDim.x) {
-    const int ci = i % 8, n = (i / 8) % 32, c = (i / 256) % 2, dp = i / 512;
-    const int f = n / 8, co = n % 8, dt = 2 * f + c;
+    const int ci = i % 8, n = (i / 8) % 56, dp = i / 448;
+    const int f = n / 8, co = n % 8;
     float v = 0.f;
-    if (dt < 7 && ci < Cin && co < Cout) v = w[(((long long)co * Cin + ci) * 7 + dp) * 7 + dt] * kWScale;
+    if (ci < Cin && co < Cout) v = w[(((long long)co * Cin + ci) * 7 + dp) * 7 + f] * kWScale;
     const __half hi = __float2half_rn(v);
     const __half lo = __float2half_rn(v - __half2float(hi));
-    img[((dp * 2 + c) * 64 + n) * 8 + ci] = hi;
-    img[((dp * 2 + c) * 64 + 32 + n) * 8 + ci] = lo;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      img[((dp * 2 + c) * 112 + n) * 8 + ci] = hi;
+      img[((dp * 2 + c) * 112 + 56 + n) * 8 + ci] = lo;
+    }
   }
 }
 
@@ -103,21 +109,21 @@ struct P2PArgs {
   const __half* in_lo;   // [B][P+6][Wd][8]
   __half* out_hi;
   __half* out_lo;        // same geometry
-  const __half* wimg;    // p2p_pack_weights_kernel image (14336 B)
+  const __half* wimg;    // p2p_pack_weights_kernel image (kP2PWBytes)
   const float* scale;    // 8: eval-mode BN scale (the 1/kWScale factor is applied in the kernel)
   const float* shift;    // 8
   int P, T, Wd;          // Wd = T + 6
   int TB, n_ttiles;      // frames per tile, tiles along time
 };
 
-constexpr uint32_t kP2PWBytes = 7 * 2 * 64 * 16;
+constexpr uint32_t kP2PWBytes = 7 * 2 * 112 * 16;
 
 __host__ __device__ inline uint32_t p2p_plane_positions(int Wt) { return (uint32_t)((kP2PRows + 6) * Wt + 136); }
 __host__ __device__ inline size_t p2p_smem_bytes(int Wt) {
-  return (size_t)2 * p2p_plane_positions(Wt) * 16 + kP2PWBytes + 6 * 128 * 16;
+  return (size_t)2 * p2p_plane_positions(Wt) * 16 + kP2PWBytes + 2 * kP2PPubFloats * 4;
 }
 
-__global__ void __launch_bounds__(160) p2p_umma_kernel(const P2PArgs a) {
+__global__ void __launch_bounds__(kP2PThreads) p2p_umma_kernel(const P2PArgs a) {
   using namespace umma;
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t tile_bar, acc_full[2], acc_empty[2];
@@ -136,9 +142,9 @@ __global__ void __launch_bounds__(160) p2p_umma_kernel(const P2PArgs a) {
   uint8_t* s_hi = smem;
   uint8_t* s_lo = smem + plane;
   uint8_t* s_w = smem + 2 * plane;
-  float4* s_ex = reinterpret_cast<float4*>(smem + 2 * plane + kP2PWBytes);  // [(phase-1)*2 + half][128 rows]
+  float* s_pub = reinterpret_cast<float*>(smem + 2 * plane + kP2PWBytes);  // per epilogue group: kP2PPubFloats
 
-  if (warp == 4) tmem_alloc(&tmem_slot, 128);
+  if (warp == 8) tmem_alloc(&tmem_slot, 256);
   if (tid == 0) {
     mbar_init(&tile_bar, 1);
     mbar_init(&acc_full[0], 1), mbar_init(&acc_full[1], 1);
@@ -168,7 +174,7 @@ __global__ void __launch_bounds__(160) p2p_umma_kernel(const P2PArgs a) {
   fence_after_sync();
   const uint32_t tmem = tmem_slot;
 
-  if (warp == 4) {
+  if (warp == 8) {
     // ------------------------------------------------------------ loader + MMA issuer
     const int rows_in = PB + 6;
     const int cols_in = min(Wt, a.Wd - t0);  // the last time tile may be narrower than Wt
@@ -183,67 +189,74 @@ __global__ void __launch_bounds__(160) p2p_umma_kernel(const P2PArgs a) {
     }
     if (lane == 0) {
       mbar_wait(&tile_bar, 0);
-      constexpr uint64_t A_DESC = desc_hi(16);        // chunk 1 = next position (next time frame)
-      constexpr uint64_t B_DESC = desc_hi(64 * 16);   // chunk stride: 64 rows x 16 B
-      constexpr uint32_t IDESC64 = idesc_f16(64), IDESC32 = idesc_f16(32);
-      const uint32_t hi0 = smem_u32(s_hi), lo0 = smem_u32(s_lo), w0 = smem_u32(s_w);
+      const uint64_t A_DESC = desc_hi(plane);         // chunk 1 = the x_lo plane at the same position
+      constexpr uint64_t B_DESC = desc_hi(112 * 16);  // chunk stride: 112 rows x 16 B
+      constexpr uint32_t IDESC = idesc_f16(112);
+      const uint32_t hi0 = smem_u32(s_hi), w0 = smem_u32(s_w);
       for (int m = 0; m < n_mb; ++m) {
         const int buf = m & 1;
         mbar_wait(&acc_empty[buf], ((m >> 1) & 1) ^ 1);
         fence_after_sync();
-        const uint32_t d = tmem + buf * 64;
+        const uint32_t d = tmem + buf * 128;
         const uint32_t a_off = (uint32_t)(m * kP2PStride) * 16;
 #pragma unroll
-        for (int dp = 0; dp < 7; ++dp) {
-          const uint32_t off = a_off + (uint32_t)(dp * Wt) * 16;
-          const uint64_t bd = make_desc(B_DESC, w0 + dp * 2048);
-          mma_f16(d, make_desc(A_DESC, hi0 + off), bd, IDESC64, dp ? 1u : 0u);
-          mma_f16(d, make_desc(A_DESC, lo0 + off), bd, IDESC32, 1u);
-        }
+        for (int dp = 0; dp < 7; ++dp)
+          mma_f16(d, make_desc(A_DESC, hi0 + a_off + (uint32_t)(dp * Wt) * 16), make_desc(B_DESC, w0 + dp * (2 * 112 * 16)), IDESC, dp ? 1u : 0u);
         commit(&acc_full[buf]);
       }
     }
   } else {
     // ------------------------------------------------------------ epilogue: thread = TMEM lane = anchor row
-    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
-    for (int m = 0; m < n_mb; ++m) {
-      const int buf = m & 1;
+    // Two groups of four warps take alternate blocks (group g owns accumulator buffer g), so the TMEM drain, the phase
+    // exchange and the stores of one block overlap the MMAs of the next two.
+    const int grp = warp >> 2, tid = threadIdx.x & 127;
+    const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    for (int m = grp; m < n_mb; m += 2) {
+      const int buf = grp;
       mbar_wait(&acc_full[buf], (m >> 1) & 1);
       fence_after_sync();
-      float v[4][8];
-      {
-        float u[16], w[16];
+      // phase f = time tap f: out[a] = sum_f D_f[a + f].  D_f of this thread's row: columns [8 f, 8 f + 8) (W_hi) + [56 + 8 f, ..) (W_lo).
+      // Rows a + f live f lanes further on: warp shuffles, plus a small shared-memory hand-over of the first 6 lanes of
+      // the next warp (fixed summation order for every anchor).
+      float o[8];
+      float* pub = s_pub + grp * kP2PPubFloats;
+      const int wq = warp & 3;
+      float nb[6][8];  // phase f values shuffled down by f (valid where lane + f < 32)
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          tmem_ld16(lane_base + buf * 64 + h * 16, u);
-          tmem_ld16(lane_base + buf * 64 + 32 + h * 16, w);
+      for (int f = 0; f < 7; ++f) {
+        float u[8], w[8];
+        tmem_ld8(lane_base + buf * 128 + 8 * f, u);
+        tmem_ld8(lane_base + buf * 128 + 56 + 8 * f, w);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[2 * h + j / 8][j % 8] = u[j] + w[j];
+        for (int c = 0; c < 8; ++c) u[c] += w[c];
+        if (f == 0) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) o[c] = u[c];
+        } else {
+          if (lane < 6) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) pub[((wq * 6 + (f - 1)) * 6 + lane) * 8 + c] = u[c];
+          }
+#pragma unroll
+          for (int c = 0; c < 8; ++c) nb[f - 1][c] = __shfl_down_sync(0xffffffffu, u[c], f);
         }
       }
       fence_before_sync();
       mbar_arrive(&acc_empty[buf]);  // accumulator drained: the issuer may start block m + 2
-      float4* ex = s_ex;
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
 #pragma unroll
-      for (int f = 1; f < 4; ++f) {
-        ex[((f - 1) * 2 + 0) * 128 + tid] = make_float4(v[f][0], v[f][1], v[f][2], v[f][3]);
-        ex[((f - 1) * 2 + 1) * 128 + tid] = make_float4(v[f][4], v[f][5], v[f][6], v[f][7]);
+      for (int f = 1; f < 7; ++f) {
+        if (lane + f >= 32 && wq < 3) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) nb[f - 1][c] = pub[(((wq + 1) * 6 + (f - 1)) * 6 + lane + f - 32) * 8 + c];
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c) o[c] += nb[f - 1][c];
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
       const int anchor = m * kP2PStride + tid;
       if (tid < kP2PStride && anchor < n_anchor) {
         const int pl = anchor / Wt, tl = anchor - pl * Wt;
         if (tl < TBv) {
-          float o[8];
-#pragma unroll
-          for (int c = 0; c < 8; ++c) o[c] = v[0][c];
-#pragma unroll
-          for (int f = 1; f < 4; ++f) {
-            const float4 x0 = ex[((f - 1) * 2 + 0) * 128 + tid + 2 * f];
-            const float4 x1 = ex[((f - 1) * 2 + 1) * 128 + tid + 2 * f];
-            o[0] += x0.x, o[1] += x0.y, o[2] += x0.z, o[3] += x0.w;
-            o[4] += x1.x, o[5] += x1.y, o[6] += x1.z, o[7] += x1.w;
-          }
 #pragma unroll
           for (int c = 0; c < 8; ++c) o[c] = leaky_f(fmaf(o[c], s_scale[c], s_shift[c]));
           uint32_t h[4], l[4];
@@ -271,12 +284,12 @@ __global__ void __launch_bounds__(160) p2p_umma_kernel(const P2PArgs a) {
           }
         }
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");  // the exchange buffer is reused by the next block
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");  // the exchange buffer is reused by the next block
     }
   }
   fence_before_sync();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem, 128);
+  if (warp == 8) tmem_dealloc(tmem, 256);
 }
 
 // ---- pool_semi conv (3x3, stride (3,1), time-circular) + BN + LeakyReLU + octave max pool, from chunk planes ------
