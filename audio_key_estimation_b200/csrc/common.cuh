@@ -58,6 +58,17 @@ inline int guarded(F&& f) {
   }
 }
 
+// SM count of the current device (persistent kernels launch one CTA, or a fixed few, per SM)
+inline int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    AKE_CUDA(cudaGetDevice(&dev));
+    AKE_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+  }
+  return n;
+}
+
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

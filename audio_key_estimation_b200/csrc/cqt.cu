@@ -275,23 +275,6 @@ struct CascadeArgs {
   const __half* img;
 };
 
-// fp32x2 packed arithmetic (sm_100: FMUL2 / FADD2) halves the scale / residual instructions of the hi/lo split
-__device__ __forceinline__ uint64_t f2_pack(float a, float b) {
-  uint64_t r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
-  return r;
-}
-__device__ __forceinline__ void f2_unpack(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
-__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
-  uint64_t r;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
-__device__ __forceinline__ uint64_t f2_sub(uint64_t a, uint64_t b) {
-  uint64_t r;
-  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
 // (a, b) -> fp16 pairs hi, lo with a ~= hi + lo
 __device__ __forceinline__ void cas_split2(uint64_t x, uint32_t& hi, uint32_t& lo) {
   float x0, x1;

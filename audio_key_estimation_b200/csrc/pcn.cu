@@ -525,11 +525,11 @@ void Fwd::run(const float* mel, float* key_out, float* tonic_out, float* genre_o
               AKE_CUDA(cudaFuncSetAttribute(p2p_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
               configured = smem;
             }
+            const int n_rt = cdiv(P, kP2PRows), n_tiles = B * n_rt * cdiv(Tn, TB);
             P2PArgs a{x[cur][0], x[cur][1], x[cur ^ 1][0], x[cur ^ 1][1],
                       reinterpret_cast<const __half*>(reinterpret_cast<const uint8_t*>(p->d_wimg) + i * kP2PWBytes),
-                      scale_of(c, false), shift_of(c, false), P, Tn, Wd, TB, cdiv(Tn, TB)};
-            dim3 grid(cdiv(P, kP2PRows) * cdiv(Tn, TB), B);
-            p2p_umma_kernel<<<grid, kP2PThreads, smem, st>>>(a);
+                      scale_of(c, false), shift_of(c, false), P, Tn, Wd, TB, cdiv(Tn, TB), n_rt, n_tiles};
+            p2p_umma_kernel<<<std::min(n_tiles, sm_count()), kP2PThreads, smem, st>>>(a);  // persistent: one CTA per SM
             AKE_LAUNCHED();
           }
           cur ^= 1;

@@ -25,9 +25,10 @@ namespace ake {
 constexpr float kWScale = 64.f;     // conv weights are scaled into fp16's normal range; folded back in the epilogue
 constexpr int kP2PStride = 122;     // anchors produced per 128-row MMA block (6 rows feed the phase shifts)
 constexpr int kP2PRows = 8;         // pitch rows per CTA tile
+constexpr int kP2PBufs = 2;         // tile buffers of the load ring
 constexpr int kP2PMaxTB = 160;      // frames per CTA tile (upper bound)
-constexpr int kP2PPubFloats = 4 * 6 * 6 * 8;  // per epilogue group: [warp 4][phase 6][lane 6][co 8] boundary values
-constexpr int kP2PThreads = 288;    // 2 epilogue groups of 4 warps + the loader / MMA-issuer warp
+constexpr int kP2PGroups = 4;       // epilogue groups of 4 warps = accumulator buffers of 128 TMEM columns
+constexpr int kP2PThreads = 32 * (4 * kP2PGroups + 2);  // + the loader warp and the MMA-issuer warp
 
 __device__ __forceinline__ float leaky_f(float v) { return v > 0.f ? v : kLeakySlope * v; }
 
@@ -86,20 +87,21 @@ __global__ void __launch_bounds__(256) p2p_prep_kernel(const PrepArgs a) {
 }
 
 // ---- weight image for the 7x7 convolution: [dp 7][chunk 2][n 112][ci 8] fp16 ------------------------------------------
-// n < 56: W_hi of (time tap f = n / 8, co = n % 8); n >= 56: W_lo.  Both chunks (x_hi, x_lo) hold the same weights.
+// n = 16 f + j: time tap f; j < 8: W_hi of output channel j, j >= 8: W_lo of output channel j - 8 (so one 16-column TMEM
+// load fetches both halves of a phase).  Both chunks (x_hi, x_lo) hold the same weights.
 __global__ void p2p_pack_weights_kernel(const float* __restrict__ w, int Cout, int Cin, __half* __restrict__ img) {
   const int n_items = 7 * 56 * 8;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_items; i += gridDim.x * blockDim.x) {
-    const int ci = i % 8, n = (i / 8) % 56, dp = i / 448;
-    const int f = n / 8, co = n % 8;
+    const int ci = i % 8, fc = (i / 8) % 56, dp = i / 448;
+    const int f = fc / 8, co = fc % 8;
     float v = 0.f;
     if (ci < Cin && co < Cout) v = w[(((long long)co * Cin + ci) * 7 + dp) * 7 + f] * kWScale;
     const __half hi = __float2half_rn(v);
     const __half lo = __float2half_rn(v - __half2float(hi));
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
-      img[((dp * 2 + c) * 112 + n) * 8 + ci] = hi;
-      img[((dp * 2 + c) * 112 + 56 + n) * 8 + ci] = lo;
+      img[((dp * 2 + c) * 112 + 16 * f + co) * 8 + ci] = hi;
+      img[((dp * 2 + c) * 112 + 16 * f + 8 + co) * 8 + ci] = lo;
     }
   }
 }
@@ -114,182 +116,236 @@ struct P2PArgs {
   const float* shift;    // 8
   int P, T, Wd;          // Wd = T + 6
   int TB, n_ttiles;      // frames per tile, tiles along time
+  int n_rtiles, n_tiles; // pitch-row tiles per clip; tiles in the launch (B * n_rtiles * n_ttiles)
 };
 
 constexpr uint32_t kP2PWBytes = 7 * 2 * 112 * 16;
+constexpr uint32_t kP2PPubBytes = 2 * 3 * 21 * 32;  // per epilogue group: [parity 2][warp 1..3][phase f = 1..6: f lanes][co 8] floats
 
 __host__ __device__ inline uint32_t p2p_plane_positions(int Wt) { return (uint32_t)((kP2PRows + 6) * Wt + 136); }
 __host__ __device__ inline size_t p2p_smem_bytes(int Wt) {
-  return (size_t)2 * p2p_plane_positions(Wt) * 16 + kP2PWBytes + 2 * kP2PPubFloats * 4;
+  return (size_t)2 * kP2PBufs * p2p_plane_positions(Wt) * 16 + kP2PWBytes + kP2PGroups * kP2PPubBytes;
 }
 
-__global__ void __launch_bounds__(kP2PThreads) p2p_umma_kernel(const P2PArgs a) {
+// Persistent CTA (one per SM), warp-specialised:
+//   warp 4G     : loader -- lands the next tile's (rows + 6) x Wt positions of the hi and lo planes in the free tile buffer
+//                 with one bulk async copy per row and plane (two tile buffers: the load of tile k+1 overlaps the MMAs of k)
+//   warp 4G + 1 : one lane issues 7 MMAs per 128-anchor block into accumulator buffer (block % G) of TMEM
+//   warps 0..4G-1: G epilogue groups of 4 warps; group g drains blocks g, g + G, ... (thread = TMEM lane = anchor):
+//                 phase realignment (shuffles + a 6-lane hand-over between neighbouring warps), BN + LeakyReLU, fp16
+//                 hi/lo split, stores of the home position and of the circular halo copies.
+__global__ void __launch_bounds__(kP2PThreads, 1) p2p_umma_kernel(const P2PArgs a) {
   using namespace umma;
+  constexpr int G = kP2PGroups;
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ __align__(8) uint64_t tile_bar, acc_full[2], acc_empty[2];
+  __shared__ __align__(8) uint64_t w_bar, full_bar[kP2PBufs], empty_bar[kP2PBufs], acc_full[G], acc_empty[G];
   __shared__ uint32_t tmem_slot;
   __shared__ float s_scale[8], s_shift[8];
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int ttile = blockIdx.x % a.n_ttiles, rtile = blockIdx.x / a.n_ttiles, b = blockIdx.y;
-  const int p0 = rtile * kP2PRows, t0 = ttile * a.TB;
-  const int PB = min(kP2PRows, a.P - p0);           // valid output rows of this tile
-  const int TBv = min(a.TB, a.T - t0);              // valid output frames
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int Wt = a.TB + 6;                          // tile pitch (positions per staged row)
-  const int n_anchor = PB * Wt;
-  const int n_mb = (n_anchor + kP2PStride - 1) / kP2PStride;
   const uint32_t plane = p2p_plane_positions(Wt) * 16;
-  uint8_t* s_hi = smem;
-  uint8_t* s_lo = smem + plane;
-  uint8_t* s_w = smem + 2 * plane;
-  float* s_pub = reinterpret_cast<float*>(smem + 2 * plane + kP2PWBytes);  // per epilogue group: kP2PPubFloats
+  uint8_t* s_w = smem + 2 * kP2PBufs * plane;
+  uint8_t* s_pub = s_w + kP2PWBytes;
+  const int tiles_per_clip = a.n_rtiles * a.n_ttiles;
 
-  if (warp == 8) tmem_alloc(&tmem_slot, 256);
-  if (tid == 0) {
-    mbar_init(&tile_bar, 1);
-    mbar_init(&acc_full[0], 1), mbar_init(&acc_full[1], 1);
-    mbar_init(&acc_empty[0], 128), mbar_init(&acc_empty[1], 128);
+  struct Geom {
+    int b, p0, t0, PB, TBv, cols_in, n_anchor, n_mb;
+  };
+  auto geom = [&](int tile) {
+    Geom g;
+    g.b = tile / tiles_per_clip;
+    const int r = tile - g.b * tiles_per_clip;
+    const int rtile = r / a.n_ttiles, ttile = r - rtile * a.n_ttiles;
+    g.p0 = rtile * kP2PRows, g.t0 = ttile * a.TB;
+    g.PB = min(kP2PRows, a.P - g.p0);          // valid output rows of this tile
+    g.TBv = min(a.TB, a.T - g.t0);             // valid output frames
+    g.cols_in = min(Wt, a.Wd - g.t0);          // the last time tile may be narrower than Wt
+    g.n_anchor = g.PB * Wt;
+    g.n_mb = (g.n_anchor + kP2PStride - 1) / kP2PStride;
+    return g;
+  };
+
+  if (warp == 4 * G + 1) tmem_alloc(&tmem_slot, 128 * G);
+  if (threadIdx.x == 0) {
+    mbar_init(&w_bar, 1);
+    for (int i = 0; i < kP2PBufs; ++i) mbar_init(&full_bar[i], 1), mbar_init(&empty_bar[i], 1);
+    for (int i = 0; i < G; ++i) mbar_init(&acc_full[i], 1), mbar_init(&acc_empty[i], 128);
     mbar_init_fence();
   }
-  if (tid < 8) s_scale[tid] = a.scale[tid] * (1.f / kWScale), s_shift[tid] = a.shift[tid];
-  {
-    // Zero what the bulk copies will not write (tail padding, the column gap of a narrow last time tile): the MMAs
-    // read it under zero weights (time tap 7) and in discarded rows, and 0 * NaN would poison a valid output.
-    const int cols_in = min(Wt, a.Wd - t0);
-    const uint32_t loaded = (uint32_t)(PB + 6) * Wt, total = p2p_plane_positions(Wt);
-    const uint4 z = make_uint4(0, 0, 0, 0);
-    for (uint32_t i = loaded + tid; i < total; i += blockDim.x)
-      reinterpret_cast<uint4*>(s_hi)[i] = z, reinterpret_cast<uint4*>(s_lo)[i] = z;
-    if (cols_in < Wt) {
-      const int gap = Wt - cols_in;
-      for (int i = tid; i < (PB + 6) * gap; i += blockDim.x) {
-        const uint32_t q = (uint32_t)(i / gap) * Wt + cols_in + i % gap;
-        reinterpret_cast<uint4*>(s_hi)[q] = z, reinterpret_cast<uint4*>(s_lo)[q] = z;
-      }
-    }
-    fence_proxy_async();
-  }
+  if (threadIdx.x < 8) s_scale[threadIdx.x] = a.scale[threadIdx.x] * (1.f / kWScale), s_shift[threadIdx.x] = a.shift[threadIdx.x];
+  // Positions the bulk copies never write (tail padding, the column gap of a narrow last time tile) only feed anchors that
+  // are discarded, but they must hold finite values once: a NaN bit pattern would be harmless too, zero is tidier.
+  for (uint32_t i = threadIdx.x; i < 2 * kP2PBufs * plane / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async();
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem = tmem_slot;
 
-  if (warp == 8) {
-    // ------------------------------------------------------------ loader + MMA issuer
-    const int rows_in = PB + 6;
-    const int cols_in = min(Wt, a.Wd - t0);  // the last time tile may be narrower than Wt
-    const uint32_t row_bytes = (uint32_t)cols_in * 16;
-    if (lane == 0) mbar_arrive_expect_tx(&tile_bar, kP2PWBytes + 2u * rows_in * row_bytes);
-    __syncwarp();
-    if (lane == 0) bulk_g2s(s_w, a.wimg, kP2PWBytes, &tile_bar);
-    for (int rr = lane; rr < rows_in; rr += 32) {
-      const long long src = (((long long)b * (a.P + 6) + p0 + rr) * a.Wd + t0) * 8;
-      bulk_g2s(s_hi + (size_t)rr * Wt * 16, a.in_hi + src, row_bytes, &tile_bar);
-      bulk_g2s(s_lo + (size_t)rr * Wt * 16, a.in_lo + src, row_bytes, &tile_bar);
-    }
+  if (warp == 4 * G) {
+    // ------------------------------------------------------------ loader
     if (lane == 0) {
-      mbar_wait(&tile_bar, 0);
-      const uint64_t A_DESC = desc_hi(plane);         // chunk 1 = the x_lo plane at the same position
-      constexpr uint64_t B_DESC = desc_hi(112 * 16);  // chunk stride: 112 rows x 16 B
-      constexpr uint32_t IDESC = idesc_f16(112);
-      const uint32_t hi0 = smem_u32(s_hi), w0 = smem_u32(s_w);
-      for (int m = 0; m < n_mb; ++m) {
-        const int buf = m & 1;
-        mbar_wait(&acc_empty[buf], ((m >> 1) & 1) ^ 1);
+      mbar_arrive_expect_tx(&w_bar, kP2PWBytes);
+      bulk_g2s(s_w, a.wimg, kP2PWBytes, &w_bar);
+    }
+    int k = 0;
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++k) {
+      const int s = k % kP2PBufs;
+      const Geom g = geom(tile);
+      const int rows_in = g.PB + 6;
+      const uint32_t row_bytes = (uint32_t)g.cols_in * 16;
+      mbar_wait(&empty_bar[s], ((k / kP2PBufs) & 1) ^ 1);
+      if (lane == 0) mbar_arrive_expect_tx(&full_bar[s], 2u * rows_in * row_bytes);
+      __syncwarp();
+      uint8_t* d_hi = smem + (size_t)s * 2 * plane;
+      for (int rr = lane; rr < rows_in; rr += 32) {
+        const long long src = (((long long)g.b * (a.P + 6) + g.p0 + rr) * a.Wd + g.t0) * 8;
+        bulk_g2s(d_hi + (size_t)rr * Wt * 16, a.in_hi + src, row_bytes, &full_bar[s]);
+        bulk_g2s(d_hi + plane + (size_t)rr * Wt * 16, a.in_lo + src, row_bytes, &full_bar[s]);
+      }
+    }
+  } else if (warp == 4 * G + 1) {
+    // ------------------------------------------------------------ MMA issuer (converged warp, one elected lane issues)
+    const uint64_t A_DESC = desc_hi(plane);         // chunk 1 = the x_lo plane at the same position
+    constexpr uint64_t B_DESC = desc_hi(112 * 16);  // chunk stride: 112 rows x 16 B
+    constexpr uint32_t IDESC = idesc_f16(112);
+    const uint32_t w0 = smem_u32(s_w);
+    mbar_wait(&w_bar, 0);
+    int k = 0;
+    uint32_t j = 0;  // block counter of this CTA (all roles walk the same sequence)
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++k) {
+      const int s = k % kP2PBufs;
+      const Geom g = geom(tile);
+      const uint32_t hi0 = smem_u32(smem + (size_t)s * 2 * plane);
+      mbar_wait(&full_bar[s], (k / kP2PBufs) & 1);
+      for (int m = 0; m < g.n_mb; ++m, ++j) {
+        const uint32_t buf = j % G;
+        mbar_wait(&acc_empty[buf], ((j / G) & 1) ^ 1);
         fence_after_sync();
         const uint32_t d = tmem + buf * 128;
-        const uint32_t a_off = (uint32_t)(m * kP2PStride) * 16;
+        const uint32_t a_off = hi0 + (uint32_t)(m * kP2PStride) * 16;
+        if (elect_one()) {
 #pragma unroll
-        for (int dp = 0; dp < 7; ++dp)
-          mma_f16(d, make_desc(A_DESC, hi0 + a_off + (uint32_t)(dp * Wt) * 16), make_desc(B_DESC, w0 + dp * (2 * 112 * 16)), IDESC, dp ? 1u : 0u);
-        commit(&acc_full[buf]);
+          for (int dp = 0; dp < 7; ++dp)
+            mma_f16(d, make_desc(A_DESC, a_off + (uint32_t)(dp * Wt) * 16), make_desc(B_DESC, w0 + dp * (2 * 112 * 16)), IDESC, dp ? 1u : 0u);
+          commit(&acc_full[buf]);
+          if (m == g.n_mb - 1) commit(&empty_bar[s]);  // the tile buffer is free once these MMAs have read it
+        }
+        __syncwarp();
       }
     }
   } else {
     // ------------------------------------------------------------ epilogue: thread = TMEM lane = anchor row
-    // Two groups of four warps take alternate blocks (group g owns accumulator buffer g), so the TMEM drain, the phase
-    // exchange and the stores of one block overlap the MMAs of the next two.
-    const int grp = warp >> 2, tid = threadIdx.x & 127;
-    const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    for (int m = grp; m < n_mb; m += 2) {
-      const int buf = grp;
-      mbar_wait(&acc_full[buf], (m >> 1) & 1);
-      fence_after_sync();
-      // phase f = time tap f: out[a] = sum_f D_f[a + f].  D_f of this thread's row: columns [8 f, 8 f + 8) (W_hi) + [56 + 8 f, ..) (W_lo).
-      // Rows a + f live f lanes further on: warp shuffles, plus a small shared-memory hand-over of the first 6 lanes of
-      // the next warp (fixed summation order for every anchor).
-      float o[8];
-      float* pub = s_pub + grp * kP2PPubFloats;
-      const int wq = warp & 3;
-      float nb[6][8];  // phase f values shuffled down by f (valid where lane + f < 32)
+    const int grp = warp >> 2, wq = warp & 3, tid = threadIdx.x & 127;
+    const uint32_t acc = tmem + ((uint32_t)(wq * 32) << 16) + grp * 128;
+    float4* pub = reinterpret_cast<float4*>(s_pub + grp * kP2PPubBytes);
+    const uint32_t wt_magic = 0xFFFFFFFFu / (uint32_t)Wt + 1;  // anchor / Wt == umulhi(anchor, magic) for anchor * Wt < 2^32
+    uint64_t sc2[4], sh2[4];
 #pragma unroll
-      for (int f = 0; f < 7; ++f) {
-        float u[8], w[8];
-        tmem_ld8(lane_base + buf * 128 + 8 * f, u);
-        tmem_ld8(lane_base + buf * 128 + 56 + 8 * f, w);
+    for (int e = 0; e < 4; ++e) sc2[e] = f2_pack(s_scale[2 * e], s_scale[2 * e + 1]), sh2[e] = f2_pack(s_shift[2 * e], s_shift[2 * e + 1]);
+    uint32_t n_done = 0;   // blocks this group has drained
+    uint32_t j = grp, j0 = 0;  // next block of this group; first block of the current tile
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+      const Geom g = geom(tile);
+      const long long base = (long long)g.b * (a.P + 6);
+      for (; j < j0 + g.n_mb; j += G, ++n_done) {
+        const int m = (int)(j - j0);
+        mbar_wait(&acc_full[grp], n_done & 1);
+        fence_after_sync();
+        // phase f = time tap f: out[a] = sum_f D_f[a + f], D_f of this thread's row = columns [16 f, 16 f + 8) (W_hi) +
+        // [16 f + 8, 16 f + 16) (W_lo).  Rows a + f live f lanes further on: warp shuffles for lane + f < 32, the first
+        // lanes of the next warp (through shared memory) otherwise -- ascending f for every anchor either way.
+        float4* pub_w = pub + (n_done & 1) * (3 * 21 * 2);
+        uint64_t o[4];
+        uint32_t r[2][16];
+        tmem_ld16_issue(acc, r[0]);
 #pragma unroll
-        for (int c = 0; c < 8; ++c) u[c] += w[c];
-        if (f == 0) {
+        for (int f = 0; f < 7; ++f) {
+          uint32_t(&v)[16] = r[f & 1];
+          tmem_ld_wait16(v);
+          if (f < 6) tmem_ld16_issue(acc + 16 * (f + 1), r[(f + 1) & 1]);
+          uint64_t u[4];
 #pragma unroll
-          for (int c = 0; c < 8; ++c) o[c] = u[c];
-        } else {
-          if (lane < 6) {
+          for (int e = 0; e < 4; ++e)
+            u[e] = f2_add(f2_pack(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1])),
+                          f2_pack(__uint_as_float(v[8 + 2 * e]), __uint_as_float(v[9 + 2 * e])));
+          if (f == 0) {
 #pragma unroll
-            for (int c = 0; c < 8; ++c) pub[((wq * 6 + (f - 1)) * 6 + lane) * 8 + c] = u[c];
+            for (int e = 0; e < 4; ++e) o[e] = u[e];
+          } else {
+            float x[8];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) f2_unpack(u[e], x[2 * e], x[2 * e + 1]);
+            if (wq > 0 && lane < f) {
+              float4* dst = pub_w + ((wq - 1) * 21 + f * (f - 1) / 2 + lane) * 2;
+              dst[0] = make_float4(x[0], x[1], x[2], x[3]), dst[1] = make_float4(x[4], x[5], x[6], x[7]);
+            }
+#pragma unroll
+            for (int c = 0; c < 8; ++c) x[c] = __shfl_down_sync(0xffffffffu, x[c], f);
+            // o += x on the lanes whose source lane exists: x * 1 + o is the same single rounding as x + o, x * 0 + o = o
+            // (an out-of-range shuffle returns the lane's own, finite, value); predicated FADD2s compile to FADD2 + 2 SEL
+            const float mk = (lane + f < 32) ? 1.f : 0.f;
+            const uint64_t mk2 = f2_pack(mk, mk);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) o[e] = f2_fma(f2_pack(x[2 * e], x[2 * e + 1]), mk2, o[e]);
           }
-#pragma unroll
-          for (int c = 0; c < 8; ++c) nb[f - 1][c] = __shfl_down_sync(0xffffffffu, u[c], f);
         }
-      }
-      fence_before_sync();
-      mbar_arrive(&acc_empty[buf]);  // accumulator drained: the issuer may start block m + 2
-      asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+        fence_before_sync();
+        mbar_arrive(&acc_empty[grp]);  // accumulator drained: the issuer may start block j + G
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+        if (wq < 3 && lane >= 26) {
 #pragma unroll
-      for (int f = 1; f < 7; ++f) {
-        if (lane + f >= 32 && wq < 3) {
-#pragma unroll
-          for (int c = 0; c < 8; ++c) nb[f - 1][c] = pub[(((wq + 1) * 6 + (f - 1)) * 6 + lane + f - 32) * 8 + c];
-        }
-#pragma unroll
-        for (int c = 0; c < 8; ++c) o[c] += nb[f - 1][c];
-      }
-      const int anchor = m * kP2PStride + tid;
-      if (tid < kP2PStride && anchor < n_anchor) {
-        const int pl = anchor / Wt, tl = anchor - pl * Wt;
-        if (tl < TBv) {
-#pragma unroll
-          for (int c = 0; c < 8; ++c) o[c] = leaky_f(fmaf(o[c], s_scale[c], s_shift[c]));
-          uint32_t h[4], l[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) split_f16x2(o[2 * e], o[2 * e + 1], h[e], l[e]);
-          const uint4 hv = make_uint4(h[0], h[1], h[2], h[3]), lv = make_uint4(l[0], l[1], l[2], l[3]);
-          const int p = p0 + pl, t = t0 + tl;
-          // home position + circular halo copies (rows p +- P, columns t +- T)
-          const int row2 = (p < 3) ? p + 3 + a.P : ((p >= a.P - 3) ? p + 3 - a.P : -1);
-          const int col2 = (t < 3) ? t + 3 + a.T : ((t >= a.T - 3) ? t + 3 - a.T : -1);
-          const long long base = (long long)b * (a.P + 6);
-          const long long q00 = ((base + p + 3) * a.Wd + t + 3) * 8;
-          *reinterpret_cast<uint4*>(a.out_hi + q00) = hv, *reinterpret_cast<uint4*>(a.out_lo + q00) = lv;
-          if (col2 >= 0) {
-            const long long q = ((base + p + 3) * a.Wd + col2) * 8;
-            *reinterpret_cast<uint4*>(a.out_hi + q) = hv, *reinterpret_cast<uint4*>(a.out_lo + q) = lv;
+          for (int f = 1; f < 7; ++f) {
+            const bool take = lane + f >= 32;
+            const float4* src = pub_w + (wq * 21 + f * (f - 1) / 2 + (take ? lane + f - 32 : 0)) * 2;
+            const float4 x0 = src[0], x1 = src[1];
+            const float mk = take ? 1.f : 0.f;
+            const uint64_t mk2 = f2_pack(mk, mk);
+            o[0] = f2_fma(f2_pack(x0.x, x0.y), mk2, o[0]), o[1] = f2_fma(f2_pack(x0.z, x0.w), mk2, o[1]);
+            o[2] = f2_fma(f2_pack(x1.x, x1.y), mk2, o[2]), o[3] = f2_fma(f2_pack(x1.z, x1.w), mk2, o[3]);
           }
-          if (row2 >= 0) {
-            const long long q = ((base + row2) * a.Wd + t + 3) * 8;
-            *reinterpret_cast<uint4*>(a.out_hi + q) = hv, *reinterpret_cast<uint4*>(a.out_lo + q) = lv;
+        }
+        const int anchor = m * kP2PStride + tid;
+        if (tid < kP2PStride && anchor < g.n_anchor) {
+          const int pl = (int)__umulhi((uint32_t)anchor, wt_magic), tl = anchor - pl * Wt;
+          if (tl < g.TBv) {
+            uint32_t h[4], l[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float y0, y1;
+              f2_unpack(f2_fma(o[e], sc2[e], sh2[e]), y0, y1);
+              y0 = fmaxf(y0, kLeakySlope * y0), y1 = fmaxf(y1, kLeakySlope * y1);  // LeakyReLU (slope < 1)
+              split_f16x2(y0, y1, h[e], l[e]);
+            }
+            const uint4 hv = make_uint4(h[0], h[1], h[2], h[3]), lv = make_uint4(l[0], l[1], l[2], l[3]);
+            const int p = g.p0 + pl, t = g.t0 + tl;
+            // home position + circular halo copies (rows p +- P, columns t +- T)
+            const int row2 = (p < 3) ? p + 3 + a.P : ((p >= a.P - 3) ? p + 3 - a.P : -1);
+            const int col2 = (t < 3) ? t + 3 + a.T : ((t >= a.T - 3) ? t + 3 - a.T : -1);
+            const long long q00 = ((base + p + 3) * a.Wd + t + 3) * 8;
+            *reinterpret_cast<uint4*>(a.out_hi + q00) = hv, *reinterpret_cast<uint4*>(a.out_lo + q00) = lv;
             if (col2 >= 0) {
-              const long long q2 = ((base + row2) * a.Wd + col2) * 8;
-              *reinterpret_cast<uint4*>(a.out_hi + q2) = hv, *reinterpret_cast<uint4*>(a.out_lo + q2) = lv;
+              const long long q = ((base + p + 3) * a.Wd + col2) * 8;
+              *reinterpret_cast<uint4*>(a.out_hi + q) = hv, *reinterpret_cast<uint4*>(a.out_lo + q) = lv;
+            }
+            if (row2 >= 0) {
+              const long long q = ((base + row2) * a.Wd + t + 3) * 8;
+              *reinterpret_cast<uint4*>(a.out_hi + q) = hv, *reinterpret_cast<uint4*>(a.out_lo + q) = lv;
+              if (col2 >= 0) {
+                const long long q2 = ((base + row2) * a.Wd + col2) * 8;
+                *reinterpret_cast<uint4*>(a.out_hi + q2) = hv, *reinterpret_cast<uint4*>(a.out_lo + q2) = lv;
+              }
             }
           }
         }
       }
-      asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");  // the exchange buffer is reused by the next block
+      j0 += g.n_mb;
     }
   }
   fence_before_sync();
   __syncthreads();
-  if (warp == 8) tmem_dealloc(tmem, 256);
+  if (warp == 4 * G + 1) tmem_dealloc(tmem, 128 * G);
 }
 
 // ---- pool_semi conv (3x3, stride (3,1), time-circular) + BN + LeakyReLU + octave max pool, from chunk planes ------

@@ -18,6 +18,43 @@
 #include <cstdint>
 
 namespace ake {
+
+// fp32x2 packed arithmetic (sm_100: FMUL2 / FADD2) halves the scale / residual instructions of the hi/lo split
+__device__ __forceinline__ uint64_t f2_pack(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t f2_sub(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+// o[e] += x[e] (four fp32 pairs) where v < 0: one predicate, four predicated FADD2 (a C++ conditional around f2_add costs
+// two extra moves per pair)
+__device__ __forceinline__ void f2_add4_if_neg(uint64_t (&o)[4], uint64_t x0, uint64_t x1, uint64_t x2, uint64_t x3, int v) {
+  asm("{\n\t.reg .pred q;\n\tsetp.lt.s32 q, %8, 0;\n\t@q add.rn.f32x2 %0, %0, %4;\n\t@q add.rn.f32x2 %1, %1, %5;\n\t"
+      "@q add.rn.f32x2 %2, %2, %6;\n\t@q add.rn.f32x2 %3, %3, %7;\n\t}\n"
+      : "+l"(o[0]), "+l"(o[1]), "+l"(o[2]), "+l"(o[3])
+      : "l"(x0), "l"(x1), "l"(x2), "l"(x3), "r"(v));
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+
 namespace umma {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -32,6 +69,18 @@ __device__ __forceinline__ uint64_t make_desc(uint64_t hi, uint32_t smem_addr) {
 // Instruction descriptor, kind::f16 with fp16 inputs (format 0) and fp32 accumulation, K-major A and B, M = 128.
 __host__ __device__ constexpr uint32_t idesc_f16(int N, int M = 128) {
   return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---- single-lane issue ---------------------------------------------------------------------------
+// tcgen05.mma / commit take their operands from the uniform datapath.  Under `if (lane == 0)` the compiler cannot prove
+// uniformity and wraps every such instruction in an ELECT / BRA.U.ANY "waterfall" with R2UR moves (~60-100 cycles per MMA
+// from one thread: slower than the MMA itself).  Keep the issuing warp converged instead: a warp index the compiler knows
+// to be uniform (shuffle broadcast) for the role branch, and elect.sync for the one lane that issues.
+__device__ __forceinline__ int uniform_warp_idx() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+  return pred != 0;
 }
 
 // ---- MMA issue / completion ---------------------------------------------------------------------
@@ -71,6 +120,22 @@ __device__ __forceinline__ void tmem_ld16(uint32_t addr, float (&v)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+// Asynchronous form: issue the load, then tmem_ld_wait16() on the same registers before reading them (the wait names the
+// registers as in/out operands so that neither nvcc nor ptxas can move a consumer above it).
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t addr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(addr));
+}
+__device__ __forceinline__ void tmem_ld_wait16(uint32_t (&r)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]),
+                 "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
 }
 __device__ __forceinline__ void tmem_ld8(uint32_t addr, float (&v)[8]) {
   uint32_t r[8];
