@@ -331,7 +331,7 @@ __global__ void __launch_bounds__(kCasThreads, 2) cascade_umma_kernel(const Casc
   float* stage = reinterpret_cast<float*>(img + kCasImgBytes);
   float* tbuf2 = reinterpret_cast<float*>(img + kCasImgBytes + kCasStageBytes);
   float* tbuf1 = reinterpret_cast<float*>(p0h);  // free between MMA1 of a tile and the conversion of the next one
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
   const int row = 32 * (warp & 3) + lane;  // accumulator lane = row of 32 outputs
   const int hf = warp >> 2;                // which 16 of them this thread handles
   const bool two = a.n_levels == 2;
@@ -469,12 +469,13 @@ __global__ void __launch_bounds__(kCasThreads, 2) cascade_umma_kernel(const Casc
     __syncthreads();
     const int nxt = next_tile(tile + gridDim.x);
     if (nxt < a.n_tiles) start_stage(nxt);
-    if (tid == 0) {
+    if (warp == 0) {  // converged warp, one elected lane issues (see umma.cuh: single-lane issue)
       mbar_wait(&img_bar, 0);
       fence_after_sync();
-      issue_level(tmem, smem_u32(p0h), smem_u32(p0l), kCasLBO0, &bar1);
+      if (elect_one()) issue_level(tmem, smem_u32(p0h), smem_u32(p0l), kCasLBO0, &bar1);
+      __syncwarp();
     }
-  } else if (tid == 0) {
+  } else if (warp == 0) {
     mbar_wait(&img_bar, 0);  // never leave with a bulk copy in flight
   }
   while (tile < a.n_tiles) {
@@ -518,9 +519,10 @@ __global__ void __launch_bounds__(kCasThreads, 2) cascade_umma_kernel(const Casc
     fence_before_sync();
     fence_proxy_async();
     __syncthreads();
-    if (two && tid == 0) {
+    if (two && warp == 0) {
       fence_after_sync();
-      issue_level(tmem + 64, smem_u32(p1h), smem_u32(p1l), kCasLBO1, &bar2);
+      if (elect_one()) issue_level(tmem + 64, smem_u32(p1h), smem_u32(p1l), kCasLBO1, &bar2);
+      __syncwarp();
     }
     {
       // rows 1..126 are owned (0 and 127 are the halo the next level needs): 1008 float4s, 8 per row
@@ -542,9 +544,10 @@ __global__ void __launch_bounds__(kCasThreads, 2) cascade_umma_kernel(const Casc
     if (nxt < a.n_tiles) {
       const int nxt2 = next_tile(nxt + gridDim.x);
       if (nxt2 < a.n_tiles) start_stage(nxt2);  // every thread has consumed the stage
-      if (tid == 0) {
+      if (warp == 0) {
         fence_after_sync();
-        issue_level(tmem, smem_u32(p0h), smem_u32(p0l), kCasLBO0, &bar1);
+        if (elect_one()) issue_level(tmem, smem_u32(p0h), smem_u32(p0l), kCasLBO0, &bar1);
+        __syncwarp();
       }
     }
     // ---- level p+2 (overlaps MMA1 of the next tile)
@@ -623,7 +626,7 @@ __global__ void __launch_bounds__(160) cqt_bank_umma_kernel(const BankArgs a) {
   __shared__ long long s_g0[128];   // index (into the octave's level array) of the first sample of frame row r
   __shared__ int2 s_valid[128];     // samples [x, y) of that frame exist (the rest is the zero padding of centred frames)
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
   const int octave = blockIdx.y;
   const long long m0 = (long long)blockIdx.x * 128;
   const int n_kb = a.n_fft / kUKB;
@@ -731,8 +734,8 @@ __global__ void __launch_bounds__(160) cqt_bank_umma_kernel(const BankArgs a) {
         }
       }
     }
-  } else if (lane == 0) {
-    // ---------------------------------------------------------------- MMA issuer
+  } else {
+    // ---------------------------------------------------------------- MMA issuer (converged warp, one elected lane issues)
     constexpr uint64_t A_DESC = desc_hi(kBankLBO);
     constexpr uint64_t B_DESC = desc_hi(2 * NPAD * 16);  // chunk stride = 2*NPAD rows x 16 B
     constexpr uint32_t IDESC_WIDE = idesc_f16(2 * NPAD), IDESC_NARROW = idesc_f16(NPAD);
@@ -741,15 +744,18 @@ __global__ void __launch_bounds__(160) cqt_bank_umma_kernel(const BankArgs a) {
       mbar_wait(&full_bar[s], (kb / kUStages) & 1);
       fence_after_sync();
       const uint32_t base = smem_u32(smem + (size_t)s * STAGE);
+      if (elect_one()) {
 #pragma unroll
-      for (int j = 0; j < kUKB / 16; ++j) {
-        const uint64_t bd = make_desc(B_DESC, base + 2 * A_HALF + j * (2 * 2 * NPAD * 16));
-        mma_f16(tmem, make_desc(A_DESC, base + j * 2 * kBankLBO), bd, IDESC_WIDE, (kb | j) ? 1u : 0u);
-        mma_f16(tmem, make_desc(A_DESC, base + A_HALF + j * 2 * kBankLBO), bd, IDESC_NARROW, 1u);
+        for (int j = 0; j < kUKB / 16; ++j) {
+          const uint64_t bd = make_desc(B_DESC, base + 2 * A_HALF + j * (2 * 2 * NPAD * 16));
+          mma_f16(tmem, make_desc(A_DESC, base + j * 2 * kBankLBO), bd, IDESC_WIDE, (kb | j) ? 1u : 0u);
+          mma_f16(tmem, make_desc(A_DESC, base + A_HALF + j * 2 * kBankLBO), bd, IDESC_NARROW, 1u);
+        }
+        commit(&empty_bar[s]);
+        if (kb == n_kb - 1) commit(&done_bar);
       }
-      commit(&empty_bar[s]);
+      __syncwarp();
     }
-    commit(&done_bar);
   }
   fence_before_sync();
   __syncthreads();

@@ -508,7 +508,7 @@ __global__ void __launch_bounds__(192) equiv_umma_kernel(const EquivArgs a) {
   __shared__ uint32_t tmem_slot;
   __shared__ float s_scale[NCO], s_shift[NCO];
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
   const int b = blockIdx.y, t0 = blockIdx.x * a.TB;
   const int TBv = min(a.TB, a.T_out - t0);
   const int Wt = a.TB + 6;
@@ -558,33 +558,35 @@ __global__ void __launch_bounds__(192) equiv_umma_kernel(const EquivArgs a) {
       bulk_g2s(s_hi + (size_t)g * GP + (size_t)r * Wt * 16, a.in_hi + src, row_bytes, &tile_bar);
       bulk_g2s(s_lo + (size_t)g * GP + (size_t)r * Wt * 16, a.in_lo + src, row_bytes, &tile_bar);
     }
-    if (lane == 0) {
-      const int n_it = n_grp * NSTG;
-      for (int it = 0; it < n_it; ++it) {
-        const int s = it % kEqWStages;
-        mbar_wait(&w_empty[s], ((it / kEqWStages) & 1) ^ 1);
+    // the weight stream: converged warp, one elected lane issues (see umma.cuh: single-lane issue)
+    const int n_it = n_grp * NSTG;
+    for (int it = 0; it < n_it; ++it) {
+      const int s = it % kEqWStages;
+      mbar_wait(&w_empty[s], ((it / kEqWStages) & 1) ^ 1);
+      if (elect_one()) {
         mbar_arrive_expect_tx(&w_full[s], kEqStageBytes);
         bulk_g2s(s_w + (size_t)s * kEqStageBytes, reinterpret_cast<const uint8_t*>(a.wimg) + (size_t)(it % NSTG) * kEqStageBytes,
                  kEqStageBytes, &w_full[s]);
       }
+      __syncwarp();
     }
   } else if (warp == 5) {
-    // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      mbar_wait(&tile_bar, 0);
-      const uint64_t A_DESC = desc_hi(GP);  // chunk 1 = the other channel group of the same position
-      constexpr uint64_t B_DESC = desc_hi(N1 * 16);
-      constexpr uint32_t IDESC1 = idesc_f16(N1), IDESC2 = idesc_f16(N2);
-      const uint32_t hi0 = smem_u32(s_hi), lo0 = smem_u32(s_lo), w0 = smem_u32(s_w);
-      int it = 0;
-      for (int grp = 0; grp < n_grp; ++grp) {
-        const int gb = grp & 1;
-        mbar_wait(&acc_empty[gb], ((grp >> 1) & 1) ^ 1);
+    // ------------------------------------------------------------ MMA issuer (converged warp, one elected lane issues)
+    mbar_wait(&tile_bar, 0);
+    const uint64_t A_DESC = desc_hi(GP);  // chunk 1 = the other channel group of the same position
+    constexpr uint64_t B_DESC = desc_hi(N1 * 16);
+    constexpr uint32_t IDESC1 = idesc_f16(N1), IDESC2 = idesc_f16(N2);
+    const uint32_t hi0 = smem_u32(s_hi), lo0 = smem_u32(s_lo), w0 = smem_u32(s_w);
+    int it = 0;
+    for (int grp = 0; grp < n_grp; ++grp) {
+      const int gb = grp & 1;
+      mbar_wait(&acc_empty[gb], ((grp >> 1) & 1) ^ 1);
+      fence_after_sync();
+      for (int stg = 0; stg < NSTG; ++stg, ++it) {
+        const int s = it % kEqWStages;
+        mbar_wait(&w_full[s], (it / kEqWStages) & 1);
         fence_after_sync();
-        for (int stg = 0; stg < NSTG; ++stg, ++it) {
-          const int s = it % kEqWStages;
-          mbar_wait(&w_full[s], (it / kEqWStages) & 1);
-          fence_after_sync();
+        if (elect_one()) {
 #pragma unroll
           for (int u = 0; u < SPS; ++u) {
             const int j = stg * SPS + u;
@@ -602,8 +604,9 @@ __global__ void __launch_bounds__(192) equiv_umma_kernel(const EquivArgs a) {
             }
           }
           commit(&w_empty[s]);
+          if (stg == NSTG - 1) commit(&acc_full[gb]);
         }
-        commit(&acc_full[gb]);
+        __syncwarp();
       }
     }
   } else {
@@ -786,7 +789,7 @@ __global__ void __launch_bounds__(160) head_tail_umma_kernel(const HeadUmmaArgs 
   __shared__ __align__(8) uint64_t tile_bar, acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_slot;
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
   const int h = blockIdx.y, b = blockIdx.z, t0 = blockIdx.x * a.TB;
   const int KH = a.KH[h], R = a.R[h], rows_out = a.rows_out[h];
   const int TBv = min(a.TB, a.Tf - t0);
@@ -838,17 +841,19 @@ __global__ void __launch_bounds__(160) head_tail_umma_kernel(const HeadUmmaArgs 
       bulk_g2s(s_hi + (size_t)g * GP + (size_t)r * Wt * 16, a.in_hi[h] + src, row_bytes, &tile_bar);
       bulk_g2s(s_lo + (size_t)g * GP + (size_t)r * Wt * 16, a.in_lo[h] + src, row_bytes, &tile_bar);
     }
-    if (lane == 0) {
-      mbar_wait(&tile_bar, 0);
-      const uint64_t A_DESC = desc_hi(GP);          // chunk 1 = the next channel group of the same position
-      constexpr uint64_t B_DESC = desc_hi(16 * 16);  // chunk stride: 16 rows x 16 B
-      constexpr uint32_t IDESC = idesc_f16(16);
-      const uint32_t hi0 = smem_u32(s_hi), lo0 = smem_u32(s_lo), w0 = smem_u32(s_w);
-      for (int m = 0; m < n_mb; ++m) {
-        const int buf = m & 1;
-        mbar_wait(&acc_empty[buf], ((m >> 1) & 1) ^ 1);
-        fence_after_sync();
-        const uint32_t d = tmem + buf * 16;
+    // converged warp, one elected lane issues (see umma.cuh: single-lane issue)
+    __syncwarp();
+    mbar_wait(&tile_bar, 0);
+    const uint64_t A_DESC = desc_hi(GP);          // chunk 1 = the next channel group of the same position
+    constexpr uint64_t B_DESC = desc_hi(16 * 16);  // chunk stride: 16 rows x 16 B
+    constexpr uint32_t IDESC = idesc_f16(16);
+    const uint32_t hi0 = smem_u32(s_hi), lo0 = smem_u32(s_lo), w0 = smem_u32(s_w);
+    for (int m = 0; m < n_mb; ++m) {
+      const int buf = m & 1;
+      mbar_wait(&acc_empty[buf], ((m >> 1) & 1) ^ 1);
+      fence_after_sync();
+      const uint32_t d = tmem + buf * 16;
+      if (elect_one()) {
         for (int dp = 0; dp < KH; ++dp) {
 #pragma unroll
           for (int kh = 0; kh < 2; ++kh) {
@@ -860,6 +865,7 @@ __global__ void __launch_bounds__(160) head_tail_umma_kernel(const HeadUmmaArgs 
         }
         commit(&acc_full[buf]);
       }
+      __syncwarp();
     }
   } else {
     // ------------------------------------------------------------ epilogue: thread = TMEM lane = anchor row
