@@ -126,7 +126,7 @@ struct ake_pcn {
   bool umma = false;
   __half* d_wimg = nullptr;         // one kP2PWBytes image per Pitch2Pitch conv, in conv-id order of `umma_convs`
   std::vector<int> umma_convs;
-  __half* d_wimg_pc = nullptr;      // equivariant convs of the layer-1 PitchClass2PitchClass stack (98,304 B each)
+  __half* d_wimg_pc = nullptr;      // equivariant convs of the layer-1 PitchClass2PitchClass stack (kPcWBytes each)
   __half* d_wimg_heads = nullptr;   // first conv of the tonic and key heads, fused along N (344,064 B)
   float* d_ss_heads = nullptr;      // [scale 64 | shift 64] of that fused conv (tonic channels first)
   __half* d_wimg_genre = nullptr;   // first conv of the genre head (1 x 7, 16 -> 32): one 16 KB stage
@@ -558,33 +558,33 @@ void Fwd::run(const float* mel, float* key_out, float* tonic_out, float* genre_o
           for (int i = 1; i < 3; ++i)
             for (int j = 0; j < 2; ++j) AKE_CUDA(cudaMemsetAsync(e[i][j], 0, sizeof(__half) * eq_halves, st));
           const int n_tt = cdiv(Tn, 32), TBe = (cdiv(Tn, n_tt) + 1) / 2 * 2;
-          const size_t smem_e = equiv_smem_bytes(TBe + 6);
+          const size_t smem_e = pc2pc_smem_bytes(TBe + 6);
           static size_t conf0 = 0, conf1 = 0;
           if (smem_e > conf0) {
-            AKE_CUDA(cudaFuncSetAttribute(equiv_umma_kernel<16, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e));
+            AKE_CUDA(cudaFuncSetAttribute(pc2pc_umma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e));
             conf0 = smem_e;
           }
           if (smem_e > conf1) {
-            AKE_CUDA(cudaFuncSetAttribute(equiv_umma_kernel<16, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e));
+            AKE_CUDA(cudaFuncSetAttribute(pc2pc_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e));
             conf1 = smem_e;
           }
-          constexpr size_t kPcImg = 48 * 2048;
           int ce = 0;
           for (size_t i = 0; i < lp.pc2pc.size(); ++i) {
             const Conv& c = p->convs[lp.pc2pc[i]];
             const bool last = i + 1 == lp.pc2pc.size();
             const int nxt = last ? ce : (ce == 1 ? 2 : 1);
-            EquivArgs ea{};
+            Pc2PcArgs ea{};
             ea.in_hi = e[ce][0], ea.in_lo = e[ce][1], ea.Wd_in = Wd, ea.T_out = Tn, ea.TB = TBe, ea.n_ttiles = cdiv(Tn, TBe);
-            ea.wimg = reinterpret_cast<const __half*>(reinterpret_cast<const uint8_t*>(p->d_wimg_pc) + i * kPcImg);
+            ea.n_tiles = ea.n_ttiles * B;
+            ea.wimg = reinterpret_cast<const __half*>(reinterpret_cast<const uint8_t*>(p->d_wimg_pc) + i * kPcWBytes);
             ea.scale = scale_of(c, false), ea.shift = shift_of(c, false);
-            dim3 grid(ea.n_ttiles, B);
+            const int grid = std::min(ea.n_tiles, sm_count());  // persistent: one CTA per SM
             if (!last) {
               ea.out_hi = e[nxt][0], ea.out_lo = e[nxt][1], ea.Wd_out = Wd, ea.col_off = 3;
-              equiv_umma_kernel<16, 2, 0><<<grid, 192, smem_e, st>>>(ea);
+              pc2pc_umma_kernel<0><<<grid, kPcThreads, smem_e, st>>>(ea);
             } else {
               ea.out_hi = umma_pc_hi, ea.out_lo = umma_pc_lo, ea.Wd_out = Th, ea.col_off = 0, ea.out_f32 = pooled.p;
-              equiv_umma_kernel<16, 2, 1><<<grid, 192, smem_e, st>>>(ea);
+              pc2pc_umma_kernel<1><<<grid, kPcThreads, smem_e, st>>>(ea);
             }
             AKE_LAUNCHED();
             ce = nxt;
@@ -812,12 +812,11 @@ static void upload_params(ake_pcn* p, const float* flat_dev, int64_t n, cudaStre
       AKE_LAUNCHED();
     }
     const std::vector<int>& pcs = p->layers[1].pc2pc;
-    constexpr size_t kPcImg = 48 * 2048;
-    if (!p->d_wimg_pc) AKE_CUDA(cudaMalloc(&p->d_wimg_pc, kPcImg * pcs.size()));
+    if (!p->d_wimg_pc) AKE_CUDA(cudaMalloc(&p->d_wimg_pc, (size_t)kPcWBytes * pcs.size()));
     for (size_t i = 0; i < pcs.size(); ++i) {
       const Conv& c = p->convs[pcs[i]];
-      equiv_pack_weights_kernel<<<96, 256, 0, st>>>(p->d_params + c.w_off, p->d_params + c.w_off, 16, 16, c.Cin, 2,
-                                                     reinterpret_cast<__half*>(reinterpret_cast<uint8_t*>(p->d_wimg_pc) + i * kPcImg));
+      pc2pc_pack_weights_kernel<<<84, 256, 0, st>>>(p->d_params + c.w_off, c.Cout, c.Cin,
+                                                     reinterpret_cast<__half*>(reinterpret_cast<uint8_t*>(p->d_wimg_pc) + i * kPcWBytes));
       AKE_LAUNCHED();
     }
     if (p->umma_heads) {

@@ -744,6 +744,256 @@ __global__ void __launch_bounds__(192) equiv_umma_kernel(const EquivArgs a) {
   if (warp == 4) tmem_dealloc(tmem, 256);
 }
 
+// ---- PitchClass2PitchClass stack (16 -> 16 channels, models.py:191-197) as a persistent 7-phase shift-GEMM ---------------
+// Same scheme as p2p_umma_kernel, with the row taps running over the 23 wrapped pitch-class rows:
+//   out[a] = sum_{dp<12} sum_{f<7} X[a + dp*Wt + f] . W[dp][f]       (a = c*Wt + tl, 16 -> 16 channels, "same" zero padding in time)
+//   MMA 1 (per dp): A = x_hi (K = 16: the two channel groups, LBO = plane pitch), B = [W_hi | W_lo], N = 224 = 2 x (7 phases x 16 co)
+//   MMA 2 (per dp): A = x_lo, B = W_hi, N = 112 (accumulates on the W_hi columns)
+// i.e. 12 x (112 + 60) = 2064 MMA cycles per 122 anchors, against 48 x (48 + 40) = 4224 per 127 for the two-phase form, and
+// the whole weight image (86 KB) stays resident in shared memory instead of streaming through a ring once per CTA.
+// EPI 0: BN + LeakyReLU -> chunk planes with wrap rows (next conv);  EPI 1: + MaxPool2d((1,2)) (models.py:349-350, 396)
+// -> chunk planes without halos + fp32 (B,16,12,T/2).
+constexpr int kPcStride = 122;
+constexpr int kPcGroups = 2;        // epilogue groups of 4 warps = accumulator buffers of 224 TMEM columns
+constexpr int kPcThreads = 32 * (4 * kPcGroups + 2);
+constexpr uint32_t kPcWBytes = 12 * 2 * 224 * 16;
+constexpr uint32_t kPcPubBytes = 3 * 21 * 64;  // per epilogue group: [warp 1..3][phase f = 1..6: f lanes][co 16] floats
+
+// [dp 12][chunk g 2][n 224][ci 8]: n < 112: W_hi of (phase f = n / 16, co = n % 16); n >= 112: W_lo
+__global__ void pc2pc_pack_weights_kernel(const float* __restrict__ w, int Cout, int Cin, __half* __restrict__ img) {
+  const int n_items = 12 * 2 * 112 * 8;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_items; i += gridDim.x * blockDim.x) {
+    const int e = i % 8, n = (i / 8) % 112, g = (i / (8 * 112)) % 2, dp = i / (16 * 112);
+    const int f = n / 16, co = n % 16, ci = g * 8 + e;
+    float v = 0.f;
+    if (ci < Cin && co < Cout) v = w[(((long long)co * Cin + ci) * 12 + dp) * 7 + f] * kWScale;
+    const __half hi = __float2half_rn(v);
+    const __half lo = __float2half_rn(v - __half2float(hi));
+    img[((dp * 2 + g) * 224 + n) * 8 + e] = hi;
+    img[((dp * 2 + g) * 224 + 112 + n) * 8 + e] = lo;
+  }
+}
+
+struct Pc2PcArgs {
+  const __half* in_hi;
+  const __half* in_lo;   // [B][2][23][Wd_in][8]: zero halo columns (3 each side), wrap rows 12..22
+  int Wd_in, T_out, TB, n_ttiles, n_tiles;
+  const __half* wimg;    // pc2pc_pack_weights_kernel image (kPcWBytes)
+  const float* scale;    // 16: eval-mode BN scale (the 1/kWScale factor is applied in the kernel)
+  const float* shift;
+  __half* out_hi;
+  __half* out_lo;        // EPI 0: [B][2][23][Wd_out][8] written at column t + col_off; EPI 1: same with t / 2
+  int Wd_out, col_off;
+  float* out_f32;        // EPI 1: (B,16,12,T_out/2)
+};
+
+__host__ __device__ inline uint32_t pc2pc_plane_positions(int Wt) { return (uint32_t)(23 * Wt + 136); }
+__host__ __device__ inline size_t pc2pc_smem_bytes(int Wt) {
+  return (size_t)2 * 4 * pc2pc_plane_positions(Wt) * 16 + kPcWBytes + kPcGroups * kPcPubBytes;
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(kPcThreads, 1) pc2pc_umma_kernel(const Pc2PcArgs a) {
+  using namespace umma;
+  constexpr int G = kPcGroups;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t w_bar, full_bar[2], empty_bar[2], acc_full[G], acc_empty[G];
+  __shared__ uint32_t tmem_slot;
+  __shared__ float s_scale[16], s_shift[16];
+
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
+  const int Wt = a.TB + 6;
+  const uint32_t plane = pc2pc_plane_positions(Wt) * 16;  // one (hi | lo, channel group) plane; a tile buffer holds [hi g0][hi g1][lo g0][lo g1]
+  uint8_t* s_w = smem + 8 * plane;
+  uint8_t* s_pub = s_w + kPcWBytes;
+  const int n_anchor = 12 * Wt;
+  const int n_mb = (n_anchor + kPcStride - 1) / kPcStride;
+
+  if (warp == 4 * G + 1) tmem_alloc(&tmem_slot, 512);
+  if (threadIdx.x == 0) {
+    mbar_init(&w_bar, 1);
+    for (int i = 0; i < 2; ++i) mbar_init(&full_bar[i], 1), mbar_init(&empty_bar[i], 1);
+    for (int i = 0; i < G; ++i) mbar_init(&acc_full[i], 1), mbar_init(&acc_empty[i], 128);
+    mbar_init_fence();
+  }
+  if (threadIdx.x < 16) s_scale[threadIdx.x] = a.scale[threadIdx.x] * (1.f / kWScale), s_shift[threadIdx.x] = a.shift[threadIdx.x];
+  // positions the bulk copies never write only feed discarded anchors; give them finite values once
+  for (uint32_t i = threadIdx.x; i < 8 * plane / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+
+  if (warp == 4 * G) {
+    // ------------------------------------------------------------ loader
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&w_bar, kPcWBytes);
+      bulk_g2s(s_w, a.wimg, kPcWBytes, &w_bar);
+    }
+    int k = 0;
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++k) {
+      const int s = k & 1;
+      const int b = tile / a.n_ttiles, t0 = (tile - b * a.n_ttiles) * a.TB;
+      const int cols_in = min(Wt, a.Wd_in - t0);
+      const uint32_t row_bytes = (uint32_t)cols_in * 16;
+      mbar_wait(&empty_bar[s], ((k >> 1) & 1) ^ 1);
+      if (lane == 0) mbar_arrive_expect_tx(&full_bar[s], 92u * row_bytes);
+      __syncwarp();
+      uint8_t* dst = smem + (size_t)s * 4 * plane;
+      for (int idx = lane; idx < 46; idx += 32) {
+        const int g = idx / 23, r = idx - g * 23;
+        const long long src = ((((long long)b * 2 + g) * 23 + r) * a.Wd_in + t0) * 8;
+        bulk_g2s(dst + (size_t)g * plane + (size_t)r * Wt * 16, a.in_hi + src, row_bytes, &full_bar[s]);
+        bulk_g2s(dst + (size_t)(2 + g) * plane + (size_t)r * Wt * 16, a.in_lo + src, row_bytes, &full_bar[s]);
+      }
+    }
+  } else if (warp == 4 * G + 1) {
+    // ------------------------------------------------------------ MMA issuer (converged warp, one elected lane issues)
+    const uint64_t A_DESC = desc_hi(plane);         // chunk 1 = the other channel group of the same position
+    constexpr uint64_t B_DESC = desc_hi(224 * 16);  // chunk stride: 224 rows x 16 B
+    constexpr uint32_t IDESC_WIDE = idesc_f16(224), IDESC_NARROW = idesc_f16(112);
+    const uint32_t w0 = smem_u32(s_w);
+    mbar_wait(&w_bar, 0);
+    int k = 0;
+    uint32_t j = 0;
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++k) {
+      const int s = k & 1;
+      const uint32_t hi0 = smem_u32(smem + (size_t)s * 4 * plane), lo0 = hi0 + 2 * plane;
+      mbar_wait(&full_bar[s], (k >> 1) & 1);
+      for (int m = 0; m < n_mb; ++m, ++j) {
+        const uint32_t buf = j % G;
+        mbar_wait(&acc_empty[buf], ((j / G) & 1) ^ 1);
+        fence_after_sync();
+        const uint32_t d = tmem + buf * 256;
+        const uint32_t a_off = (uint32_t)(m * kPcStride) * 16;
+        if (elect_one()) {
+#pragma unroll
+          for (int dp = 0; dp < 12; ++dp) {
+            const uint32_t off = a_off + (uint32_t)(dp * Wt) * 16;
+            const uint64_t bd = make_desc(B_DESC, w0 + dp * (2 * 224 * 16));
+            mma_f16(d, make_desc(A_DESC, hi0 + off), bd, IDESC_WIDE, dp ? 1u : 0u);
+            mma_f16(d, make_desc(A_DESC, lo0 + off), bd, IDESC_NARROW, 1u);
+          }
+          commit(&acc_full[buf]);
+          if (m == n_mb - 1) commit(&empty_bar[s]);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue: thread = TMEM lane = anchor row
+    const int grp = warp >> 2, wq = warp & 3, tid = threadIdx.x & 127;
+    const uint32_t acc = tmem + ((uint32_t)(wq * 32) << 16) + grp * 256;
+    float4* pub = reinterpret_cast<float4*>(s_pub + grp * kPcPubBytes);
+    const uint32_t wt_magic = 0xFFFFFFFFu / (uint32_t)Wt + 1;
+    uint32_t n_done = 0;
+    uint32_t j = grp, j0 = 0;
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+      const int b = tile / a.n_ttiles, t0 = (tile - b * a.n_ttiles) * a.TB;
+      const int TBv = min(a.TB, a.T_out - t0);
+      for (; j < j0 + n_mb; j += G, ++n_done) {
+        const int m = (int)(j - j0);
+        mbar_wait(&acc_full[grp], n_done & 1);
+        fence_after_sync();
+        // phase f = time tap f: out[a] = sum_f D_f[a + f]; D_f = columns [16 f, 16 f + 16) (x . W_hi) + [112 + 16 f, ..) (x_hi . W_lo)
+        uint64_t o[8];
+#pragma unroll
+        for (int f = 0; f < 7; ++f) {
+          uint32_t vh[16], vl[16];
+          tmem_ld16_issue(acc + 16 * f, vh);
+          tmem_ld16_issue(acc + 112 + 16 * f, vl);
+          tmem_ld_wait16(vh);
+          tmem_ld_wait16(vl);
+          uint64_t u[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            u[e] = f2_add(f2_pack(__uint_as_float(vh[2 * e]), __uint_as_float(vh[2 * e + 1])),
+                          f2_pack(__uint_as_float(vl[2 * e]), __uint_as_float(vl[2 * e + 1])));
+          if (f == 0) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = u[e];
+          } else {
+            float x[16];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f2_unpack(u[e], x[2 * e], x[2 * e + 1]);
+            if (wq > 0 && lane < f) {
+              float4* dst = pub + ((wq - 1) * 21 + f * (f - 1) / 2 + lane) * 4;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) dst[q] = make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+            }
+#pragma unroll
+            for (int c = 0; c < 16; ++c) x[c] = __shfl_down_sync(0xffffffffu, x[c], f);
+            const float mk = (lane + f < 32) ? 1.f : 0.f;  // see p2p_umma_kernel: masked FMA = predicated add
+            const uint64_t mk2 = f2_pack(mk, mk);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = f2_fma(f2_pack(x[2 * e], x[2 * e + 1]), mk2, o[e]);
+          }
+        }
+        fence_before_sync();
+        mbar_arrive(&acc_empty[grp]);
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+        if (wq < 3 && lane >= 26) {
+#pragma unroll
+          for (int f = 1; f < 7; ++f) {
+            const bool take = lane + f >= 32;
+            const float4* src = pub + (wq * 21 + f * (f - 1) / 2 + (take ? lane + f - 32 : 0)) * 4;
+            const float mk = take ? 1.f : 0.f;
+            const uint64_t mk2 = f2_pack(mk, mk);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float4 x = src[q];
+              o[2 * q] = f2_fma(f2_pack(x.x, x.y), mk2, o[2 * q]), o[2 * q + 1] = f2_fma(f2_pack(x.z, x.w), mk2, o[2 * q + 1]);
+            }
+          }
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");  // the hand-over buffer is reused by the next block
+        float y[16];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          f2_unpack(f2_fma(o[e], f2_pack(s_scale[2 * e], s_scale[2 * e + 1]), f2_pack(s_shift[2 * e], s_shift[2 * e + 1])), y[2 * e], y[2 * e + 1]);
+          y[2 * e] = fmaxf(y[2 * e], kLeakySlope * y[2 * e]), y[2 * e + 1] = fmaxf(y[2 * e + 1], kLeakySlope * y[2 * e + 1]);
+        }
+        const int anchor = m * kPcStride + tid;
+        const int c = (int)__umulhi((uint32_t)anchor, wt_magic), tl = anchor - c * Wt;
+        const int t = t0 + tl;
+        bool valid = tid < kPcStride && anchor < n_anchor && tl < TBv;
+        int col = t + a.col_off;
+        if constexpr (EPI == 1) {
+          // fused MaxPool2d((1,2)): frames (2u, 2u+1) are neighbouring anchors of one warp (t0, TB, Wt and the block stride are even)
+#pragma unroll
+          for (int i = 0; i < 16; ++i) y[i] = fmaxf(y[i], __shfl_down_sync(0xffffffffu, y[i], 1));
+          const int Th = a.T_out / 2;
+          valid = valid && (t & 1) == 0 && (t >> 1) < Th;
+          col = (t >> 1) + a.col_off;
+          if (valid) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) a.out_f32[(((long long)b * 16 + i) * 12 + c) * Th + (t >> 1)] = y[i];
+          }
+        }
+        if (valid) {
+          float g0[8], g1[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) g0[e] = y[e], g1[e] = y[8 + e];
+          const long long q0 = ((((long long)b * 2 + 0) * 23 + c) * a.Wd_out + col) * 8;
+          const long long q1 = ((((long long)b * 2 + 1) * 23 + c) * a.Wd_out + col) * 8;
+          store_split8(a.out_hi + q0, a.out_lo + q0, g0);
+          store_split8(a.out_hi + q1, a.out_lo + q1, g1);
+          if (c < 11) {  // wrap rows 12..22 = rows 0..10 (models.py:27-28)
+            const long long wr = (long long)12 * a.Wd_out * 8;
+            store_split8(a.out_hi + q0 + wr, a.out_lo + q0 + wr, g0);
+            store_split8(a.out_hi + q1 + wr, a.out_lo + q1 + wr, g1);
+          }
+        }
+      }
+      j0 += n_mb;
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 4 * G + 1) tmem_dealloc(tmem, 512);
+}
+
 // ---- last convolution of the classifier heads on tensor cores (models.py:716-733: 32 -> 1 channel, valid in time) -----
 //   out[c, t] = bias + sum_{ci<32, dp<KH, dt<7} W[ci, dp, dt] x[ci, c + dp, t + dt]     (rows wrap for tonic / key: 23-row planes)
 // One output channel would leave the MMA's N idle, so the 7 time taps are the N-phases:
