@@ -251,8 +251,7 @@ static int frames_for(const ake_cqt* p, long long n) {
 // row are the 8 planes (LBO = plane pitch) and chunks 8..15 the same planes one row further (start address + 16 B).
 // One CTA tile fuses TWO octave steps: 129 input rows -> 128 rows of level p+1 (4096 samples, kept in shared memory as
 // the next operand and written to global memory) -> 63 rows of level p+2 (2016 samples).  Each tile recomputes a halo of
-// 32 + 2*32 input samples per side (2.4 %) instead of exchanging state with its neighbours.  Persistent CTAs, 2 per SM; the next tile's
-// span is landed in shared memory by cp.async while the current tile runs its MMAs and epilogues.
+// 32 + 2*32 input samples per side (2.4 %) instead of exchanging state with its neighbours.
 constexpr int kCasRows2 = 63;                       // level p+2 rows (of 32 outputs) per tile
 constexpr int kCasOwn2 = kCasRows2 * 32;            // 2016 level p+2 outputs owned by a tile
 constexpr int kCasOwn1 = 2 * kCasOwn2;              // 4032 level p+1 outputs owned by a tile (rows 1..126 of 128)
@@ -260,7 +259,6 @@ constexpr int kCasP0Rows = 129, kCasP1Rows = 65;    // plane rows (16 B each) of
 constexpr uint32_t kCasLBO0 = kCasP0Rows * 16, kCasLBO1 = kCasP1Rows * 16;  // odd multiples of 16 B: conflict-free scatter
 constexpr uint32_t kCasP0Bytes = 8 * kCasLBO0, kCasP1Bytes = 8 * kCasLBO1;
 constexpr uint32_t kCasImgBytes = 16 * 64 * 16;     // Toeplitz image: [chunk 16][n 64 = Hh 32 | Hl 32][8 halves]
-constexpr uint32_t kCasSmem = 2 * kCasP1Bytes + 2 * kCasP0Bytes + kCasImgBytes;
 
 struct CascadeArgs {
   const float* in;      // level p, clip b at in + b * in_stride
@@ -273,6 +271,7 @@ struct CascadeArgs {
   long long n_uniform;
   int level_in, n_levels, tiles_per_clip, n_tiles;
   const __half* img;
+  int sparse_hop, sparse_nfft;  // > 0: level p+1 is only read by the filter bank (hop, n_fft at that level): store just those rows
 };
 
 // (a, b) -> fp16 pairs hi, lo with a ~= hi + lo
@@ -300,85 +299,65 @@ __device__ __forceinline__ void cas_store_split8(uint8_t* hi_dst, uint8_t* lo_ds
   *reinterpret_cast<uint4*>(lo_dst) = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
-constexpr int kCasThreads = 256;  // warps w and w+4 share accumulator lanes 32 (w % 4) ..: each takes 16 of a row's 32 outputs
+// Warp roles of the persistent CTA (one per SM); every role walks the same tile sequence and hands over through mbarriers:
+//   warps 0-7   epilogue 1, two groups of four warps taking alternate tiles: level p+1 accumulators -> fp16 hi/lo planes
+//               (operand of the level p+2 MMAs) and, through a transposition buffer, row-contiguous fp32 stores (only the
+//               rows the filter bank reads when `sparse_hop` > 0)
+//   warps 8-9   epilogue 2: level p+2 accumulators (63 rows) -> fp32 stores
+//   warps 10-17 converter: landed fp32 span -> fp16 hi/lo transposed chunk planes (level-p operand), double buffered
+//   warp 18     loader: one bulk async copy per tile span into a two-stage ring
+//   warp 19     MMA issuer (converged, elect.sync): MMA1(i+2) is issued as soon as epilogue 1 has drained accumulator i,
+//               MMA2(i) as soon as its operand planes exist, so the tensor pipe never waits for a whole epilogue
+constexpr int kCasThreads = 640;
+constexpr int kCasConvThreads = 256;
 constexpr int kCasChunks = kCasP0Rows * 8;                 // 1032 chunks of 8 samples per tile span
 constexpr int kCasSpan = kCasChunks * 8;                   // 8256 input samples per tile
-constexpr int kCasPer = (kCasChunks + kCasThreads - 1) / kCasThreads;  // chunks per thread (the last round holds 8)
-constexpr int kCasPer4 = (2 * kCasChunks + kCasThreads - 1) / kCasThreads;  // float4s per thread
-constexpr uint32_t kCasStageBytes = kCasSpan * 4;          // fp32 landing buffer of the next tile's span (bulk async copy)
+constexpr int kCasPer4 = (2 * kCasChunks + kCasConvThreads - 1) / kCasConvThreads;  // float4s per converter thread
+constexpr uint32_t kCasStageBytes = kCasSpan * 4;          // fp32 landing buffer of one tile span (bulk async copy)
 constexpr int kCasTPitch = 36;                             // floats per row of the store-transposition buffers (144 B: conflict-free)
-constexpr uint32_t kCasT2Bytes = kCasRows2 * kCasTPitch * 4;  // level p+2 outputs on their way to coalesced global stores
-constexpr uint32_t kCasSmemTotal = kCasSmem + kCasStageBytes + kCasT2Bytes;
-static_assert(128 * kCasTPitch * 4 <= 2 * kCasP0Bytes, "the level p+1 transposition buffer aliases the level-p planes");
+constexpr uint32_t kCasT1Bytes = 128 * kCasTPitch * 4;     // level p+1 outputs on their way to coalesced global stores
+constexpr uint32_t kCasT2Bytes = 64 * kCasTPitch * 4;      // level p+2
+constexpr uint32_t kCasSmemTotal = 2 * 2 * kCasP1Bytes + 2 * 2 * kCasP0Bytes + kCasImgBytes + 2 * kCasStageBytes + 2 * kCasT1Bytes + kCasT2Bytes;
 
-// Software pipeline of one persistent CTA (two per SM), tile i, next tile j:
-//   wait MMA1(i) -> epilogue 1(i): level p+1 to global memory and, as fp16 hi/lo planes, to shared memory
-//   issue MMA2(i)                     | meanwhile: convert the landed span of tile j into the level-p planes
-//   issue MMA1(j), start the bulk copy of the tile after j | meanwhile: wait MMA2(i) -> epilogue 2(i): level p+2 to global memory
-// Levels 1 and 2 accumulate in separate TMEM columns so MMA1(j) can overlap epilogue 2(i).
-__global__ void __launch_bounds__(kCasThreads, 2) cascade_umma_kernel(const CascadeArgs a) {
+__global__ void __launch_bounds__(kCasThreads, 1) cascade_umma_kernel(const CascadeArgs a) {
   using namespace umma;
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ __align__(8) uint64_t img_bar, bar1, bar2, stage_bar;
+  __shared__ __align__(8) uint64_t img_bar, stage_full[2], stage_empty[2], p0_full[2], p0_empty[2], p1_full[2], p1_empty[2], acc1_full[2],
+      acc1_empty[2], acc2_full[2], acc2_empty[2];
   __shared__ uint32_t tmem_slot;
-  // Order matters: the level p+2 MMA runs M = 128 over 63 useful rows; its surplus rows read on into the next buffer,
+  // Order matters: the level p+2 MMA runs M = 128 over 63 useful rows; its surplus rows read on into the following buffers,
   // which must hold finite fp16 data (their products only reach accumulator rows that are never read back).
-  uint8_t* p1h = smem;
-  uint8_t* p1l = smem + kCasP1Bytes;
-  uint8_t* p0h = smem + 2 * kCasP1Bytes;
-  uint8_t* p0l = p0h + kCasP0Bytes;
-  uint8_t* img = p0l + kCasP0Bytes;
-  float* stage = reinterpret_cast<float*>(img + kCasImgBytes);
-  float* tbuf2 = reinterpret_cast<float*>(img + kCasImgBytes + kCasStageBytes);
-  float* tbuf1 = reinterpret_cast<float*>(p0h);  // free between MMA1 of a tile and the conversion of the next one
+  uint8_t* p1 = smem;                                  // [buf 2][hi | lo][kCasP1Bytes]
+  uint8_t* p0 = smem + 4 * kCasP1Bytes;                // [buf 2][hi | lo][kCasP0Bytes]
+  uint8_t* img = p0 + 4 * kCasP0Bytes;
+  float* stage = reinterpret_cast<float*>(img + kCasImgBytes);  // [2][kCasSpan]
+  float* tbuf1 = reinterpret_cast<float*>(img + kCasImgBytes + 2 * kCasStageBytes);  // [group 2]
+  float* tbuf2 = reinterpret_cast<float*>(img + kCasImgBytes + 2 * kCasStageBytes + 2 * kCasT1Bytes);
   const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
-  const int row = 32 * (warp & 3) + lane;  // accumulator lane = row of 32 outputs
-  const int hf = warp >> 2;                // which 16 of them this thread handles
   const bool two = a.n_levels == 2;
 
-  if (warp == 0) tmem_alloc(&tmem_slot, 128);
+  if (warp == 19) tmem_alloc(&tmem_slot, 256);
   if (tid == 0) {
-    mbar_init(&img_bar, 1), mbar_init(&bar1, 1), mbar_init(&bar2, 1), mbar_init(&stage_bar, 1);
+    mbar_init(&img_bar, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&stage_full[i], 1), mbar_init(&stage_empty[i], kCasConvThreads);
+      mbar_init(&p0_full[i], kCasConvThreads), mbar_init(&p0_empty[i], 1);
+      mbar_init(&p1_full[i], 128), mbar_init(&p1_empty[i], 1);
+      mbar_init(&acc1_full[i], 1), mbar_init(&acc1_empty[i], 128);
+      mbar_init(&acc2_full[i], 1), mbar_init(&acc2_empty[i], 64);
+    }
     mbar_init_fence();
   }
-  for (uint32_t i = tid; i < (2 * kCasP1Bytes + 2 * kCasP0Bytes) / 16; i += kCasThreads) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  for (uint32_t i = tid; i < (4 * kCasP1Bytes + 4 * kCasP0Bytes) / 16; i += kCasThreads) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
   fence_proxy_async();
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
-  if (tid == 0) {
-    mbar_arrive_expect_tx(&img_bar, kCasImgBytes);
-    bulk_g2s(img, a.img, kCasImgBytes, &img_bar);
-  }
   const uint32_t tmem = tmem_slot;
-  const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16) + 16 * hf;
-  uint32_t ph1 = 0, ph2 = 0, phs = 0;
   // accumulator -> sample: level p+1 carries kXScale * kDecScale, level p+2 one more kDecScale (the level p+1 operand is the
   // raw accumulator: no rescaling between the two steps)
   constexpr float kInv1 = 1.f / (kXScale * kDecScale), kInv2 = kInv1 / kDecScale;
 
-  auto issue_level = [&](uint32_t d, uint32_t hi0, uint32_t lo0, uint32_t lbo, uint64_t* bar) {
-    const uint64_t a_desc = desc_hi(lbo);
-    constexpr uint64_t B_DESC = desc_hi(64 * 16);
-    constexpr uint32_t IDESC64 = idesc_f16(64), IDESC32 = idesc_f16(32);
-    const uint32_t w0 = smem_u32(img);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const uint32_t off = (uint32_t)((2 * j) & 7) * lbo + (j >= 4 ? 16u : 0u);  // chunks 8..15 = planes 0..7, one row on
-      const uint64_t bd = make_desc(B_DESC, w0 + (uint32_t)j * 2048);
-      mma_f16(d, make_desc(a_desc, hi0 + off), bd, IDESC64, j ? 1u : 0u);
-      mma_f16(d, make_desc(a_desc, lo0 + off), bd, IDESC32, 1u);
-    }
-    commit(bar);
-  };
-  // this thread's 16 accumulator columns: out[n] = D[n] + D[32 + n]
-  auto read_acc = [&](uint32_t col0, float (&o)[16]) {
-    float w[16];
-    tmem_ld16(lane_base + col0, o);
-    tmem_ld16(lane_base + col0 + 32, w);
-#pragma unroll
-    for (int j = 0; j < 16; ++j) o[j] += w[j];
-  };
   auto clip_len = [&](int b) {  // samples of level p in clip b
     const long long n0 = a.lengths ? a.lengths[b] : a.n_uniform;
     return (n0 + (1LL << a.level_in) - 1) >> a.level_in;
@@ -405,191 +384,279 @@ __global__ void __launch_bounds__(kCasThreads, 2) cascade_umma_kernel(const Casc
     s.bulk = (reinterpret_cast<uintptr_t>(s.src) & 15) == 0;
     return s;
   };
-  // Start landing a tile's span in the stage (call when no thread reads the stage any more).  Aligned clips: thread 0 sends
-  // one bulk copy of the existing samples (whole float4s) and patches the <= 3 tail samples; otherwise every thread fetches
-  // the chunks it will convert itself.  Samples outside [vlo, vhi) are masked at conversion time, not written here.
-  auto start_stage = [&](int tile) {
-    const Span s = span_of(tile);
-    if (s.bulk) {
-      if (tid == 0) {
-        const int n4 = (s.vhi - s.vlo) & ~3;
-        for (int i = s.vlo + n4; i < s.vhi; ++i) stage[i] = __ldg(s.src + i);
-        if (n4 > 0) {
-          mbar_arrive_expect_tx(&stage_bar, (uint32_t)n4 * 4);
-          bulk_g2s(stage + s.vlo, s.src + s.vlo, (uint32_t)n4 * 4, &stage_bar);
-        } else {
-          mbar_arrive(&stage_bar);
-        }
-      }
-    } else {
-      for (int i = 0; i < kCasPer; ++i) {
-        const int q = tid + kCasThreads * i;
-        if (q < kCasChunks)
-          for (int e = 0; e < 8; ++e)
-            if (8 * q + e >= s.vlo && 8 * q + e < s.vhi) stage[8 * q + e] = __ldg(s.src + 8 * q + e);
-      }
-      if (tid == 0) mbar_arrive(&stage_bar);
+
+  if (warp == 18) {
+    // ------------------------------------------------------------------ loader
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&img_bar, kCasImgBytes);
+      bulk_g2s(img, a.img, kCasImgBytes, &img_bar);
     }
-  };
-  // stage -> level-p operand planes (fp16 hi/lo, transposed chunk planes)
-  auto convert = [&](int tile) {
-    const Span s = span_of(tile);
-    mbar_wait(&stage_bar, phs);
-    phs ^= 1;
-    const bool interior = s.vlo == 0 && s.vhi == kCasSpan;
-    const uint64_t ss = f2_pack(kXScale, kXScale);
-    // one float4 per thread and round: consecutive lanes read consecutive 16 B of the stage and write 8-byte halves of the
-    // operand chunks (both conflict-free)
+    int i = 0;
+    for (int tile = next_tile(blockIdx.x); tile < a.n_tiles; tile = next_tile(tile + gridDim.x), ++i) {
+      const int s = i & 1;
+      float* st = stage + (size_t)s * kCasSpan;
+      const Span sp = span_of(tile);
+      mbar_wait(&stage_empty[s], ((i >> 1) & 1) ^ 1);
+      if (sp.bulk) {
+        // one bulk copy of the existing samples (whole float4s); lane 0 patches the <= 3 tail samples.  Samples outside
+        // [vlo, vhi) are masked at conversion time, not written here.
+        if (lane == 0) {
+          const int n4 = (sp.vhi - sp.vlo) & ~3;
+          for (int q = sp.vlo + n4; q < sp.vhi; ++q) st[q] = __ldg(sp.src + q);
+          if (n4 > 0) {
+            mbar_arrive_expect_tx(&stage_full[s], (uint32_t)n4 * 4);
+            bulk_g2s(st + sp.vlo, sp.src + sp.vlo, (uint32_t)n4 * 4, &stage_full[s]);
+          } else {
+            mbar_arrive(&stage_full[s]);
+          }
+        }
+      } else {
+        for (int q = sp.vlo + lane; q < sp.vhi; q += 32) st[q] = __ldg(sp.src + q);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&stage_full[s]);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 19) {
+    // ------------------------------------------------------------------ MMA issuer
+    int n_my = 0;
+    for (int tile = next_tile(blockIdx.x); tile < a.n_tiles; tile = next_tile(tile + gridDim.x)) ++n_my;
+    mbar_wait(&img_bar, 0);
+    const uint32_t w0 = smem_u32(img);
+    auto issue_level = [&](uint32_t d, uint32_t hi0, uint32_t lo0, uint32_t lbo, uint64_t* bar_acc, uint64_t* bar_planes) {
+      const uint64_t a_desc = desc_hi(lbo);
+      constexpr uint64_t B_DESC = desc_hi(64 * 16);
+      constexpr uint32_t IDESC64 = idesc_f16(64), IDESC32 = idesc_f16(32);
 #pragma unroll
-    for (int i = 0; i < kCasPer4; ++i) {
-      const int f = tid + kCasThreads * i;
-      if (f < 2 * kCasChunks) {
-        const float4 v = *reinterpret_cast<const float4*>(stage + 4 * f);
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t off = (uint32_t)((2 * j) & 7) * lbo + (j >= 4 ? 16u : 0u);  // chunks 8..15 = planes 0..7, one row on
+        const uint64_t bd = make_desc(B_DESC, w0 + (uint32_t)j * 2048);
+        mma_f16(d, make_desc(a_desc, hi0 + off), bd, IDESC64, j ? 1u : 0u);
+        mma_f16(d, make_desc(a_desc, lo0 + off), bd, IDESC32, 1u);
+      }
+      commit(bar_acc);
+      commit(bar_planes);
+    };
+    auto issue1 = [&](int i) {
+      const int bf = i & 1;
+      const uint32_t ph = (i >> 1) & 1;
+      mbar_wait(&p0_full[bf], ph);
+      mbar_wait(&acc1_empty[bf], ph ^ 1);
+      fence_after_sync();
+      const uint32_t hi0 = smem_u32(p0 + (size_t)bf * 2 * kCasP0Bytes);
+      if (elect_one()) issue_level(tmem + bf * 64, hi0, hi0 + kCasP0Bytes, kCasLBO0, &acc1_full[bf], &p0_empty[bf]);
+      __syncwarp();
+    };
+    auto issue2 = [&](int i) {
+      const int bf = i & 1;
+      const uint32_t ph = (i >> 1) & 1;
+      mbar_wait(&p1_full[bf], ph);
+      mbar_wait(&acc2_empty[bf], ph ^ 1);
+      fence_after_sync();
+      const uint32_t hi0 = smem_u32(p1 + (size_t)bf * 2 * kCasP1Bytes);
+      if (elect_one()) issue_level(tmem + 128 + bf * 64, hi0, hi0 + kCasP1Bytes, kCasLBO1, &acc2_full[bf], &p1_empty[bf]);
+      __syncwarp();
+    };
+    if (n_my > 0) issue1(0);
+    if (n_my > 1) issue1(1);
+    for (int i = 0; i < n_my; ++i) {
+      if (two) issue2(i);
+      if (i + 2 < n_my) issue1(i + 2);
+    }
+  } else if (warp >= 10) {
+    // ------------------------------------------------------------------ converter: stage -> level-p operand planes
+    const int ct = tid - 10 * 32;
+    const uint64_t ss = f2_pack(kXScale, kXScale);
+    int i = 0;
+    for (int tile = next_tile(blockIdx.x); tile < a.n_tiles; tile = next_tile(tile + gridDim.x), ++i) {
+      const int bf = i & 1;
+      const uint32_t ph = (i >> 1) & 1;
+      const Span sp = span_of(tile);
+      const float* st = stage + (size_t)bf * kCasSpan;
+      uint8_t* p0h = p0 + (size_t)bf * 2 * kCasP0Bytes;
+      uint8_t* p0l = p0h + kCasP0Bytes;
+      mbar_wait(&stage_full[bf], ph);
+      mbar_wait(&p0_empty[bf], ph ^ 1);
+      const bool interior = sp.vlo == 0 && sp.vhi == kCasSpan;
+      // one float4 per thread and round: consecutive lanes read consecutive 16 B of the stage and write 8-byte halves of the
+      // operand chunks (both conflict-free).  float4 f = ct + 256 r is half (f & 1) of chunk q = f / 2, which lives at
+      // plane (q & 7), row (q >> 3): the plane and the half are fixed per thread, the row advances by 16 per round.
+      const uint32_t off0 = (uint32_t)((ct >> 1) & 7) * kCasLBO0 + (uint32_t)(ct >> 4) * 16 + (uint32_t)(ct & 1) * 8;
+      auto convert4 = [&](int r) {
+        const int f = ct + kCasConvThreads * r;
+        const float4 v = *reinterpret_cast<const float4*>(st + 4 * f);
         float x[4] = {v.x, v.y, v.z, v.w};
         if (!interior) {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) x[e] = (4 * f + e >= s.vlo && 4 * f + e < s.vhi) ? x[e] : 0.f;
+          for (int e = 0; e < 4; ++e) x[e] = (4 * f + e >= sp.vlo && 4 * f + e < sp.vhi) ? x[e] : 0.f;
         }
         uint32_t h[2], l[2];
         cas_split2(f2_mul(f2_pack(x[0], x[1]), ss), h[0], l[0]);
         cas_split2(f2_mul(f2_pack(x[2], x[3]), ss), h[1], l[1]);
-        const int q = f >> 1;
-        const uint32_t off = (uint32_t)(q & 7) * kCasLBO0 + (uint32_t)(q >> 3) * 16 + (uint32_t)(f & 1) * 8;
+        const uint32_t off = off0 + 256u * (uint32_t)r;
         *reinterpret_cast<uint2*>(p0h + off) = make_uint2(h[0], h[1]);
         *reinterpret_cast<uint2*>(p0l + off) = make_uint2(l[0], l[1]);
-      }
+      };
+      static_assert(kCasPer4 == 9 && 2 * kCasChunks - 8 * kCasConvThreads == 16, "8 full rounds + 16 float4s");
+#pragma unroll
+      for (int r = 0; r < 8; ++r) convert4(r);
+      if (ct < 16) convert4(8);
+      fence_proxy_async();
+      mbar_arrive(&p0_full[bf]);
+      mbar_arrive(&stage_empty[bf]);
     }
-  };
-
-  int tile = next_tile(blockIdx.x);
-  if (tile < a.n_tiles) {
-    start_stage(tile);
-    convert(tile);
-    fence_proxy_async();
-    __syncthreads();
-    const int nxt = next_tile(tile + gridDim.x);
-    if (nxt < a.n_tiles) start_stage(nxt);
-    if (warp == 0) {  // converged warp, one elected lane issues (see umma.cuh: single-lane issue)
-      mbar_wait(&img_bar, 0);
+  } else if (warp < 8) {
+    // ------------------------------------------------------------------ epilogue 1: accumulator lane = row of 32 level p+1 outputs
+    const int grp = warp >> 2, row = tid & 127;  // group g drains the tiles i = g, g + 2, ... (accumulator / plane buffer g)
+    const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16) + grp * 64;
+    float* tb = tbuf1 + (size_t)grp * (kCasT1Bytes / 4);
+    uint8_t* p1h = p1 + (size_t)grp * 2 * kCasP1Bytes;
+    uint8_t* p1l = p1h + kCasP1Bytes;
+    const uint64_t inv1 = f2_pack(kInv1, kInv1);
+    int i = 0;
+    for (int tile = next_tile(blockIdx.x); tile < a.n_tiles; tile = next_tile(tile + gridDim.x), ++i) {
+      if ((i & 1) != grp) continue;
+      const uint32_t ph = (i >> 1) & 1;
+      const int b = tile / a.tiles_per_clip, t = tile - b * a.tiles_per_clip;
+      const long long n_p = clip_len(b);
+      const long long n_half1 = n_p >> 1, n1 = (n_p + 1) >> 1;
+      const long long o_lo1 = (long long)kCasOwn1 * t - 32;
+      mbar_wait(&acc1_full[grp], ph);
       fence_after_sync();
-      if (elect_one()) issue_level(tmem, smem_u32(p0h), smem_u32(p0l), kCasLBO0, &bar1);
-      __syncwarp();
-    }
-  } else if (warp == 0) {
-    mbar_wait(&img_bar, 0);  // never leave with a bulk copy in flight
-  }
-  while (tile < a.n_tiles) {
-    const int b = tile / a.tiles_per_clip, t = tile - b * a.tiles_per_clip;
-    const long long n_p = clip_len(b);
-    const long long n_half1 = n_p >> 1, n1 = (n_p + 1) >> 1, n_half2 = n1 >> 1, n2 = (n1 + 1) >> 1;
-    const long long o_lo2 = (long long)kCasOwn2 * t, o_lo1 = (long long)kCasOwn1 * t - 32;
-    const int nxt = next_tile(tile + gridDim.x);
-
-    // ---- level p+1
-    mbar_wait(&bar1, ph1);
-    ph1 ^= 1;
-    fence_after_sync();
-    {
-      float o[16];
-      read_acc(0, o);
-      const long long i1 = o_lo1 + 32LL * row + 16 * hf;  // level p+1 index of o[0]
+      uint64_t o[16];  // 32 outputs as fp32 pairs
+      {
+        uint32_t u0[16], u1[16], w0[16], w1[16];
+        tmem_ld16_issue(lane_base, u0);
+        tmem_ld16_issue(lane_base + 16, u1);
+        tmem_ld16_issue(lane_base + 32, w0);
+        tmem_ld16_issue(lane_base + 48, w1);
+        tmem_ld_wait16(u0), tmem_ld_wait16(u1), tmem_ld_wait16(w0), tmem_ld_wait16(w1);
+#pragma unroll
+        for (int n = 0; n < 8; ++n) {
+          o[n] = f2_add(f2_pack(__uint_as_float(u0[2 * n]), __uint_as_float(u0[2 * n + 1])), f2_pack(__uint_as_float(w0[2 * n]), __uint_as_float(w0[2 * n + 1])));
+          o[8 + n] = f2_add(f2_pack(__uint_as_float(u1[2 * n]), __uint_as_float(u1[2 * n + 1])), f2_pack(__uint_as_float(w1[2 * n]), __uint_as_float(w1[2 * n + 1])));
+        }
+      }
+      fence_before_sync();
+      mbar_arrive(&acc1_empty[grp]);  // accumulator drained: MMA1 of tile i + 2 may start
       if (o_lo1 < 0 || o_lo1 + 128 * 32 > n_half1) {
         // samples that do not exist (index < 0 or >= floor(n_p / 2)) are zero
-        const int zlo = (int)min(16LL, max(0LL, -i1)), zhi = (int)min(16LL, max(0LL, n_half1 - i1));
+        const long long i1 = o_lo1 + 32LL * row;  // level p+1 index of the row's first output
+        const int zlo = (int)min(32LL, max(0LL, -i1)), zhi = (int)min(32LL, max(0LL, n_half1 - i1));
 #pragma unroll
-        for (int n = 0; n < 16; ++n) o[n] = (n >= zlo && n < zhi) ? o[n] : 0.f;
+        for (int n = 0; n < 16; ++n) {
+          float x0, x1;
+          f2_unpack(o[n], x0, x1);
+          o[n] = f2_pack((2 * n >= zlo && 2 * n < zhi) ? x0 : 0.f, (2 * n + 1 >= zlo && 2 * n + 1 < zhi) ? x1 : 0.f);
+        }
+      }
+      if (two) {
+        // level p+1 as the next operand: row r = half of operand row r / 2, chunks 4 (r & 1) .. + 3
+        mbar_wait(&p1_empty[grp], ph ^ 1);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t h[4], l[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) cas_split2(o[4 * c + e], h[e], l[e]);
+          const uint32_t off = (uint32_t)(4 * (row & 1) + c) * kCasLBO1 + (uint32_t)(row >> 1) * 16;
+          *reinterpret_cast<uint4*>(p1h + off) = make_uint4(h[0], h[1], h[2], h[3]);
+          *reinterpret_cast<uint4*>(p1l + off) = make_uint4(l[0], l[1], l[2], l[3]);
+        }
+        fence_proxy_async();
+        mbar_arrive(&p1_full[grp]);
       }
       // fp32 outputs go through shared memory so that the global stores are row-contiguous (a thread owns a row: storing
       // straight from registers would touch 32 different lines per instruction)
 #pragma unroll
-      for (int q = 0; q < 4; ++q)
-        *reinterpret_cast<float4*>(tbuf1 + row * kCasTPitch + 16 * hf + 4 * q) =
-            make_float4(o[4 * q] * kInv1, o[4 * q + 1] * kInv1, o[4 * q + 2] * kInv1, o[4 * q + 3] * kInv1);
-      if (two) {
+      for (int q = 0; q < 8; ++q) {
+        float4 v;
+        f2_unpack(f2_mul(o[2 * q], inv1), v.x, v.y);
+        f2_unpack(f2_mul(o[2 * q + 1], inv1), v.z, v.w);
+        *reinterpret_cast<float4*>(tb + row * kCasTPitch + 4 * q) = v;
+      }
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+      {
+        // rows 1..126 are owned (0 and 127 are the halo the next level needs): 1008 float4s, 8 per row; thread `row` stores
+        // float4 (row & 7) of the rows 1 + (row >> 3) + 16 k
+        float* dst = a.out1 + (long long)b * a.stride1 + o_lo1 + 32 * (1 + (row >> 3)) + 4 * (row & 7);
+        const float* src = tb + (1 + (row >> 3)) * kCasTPitch + 4 * (row & 7);
+        // rows with 32 r < lim exist (the buffers are padded to whole rows of 32)
+        const int r_lim = (int)min(127LL, max(0LL, (n1 - o_lo1 + 31) >> 5));
+        const bool sparse = a.sparse_hop > 0;
+        int u = 0;
+        if (sparse) {
+          u = (int)((unsigned long long)(o_lo1 + a.sparse_nfft / 2) % (unsigned)a.sparse_hop) + 32 * (1 + (row >> 3));
+          u -= (u >= a.sparse_hop) ? a.sparse_hop : 0;
+        }
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          float v[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] = o[8 * i + e];
-          const uint32_t off = (uint32_t)(4 * (row & 1) + 2 * hf + i) * kCasLBO1 + (uint32_t)(row >> 1) * 16;
-          cas_store_split8<false>(p1h + off, p1l + off, v, 1.f);
+        for (int k = 0; k < 8; ++k) {
+          const int r = 1 + (row >> 3) + 16 * k;
+          bool need = r < r_lim;
+          // sparse: the only reader of this level is the filter bank, frames [t hop - n_fft/2, t hop + n_fft/2): keep the rows
+          // whose offset u into the hop period (advanced by 16 rows = 512 samples per round) falls into a frame
+          if (sparse) need = need && (u < a.sparse_nfft || u + 31 >= a.sparse_hop);
+          u += 512;
+          u -= (u >= a.sparse_hop) ? a.sparse_hop : 0;
+          if (need) *reinterpret_cast<float4*>(dst + 512 * k) = *reinterpret_cast<const float4*>(src + 16 * k * kCasTPitch);
         }
       }
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");  // the transposition buffer is reused by the group's next tile
     }
-    fence_before_sync();
-    fence_proxy_async();
-    __syncthreads();
-    if (two && warp == 0) {
+  } else if (two) {
+    // ------------------------------------------------------------------ epilogue 2 (warps 8, 9): rows 0..62 of level p+2
+    const int row = tid - 256;  // accumulator lane (warp 8: lanes 0..31, warp 9: 32..63)
+    const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16) + 128;
+    int i = 0;
+    for (int tile = next_tile(blockIdx.x); tile < a.n_tiles; tile = next_tile(tile + gridDim.x), ++i) {
+      const int bf = i & 1;
+      const uint32_t ph = (i >> 1) & 1;
+      const int b = tile / a.tiles_per_clip, t = tile - b * a.tiles_per_clip;
+      const long long n_p = clip_len(b);
+      const long long n1 = (n_p + 1) >> 1, n_half2 = n1 >> 1, n2 = (n1 + 1) >> 1;
+      const long long o_lo2 = (long long)kCasOwn2 * t;
+      mbar_wait(&acc2_full[bf], ph);
       fence_after_sync();
-      if (elect_one()) issue_level(tmem + 64, smem_u32(p1h), smem_u32(p1l), kCasLBO1, &bar2);
-      __syncwarp();
-    }
-    {
-      // rows 1..126 are owned (0 and 127 are the halo the next level needs): 1008 float4s, 8 per row
-      float* dst = a.out1 + (long long)b * a.stride1 + o_lo1;
-      const long long lim = n1 - o_lo1;  // row-local indices < lim exist (the buffers are padded to whole rows of 32)
+      float o[32];
+      {
+        uint32_t u0[16], u1[16], w0[16], w1[16];
+        tmem_ld16_issue(lane_base + bf * 64, u0);
+        tmem_ld16_issue(lane_base + bf * 64 + 16, u1);
+        tmem_ld16_issue(lane_base + bf * 64 + 32, w0);
+        tmem_ld16_issue(lane_base + bf * 64 + 48, w1);
+        tmem_ld_wait16(u0), tmem_ld_wait16(u1), tmem_ld_wait16(w0), tmem_ld_wait16(w1);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int idx = tid + kCasThreads * i;
-        const int r = 1 + (idx >> 3), c4 = idx & 7;
-        if (idx < 126 * 8 && 32LL * r < lim)
-          *reinterpret_cast<float4*>(dst + 32 * r + 4 * c4) = *reinterpret_cast<const float4*>(tbuf1 + r * kCasTPitch + 4 * c4);
+        for (int n = 0; n < 16; ++n) o[n] = __uint_as_float(u0[n]) + __uint_as_float(w0[n]), o[16 + n] = __uint_as_float(u1[n]) + __uint_as_float(w1[n]);
       }
-    }
-    __syncthreads();  // tbuf1 aliases the level-p planes the conversion below overwrites
-    // ---- next tile's operand while MMA2 runs (the level-p planes are free: MMA1 of this tile has completed)
-    if (nxt < a.n_tiles) convert(nxt);
-    fence_proxy_async();
-    __syncthreads();
-    if (nxt < a.n_tiles) {
-      const int nxt2 = next_tile(nxt + gridDim.x);
-      if (nxt2 < a.n_tiles) start_stage(nxt2);  // every thread has consumed the stage
-      if (warp == 0) {
-        fence_after_sync();
-        if (elect_one()) issue_level(tmem, smem_u32(p0h), smem_u32(p0l), kCasLBO0, &bar1);
-        __syncwarp();
-      }
-    }
-    // ---- level p+2 (overlaps MMA1 of the next tile)
-    if (two) {
-      mbar_wait(&bar2, ph2);
-      ph2 ^= 1;
-      fence_after_sync();
-      if ((warp & 3) < 2) {  // rows 0..62 live in accumulator lanes 0..63 (tcgen05.ld is warp-collective: no per-thread predicate)
-        float o[16];
-        read_acc(64, o);
-        const long long i2 = o_lo2 + 32LL * row + 16 * hf;
-        const int zhi = (int)min(16LL, max(0LL, n_half2 - i2));
-        if (row < kCasRows2) {
+      fence_before_sync();
+      mbar_arrive(&acc2_empty[bf]);
+      if (o_lo2 + kCasRows2 * 32 > n_half2) {
+        // samples at or beyond floor(n1 / 2) do not exist: zero
+        const int zhi = (int)min(32LL, max(0LL, n_half2 - (o_lo2 + 32LL * row)));
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            float4 v;
-            v.x = (4 * q + 0 < zhi) ? o[4 * q + 0] * kInv2 : 0.f;
-            v.y = (4 * q + 1 < zhi) ? o[4 * q + 1] * kInv2 : 0.f;
-            v.z = (4 * q + 2 < zhi) ? o[4 * q + 2] * kInv2 : 0.f;
-            v.w = (4 * q + 3 < zhi) ? o[4 * q + 3] * kInv2 : 0.f;
-            *reinterpret_cast<float4*>(tbuf2 + row * kCasTPitch + 16 * hf + 4 * q) = v;
-          }
-        }
-        asm volatile("bar.sync 1, 128;" ::: "memory");  // warps 0, 1, 4, 5
-        float* dst = a.out2 + (long long)b * a.stride2 + o_lo2;
-        const long long lim = n2 - o_lo2;
-        const int t128 = (warp >> 2) * 64 + (warp & 1) * 32 + lane;  // 0..127 over the four warps
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int idx = t128 + 128 * i;
-          const int r = idx >> 3, c4 = idx & 7;
-          if (idx < kCasRows2 * 8 && 32LL * r < lim)
-            *reinterpret_cast<float4*>(dst + 32 * r + 4 * c4) = *reinterpret_cast<const float4*>(tbuf2 + r * kCasTPitch + 4 * c4);
-        }
+        for (int n = 0; n < 32; ++n) o[n] = (n < zhi) ? o[n] : 0.f;
       }
-      fence_before_sync();  // ordered before the next MMA2 by the barrier that precedes its issue
+      if (row < kCasRows2) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<float4*>(tbuf2 + row * kCasTPitch + 4 * q) =
+              make_float4(o[4 * q] * kInv2, o[4 * q + 1] * kInv2, o[4 * q + 2] * kInv2, o[4 * q + 3] * kInv2);
+      }
+      asm volatile("bar.sync 3, 64;" ::: "memory");
+      float* dst = a.out2 + (long long)b * a.stride2 + o_lo2;
+      const long long lim = n2 - o_lo2;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int idx = row + 64 * k;
+        const int r = idx >> 3, c4 = idx & 7;
+        if (idx < kCasRows2 * 8 && 32LL * r < lim)
+          *reinterpret_cast<float4*>(dst + 32 * r + 4 * c4) = *reinterpret_cast<const float4*>(tbuf2 + r * kCasTPitch + 4 * c4);
+      }
+      asm volatile("bar.sync 3, 64;" ::: "memory");
     }
-    tile = nxt;
   }
   fence_before_sync();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, 128);
+  if (warp == 19) tmem_dealloc(tmem, 256);
 }
 
 // ---- tensor-core filter bank (tcgen05): one CTA = 128 frames of one octave x all filters x all of K ----------------
@@ -667,9 +734,22 @@ __global__ void __launch_bounds__(160) cqt_bank_umma_kernel(const BankArgs a) {
     // lanes 16-31 those of the next (coalesced 256-byte runs), convert to fp16 hi/lo and scatter 8-byte halves of the
     // operand chunks (chunk c of row r at c * kBankLBO + r * 16).
     const float* level = a.level[octave];
-    const bool base_aligned = (reinterpret_cast<uintptr_t>(level) & 15) == 0;
     const int f = lane & 15;
     const uint64_t ss = f2_pack(kXScale, kXScale);
+    // The 16 rows this thread feeds are the same for every block of K: their sample pointers (frame-local index 4 f of the
+    // first block) and a 2-bit class live in registers.  Class 0: the whole frame exists and the pointer is 16-byte aligned
+    // (one vector load); 1: the whole frame exists (four scalar loads); 2: centred-frame zero padding or the clip's end
+    // cuts the frame (per-sample predicates).
+    const float* rowp[16];
+    uint32_t cls = 0;
+#pragma unroll
+    for (int it = 0; it < 16; ++it) {
+      const int r = warp * 32 + 2 * it + (lane >> 4);
+      const int2 v = s_valid[r];
+      rowp[it] = level + s_g0[r] + 4 * f;
+      const uint32_t c = (v.x == 0 && v.y == a.n_fft) ? (((reinterpret_cast<uintptr_t>(rowp[it]) & 15) == 0) ? 0u : 1u) : 2u;
+      cls |= c << (2 * it);
+    }
     for (int kb = 0; kb < n_kb; ++kb) {
       const int s = kb % kUStages;
       const uint32_t phase = (kb / kUStages) & 1;
@@ -680,28 +760,31 @@ __global__ void __launch_bounds__(160) cqt_bank_umma_kernel(const BankArgs a) {
         bulk_g2s(stage + 2 * A_HALF, reinterpret_cast<const uint8_t*>(a.bank_img) + (size_t)kb * B_BYTES, B_BYTES, &full_bar[s]);
       }
       const int i0 = kb * kUKB + 4 * f;  // frame-local index of this lane's first sample
-      // all 16 loads are issued before the first conversion consumes one (the branch below must not serialise them)
-      float x[16][4];
+      // all 16 loads are issued before the first conversion consumes one
+      float4 x[16];
 #pragma unroll
       for (int it = 0; it < 16; ++it) {
-        const int r = warp * 32 + 2 * it + (lane >> 4);
-        const long long g = s_g0[r] + i0;
-        const int2 v = s_valid[r];
-        if (i0 >= v.x && i0 + 4 <= v.y && base_aligned && (g & 3) == 0) {
-          const float4 q = __ldg(reinterpret_cast<const float4*>(level + g));
-          x[it][0] = q.x, x[it][1] = q.y, x[it][2] = q.z, x[it][3] = q.w;
+        const float* src = rowp[it] + kb * kUKB;
+        const uint32_t c = (cls >> (2 * it)) & 3u;
+        if (c == 0) {
+          x[it] = __ldg(reinterpret_cast<const float4*>(src));
+        } else if (c == 1) {
+          x[it] = make_float4(__ldg(src), __ldg(src + 1), __ldg(src + 2), __ldg(src + 3));
         } else {
-#pragma unroll
-          for (int e = 0; e < 4; ++e) x[it][e] = (i0 + e >= v.x && i0 + e < v.y) ? __ldg(level + g + e) : 0.f;
+          const int2 v = s_valid[warp * 32 + 2 * it + (lane >> 4)];
+          x[it].x = (i0 + 0 >= v.x && i0 + 0 < v.y) ? __ldg(src + 0) : 0.f;
+          x[it].y = (i0 + 1 >= v.x && i0 + 1 < v.y) ? __ldg(src + 1) : 0.f;
+          x[it].z = (i0 + 2 >= v.x && i0 + 2 < v.y) ? __ldg(src + 2) : 0.f;
+          x[it].w = (i0 + 3 >= v.x && i0 + 3 < v.y) ? __ldg(src + 3) : 0.f;
         }
       }
+      const uint32_t off0 = (uint32_t)(f >> 1) * kBankLBO + (uint32_t)(warp * 32 + (lane >> 4)) * 16 + (uint32_t)(f & 1) * 8;
 #pragma unroll
       for (int it = 0; it < 16; ++it) {
-        const int r = warp * 32 + 2 * it + (lane >> 4);
         uint32_t h0, l0, h1, l1;
-        cas_split2(f2_mul(f2_pack(x[it][0], x[it][1]), ss), h0, l0);
-        cas_split2(f2_mul(f2_pack(x[it][2], x[it][3]), ss), h1, l1);
-        const uint32_t off = (uint32_t)(f >> 1) * kBankLBO + (uint32_t)r * 16 + (uint32_t)(f & 1) * 8;
+        cas_split2(f2_mul(f2_pack(x[it].x, x[it].y), ss), h0, l0);
+        cas_split2(f2_mul(f2_pack(x[it].z, x[it].w), ss), h1, l1);
+        const uint32_t off = off0 + 32u * it;  // row r = warp * 32 + 2 it + (lane >> 4)
         *reinterpret_cast<uint2*>(stage + off) = make_uint2(h0, h1);
         *reinterpret_cast<uint2*>(stage + A_HALF + off) = make_uint2(l0, l1);
       }
@@ -807,7 +890,7 @@ static void run_cqt(ake_cqt* p, const float* audio, long long stride, const int6
   w.level[0] = const_cast<float*>(audio);
   w.stride[0] = stride;
   if (p->n_oct > 1) {
-    // resampling cascade: two octave steps per pass (level p -> p+1, p+2), persistent CTAs, 3 per SM
+    // resampling cascade: two octave steps per pass (level p -> p+1, p+2), one persistent warp-specialised CTA per SM
     ProfScope prof("cqt.decimate", st);
     static bool configured = false;
     static int n_sm = 0;
@@ -828,7 +911,11 @@ static void run_cqt(ake_cqt* p, const float* audio, long long stride, const int6
       ca.tiles_per_clip = (int)cdiv64(len_at(n_max, lv + 1), kCasOwn1);
       ca.n_tiles = ca.tiles_per_clip * B;
       ca.img = p->d_dec_img;
-      const int grid = std::min(ca.n_tiles, 2 * n_sm);
+      // level lv+1 is consumed by the filter bank only (the next pass reads level lv+2): when its frames do not overlap,
+      // the samples between them are never written
+      const int hop1 = p->hop >> (lv + 1);
+      ca.sparse_hop = (ca.n_levels == 2 && hop1 >= p->n_fft + 64) ? hop1 : 0, ca.sparse_nfft = p->n_fft;
+      const int grid = std::min(ca.n_tiles, n_sm);  // persistent: one CTA per SM
       cascade_umma_kernel<<<grid, kCasThreads, kCasSmemTotal, st>>>(ca);
       AKE_LAUNCHED();
     }
