@@ -396,7 +396,7 @@ __global__ void __launch_bounds__(kCasThreads, 1) cascade_umma_kernel(const Casc
       const int s = i & 1;
       float* st = stage + (size_t)s * kCasSpan;
       const Span sp = span_of(tile);
-      mbar_wait(&stage_empty[s], ((i >> 1) & 1) ^ 1);
+      mbar_wait_relaxed(&stage_empty[s], ((i >> 1) & 1) ^ 1);
       if (sp.bulk) {
         // one bulk copy of the existing samples (whole float4s); lane 0 patches the <= 3 tail samples.  Samples outside
         // [vlo, vhi) are masked at conversion time, not written here.
@@ -475,8 +475,8 @@ __global__ void __launch_bounds__(kCasThreads, 1) cascade_umma_kernel(const Casc
       const float* st = stage + (size_t)bf * kCasSpan;
       uint8_t* p0h = p0 + (size_t)bf * 2 * kCasP0Bytes;
       uint8_t* p0l = p0h + kCasP0Bytes;
-      mbar_wait(&stage_full[bf], ph);
-      mbar_wait(&p0_empty[bf], ph ^ 1);
+      mbar_wait_relaxed(&stage_full[bf], ph);
+      mbar_wait_relaxed(&p0_empty[bf], ph ^ 1);
       const bool interior = sp.vlo == 0 && sp.vhi == kCasSpan;
       // one float4 per thread and round: consecutive lanes read consecutive 16 B of the stage and write 8-byte halves of the
       // operand chunks (both conflict-free).  float4 f = ct + 256 r is half (f & 1) of chunk q = f / 2, which lives at
@@ -498,7 +498,7 @@ __global__ void __launch_bounds__(kCasThreads, 1) cascade_umma_kernel(const Casc
         *reinterpret_cast<uint2*>(p0l + off) = make_uint2(l[0], l[1]);
       };
       static_assert(kCasPer4 == 9 && 2 * kCasChunks - 8 * kCasConvThreads == 16, "8 full rounds + 16 float4s");
-#pragma unroll
+#pragma unroll 2
       for (int r = 0; r < 8; ++r) convert4(r);
       if (ct < 16) convert4(8);
       fence_proxy_async();
@@ -521,7 +521,7 @@ __global__ void __launch_bounds__(kCasThreads, 1) cascade_umma_kernel(const Casc
       const long long n_p = clip_len(b);
       const long long n_half1 = n_p >> 1, n1 = (n_p + 1) >> 1;
       const long long o_lo1 = (long long)kCasOwn1 * t - 32;
-      mbar_wait(&acc1_full[grp], ph);
+      mbar_wait_relaxed(&acc1_full[grp], ph);
       fence_after_sync();
       uint64_t o[16];  // 32 outputs as fp32 pairs
       {
@@ -614,7 +614,7 @@ __global__ void __launch_bounds__(kCasThreads, 1) cascade_umma_kernel(const Casc
       const long long n_p = clip_len(b);
       const long long n1 = (n_p + 1) >> 1, n_half2 = n1 >> 1, n2 = (n1 + 1) >> 1;
       const long long o_lo2 = (long long)kCasOwn2 * t;
-      mbar_wait(&acc2_full[bf], ph);
+      mbar_wait_relaxed(&acc2_full[bf], ph);
       fence_after_sync();
       float o[32];
       {
@@ -753,7 +753,7 @@ __global__ void __launch_bounds__(160) cqt_bank_umma_kernel(const BankArgs a) {
     for (int kb = 0; kb < n_kb; ++kb) {
       const int s = kb % kUStages;
       const uint32_t phase = (kb / kUStages) & 1;
-      mbar_wait(&empty_bar[s], phase ^ 1);
+      mbar_wait_relaxed(&empty_bar[s], phase ^ 1);
       uint8_t* stage = smem + (size_t)s * STAGE;
       if (tid == 0) {
         mbar_arrive_expect_tx(&full_bar[s], B_BYTES);
@@ -792,7 +792,7 @@ __global__ void __launch_bounds__(160) cqt_bank_umma_kernel(const BankArgs a) {
       if (tid != 0) mbar_arrive(&full_bar[s]);
     }
     // ---------------------------------------------------------------- epilogue: TMEM lane `tid` = frame row `tid`
-    mbar_wait(&done_bar, 0);
+    mbar_wait_relaxed(&done_bar, 0);
     fence_after_sync();
     const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
     const int bpo = a.bpo;

@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(kP2PThreads, 1) p2p_umma_kernel(const P2PArgs 
       const Geom g = geom(tile);
       const int rows_in = g.PB + 6;
       const uint32_t row_bytes = (uint32_t)g.cols_in * 16;
-      mbar_wait(&empty_bar[s], ((k / kP2PBufs) & 1) ^ 1);
+      mbar_wait_relaxed(&empty_bar[s], ((k / kP2PBufs) & 1) ^ 1);
       if (lane == 0) mbar_arrive_expect_tx(&full_bar[s], 2u * rows_in * row_bytes);
       __syncwarp();
       uint8_t* d_hi = smem + (size_t)s * 2 * plane;
@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(kP2PThreads, 1) p2p_umma_kernel(const P2PArgs 
       const long long base = (long long)g.b * (a.P + 6);
       for (; j < j0 + g.n_mb; j += G, ++n_done) {
         const int m = (int)(j - j0);
-        mbar_wait(&acc_full[grp], n_done & 1);
+        mbar_wait_relaxed(&acc_full[grp], n_done & 1);
         fence_after_sync();
         // phase f = time tap f: out[a] = sum_f D_f[a + f], D_f of this thread's row = columns [16 f, 16 f + 8) (W_hi) +
         // [16 f + 8, 16 f + 16) (W_lo).  Rows a + f live f lanes further on: warp shuffles for lane + f < 32, the first
@@ -837,7 +837,7 @@ __global__ void __launch_bounds__(kPcThreads, 1) pc2pc_umma_kernel(const Pc2PcAr
       const int b = tile / a.n_ttiles, t0 = (tile - b * a.n_ttiles) * a.TB;
       const int cols_in = min(Wt, a.Wd_in - t0);
       const uint32_t row_bytes = (uint32_t)cols_in * 16;
-      mbar_wait(&empty_bar[s], ((k >> 1) & 1) ^ 1);
+      mbar_wait_relaxed(&empty_bar[s], ((k >> 1) & 1) ^ 1);
       if (lane == 0) mbar_arrive_expect_tx(&full_bar[s], 92u * row_bytes);
       __syncwarp();
       uint8_t* dst = smem + (size_t)s * 4 * plane;
@@ -894,7 +894,7 @@ __global__ void __launch_bounds__(kPcThreads, 1) pc2pc_umma_kernel(const Pc2PcAr
       const int TBv = min(a.TB, a.T_out - t0);
       for (; j < j0 + n_mb; j += G, ++n_done) {
         const int m = (int)(j - j0);
-        mbar_wait(&acc_full[grp], n_done & 1);
+        mbar_wait_relaxed(&acc_full[grp], n_done & 1);
         fence_after_sync();
         // phase f = time tap f: out[a] = sum_f D_f[a + f]; D_f = columns [16 f, 16 f + 16) (x . W_hi) + [112 + 16 f, ..) (x_hi . W_lo)
         uint64_t o[8];
