@@ -152,11 +152,14 @@ __global__ void __launch_bounds__(kP2PThreads, 1) p2p_umma_kernel(const P2PArgs 
   struct Geom {
     int b, p0, t0, PB, TBv, cols_in, n_anchor, n_mb;
   };
+  // tile -> (clip, row tile, time tile) by multiply-high: the issuer warp decodes a tile between two MMA blocks, and a
+  // hardware-less integer division is ~150 dependent instructions there (x / d == umulhi(x, 2^32 / d + 1) for x * d < 2^32)
+  const uint32_t tpc_magic = 0xFFFFFFFFu / (uint32_t)tiles_per_clip + 1, ntt_magic = 0xFFFFFFFFu / (uint32_t)a.n_ttiles + 1;
   auto geom = [&](int tile) {
     Geom g;
-    g.b = tile / tiles_per_clip;
+    g.b = tiles_per_clip == 1 ? tile : (int)__umulhi((uint32_t)tile, tpc_magic);
     const int r = tile - g.b * tiles_per_clip;
-    const int rtile = r / a.n_ttiles, ttile = r - rtile * a.n_ttiles;
+    const int rtile = a.n_ttiles == 1 ? r : (int)__umulhi((uint32_t)r, ntt_magic), ttile = r - rtile * a.n_ttiles;
     g.p0 = rtile * kP2PRows, g.t0 = ttile * a.TB;
     g.PB = min(kP2PRows, a.P - g.p0);          // valid output rows of this tile
     g.TBv = min(a.TB, a.T - g.t0);             // valid output frames
@@ -203,6 +206,18 @@ __global__ void __launch_bounds__(kP2PThreads, 1) p2p_umma_kernel(const P2PArgs 
         const long long src = (((long long)g.b * (a.P + 6) + g.p0 + rr) * a.Wd + g.t0) * 8;
         bulk_g2s(d_hi + (size_t)rr * Wt * 16, a.in_hi + src, row_bytes, &full_bar[s]);
         bulk_g2s(d_hi + plane + (size_t)rr * Wt * 16, a.in_lo + src, row_bytes, &full_bar[s]);
+      }
+      // The tile after this one cannot be copied before a buffer frees up (one tile time from now): pull it into L2
+      // meanwhile, so that copy pays the L2 latency instead of the HBM latency.
+      const int tile2 = tile + (kP2PBufs - 1) * (int)gridDim.x;
+      if (tile2 < a.n_tiles) {
+        const Geom g2 = geom(tile2);
+        const uint32_t rb2 = (uint32_t)g2.cols_in * 16;
+        for (int rr = lane; rr < g2.PB + 6; rr += 32) {
+          const long long src = (((long long)g2.b * (a.P + 6) + g2.p0 + rr) * a.Wd + g2.t0) * 8;
+          bulk_prefetch_l2(a.in_hi + src, rb2);
+          bulk_prefetch_l2(a.in_lo + src, rb2);
+        }
       }
     }
   } else if (warp == 4 * G + 1) {

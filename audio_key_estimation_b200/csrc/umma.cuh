@@ -190,6 +190,12 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                : "memory");
 }
 
+// Pull `bytes` (multiple of 16) of global memory into L2 ahead of the bulk copy that will land it in shared memory: a
+// bulk copy cannot start before its shared-memory buffer is free, a prefetch can.
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src_gmem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
+}
+
 // ---- fp16 two-term split ------------------------------------------------------------------------
 // x ~= hi + lo with hi = fp16(x), lo = fp16(x - hi): 22 significant bits while |x| stays in fp16's normal range.
 // Products are formed as hi*Whi + lo*Whi + hi*Wlo (fp32 accumulation in TMEM); the dropped lo*lo term is ~2^-22.
