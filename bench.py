@@ -306,10 +306,19 @@ def run_b200(args):
     dec_ms, dec_n = sec("cqt.decimate")
     bank_ms, bank_n = sec("cqt.bank")
     p2p_tflops = 2.0 * p2p_macs_clip * B / (p2p_ms * 1e-3) / 1e12 if p2p_ms else None
+    # DRAM bytes per launch of the dominant kernel come from the committed ncu capture (profiles/), valid for the default
+    # workload only; never measured live (a number taken under a profiler is not a bench value)
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "r01_roofline_traffic.json")
+    if os.path.exists(tpath) and B == 256 and abs(args.seconds - SECONDS_STD) < 1e-9 and genre:
+        with open(tpath) as fh:
+            tj = json.load(fh)
+        traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
     roofline = {
         "kernel": "pcn.p2p: 3 x Conv2d 7x7 circular (pitch,time) + BN + LeakyReLU (64.6% of the forward's MACs)",
         "bound": "tensor", "achieved": p2p_tflops, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-        "frac": (p2p_tflops / peaks["bf16_tflops_sustained"]) if p2p_tflops else None, "traffic": None,
+        "frac": (p2p_tflops / peaks["bf16_tflops_sustained"]) if p2p_tflops else None, "traffic": traffic, "traffic_source": traffic_src,
+        "algorithmic_flops_per_launch": 2.0 * p2p_macs_clip * B / max(1, p2p_n),
         "peak_source": f"{peaks['source']} bf16 dense, sustained (kernel timed inside a long step)",
         "launches_per_step": p2p_n, "ms_per_step": p2p_ms,
         "algorithmic_flops_per_step": 2.0 * p2p_macs_clip * B,
