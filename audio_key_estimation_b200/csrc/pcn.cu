@@ -127,6 +127,7 @@ struct ake_pcn {
   __half* d_wimg = nullptr;         // one kP2PWBytes image per Pitch2Pitch conv, in conv-id order of `umma_convs`
   std::vector<int> umma_convs;
   __half* d_wimg_pc = nullptr;      // equivariant convs of the layer-1 PitchClass2PitchClass stack (kPcWBytes each)
+  __half* d_wimg_l0 = nullptr;      // equivariant convs of the layer-0 PitchClass2PitchClass stack (kPc8WBytes each)
   __half* d_wimg_heads = nullptr;   // first conv of the tonic and key heads, fused along N (344,064 B)
   float* d_ss_heads = nullptr;      // [scale 64 | shift 64] of that fused conv (tonic channels first)
   __half* d_wimg_genre = nullptr;   // first conv of the genre head (1 x 7, 16 -> 32): one 16 KB stage
@@ -344,6 +345,8 @@ struct Fwd {
   __half* umma_pc_hi = nullptr;  // tensor-core path: final pitch-class features as chunk planes [B][2][23][T/2][8]
   __half* umma_pc_lo = nullptr;
   bool umma_pc_ready = false;
+  bool l0_fast = false;
+  __half* l0_planes[3][2] = {};
   double* d_stats = nullptr;  // train: per conv channel (sum, sumsq)
   float* d_ss_train = nullptr;
 
@@ -479,10 +482,18 @@ void Fwd::run(const float* mel, float* key_out, float* tonic_out, float* genre_o
         // eval mode: conv + BN + act + octave pool in one pass over the log-CQT
         const Conv& c = p->convs[lp.sem];
         View semi = alloc(1, S, Tn);
+        // tensor-core path of the layer-0 equivariant stack (1 -> 4 -> 4 -> 4 channels): 8-channel chunk planes
+        l0_fast = p->umma && Tn >= 7;
+        for (int id : lp.pc2pc) l0_fast = l0_fast && p->convs[id].Cin <= 8 && p->convs[id].Cout <= 8;
+        if (l0_fast)
+          for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 2; ++j) l0_planes[i][j] = arena.take<__half>((size_t)B * 23 * (Tn + 6) * 8);
         if (!dry) {
           ProfScope prof("pcn.semitone", st);
           l0_semitone_pool_kernel<<<dim3(cdiv(Tn, 128), 12, B), 128, 0, st>>>(p_in.p, p->d_params + c.w_off, scale_of(c, false),
-                                                                            shift_of(c, false), semi.p, cat.p, P, Tn, 1, 0);
+                                                                            shift_of(c, false), semi.p, cat.p, P, Tn, 1, 0,
+                                                                            l0_fast ? l0_planes[0][0] : nullptr,
+                                                                            l0_fast ? l0_planes[0][1] : nullptr);
           AKE_LAUNCHED();
         }
         tap("l0.semi", semi);
@@ -636,6 +647,49 @@ void Fwd::run(const float* mel, float* key_out, float* tonic_out, float* genre_o
       }
     }
     if (umma_pc_ready && L == 1) continue;
+    if (L == 0 && l0_fast) {
+      // PitchClass2PitchClass stack of layer 0 on tensor cores (pc8_umma_kernel): planes -> planes -> planes -> fp32 pc
+      View out = alloc(lp.out_pc, 12, Tn);
+      if (!dry) {
+        ProfScope prof("pcn.l0", st);
+        const int Wd = Tn + 6;
+        const size_t halves = (size_t)B * 23 * Wd * 8;
+        for (int i = 1; i < 3; ++i)  // zero halo columns of the intermediate planes = the "same" padding of the next conv
+          for (int j = 0; j < 2; ++j) AKE_CUDA(cudaMemsetAsync(l0_planes[i][j], 0, sizeof(__half) * halves, st));
+        const int n_tt = cdiv(Tn, kPc8MaxTB), TB8 = (cdiv(Tn, n_tt) + 1) / 2 * 2;
+        const size_t smem8 = pc8_smem_bytes(TB8 + 6);
+        static size_t c0 = 0, c2 = 0;
+        if (smem8 > c0) {
+          AKE_CUDA(cudaFuncSetAttribute(pc8_umma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
+          c0 = smem8;
+        }
+        if (smem8 > c2) {
+          AKE_CUDA(cudaFuncSetAttribute(pc8_umma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
+          c2 = smem8;
+        }
+        for (size_t i = 0; i < lp.pc2pc.size(); ++i) {
+          const Conv& c = p->convs[lp.pc2pc[i]];
+          const bool last = i + 1 == lp.pc2pc.size();
+          const int in = (int)(i % 3), nxt = (int)((i + 1) % 3);
+          Pc8Args pa{};
+          pa.in_hi = l0_planes[in][0], pa.in_lo = l0_planes[in][1], pa.Wd_in = Wd, pa.T_out = Tn, pa.TB = TB8;
+          pa.n_ttiles = cdiv(Tn, TB8), pa.n_tiles = pa.n_ttiles * B;
+          pa.wimg = reinterpret_cast<const __half*>(reinterpret_cast<const uint8_t*>(p->d_wimg_l0) + i * kPc8WBytes);
+          pa.scale = scale_of(c, false), pa.shift = shift_of(c, false), pa.Cout = c.Cout;
+          const int grid = std::min(pa.n_tiles, sm_count());
+          if (!last) {
+            pa.out_hi = l0_planes[nxt][0], pa.out_lo = l0_planes[nxt][1], pa.Wd_out = Wd;
+            pc8_umma_kernel<0><<<grid, kPc8Threads, smem8, st>>>(pa);
+          } else {
+            pa.out_f32 = out.p;
+            pc8_umma_kernel<2><<<grid, kPc8Threads, smem8, st>>>(pa);
+          }
+          AKE_LAUNCHED();
+        }
+      }
+      pc = out;
+      continue;
+    }
     // PitchClass2PitchClass stack (models.py:369 / 393), zero padding in time
     View a = alloc(lp.out_pc, 12, Tn), b2 = alloc(lp.out_pc, 12, Tn);
     View* src = &cat;
@@ -811,6 +865,16 @@ static void upload_params(ake_pcn* p, const float* flat_dev, int64_t n, cudaStre
                                                    reinterpret_cast<__half*>(reinterpret_cast<uint8_t*>(p->d_wimg) + i * kP2PWBytes));
       AKE_LAUNCHED();
     }
+    {
+      const std::vector<int>& l0 = p->layers[0].pc2pc;
+      if (!p->d_wimg_l0) AKE_CUDA(cudaMalloc(&p->d_wimg_l0, (size_t)kPc8WBytes * l0.size()));
+      for (size_t i = 0; i < l0.size(); ++i) {
+        const Conv& c = p->convs[l0[i]];
+        pc8_pack_weights_kernel<<<21, 256, 0, st>>>(p->d_params + c.w_off, c.Cout, c.Cin,
+                                                     reinterpret_cast<__half*>(reinterpret_cast<uint8_t*>(p->d_wimg_l0) + i * kPc8WBytes));
+        AKE_LAUNCHED();
+      }
+    }
     const std::vector<int>& pcs = p->layers[1].pc2pc;
     if (!p->d_wimg_pc) AKE_CUDA(cudaMalloc(&p->d_wimg_pc, (size_t)kPcWBytes * pcs.size()));
     for (size_t i = 0; i < pcs.size(); ++i) {
@@ -941,6 +1005,7 @@ void ake_pcn_destroy(ake_pcn* p) {
   cudaFree(p->d_ss_raw);
   cudaFree(p->d_wimg);
   cudaFree(p->d_wimg_pc);
+  cudaFree(p->d_wimg_l0);
   cudaFree(p->d_wimg_heads);
   cudaFree(p->d_ss_heads);
   cudaFree(p->d_wimg_genre);

@@ -12,6 +12,8 @@
 // K = Cin*KH*KW products in the same order (ci, dr, dt ascending) with the same instructions no matter
 // which row it is; rows only enter through load addresses (mod rows); no atomics are used.
 #pragma once
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace ake {
@@ -325,7 +327,8 @@ __global__ void octmax_kernel(const float* __restrict__ in, int B, int C, int R,
 __global__ void __launch_bounds__(128) l0_semitone_pool_kernel(const float* __restrict__ mel, const float* __restrict__ w,
                                                                 const float* __restrict__ scale, const float* __restrict__ shift,
                                                                 float* __restrict__ semi, float* __restrict__ pc, int P, int T,
-                                                                int C_total, int coff) {
+                                                                int C_total, int coff, __half* __restrict__ pl_hi = nullptr,
+                                                                __half* __restrict__ pl_lo = nullptr) {
   const int t = blockIdx.x * 128 + threadIdx.x, c = blockIdx.y, b = blockIdx.z;
   if (t >= T) return;
   const int tm = t == 0 ? T - 1 : t - 1, tp = t == T - 1 ? 0 : t + 1;
@@ -350,6 +353,22 @@ __global__ void __launch_bounds__(128) l0_semitone_pool_kernel(const float* __re
     best = fmaxf(best, v);
   }
   pc[(((long long)b * C_total + coff) * 12 + c) * T + t] = best;
+  if (pl_hi) {
+    // the same map as 8-channel chunk planes [B][23][T + 6][8] (channel 0 only) for the tensor-core equivariant convs:
+    // column t + 3, wrap rows 12..22 = rows 0..10, zero halo columns (the "same" padding in time)
+    const __half h = __float2half_rn(best), l = __float2half_rn(best - __half2float(h));
+    const uint4 hv = make_uint4((uint32_t)__half_as_ushort(h), 0, 0, 0), lv = make_uint4((uint32_t)__half_as_ushort(l), 0, 0, 0);
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    const int Wd = T + 6;
+    for (int row = c; row < 23; row += 12) {
+      const long long q = ((long long)b * 23 + row) * Wd;
+      reinterpret_cast<uint4*>(pl_hi)[q + t + 3] = hv, reinterpret_cast<uint4*>(pl_lo)[q + t + 3] = lv;
+      if (t < 3) {
+        reinterpret_cast<uint4*>(pl_hi)[q + t] = z, reinterpret_cast<uint4*>(pl_lo)[q + t] = z;
+        reinterpret_cast<uint4*>(pl_hi)[q + T + 3 + t] = z, reinterpret_cast<uint4*>(pl_lo)[q + T + 3 + t] = z;
+      }
+    }
+  }
 }
 
 // ---- train-mode BatchNorm pieces (batch statistics over (B, rows, T) per channel) ---------------

@@ -1009,6 +1009,242 @@ __global__ void __launch_bounds__(kPcThreads, 1) pc2pc_umma_kernel(const Pc2PcAr
   if (warp == 4 * G + 1) tmem_dealloc(tmem, 512);
 }
 
+// ---- narrow equivariant pitch-class convolutions (<= 8 -> <= 8 channels: the layer-0 PitchClass2PitchClass stack) ------------
+// models.py:22-51, 191-197 with 1 -> 4 -> 4 -> 4 channels.  One channel group, so the K = 16 of an MMA holds [x_hi | x_lo]
+// (as in p2p_umma_kernel) and ONE MMA per row tap does all three products: N = 112 = 7 phases x {W_hi 8, W_lo 8}, 12 row taps
+// = 720 MMA cycles per 122 anchors.  Persistent CTA per SM, resident weights (43 KB), double-buffered tiles, 4 epilogue groups.
+// EPI 0: BN + LeakyReLU -> chunk planes with wrap rows (next conv);  EPI 2: -> fp32 (B, Cout, 12, T).
+constexpr int kPc8Groups = 4;
+constexpr int kPc8Threads = 32 * (4 * kPc8Groups + 2);
+constexpr uint32_t kPc8WBytes = 12 * 2 * 112 * 16;
+constexpr int kPc8MaxTB = 76;
+
+// [dp 12][chunk 2][n 112][ci 8]: n = 16 f + j; j < 8: W_hi of output channel j, j >= 8: W_lo; both chunks hold the same weights
+__global__ void pc8_pack_weights_kernel(const float* __restrict__ w, int Cout, int Cin, __half* __restrict__ img) {
+  const int n_items = 12 * 56 * 8;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_items; i += gridDim.x * blockDim.x) {
+    const int ci = i % 8, fc = (i / 8) % 56, dp = i / 448;
+    const int f = fc / 8, co = fc % 8;
+    float v = 0.f;
+    if (ci < Cin && co < Cout) v = w[(((long long)co * Cin + ci) * 12 + dp) * 7 + f] * kWScale;
+    const __half hi = __float2half_rn(v);
+    const __half lo = __float2half_rn(v - __half2float(hi));
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      img[((dp * 2 + c) * 112 + 16 * f + co) * 8 + ci] = hi;
+      img[((dp * 2 + c) * 112 + 16 * f + 8 + co) * 8 + ci] = lo;
+    }
+  }
+}
+
+struct Pc8Args {
+  const __half* in_hi;
+  const __half* in_lo;   // [B][23][Wd_in][8]: zero halo columns (3 each side), wrap rows 12..22
+  int Wd_in, T_out, TB, n_ttiles, n_tiles;
+  const __half* wimg;    // pc8_pack_weights_kernel image (kPc8WBytes)
+  const float* scale;    // Cout: eval-mode BN scale (the 1/kWScale factor is applied in the kernel)
+  const float* shift;
+  int Cout;
+  __half* out_hi;
+  __half* out_lo;        // EPI 0: [B][23][Wd_out][8] written at column t + 3
+  int Wd_out;
+  float* out_f32;        // EPI 2: (B, Cout, 12, T_out)
+};
+
+__host__ __device__ inline uint32_t pc8_plane_positions(int Wt) { return (uint32_t)(23 * Wt + 136); }
+__host__ __device__ inline size_t pc8_smem_bytes(int Wt) {
+  return (size_t)2 * 2 * pc8_plane_positions(Wt) * 16 + kPc8WBytes + kPc8Groups * kP2PPubBytes;
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(kPc8Threads, 1) pc8_umma_kernel(const Pc8Args a) {
+  using namespace umma;
+  constexpr int G = kPc8Groups;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t w_bar, full_bar[2], empty_bar[2], acc_full[G], acc_empty[G];
+  __shared__ uint32_t tmem_slot;
+  __shared__ float s_scale[8], s_shift[8];
+
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
+  const int Wt = a.TB + 6;
+  const uint32_t plane = pc8_plane_positions(Wt) * 16;  // a tile buffer holds [hi][lo]
+  uint8_t* s_w = smem + 4 * plane;
+  uint8_t* s_pub = s_w + kPc8WBytes;
+  const int n_anchor = 12 * Wt;
+  const int n_mb = (n_anchor + kP2PStride - 1) / kP2PStride;
+  const uint32_t ntt_magic = 0xFFFFFFFFu / (uint32_t)a.n_ttiles + 1;
+  auto clip_of = [&](int tile) { return a.n_ttiles == 1 ? tile : (int)__umulhi((uint32_t)tile, ntt_magic); };
+
+  if (warp == 4 * G + 1) tmem_alloc(&tmem_slot, 128 * G);
+  if (threadIdx.x == 0) {
+    mbar_init(&w_bar, 1);
+    for (int i = 0; i < 2; ++i) mbar_init(&full_bar[i], 1), mbar_init(&empty_bar[i], 1);
+    for (int i = 0; i < G; ++i) mbar_init(&acc_full[i], 1), mbar_init(&acc_empty[i], 128);
+    mbar_init_fence();
+  }
+  if (threadIdx.x < 8) {
+    const bool on = (int)threadIdx.x < a.Cout;
+    s_scale[threadIdx.x] = on ? a.scale[threadIdx.x] * (1.f / kWScale) : 0.f, s_shift[threadIdx.x] = on ? a.shift[threadIdx.x] : 0.f;
+  }
+  // positions the bulk copies never write only feed discarded anchors; give them finite values once
+  for (uint32_t i = threadIdx.x; i < 4 * plane / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+
+  if (warp == 4 * G) {
+    // ------------------------------------------------------------ loader
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&w_bar, kPc8WBytes);
+      bulk_g2s(s_w, a.wimg, kPc8WBytes, &w_bar);
+    }
+    int k = 0;
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++k) {
+      const int s = k & 1;
+      const int b = clip_of(tile), t0 = (tile - b * a.n_ttiles) * a.TB;
+      const int cols_in = min(Wt, a.Wd_in - t0);
+      const uint32_t row_bytes = (uint32_t)cols_in * 16;
+      mbar_wait_relaxed(&empty_bar[s], ((k >> 1) & 1) ^ 1);
+      if (lane == 0) mbar_arrive_expect_tx(&full_bar[s], 46u * row_bytes);
+      __syncwarp();
+      uint8_t* dst = smem + (size_t)s * 2 * plane;
+      if (lane < 23) {
+        const long long src = (((long long)b * 23 + lane) * a.Wd_in + t0) * 8;
+        bulk_g2s(dst + (size_t)lane * Wt * 16, a.in_hi + src, row_bytes, &full_bar[s]);
+        bulk_g2s(dst + plane + (size_t)lane * Wt * 16, a.in_lo + src, row_bytes, &full_bar[s]);
+      }
+    }
+  } else if (warp == 4 * G + 1) {
+    // ------------------------------------------------------------ MMA issuer (converged warp, one elected lane issues)
+    const uint64_t A_DESC = desc_hi(plane);         // chunk 1 = the x_lo plane at the same position
+    constexpr uint64_t B_DESC = desc_hi(112 * 16);
+    constexpr uint32_t IDESC = idesc_f16(112);
+    const uint32_t w0 = smem_u32(s_w);
+    mbar_wait(&w_bar, 0);
+    int k = 0;
+    uint32_t j = 0;
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++k) {
+      const int s = k & 1;
+      const uint32_t hi0 = smem_u32(smem + (size_t)s * 2 * plane);
+      mbar_wait(&full_bar[s], (k >> 1) & 1);
+      for (int m = 0; m < n_mb; ++m, ++j) {
+        const uint32_t buf = j % G;
+        mbar_wait(&acc_empty[buf], ((j / G) & 1) ^ 1);
+        fence_after_sync();
+        const uint32_t d = tmem + buf * 128;
+        const uint32_t a_off = hi0 + (uint32_t)(m * kP2PStride) * 16;
+        if (elect_one()) {
+#pragma unroll
+          for (int dp = 0; dp < 12; ++dp)
+            mma_f16(d, make_desc(A_DESC, a_off + (uint32_t)(dp * Wt) * 16), make_desc(B_DESC, w0 + dp * (2 * 112 * 16)), IDESC, dp ? 1u : 0u);
+          commit(&acc_full[buf]);
+          if (m == n_mb - 1) commit(&empty_bar[s]);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue (as p2p_umma_kernel): thread = TMEM lane = anchor row
+    const int grp = warp >> 2, wq = warp & 3, tid = threadIdx.x & 127;
+    const uint32_t acc = tmem + ((uint32_t)(wq * 32) << 16) + grp * 128;
+    float4* pub = reinterpret_cast<float4*>(s_pub + grp * kP2PPubBytes);
+    const uint32_t wt_magic = 0xFFFFFFFFu / (uint32_t)Wt + 1;
+    uint64_t sc2[4], sh2[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) sc2[e] = f2_pack(s_scale[2 * e], s_scale[2 * e + 1]), sh2[e] = f2_pack(s_shift[2 * e], s_shift[2 * e + 1]);
+    uint32_t n_done = 0;
+    uint32_t j = grp, j0 = 0;
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+      const int b = clip_of(tile), t0 = (tile - b * a.n_ttiles) * a.TB;
+      const int TBv = min(a.TB, a.T_out - t0);
+      for (; j < j0 + n_mb; j += G, ++n_done) {
+        const int m = (int)(j - j0);
+        mbar_wait_relaxed(&acc_full[grp], n_done & 1);
+        fence_after_sync();
+        float4* pub_w = pub + (n_done & 1) * (3 * 21 * 2);
+        uint64_t o[4];
+        uint32_t r[2][16];
+        tmem_ld16_issue(acc, r[0]);
+#pragma unroll
+        for (int f = 0; f < 7; ++f) {
+          uint32_t(&v)[16] = r[f & 1];
+          tmem_ld_wait16(v);
+          if (f < 6) tmem_ld16_issue(acc + 16 * (f + 1), r[(f + 1) & 1]);
+          uint64_t u[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            u[e] = f2_add(f2_pack(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1])),
+                          f2_pack(__uint_as_float(v[8 + 2 * e]), __uint_as_float(v[9 + 2 * e])));
+          if (f == 0) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) o[e] = u[e];
+          } else {
+            float x[8];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) f2_unpack(u[e], x[2 * e], x[2 * e + 1]);
+            if (wq > 0 && lane < f) {
+              float4* dst = pub_w + ((wq - 1) * 21 + f * (f - 1) / 2 + lane) * 2;
+              dst[0] = make_float4(x[0], x[1], x[2], x[3]), dst[1] = make_float4(x[4], x[5], x[6], x[7]);
+            }
+#pragma unroll
+            for (int c = 0; c < 8; ++c) x[c] = __shfl_down_sync(0xffffffffu, x[c], f);
+            const float mk = (lane + f < 32) ? 1.f : 0.f;
+            const uint64_t mk2 = f2_pack(mk, mk);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) o[e] = f2_fma(f2_pack(x[2 * e], x[2 * e + 1]), mk2, o[e]);
+          }
+        }
+        fence_before_sync();
+        mbar_arrive(&acc_empty[grp]);
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+        if (wq < 3 && lane >= 26) {
+#pragma unroll
+          for (int f = 1; f < 7; ++f) {
+            const bool take = lane + f >= 32;
+            const float4* src = pub_w + (wq * 21 + f * (f - 1) / 2 + (take ? lane + f - 32 : 0)) * 2;
+            const float4 x0 = src[0], x1 = src[1];
+            const float mk = take ? 1.f : 0.f;
+            const uint64_t mk2 = f2_pack(mk, mk);
+            o[0] = f2_fma(f2_pack(x0.x, x0.y), mk2, o[0]), o[1] = f2_fma(f2_pack(x0.z, x0.w), mk2, o[1]);
+            o[2] = f2_fma(f2_pack(x1.x, x1.y), mk2, o[2]), o[3] = f2_fma(f2_pack(x1.z, x1.w), mk2, o[3]);
+          }
+        }
+        const int anchor = m * kP2PStride + tid;
+        if (tid < kP2PStride && anchor < n_anchor) {
+          const int c = (int)__umulhi((uint32_t)anchor, wt_magic), tl = anchor - c * Wt;
+          if (tl < TBv) {
+            float y[8];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              f2_unpack(f2_fma(o[e], sc2[e], sh2[e]), y[2 * e], y[2 * e + 1]);
+              y[2 * e] = fmaxf(y[2 * e], kLeakySlope * y[2 * e]), y[2 * e + 1] = fmaxf(y[2 * e + 1], kLeakySlope * y[2 * e + 1]);
+            }
+            const int t = t0 + tl;
+            if constexpr (EPI == 0) {
+              const long long q0 = (((long long)b * 23 + c) * a.Wd_out + t + 3) * 8;
+              store_split8(a.out_hi + q0, a.out_lo + q0, y);
+              if (c < 11) {  // wrap rows 12..22 = rows 0..10 (models.py:27-28)
+                const long long wr = (long long)12 * a.Wd_out * 8;
+                store_split8(a.out_hi + q0 + wr, a.out_lo + q0 + wr, y);
+              }
+            } else {
+#pragma unroll
+              for (int co = 0; co < 8; ++co)
+                if (co < a.Cout) a.out_f32[(((long long)b * a.Cout + co) * 12 + c) * a.T_out + t] = y[co];
+            }
+          }
+        }
+      }
+      j0 += n_mb;
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 4 * G + 1) tmem_dealloc(tmem, 128 * G);
+}
+
 // ---- last convolution of the classifier heads on tensor cores (models.py:716-733: 32 -> 1 channel, valid in time) -----
 //   out[c, t] = bias + sum_{ci<32, dp<KH, dt<7} W[ci, dp, dt] x[ci, c + dp, t + dt]     (rows wrap for tonic / key: 23-row planes)
 // One output channel would leave the MMA's N idle, so the 7 time taps are the N-phases:
