@@ -678,10 +678,11 @@ struct BankArgs {
 };
 
 constexpr uint32_t kBankLBO = 129 * 16;                  // chunk pitch of the frame operand: odd multiple of 16 B (conflict-free 8-byte scatter)
-constexpr uint32_t kBankAHalf = (kUKB / 8) * kBankLBO;   // one of {hi, lo}: 8 chunks x 128 rows x 16 B (+ pad)
+constexpr uint32_t kBankAHalf = (kUKB / 8) * kBankLBO;
+constexpr int kBankThreads = 288;                         // 8 producer warps (0-3 also run the epilogue) + the MMA-issuer warp   // one of {hi, lo}: 8 chunks x 128 rows x 16 B (+ pad)
 
 template <int NPAD>
-__global__ void __launch_bounds__(160) cqt_bank_umma_kernel(const BankArgs a) {
+__global__ void __launch_bounds__(kBankThreads) cqt_bank_umma_kernel(const BankArgs a) {
   using namespace umma;
   constexpr uint32_t A_HALF = kBankAHalf;
   constexpr uint32_t B_BYTES = (kUKB / 8) * 2 * NPAD * 16;   // 8 chunks x 2*NPAD rows x 16 B
@@ -698,9 +699,9 @@ __global__ void __launch_bounds__(160) cqt_bank_umma_kernel(const BankArgs a) {
   const long long m0 = (long long)blockIdx.x * 128;
   const int n_kb = a.n_fft / kUKB;
 
-  if (warp == 4) tmem_alloc(&tmem_slot, TMEM_COLS);
+  if (warp == 8) tmem_alloc(&tmem_slot, TMEM_COLS);
   if (tid == 0) {
-    for (int s = 0; s < kUStages; ++s) mbar_init(&full_bar[s], 128), mbar_init(&empty_bar[s], 1);
+    for (int s = 0; s < kUStages; ++s) mbar_init(&full_bar[s], 256), mbar_init(&empty_bar[s], 1);
     mbar_init(&done_bar, 1);
     mbar_init_fence();
   }
@@ -728,11 +729,12 @@ __global__ void __launch_bounds__(160) cqt_bank_umma_kernel(const BankArgs a) {
   fence_after_sync();
   const uint32_t tmem = tmem_slot;
 
-  if (warp < 4) {
-    // ---------------------------------------------------------------- producer
-    // A warp stages 32 frame rows; one instruction covers two rows x 64 samples: lanes 0-15 read the 16 float4s of one row,
-    // lanes 16-31 those of the next (coalesced 256-byte runs), convert to fp16 hi/lo and scatter 8-byte halves of the
-    // operand chunks (chunk c of row r at c * kBankLBO + r * 16).
+  if (warp < 8) {
+    // ---------------------------------------------------------------- producer (8 warps: twice the loads in flight per SM)
+    // Warps w and w + 4 stage the same 32 frame rows, 8 of the 16 row pairs each; one instruction covers two rows x 64
+    // samples: lanes 0-15 read the 16 float4s of one row, lanes 16-31 those of the next (coalesced 256-byte runs), convert to
+    // fp16 hi/lo and scatter 8-byte halves of the operand chunks (chunk c of row r at c * kBankLBO + r * 16).
+    const int pw = warp & 3, it0 = 8 * (warp >> 2);
     const float* level = a.level[octave];
     const int f = lane & 15;
     const uint64_t ss = f2_pack(kXScale, kXScale);
@@ -740,11 +742,11 @@ __global__ void __launch_bounds__(160) cqt_bank_umma_kernel(const BankArgs a) {
     // first block) and a 2-bit class live in registers.  Class 0: the whole frame exists and the pointer is 16-byte aligned
     // (one vector load); 1: the whole frame exists (four scalar loads); 2: centred-frame zero padding or the clip's end
     // cuts the frame (per-sample predicates).
-    const float* rowp[16];
+    const float* rowp[8];
     uint32_t cls = 0;
 #pragma unroll
-    for (int it = 0; it < 16; ++it) {
-      const int r = warp * 32 + 2 * it + (lane >> 4);
+    for (int it = 0; it < 8; ++it) {
+      const int r = pw * 32 + 2 * (it0 + it) + (lane >> 4);
       const int2 v = s_valid[r];
       rowp[it] = level + s_g0[r] + 4 * f;
       const uint32_t c = (v.x == 0 && v.y == a.n_fft) ? (((reinterpret_cast<uintptr_t>(rowp[it]) & 15) == 0) ? 0u : 1u) : 2u;
@@ -761,9 +763,9 @@ __global__ void __launch_bounds__(160) cqt_bank_umma_kernel(const BankArgs a) {
       }
       const int i0 = kb * kUKB + 4 * f;  // frame-local index of this lane's first sample
       // all 16 loads are issued before the first conversion consumes one
-      float4 x[16];
+      float4 x[8];
 #pragma unroll
-      for (int it = 0; it < 16; ++it) {
+      for (int it = 0; it < 8; ++it) {
         const float* src = rowp[it] + kb * kUKB;
         const uint32_t c = (cls >> (2 * it)) & 3u;
         if (c == 0) {
@@ -771,27 +773,28 @@ __global__ void __launch_bounds__(160) cqt_bank_umma_kernel(const BankArgs a) {
         } else if (c == 1) {
           x[it] = make_float4(__ldg(src), __ldg(src + 1), __ldg(src + 2), __ldg(src + 3));
         } else {
-          const int2 v = s_valid[warp * 32 + 2 * it + (lane >> 4)];
+          const int2 v = s_valid[pw * 32 + 2 * (it0 + it) + (lane >> 4)];
           x[it].x = (i0 + 0 >= v.x && i0 + 0 < v.y) ? __ldg(src + 0) : 0.f;
           x[it].y = (i0 + 1 >= v.x && i0 + 1 < v.y) ? __ldg(src + 1) : 0.f;
           x[it].z = (i0 + 2 >= v.x && i0 + 2 < v.y) ? __ldg(src + 2) : 0.f;
           x[it].w = (i0 + 3 >= v.x && i0 + 3 < v.y) ? __ldg(src + 3) : 0.f;
         }
       }
-      const uint32_t off0 = (uint32_t)(f >> 1) * kBankLBO + (uint32_t)(warp * 32 + (lane >> 4)) * 16 + (uint32_t)(f & 1) * 8;
+      const uint32_t off0 = (uint32_t)(f >> 1) * kBankLBO + (uint32_t)(pw * 32 + 2 * it0 + (lane >> 4)) * 16 + (uint32_t)(f & 1) * 8;
 #pragma unroll
-      for (int it = 0; it < 16; ++it) {
+      for (int it = 0; it < 8; ++it) {
         uint32_t h0, l0, h1, l1;
         cas_split2(f2_mul(f2_pack(x[it].x, x[it].y), ss), h0, l0);
         cas_split2(f2_mul(f2_pack(x[it].z, x[it].w), ss), h1, l1);
-        const uint32_t off = off0 + 32u * it;  // row r = warp * 32 + 2 it + (lane >> 4)
+        const uint32_t off = off0 + 32u * it;  // row r = pw * 32 + 2 (it0 + it) + (lane >> 4)
         *reinterpret_cast<uint2*>(stage + off) = make_uint2(h0, h1);
         *reinterpret_cast<uint2*>(stage + A_HALF + off) = make_uint2(l0, l1);
       }
       fence_proxy_async();
       if (tid != 0) mbar_arrive(&full_bar[s]);
     }
-    // ---------------------------------------------------------------- epilogue: TMEM lane `tid` = frame row `tid`
+    // ---------------------------------------------------------------- epilogue (warps 0-3): TMEM lane `tid` = frame row `tid`
+    if (warp < 4) {
     mbar_wait_relaxed(&done_bar, 0);
     fence_after_sync();
     const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
@@ -816,6 +819,7 @@ __global__ void __launch_bounds__(160) cqt_bank_umma_kernel(const BankArgs a) {
           reinterpret_cast<float2*>(a.out)[((long long)b * a.n_bins + bin) * a.T_max + t] = make_float2(re, im);
         }
       }
+    }
     }
   } else {
     // ---------------------------------------------------------------- MMA issuer (converged warp, one elected lane issues)
@@ -842,7 +846,7 @@ __global__ void __launch_bounds__(160) cqt_bank_umma_kernel(const BankArgs a) {
   }
   fence_before_sync();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem, TMEM_COLS);
+  if (warp == 8) tmem_dealloc(tmem, TMEM_COLS);
 }
 
 __global__ void cqt_seqlen_kernel(const long long* __restrict__ lengths, long long n_uniform, int B, int n_oct, int hop0,
@@ -936,7 +940,7 @@ static void run_cqt(ake_cqt* p, const float* audio, long long stride, const int6
         AKE_CUDA(cudaFuncSetAttribute(cqt_bank_umma_kernel<80>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
       }
-      cqt_bank_umma_kernel<80><<<grid, 160, smem, st>>>(ba);
+      cqt_bank_umma_kernel<80><<<grid, kBankThreads, smem, st>>>(ba);
     } else {
       constexpr size_t smem = kUStages * (2 * kBankAHalf + (kUKB / 8) * 2 * 32 * 16);
       static bool configured = false;
@@ -944,7 +948,7 @@ static void run_cqt(ake_cqt* p, const float* audio, long long stride, const int6
         AKE_CUDA(cudaFuncSetAttribute(cqt_bank_umma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
       }
-      cqt_bank_umma_kernel<32><<<grid, 160, smem, st>>>(ba);
+      cqt_bank_umma_kernel<32><<<grid, kBankThreads, smem, st>>>(ba);
     }
     AKE_LAUNCHED();
   } else {
