@@ -48,6 +48,9 @@ _SIGNATURES = {
     "ake_pcn_get_config": (C.c_int, [_P, C.POINTER(PcnConfig)]),
     "ake_pcn_get_tap": (C.c_int64, [_P, C.c_char_p, _P, C.c_int64, _P]),
     "ake_decode_f32": (C.c_int, [_P, _P, _P, C.c_int, _P, _P, _P, _P]),
+    "ake_mirex_f32": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, _P, _P, _P, _P]),
+    "ake_adam_step_f32": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
+                                    C.c_float, C.c_int, _P]),
     "ake_cqt_create": (C.c_int, [C.c_double, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double,
                                  C.POINTER(_P)]),
     "ake_cqt_destroy": (None, [_P]),

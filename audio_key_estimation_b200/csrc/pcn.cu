@@ -1139,4 +1139,34 @@ int ake_decode_f32(const float* key_out_dev, const float* tonic_out_dev, const f
   });
 }
 
+int ake_mirex_f32(const float* key_out_dev, const float* tonic_out_dev, const float* key_labels_dev,
+                  const float* tonic_labels_dev, const float* key_signature_id_dev, int B, uint64_t* counters_dev,
+                  float* similarity_out_dev, int32_t* category_out_dev, void* stream) {
+  return guarded([&] {
+    if (B <= 0) fail(AKE_ERR_INVALID, "B must be positive");
+    if (!key_out_dev || !tonic_out_dev || !key_labels_dev || !tonic_labels_dev || !key_signature_id_dev || !counters_dev)
+      fail(AKE_ERR_INVALID, "null argument");
+    static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "counter width");
+    mirex_kernel<<<cdiv(B, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        key_out_dev, tonic_out_dev, key_labels_dev, tonic_labels_dev, key_signature_id_dev, B,
+        reinterpret_cast<unsigned long long*>(counters_dev), similarity_out_dev, category_out_dev);
+    AKE_LAUNCHED();
+  });
+}
+
+int ake_adam_step_f32(const float* flat_grads_dev, float* m_flat_dev, float* v_flat_dev, float* const* param_ptrs_dev,
+                      const int64_t* offsets_dev, int n_tensors, int64_t total, float lr, float beta1, float beta2, float eps,
+                      float weight_decay, float grad_scale, int step, void* stream) {
+  return guarded([&] {
+    if (!flat_grads_dev || !m_flat_dev || !v_flat_dev || !param_ptrs_dev || !offsets_dev) fail(AKE_ERR_INVALID, "null argument");
+    if (n_tensors <= 0 || total <= 0 || step < 1) fail(AKE_ERR_INVALID, "n_tensors, total and step must be positive");
+    static_assert(sizeof(long long) == sizeof(int64_t), "offset width");
+    AdamArgs a{flat_grads_dev, m_flat_dev, v_flat_dev, param_ptrs_dev, reinterpret_cast<const long long*>(offsets_dev), n_tensors,
+               (long long)total, lr, beta1, beta2, eps, weight_decay, grad_scale,
+               (float)(1.0 - std::pow((double)beta1, step)), (float)std::sqrt(1.0 - std::pow((double)beta2, step))};
+    adam_step_kernel<<<ew_blocks(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    AKE_LAUNCHED();
+  });
+}
+
 }  // extern "C"

@@ -543,6 +543,62 @@ __global__ void decode_kernel(const float* __restrict__ key_out, const float* __
   }
 }
 
+// ---- MIREX-weighted key score (models.py:1065-1116): per-clip category + batch counters ----------
+// counters[9] (accumulated): samples, correct, fifths, relative, parallel, other, all 12 key bits right ("accuracy"),
+// correct tonics, key bits right.  One thread per clip; the categories follow the reference's if-chain (first match wins).
+__global__ void __launch_bounds__(128) mirex_kernel(const float* __restrict__ key_out, const float* __restrict__ tonic_out,
+                                                    const float* __restrict__ key_labels, const float* __restrict__ tonic_labels,
+                                                    const float* __restrict__ key_sig_id, int B, unsigned long long* __restrict__ counters,
+                                                    float* __restrict__ sim_out, int* __restrict__ cat_out) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned int c[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  if (b < B) {
+    float k[12], lab[12], nk = 0.f, nl = 0.f, dot = 0.f;
+    for (int i = 0; i < 12; ++i) {
+      k[i] = key_out[b * 12 + i], lab[i] = key_labels[b * 12 + i];
+      nk = fmaf(k[i], k[i], nk), nl = fmaf(lab[i], lab[i], nl), dot = fmaf(k[i], lab[i], dot);
+    }
+    // argmax_r cos(key_out, MAP[r]) exactly as decode_kernel
+    const float inv = 1.f / (fmaxf(sqrtf(nk), 1e-8f) * sqrtf(7.f));
+    int pred = 0;
+    float bv = -INFINITY;
+    for (int r = 0; r < 21; ++r) {
+      float d = 0.f;
+      for (int i = 0; i < 12; ++i)
+        if ((kKeySignatureBits[r] >> (11 - i)) & 1) d += k[i];
+      d *= inv;
+      if (d > bv) bv = d, pred = r;
+    }
+    int label = 0;
+    for (int r = 1; r < 21; ++r)
+      if (key_sig_id[b * 21 + r] > key_sig_id[b * 21 + label]) label = r;
+    int bits = 0;
+    for (int i = 0; i < 12; ++i) bits += (float)((kKeySignatureBits[pred] >> (11 - i)) & 1) == lab[i];
+    int tl = 0, tp = 0;
+    for (int i = 1; i < 12; ++i) {
+      if (tonic_labels[b * 12 + i] > tonic_labels[b * 12 + tl]) tl = i;
+      if (tonic_out[b * 12 + i] > tonic_out[b * 12 + tp]) tp = i;
+    }
+    const bool tonic_ok = tl == tp, keys_ok = bits == 12;
+    const int diff = abs(pred - label);
+    int cat;
+    if (diff == 1 && !(tonic_ok && keys_ok)) cat = 1;   // fifth
+    else if (tonic_ok && keys_ok) cat = 0;               // correct
+    else if (keys_ok) cat = 2;                           // relative
+    else if (tonic_ok) cat = 3;                          // parallel
+    else cat = 4;                                        // other
+    c[0] = 1, c[1 + cat] = 1, c[6] = keys_ok, c[7] = tonic_ok, c[8] = (unsigned)bits;
+    if (cat_out) cat_out[b] = cat;
+    if (sim_out) sim_out[b] = dot / (fmaxf(sqrtf(nk), 1e-8f) * fmaxf(sqrtf(nl), 1e-8f));  // nn.CosineSimilarity(dim=0), :1094
+  }
+#pragma unroll
+  for (int i = 0; i < 9; ++i) {
+    unsigned int v = c[i];
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(counters + i, (unsigned long long)v);
+  }
+}
+
 // ---- parameter preparation ---------------------------------------------------------------------
 // Repack a (Cout,Cin,KH,KW) conv weight to [Cin][KH][KW][cout_pad] (zero padded output channels).
 __global__ void pack_conv_kernel(const float* __restrict__ w, int Cout, int Cin, int KHW, int cout_pad,

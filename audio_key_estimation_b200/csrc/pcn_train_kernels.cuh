@@ -454,4 +454,41 @@ __global__ void loss_kernel(const float* __restrict__ key_out, const float* __re
   }
 }
 
+// ---- fused optimizer step (models.py:1017-1027: torch.optim.Adam(betas=(0.9, 0.999), lr, weight_decay=reg)) ----------
+// One launch over the flat gradient bucket: element i belongs to the tensor t with off[t] <= i < off[t + 1] (binary search
+// over the <= 64 tensor offsets); tensors without a parameter (running statistics) have a null pointer and are skipped.
+// torch.optim.Adam, single-tensor form: g += wd p; m = b1 m + (1 - b1) g; v = b2 v + (1 - b2) g^2;
+// p -= (lr / (1 - b1^t)) * m / (sqrt(v) / sqrt(1 - b2^t) + eps).
+struct AdamArgs {
+  const float* grads;          // flat, layout of the parameter buffer
+  float* m;
+  float* v;                    // flat moments, same layout
+  float* const* params;        // device table: parameter storage of every tensor (null: not trainable)
+  const long long* offsets;    // device table: n_tensors + 1 offsets into the flat buffers
+  int n_tensors;
+  long long total;
+  float lr, beta1, beta2, eps, weight_decay, grad_scale, bias1, bias2_sqrt;  // bias1 = 1 - b1^t, bias2_sqrt = sqrt(1 - b2^t)
+};
+
+__global__ void __launch_bounds__(256) adam_step_kernel(const AdamArgs a) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < a.total; i += (long long)gridDim.x * blockDim.x) {
+    int lo = 0, hi = a.n_tensors;  // offsets[lo] <= i < offsets[hi]
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (__ldg(a.offsets + mid) <= i) lo = mid;
+      else hi = mid;
+    }
+    float* p = a.params[lo];
+    if (!p) continue;
+    p += i - __ldg(a.offsets + lo);
+    const float w = *p;
+    const float g = fmaf(a.weight_decay, w, a.grads[i] * a.grad_scale);
+    const float m = a.beta1 * a.m[i] + (1.f - a.beta1) * g;   // m.lerp_(g, 1 - beta1) rounds this way
+    const float v = a.beta2 * a.v[i] + (1.f - a.beta2) * g * g;
+    a.m[i] = m, a.v[i] = v;
+    const float denom = sqrtf(v) / a.bias2_sqrt + a.eps;
+    *p = w - (a.lr / a.bias1) * (m / denom);
+  }
+}
+
 }  // namespace ake

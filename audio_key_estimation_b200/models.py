@@ -343,3 +343,41 @@ def decode(key_out: torch.Tensor, tonic_out: torch.Tensor, genre_out: Optional[t
         check(lib.ake_decode_f32(k.data_ptr(), t.data_ptr(), g.data_ptr() if g is not None else None, B,
                                  ids[0].data_ptr(), ids[1].data_ptr(), ids[2].data_ptr(), stream))
     return (ids[0], ids[1]) + ((ids[2],) if g is not None else ())
+
+
+MIREX_COUNTERS = ("samples", "correct", "fifths", "relative", "parallel", "other", "all_keys", "tonics", "key_bits")
+
+
+def mirex_counters(key_out: torch.Tensor, tonic_out: torch.Tensor, key_labels: torch.Tensor, tonic_labels: torch.Tensor,
+                   key_signature_id: torch.Tensor, counters: Optional[torch.Tensor] = None, return_details: bool = False):
+    """Category counters of the reference's ``mirex_score`` loop (models.py:1065-1116), computed on the device.
+
+    Returns an int64 tensor of 9 counters (``MIREX_COUNTERS``) on ``key_out.device``; pass ``counters`` to keep accumulating
+    over batches, and sum it over ranks with ``distributed.reduce_counters`` before ``mirex_from_counters``.  With
+    ``return_details`` also returns the per-clip cosine similarity (models.py:1094) and category ids."""
+    if not key_out.is_cuda:
+        raise RuntimeError("mirex_counters runs on CUDA tensors only")
+    lib = _lib.lib()
+    dev = key_out.device
+    B = key_out.shape[0]
+    f = lambda x: x.detach().to(device=dev, dtype=torch.float32).contiguous()  # noqa: E731
+    k, t, kl, tl, sid = f(key_out), f(tonic_out), f(key_labels), f(tonic_labels), f(key_signature_id)
+    if kl.shape != (B, 12) or tl.shape != (B, 12) or sid.shape != (B, 21) or t.shape != (B, 12) or k.shape != (B, 12):
+        raise ValueError("expected key/tonic outputs and labels of shape (B, 12) and key_signature_id of shape (B, 21)")
+    if counters is None:
+        counters = torch.zeros(len(MIREX_COUNTERS), dtype=torch.int64, device=dev)
+    sim = torch.empty(B, dtype=torch.float32, device=dev) if return_details else None
+    cat = torch.empty(B, dtype=torch.int32, device=dev) if return_details else None
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        check(lib.ake_mirex_f32(k.data_ptr(), t.data_ptr(), kl.data_ptr(), tl.data_ptr(), sid.data_ptr(), B, counters.data_ptr(),
+                                sim.data_ptr() if sim is not None else None, cat.data_ptr() if cat is not None else None, stream))
+    return (counters, sim, cat) if return_details else counters
+
+
+def mirex_from_counters(counters: torch.Tensor):
+    """(mirex, correct, fifths, relative, parallel, other, accuracy) exactly as models.py:1113-1115 returns them."""
+    c = [int(v) for v in counters.tolist()]
+    n = max(1, c[0])
+    mirex = 1.0 * c[1] + 0.5 * c[2] + 0.3 * c[3] + 0.2 * c[4]
+    return tuple(torch.tensor(v / n).float() for v in (mirex, c[1], c[2], c[3], c[4], c[5], c[6]))

@@ -4,7 +4,8 @@
 in train mode, whose backward runs in CUDA); ``TrainStep`` is the fused path: forward that keeps its
 activations -> ``ake_loss_f32`` -> ``ake_pcn_backward_f32`` -> ONE flat gradient buffer in the layout of
 the parameter buffer, which a data-parallel job all-reduces as a single bucket (distributed.allreduce_gradients)
-before the optimizer step.  The optimizer itself (Adam + ExponentialLR, models.py:1017-1027) stays torch's.
+before the optimizer step.  ``FusedAdam`` is the optimizer of models.py:1017-1027 (Adam + ExponentialLR) as one launch over
+that bucket; torch's own ``torch.optim.Adam`` keeps working on the per-parameter ``.grad`` views as well.
 """
 from __future__ import annotations
 
@@ -106,3 +107,67 @@ class TrainStep:
         """Point every parameter's .grad at its slice of the flat buffer (call again after an all-reduce in place)."""
         for prm, g in zip(self.net._grad_params(), self.net._split_flat_grads(self.flat_grads)):
             prm.grad = g
+
+
+class FusedAdam:
+    """models.py:1017-1027 on the flat gradient bucket: ``torch.optim.Adam(params, betas=(0.9, 0.999), lr=opt.lr,
+    weight_decay=opt.reg)`` + ``ExponentialLR(gamma=opt.gamma)`` (``epoch_end()`` = scheduler.step()), one kernel launch
+    per step (``ake_adam_step_f32``) instead of torch's per-tensor loop.  ``grad_scale`` folds in the 1/accumulate_grad_batches
+    of train_model.py:120 (or 1/world_size after a summing all-reduce)."""
+
+    def __init__(self, net: PitchClassNet, lr: Optional[float] = None, betas=(0.9, 0.999), eps: float = 1e-8,
+                 weight_decay: Optional[float] = None, gamma: Optional[float] = None):
+        self.net = net
+        self.lr0 = float(_opt(net.opt, "lr", 3e-4) if lr is None else lr)
+        self.weight_decay = float(_opt(net.opt, "reg", 0.0) if weight_decay is None else weight_decay)
+        self.gamma = float(_opt(net.opt, "gamma", 0.96) if gamma is None else gamma)
+        self.betas, self.eps = (float(betas[0]), float(betas[1])), float(eps)
+        self.epoch, self.t = 0, 0
+        self._m = self._v = self._ptrs = self._offsets = None
+
+    @property
+    def lr(self) -> float:
+        return self.lr0 * self.gamma ** self.epoch
+
+    def epoch_end(self) -> None:
+        self.epoch += 1
+
+    def _tables(self, dev):
+        net = self.net
+        ptrs, offs, off = [], [0], 0
+        for n in net._tensor_names:
+            t = net._lookup(n)
+            if isinstance(t, nn.Parameter):
+                if t.dtype != torch.float32 or not t.is_cuda or not t.is_contiguous():
+                    raise RuntimeError("FusedAdam updates contiguous float32 CUDA parameters in place")
+                ptrs.append(t.data_ptr())
+            else:
+                ptrs.append(0)
+            off += t.numel()
+            offs.append(off)
+        self._ptrs = torch.tensor(ptrs, dtype=torch.int64, device=dev)
+        self._offsets = torch.tensor(offs, dtype=torch.int64, device=dev)
+        self._key = tuple(ptrs)
+        return off
+
+    def step(self, flat_grads: torch.Tensor, grad_scale: float = 1.0) -> None:
+        if not flat_grads.is_cuda or flat_grads.dtype != torch.float32:
+            raise RuntimeError("FusedAdam runs on the float32 CUDA gradient bucket; there is no CPU fallback")
+        dev = flat_grads.device
+        net = self.net
+        cur = tuple(net._lookup(n).data_ptr() if isinstance(net._lookup(n), nn.Parameter) else 0 for n in net._tensor_names)
+        if self._ptrs is None or cur != self._key:
+            total = self._tables(dev)
+            if self._m is None:
+                self._m = torch.zeros(total, dtype=torch.float32, device=dev)
+                self._v = torch.zeros(total, dtype=torch.float32, device=dev)
+        if flat_grads.numel() != self._m.numel():
+            raise ValueError("gradient bucket does not match the parameter buffer layout")
+        self.t += 1
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            check(_lib.lib().ake_adam_step_f32(flat_grads.data_ptr(), self._m.data_ptr(), self._v.data_ptr(), self._ptrs.data_ptr(),
+                                               self._offsets.data_ptr(), len(net._tensor_names), self._m.numel(), self.lr,
+                                               self.betas[0], self.betas[1], self.eps, self.weight_decay, float(grad_scale), self.t,
+                                               stream))
+        net._param_key = None  # the kernel wrote the parameters behind torch's version counters: re-upload on the next forward

@@ -134,6 +134,26 @@ int64_t ake_pcn_get_tap(const ake_pcn* plan, const char* name, float* out_dev, i
 int ake_decode_f32(const float* key_out_dev, const float* tonic_out_dev, const float* genre_out_dev, int B,
                    int32_t* key_id_dev, int32_t* tonic_id_dev, int32_t* genre_id_dev, void* stream);
 
+/* Fused optimizer step of the reference's training loop (models.py:1017-1027: torch.optim.Adam(betas, lr, weight_decay=reg),
+ * the ExponentialLR factor folded into `lr` by the caller, accumulate_grad_batches folded into grad_scale): ONE launch over
+ * the flat gradient bucket ake_pcn_backward_f32 fills.  m/v are flat moment buffers in the same layout (zero them once);
+ * param_ptrs_dev[n_tensors] is a device table of the parameter storages in flat-buffer order (NULL: no parameter there,
+ * e.g. BatchNorm running statistics), offsets_dev[n_tensors + 1] their offsets into the flat buffers; step counts from 1. */
+int ake_adam_step_f32(const float* flat_grads_dev, float* m_flat_dev, float* v_flat_dev, float* const* param_ptrs_dev,
+                      const int64_t* offsets_dev, int n_tensors, int64_t total, float lr, float beta1, float beta2, float eps,
+                      float weight_decay, float grad_scale, int step, void* stream);
+
+/* MIREX-weighted key score of models.py:1065-1116 (mirex_score) on the device, one thread per clip: the reference's
+ * per-sample Python loop (cosine argmax against the 21-row table, 12-bit key comparison, tonic argmax, |signature id
+ * difference| == 1 -> "fifth") with its per-sample .cuda() upload of the table.  ACCUMULATES into counters_dev[9] =
+ * {samples, correct, fifths, relative, parallel, other, all-12-keys-right ("accuracy"), correct tonics, key bits right}
+ * (zero them first; sum them over ranks with one all-reduce); mirex = (1.0 correct + 0.5 fifths + 0.3 relative +
+ * 0.2 parallel) / samples.  similarity_out_dev (B, cos(key_out, key_label), models.py:1094) and category_out_dev
+ * (B, 0 correct / 1 fifth / 2 relative / 3 parallel / 4 other) may be NULL. */
+int ake_mirex_f32(const float* key_out_dev, const float* tonic_out_dev, const float* key_labels_dev,
+                  const float* tonic_labels_dev, const float* key_signature_id_dev, int B, uint64_t* counters_dev,
+                  float* similarity_out_dev, int32_t* category_out_dev, void* stream);
+
 /* ---------------------------------------------------------------- constant-Q front-end */
 
 /* librosa.cqt(y, sr, hop_length, fmin, n_bins, bins_per_octave, filter_scale, sparsity) with the other

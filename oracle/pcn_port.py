@@ -226,6 +226,49 @@ def decode(key_out: Tensor, tonic_out: Tensor, genre_out: Optional[Tensor] = Non
     return tuple(out)
 
 
+# --- MIREX-weighted key score (models.py:1065-1116, mirex_score) -----------------------------------
+MIREX_COUNTERS = ("samples", "correct", "fifths", "relative", "parallel", "other", "all_keys", "tonics", "key_bits")
+
+
+def mirex_counters(key_out: Tensor, tonic_out: Tensor, key_labels: Tensor, tonic_labels: Tensor, key_signature_id: Tensor):
+    """Per-batch category counts of the reference's per-sample loop (models.py:1070-1112) + per-clip cosine similarity
+    (models.py:1093).  Returns (dict of ints keyed by MIREX_COUNTERS, similarity (B,))."""
+    m = key_signature_map(key_out.dtype)
+    cnt = dict.fromkeys(MIREX_COUNTERS, 0)
+    sims = []
+    for i in range(key_out.shape[0]):
+        pred_id = int(F.cosine_similarity(key_out[i][None], m, dim=1).argmax())        # :1083-1084
+        key_pred = m[pred_id]                                                           # :1085
+        label_id = int(key_signature_id[i].argmax())                                   # :1086
+        correct_keys = int((key_pred == key_labels[i]).sum())                          # :1090
+        sims.append(F.cosine_similarity(key_out[i], key_labels[i], dim=0))             # :1094
+        diff = abs(pred_id - label_id)                                                 # :1095
+        correct_tonic = int(tonic_labels[i].argmax() == tonic_out[i].argmax())         # :1096
+        cnt["samples"] += 1
+        cnt["key_bits"] += correct_keys
+        cnt["all_keys"] += int(correct_keys == 12)
+        cnt["tonics"] += correct_tonic
+        if diff == 1 and not (correct_tonic == 1 and correct_keys == 12):              # :1100-1111, first match wins
+            cnt["fifths"] += 1
+        elif correct_tonic == 1 and correct_keys == 12:
+            cnt["correct"] += 1
+        elif correct_keys == 12 and correct_tonic == 0:
+            cnt["relative"] += 1
+        elif correct_tonic == 1 and correct_keys != 12:
+            cnt["parallel"] += 1
+        else:
+            cnt["other"] += 1
+    return cnt, torch.stack(sims)
+
+
+def mirex_from_counters(cnt) -> Tuple[float, ...]:
+    """(mirex, correct, fifths, relative, parallel, other, accuracy) as models.py:1113-1115 returns them."""
+    n = max(1, cnt["samples"])
+    mirex = 1.0 * cnt["correct"] + 0.5 * cnt["fifths"] + 0.3 * cnt["relative"] + 0.2 * cnt["parallel"]
+    return (mirex / n, cnt["correct"] / n, cnt["fifths"] / n, cnt["relative"] / n, cnt["parallel"] / n, cnt["other"] / n,
+            cnt["all_keys"] / n)
+
+
 def count_macs(sd: Dict[str, Tensor], pitches: int, T: int, time_pool_size: int = 2) -> int:
     """Algorithmic MACs of one clip's forward (out_elems * Cin * kh * kw per conv)."""
     total = 0

@@ -88,3 +88,44 @@ def test_unsupported_training_configs_fail_loudly(fwd_golden):
     mel = torch.from_numpy(fwd_golden["mel"])[:, None].cuda()
     with pytest.raises((NotImplementedError, ValueError)):
         net(mel, None)
+
+
+def test_fused_adam_matches_torch_adam():
+    """models.py:1017-1027: Adam(betas=(0.9, 0.999), lr, weight_decay=reg) + ExponentialLR(gamma).  The reference's optimizer
+    IS torch.optim.Adam, so the fused one-launch step is checked against it on the same gradients for several steps/epochs."""
+    import audio_key_estimation_b200 as ake
+
+    torch.manual_seed(3)
+    opt = ake.default_opt(genre=True)
+    opt.lr, opt.reg, opt.gamma = 3e-3, 1e-2, 0.9
+    net = ake.PitchClassNet(288, 12, 2, 7, opt=opt).cuda().train()
+    ref = ake.PitchClassNet(288, 12, 2, 7, opt=opt).cuda().train()
+    ref.load_state_dict(net.state_dict(), strict=True)
+    ref_params = ref._grad_params()
+    adam = torch.optim.Adam(ref_params, betas=(0.9, 0.999), lr=opt.lr, weight_decay=opt.reg)
+    sched = torch.optim.lr_scheduler.ExponentialLR(adam, gamma=opt.gamma)
+    fused = ake.FusedAdam(net)
+    n_flat = sum(net._lookup(n).numel() for n in net._tensor_names)
+    for step in range(6):
+        flat = torch.randn(n_flat, device="cuda") * 0.1
+        for p, g in zip(ref_params, ref._split_flat_grads(flat)):
+            p.grad = g.clone()
+        adam.step()
+        fused.step(flat)
+        if step % 2 == 1:
+            sched.step()
+            fused.epoch_end()
+    worst = 0.0
+    for a, b in zip(net._grad_params(), ref_params):
+        worst = max(worst, (a.detach() - b.detach()).abs().max().item() / max(1e-3, b.detach().abs().max().item()))
+    assert worst <= 2e-6, worst  # same formula in fp32; only the rounding of a few fused multiply-adds differs
+    # buffers (running statistics) are not parameters: untouched
+    for (n1, b1), (n2, b2) in zip(net.named_buffers(), ref.named_buffers()):
+        assert torch.equal(b1, b2), n1
+    # the next forward sees the updated parameters (the plan re-uploads them)
+    mel = torch.rand(2, 1, 288, 40, device="cuda")
+    net.eval(), ref.eval()
+    with torch.no_grad():
+        o1, o2 = net(mel, None), ref(mel, None)
+    for x, y in zip(o1, o2):
+        assert (x - y).abs().max().item() <= 1e-4
