@@ -7,7 +7,8 @@ thin Python host layer mirroring the reference's PyTorch-facing surface.
 from .models import PitchClassNet, decode, mirex_counters, mirex_from_counters  # noqa: F401
 from .cqt import CQTPlan, cqt, cqt_logmag  # noqa: F401
 from .pipeline import KeyEstimator  # noqa: F401
+from .cache import cache_name, write_cqt_cache  # noqa: F401
 from .options import default_opt  # noqa: F401
 from .training import FusedAdam, TrainStep, criterion  # noqa: F401
 
-__all__ = ["PitchClassNet", "decode", "mirex_counters", "mirex_from_counters", "CQTPlan", "cqt", "cqt_logmag", "KeyEstimator", "default_opt", "TrainStep", "FusedAdam", "criterion"]
+__all__ = ["PitchClassNet", "decode", "mirex_counters", "mirex_from_counters", "CQTPlan", "cqt", "cqt_logmag", "KeyEstimator", "cache_name", "write_cqt_cache", "default_opt", "TrainStep", "FusedAdam", "criterion"]

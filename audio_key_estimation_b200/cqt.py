@@ -102,7 +102,7 @@ def cqt(y: torch.Tensor, sr: float = 22050, hop_length: int = 512, fmin: Optiona
 
 
 def cqt_logmag(audio: Union[torch.Tensor, Sequence[torch.Tensor]], sr: float, frames: int = 5, octaves: int = 8,
-               lengths: Optional[Sequence[int]] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+               lengths: Optional[Sequence[int]] = None, bins_per_octave: int = 36) -> Tuple[torch.Tensor, torch.Tensor]:
     """The network input of KeyDataset.py:485-509 for a batch of clips, computed on the GPU.
 
     Returns ``mel`` (B, 1, 36*octaves, T_max) fp32, zero-padded beyond each clip's frames
@@ -116,5 +116,5 @@ def cqt_logmag(audio: Union[torch.Tensor, Sequence[torch.Tensor]], sr: float, fr
             batch[i, : a.numel()] = a.reshape(-1)
         audio = batch
     hop = round(sr / frames)
-    plan = CQTPlan.get(sr, hop, 36 * octaves, 36)
+    plan = CQTPlan.get(sr, hop, bins_per_octave * octaves, bins_per_octave)  # 12 per octave: opt.only_semitones (KeyDataset.py:493)
     return plan.run(audio, lengths=lengths, mode=_lib.CQT_LOGMAG)

@@ -83,3 +83,25 @@ def test_other_bank_shapes_and_errors():
     assert np.abs(got.cpu().numpy() - want).max() <= 2e-4 * np.abs(want).max()
     with pytest.raises(ValueError):
         ake.cqt(y, sr=44100, hop_length=8820, n_bins=288, bins_per_octave=36)
+
+
+def test_cache_writer_files_load_like_the_reference_expects(tmp_path):
+    """torch.load(name).shape[1] == 288 and the tensor is the (1, 288, T) float64 log-CQT (KeyDataset.py:182-185, 509)."""
+    import argparse
+
+    import audio_key_estimation_b200 as ake
+    from audio_key_estimation_b200 import cache, synth
+
+    opt = argparse.Namespace(octaves=8, frames=5, only_semitones=False)
+    sr = 48000
+    lens = [sr * 3, sr * 2 + 1234]
+    waves = [synth.synth_clip(40 + i, n, sr, "cpu") for i, n in enumerate(lens)]
+    paths = [str(tmp_path / "a.wav"), str(tmp_path / "sub.dir.mp3")]
+    written = ake.write_cqt_cache(paths, waves, sr, opt)
+    assert written == [cache.cache_name(p, opt) for p in paths]
+    mel, seq = ake.cqt_logmag([w.cuda() for w in waves], sr=sr, frames=5, octaves=8)
+    for i, name in enumerate(written):
+        t = torch.load(name)
+        assert t.dtype == torch.float64 and t.shape == (1, 288, int(seq[i])) and t.shape[1] == cache.expected_bins(opt)
+        assert torch.equal(t, mel[i][:, :, : int(seq[i])].double().cpu())
+    assert ake.write_cqt_cache(paths, waves, sr, opt) == []          # existing files are kept, as the reference does

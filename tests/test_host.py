@@ -87,3 +87,34 @@ def test_shard_ranges():
         assert akd.shard_counts(n, w) == [b - a for a, b in ranges]
     with pytest.raises(ValueError):
         akd.shard_range(4, 2, 2)
+
+
+def test_cqt_cache_names_follow_the_reference_table():
+    """KeyDataset.py:154-180: file-name suffix and accepted bin count per (octaves, frames, only_semitones)."""
+    import argparse
+
+    import torch
+
+    from audio_key_estimation_b200 import cache
+
+    def opt(**kw):
+        d = dict(octaves=8, frames=5, only_semitones=False)
+        d.update(kw)
+        return argparse.Namespace(**d)
+
+    assert cache.cache_name("/d/song.wav", opt()) == "/d/song8oct.pt"
+    assert cache.cache_name("/d/a.b/song.mp3", opt(octaves=7)) == "/d/a.b/song7oct.pt"
+    assert cache.cache_name("s.wav", opt(octaves=5)) == "s5oct_5frames.pt"
+    assert cache.cache_name("s.wav", opt(octaves=5, frames=10)) == "s5oct_10frames.pt"
+    assert cache.cache_name("s.wav", opt(octaves=5, frames=20)) == "s5oct_20frames.pt"
+    assert cache.cache_name("s.wav", opt(octaves=5, frames=3)) == "sfmin64.pt"
+    assert cache.cache_name("s.wav", opt(only_semitones=True)) == "s8oct_no_semi.pt"
+    with pytest.raises(ValueError):
+        cache.cache_name("s.wav", opt(octaves=6))          # the reference leaves `name` unbound there
+    assert [cache.expected_bins(opt(octaves=o)) for o in (5, 7, 8, 6)] == [180, 252, 288, 360]
+    assert cache.expected_bins(opt(only_semitones=True)) == 96
+    # entry format of KeyDataset.py:509: (1, n_bins, T) float64 on the CPU, batch padding removed
+    mel = torch.arange(2 * 288 * 7, dtype=torch.float32).reshape(2, 1, 288, 7)
+    e = cache.cache_entry(mel[1], 5)
+    assert e.shape == (1, 288, 5) and e.dtype == torch.float64 and e.device.type == "cpu"
+    assert torch.equal(e, mel[1][:, :, :5].double())
