@@ -358,6 +358,10 @@ __global__ void __launch_bounds__(kCasThreads, 1) cascade_umma_kernel(const Casc
   // raw accumulator: no rescaling between the two steps)
   constexpr float kInv1 = 1.f / (kXScale * kDecScale), kInv2 = kInv1 / kDecScale;
 
+  // tile -> clip by multiply-high: every role decodes every tile, and an integer division is ~50 dependent instructions
+  // (x / d == umulhi(x, 2^32 / d + 1) while x * d < 2^32)
+  const uint32_t tpc_magic = 0xFFFFFFFFu / (uint32_t)a.tiles_per_clip + 1;
+  auto clip_of = [&](int tile) { return a.tiles_per_clip == 1 ? tile : (int)__umulhi((uint32_t)tile, tpc_magic); };
   auto clip_len = [&](int b) {  // samples of level p in clip b
     const long long n0 = a.lengths ? a.lengths[b] : a.n_uniform;
     return (n0 + (1LL << a.level_in) - 1) >> a.level_in;
@@ -365,7 +369,7 @@ __global__ void __launch_bounds__(kCasThreads, 1) cascade_umma_kernel(const Casc
   // first tile at or after `tile` (in this CTA's stride) that has data; tiles beyond a short clip's end write nothing
   auto next_tile = [&](int tile) {
     for (; tile < a.n_tiles; tile += gridDim.x) {
-      const int b = tile / a.tiles_per_clip, t = tile - b * a.tiles_per_clip;
+      const int b = clip_of(tile), t = tile - b * a.tiles_per_clip;
       if ((long long)kCasOwn1 * t < ((clip_len(b) + 1) >> 1)) break;
     }
     return tile;
@@ -376,7 +380,7 @@ __global__ void __launch_bounds__(kCasThreads, 1) cascade_umma_kernel(const Casc
     bool bulk;         // 16-byte aligned: landed by one bulk async copy
   };
   auto span_of = [&](int tile) {
-    const int b = tile / a.tiles_per_clip, t = tile - b * a.tiles_per_clip;
+    const int b = clip_of(tile), t = tile - b * a.tiles_per_clip;
     const long long base0 = 2 * ((long long)kCasOwn1 * t - 32) - 32;
     Span s;
     s.src = a.in + (long long)b * a.in_stride + base0;
@@ -482,11 +486,11 @@ __global__ void __launch_bounds__(kCasThreads, 1) cascade_umma_kernel(const Casc
       // operand chunks (both conflict-free).  float4 f = ct + 256 r is half (f & 1) of chunk q = f / 2, which lives at
       // plane (q & 7), row (q >> 3): the plane and the half are fixed per thread, the row advances by 16 per round.
       const uint32_t off0 = (uint32_t)((ct >> 1) & 7) * kCasLBO0 + (uint32_t)(ct >> 4) * 16 + (uint32_t)(ct & 1) * 8;
-      auto convert4 = [&](int r) {
+      auto convert4 = [&](int r, bool masked) {
         const int f = ct + kCasConvThreads * r;
         const float4 v = *reinterpret_cast<const float4*>(st + 4 * f);
         float x[4] = {v.x, v.y, v.z, v.w};
-        if (!interior) {
+        if (masked) {
 #pragma unroll
           for (int e = 0; e < 4; ++e) x[e] = (4 * f + e >= sp.vlo && 4 * f + e < sp.vhi) ? x[e] : 0.f;
         }
@@ -498,9 +502,15 @@ __global__ void __launch_bounds__(kCasThreads, 1) cascade_umma_kernel(const Casc
         *reinterpret_cast<uint2*>(p0l + off) = make_uint2(l[0], l[1]);
       };
       static_assert(kCasPer4 == 9 && 2 * kCasChunks - 8 * kCasConvThreads == 16, "8 full rounds + 16 float4s");
+      if (interior) {  // all but the first and last tiles of a clip: no per-sample predicates
 #pragma unroll 2
-      for (int r = 0; r < 8; ++r) convert4(r);
-      if (ct < 16) convert4(8);
+        for (int r = 0; r < 8; ++r) convert4(r, false);
+        if (ct < 16) convert4(8, false);
+      } else {
+#pragma unroll 1
+        for (int r = 0; r < 8; ++r) convert4(r, true);
+        if (ct < 16) convert4(8, true);
+      }
       fence_proxy_async();
       mbar_arrive(&p0_full[bf]);
       mbar_arrive(&stage_empty[bf]);
@@ -517,7 +527,7 @@ __global__ void __launch_bounds__(kCasThreads, 1) cascade_umma_kernel(const Casc
     for (int tile = next_tile(blockIdx.x); tile < a.n_tiles; tile = next_tile(tile + gridDim.x), ++i) {
       if ((i & 1) != grp) continue;
       const uint32_t ph = (i >> 1) & 1;
-      const int b = tile / a.tiles_per_clip, t = tile - b * a.tiles_per_clip;
+      const int b = clip_of(tile), t = tile - b * a.tiles_per_clip;
       const long long n_p = clip_len(b);
       const long long n_half1 = n_p >> 1, n1 = (n_p + 1) >> 1;
       const long long o_lo1 = (long long)kCasOwn1 * t - 32;
@@ -606,17 +616,18 @@ __global__ void __launch_bounds__(kCasThreads, 1) cascade_umma_kernel(const Casc
     // ------------------------------------------------------------------ epilogue 2 (warps 8, 9): rows 0..62 of level p+2
     const int row = tid - 256;  // accumulator lane (warp 8: lanes 0..31, warp 9: 32..63)
     const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16) + 128;
+    const uint64_t inv2 = f2_pack(kInv2, kInv2);
     int i = 0;
     for (int tile = next_tile(blockIdx.x); tile < a.n_tiles; tile = next_tile(tile + gridDim.x), ++i) {
       const int bf = i & 1;
       const uint32_t ph = (i >> 1) & 1;
-      const int b = tile / a.tiles_per_clip, t = tile - b * a.tiles_per_clip;
+      const int b = clip_of(tile), t = tile - b * a.tiles_per_clip;
       const long long n_p = clip_len(b);
       const long long n1 = (n_p + 1) >> 1, n_half2 = n1 >> 1, n2 = (n1 + 1) >> 1;
       const long long o_lo2 = (long long)kCasOwn2 * t;
       mbar_wait_relaxed(&acc2_full[bf], ph);
       fence_after_sync();
-      float o[32];
+      uint64_t o[16];  // 32 outputs as fp32 pairs
       {
         uint32_t u0[16], u1[16], w0[16], w1[16];
         tmem_ld16_issue(lane_base + bf * 64, u0);
@@ -625,7 +636,10 @@ __global__ void __launch_bounds__(kCasThreads, 1) cascade_umma_kernel(const Casc
         tmem_ld16_issue(lane_base + bf * 64 + 48, w1);
         tmem_ld_wait16(u0), tmem_ld_wait16(u1), tmem_ld_wait16(w0), tmem_ld_wait16(w1);
 #pragma unroll
-        for (int n = 0; n < 16; ++n) o[n] = __uint_as_float(u0[n]) + __uint_as_float(w0[n]), o[16 + n] = __uint_as_float(u1[n]) + __uint_as_float(w1[n]);
+        for (int n = 0; n < 8; ++n) {
+          o[n] = f2_add(f2_pack(__uint_as_float(u0[2 * n]), __uint_as_float(u0[2 * n + 1])), f2_pack(__uint_as_float(w0[2 * n]), __uint_as_float(w0[2 * n + 1])));
+          o[8 + n] = f2_add(f2_pack(__uint_as_float(u1[2 * n]), __uint_as_float(u1[2 * n + 1])), f2_pack(__uint_as_float(w1[2 * n]), __uint_as_float(w1[2 * n + 1])));
+        }
       }
       fence_before_sync();
       mbar_arrive(&acc2_empty[bf]);
@@ -633,25 +647,32 @@ __global__ void __launch_bounds__(kCasThreads, 1) cascade_umma_kernel(const Casc
         // samples at or beyond floor(n1 / 2) do not exist: zero
         const int zhi = (int)min(32LL, max(0LL, n_half2 - (o_lo2 + 32LL * row)));
 #pragma unroll
-        for (int n = 0; n < 32; ++n) o[n] = (n < zhi) ? o[n] : 0.f;
+        for (int n = 0; n < 16; ++n) {
+          float x0, x1;
+          f2_unpack(o[n], x0, x1);
+          o[n] = f2_pack(2 * n < zhi ? x0 : 0.f, 2 * n + 1 < zhi ? x1 : 0.f);
+        }
       }
       if (row < kCasRows2) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q)
-          *reinterpret_cast<float4*>(tbuf2 + row * kCasTPitch + 4 * q) =
-              make_float4(o[4 * q] * kInv2, o[4 * q + 1] * kInv2, o[4 * q + 2] * kInv2, o[4 * q + 3] * kInv2);
+        for (int q = 0; q < 8; ++q) {
+          float4 v;
+          f2_unpack(f2_mul(o[2 * q], inv2), v.x, v.y);
+          f2_unpack(f2_mul(o[2 * q + 1], inv2), v.z, v.w);
+          *reinterpret_cast<float4*>(tbuf2 + row * kCasTPitch + 4 * q) = v;
+        }
       }
       asm volatile("bar.sync 3, 64;" ::: "memory");
-      float* dst = a.out2 + (long long)b * a.stride2 + o_lo2;
-      const long long lim = n2 - o_lo2;
+      {
+        // 63 rows x 8 float4s; thread `row` stores float4 (row & 7) of the rows (row >> 3) + 8 k
+        float* dst = a.out2 + (long long)b * a.stride2 + o_lo2 + 32 * (row >> 3) + 4 * (row & 7);
+        const float* src = tbuf2 + (row >> 3) * kCasTPitch + 4 * (row & 7);
+        const int r_lim = (int)min((long long)kCasRows2, max(0LL, (n2 - o_lo2 + 31) >> 5));  // rows with 32 r < n2 - o_lo2 exist
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const int idx = row + 64 * k;
-        const int r = idx >> 3, c4 = idx & 7;
-        if (idx < kCasRows2 * 8 && 32LL * r < lim)
-          *reinterpret_cast<float4*>(dst + 32 * r + 4 * c4) = *reinterpret_cast<const float4*>(tbuf2 + r * kCasTPitch + 4 * c4);
+        for (int k = 0; k < 8; ++k)
+          if ((row >> 3) + 8 * k < r_lim) *reinterpret_cast<float4*>(dst + 256 * k) = *reinterpret_cast<const float4*>(src + 8 * k * kCasTPitch);
       }
-      asm volatile("bar.sync 3, 64;" ::: "memory");
+      asm volatile("bar.sync 3, 64;" ::: "memory");  // the transposition buffer is reused by the next tile
     }
   }
   fence_before_sync();
