@@ -304,15 +304,14 @@ __device__ __forceinline__ void cas_store_split8(uint8_t* hi_dst, uint8_t* lo_ds
 //               (operand of the level p+2 MMAs) and, through a transposition buffer, row-contiguous fp32 stores (only the
 //               rows the filter bank reads when `sparse_hop` > 0)
 //   warps 8-9   epilogue 2: level p+2 accumulators (63 rows) -> fp32 stores
-//   warps 10-17 converter: landed fp32 span -> fp16 hi/lo transposed chunk planes (level-p operand), double buffered
-//   warp 18     loader: one bulk async copy per tile span into a two-stage ring
-//   warp 19     MMA issuer (converged, elect.sync): MMA1(i+2) is issued as soon as epilogue 1 has drained accumulator i,
+//   warps 10-21 converter: landed fp32 span -> fp16 hi/lo transposed chunk planes (level-p operand), double buffered
+//   warp 22     loader: one bulk async copy per tile span into a two-stage ring
+//   warp 23     MMA issuer (converged, elect.sync): MMA1(i+2) is issued as soon as epilogue 1 has drained accumulator i,
 //               MMA2(i) as soon as its operand planes exist, so the tensor pipe never waits for a whole epilogue
-constexpr int kCasThreads = 640;
-constexpr int kCasConvThreads = 256;
+constexpr int kCasThreads = 768;
+constexpr int kCasConvThreads = 384;
 constexpr int kCasChunks = kCasP0Rows * 8;                 // 1032 chunks of 8 samples per tile span
 constexpr int kCasSpan = kCasChunks * 8;                   // 8256 input samples per tile
-constexpr int kCasPer4 = (2 * kCasChunks + kCasConvThreads - 1) / kCasConvThreads;  // float4s per converter thread
 constexpr uint32_t kCasStageBytes = kCasSpan * 4;          // fp32 landing buffer of one tile span (bulk async copy)
 constexpr int kCasTPitch = 36;                             // floats per row of the store-transposition buffers (144 B: conflict-free)
 constexpr uint32_t kCasT1Bytes = 128 * kCasTPitch * 4;     // level p+1 outputs on their way to coalesced global stores
@@ -336,7 +335,7 @@ __global__ void __launch_bounds__(kCasThreads, 1) cascade_umma_kernel(const Casc
   const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
   const bool two = a.n_levels == 2;
 
-  if (warp == 19) tmem_alloc(&tmem_slot, 256);
+  if (warp == 23) tmem_alloc(&tmem_slot, 256);
   if (tid == 0) {
     mbar_init(&img_bar, 1);
     for (int i = 0; i < 2; ++i) {
@@ -389,7 +388,7 @@ __global__ void __launch_bounds__(kCasThreads, 1) cascade_umma_kernel(const Casc
     return s;
   };
 
-  if (warp == 18) {
+  if (warp == 22) {
     // ------------------------------------------------------------------ loader
     if (lane == 0) {
       mbar_arrive_expect_tx(&img_bar, kCasImgBytes);
@@ -421,7 +420,7 @@ __global__ void __launch_bounds__(kCasThreads, 1) cascade_umma_kernel(const Casc
       }
       __syncwarp();
     }
-  } else if (warp == 19) {
+  } else if (warp == 23) {
     // ------------------------------------------------------------------ MMA issuer
     int n_my = 0;
     for (int tile = next_tile(blockIdx.x); tile < a.n_tiles; tile = next_tile(tile + gridDim.x)) ++n_my;
@@ -483,12 +482,11 @@ __global__ void __launch_bounds__(kCasThreads, 1) cascade_umma_kernel(const Casc
       mbar_wait_relaxed(&p0_empty[bf], ph ^ 1);
       const bool interior = sp.vlo == 0 && sp.vhi == kCasSpan;
       // one float4 per thread and round: consecutive lanes read consecutive 16 B of the stage and write 8-byte halves of the
-      // operand chunks (both conflict-free).  float4 f = ct + 256 r is half (f & 1) of chunk q = f / 2, which lives at
-      // plane (q & 7), row (q >> 3): the plane and the half are fixed per thread, the row advances by 16 per round.
+      // operand chunks (both conflict-free).  float4 f = ct + kCasConvThreads r is half (f & 1) of chunk q = f / 2, which lives
+      // at plane (q & 7), row (q >> 3): the plane and the half are fixed per thread, the row advances by a constant per round.
       const uint32_t off0 = (uint32_t)((ct >> 1) & 7) * kCasLBO0 + (uint32_t)(ct >> 4) * 16 + (uint32_t)(ct & 1) * 8;
-      auto convert4 = [&](int r, bool masked) {
+      auto convert4 = [&](int r, float4 v, bool masked) {
         const int f = ct + kCasConvThreads * r;
-        const float4 v = *reinterpret_cast<const float4*>(st + 4 * f);
         float x[4] = {v.x, v.y, v.z, v.w};
         if (masked) {
 #pragma unroll
@@ -497,20 +495,28 @@ __global__ void __launch_bounds__(kCasThreads, 1) cascade_umma_kernel(const Casc
         uint32_t h[2], l[2];
         cas_split2(f2_mul(f2_pack(x[0], x[1]), ss), h[0], l[0]);
         cas_split2(f2_mul(f2_pack(x[2], x[3]), ss), h[1], l[1]);
-        const uint32_t off = off0 + 256u * (uint32_t)r;
+        const uint32_t off = off0 + (uint32_t)(kCasConvThreads / 16 * 16) * (uint32_t)r;  // kCasConvThreads / 16 operand rows per round
         *reinterpret_cast<uint2*>(p0h + off) = make_uint2(h[0], h[1]);
         *reinterpret_cast<uint2*>(p0l + off) = make_uint2(l[0], l[1]);
       };
-      static_assert(kCasPer4 == 9 && 2 * kCasChunks - 8 * kCasConvThreads == 16, "8 full rounds + 16 float4s");
+      constexpr int kFull = 2 * kCasChunks / kCasConvThreads, kRest = 2 * kCasChunks - kFull * kCasConvThreads;
+      static_assert(kCasConvThreads % 16 == 0 && kFull == 5 && kRest > 0, "5 full rounds + a partial one");
+      // The stage reads of a tile are issued before the first conversion: the compiler cannot hoist a shared-memory load
+      // above the plane stores of the previous round (it cannot prove they do not alias), and one LDS latency per float4
+      // was 40 % of the converter's time.
+      const float4* st4 = reinterpret_cast<const float4*>(st) + ct;
+      float4 v[kFull + 1];
+#pragma unroll
+      for (int u = 0; u < kFull; ++u) v[u] = st4[kCasConvThreads * u];
+      v[kFull] = ct < kRest ? st4[kCasConvThreads * kFull] : make_float4(0.f, 0.f, 0.f, 0.f);
       if (interior) {  // all but the first and last tiles of a clip: no per-sample predicates
-#pragma unroll 2
-        for (int r = 0; r < 8; ++r) convert4(r, false);
-        if (ct < 16) convert4(8, false);
+#pragma unroll
+        for (int u = 0; u < kFull; ++u) convert4(u, v[u], false);
       } else {
-#pragma unroll 1
-        for (int r = 0; r < 8; ++r) convert4(r, true);
-        if (ct < 16) convert4(8, true);
+#pragma unroll
+        for (int u = 0; u < kFull; ++u) convert4(u, v[u], true);
       }
+      if (ct < kRest) convert4(kFull, v[kFull], !interior);
       fence_proxy_async();
       mbar_arrive(&p0_full[bf]);
       mbar_arrive(&stage_empty[bf]);
@@ -677,7 +683,7 @@ __global__ void __launch_bounds__(kCasThreads, 1) cascade_umma_kernel(const Casc
   }
   fence_before_sync();
   __syncthreads();
-  if (warp == 19) tmem_dealloc(tmem, 256);
+  if (warp == 23) tmem_dealloc(tmem, 256);
 }
 
 // ---- tensor-core filter bank (tcgen05): one CTA = 128 frames of one octave x all filters x all of K ----------------
