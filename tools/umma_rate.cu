@@ -71,6 +71,85 @@ __global__ void __launch_bounds__(128) rate_kernel(Cfg c, int iters, long long* 
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128));
 }
 
+// Blocks of `per` MMAs into rotating accumulators (the first MMA of a block overwrites), one tcgen05.commit per block on a
+// barrier nobody waits for: does switching accumulators / committing cost tensor-pipe cycles?
+__global__ void __launch_bounds__(128) block_kernel(int N, int per, int nacc, int commit_each, int iters, long long* cycles) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ __align__(8) uint64_t bar, bars[8];
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  for (int i = tid; i < 96 * 1024 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+    for (int i = 0; i < 8; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bars[i])));
+    asm volatile("fence.mbarrier_init.release.cluster;");
+  }
+  asm volatile("fence.proxy.async.shared::cta;");
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  const uint32_t tmem = tmem_base_s;
+  // converged warp + elect.sync, blocks unrolled: the issue path of the library's kernels (umma.cuh: single-lane issue)
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
+  if (warp_u == 0) {
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint64_t v1 = (uint64_t)1 << 46;
+    const uint64_t hi_a = v1 | ((uint64_t)(128 >> 4) << 32) | ((uint64_t)(37344 >> 4) << 16);
+    const uint64_t hi_b = v1 | ((uint64_t)(128 >> 4) << 32) | ((uint64_t)((uint32_t)N * 16 >> 4) << 16);
+    const uint32_t a0 = smem_u32(smem), b0 = smem_u32(smem) + 80 * 1024;
+    long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+      const uint32_t d = tmem + (uint32_t)(it & (nacc - 1)) * 128;  // nacc is a power of two: no division on the issue path
+      const uint32_t ab = a0 + (uint32_t)(it & 7) * 1952;
+      uint32_t el;
+      asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(el));
+      if (el) {
+        if (per == 7) {
+#pragma unroll
+          for (int u = 0; u < 7; ++u)
+            mma_f16(d, hi_a | (uint64_t)(((ab + (uint32_t)u * 2512) >> 4) & 0x3FFF), hi_b | (uint64_t)(((b0 + (uint32_t)(u % 4) * 3584) >> 4) & 0x3FFF), idesc, u ? 1u : 0u);
+        } else {
+#pragma unroll 4
+          for (int u = 0; u < per; ++u)
+            mma_f16(d, hi_a | (uint64_t)(((ab + (uint32_t)u * 2512) >> 4) & 0x3FFF), hi_b | (uint64_t)(((b0 + (uint32_t)(u % 4) * 3584) >> 4) & 0x3FFF), idesc, u ? 1u : 0u);
+        }
+        if (commit_each) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bars[it & 7])));
+      }
+      __syncwarp();
+    }
+    if (tid == 0) {
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)));
+      uint32_t done = 0;
+      while (!done) asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(done) : "r"(smem_u32(&bar)), "r"(0));
+      cycles[blockIdx.x] = clock64() - t0;
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+}
+
+static void go_blocks(int N, int per, int nacc, int commit_each) {
+  const int n_cta = 148, iters = 800;
+  long long* cyc_d;
+  CK(cudaMalloc(&cyc_d, 8 * n_cta));
+  CK(cudaFuncSetAttribute(block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  block_kernel<<<n_cta, 128, 160 * 1024>>>(N, per, nacc, commit_each, iters, cyc_d);
+  CK(cudaDeviceSynchronize());
+  long long* cyc = new long long[n_cta];
+  CK(cudaMemcpy(cyc, cyc_d, 8 * n_cta, cudaMemcpyDeviceToHost));
+  double mx = 0;
+  for (int i = 0; i < n_cta; ++i) mx = cyc[i] > mx ? cyc[i] : mx;
+  printf("blocks of %2d MMAs N%-3d, %d accumulators, commit per block %d: %6.1f cycles/MMA (%6.1f per block)\n", per, N, nacc, commit_each,
+         mx / ((double)iters * per), mx / iters);
+  delete[] cyc;
+  cudaFree(cyc_d);
+}
+
 static void go(const char* what, Cfg c, int ctas_per_sm = 1) {
   const int n_cta = 148 * ctas_per_sm;
   long long* cyc_d;
@@ -91,7 +170,28 @@ static void go(const char* what, Cfg c, int ctas_per_sm = 1) {
   cudaFree(cyc_d);
 }
 
-int main() {
+int main(int argc, char** argv) {
+  if (argc > 1 && argv[1][0] == 'b') {
+    for (int nacc : {1, 2, 4})
+      for (int ce : {0, 1}) go_blocks(112, 7, nacc, ce);
+    go_blocks(112, 14, 4, 1);
+    go_blocks(224, 12, 2, 1);
+    go_blocks(64, 8, 4, 1);
+    return 0;
+  }
+  if (argc > 1) {
+    // p2p-like operand walk: which of {N, LBO between the two K chunks, start-address step, accumulators} costs cycles?
+    for (int N : {96, 112, 128})
+      for (uint32_t lbo : {2064u, 37344u})
+        for (uint32_t step : {16u, 2512u})
+          for (int nacc : {1, 4}) {
+            if (N * nacc > 128) continue;
+            char what[64];
+            snprintf(what, sizeof what, "A LBO=%u step=%u", lbo, step);
+            go(what, Cfg{N, 128, nacc, 0, lbo, step, 0, (uint32_t)N * 16}, 1);
+          }
+    return 0;
+  }
   for (int N : {16, 32, 64, 96, 128})
     for (int k : {1, 2, 3, 4}) go("none A LBO=2064, B none", Cfg{N, 128, 1, 0, 2064, 16, 0, (uint32_t)N * 16}, k);
   return 0;
