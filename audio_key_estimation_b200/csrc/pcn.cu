@@ -518,10 +518,13 @@ void Fwd::run(const float* mel, float* key_out, float* tonic_out, float* genre_o
         for (int i = 0; i < 2; ++i)
           for (int j = 0; j < 2; ++j) x[i][j] = arena.take<__half>(plane_halves);
         const Conv& cu = p->convs[lp.up];
+        // up_sixth (models.py:372-374) as a (B, 36, T) x 4-channel table; the first 7x7 conv generates its input tiles
+        // cat[p, tile(up)] from it and the log-CQT in shared memory (no operand planes for the 5-channel input at all)
+        float4* up_tab = reinterpret_cast<float4*>(arena.take<float>((size_t)B * 36 * Tn * 4));
         if (!dry) {
           ProfScope prof("pcn.prep", st);
-          PrepArgs pa{p_in.p, pc.p, p->d_params + cu.w_off, scale_of(cu, false), shift_of(cu, false), x[0][0], x[0][1], B, P, Tn, Wd};
-          p2p_prep_kernel<<<ew_blocks((long long)B * (P + 6) * Wd), 256, 0, st>>>(pa);
+          upsixth_table_kernel<<<dim3(cdiv(Tn, 128), 36, B), 128, 0, st>>>(pc.p, p->d_params + cu.w_off, scale_of(cu, false),
+                                                                           shift_of(cu, false), up_tab, Tn);
           AKE_LAUNCHED();
         }
         const int n_tt = cdiv(Tn, kP2PMaxTB), TB = cdiv(Tn, n_tt);
@@ -533,14 +536,17 @@ void Fwd::run(const float* mel, float* key_out, float* tonic_out, float* genre_o
             ProfScope prof("pcn.p2p", st);
             static size_t configured = 0;
             if (smem > configured) {
-              AKE_CUDA(cudaFuncSetAttribute(p2p_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+              AKE_CUDA(cudaFuncSetAttribute(p2p_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+              AKE_CUDA(cudaFuncSetAttribute(p2p_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
               configured = smem;
             }
             const int n_rt = cdiv(P, kP2PRows), n_tiles = B * n_rt * cdiv(Tn, TB);
             P2PArgs a{x[cur][0], x[cur][1], x[cur ^ 1][0], x[cur ^ 1][1],
                       reinterpret_cast<const __half*>(reinterpret_cast<const uint8_t*>(p->d_wimg) + i * kP2PWBytes),
-                      scale_of(c, false), shift_of(c, false), P, Tn, Wd, TB, cdiv(Tn, TB), n_rt, n_tiles};
-            p2p_umma_kernel<<<std::min(n_tiles, sm_count()), kP2PThreads, smem, st>>>(a);  // persistent: one CTA per SM
+                      scale_of(c, false), shift_of(c, false), P, Tn, Wd, TB, cdiv(Tn, TB), n_rt, n_tiles, p_in.p, up_tab};
+            const int grid = std::min(n_tiles, sm_count());  // persistent: one CTA per SM
+            if (i == 0) p2p_umma_kernel<true><<<grid, kP2PThreadsGen, smem, st>>>(a);
+            else p2p_umma_kernel<false><<<grid, kP2PThreads, smem, st>>>(a);
             AKE_LAUNCHED();
           }
           cur ^= 1;

@@ -28,7 +28,9 @@ constexpr int kP2PRows = 8;         // pitch rows per CTA tile
 constexpr int kP2PBufs = 2;         // tile buffers of the load ring
 constexpr int kP2PMaxTB = 160;      // frames per CTA tile (upper bound)
 constexpr int kP2PGroups = 4;       // epilogue groups of 4 warps = accumulator buffers of 128 TMEM columns
-constexpr int kP2PThreads = 32 * (4 * kP2PGroups + 2);  // + the loader warp and the MMA-issuer warp
+constexpr int kP2PGenWarps = 8;      // tile-generator warps of the first conv (instead of the one loader warp)
+constexpr int kP2PThreads = 32 * (4 * kP2PGroups + 2);                    // + the loader warp and the MMA-issuer warp
+constexpr int kP2PThreadsGen = 32 * (4 * kP2PGroups + kP2PGenWarps + 1);  // + the generator warps and the MMA-issuer warp
 
 __device__ __forceinline__ float leaky_f(float v) { return v > 0.f ? v : kLeakySlope * v; }
 
@@ -40,50 +42,29 @@ __device__ __forceinline__ void store_split8(__half* hi_dst, __half* lo_dst, con
   *reinterpret_cast<uint4*>(lo_dst) = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
-// ---- layer >= 1 input: cat[p (1 ch), tile(up_sixth(pc)) (4 ch)] -> chunk planes with circular halos ---------------
-// models.py:372-383: ConvTranspose2d(4,4,(3,1),stride (3,1)) + BN + LeakyReLU on pc, tiled x8 along pitch
-// (PitchClass2Pitch, :135-143), concatenated behind the raw CQT channel.  One thread per halo'd position.
-struct PrepArgs {
-  const float* mel;   // (B,1,P,T)
-  const float* pc;    // (B,4,12,T)
-  const float* w_up;  // (4 ci, 4 co, 3, 1)
-  const float* scale; // 4 (eval-mode BN folded, bias included)
-  const float* shift;
-  __half* out_hi;
-  __half* out_lo;
-  int B, P, T, Wd;
-};
-
-__global__ void __launch_bounds__(256) p2p_prep_kernel(const PrepArgs a) {
-  __shared__ float w[48], sc[4], sh[4];
-  if (threadIdx.x < 48) w[threadIdx.x] = a.w_up[threadIdx.x];
-  if (threadIdx.x < 4) sc[threadIdx.x] = a.scale[threadIdx.x], sh[threadIdx.x] = a.shift[threadIdx.x];
-  __syncthreads();
-  const int rows = a.P + 6;
-  const long long n = (long long)a.B * rows * a.Wd;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const int col = i % a.Wd;
-    const long long q = i / a.Wd;
-    const int row = q % rows, b = q / rows;
-    int p = row - 3, t = col - 3;
-    p += (p < 0) ? a.P : 0, p -= (p >= a.P) ? a.P : 0;
-    t += (t < 0) ? a.T : 0, t -= (t >= a.T) ? a.T : 0;
-    float v[8];
-    v[0] = __ldg(a.mel + ((long long)b * a.P + p) * a.T + t);
-    const int p36 = p % 36, c = p36 / 3, r = p36 - 3 * c;
-    float x[4];
+// ---- layer >= 1 input: cat[p (1 ch), tile(up_sixth(pc)) (4 ch)] (models.py:372-383) --------------------------------------
+// Never materialised: the first 7x7 convolution generates its input tiles in shared memory (p2p_umma_kernel<true>) from the
+// log-CQT and the table below.
+// up_sixth of models.py:372-374 as a table: ConvTranspose2d(4,4,(3,1),stride (3,1)) + BN + LeakyReLU maps the 12 pitch classes to
+// 36 rows; PitchClass2Pitch (:135-143) then tiles those 36 rows over all pitches, so row p of the conv input is table row p % 36.
+// grid (ceil(T / 128), 36, B) -> up[b][p36][t] = 4 channels.
+__global__ void __launch_bounds__(128) upsixth_table_kernel(const float* __restrict__ pc, const float* __restrict__ w_up,
+                                                            const float* __restrict__ scale, const float* __restrict__ shift,
+                                                            float4* __restrict__ up, int T) {
+  const int t = blockIdx.x * 128 + threadIdx.x, p36 = blockIdx.y, b = blockIdx.z;
+  if (t >= T) return;
+  const int c = p36 / 3, r = p36 - 3 * c;
+  float x[4], y[4];
 #pragma unroll
-    for (int ci = 0; ci < 4; ++ci) x[ci] = __ldg(a.pc + (((long long)b * 4 + ci) * 12 + c) * a.T + t);
+  for (int ci = 0; ci < 4; ++ci) x[ci] = __ldg(pc + (((long long)b * 4 + ci) * 12 + c) * T + t);
 #pragma unroll
-    for (int co = 0; co < 4; ++co) {
-      float acc = 0.f;
+  for (int co = 0; co < 4; ++co) {
+    float acc = 0.f;
 #pragma unroll
-      for (int ci = 0; ci < 4; ++ci) acc = fmaf(w[(ci * 4 + co) * 3 + r], x[ci], acc);
-      v[1 + co] = leaky_f(fmaf(acc, sc[co], sh[co]));
-    }
-    v[5] = v[6] = v[7] = 0.f;
-    store_split8(a.out_hi + i * 8, a.out_lo + i * 8, v);
+    for (int ci = 0; ci < 4; ++ci) acc = fmaf(__ldg(w_up + (ci * 4 + co) * 3 + r), x[ci], acc);
+    y[co] = leaky_f(fmaf(acc, __ldg(scale + co), __ldg(shift + co)));
   }
+  up[((long long)b * 36 + p36) * T + t] = make_float4(y[0], y[1], y[2], y[3]);
 }
 
 // ---- weight image for the 7x7 convolution: [dp 7][chunk 2][n 112][ci 8] fp16 ------------------------------------------
@@ -117,6 +98,10 @@ struct P2PArgs {
   int P, T, Wd;          // Wd = T + 6
   int TB, n_ttiles;      // frames per tile, tiles along time
   int n_rtiles, n_tiles; // pitch-row tiles per clip; tiles in the launch (B * n_rtiles * n_ttiles)
+  // GEN = true (first conv of the stack): the input tile cat[p, tile(up_sixth(pc))] (models.py:372-383) is generated in shared
+  // memory from the log-CQT and the 36-row up-sampled table instead of being read from operand planes
+  const float* mel;      // (B, 1, P, T)
+  const float4* up;      // (B, 36, T) x 4 channels: act(bn(ConvTranspose2d(pc))) per pitch class third (upsixth_table_kernel)
 };
 
 constexpr uint32_t kP2PWBytes = 7 * 2 * 112 * 16;
@@ -134,9 +119,11 @@ __host__ __device__ inline size_t p2p_smem_bytes(int Wt) {
 //   warps 0..4G-1: G epilogue groups of 4 warps; group g drains blocks g, g + G, ... (thread = TMEM lane = anchor):
 //                 phase realignment (shuffles + a 6-lane hand-over between neighbouring warps), BN + LeakyReLU, fp16
 //                 hi/lo split, stores of the home position and of the circular halo copies.
-__global__ void __launch_bounds__(kP2PThreads, 1) p2p_umma_kernel(const P2PArgs a) {
+template <bool GEN>
+__global__ void __launch_bounds__(GEN ? kP2PThreadsGen : kP2PThreads, 1) p2p_umma_kernel(const P2PArgs a) {
   using namespace umma;
   constexpr int G = kP2PGroups;
+  constexpr int NLOAD = GEN ? kP2PGenWarps : 1, ISSUER = 4 * G + NLOAD;  // warp roles: [0, 4G) epilogue, [4G, 4G + NLOAD) tile producers, ISSUER
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t w_bar, full_bar[kP2PBufs], empty_bar[kP2PBufs], acc_full[G], acc_empty[G];
   __shared__ uint32_t tmem_slot;
@@ -169,10 +156,10 @@ __global__ void __launch_bounds__(kP2PThreads, 1) p2p_umma_kernel(const P2PArgs 
     return g;
   };
 
-  if (warp == 4 * G + 1) tmem_alloc(&tmem_slot, 128 * G);
+  if (warp == ISSUER) tmem_alloc(&tmem_slot, 128 * G);
   if (threadIdx.x == 0) {
     mbar_init(&w_bar, 1);
-    for (int i = 0; i < kP2PBufs; ++i) mbar_init(&full_bar[i], 1), mbar_init(&empty_bar[i], 1);
+    for (int i = 0; i < kP2PBufs; ++i) mbar_init(&full_bar[i], GEN ? 32 * NLOAD : 1), mbar_init(&empty_bar[i], 1);
     for (int i = 0; i < G; ++i) mbar_init(&acc_full[i], 1), mbar_init(&acc_empty[i], 128);
     mbar_init_fence();
   }
@@ -186,41 +173,97 @@ __global__ void __launch_bounds__(kP2PThreads, 1) p2p_umma_kernel(const P2PArgs 
   fence_after_sync();
   const uint32_t tmem = tmem_slot;
 
-  if (warp == 4 * G) {
-    // ------------------------------------------------------------ loader
-    if (lane == 0) {
-      mbar_arrive_expect_tx(&w_bar, kP2PWBytes);
-      bulk_g2s(s_w, a.wimg, kP2PWBytes, &w_bar);
-    }
-    int k = 0;
-    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++k) {
-      const int s = k % kP2PBufs;
-      const Geom g = geom(tile);
-      const int rows_in = g.PB + 6;
-      const uint32_t row_bytes = (uint32_t)g.cols_in * 16;
-      mbar_wait_relaxed(&empty_bar[s], ((k / kP2PBufs) & 1) ^ 1);
-      if (lane == 0) mbar_arrive_expect_tx(&full_bar[s], 2u * rows_in * row_bytes);
-      __syncwarp();
-      uint8_t* d_hi = smem + (size_t)s * 2 * plane;
-      for (int rr = lane; rr < rows_in; rr += 32) {
-        const long long src = (((long long)g.b * (a.P + 6) + g.p0 + rr) * a.Wd + g.t0) * 8;
-        bulk_g2s(d_hi + (size_t)rr * Wt * 16, a.in_hi + src, row_bytes, &full_bar[s]);
-        bulk_g2s(d_hi + plane + (size_t)rr * Wt * 16, a.in_lo + src, row_bytes, &full_bar[s]);
+  if (warp >= 4 * G && warp < ISSUER) {
+    if constexpr (GEN) {
+      // ------------------------------------------------------------ tile generators (first conv): position q of the tile =
+      // [log-CQT (1 ch) | up-sampled pitch-class features (4 ch) | 0 0 0], circular in pitch and time, split into fp16 hi / lo
+      const int gt = threadIdx.x - 128 * G;
+      if (gt == 0) {
+        mbar_arrive_expect_tx(&w_bar, kP2PWBytes);
+        bulk_g2s(s_w, a.wimg, kP2PWBytes, &w_bar);
       }
-      // The tile after this one cannot be copied before a buffer frees up (one tile time from now): pull it into L2
-      // meanwhile, so that copy pays the L2 latency instead of the HBM latency.
-      const int tile2 = tile + (kP2PBufs - 1) * (int)gridDim.x;
-      if (tile2 < a.n_tiles) {
-        const Geom g2 = geom(tile2);
-        const uint32_t rb2 = (uint32_t)g2.cols_in * 16;
-        for (int rr = lane; rr < g2.PB + 6; rr += 32) {
-          const long long src = (((long long)g2.b * (a.P + 6) + g2.p0 + rr) * a.Wd + g2.t0) * 8;
-          bulk_prefetch_l2(a.in_hi + src, rb2);
-          bulk_prefetch_l2(a.in_lo + src, rb2);
+      const uint32_t wt_magic = 0xFFFFFFFFu / (uint32_t)Wt + 1;
+      int k = 0;
+      for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++k) {
+        const int s = k % kP2PBufs;
+        const Geom g = geom(tile);
+        const int n_pos = (g.PB + 6) * Wt;
+        mbar_wait_relaxed(&empty_bar[s], ((k / kP2PBufs) & 1) ^ 1);
+        uint4* d_hi = reinterpret_cast<uint4*>(smem + (size_t)s * 2 * plane);
+        uint4* d_lo = reinterpret_cast<uint4*>(smem + (size_t)s * 2 * plane + plane);
+        const float* mel_b = a.mel + (long long)g.b * a.P * a.T;
+        const float4* up_b = a.up + (long long)g.b * 36 * a.T;
+        // six positions per round, all twelve loads in flight before the first split (one round trip to L2 per round, not per
+        // position: 17 positions per thread and tile would otherwise cost more than the tile's MMAs)
+        constexpr int kBatch = 3;
+        for (int q0 = gt; q0 < n_pos; q0 += kBatch * 32 * NLOAD) {
+          float m0[kBatch];
+          float4 u[kBatch];
+#pragma unroll
+          for (int i = 0; i < kBatch; ++i) {
+            const int q = q0 + i * 32 * NLOAD;
+            const int row = (int)__umulhi((uint32_t)q, wt_magic), col = q - row * Wt;
+            m0[i] = 0.f, u[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            // columns beyond the planes' width (narrow last time tile) only feed discarded anchors: zeros
+            if (q < n_pos && col < g.cols_in) {
+              int p = g.p0 + row - 3, t = g.t0 + col - 3;
+              p += (p < 0) ? a.P : 0, p -= (p >= a.P) ? a.P : 0;
+              t += (t < 0) ? a.T : 0, t -= (t >= a.T) ? a.T : 0;
+              m0[i] = __ldg(mel_b + (long long)p * a.T + t);
+              u[i] = __ldg(up_b + (p % 36) * a.T + t);
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < kBatch; ++i) {
+            const int q = q0 + i * 32 * NLOAD;
+            if (q < n_pos) {
+              uint32_t h[3], l[3];
+              split_f16x2(m0[i], u[i].x, h[0], l[0]);
+              split_f16x2(u[i].y, u[i].z, h[1], l[1]);
+              split_f16x2(u[i].w, 0.f, h[2], l[2]);
+              d_hi[q] = make_uint4(h[0], h[1], h[2], 0), d_lo[q] = make_uint4(l[0], l[1], l[2], 0);
+            }
+          }
+        }
+        fence_proxy_async();
+        mbar_arrive(&full_bar[s]);
+      }
+    } else {
+      // ------------------------------------------------------------ loader
+      if (lane == 0) {
+        mbar_arrive_expect_tx(&w_bar, kP2PWBytes);
+        bulk_g2s(s_w, a.wimg, kP2PWBytes, &w_bar);
+      }
+      int k = 0;
+      for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++k) {
+        const int s = k % kP2PBufs;
+        const Geom g = geom(tile);
+        const int rows_in = g.PB + 6;
+        const uint32_t row_bytes = (uint32_t)g.cols_in * 16;
+        mbar_wait_relaxed(&empty_bar[s], ((k / kP2PBufs) & 1) ^ 1);
+        if (lane == 0) mbar_arrive_expect_tx(&full_bar[s], 2u * rows_in * row_bytes);
+        __syncwarp();
+        uint8_t* d_hi = smem + (size_t)s * 2 * plane;
+        for (int rr = lane; rr < rows_in; rr += 32) {
+          const long long src = (((long long)g.b * (a.P + 6) + g.p0 + rr) * a.Wd + g.t0) * 8;
+          bulk_g2s(d_hi + (size_t)rr * Wt * 16, a.in_hi + src, row_bytes, &full_bar[s]);
+          bulk_g2s(d_hi + plane + (size_t)rr * Wt * 16, a.in_lo + src, row_bytes, &full_bar[s]);
+        }
+        // The tile after this one cannot be copied before a buffer frees up (one tile time from now): pull it into L2
+        // meanwhile, so that copy pays the L2 latency instead of the HBM latency.
+        const int tile2 = tile + (kP2PBufs - 1) * (int)gridDim.x;
+        if (tile2 < a.n_tiles) {
+          const Geom g2 = geom(tile2);
+          const uint32_t rb2 = (uint32_t)g2.cols_in * 16;
+          for (int rr = lane; rr < g2.PB + 6; rr += 32) {
+            const long long src = (((long long)g2.b * (a.P + 6) + g2.p0 + rr) * a.Wd + g2.t0) * 8;
+            bulk_prefetch_l2(a.in_hi + src, rb2);
+            bulk_prefetch_l2(a.in_lo + src, rb2);
+          }
         }
       }
     }
-  } else if (warp == 4 * G + 1) {
+  } else if (warp == ISSUER) {
     // ------------------------------------------------------------ MMA issuer (converged warp, one elected lane issues)
     const uint64_t A_DESC = desc_hi(plane);         // chunk 1 = the x_lo plane at the same position
     constexpr uint64_t B_DESC = desc_hi(112 * 16);  // chunk stride: 112 rows x 16 B
@@ -360,7 +403,7 @@ __global__ void __launch_bounds__(kP2PThreads, 1) p2p_umma_kernel(const P2PArgs 
   }
   fence_before_sync();
   __syncthreads();
-  if (warp == 4 * G + 1) tmem_dealloc(tmem, 128 * G);
+  if (warp == ISSUER) tmem_dealloc(tmem, 128 * G);
 }
 
 // ---- pool_semi conv (3x3, stride (3,1), time-circular) + BN + LeakyReLU + octave max pool, from chunk planes ------
