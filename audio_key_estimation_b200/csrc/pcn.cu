@@ -128,6 +128,7 @@ struct ake_pcn {
   std::vector<int> umma_convs;
   __half* d_wimg_pc = nullptr;      // equivariant convs of the layer-1 PitchClass2PitchClass stack (kPcWBytes each)
   __half* d_wimg_l0 = nullptr;      // equivariant convs of the layer-0 PitchClass2PitchClass stack (kPc8WBytes each)
+  __half* d_wimg_semi = nullptr;    // pool_semi conv of layer 1 (kSemiWBytes)
   __half* d_wimg_heads = nullptr;   // first conv of the tonic and key heads, fused along N (344,064 B)
   float* d_ss_heads = nullptr;      // [scale 64 | shift 64] of that fused conv (tonic channels first)
   __half* d_wimg_genre = nullptr;   // first conv of the genre head (1 x 7, 16 -> 32): one 16 KB stage
@@ -559,9 +560,26 @@ void Fwd::run(const float* mel, float* key_out, float* tonic_out, float* genre_o
           for (int j = 0; j < 2; ++j) e[i][j] = arena.take<__half>(eq_halves);
         if (!dry) {
           ProfScope prof("pcn.semitone", st);
-          SemiArgs sa{x[cur][0], x[cur][1], p->d_params + cs.w_off, scale_of(cs, false), shift_of(cs, false), pc.p,
-                      e[0][0], e[0][1], B, P, Tn, Wd};
-          semitone_pool_chunks_kernel<<<dim3(cdiv(Wd, 128), 12, B), 128, 0, st>>>(sa);
+          const int n_oct = P / 36;
+          if (p->d_wimg_semi && P % 36 == 0 && n_oct <= kSemiMaxOct) {
+            // tensor cores: all octaves of a (clip, pitch class, time tile) accumulate side by side in TMEM
+            // tile width: TB + 2 <= 128 anchors, and two double-buffered tiles of 3 n_oct rows (hi + lo) must fit in shared memory
+            const int tb_cap = std::min(kSemiMaxTB, 3200 / (3 * n_oct) - 2);
+            const int n_tt = cdiv(Tn, tb_cap), TBs = cdiv(Tn, n_tt);
+            SemiUmmaArgs sa{x[cur][0], x[cur][1], p->d_wimg_semi, scale_of(cs, false), shift_of(cs, false), pc.p, e[0][0], e[0][1],
+                            B, P, Tn, Wd, n_oct, TBs, n_tt, B * 12 * n_tt};
+            const size_t smem_s = semi_smem_bytes(n_oct, TBs + 2);
+            static size_t conf_s = 0;
+            if (smem_s > conf_s) {
+              AKE_CUDA(cudaFuncSetAttribute(semi_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
+              conf_s = smem_s;
+            }
+            semi_umma_kernel<<<std::min(sa.n_items, sm_count()), kSemiThreads, smem_s, st>>>(sa);
+          } else {
+            SemiArgs sa{x[cur][0], x[cur][1], p->d_params + cs.w_off, scale_of(cs, false), shift_of(cs, false), pc.p,
+                        e[0][0], e[0][1], B, P, Tn, Wd};
+            semitone_pool_chunks_kernel<<<dim3(cdiv(Wd, 128), 12, B), 128, 0, st>>>(sa);
+          }
           AKE_LAUNCHED();
         }
         // PitchClass2PitchClass stack (models.py:393) on tensor cores; MaxPool2d((1,2)) fused into the last conv
@@ -872,6 +890,14 @@ static void upload_params(ake_pcn* p, const float* flat_dev, int64_t n, cudaStre
       AKE_LAUNCHED();
     }
     {
+      const Conv& cs = p->convs[p->layers[1].sem];
+      if (cs.Cin == 8 && cs.Cout == 8) {
+        if (!p->d_wimg_semi) AKE_CUDA(cudaMalloc(&p->d_wimg_semi, kSemiWBytes));
+        semi_pack_weights_kernel<<<5, 128, 0, st>>>(p->d_params + cs.w_off, p->d_wimg_semi);
+        AKE_LAUNCHED();
+      }
+    }
+    {
       const std::vector<int>& l0 = p->layers[0].pc2pc;
       if (!p->d_wimg_l0) AKE_CUDA(cudaMalloc(&p->d_wimg_l0, (size_t)kPc8WBytes * l0.size()));
       for (size_t i = 0; i < l0.size(); ++i) {
@@ -1012,6 +1038,7 @@ void ake_pcn_destroy(ake_pcn* p) {
   cudaFree(p->d_wimg);
   cudaFree(p->d_wimg_pc);
   cudaFree(p->d_wimg_l0);
+  cudaFree(p->d_wimg_semi);
   cudaFree(p->d_wimg_heads);
   cudaFree(p->d_ss_heads);
   cudaFree(p->d_wimg_genre);

@@ -489,6 +489,244 @@ __global__ void __launch_bounds__(128) semitone_pool_chunks_kernel(const SemiArg
   }
 }
 
+// ---- pool_semi + octave pool on tensor cores ---------------------------------------------------------------------------
+// Same operator as semitone_pool_chunks_kernel (models.py:337-339, 386-392), as a shift-GEMM: for pitch class c and octave o
+// the three input rows 3 (c + 12 o) + dp are three row taps, K = 16 = [x_hi | x_lo] chunks, N = 48 = 3 time-tap phases x
+// {W_hi 8, W_lo 8}; the accumulators of ALL octaves of a work item (b, c, time tile) sit side by side in TMEM (48 columns
+// each), and the epilogue re-aligns the phases, applies BN + LeakyReLU and takes the octave max in registers.  The kernel
+// streams the last Pitch2Pitch output once (HBM-bound) instead of spending 4608 FFMAs per output on it.
+// Persistent CTA per SM: warps 0-3 epilogue (thread = anchor = frame), warp 4 loader (double-buffered tiles), warp 5 issuer.
+constexpr int kSemiMaxTB = 126;     // frames per tile: TB + 2 <= 128 anchors
+constexpr int kSemiMaxOct = 10;     // 48 TMEM columns per octave
+constexpr int kSemiThreads = 192;
+constexpr uint32_t kSemiWBytes = 3 * 2 * 48 * 16;
+
+// [dp 3][chunk 2][n 48][ci 8]: n = 16 dt + j; j < 8: W_hi of output channel j, j >= 8: W_lo; both chunks hold the same weights
+__global__ void semi_pack_weights_kernel(const float* __restrict__ w, __half* __restrict__ img) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 3 * 3 * 8 * 8) return;
+  const int ci = i % 8, co = (i / 8) % 8, dt = (i / 64) % 3, dp = i / 192;
+  const float v = w[((co * 8 + ci) * 3 + dp) * 3 + dt] * kWScale;
+  const __half hi = __float2half_rn(v);
+  const __half lo = __float2half_rn(v - __half2float(hi));
+  for (int c = 0; c < 2; ++c) {
+    img[((dp * 2 + c) * 48 + 16 * dt + co) * 8 + ci] = hi;
+    img[((dp * 2 + c) * 48 + 16 * dt + 8 + co) * 8 + ci] = lo;
+  }
+}
+
+struct SemiUmmaArgs {
+  const __half* in_hi;
+  const __half* in_lo;  // [B][P+6][Wd][8]
+  const __half* wimg;   // semi_pack_weights_kernel image
+  const float* scale;
+  const float* shift;   // 8
+  const float* pc_prev; // (B, 4, 12, T) fp32
+  __half* out_hi;
+  __half* out_lo;       // [B][2][23][Wd][8]: channels [pc_prev 4 | pooled 8 | 0 x 4]
+  int B, P, T, Wd, n_oct, TB, n_ttiles, n_items;
+};
+
+__host__ __device__ inline uint32_t semi_plane_positions(int n_oct, int Wt) { return (uint32_t)(3 * n_oct * Wt + 136); }
+__host__ __device__ inline size_t semi_smem_bytes(int n_oct, int Wt) {
+  return (size_t)2 * 2 * semi_plane_positions(n_oct, Wt) * 16 + kSemiWBytes + (size_t)kSemiMaxOct * 3 * 3 * 32;
+}
+
+__global__ void __launch_bounds__(kSemiThreads, 1) semi_umma_kernel(const SemiUmmaArgs a) {
+  using namespace umma;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t w_bar, full_bar[2], empty_bar[2], acc_full, acc_empty;
+  __shared__ uint32_t tmem_slot;
+  __shared__ float s_scale[8], s_shift[8];
+
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
+  const int Wt = a.TB + 2, n_oct = a.n_oct, rows_in = 3 * n_oct;
+  const uint32_t plane = semi_plane_positions(n_oct, Wt) * 16;  // a tile buffer holds [hi][lo]
+  uint8_t* s_w = smem + 4 * plane;
+  float4* pub = reinterpret_cast<float4*>(s_w + kSemiWBytes);    // [octave][warp 1..3][slot 3 = (f 1: lane 0), (f 2: lanes 0, 1)][8 floats]
+  const int per_clip = 12 * a.n_ttiles;
+  const uint32_t pc_magic = 0xFFFFFFFFu / (uint32_t)per_clip + 1, tt_magic = 0xFFFFFFFFu / (uint32_t)a.n_ttiles + 1;
+  auto decode = [&](int item, int& b, int& c, int& t0) {
+    b = (int)__umulhi((uint32_t)item, pc_magic);
+    const int r = item - b * per_clip;
+    c = a.n_ttiles == 1 ? r : (int)__umulhi((uint32_t)r, tt_magic);
+    t0 = (r - c * a.n_ttiles) * a.TB;
+  };
+
+  if (warp == 5) tmem_alloc(&tmem_slot, 512);
+  if (threadIdx.x == 0) {
+    mbar_init(&w_bar, 1);
+    for (int i = 0; i < 2; ++i) mbar_init(&full_bar[i], 1), mbar_init(&empty_bar[i], 1);
+    mbar_init(&acc_full, 1), mbar_init(&acc_empty, 128);
+    mbar_init_fence();
+  }
+  if (threadIdx.x < 8) s_scale[threadIdx.x] = a.scale[threadIdx.x] * (1.f / kWScale), s_shift[threadIdx.x] = a.shift[threadIdx.x];
+  for (uint32_t i = threadIdx.x; i < 4 * plane / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+
+  if (warp == 4) {
+    // ------------------------------------------------------------ loader: rows 3 (c + 12 o) + dp of the halo'd planes
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&w_bar, kSemiWBytes);
+      bulk_g2s(s_w, a.wimg, kSemiWBytes, &w_bar);
+    }
+    int k = 0;
+    for (int item = blockIdx.x; item < a.n_items; item += gridDim.x, ++k) {
+      const int s = k & 1;
+      int b, c, t0;
+      decode(item, b, c, t0);
+      const int cols_in = min(Wt, a.Wd - (t0 + 2));
+      const uint32_t row_bytes = (uint32_t)cols_in * 16;
+      mbar_wait_relaxed(&empty_bar[s], ((k >> 1) & 1) ^ 1);
+      if (lane == 0) mbar_arrive_expect_tx(&full_bar[s], 2u * rows_in * row_bytes);
+      __syncwarp();
+      uint8_t* dst = smem + (size_t)s * 2 * plane;
+      for (int r = lane; r < rows_in; r += 32) {
+        const int o = r / 3, dp = r - 3 * o;
+        const long long src = (((long long)b * (a.P + 6) + 3 * (c + 12 * o) + dp + 3) * a.Wd + t0 + 2) * 8;
+        bulk_g2s(dst + (size_t)r * Wt * 16, a.in_hi + src, row_bytes, &full_bar[s]);
+        bulk_g2s(dst + plane + (size_t)r * Wt * 16, a.in_lo + src, row_bytes, &full_bar[s]);
+      }
+    }
+  } else if (warp == 5) {
+    // ------------------------------------------------------------ MMA issuer (converged warp, one elected lane issues)
+    const uint64_t A_DESC = desc_hi(plane);        // chunk 1 = the x_lo plane at the same position
+    constexpr uint64_t B_DESC = desc_hi(48 * 16);  // chunk stride: 48 rows x 16 B
+    constexpr uint32_t IDESC = idesc_f16(48);
+    const uint32_t w0 = smem_u32(s_w);
+    mbar_wait(&w_bar, 0);
+    int k = 0;
+    for (int item = blockIdx.x; item < a.n_items; item += gridDim.x, ++k) {
+      const int s = k & 1;
+      const uint32_t hi0 = smem_u32(smem + (size_t)s * 2 * plane);
+      mbar_wait(&full_bar[s], (k >> 1) & 1);
+      mbar_wait(&acc_empty, (k & 1) ^ 1);
+      fence_after_sync();
+      if (elect_one()) {
+        for (int o = 0; o < n_oct; ++o) {
+#pragma unroll
+          for (int dp = 0; dp < 3; ++dp)
+            mma_f16(tmem + o * 48, make_desc(A_DESC, hi0 + (uint32_t)((3 * o + dp) * Wt) * 16), make_desc(B_DESC, w0 + dp * (2 * 48 * 16)), IDESC,
+                    dp ? 1u : 0u);
+        }
+        commit(&acc_full);
+        commit(&empty_bar[s]);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue: thread = TMEM lane = frame t0 + tid
+    const int tid = threadIdx.x, wq = warp;
+    const uint32_t acc = tmem + ((uint32_t)(wq * 32) << 16);
+    int k = 0;
+    for (int item = blockIdx.x; item < a.n_items; item += gridDim.x, ++k) {
+      int b, c, t0;
+      decode(item, b, c, t0);
+      mbar_wait_relaxed(&acc_full, k & 1);
+      fence_after_sync();
+      // pass 1: per octave, D_dt = columns [16 dt, 16 dt + 8) + [16 dt + 8, 16 dt + 16); s = D_0[a] + D_1[a + 1] + D_2[a + 2] with
+      // the in-warp part by shuffles; lanes 0, 1 of warps 1..3 publish what lanes 30, 31 of the previous warp still need
+      uint64_t sacc[kSemiMaxOct][4];
+#pragma unroll
+      for (int o = 0; o < kSemiMaxOct; ++o) {
+        if (o < n_oct) {
+          uint32_t v0[16], v1[16], v2[16];
+          tmem_ld16_issue(acc + o * 48, v0);
+          tmem_ld16_issue(acc + o * 48 + 16, v1);
+          tmem_ld16_issue(acc + o * 48 + 32, v2);
+          tmem_ld_wait16(v0), tmem_ld_wait16(v1), tmem_ld_wait16(v2);
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            sacc[o][e] = f2_add(f2_pack(__uint_as_float(v0[2 * e]), __uint_as_float(v0[2 * e + 1])),
+                                f2_pack(__uint_as_float(v0[8 + 2 * e]), __uint_as_float(v0[9 + 2 * e])));
+#pragma unroll
+          for (int f = 1; f < 3; ++f) {
+            const uint32_t(&v)[16] = f == 1 ? v1 : v2;
+            float x[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) x[e] = __uint_as_float(v[e]) + __uint_as_float(v[8 + e]);
+            if (wq > 0 && lane < f) {
+              float4* dst = pub + ((o * 3 + (wq - 1)) * 3 + (f - 1) + lane) * 2;
+              dst[0] = make_float4(x[0], x[1], x[2], x[3]), dst[1] = make_float4(x[4], x[5], x[6], x[7]);
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) x[e] = __shfl_down_sync(0xffffffffu, x[e], f);
+            const float mk = (lane + f < 32) ? 1.f : 0.f;  // masked FMA = predicated add (see p2p_umma_kernel)
+            const uint64_t mk2 = f2_pack(mk, mk);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) sacc[o][e] = f2_fma(f2_pack(x[2 * e], x[2 * e + 1]), mk2, sacc[o][e]);
+          }
+        }
+      }
+      fence_before_sync();
+      mbar_arrive(&acc_empty);  // accumulators drained: the issuer may start the next item
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      // pass 2: the cross-warp contributions (ascending tap order on every lane), BN + LeakyReLU, octave max
+      float best[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) best[e] = -INFINITY;
+#pragma unroll
+      for (int o = 0; o < kSemiMaxOct; ++o) {
+        if (o < n_oct) {
+          if (wq < 3 && lane >= 30) {
+#pragma unroll
+            for (int f = 1; f < 3; ++f) {
+              const bool take = lane + f >= 32;
+              const float4* src = pub + ((o * 3 + wq) * 3 + (f - 1) + (take ? lane + f - 32 : 0)) * 2;
+              const float4 x0 = src[0], x1 = src[1];
+              const float mk = take ? 1.f : 0.f;
+              const uint64_t mk2 = f2_pack(mk, mk);
+              sacc[o][0] = f2_fma(f2_pack(x0.x, x0.y), mk2, sacc[o][0]), sacc[o][1] = f2_fma(f2_pack(x0.z, x0.w), mk2, sacc[o][1]);
+              sacc[o][2] = f2_fma(f2_pack(x1.x, x1.y), mk2, sacc[o][2]), sacc[o][3] = f2_fma(f2_pack(x1.z, x1.w), mk2, sacc[o][3]);
+            }
+          }
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float y0, y1;
+            f2_unpack(f2_fma(sacc[o][e], f2_pack(s_scale[2 * e], s_scale[2 * e + 1]), f2_pack(s_shift[2 * e], s_shift[2 * e + 1])), y0, y1);
+            best[2 * e] = fmaxf(best[2 * e], fmaxf(y0, kLeakySlope * y0)), best[2 * e + 1] = fmaxf(best[2 * e + 1], fmaxf(y1, kLeakySlope * y1));
+          }
+        }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // the hand-over buffer is reused by the next item
+      const int t = t0 + tid;
+      const long long row0 = (((long long)b * 2 + 0) * 23 + c) * a.Wd, row1 = (((long long)b * 2 + 1) * 23 + c) * a.Wd;
+      const long long wr = (long long)12 * a.Wd * 8;
+      if (tid < a.TB && t < a.T) {
+        float g0[8], g1[8];
+#pragma unroll
+        for (int ci = 0; ci < 4; ++ci) g0[ci] = __ldg(a.pc_prev + (((long long)b * 4 + ci) * 12 + c) * a.T + t);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) g0[4 + e] = best[e], g1[e] = best[4 + e], g1[4 + e] = 0.f;
+        const long long q0 = (row0 + t + 3) * 8, q1 = (row1 + t + 3) * 8;
+        store_split8(a.out_hi + q0, a.out_lo + q0, g0);
+        store_split8(a.out_hi + q1, a.out_lo + q1, g1);
+        if (c < 11) {  // wrap rows 12..22 = rows 0..10 (models.py:27-28)
+          store_split8(a.out_hi + q0 + wr, a.out_lo + q0 + wr, g0);
+          store_split8(a.out_hi + q1 + wr, a.out_lo + q1 + wr, g1);
+        }
+      }
+      if (t0 == 0 && tid < 6) {
+        // zero halo columns 0..2 and T + 3..T + 5 (the "same" padding of the equivariant convs, models.py:45-47)
+        const int col = tid < 3 ? tid : a.T + tid;
+        const uint4 z = make_uint4(0, 0, 0, 0);
+        for (int g = 0; g < 2; ++g) {
+          const long long q = ((g ? row1 : row0) + col) * 8;
+          *reinterpret_cast<uint4*>(a.out_hi + q) = z, *reinterpret_cast<uint4*>(a.out_lo + q) = z;
+          if (c < 11) *reinterpret_cast<uint4*>(a.out_hi + q + wr) = z, *reinterpret_cast<uint4*>(a.out_lo + q + wr) = z;
+        }
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc(tmem, 512);
+}
+
 // ---- equivariant pitch-class convolution (models.py:22-51) on tensor cores -----------------------------------------
 //   out[co, c, t] = sum_{ci<16, dp<12, dt<7} W[co,ci,dp,dt] x[ci, (c+dp) mod 12, t + dt - pad]
 // Input: 16-channel chunk planes [B][2 groups][23 rows][Wd][8] (rows 12..22 wrap, zero halo columns for "same" layers).
