@@ -770,7 +770,7 @@ void Fwd::run(const float* mel, float* key_out, float* tonic_out, float* genre_o
     return x;
   };
   View tonic_f, key_f, genre_f;
-  bool heads_done = false;
+  bool heads_done = false, heads_folded = false;
   if (umma_pc_ready && p->umma_heads && Tn >= 13) {
     // first conv of both heads in one tensor-core pass (16 -> 32 | 32, valid in time), then the 32 -> 1 convs
     const int T1 = Tn - (k - 1), Tf = T1 - (k - 1);
@@ -810,7 +810,27 @@ void Fwd::run(const float* mel, float* key_out, float* tonic_out, float* genre_o
     // last conv of every head (32 -> 1) in one tensor-core launch
     tonic_f = alloc(1, 12, Tf), key_f = alloc(1, 12, Tf);
     if (cfg.genre) genre_f = alloc(1, 11, Tf);
-    if (!dry && Tf > 0) {
+    if (!dry && Tf > 0 && !cfg.max_pool) {
+      // the last conv is linear and only its temporal mean is used: fold it into 7 windowed time sums per (channel, row)
+      ProfScope prof("pcn.heads", st);
+      HeadFoldArgs fa{};
+      const int nh = cfg.genre ? 3 : 2;
+      const Conv* hc[3] = {&p->convs[p->tonic_head[1]], &p->convs[p->key_head[1]], cfg.genre ? &p->convs[p->genre_head[1]] : nullptr};
+      float* ho[3] = {tonic_out, key_out, genre_out};
+      for (int h = 0; h < nh; ++h) {
+        const bool eq = h < 2;
+        fa.in_hi[h] = eq ? hk_hi : g_hi, fa.in_lo[h] = eq ? hk_lo : g_lo;
+        fa.G_total[h] = eq ? 8 : 4, fa.g0[h] = h == 1 ? 4 : 0, fa.R[h] = eq ? 23 : 12, fa.KH[h] = hc[h]->KH, fa.rows_out[h] = eq ? 12 : 11;
+        fa.wrap[h] = eq, fa.sigmoid[h] = h == 1;
+        fa.w[h] = p->d_params + hc[h]->w_off, fa.bias[h] = p->d_params + hc[h]->b_off, fa.out[h] = ho[h];
+      }
+      int pool_div = 1;
+      for (int i = 0; i < cfg.num_layers - 1; ++i) pool_div *= cfg.time_pool_size;
+      fa.seq_len = seq_len, fa.T1 = T1, fa.Tf = Tf, fa.pool_div = pool_div, fa.head_shrink = (k - 1) * cfg.head_layers;
+      head_fold_kernel<<<dim3(B, nh), 256, 0, st>>>(fa);
+      AKE_LAUNCHED();
+      heads_folded = true;
+    } else if (!dry && Tf > 0) {
       ProfScope prof("pcn.heads", st);
       HeadUmmaArgs ha{};
       const int nh = cfg.genre ? 3 : 2;
@@ -834,7 +854,7 @@ void Fwd::run(const float* mel, float* key_out, float* tonic_out, float* genre_o
       head_tail_umma_kernel<<<dim3(ha.n_ttiles, nh, B), 160, smem_h, st>>>(ha);
       AKE_LAUNCHED();
     }
-    tap("tonic_frames", tonic_f), tap("key_frames", key_f);
+    if (!heads_folded) tap("tonic_frames", tonic_f), tap("key_frames", key_f);  // folded: no per-frame head outputs exist
     heads_done = true;
   } else {
     tonic_f = head(p->tonic_head, true, "tonic_frames");
@@ -843,7 +863,7 @@ void Fwd::run(const float* mel, float* key_out, float* tonic_out, float* genre_o
   if (cfg.genre && !heads_done) genre_f = head(p->genre_head, false, "genre_frames");
   if (tonic_f.T <= 0) fail(AKE_ERR_INVALID, "T=%d is too short: the heads need more than %d frames after pooling", T,
                            (k - 1) * cfg.head_layers);
-  if (!dry) {
+  if (!dry && !heads_folded) {
     int pool_div = 1;
     for (int i = 0; i < cfg.num_layers - 1; ++i) pool_div *= cfg.time_pool_size;
     const int rows = cfg.genre ? 35 : 24;

@@ -500,6 +500,107 @@ __global__ void head_reduce_kernel(const float* __restrict__ key_f, const float*
   if (lane == 0) *dst = v;
 }
 
+// ---- last head convolution folded into the temporal mean (eval fast path, max_pool off) ------------------------------------
+// models.py:716-742, 754-804: out[c] = mean_{t < n} conv2(y)[c, t] with conv2 linear (32 -> 1 channel, KH x 7, valid in time, no
+// activation behind it), hence  out[c] = b + (1/n) sum_{ci, dp, dt} W[ci, dp, dt] * S[ci, row(c, dp), dt],
+// S[ci, r, dt] = sum_{t < n} y[ci, r, t + dt]  -- 7 windowed time sums per (channel, row) instead of a convolution over every frame.
+// One block per (clip, head).  y = first-conv output as fp16 hi/lo chunk planes [B][G_total][R][T1][8] (equiv_umma_kernel EPI 3).
+// Every row / pitch class runs the same instruction sequence (bit-exact transposition equivariance of key and tonic).
+struct HeadFoldArgs {
+  const __half* in_hi[3];
+  const __half* in_lo[3];
+  const float* w[3];      // (1, 32, KH, 7) fp32, reference layout
+  const float* bias[3];
+  float* out[3];          // key_out (B,12) [sigmoid], tonic_out (B,12), genre_out (B,11)
+  int G_total[3], g0[3], R[3], KH[3], rows_out[3], wrap[3], sigmoid[3];
+  const int* seq_len;     // or NULL
+  int T1, Tf, pool_div, head_shrink;
+};
+
+__global__ void __launch_bounds__(256) head_fold_kernel(const HeadFoldArgs a) {
+  __shared__ float S[32 * 12 * 7];     // [ci][row][dt]
+  __shared__ float edge[4 * 12 * 12 * 8];  // [group][row][j 12 = head 0..5, tail 0..5][8 ch]: y[j] and y[n + j]
+  const int h = blockIdx.y, b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int n = a.Tf;
+  if (a.seq_len) n = min(a.Tf, a.seq_len[b] / a.pool_div - a.head_shrink);  // models.py:757-760; slicing clamps
+  float* out = a.out[h] + (long long)b * a.rows_out[h];
+  if (n <= 0) {  // empty slice: torch.mean -> nan
+    if (threadIdx.x < a.rows_out[h]) out[threadIdx.x] = __int_as_float(0x7fc00000);
+    return;
+  }
+  const int R = a.R[h];
+  // ---- windowed sums: unit (group g, row r) per warp; lanes stride over frames
+  for (int u = warp; u < 48; u += 8) {
+    const int g = u / 12, r = u - 12 * g;
+    const long long base = ((((long long)b * a.G_total[h] + a.g0[h] + g) * R + r) * a.T1) * 8;
+    float s0[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s0[e] = 0.f;
+    for (int t = lane; t < n + 6; t += 32) {
+      const uint4 hv = __ldg(reinterpret_cast<const uint4*>(a.in_hi[h] + base + (long long)t * 8));
+      const uint4 lv = __ldg(reinterpret_cast<const uint4*>(a.in_lo[h] + base + (long long)t * 8));
+      const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w}, lw[4] = {lv.x, lv.y, lv.z, lv.w};
+      float y[8];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[e]));
+        const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lw[e]));
+        y[2 * e] = hf.x + lf.x, y[2 * e + 1] = hf.y + lf.y;
+      }
+      if (t < n) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) s0[e] += y[e];
+      }
+      if (t < 6 || t >= n) {
+        const int j = t < 6 ? t : 6 + (t - n);  // a frame can be both (n < 6): the tail copy is written by the second branch below
+        float* d = edge + ((g * 12 + r) * 12 + j) * 8;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) d[e] = y[e];
+        if (t < 6 && t >= n) {
+          float* d2 = edge + ((g * 12 + r) * 12 + 6 + (t - n)) * 8;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) d2[e] = y[e];
+        }
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+      for (int o = 16; o; o >>= 1) s0[e] += __shfl_xor_sync(0xffffffffu, s0[e], o);
+    __syncwarp();
+    // S[dt] = S[dt - 1] - y[dt - 1] + y[n + dt - 1]: lanes 0..7 = the 8 channels of the group
+    if (lane < 8) {
+      float sv = s0[lane];
+      const float* ed = edge + (g * 12 + r) * 12 * 8 + lane;
+      float* dst = S + ((g * 8 + lane) * 12 + r) * 7;
+      dst[0] = sv;
+#pragma unroll
+      for (int dt = 1; dt < 7; ++dt) {
+        sv = sv - ed[(dt - 1) * 8] + ed[(6 + dt - 1) * 8];
+        dst[dt] = sv;
+      }
+    }
+  }
+  __syncthreads();
+  // ---- out[c] = b + (1/n) sum W[ci][dp][dt] S[ci][row][dt]: one warp per output row, lanes over the (ci, dp, dt) triples
+  const int KH = a.KH[h], n_w = 32 * KH * 7;
+  const float* w = a.w[h];
+  for (int c = warp; c < a.rows_out[h]; c += 8) {
+    float acc = 0.f;
+    for (int i = lane; i < n_w; i += 32) {
+      const int dt = i % 7, q = i / 7, dp = q % KH, ci = q / KH;
+      int row = c + dp;
+      if (a.wrap[h]) row -= row >= 12 ? 12 : 0;
+      acc = fmaf(__ldg(w + i), S[(ci * 12 + row) * 7 + dt], acc);
+    }
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+      float v = acc / (float)n + __ldg(a.bias[h]);
+      if (a.sigmoid[h]) v = 1.f / (1.f + expf(-v));
+      out[c] = v;
+    }
+  }
+}
+
 // ---- key / tonic / genre decode (models.py:1083-1085, 1096, 923) --------------------------------
 __constant__ unsigned short kKeySignatureBits[21] = {
     // bit (11 - pc) set when pitch class pc belongs to the signature; rows of utils/key_signatures.py:19-42

@@ -182,47 +182,60 @@ __global__ void __launch_bounds__(GEN ? kP2PThreadsGen : kP2PThreads, 1) p2p_umm
         mbar_arrive_expect_tx(&w_bar, kP2PWBytes);
         bulk_g2s(s_w, a.wimg, kP2PWBytes, &w_bar);
       }
-      const uint32_t wt_magic = 0xFFFFFFFFu / (uint32_t)Wt + 1;
+      const int gw = warp - 4 * G;  // generator warp: rows gw, gw + NLOAD, ... of the tile, 32 consecutive columns per round
       int k = 0;
       for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++k) {
         const int s = k % kP2PBufs;
         const Geom g = geom(tile);
-        const int n_pos = (g.PB + 6) * Wt;
         mbar_wait_relaxed(&empty_bar[s], ((k / kP2PBufs) & 1) ^ 1);
         uint4* d_hi = reinterpret_cast<uint4*>(smem + (size_t)s * 2 * plane);
         uint4* d_lo = reinterpret_cast<uint4*>(smem + (size_t)s * 2 * plane + plane);
         const float* mel_b = a.mel + (long long)g.b * a.P * a.T;
         const float4* up_b = a.up + (long long)g.b * 36 * a.T;
-        // six positions per round, all twelve loads in flight before the first split (one round trip to L2 per round, not per
-        // position: 17 positions per thread and tile would otherwise cost more than the tile's MMAs)
-        constexpr int kBatch = 3;
-        for (int q0 = gt; q0 < n_pos; q0 += kBatch * 32 * NLOAD) {
+        for (int row = gw; row < g.PB + 6; row += NLOAD) {
+          // per row: the (circular) pitch and its table row are fixed; columns beyond the planes' width (narrow last time
+          // tile) only feed discarded anchors and are skipped
+          int p = g.p0 + row - 3;
+          p += (p < 0) ? a.P : 0, p -= (p >= a.P) ? a.P : 0;
+          const float* mel_r = mel_b + (long long)p * a.T;
+          const float4* up_r = up_b + (p % 36) * a.T;
+          uint4* r_hi = d_hi + row * Wt;
+          uint4* r_lo = d_lo + row * Wt;
+          constexpr int kBatch = 5;  // 5 x 32 columns >= kP2PMaxTB + 6: all loads of a row in flight before the first split
           float m0[kBatch];
           float4 u[kBatch];
 #pragma unroll
           for (int i = 0; i < kBatch; ++i) {
-            const int q = q0 + i * 32 * NLOAD;
-            const int row = (int)__umulhi((uint32_t)q, wt_magic), col = q - row * Wt;
+            const int col = lane + 32 * i;
             m0[i] = 0.f, u[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            // columns beyond the planes' width (narrow last time tile) only feed discarded anchors: zeros
-            if (q < n_pos && col < g.cols_in) {
-              int p = g.p0 + row - 3, t = g.t0 + col - 3;
-              p += (p < 0) ? a.P : 0, p -= (p >= a.P) ? a.P : 0;
+            if (col < g.cols_in) {
+              int t = g.t0 + col - 3;
               t += (t < 0) ? a.T : 0, t -= (t >= a.T) ? a.T : 0;
-              m0[i] = __ldg(mel_b + (long long)p * a.T + t);
-              u[i] = __ldg(up_b + (p % 36) * a.T + t);
+              m0[i] = __ldg(mel_r + t);
+              u[i] = __ldg(up_r + t);
             }
           }
 #pragma unroll
           for (int i = 0; i < kBatch; ++i) {
-            const int q = q0 + i * 32 * NLOAD;
-            if (q < n_pos) {
+            const int col = lane + 32 * i;
+            if (col < g.cols_in) {
               uint32_t h[3], l[3];
               split_f16x2(m0[i], u[i].x, h[0], l[0]);
               split_f16x2(u[i].y, u[i].z, h[1], l[1]);
               split_f16x2(u[i].w, 0.f, h[2], l[2]);
-              d_hi[q] = make_uint4(h[0], h[1], h[2], 0), d_lo[q] = make_uint4(l[0], l[1], l[2], 0);
+              r_hi[col] = make_uint4(h[0], h[1], h[2], 0), r_lo[col] = make_uint4(l[0], l[1], l[2], 0);
             }
+          }
+          for (int col = lane + 32 * kBatch; col < g.cols_in; col += 32) {  // (wider tiles than kP2PMaxTB allows: not reached)
+            int t = g.t0 + col - 3;
+            t += (t < 0) ? a.T : 0, t -= (t >= a.T) ? a.T : 0;
+            const float mm = __ldg(mel_r + t);
+            const float4 uu = __ldg(up_r + t);
+            uint32_t h[3], l[3];
+            split_f16x2(mm, uu.x, h[0], l[0]);
+            split_f16x2(uu.y, uu.z, h[1], l[1]);
+            split_f16x2(uu.w, 0.f, h[2], l[2]);
+            r_hi[col] = make_uint4(h[0], h[1], h[2], 0), r_lo[col] = make_uint4(l[0], l[1], l[2], 0);
           }
         }
         fence_proxy_async();

@@ -109,7 +109,7 @@ def test_layer_by_layer_against_oracle(cfg, B, T):
             continue
         _close(t.reshape(ref.shape), ref.numpy(), 5e-5)
         checked += 1
-    assert checked >= 4
+    assert checked >= 3  # (the fast path folds the last head conv into the temporal mean: no per-frame head outputs to tap)
     for r, w in zip(got, want):
         _close(r, w.numpy())
     assert len(got) == len(want) == (3 if genre else 2)
