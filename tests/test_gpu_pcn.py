@@ -204,3 +204,10 @@ def test_tensor_core_and_cuda_core_paths_agree(monkeypatch, fwd_golden):
     xl = (torch.rand(2, 1, 288, 401) * 3).cuda()
     for a, b in zip(fast(xl, None), slow(xl, None)):
         assert (a - b).abs().max().item() <= 2e-5
+    # tile-boundary shapes of the persistent kernels: minimum length for the heads (26 frames), odd / even lengths around the
+    # 32-, 76-, 126- and 160-frame tile widths, ragged seq_length, a batch larger than the SM count of work units per clip
+    for B, T in ((1, 26), (3, 27), (2, 63), (2, 64), (1, 127), (2, 153), (1, 160), (1, 161), (2, 255), (1, 321), (7, 77)):
+        xs = (torch.rand(B, 1, 288, T) * 3).cuda()
+        sq = torch.randint(max(26, T - 9), T + 1, (B,)).cuda()
+        for a, b in zip(fast(xs, sq), slow(xs, sq)):
+            assert torch.isfinite(a).all() and (a - b).abs().max().item() <= 2e-5 * max(1.0, b.abs().max().item()), (B, T)
