@@ -40,11 +40,51 @@ def criterion(outputs, key_labels: torch.Tensor, tonic_labels: torch.Tensor, gen
 
 class TrainStep:
     """Fused forward + loss + backward on the device.  ``step(...)`` returns the loss terms and leaves the
-    gradients in ``self.flat_grads`` (and, as views of it, in every parameter's ``.grad``)."""
+    gradients in ``self.flat_grads`` (and, as views of it, in every parameter's ``.grad``).
 
-    def __init__(self, net: PitchClassNet, opt=None):
+    ``graph=True`` captures the ~230 launches of forward + loss + backward into ONE CUDA graph per input shape (static
+    input / output / workspace buffers; the batch is copied into the static inputs and the graph replayed): at the
+    reference's batch size of 8 the step is launch-bound, not compute-bound."""
+
+    def __init__(self, net: PitchClassNet, opt=None, graph: bool = False):
         self.net, self.opt = net, opt if opt is not None else net.opt
         self.flat_grads: Optional[torch.Tensor] = None
+        self.use_graph = bool(graph)
+        self._graphs = {}
+
+    def _buffers(self, dev, B: int, T: int, has_seq: bool):
+        net, lib = self.net, _lib.lib()
+        ws_bytes = lib.ake_pcn_workspace_bytes(net._plan, B, T, 2)
+        if ws_bytes == 0:
+            check(_lib.AKE_ERR_UNSUPPORTED)
+        f32 = dict(dtype=torch.float32, device=dev)
+        i32 = dict(dtype=torch.int32, device=dev)
+        return {
+            "mel": torch.empty((B, 1, net.pitches, T), **f32), "seq": torch.empty(B, **i32) if has_seq else None,
+            "keyl": torch.empty((B, 12), **f32), "tonic_idx": torch.empty(B, **i32),
+            "genre_idx": torch.empty(B, **i32) if net._genre else None,
+            "ws": torch.empty(ws_bytes, dtype=torch.uint8, device=dev),
+            "key": torch.empty((B, 12), **f32), "tonic": torch.empty((B, 12), **f32),
+            "genre": torch.empty((B, 11), **f32) if net._genre else None,
+            "stats": torch.empty(2 * sum(net._bn_channels), **f32), "loss": torch.empty(4, **f32),
+            "dk": torch.empty((B, 12), **f32), "dt": torch.empty((B, 12), **f32),
+            "dg": torch.empty((B, 11), **f32) if net._genre else None,
+            "flat": torch.empty(lib.ake_pcn_param_floats(net._plan), **f32),
+        }
+
+    def _launch(self, bf, B: int, T: int) -> None:
+        """forward (activations kept) -> loss + d(loss)/d(outputs) -> backward, on the current stream."""
+        net, lib = self.net, _lib.lib()
+        ptr = lambda t: t.data_ptr() if t is not None else None  # noqa: E731
+        stream = torch.cuda.current_stream(bf["mel"].device).cuda_stream
+        check(lib.ake_pcn_forward_f32(net._plan, ptr(bf["mel"]), B, T, ptr(bf["seq"]), 2, ptr(bf["key"]), ptr(bf["tonic"]),
+                                      ptr(bf["genre"]), ptr(bf["stats"]), ptr(bf["ws"]), bf["ws"].numel(), stream))
+        check(lib.ake_loss_f32(ptr(bf["key"]), ptr(bf["tonic"]), ptr(bf["genre"]), ptr(bf["keyl"]), ptr(bf["tonic_idx"]),
+                               ptr(bf["genre_idx"]), B, float(_opt(self.opt, "key_weight", 1.0)),
+                               float(_opt(self.opt, "tonic_weight", 1.0)), float(_opt(self.opt, "genre_weight", 0.1)),
+                               ptr(bf["loss"]), ptr(bf["dk"]), ptr(bf["dt"]), ptr(bf["dg"]), stream))
+        check(lib.ake_pcn_backward_f32(net._plan, ptr(bf["dk"]), ptr(bf["dt"]), ptr(bf["dg"]), ptr(bf["flat"]), bf["flat"].numel(),
+                                       ptr(bf["ws"]), bf["ws"].numel(), stream))
 
     def step(self, mel: torch.Tensor, seq_length, key_labels: torch.Tensor, tonic_labels: torch.Tensor,
              genre_labels: Optional[torch.Tensor] = None, assign_grads: bool = True) -> dict:
@@ -53,55 +93,55 @@ class TrainStep:
             raise RuntimeError("TrainStep needs the network in train mode (batch-statistics BatchNorm)")
         if not mel.is_cuda:
             raise RuntimeError("the training step runs on CUDA tensors only; there is no CPU fallback")
-        lib = _lib.lib()
         dev = mel.device
         B, T = int(mel.shape[0]), int(mel.shape[3])
-        x = mel.detach().to(torch.float32).contiguous()
         seq = None
         if seq_length is not None:
-            seq = torch.as_tensor(seq_length).reshape(-1).to(device=dev, dtype=torch.int32).contiguous()
+            seq = torch.as_tensor(seq_length).reshape(-1).to(device=dev, dtype=torch.int32)
             if seq.numel() == 1 and B > 1:
-                seq = seq.expand(B).contiguous()
-        keyl = key_labels.to(device=dev, dtype=torch.float32).contiguous()
-        tonic_idx = tonic_labels.to(dev).argmax(dim=1).to(torch.int32).contiguous()
+                seq = seq.expand(B)
+        tonic_idx = tonic_labels.to(dev).argmax(dim=1).to(torch.int32)
         genre_idx = None
         if net._genre:
             if genre_labels is None:
                 genre_idx = torch.full((B,), -1, dtype=torch.int32, device=dev)
             else:
                 gl = genre_labels.to(dev)
-                genre_idx = torch.where(gl.sum(dim=1) == 1, gl.argmax(dim=1), torch.full((B,), -1, device=dev)).to(torch.int32).contiguous()
+                genre_idx = torch.where(gl.sum(dim=1) == 1, gl.argmax(dim=1), torch.full((B,), -1, device=dev)).to(torch.int32)
         with torch.cuda.device(dev):
-            stream = torch.cuda.current_stream(dev).cuda_stream
-            net._sync_params(dev, stream)
-            ws_bytes = lib.ake_pcn_workspace_bytes(net._plan, B, T, 2)
-            if ws_bytes == 0:
-                check(_lib.AKE_ERR_UNSUPPORTED)
-            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-            key = torch.empty((B, 12), dtype=torch.float32, device=dev)
-            tonic = torch.empty((B, 12), dtype=torch.float32, device=dev)
-            genre = torch.empty((B, 11), dtype=torch.float32, device=dev) if net._genre else None
-            stats = torch.empty(2 * sum(net._bn_channels), dtype=torch.float32, device=dev)
-            check(lib.ake_pcn_forward_f32(net._plan, x.data_ptr(), B, T, seq.data_ptr() if seq is not None else None, 2,
-                                          key.data_ptr(), tonic.data_ptr(), genre.data_ptr() if genre is not None else None,
-                                          stats.data_ptr(), ws.data_ptr(), ws.numel(), stream))
-            loss = torch.empty(4, dtype=torch.float32, device=dev)
-            dk, dt = torch.empty_like(key), torch.empty_like(tonic)
-            dg = torch.empty_like(genre) if genre is not None else None
-            check(lib.ake_loss_f32(key.data_ptr(), tonic.data_ptr(), genre.data_ptr() if genre is not None else None,
-                                   keyl.data_ptr(), tonic_idx.data_ptr(), genre_idx.data_ptr() if genre_idx is not None else None, B,
-                                   float(_opt(self.opt, "key_weight", 1.0)), float(_opt(self.opt, "tonic_weight", 1.0)),
-                                   float(_opt(self.opt, "genre_weight", 0.1)), loss.data_ptr(), dk.data_ptr(), dt.data_ptr(),
-                                   dg.data_ptr() if dg is not None else None, stream))
-            flat = torch.empty(lib.ake_pcn_param_floats(net._plan), dtype=torch.float32, device=dev)
-            check(lib.ake_pcn_backward_f32(net._plan, dk.data_ptr(), dt.data_ptr(), dg.data_ptr() if dg is not None else None,
-                                           flat.data_ptr(), flat.numel(), ws.data_ptr(), ws.numel(), stream))
-        net._update_running_stats(stats, B, T)
-        self.flat_grads = flat
+            net._sync_params(dev, torch.cuda.current_stream(dev).cuda_stream)
+            sig = (str(dev), B, T, seq is not None)
+            entry = self._graphs.get(sig) if self.use_graph else None
+            bf = entry[0] if entry else self._buffers(dev, B, T, seq is not None)
+            bf["mel"].copy_(mel.detach().reshape(bf["mel"].shape))
+            bf["keyl"].copy_(key_labels.to(dev))
+            bf["tonic_idx"].copy_(tonic_idx)
+            if seq is not None:
+                bf["seq"].copy_(seq)
+            if genre_idx is not None:
+                bf["genre_idx"].copy_(genre_idx)
+            if not self.use_graph:
+                self._launch(bf, B, T)
+            else:
+                if entry is None:
+                    # warm-up on a side stream (lazy one-time initialisation must not happen under capture), then capture
+                    side = torch.cuda.Stream(device=dev)
+                    side.wait_stream(torch.cuda.current_stream(dev))
+                    with torch.cuda.stream(side):
+                        self._launch(bf, B, T)
+                    torch.cuda.current_stream(dev).wait_stream(side)
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        self._launch(bf, B, T)
+                    entry = (bf, g)
+                    self._graphs[sig] = entry
+                entry[1].replay()
+        net._update_running_stats(bf["stats"], B, T)
+        self.flat_grads = bf["flat"]
         if assign_grads:
             self.assign_grads()
-        return {"loss": loss[0], "bce": loss[1], "tonic": loss[2], "genre": loss[3], "key_out": key, "tonic_out": tonic,
-                "genre_out": genre}
+        return {"loss": bf["loss"][0], "bce": bf["loss"][1], "tonic": bf["loss"][2], "genre": bf["loss"][3], "key_out": bf["key"],
+                "tonic_out": bf["tonic"], "genre_out": bf["genre"]}
 
     def assign_grads(self) -> None:
         """Point every parameter's .grad at its slice of the flat buffer (call again after an all-reduce in place)."""

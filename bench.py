@@ -41,6 +41,7 @@ def parse_args():
     ap.add_argument("--no-genre", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="--train: launch the step's kernels one by one instead of as a CUDA graph")
     ap.add_argument("--train", action="store_true",
                     help="BASELINE configs[4] instead of the headline metric: training step (fwd + loss + bwd, batch 8 per GPU, "
                          "train-mode BN) with ONE flat gradient all-reduce over NCCL; prints its own JSON line")
@@ -401,7 +402,7 @@ def run_train(args):
     net = ake.PitchClassNet(36 * OCTAVES, 12, 2, 7, opt=ake.default_opt(genre=True))
     net.load_state_dict(sd, strict=True)
     net = net.to(dev).train()
-    ts = ake.TrainStep(net)
+    ts = ake.TrainStep(net, graph=not args.no_graph)  # the step's ~230 launches replayed as one CUDA graph
     mel, seq, key_labels, tonic_1h, genre_1h = (t.to(dev) for t in (mel, seq, key_labels, tonic_1h, genre_1h))
 
     def step():

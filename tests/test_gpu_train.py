@@ -129,3 +129,40 @@ def test_fused_adam_matches_torch_adam():
         o1, o2 = net(mel, None), ref(mel, None)
     for x, y in zip(o1, o2):
         assert (x - y).abs().max().item() <= 1e-4
+
+
+def test_graph_replay_equals_eager_step():
+    """TrainStep(graph=True): forward + loss + backward captured once per shape and replayed; gradients, loss and
+    BatchNorm statistics must equal the eager launches (same kernels, same order; gradients to the rounding of their atomic
+    accumulation), also after the inputs and the parameters change between replays."""
+    import audio_key_estimation_b200 as ake
+
+    torch.manual_seed(1)
+    opt = ake.default_opt(genre=True)
+    nets = []
+    for _ in range(2):
+        n = ake.PitchClassNet(288, 12, 2, 7, opt=opt).cuda().train()
+        nets.append(n)
+    nets[1].load_state_dict(nets[0].state_dict(), strict=True)
+    eager, graph = ake.TrainStep(nets[0]), ake.TrainStep(nets[1], graph=True)
+    B, T = 4, 61
+    for it in range(3):
+        mel = torch.rand(B, 1, 288, T, device="cuda") * 3
+        seq = torch.randint(40, T + 1, (B,), device="cuda")
+        keyl = (torch.rand(B, 12, device="cuda") < 0.6).float()
+        tonic = torch.nn.functional.one_hot(torch.randint(0, 12, (B,)), 12).cuda()
+        genre = torch.nn.functional.one_hot(torch.randint(0, 11, (B,)), 11).cuda()
+        r0 = eager.step(mel, seq, keyl, tonic, genre)
+        r1 = graph.step(mel, seq, keyl, tonic, genre)
+        assert torch.equal(r0["loss"], r1["loss"]), it  # the forward is deterministic
+        # the weight-gradient kernels accumulate with fp32 atomics: two runs agree to rounding, not bit for bit
+        scale = eager.flat_grads.abs().max().item()
+        assert (eager.flat_grads - graph.flat_grads).abs().max().item() <= 1e-5 * scale, it
+        for (n0, b0), (n1, b1) in zip(nets[0].named_buffers(), nets[1].named_buffers()):
+            assert torch.equal(b0, b1), n0
+        with torch.no_grad():  # an optimizer step between replays: the graph must see the new parameters
+            for p0, p1 in zip(nets[0].parameters(), nets[1].parameters()):
+                upd = 0.01 * torch.sign(p0.grad)  # the same update on both copies
+                p0.add_(upd)
+                p1.add_(upd)
+    assert len(graph._graphs) == 1
