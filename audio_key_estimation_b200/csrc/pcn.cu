@@ -827,7 +827,7 @@ void Fwd::run(const float* mel, float* key_out, float* tonic_out, float* genre_o
       int pool_div = 1;
       for (int i = 0; i < cfg.num_layers - 1; ++i) pool_div *= cfg.time_pool_size;
       fa.seq_len = seq_len, fa.T1 = T1, fa.Tf = Tf, fa.pool_div = pool_div, fa.head_shrink = (k - 1) * cfg.head_layers;
-      head_fold_kernel<<<dim3(B, nh), 256, 0, st>>>(fa);
+      head_fold_kernel<<<dim3(B, nh), 512, 0, st>>>(fa);
       AKE_LAUNCHED();
       heads_folded = true;
     } else if (!dry && Tf > 0) {

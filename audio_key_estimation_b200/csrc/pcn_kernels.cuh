@@ -517,7 +517,7 @@ struct HeadFoldArgs {
   int T1, Tf, pool_div, head_shrink;
 };
 
-__global__ void __launch_bounds__(256) head_fold_kernel(const HeadFoldArgs a) {
+__global__ void __launch_bounds__(512) head_fold_kernel(const HeadFoldArgs a) {
   __shared__ float S[32 * 12 * 7];     // [ci][row][dt]
   __shared__ float edge[4 * 12 * 12 * 8];  // [group][row][j 12 = head 0..5, tail 0..5][8 ch]: y[j] and y[n + j]
   const int h = blockIdx.y, b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -530,12 +530,14 @@ __global__ void __launch_bounds__(256) head_fold_kernel(const HeadFoldArgs a) {
   }
   const int R = a.R[h];
   // ---- windowed sums: unit (group g, row r) per warp; lanes stride over frames
-  for (int u = warp; u < 48; u += 8) {
+  constexpr int kWarps = 16;
+  for (int u = warp; u < 48; u += kWarps) {
     const int g = u / 12, r = u - 12 * g;
     const long long base = ((((long long)b * a.G_total[h] + a.g0[h] + g) * R + r) * a.T1) * 8;
     float s0[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) s0[e] = 0.f;
+#pragma unroll 3
     for (int t = lane; t < n + 6; t += 32) {
       const uint4 hv = __ldg(reinterpret_cast<const uint4*>(a.in_hi[h] + base + (long long)t * 8));
       const uint4 lv = __ldg(reinterpret_cast<const uint4*>(a.in_lo[h] + base + (long long)t * 8));
@@ -584,8 +586,9 @@ __global__ void __launch_bounds__(256) head_fold_kernel(const HeadFoldArgs a) {
   // ---- out[c] = b + (1/n) sum W[ci][dp][dt] S[ci][row][dt]: one warp per output row, lanes over the (ci, dp, dt) triples
   const int KH = a.KH[h], n_w = 32 * KH * 7;
   const float* w = a.w[h];
-  for (int c = warp; c < a.rows_out[h]; c += 8) {
+  for (int c = warp; c < a.rows_out[h]; c += kWarps) {
     float acc = 0.f;
+#pragma unroll 4
     for (int i = lane; i < n_w; i += 32) {
       const int dt = i % 7, q = i / 7, dp = q % KH, ci = q / KH;
       int row = c + dp;
