@@ -51,6 +51,7 @@ class TrainStep:
         self.flat_grads: Optional[torch.Tensor] = None
         self.use_graph = bool(graph)
         self._graphs = {}
+        self.launches_per_step = 0  # graph mode: kernels in the captured step (the library's launch counter only sees the capture)
 
     def _buffers(self, dev, B: int, T: int, has_seq: bool):
         net, lib = self.net, _lib.lib()
@@ -128,7 +129,9 @@ class TrainStep:
                     side = torch.cuda.Stream(device=dev)
                     side.wait_stream(torch.cuda.current_stream(dev))
                     with torch.cuda.stream(side):
+                        n0 = _lib.lib().ake_launch_count(0)
                         self._launch(bf, B, T)
+                        self.launches_per_step = int(_lib.lib().ake_launch_count(0) - n0)  # kernels one replay launches
                     torch.cuda.current_stream(dev).wait_stream(side)
                     g = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(g):

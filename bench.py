@@ -429,6 +429,8 @@ def run_train(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     launches = int(_lib.lib().ake_launch_count(1))
+    if ts.use_graph:  # replays do not pass through the library's launch counter: kernels per captured step x steps
+        launches = ts.launches_per_step * args.steps
     if rank == 0:
         print(json.dumps({"metric": "clips/s PitchClassNet training step (fwd+loss+bwd+grad all-reduce)", "value": B * world * args.steps / (ms * 1e-3),
                           "unit": "clips/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
