@@ -76,7 +76,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "25",
                                           "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
             self.th.start()
@@ -86,7 +86,7 @@ class ClockSampler:
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.03)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
@@ -252,7 +252,6 @@ def run_b200(args):
     launches = int(lib.ake_launch_count(1))
     prof = _lib.profile_collect()
     _lib.profile_enable(False)
-    clocks = sampler.stop() if rank == 0 else None
     value = B * world * args.steps / (ms_total * 1e-3)
 
     # ---- end to end through the C ABI with host buffers ("e2e")
@@ -284,6 +283,7 @@ def run_b200(args):
             if not torch.equal(out_bufs["ids"][j].to(dev), dev_ids):
                 raise SystemExit("e2e ids differ from the device-resident path")
 
+    clocks = sampler.stop() if rank == 0 else None  # sampled across both timed regions (device-resident and end to end)
     if rank != 0:
         if world > 1:
             dist.barrier()
