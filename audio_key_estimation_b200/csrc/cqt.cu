@@ -306,9 +306,10 @@ __device__ __forceinline__ void cas_store_split8(uint8_t* hi_dst, uint8_t* lo_ds
 //   warps 8-9   epilogue 2: level p+2 accumulators (63 rows) -> fp32 stores
 //   warps 10-21 converter: landed fp32 span -> fp16 hi/lo transposed chunk planes (level-p operand), double buffered
 //   warp 22     loader: one bulk async copy per tile span into a two-stage ring
-//   warp 23     MMA issuer (converged, elect.sync): MMA1(i+2) is issued as soon as epilogue 1 has drained accumulator i,
-//               MMA2(i) as soon as its operand planes exist, so the tensor pipe never waits for a whole epilogue
-constexpr int kCasThreads = 768;
+//   warps 23-24 MMA issuers (converged, elect.sync), one per level: MMA1(i+2) is issued as soon as epilogue 1 has drained
+//               accumulator i, MMA2(i) as soon as its operand planes exist; two warps because one cannot issue MMAs of
+//               N <= 64 as fast as the tensor pipe executes them
+constexpr int kCasThreads = 800;
 constexpr int kCasConvThreads = 384;
 constexpr int kCasChunks = kCasP0Rows * 8;                 // 1032 chunks of 8 samples per tile span
 constexpr int kCasSpan = kCasChunks * 8;                   // 8256 input samples per tile
@@ -420,8 +421,8 @@ __global__ void __launch_bounds__(kCasThreads, 1) cascade_umma_kernel(const Casc
       }
       __syncwarp();
     }
-  } else if (warp == 23) {
-    // ------------------------------------------------------------------ MMA issuer
+  } else if (warp >= 23) {
+    // ------------------------------------------------------------------ MMA issuers (warp 23: level p+1, warp 24: level p+2)
     int n_my = 0;
     for (int tile = next_tile(blockIdx.x); tile < a.n_tiles; tile = next_tile(tile + gridDim.x)) ++n_my;
     mbar_wait(&img_bar, 0);
@@ -460,11 +461,13 @@ __global__ void __launch_bounds__(kCasThreads, 1) cascade_umma_kernel(const Casc
       if (elect_one()) issue_level(tmem + 128 + bf * 64, hi0, hi0 + kCasP1Bytes, kCasLBO1, &acc2_full[bf], &p1_empty[bf]);
       __syncwarp();
     };
-    if (n_my > 0) issue1(0);
-    if (n_my > 1) issue1(1);
-    for (int i = 0; i < n_my; ++i) {
-      if (two) issue2(i);
-      if (i + 2 < n_my) issue1(i + 2);
+    // One warp issues at most one MMA per ~65 cycles (tools/umma_rate.cu: 7 x N=64 MMAs per block take 65 cycles each from
+    // one warp, 48 -- the shared-memory operand rate -- from two), so the two levels are issued by two warps: independent
+    // streams that only meet through the plane / accumulator barriers.
+    if (warp == 23) {
+      for (int i = 0; i < n_my; ++i) issue1(i);
+    } else if (two) {
+      for (int i = 0; i < n_my; ++i) issue2(i);
     }
   } else if (warp >= 10) {
     // ------------------------------------------------------------------ converter: stage -> level-p operand planes

@@ -73,7 +73,8 @@ __global__ void __launch_bounds__(128) rate_kernel(Cfg c, int iters, long long* 
 
 // Blocks of `per` MMAs into rotating accumulators (the first MMA of a block overwrites), one tcgen05.commit per block on a
 // barrier nobody waits for: does switching accumulators / committing cost tensor-pipe cycles?
-__global__ void __launch_bounds__(128) block_kernel(int N, int per, int nacc, int commit_each, int iters, long long* cycles) {
+__global__ void __launch_bounds__(128) block_kernel(int N, int per, int nacc, int commit_each, int iters, long long* cycles, uint32_t blk_step,
+                                                     uint32_t tap_step, uint32_t first_acc, int distinct, int n_issue) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(8) uint64_t bar, bars[8];
@@ -95,7 +96,7 @@ __global__ void __launch_bounds__(128) block_kernel(int N, int per, int nacc, in
   const uint32_t tmem = tmem_base_s;
   // converged warp + elect.sync, blocks unrolled: the issue path of the library's kernels (umma.cuh: single-lane issue)
   const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
-  if (warp_u == 0) {
+  if (warp_u < n_issue) {
     const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const uint64_t v1 = (uint64_t)1 << 46;
     const uint64_t hi_a = v1 | ((uint64_t)(128 >> 4) << 32) | ((uint64_t)(37344 >> 4) << 16);
@@ -103,29 +104,41 @@ __global__ void __launch_bounds__(128) block_kernel(int N, int per, int nacc, in
     const uint32_t a0 = smem_u32(smem), b0 = smem_u32(smem) + 80 * 1024;
     long long t0 = clock64();
     for (int it = 0; it < iters; ++it) {
-      const uint32_t d = tmem + (uint32_t)(it & (nacc - 1)) * 128;  // nacc is a power of two: no division on the issue path
-      const uint32_t ab = a0 + (uint32_t)(it & 7) * 1952;
+      const uint32_t d = tmem + (uint32_t)(it & (nacc - 1)) * 128 + (uint32_t)warp_u * 256;  // nacc is a power of two: no division on the issue path
+      const uint32_t ab = a0 + (uint32_t)(it & 7) * blk_step;
       uint32_t el;
       asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(el));
       if (el) {
-        if (per == 7) {
+        if (per == 7 && distinct) {
+          // every MMA gets its own copies of the accumulator address and the instruction descriptor (volatile moves the
+          // compiler cannot merge): do back-to-back UTCHMMAs stall on shared uniform source registers?
+          uint32_t dd[7], id[7];
+#pragma unroll
+          for (int u = 0; u < 7; ++u) {
+            asm volatile("mov.b32 %0, %1;" : "=r"(dd[u]) : "r"(d));
+            asm volatile("mov.b32 %0, %1;" : "=r"(id[u]) : "r"(idesc));
+          }
 #pragma unroll
           for (int u = 0; u < 7; ++u)
-            mma_f16(d, hi_a | (uint64_t)(((ab + (uint32_t)u * 2512) >> 4) & 0x3FFF), hi_b | (uint64_t)(((b0 + (uint32_t)(u % 4) * 3584) >> 4) & 0x3FFF), idesc, u ? 1u : 0u);
+            mma_f16(dd[u], hi_a | (uint64_t)(((ab + (uint32_t)u * tap_step) >> 4) & 0x3FFF), hi_b | (uint64_t)(((b0 + (uint32_t)(u % 4) * 3584) >> 4) & 0x3FFF), id[u], u ? 1u : first_acc);
+        } else if (per == 7) {
+#pragma unroll
+          for (int u = 0; u < 7; ++u)
+            mma_f16(d, hi_a | (uint64_t)(((ab + (uint32_t)u * tap_step) >> 4) & 0x3FFF), hi_b | (uint64_t)(((b0 + (uint32_t)(u % 4) * 3584) >> 4) & 0x3FFF), idesc, u ? 1u : first_acc);
         } else {
 #pragma unroll 4
           for (int u = 0; u < per; ++u)
-            mma_f16(d, hi_a | (uint64_t)(((ab + (uint32_t)u * 2512) >> 4) & 0x3FFF), hi_b | (uint64_t)(((b0 + (uint32_t)(u % 4) * 3584) >> 4) & 0x3FFF), idesc, u ? 1u : 0u);
+            mma_f16(d, hi_a | (uint64_t)(((ab + (uint32_t)u * tap_step) >> 4) & 0x3FFF), hi_b | (uint64_t)(((b0 + (uint32_t)(u % 4) * 3584) >> 4) & 0x3FFF), idesc, u ? 1u : 0u);
         }
         if (commit_each) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bars[it & 7])));
       }
       __syncwarp();
     }
-    if (tid == 0) {
-      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)));
+    if ((tid & 31) == 0) {
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(warp_u ? &bars[7] : &bar)));
       uint32_t done = 0;
-      while (!done) asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(done) : "r"(smem_u32(&bar)), "r"(0));
-      cycles[blockIdx.x] = clock64() - t0;
+      while (!done) asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(done) : "r"(smem_u32(warp_u ? &bars[7] : &bar)), "r"(0));
+      if (warp_u == 0) cycles[blockIdx.x] = clock64() - t0;
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;");
@@ -133,18 +146,19 @@ __global__ void __launch_bounds__(128) block_kernel(int N, int per, int nacc, in
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
 }
 
-static void go_blocks(int N, int per, int nacc, int commit_each) {
+static void go_blocks(int N, int per, int nacc, int commit_each, uint32_t blk_step = 1952, uint32_t tap_step = 2512, uint32_t first_acc = 0, int distinct = 0, int n_issue = 1) {
   const int n_cta = 148, iters = 800;
   long long* cyc_d;
   CK(cudaMalloc(&cyc_d, 8 * n_cta));
   CK(cudaFuncSetAttribute(block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-  block_kernel<<<n_cta, 128, 160 * 1024>>>(N, per, nacc, commit_each, iters, cyc_d);
+  block_kernel<<<n_cta, 128, 160 * 1024>>>(N, per, nacc, commit_each, iters, cyc_d, blk_step, tap_step, first_acc, distinct, n_issue);
   CK(cudaDeviceSynchronize());
   long long* cyc = new long long[n_cta];
   CK(cudaMemcpy(cyc, cyc_d, 8 * n_cta, cudaMemcpyDeviceToHost));
   double mx = 0;
   for (int i = 0; i < n_cta; ++i) mx = cyc[i] > mx ? cyc[i] : mx;
-  printf("blocks of %2d MMAs N%-3d, %d accumulators, commit per block %d: %6.1f cycles/MMA (%6.1f per block)\n", per, N, nacc, commit_each,
+  printf("blocks of %2d MMAs N%-3d, %d accumulators, commit per block %d, A steps %u/%u B: %6.1f cycles/MMA (%6.1f per block)\n", per, N, nacc,
+         commit_each, blk_step, tap_step,
          mx / ((double)iters * per), mx / iters);
   delete[] cyc;
   cudaFree(cyc_d);
@@ -175,6 +189,24 @@ int main(int argc, char** argv) {
     for (int nacc : {1, 2, 4})
       for (int ce : {0, 1}) go_blocks(112, 7, nacc, ce);
     go_blocks(112, 14, 4, 1);
+    go_blocks(112, 7, 4, 1, 1920, 2560);  // every A start 128-byte aligned
+    go_blocks(112, 7, 4, 1, 2048, 2048);
+    go_blocks(112, 7, 4, 1, 1952, 2560);
+    go_blocks(112, 7, 4, 1, 0, 2512);  // loop-invariant descriptors: the bare UTCHMMA issue rate
+    go_blocks(112, 7, 1, 0, 0, 2512);
+    go_blocks(64, 8, 1, 0, 0, 2512);
+    printf("-- first MMA of a block accumulates too (no overwrite):\n");
+    go_blocks(112, 7, 4, 1, 1952, 2512, 1);
+    go_blocks(112, 7, 1, 0, 0, 2512, 1);
+    printf("-- distinct uniform registers per MMA:\n");
+    go_blocks(112, 7, 4, 1, 1952, 2512, 0, 1);
+    go_blocks(64, 7, 4, 1, 1952, 2512, 0, 1);
+    go_blocks(64, 7, 4, 1, 1952, 2512, 0, 0);
+    printf("-- two issuing warps (cycles per MMA of EACH warp: halve for the SM rate):\n");
+    go_blocks(64, 7, 2, 1, 1952, 2512, 0, 0, 2);
+    go_blocks(112, 7, 2, 1, 1952, 2512, 0, 0, 2);
+    go_blocks(32, 7, 2, 1, 1952, 2512, 0, 0, 2);
+    go_blocks(32, 7, 2, 1, 1952, 2512, 0, 0, 1);
     go_blocks(224, 12, 2, 1);
     go_blocks(64, 8, 4, 1);
     return 0;
