@@ -362,12 +362,16 @@ __global__ void __launch_bounds__(kCasThreads, 1) cascade_umma_kernel(const Casc
   // (x / d == umulhi(x, 2^32 / d + 1) while x * d < 2^32)
   const uint32_t tpc_magic = 0xFFFFFFFFu / (uint32_t)a.tiles_per_clip + 1;
   auto clip_of = [&](int tile) { return a.tiles_per_clip == 1 ? tile : (int)__umulhi((uint32_t)tile, tpc_magic); };
+  // Every role decodes every tile between two hand-overs, so this scalar code sits on the pipeline's critical path: the
+  // uniform-length case (no lengths array) takes no global load, no loop and no 64-bit shifts per tile.
+  const bool ragged = a.lengths != nullptr;
+  const long long len_uniform = (a.n_uniform + (1LL << a.level_in) - 1) >> a.level_in;
   auto clip_len = [&](int b) {  // samples of level p in clip b
-    const long long n0 = a.lengths ? a.lengths[b] : a.n_uniform;
-    return (n0 + (1LL << a.level_in) - 1) >> a.level_in;
+    return ragged ? ((a.lengths[b] + (1LL << a.level_in) - 1) >> a.level_in) : len_uniform;
   };
   // first tile at or after `tile` (in this CTA's stride) that has data; tiles beyond a short clip's end write nothing
   auto next_tile = [&](int tile) {
+    if (!ragged) return tile;  // tiles_per_clip covers exactly the tiles that have data
     for (; tile < a.n_tiles; tile += gridDim.x) {
       const int b = clip_of(tile), t = tile - b * a.tiles_per_clip;
       if ((long long)kCasOwn1 * t < ((clip_len(b) + 1) >> 1)) break;
@@ -944,6 +948,10 @@ static void run_cqt(ake_cqt* p, const float* audio, long long stride, const int6
       ca.lengths = d_len, ca.n_uniform = n_max, ca.level_in = lv;
       ca.tiles_per_clip = (int)cdiv64(len_at(n_max, lv + 1), kCasOwn1);
       ca.n_tiles = ca.tiles_per_clip * B;
+      // the kernel decodes tile -> clip by multiply-high, exact while n_tiles * tiles_per_clip < 2^32 (very many very long clips
+      // exceed it): refuse instead of decoding wrongly
+      if ((long long)ca.tiles_per_clip * B * ca.tiles_per_clip >= (1LL << 32))
+        fail(AKE_ERR_UNSUPPORTED, "%d clips x %d tiles exceed the cascade's index decode range; split the batch", B, ca.tiles_per_clip);
       ca.img = p->d_dec_img;
       // level lv+1 is consumed by the filter bank only (the next pass reads level lv+2): when its frames do not overlap,
       // the samples between them are never written

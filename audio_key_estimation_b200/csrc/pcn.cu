@@ -333,6 +333,13 @@ static void launch_conv(const ConvArgs& a, const ConvGeom& g, int co_tile, int B
   fail(AKE_ERR_UNSUPPORTED, "no conv kernel for KH=%d KW=%d SR=%d co_tile=%d", g.KH, g.KW, g.SR, co_tile);
 }
 
+// The persistent kernels decode work-item indices with multiply-high (x / d == umulhi(x, 2^32 / d + 1)), which is exact while
+// x * d < 2^32: refuse launches beyond that instead of decoding wrongly.
+static void check_decode_range(long long n_items, long long divisor, const char* what) {
+  if (n_items * divisor >= (1LL << 32))
+    fail(AKE_ERR_UNSUPPORTED, "%s: %lld work items x %lld exceed the index decode range; split the batch", what, n_items, divisor);
+}
+
 static int ew_blocks(long long n) { return (int)std::min<long long>(cdiv64(n, 256), 148LL * 16); }
 
 struct Fwd {
@@ -542,6 +549,7 @@ void Fwd::run(const float* mel, float* key_out, float* tonic_out, float* genre_o
               configured = smem;
             }
             const int n_rt = cdiv(P, kP2PRows), n_tiles = B * n_rt * cdiv(Tn, TB);
+            check_decode_range((long long)B * n_rt * cdiv(Tn, TB), (long long)n_rt * cdiv(Tn, TB), "Pitch2Pitch");
             P2PArgs a{x[cur][0], x[cur][1], x[cur ^ 1][0], x[cur ^ 1][1],
                       reinterpret_cast<const __half*>(reinterpret_cast<const uint8_t*>(p->d_wimg) + i * kP2PWBytes),
                       scale_of(c, false), shift_of(c, false), P, Tn, Wd, TB, cdiv(Tn, TB), n_rt, n_tiles, p_in.p, up_tab};
@@ -568,6 +576,7 @@ void Fwd::run(const float* mel, float* key_out, float* tonic_out, float* genre_o
             const int n_tt = cdiv(Tn, tb_cap), TBs = cdiv(Tn, n_tt);
             SemiUmmaArgs sa{x[cur][0], x[cur][1], p->d_wimg_semi, scale_of(cs, false), shift_of(cs, false), pc.p, e[0][0], e[0][1],
                             B, P, Tn, Wd, n_oct, TBs, n_tt, B * 12 * n_tt};
+            check_decode_range((long long)B * 12 * n_tt, 12LL * n_tt, "pool_semi");
             const size_t smem_s = semi_smem_bytes(n_oct, TBs + 2);
             static size_t conf_s = 0;
             if (smem_s > conf_s) {
@@ -611,6 +620,7 @@ void Fwd::run(const float* mel, float* key_out, float* tonic_out, float* genre_o
             Pc2PcArgs ea{};
             ea.in_hi = e[ce][0], ea.in_lo = e[ce][1], ea.Wd_in = Wd, ea.T_out = Tn, ea.TB = TBe, ea.n_ttiles = cdiv(Tn, TBe);
             ea.n_tiles = ea.n_ttiles * B;
+            check_decode_range((long long)ea.n_ttiles * B, ea.n_ttiles, "PitchClass2PitchClass");
             ea.wimg = reinterpret_cast<const __half*>(reinterpret_cast<const uint8_t*>(p->d_wimg_pc) + i * kPcWBytes);
             ea.scale = scale_of(c, false), ea.shift = shift_of(c, false);
             const int grid = std::min(ea.n_tiles, sm_count());  // persistent: one CTA per SM
@@ -698,6 +708,7 @@ void Fwd::run(const float* mel, float* key_out, float* tonic_out, float* genre_o
           Pc8Args pa{};
           pa.in_hi = l0_planes[in][0], pa.in_lo = l0_planes[in][1], pa.Wd_in = Wd, pa.T_out = Tn, pa.TB = TB8;
           pa.n_ttiles = cdiv(Tn, TB8), pa.n_tiles = pa.n_ttiles * B;
+          check_decode_range((long long)pa.n_ttiles * B, pa.n_ttiles, "layer-0 PitchClass2PitchClass");
           pa.wimg = reinterpret_cast<const __half*>(reinterpret_cast<const uint8_t*>(p->d_wimg_l0) + i * kPc8WBytes);
           pa.scale = scale_of(c, false), pa.shift = shift_of(c, false), pa.Cout = c.Cout;
           const int grid = std::min(pa.n_tiles, sm_count());
