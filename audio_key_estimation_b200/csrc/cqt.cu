@@ -365,16 +365,16 @@ __global__ void __launch_bounds__(kCasThreads, 1) cascade_umma_kernel(const Casc
   // Every role decodes every tile between two hand-overs, so this scalar code sits on the pipeline's critical path: the
   // uniform-length case (no lengths array) takes no global load, no loop and no 64-bit shifts per tile.
   const bool ragged = a.lengths != nullptr;
-  const long long len_uniform = (a.n_uniform + (1LL << a.level_in) - 1) >> a.level_in;
-  auto clip_len = [&](int b) {  // samples of level p in clip b
-    return ragged ? ((a.lengths[b] + (1LL << a.level_in) - 1) >> a.level_in) : len_uniform;
+  const int len_uniform = (int)((a.n_uniform + (1LL << a.level_in) - 1) >> a.level_in);
+  auto clip_len = [&](int b) {  // samples of level p in clip b (< 2^31: checked on the host; all per-tile arithmetic is 32-bit)
+    return ragged ? (int)((a.lengths[b] + (1LL << a.level_in) - 1) >> a.level_in) : len_uniform;
   };
   // first tile at or after `tile` (in this CTA's stride) that has data; tiles beyond a short clip's end write nothing
   auto next_tile = [&](int tile) {
     if (!ragged) return tile;  // tiles_per_clip covers exactly the tiles that have data
     for (; tile < a.n_tiles; tile += gridDim.x) {
       const int b = clip_of(tile), t = tile - b * a.tiles_per_clip;
-      if ((long long)kCasOwn1 * t < ((clip_len(b) + 1) >> 1)) break;
+      if (kCasOwn1 * t < ((clip_len(b) + 1) >> 1)) break;
     }
     return tile;
   };
@@ -385,10 +385,10 @@ __global__ void __launch_bounds__(kCasThreads, 1) cascade_umma_kernel(const Casc
   };
   auto span_of = [&](int tile) {
     const int b = clip_of(tile), t = tile - b * a.tiles_per_clip;
-    const long long base0 = 2 * ((long long)kCasOwn1 * t - 32) - 32;
+    const int base0 = 2 * (kCasOwn1 * t - 32) - 32;
     Span s;
-    s.src = a.in + (long long)b * a.in_stride + base0;
-    s.vlo = (int)max(0LL, -base0), s.vhi = (int)min((long long)kCasSpan, clip_len(b) - base0);
+    s.src = a.in + ((long long)b * a.in_stride + base0);
+    s.vlo = max(0, -base0), s.vhi = min(kCasSpan, clip_len(b) - base0);
     s.bulk = (reinterpret_cast<uintptr_t>(s.src) & 15) == 0;
     return s;
   };
@@ -541,9 +541,9 @@ __global__ void __launch_bounds__(kCasThreads, 1) cascade_umma_kernel(const Casc
       if ((i & 1) != grp) continue;
       const uint32_t ph = (i >> 1) & 1;
       const int b = clip_of(tile), t = tile - b * a.tiles_per_clip;
-      const long long n_p = clip_len(b);
-      const long long n_half1 = n_p >> 1, n1 = (n_p + 1) >> 1;
-      const long long o_lo1 = (long long)kCasOwn1 * t - 32;
+      const int n_p = clip_len(b);
+      const int n_half1 = n_p >> 1, n1 = (n_p + 1) >> 1;
+      const int o_lo1 = kCasOwn1 * t - 32;
       mbar_wait_relaxed(&acc1_full[grp], ph);
       fence_after_sync();
       uint64_t o[16];  // 32 outputs as fp32 pairs
@@ -564,8 +564,8 @@ __global__ void __launch_bounds__(kCasThreads, 1) cascade_umma_kernel(const Casc
       mbar_arrive(&acc1_empty[grp]);  // accumulator drained: MMA1 of tile i + 2 may start
       if (o_lo1 < 0 || o_lo1 + 128 * 32 > n_half1) {
         // samples that do not exist (index < 0 or >= floor(n_p / 2)) are zero
-        const long long i1 = o_lo1 + 32LL * row;  // level p+1 index of the row's first output
-        const int zlo = (int)min(32LL, max(0LL, -i1)), zhi = (int)min(32LL, max(0LL, n_half1 - i1));
+        const int i1 = o_lo1 + 32 * row;  // level p+1 index of the row's first output
+        const int zlo = min(32, max(0, -i1)), zhi = min(32, max(0, n_half1 - i1));
 #pragma unroll
         for (int n = 0; n < 16; ++n) {
           float x0, x1;
@@ -601,14 +601,14 @@ __global__ void __launch_bounds__(kCasThreads, 1) cascade_umma_kernel(const Casc
       {
         // rows 1..126 are owned (0 and 127 are the halo the next level needs): 1008 float4s, 8 per row; thread `row` stores
         // float4 (row & 7) of the rows 1 + (row >> 3) + 16 k
-        float* dst = a.out1 + (long long)b * a.stride1 + o_lo1 + 32 * (1 + (row >> 3)) + 4 * (row & 7);
+        float* dst = a.out1 + ((long long)b * a.stride1 + (o_lo1 + 32 * (1 + (row >> 3)) + 4 * (row & 7)));
         const float* src = tb + (1 + (row >> 3)) * kCasTPitch + 4 * (row & 7);
         // rows with 32 r < lim exist (the buffers are padded to whole rows of 32)
-        const int r_lim = (int)min(127LL, max(0LL, (n1 - o_lo1 + 31) >> 5));
+        const int r_lim = min(127, max(0, (n1 - o_lo1 + 31) >> 5));
         const bool sparse = a.sparse_hop > 0;
         int u = 0;
         if (sparse) {
-          u = (int)((unsigned long long)(o_lo1 + a.sparse_nfft / 2) % (unsigned)a.sparse_hop) + 32 * (1 + (row >> 3));
+          u = (int)((unsigned)(o_lo1 + a.sparse_nfft / 2) % (unsigned)a.sparse_hop) + 32 * (1 + (row >> 3));  // o_lo1 + n_fft/2 > 0
           u -= (u >= a.sparse_hop) ? a.sparse_hop : 0;
         }
 #pragma unroll
@@ -635,9 +635,9 @@ __global__ void __launch_bounds__(kCasThreads, 1) cascade_umma_kernel(const Casc
       const int bf = i & 1;
       const uint32_t ph = (i >> 1) & 1;
       const int b = clip_of(tile), t = tile - b * a.tiles_per_clip;
-      const long long n_p = clip_len(b);
-      const long long n1 = (n_p + 1) >> 1, n_half2 = n1 >> 1, n2 = (n1 + 1) >> 1;
-      const long long o_lo2 = (long long)kCasOwn2 * t;
+      const int n_p = clip_len(b);
+      const int n1 = (n_p + 1) >> 1, n_half2 = n1 >> 1, n2 = (n1 + 1) >> 1;
+      const int o_lo2 = kCasOwn2 * t;
       mbar_wait_relaxed(&acc2_full[bf], ph);
       fence_after_sync();
       uint64_t o[16];  // 32 outputs as fp32 pairs
@@ -658,7 +658,7 @@ __global__ void __launch_bounds__(kCasThreads, 1) cascade_umma_kernel(const Casc
       mbar_arrive(&acc2_empty[bf]);
       if (o_lo2 + kCasRows2 * 32 > n_half2) {
         // samples at or beyond floor(n1 / 2) do not exist: zero
-        const int zhi = (int)min(32LL, max(0LL, n_half2 - (o_lo2 + 32LL * row)));
+        const int zhi = min(32, max(0, n_half2 - (o_lo2 + 32 * row)));
 #pragma unroll
         for (int n = 0; n < 16; ++n) {
           float x0, x1;
@@ -678,9 +678,9 @@ __global__ void __launch_bounds__(kCasThreads, 1) cascade_umma_kernel(const Casc
       asm volatile("bar.sync 3, 64;" ::: "memory");
       {
         // 63 rows x 8 float4s; thread `row` stores float4 (row & 7) of the rows (row >> 3) + 8 k
-        float* dst = a.out2 + (long long)b * a.stride2 + o_lo2 + 32 * (row >> 3) + 4 * (row & 7);
+        float* dst = a.out2 + ((long long)b * a.stride2 + (o_lo2 + 32 * (row >> 3) + 4 * (row & 7)));
         const float* src = tbuf2 + (row >> 3) * kCasTPitch + 4 * (row & 7);
-        const int r_lim = (int)min((long long)kCasRows2, max(0LL, (n2 - o_lo2 + 31) >> 5));  // rows with 32 r < n2 - o_lo2 exist
+        const int r_lim = min(kCasRows2, max(0, (n2 - o_lo2 + 31) >> 5));  // rows with 32 r < n2 - o_lo2 exist
 #pragma unroll
         for (int k = 0; k < 8; ++k)
           if ((row >> 3) + 8 * k < r_lim) *reinterpret_cast<float4*>(dst + 256 * k) = *reinterpret_cast<const float4*>(src + 8 * k * kCasTPitch);
@@ -915,6 +915,7 @@ static CqtWs carve(const ake_cqt* p, Arena& ar, int B, long long n_max) {
 static void run_cqt(ake_cqt* p, const float* audio, long long stride, const int64_t* lengths_host, int B, long long n_max,
                     int mode, float* out, int T_max, int* seq_len_out, void* ws, size_t ws_bytes, cudaStream_t st) {
   if (p->n_oct > 15) fail(AKE_ERR_UNSUPPORTED, "too many octaves");
+  if (n_max >= (1LL << 31) - 65536) fail(AKE_ERR_UNSUPPORTED, "clips of 2^31 samples or more are not supported (32-bit sample indices in the cascade)");
   ensure_device(p);
   Arena ar(ws, ws_bytes);
   CqtWs w = carve(p, ar, B, n_max);
