@@ -697,8 +697,10 @@ __global__ void __launch_bounds__(kCasThreads, 1) cascade_umma_kernel(const Casc
 //   D[frame, n] = sum_k x[frame, k] * K[n, k],  x ~= xh + xl, K ~= Kh + Kl (fp16 pairs, fp32 accumulation in TMEM)
 //   MMA 1: A = xh, B = [Kh | Kl]  (N = 2*NPAD)  -> columns [0,NPAD) += xh*Kh, [NPAD,2*NPAD) += xh*Kl
 //   MMA 2: A = xl, B =  Kh        (N =   NPAD)  -> columns [0,NPAD) += xl*Kh
-// Warps 0-3: stage frames (fp32 -> fp16 hi/lo, operand layout of umma.cuh) and run the |.|, scale, log1p epilogue out
-// of TMEM; warp 4 lane 0 issues the MMAs; the bank block of each stage arrives by one bulk async copy.
+// Producer warps stage frames (fp32 -> fp16 hi/lo, operand layout of umma.cuh), four of every eight also run the |.|, scale,
+// log1p epilogue out of TMEM; the last warp issues the MMAs; the bank block of each stage arrives by one bulk async copy.
+// The kernel is bound by L2 -> SM traffic (frames 4 KB per row + the 327 KB bank image per CTA, ~7 TB/s in total): a CTA
+// multiplies MB blocks of 128 frame rows by every bank block it fetches, so the image is read once per 128 * MB rows.
 
 struct BankArgs {
   const float* level[16];
@@ -713,37 +715,45 @@ struct BankArgs {
 
 constexpr uint32_t kBankLBO = 129 * 16;                  // chunk pitch of the frame operand: odd multiple of 16 B (conflict-free 8-byte scatter)
 constexpr uint32_t kBankAHalf = (kUKB / 8) * kBankLBO;
-constexpr int kBankThreads = 288;                         // 8 producer warps (0-3 also run the epilogue) + the MMA-issuer warp   // one of {hi, lo}: 8 chunks x 128 rows x 16 B (+ pad)
+constexpr int kBankMB = 2;                                // blocks of 128 frame rows per CTA (one TMEM accumulator each)
+constexpr int kBankThreads = 32 * (8 * kBankMB + 1);      // 8 producer warps per row block (4 of them also run its epilogue) + the MMA-issuer warp
+__host__ __device__ constexpr uint32_t bank_stage_bytes(int npad, int mb) { return mb * 2 * kBankAHalf + (kUKB / 8) * 2 * npad * 16; }
 
-template <int NPAD>
-__global__ void __launch_bounds__(kBankThreads) cqt_bank_umma_kernel(const BankArgs a) {
+template <int NPAD, int MB>
+__global__ void __launch_bounds__(32 * (8 * MB + 1), 1) cqt_bank_umma_kernel(const BankArgs a) {
   using namespace umma;
-  constexpr uint32_t A_HALF = kBankAHalf;
+  constexpr uint32_t A_HALF = kBankAHalf;                    // one of {hi, lo}: 8 chunks x 128 rows x 16 B (+ pad)
   constexpr uint32_t B_BYTES = (kUKB / 8) * 2 * NPAD * 16;   // 8 chunks x 2*NPAD rows x 16 B
-  constexpr uint32_t STAGE = 2 * A_HALF + B_BYTES;
-  constexpr uint32_t TMEM_COLS = (2 * NPAD <= 64) ? 64 : ((2 * NPAD <= 128) ? 128 : 256);
+  constexpr uint32_t STAGE = bank_stage_bytes(NPAD, MB);     // [row block 0: hi, lo] ... [row block MB-1: hi, lo] [bank block]
+  constexpr uint32_t B_OFF = MB * 2 * A_HALF;
+  constexpr uint32_t TMEM_NEED = MB * 2 * NPAD;
+  constexpr uint32_t TMEM_COLS = (TMEM_NEED <= 64) ? 64 : ((TMEM_NEED <= 128) ? 128 : ((TMEM_NEED <= 256) ? 256 : 512));
+  static_assert(TMEM_NEED <= 512, "accumulators exceed TMEM");
+  constexpr int ISSUER = 8 * MB;
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t full_bar[kUStages], empty_bar[kUStages], done_bar;
   __shared__ uint32_t tmem_slot;
-  __shared__ long long s_g0[128];   // index (into the octave's level array) of the first sample of frame row r
-  __shared__ int2 s_valid[128];     // samples [x, y) of that frame exist (the rest is the zero padding of centred frames)
+  __shared__ long long s_g0[128 * MB];   // index (into the octave's level array) of the first sample of frame row r
+  __shared__ int2 s_valid[128 * MB];     // samples [x, y) of that frame exist (the rest is the zero padding of centred frames)
 
   const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
   const int octave = blockIdx.y;
-  const long long m0 = (long long)blockIdx.x * 128;
+  const long long m0 = (long long)blockIdx.x * (128 * MB);
   const int n_kb = a.n_fft / kUKB;
+  const int mb = warp >> 3;                                   // row block of this producer warp
+  const int row_e = 128 * mb + 32 * (warp & 3) + lane;        // epilogue warps (warp & 7) < 4: TMEM lane 32 (warp & 3) + lane of accumulator mb
 
-  if (warp == 8) tmem_alloc(&tmem_slot, TMEM_COLS);
+  if (warp == ISSUER) tmem_alloc(&tmem_slot, TMEM_COLS);
   if (tid == 0) {
-    for (int s = 0; s < kUStages; ++s) mbar_init(&full_bar[s], 256), mbar_init(&empty_bar[s], 1);
+    for (int s = 0; s < kUStages; ++s) mbar_init(&full_bar[s], 256 * MB), mbar_init(&empty_bar[s], 1);
     mbar_init(&done_bar, 1);
     mbar_init_fence();
   }
-  // ---- frame row `tid`: which clip / frame, where its samples live
+  // ---- frame row `row_e`: which clip / frame, where its samples live
   bool in_range = false, real_frame = false;
   int b = 0, t = 0;
-  if (warp < 4) {
-    const long long m = m0 + tid;
+  if (warp < ISSUER && (warp & 7) < 4) {
+    const long long m = m0 + row_e;
     in_range = m < (long long)a.B * a.T_max;
     b = in_range ? (int)(m / a.T_max) : 0, t = in_range ? (int)(m % a.T_max) : 0;
     const long long n0 = a.lengths ? a.lengths[b] : a.n_uniform;
@@ -755,20 +765,22 @@ __global__ void __launch_bounds__(kBankThreads) cqt_bank_umma_kernel(const BankA
     real_frame = in_range && t < T;
     const long long len = (n0 + (1LL << octave) - 1) >> octave;
     const long long first = (long long)t * (a.hop0 >> octave) - a.n_fft / 2;  // centred frame, zero padded (pad_mode='constant')
-    s_g0[tid] = (long long)b * a.stride[octave] + first;
-    s_valid[tid] = real_frame ? make_int2((int)max(0LL, -first), (int)max(0LL, min((long long)a.n_fft, len - first))) : make_int2(0, 0);
+    s_g0[row_e] = (long long)b * a.stride[octave] + first;
+    s_valid[row_e] = real_frame ? make_int2((int)max(0LL, -first), (int)max(0LL, min((long long)a.n_fft, len - first))) : make_int2(0, 0);
   }
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem = tmem_slot;
 
-  if (warp < 8) {
-    // ---------------------------------------------------------------- producer (8 warps: twice the loads in flight per SM)
-    // Warps w and w + 4 stage the same 32 frame rows, 8 of the 16 row pairs each; one instruction covers two rows x 64
+  if (warp < ISSUER) {
+    // ---------------------------------------------------------------- producer (8 warps per row block)
+    // Warps w and w + 4 of a row block stage the same 32 frame rows, 8 of the 16 row pairs each; one instruction covers two rows x 64
     // samples: lanes 0-15 read the 16 float4s of one row, lanes 16-31 those of the next (coalesced 256-byte runs), convert to
     // fp16 hi/lo and scatter 8-byte halves of the operand chunks (chunk c of row r at c * kBankLBO + r * 16).
-    const int pw = warp & 3, it0 = 8 * (warp >> 2);
+    const int pw = warp & 3, it0 = 8 * ((warp >> 2) & 1);
+    const int rb = 128 * mb;            // first row of this warp's row block
+    const uint32_t a_off = (uint32_t)mb * 2 * A_HALF;
     const float* level = a.level[octave];
     const int f = lane & 15;
     const uint64_t ss = f2_pack(kXScale, kXScale);
@@ -780,7 +792,7 @@ __global__ void __launch_bounds__(kBankThreads) cqt_bank_umma_kernel(const BankA
     uint32_t cls = 0;
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
-      const int r = pw * 32 + 2 * (it0 + it) + (lane >> 4);
+      const int r = rb + pw * 32 + 2 * (it0 + it) + (lane >> 4);
       const int2 v = s_valid[r];
       rowp[it] = level + s_g0[r] + 4 * f;
       const uint32_t c = (v.x == 0 && v.y == a.n_fft) ? (((reinterpret_cast<uintptr_t>(rowp[it]) & 15) == 0) ? 0u : 1u) : 2u;
@@ -793,7 +805,7 @@ __global__ void __launch_bounds__(kBankThreads) cqt_bank_umma_kernel(const BankA
       uint8_t* stage = smem + (size_t)s * STAGE;
       if (tid == 0) {
         mbar_arrive_expect_tx(&full_bar[s], B_BYTES);
-        bulk_g2s(stage + 2 * A_HALF, reinterpret_cast<const uint8_t*>(a.bank_img) + (size_t)kb * B_BYTES, B_BYTES, &full_bar[s]);
+        bulk_g2s(stage + B_OFF, reinterpret_cast<const uint8_t*>(a.bank_img) + (size_t)kb * B_BYTES, B_BYTES, &full_bar[s]);
       }
       const int i0 = kb * kUKB + 4 * f;  // frame-local index of this lane's first sample
       // all 16 loads are issued before the first conversion consumes one
@@ -807,14 +819,14 @@ __global__ void __launch_bounds__(kBankThreads) cqt_bank_umma_kernel(const BankA
         } else if (c == 1) {
           x[it] = make_float4(__ldg(src), __ldg(src + 1), __ldg(src + 2), __ldg(src + 3));
         } else {
-          const int2 v = s_valid[pw * 32 + 2 * (it0 + it) + (lane >> 4)];
+          const int2 v = s_valid[rb + pw * 32 + 2 * (it0 + it) + (lane >> 4)];
           x[it].x = (i0 + 0 >= v.x && i0 + 0 < v.y) ? __ldg(src + 0) : 0.f;
           x[it].y = (i0 + 1 >= v.x && i0 + 1 < v.y) ? __ldg(src + 1) : 0.f;
           x[it].z = (i0 + 2 >= v.x && i0 + 2 < v.y) ? __ldg(src + 2) : 0.f;
           x[it].w = (i0 + 3 >= v.x && i0 + 3 < v.y) ? __ldg(src + 3) : 0.f;
         }
       }
-      const uint32_t off0 = (uint32_t)(f >> 1) * kBankLBO + (uint32_t)(pw * 32 + 2 * it0 + (lane >> 4)) * 16 + (uint32_t)(f & 1) * 8;
+      const uint32_t off0 = a_off + (uint32_t)(f >> 1) * kBankLBO + (uint32_t)(pw * 32 + 2 * it0 + (lane >> 4)) * 16 + (uint32_t)(f & 1) * 8;
 #pragma unroll
       for (int it = 0; it < 8; ++it) {
         uint32_t h0, l0, h1, l1;
@@ -827,11 +839,11 @@ __global__ void __launch_bounds__(kBankThreads) cqt_bank_umma_kernel(const BankA
       fence_proxy_async();
       if (tid != 0) mbar_arrive(&full_bar[s]);
     }
-    // ---------------------------------------------------------------- epilogue (warps 0-3): TMEM lane `tid` = frame row `tid`
-    if (warp < 4) {
+    // ---------------------------------------------------------------- epilogue (4 warps per row block): TMEM lane = frame row within the block
+    if ((warp & 7) < 4) {
     mbar_wait_relaxed(&done_bar, 0);
     fence_after_sync();
-    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+    const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)mb * 2 * NPAD;
     const int bpo = a.bpo;
 #pragma unroll 1
     for (int c0 = 0; c0 < NPAD; c0 += 16) {
@@ -868,9 +880,13 @@ __global__ void __launch_bounds__(kBankThreads) cqt_bank_umma_kernel(const BankA
       if (elect_one()) {
 #pragma unroll
         for (int j = 0; j < kUKB / 16; ++j) {
-          const uint64_t bd = make_desc(B_DESC, base + 2 * A_HALF + j * (2 * 2 * NPAD * 16));
-          mma_f16(tmem, make_desc(A_DESC, base + j * 2 * kBankLBO), bd, IDESC_WIDE, (kb | j) ? 1u : 0u);
-          mma_f16(tmem, make_desc(A_DESC, base + A_HALF + j * 2 * kBankLBO), bd, IDESC_NARROW, 1u);
+          const uint64_t bd = make_desc(B_DESC, base + B_OFF + j * (2 * 2 * NPAD * 16));
+#pragma unroll
+          for (int q = 0; q < MB; ++q) {
+            const uint32_t ab = base + q * 2 * A_HALF + j * 2 * kBankLBO, d = tmem + q * 2 * NPAD;
+            mma_f16(d, make_desc(A_DESC, ab), bd, IDESC_WIDE, (kb | j) ? 1u : 0u);
+            mma_f16(d, make_desc(A_DESC, ab + A_HALF), bd, IDESC_NARROW, 1u);
+          }
         }
         commit(&empty_bar[s]);
         if (kb == n_kb - 1) commit(&done_bar);
@@ -880,7 +896,7 @@ __global__ void __launch_bounds__(kBankThreads) cqt_bank_umma_kernel(const BankA
   }
   fence_before_sync();
   __syncthreads();
-  if (warp == 8) tmem_dealloc(tmem, TMEM_COLS);
+  if (warp == ISSUER) tmem_dealloc(tmem, TMEM_COLS);
 }
 
 __global__ void cqt_seqlen_kernel(const long long* __restrict__ lengths, long long n_uniform, int B, int n_oct, int hop0,
@@ -971,23 +987,23 @@ static void run_cqt(ake_cqt* p, const float* audio, long long stride, const int6
     for (int i = 0; i < p->n_oct; ++i) ba.level[i] = w.level[i], ba.stride[i] = w.stride[i];
     ba.lengths = d_len, ba.n_uniform = n_max, ba.n_oct = p->n_oct, ba.hop0 = p->hop, ba.n_fft = p->n_fft, ba.B = B, ba.T_max = T_max;
     ba.n_bins = p->n_bins, ba.bpo = p->bpo, ba.mode = mode, ba.bank_img = p->d_bank_img, ba.scale = p->d_scale_umma, ba.out = out;
-    dim3 grid((unsigned)cdiv64(rows, 128), p->n_oct);
+    dim3 grid((unsigned)cdiv64(rows, 128 * kBankMB), p->n_oct);
     if (p->npad == 80) {
-      constexpr size_t smem = kUStages * (2 * kBankAHalf + (kUKB / 8) * 2 * 80 * 16);
+      constexpr size_t smem = kUStages * bank_stage_bytes(80, kBankMB);
       static bool configured = false;
       if (!configured) {
-        AKE_CUDA(cudaFuncSetAttribute(cqt_bank_umma_kernel<80>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        AKE_CUDA(cudaFuncSetAttribute(cqt_bank_umma_kernel<80, kBankMB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
       }
-      cqt_bank_umma_kernel<80><<<grid, kBankThreads, smem, st>>>(ba);
+      cqt_bank_umma_kernel<80, kBankMB><<<grid, kBankThreads, smem, st>>>(ba);
     } else {
-      constexpr size_t smem = kUStages * (2 * kBankAHalf + (kUKB / 8) * 2 * 32 * 16);
+      constexpr size_t smem = kUStages * bank_stage_bytes(32, kBankMB);
       static bool configured = false;
       if (!configured) {
-        AKE_CUDA(cudaFuncSetAttribute(cqt_bank_umma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        AKE_CUDA(cudaFuncSetAttribute(cqt_bank_umma_kernel<32, kBankMB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
       }
-      cqt_bank_umma_kernel<32><<<grid, kBankThreads, smem, st>>>(ba);
+      cqt_bank_umma_kernel<32, kBankMB><<<grid, kBankThreads, smem, st>>>(ba);
     }
     AKE_LAUNCHED();
   } else {

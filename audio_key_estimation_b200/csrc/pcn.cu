@@ -571,8 +571,8 @@ void Fwd::run(const float* mel, float* key_out, float* tonic_out, float* genre_o
           const int n_oct = P / 36;
           if (p->d_wimg_semi && P % 36 == 0 && n_oct <= kSemiMaxOct) {
             // tensor cores: all octaves of a (clip, pitch class, time tile) accumulate side by side in TMEM
-            // tile width: TB + 2 <= 128 anchors, and two double-buffered tiles of 3 n_oct rows (hi + lo) must fit in shared memory
-            const int tb_cap = std::min(kSemiMaxTB, 3200 / (3 * n_oct) - 2);
+            // tile width: TB + 2 <= 128 anchors, and kSemiBufs tiles of 3 n_oct rows (hi + lo) must fit in shared memory
+            const int tb_cap = std::min(kSemiMaxTB, (6400 / kSemiBufs) / (3 * n_oct) - 2);
             const int n_tt = cdiv(Tn, tb_cap), TBs = cdiv(Tn, n_tt);
             SemiUmmaArgs sa{x[cur][0], x[cur][1], p->d_wimg_semi, scale_of(cs, false), shift_of(cs, false), pc.p, e[0][0], e[0][1],
                             B, P, Tn, Wd, n_oct, TBs, n_tt, B * 12 * n_tt};

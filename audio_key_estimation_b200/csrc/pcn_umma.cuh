@@ -512,6 +512,8 @@ __global__ void __launch_bounds__(128) semitone_pool_chunks_kernel(const SemiArg
 constexpr int kSemiMaxTB = 126;     // frames per tile: TB + 2 <= 128 anchors
 constexpr int kSemiMaxOct = 10;     // 48 TMEM columns per octave
 constexpr int kSemiThreads = 192;
+constexpr int kSemiBufs = 3;        // tile buffers: two loads in flight while one tile is multiplied (a single 64 KB load in flight per SM
+                                    // runs at its ~3 us loaded latency, far below the HBM rate)
 constexpr uint32_t kSemiWBytes = 3 * 2 * 48 * 16;
 
 // [dp 3][chunk 2][n 48][ci 8]: n = 16 dt + j; j < 8: W_hi of output channel j, j >= 8: W_lo; both chunks hold the same weights
@@ -542,20 +544,20 @@ struct SemiUmmaArgs {
 
 __host__ __device__ inline uint32_t semi_plane_positions(int n_oct, int Wt) { return (uint32_t)(3 * n_oct * Wt + 136); }
 __host__ __device__ inline size_t semi_smem_bytes(int n_oct, int Wt) {
-  return (size_t)2 * 2 * semi_plane_positions(n_oct, Wt) * 16 + kSemiWBytes + (size_t)kSemiMaxOct * 3 * 3 * 32;
+  return (size_t)kSemiBufs * 2 * semi_plane_positions(n_oct, Wt) * 16 + kSemiWBytes + (size_t)kSemiMaxOct * 3 * 3 * 32;
 }
 
 __global__ void __launch_bounds__(kSemiThreads, 1) semi_umma_kernel(const SemiUmmaArgs a) {
   using namespace umma;
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ __align__(8) uint64_t w_bar, full_bar[2], empty_bar[2], acc_full, acc_empty;
+  __shared__ __align__(8) uint64_t w_bar, full_bar[kSemiBufs], empty_bar[kSemiBufs], acc_full, acc_empty;
   __shared__ uint32_t tmem_slot;
   __shared__ float s_scale[8], s_shift[8];
 
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int Wt = a.TB + 2, n_oct = a.n_oct, rows_in = 3 * n_oct;
   const uint32_t plane = semi_plane_positions(n_oct, Wt) * 16;  // a tile buffer holds [hi][lo]
-  uint8_t* s_w = smem + 4 * plane;
+  uint8_t* s_w = smem + 2 * kSemiBufs * plane;
   float4* pub = reinterpret_cast<float4*>(s_w + kSemiWBytes);    // [octave][warp 1..3][slot 3 = (f 1: lane 0), (f 2: lanes 0, 1)][8 floats]
   const int per_clip = 12 * a.n_ttiles;
   const uint32_t pc_magic = 0xFFFFFFFFu / (uint32_t)per_clip + 1, tt_magic = 0xFFFFFFFFu / (uint32_t)a.n_ttiles + 1;
@@ -569,12 +571,12 @@ __global__ void __launch_bounds__(kSemiThreads, 1) semi_umma_kernel(const SemiUm
   if (warp == 5) tmem_alloc(&tmem_slot, 512);
   if (threadIdx.x == 0) {
     mbar_init(&w_bar, 1);
-    for (int i = 0; i < 2; ++i) mbar_init(&full_bar[i], 1), mbar_init(&empty_bar[i], 1);
+    for (int i = 0; i < kSemiBufs; ++i) mbar_init(&full_bar[i], 1), mbar_init(&empty_bar[i], 1);
     mbar_init(&acc_full, 1), mbar_init(&acc_empty, 128);
     mbar_init_fence();
   }
   if (threadIdx.x < 8) s_scale[threadIdx.x] = a.scale[threadIdx.x] * (1.f / kWScale), s_shift[threadIdx.x] = a.shift[threadIdx.x];
-  for (uint32_t i = threadIdx.x; i < 4 * plane / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  for (uint32_t i = threadIdx.x; i < 2 * kSemiBufs * plane / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
   fence_proxy_async();
   fence_before_sync();
   __syncthreads();
@@ -589,12 +591,12 @@ __global__ void __launch_bounds__(kSemiThreads, 1) semi_umma_kernel(const SemiUm
     }
     int k = 0;
     for (int item = blockIdx.x; item < a.n_items; item += gridDim.x, ++k) {
-      const int s = k & 1;
+      const int s = k % kSemiBufs;
       int b, c, t0;
       decode(item, b, c, t0);
       const int cols_in = min(Wt, a.Wd - (t0 + 2));
       const uint32_t row_bytes = (uint32_t)cols_in * 16;
-      mbar_wait_relaxed(&empty_bar[s], ((k >> 1) & 1) ^ 1);
+      mbar_wait_relaxed(&empty_bar[s], ((k / kSemiBufs) & 1) ^ 1);
       if (lane == 0) mbar_arrive_expect_tx(&full_bar[s], 2u * rows_in * row_bytes);
       __syncwarp();
       uint8_t* dst = smem + (size_t)s * 2 * plane;
@@ -614,9 +616,9 @@ __global__ void __launch_bounds__(kSemiThreads, 1) semi_umma_kernel(const SemiUm
     mbar_wait(&w_bar, 0);
     int k = 0;
     for (int item = blockIdx.x; item < a.n_items; item += gridDim.x, ++k) {
-      const int s = k & 1;
+      const int s = k % kSemiBufs;
       const uint32_t hi0 = smem_u32(smem + (size_t)s * 2 * plane);
-      mbar_wait(&full_bar[s], (k >> 1) & 1);
+      mbar_wait(&full_bar[s], (k / kSemiBufs) & 1);
       mbar_wait(&acc_empty, (k & 1) ^ 1);
       fence_after_sync();
       if (elect_one()) {
