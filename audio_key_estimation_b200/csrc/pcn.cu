@@ -18,6 +18,7 @@
 #include "pcn_kernels.cuh"
 #include "pcn_train_kernels.cuh"
 #include "pcn_umma.cuh"
+#include "pcn_p2p1.cuh"
 
 namespace ake {
 
@@ -126,6 +127,7 @@ struct ake_pcn {
   bool umma = false;
   __half* d_wimg = nullptr;         // one kP2PWBytes image per Pitch2Pitch conv, in conv-id order of `umma_convs`
   std::vector<int> umma_convs;
+  __half* d_wimg_f1 = nullptr;      // first Pitch2Pitch conv split by input channel (pcn_p2p1.cuh): [mel image, 4 KB | periodic-part image, kP2PWBytes]
   __half* d_wimg_pc = nullptr;      // equivariant convs of the layer-1 PitchClass2PitchClass stack (kPcWBytes each)
   __half* d_wimg_l0 = nullptr;      // equivariant convs of the layer-0 PitchClass2PitchClass stack (kPc8WBytes each)
   __half* d_wimg_semi = nullptr;    // pool_semi conv of layer 1 (kSemiWBytes)
@@ -528,11 +530,26 @@ void Fwd::run(const float* mel, float* key_out, float* tonic_out, float* genre_o
         const Conv& cu = p->convs[lp.up];
         // up_sixth (models.py:372-374) as a (B, 36, T) x 4-channel table; the first 7x7 conv generates its input tiles
         // cat[p, tile(up)] from it and the log-CQT in shared memory (no operand planes for the 5-channel input at all)
-        float4* up_tab = reinterpret_cast<float4*>(arena.take<float>((size_t)B * 36 * Tn * 4));
+        // first conv split by input channel (pcn_p2p1.cuh): the 4 up-sampled channels have period 36 in pitch
+        const Conv& c_first = p->convs[lp.p2p[0]];
+        const bool split1 = p->d_wimg_f1 && P % 36 == 0 && Tn >= 16 && c_first.Cin == 5 && c_first.Cout == 8 && !getenv("AKE_NO_SPLIT1");
+        float4* up_tab = nullptr;
+        __half *up_hi = nullptr, *up_lo = nullptr;
+        float* per_tab = nullptr;
+        if (split1) {
+          up_hi = arena.take<__half>((size_t)B * 42 * Wd * 8), up_lo = arena.take<__half>((size_t)B * 42 * Wd * 8);
+          per_tab = arena.take<float>((size_t)B * 36 * Tn * 8);
+        } else {
+          up_tab = reinterpret_cast<float4*>(arena.take<float>((size_t)B * 36 * Tn * 4));
+        }
         if (!dry) {
           ProfScope prof("pcn.prep", st);
-          upsixth_table_kernel<<<dim3(cdiv(Tn, 128), 36, B), 128, 0, st>>>(pc.p, p->d_params + cu.w_off, scale_of(cu, false),
-                                                                           shift_of(cu, false), up_tab, Tn);
+          if (split1)
+            upsixth_planes_kernel<<<dim3(cdiv(Tn, 128), 36, B), 128, 0, st>>>(pc.p, p->d_params + cu.w_off, scale_of(cu, false),
+                                                                              shift_of(cu, false), up_hi, up_lo, Tn, Wd);
+          else
+            upsixth_table_kernel<<<dim3(cdiv(Tn, 128), 36, B), 128, 0, st>>>(pc.p, p->d_params + cu.w_off, scale_of(cu, false),
+                                                                             shift_of(cu, false), up_tab, Tn);
           AKE_LAUNCHED();
         }
         const int n_tt = cdiv(Tn, kP2PMaxTB), TB = cdiv(Tn, n_tt);
@@ -546,6 +563,8 @@ void Fwd::run(const float* mel, float* key_out, float* tonic_out, float* genre_o
             if (smem > configured) {
               AKE_CUDA(cudaFuncSetAttribute(p2p_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
               AKE_CUDA(cudaFuncSetAttribute(p2p_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+              AKE_CUDA(cudaFuncSetAttribute((p2p_umma_kernel<false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+              AKE_CUDA(cudaFuncSetAttribute(p2p1_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f1_smem_bytes(TB)));
               configured = smem;
             }
             const int n_rt = cdiv(P, kP2PRows), n_tiles = B * n_rt * cdiv(Tn, TB);
@@ -554,8 +573,22 @@ void Fwd::run(const float* mel, float* key_out, float* tonic_out, float* genre_o
                       reinterpret_cast<const __half*>(reinterpret_cast<const uint8_t*>(p->d_wimg) + i * kP2PWBytes),
                       scale_of(c, false), shift_of(c, false), P, Tn, Wd, TB, cdiv(Tn, TB), n_rt, n_tiles, p_in.p, up_tab};
             const int grid = std::min(n_tiles, sm_count());  // persistent: one CTA per SM
-            if (i == 0) p2p_umma_kernel<true><<<grid, kP2PThreadsGen, smem, st>>>(a);
-            else p2p_umma_kernel<false><<<grid, kP2PThreads, smem, st>>>(a);
+            if (i == 0 && split1) {
+              // periodic part on the 36-row image (raw accumulators), then the mel channel + periodic part + BN + LeakyReLU
+              const int n_rt36 = cdiv(36, kP2PRows), n_tiles36 = B * n_rt36 * cdiv(Tn, TB);
+              const __half* w_per = reinterpret_cast<const __half*>(reinterpret_cast<const uint8_t*>(p->d_wimg_f1) + 4096);
+              P2PArgs ap{up_hi, up_lo, nullptr, nullptr, w_per, scale_of(c, false), shift_of(c, false), 36, Tn, Wd, TB, cdiv(Tn, TB),
+                         n_rt36, n_tiles36, nullptr, nullptr, per_tab};
+              p2p_umma_kernel<false, true><<<std::min(n_tiles36, sm_count()), kP2PThreads, smem, st>>>(ap);
+              AKE_LAUNCHED();
+              P2P1Args a1{p_in.p, per_tab, x[cur ^ 1][0], x[cur ^ 1][1], p->d_wimg_f1, scale_of(c, false), shift_of(c, false),
+                          P, Tn, Wd, TB, cdiv(Tn, TB), n_rt, n_tiles};
+              p2p1_umma_kernel<<<grid, kF1Threads, f1_smem_bytes(TB), st>>>(a1);
+            } else if (i == 0) {
+              p2p_umma_kernel<true><<<grid, kP2PThreadsGen, smem, st>>>(a);
+            } else {
+              p2p_umma_kernel<false><<<grid, kP2PThreads, smem, st>>>(a);
+            }
             AKE_LAUNCHED();
           }
           cur ^= 1;
@@ -920,6 +953,17 @@ static void upload_params(ake_pcn* p, const float* flat_dev, int64_t n, cudaStre
                                                    reinterpret_cast<__half*>(reinterpret_cast<uint8_t*>(p->d_wimg) + i * kP2PWBytes));
       AKE_LAUNCHED();
     }
+    if (!p->umma_convs.empty()) {
+      const Conv& c = p->convs[p->umma_convs[0]];
+      if (c.Cin == 5 && c.Cout == 8) {
+        if (!p->d_wimg_f1) AKE_CUDA(cudaMalloc(&p->d_wimg_f1, 4096 + kP2PWBytes));
+        p2p1_pack_mel_kernel<<<2, 256, 0, st>>>(p->d_params + c.w_off, c.Cout, c.Cin, p->d_wimg_f1);
+        AKE_LAUNCHED();
+        p2p_pack_weights_sub_kernel<<<14, 256, 0, st>>>(p->d_params + c.w_off, c.Cout, c.Cin, 1, 4,
+                                                       reinterpret_cast<__half*>(reinterpret_cast<uint8_t*>(p->d_wimg_f1) + 4096));
+        AKE_LAUNCHED();
+      }
+    }
     {
       const Conv& cs = p->convs[p->layers[1].sem];
       if (cs.Cin == 8 && cs.Cout == 8) {
@@ -1067,6 +1111,7 @@ void ake_pcn_destroy(ake_pcn* p) {
   cudaFree(p->d_ss_eval);
   cudaFree(p->d_ss_raw);
   cudaFree(p->d_wimg);
+  cudaFree(p->d_wimg_f1);
   cudaFree(p->d_wimg_pc);
   cudaFree(p->d_wimg_l0);
   cudaFree(p->d_wimg_semi);

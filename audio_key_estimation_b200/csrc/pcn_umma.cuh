@@ -102,6 +102,8 @@ struct P2PArgs {
   // memory from the log-CQT and the 36-row up-sampled table instead of being read from operand planes
   const float* mel;      // (B, 1, P, T)
   const float4* up;      // (B, 36, T) x 4 channels: act(bn(ConvTranspose2d(pc))) per pitch class third (upsixth_table_kernel)
+  // RAW = true (periodic part of the first conv, pcn_p2p1.cuh): the accumulators, before BN, as fp32 (B, P, T, 8)
+  float* raw_out;
 };
 
 constexpr uint32_t kP2PWBytes = 7 * 2 * 112 * 16;
@@ -119,7 +121,7 @@ __host__ __device__ inline size_t p2p_smem_bytes(int Wt) {
 //   warps 0..4G-1: G epilogue groups of 4 warps; group g drains blocks g, g + G, ... (thread = TMEM lane = anchor):
 //                 phase realignment (shuffles + a 6-lane hand-over between neighbouring warps), BN + LeakyReLU, fp16
 //                 hi/lo split, stores of the home position and of the circular halo copies.
-template <bool GEN>
+template <bool GEN, bool RAW = false>
 __global__ void __launch_bounds__(GEN ? kP2PThreadsGen : kP2PThreads, 1) p2p_umma_kernel(const P2PArgs a) {
   using namespace umma;
   constexpr int G = kP2PGroups;
@@ -380,7 +382,13 @@ __global__ void __launch_bounds__(GEN ? kP2PThreadsGen : kP2PThreads, 1) p2p_umm
         const int anchor = m * kP2PStride + tid;
         if (tid < kP2PStride && anchor < g.n_anchor) {
           const int pl = (int)__umulhi((uint32_t)anchor, wt_magic), tl = anchor - pl * Wt;
-          if (tl < g.TBv) {
+          if (RAW && tl < g.TBv) {
+            float y[8];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) f2_unpack(o[e], y[2 * e], y[2 * e + 1]);
+            float4* dst = reinterpret_cast<float4*>(a.raw_out + (((long long)g.b * a.P + g.p0 + pl) * a.T + g.t0 + tl) * 8);
+            dst[0] = make_float4(y[0], y[1], y[2], y[3]), dst[1] = make_float4(y[4], y[5], y[6], y[7]);
+          } else if (tl < g.TBv) {
             uint32_t h[4], l[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
