@@ -532,7 +532,7 @@ void Fwd::run(const float* mel, float* key_out, float* tonic_out, float* genre_o
         // cat[p, tile(up)] from it and the log-CQT in shared memory (no operand planes for the 5-channel input at all)
         // first conv split by input channel (pcn_p2p1.cuh): the 4 up-sampled channels have period 36 in pitch
         const Conv& c_first = p->convs[lp.p2p[0]];
-        const bool split1 = p->d_wimg_f1 && P % 36 == 0 && Tn >= 16 && c_first.Cin == 5 && c_first.Cout == 8 && !getenv("AKE_NO_SPLIT1");
+        const bool split1 = p->d_wimg_f1 && P % 36 == 0 && Tn >= 64 && c_first.Cin == 5 && c_first.Cout == 8;
         float4* up_tab = nullptr;
         __half *up_hi = nullptr, *up_lo = nullptr;
         float* per_tab = nullptr;

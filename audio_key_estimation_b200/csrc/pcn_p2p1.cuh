@@ -18,8 +18,9 @@
 
 namespace ake {
 
-constexpr int kF1Groups = 4;       // epilogue groups of 4 warps = accumulator buffers of 16 TMEM columns
-constexpr int kF1GenWarps = 8;     // tile-generator warps
+constexpr int kF1Groups = 4;       // epilogue groups of 4 warps = accumulator buffers of 16 TMEM columns; a multiple of kF1Issuers, so that
+                                   // every accumulator belongs to ONE issuer (mbarrier parity waits must not skip a phase)
+constexpr int kF1GenWarps = 9;     // tile-generator warps: 288 threads >= (8 + 6) rows x 20 column groups, one item per thread and tile
 constexpr int kF1Issuers = 2;      // MMA-issuer warps (alternate blocks; one warp issues at most one MMA per ~61 cycles)
 constexpr int kF1Threads = 32 * (4 * kF1Groups + kF1GenWarps + kF1Issuers);
 constexpr int kF1Bufs = 2;
@@ -114,7 +115,7 @@ struct P2P1Args {
   const float* scale;    // 8: eval-mode BN scale (the 1/kWScale factor is applied in the kernel)
   const float* shift;    // 8
   int P, T, Wd;
-  int TB, n_ttiles;      // frames per tile (>= 16), tiles along time
+  int TB, n_ttiles;      // frames per tile, tiles along time (T >= 64)
   int n_rtiles, n_tiles;
 };
 
@@ -125,6 +126,7 @@ struct P2P1Args {
 __global__ void __launch_bounds__(kF1Threads, 1) p2p1_umma_kernel(const P2P1Args a) {
   using namespace umma;
   constexpr int G = kF1Groups, NGEN = kF1GenWarps, ISSUER0 = 4 * G + NGEN, NI = kF1Issuers;
+  static_assert(G % NI == 0, "every accumulator must belong to one issuer");
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t w_bar, full_bar[kF1Bufs], empty_bar[kF1Bufs], acc_full[G], acc_empty[G];
   __shared__ uint32_t tmem_slot;
@@ -177,57 +179,76 @@ __global__ void __launch_bounds__(kF1Threads, 1) p2p1_umma_kernel(const P2P1Args
       mbar_arrive_expect_tx(&w_bar, kF1WBytes);
       bulk_g2s(s_w, a.wimg, kF1WBytes, &w_bar);
     }
-    const int n_cg = (TB + 7) >> 3;  // groups of 8 columns per row
-    const uint32_t cg_magic = 0xFFFFFFFFu / (uint32_t)n_cg + 1;
-    int k = 0;
-    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++k) {
-      const int s = k % kF1Bufs;
-      const Geom g = geom(tile);
-      mbar_wait_relaxed(&empty_bar[s], ((k / kF1Bufs) & 1) ^ 1);
+    // Warp item = (tile row, segment of 26 columns): lane L loads ONE sample (input column 26 seg - 3 + L), splits it into
+    // fp16 hi / lo once, and the seven time taps of a position come from the neighbouring lanes by shuffle; lanes 3..28 store
+    // the two 16-byte chunks of their position (consecutive lanes = consecutive positions: conflict-free).  The samples of
+    // the NEXT tile are loaded before this tile is converted (software pipeline: the generators would otherwise sit out one
+    // L2 round trip per tile).
+    const int gw = warp - 4 * G;
+    const int n_seg = (TB + 25) / 26;
+    const uint32_t seg_magic = 0xFFFFFFFFu / (uint32_t)n_seg + 1;
+    constexpr int MAXI = 11;  // items per warp and tile: (8 + 6) rows x 7 segments (TB <= 182) / 9 warps
+    auto fetch_tile = [&](const Geom& g, float (&x)[MAXI]) {
+      const int n_it = (g.PB + 6) * n_seg;
+      const float* mel_b = a.mel + (long long)g.b * a.P * a.T;
+#pragma unroll
+      for (int i = 0; i < MAXI; ++i) {
+        const int item = gw + i * NGEN;
+        x[i] = 0.f;
+        if (item < n_it) {
+          const int row = (int)__umulhi((uint32_t)item, seg_magic), sgm = item - row * n_seg;
+          int p = g.p0 + row - 3;
+          p += (p < 0) ? a.P : 0, p -= (p >= a.P) ? a.P : 0;
+          int t = g.t0 + 26 * sgm - 3 + lane;  // circular in time (T >= 64: one wrap each way suffices)
+          t += (t < 0) ? a.T : 0, t -= (t >= a.T) ? a.T : 0;
+          x[i] = __ldg(mel_b + (long long)p * a.T + t);
+        }
+      }
+    };
+    auto emit_tile = [&](const Geom& g, int s, const float (&x)[MAXI]) {
+      const int n_it = (g.PB + 6) * n_seg;
       uint4* d_hi = reinterpret_cast<uint4*>(smem + (size_t)s * 2 * plane);
       uint4* d_lo = reinterpret_cast<uint4*>(smem + (size_t)s * 2 * plane + plane);
-      const float* mel_b = a.mel + (long long)g.b * a.P * a.T;
-      const int n_items = (g.PB + 6) * n_cg;
-      for (int it = gt; it < n_items; it += 32 * NGEN) {
-        // item = (row, 8 consecutive columns): 14 samples of one mel row -> 8 chunks of seven time taps
-        const int row = (int)__umulhi((uint32_t)it, cg_magic), c0 = (it - row * n_cg) * 8;
-        int p = g.p0 + row - 3;
-        p += (p < 0) ? a.P : 0, p -= (p >= a.P) ? a.P : 0;
-        const float* mel_r = mel_b + (long long)p * a.T;
-        int tb = g.t0 + c0 - 3;  // circular in time (T >= 16: one wrap suffices)
-        tb += (tb < 0) ? a.T : 0, tb -= (tb >= a.T) ? a.T : 0;
-        float v[14];
 #pragma unroll
-        for (int i = 0; i < 14; ++i) {
-          int t = tb + i;
-          t -= (t >= a.T) ? a.T : 0;
-          v[i] = __ldg(mel_r + t);
-        }
-        __half h[14];
-        float r[14];
+      for (int i = 0; i < MAXI; ++i) {
+        const int item = gw + i * NGEN;
+        if (item < n_it) {  // warp-uniform
+          const int row = (int)__umulhi((uint32_t)item, seg_magic), sgm = item - row * n_seg;
+          const __half h = __float2half_rn(x[i]);
+          const __half l = __float2half_rn(x[i] - __half2float(h));
+          const uint32_t u = pack_h2(h, l);  // hi in the low half, lo in the high half
+          uint32_t n[7];
 #pragma unroll
-        for (int i = 0; i < 14; ++i) h[i] = __float2half_rn(v[i]), r[i] = v[i] - __half2float(h[i]);
-        uint32_t ph[13], pl[13];  // pairs (i, i + 1)
-#pragma unroll
-        for (int i = 0; i < 13; ++i) {
-          ph[i] = pack_h2(h[i], h[i + 1]);
-          const __half2 l2 = __floats2half2_rn(r[i], r[i + 1]);
-          pl[i] = *reinterpret_cast<const uint32_t*>(&l2);
-        }
-        uint4* r_hi = d_hi + row * TB + c0;
-        uint4* r_lo = d_lo + row * TB + c0;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if (c0 + j < TB) {
-            const __half2 l1 = __floats2half2_rn(r[j + 6], 0.f);
-            r_hi[j] = make_uint4(ph[j], ph[j + 2], ph[j + 4], (uint32_t)__half_as_ushort(h[j + 6]));
-            r_lo[j] = make_uint4(pl[j], pl[j + 2], pl[j + 4], *reinterpret_cast<const uint32_t*>(&l1));
+          for (int d = 0; d < 7; ++d) n[d] = __shfl_sync(0xffffffffu, u, lane + d - 3);
+          const int col = 26 * sgm + lane - 3;
+          if (lane >= 3 && lane < 29 && col < TB) {
+            const int q = row * TB + col;
+            d_hi[q] = make_uint4(__byte_perm(n[0], n[1], 0x5410), __byte_perm(n[2], n[3], 0x5410), __byte_perm(n[4], n[5], 0x5410), n[6] & 0xFFFFu);
+            d_lo[q] = make_uint4(__byte_perm(n[0], n[1], 0x7632), __byte_perm(n[2], n[3], 0x7632), __byte_perm(n[4], n[5], 0x7632), n[6] >> 16);
           }
         }
       }
+    };
+    float x[MAXI], xn[MAXI];
+    Geom g = geom(min((int)blockIdx.x, a.n_tiles - 1));
+    fetch_tile(g, x);
+    int k = 0;
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++k) {
+      const int s = k % kF1Bufs;
+      const int tile_n = tile + (int)gridDim.x;
+      Geom gn = g;
+      if (tile_n < a.n_tiles) {
+        gn = geom(tile_n);
+        fetch_tile(gn, xn);
+      }
+      mbar_wait_relaxed(&empty_bar[s], ((k / kF1Bufs) & 1) ^ 1);
+      emit_tile(g, s, x);
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&full_bar[s]);
+#pragma unroll
+      for (int i = 0; i < MAXI; ++i) x[i] = xn[i];
+      g = gn;
     }
   } else if (warp >= ISSUER0) {
     // ------------------------------------------------------------ MMA issuers: warp iw issues blocks j with j % NI == iw

@@ -316,7 +316,8 @@ def run_b200(args):
             tj = json.load(fh)
         traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
     roofline = {
-        "kernel": "pcn.p2p: 3 x Conv2d 7x7 circular (pitch,time) + BN + LeakyReLU (64.6% of the forward's MACs)",
+        "kernel": "pcn.p2p: 3 x Conv2d 7x7 circular (pitch,time) + BN + LeakyReLU (64.6% of the reference forward's MACs); "
+                  "4 launches: first conv split into its 36-periodic part + mel part (pcn_p2p1.cuh), then 2 x p2p_umma_kernel",
         "bound": "tensor", "achieved": p2p_tflops, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
         "frac": (p2p_tflops / peaks["bf16_tflops_sustained"]) if p2p_tflops else None, "traffic": traffic, "traffic_source": traffic_src,
         "algorithmic_flops_per_launch": 2.0 * p2p_macs_clip * B / max(1, p2p_n),
