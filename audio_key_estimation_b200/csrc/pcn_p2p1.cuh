@@ -313,7 +313,7 @@ __global__ void __launch_bounds__(kF1Threads, 1) p2p1_umma_kernel(const P2P1Args
           const float4* src = reinterpret_cast<const float4*>(a.tab + (((long long)g.b * 36 + p36) * a.T + t) * 8);
           q0 = __ldg(src), q1 = __ldg(src + 1);
         }
-        mbar_wait_relaxed(&acc_full[grp], n_done & 1);
+        mbar_wait_sleep<160>(&acc_full[grp], n_done & 1);
         fence_after_sync();
         uint32_t v[16];
         tmem_ld16_issue(acc, v);
