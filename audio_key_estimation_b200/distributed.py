@@ -51,6 +51,32 @@ def init_from_env(backend: Optional[str] = None) -> Tuple[int, int, int]:
     return rank, local, world
 
 
+def bind_to_gpu_numa_node(device_index: int) -> Optional[int]:
+    """Pin this process (one per GPU) to the CPUs of the NUMA node its GPU hangs off, BEFORE it allocates pinned host buffers:
+    first-touch then places those buffers in the memory next to the GPU's PCIe root, so N ranks streaming audio to N GPUs do
+    not all pull from one socket's memory.  Best effort: returns the node, or None when the topology is not exposed (single
+    node, container without sysfs) -- nothing is changed then."""
+    try:
+        props = torch.cuda.get_device_properties(device_index)
+        bdf = f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as fh:
+            node = int(fh.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as fh:
+            cpus = set()
+            for part in fh.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except (OSError, ValueError, AttributeError):
+        return None
+
+
 def pack_rows(key: torch.Tensor, tonic: torch.Tensor, genre: Optional[torch.Tensor]) -> torch.Tensor:
     """(n, 35) fp32 rows [key | tonic | genre-or-zeros]."""
     n = key.shape[0]

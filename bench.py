@@ -196,6 +196,10 @@ def run_b200(args):
             raise SystemExit("launch with torchrun for --gpus > 1 (python -m torch.distributed.run --nproc-per-node N bench.py ...)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # one process per GPU: keep each rank's pinned host buffers in the memory next to its GPU (multi-rank runs only, so the
+    # N = 1 CPU baseline keeps every host core)
+    if world > 1 and not os.environ.get("AKE_NO_NUMA_BIND"):
+        akd.bind_to_gpu_numa_node(local)
     genre = not args.no_genre
     peaks = load_peaks()
     B, n_samples = args.batch, int(round(args.seconds * SR))
