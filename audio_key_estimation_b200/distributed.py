@@ -73,7 +73,7 @@ def bind_to_gpu_numa_node(device_index: int) -> Optional[int]:
             return None
         os.sched_setaffinity(0, allowed)
         return node
-    except (OSError, ValueError, AttributeError):
+    except Exception:  # best effort by contract: no CUDA, no sysfs, odd cpulist -> leave the affinity alone
         return None
 
 

@@ -118,3 +118,14 @@ def test_cqt_cache_names_follow_the_reference_table():
     e = cache.cache_entry(mel[1], 5)
     assert e.shape == (1, 288, 5) and e.dtype == torch.float64 and e.device.type == "cpu"
     assert torch.equal(e, mel[1][:, :, :5].double())
+
+
+def test_numa_bind_is_best_effort():
+    """distributed.bind_to_gpu_numa_node never raises and leaves the affinity alone when the topology is not exposed (no GPU here)."""
+    import os
+    from audio_key_estimation_b200 import distributed as akd
+    before = os.sched_getaffinity(0)
+    node = akd.bind_to_gpu_numa_node(0)
+    assert node is None or isinstance(node, int)
+    if node is None:
+        assert os.sched_getaffinity(0) == before
