@@ -15,6 +15,7 @@ from . import build as _build
 
 AKE_OK = 0
 AKE_ERR_INVALID, AKE_ERR_UNSUPPORTED, AKE_ERR_CUDA, AKE_ERR_WORKSPACE = -1, -2, -3, -4
+ROW_FLOATS = 35  # AKE_ROW_FLOATS: 12 key + 12 tonic + 11 genre
 CQT_LOGMAG, CQT_COMPLEX = 0, 1
 
 
@@ -43,12 +44,13 @@ _SIGNATURES = {
     "ake_pcn_workspace_bytes": (C.c_size_t, [_P, C.c_int, C.c_int, C.c_int]),
     "ake_pcn_forward_f32": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, C.c_int, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "ake_pcn_bn_channels": (C.c_int, [_P]),
+    "ake_pcn_forward_rows_f32": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P, _P, _P, C.c_size_t, _P]),
     "ake_pcn_backward_f32": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, _P, C.c_size_t, _P]),
     "ake_loss_f32": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_float, C.c_float, C.c_float, _P, _P, _P, _P, _P]),
     "ake_pcn_get_config": (C.c_int, [_P, C.POINTER(PcnConfig)]),
     "ake_pcn_get_tap": (C.c_int64, [_P, C.c_char_p, _P, C.c_int64, _P]),
     "ake_decode_f32": (C.c_int, [_P, _P, _P, C.c_int, _P, _P, _P, _P]),
-    "ake_mirex_f32": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, _P, _P, _P, _P]),
+    "ake_mirex_f32": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, _P, _P, _P, _P]),
     "ake_adam_step_f32": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
                                     C.c_float, C.c_int, _P]),
     "ake_cqt_create": (C.c_int, [C.c_double, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double,
@@ -64,6 +66,9 @@ _SIGNATURES = {
                                   C.c_size_t, _P]),
     "ake_estimate_workspace_bytes": (C.c_size_t, [_P, _P, C.c_int, C.c_int64]),
     "ake_estimate_host_f32": (C.c_int, [_P, _P, _P, C.c_int64, _P, C.c_int, C.c_int64, _P, _P, _P, _P, _P,
+                                        C.c_size_t, _P]),
+    "ake_estimate_workspace_bytes_i16": (C.c_size_t, [_P, _P, C.c_int, C.c_int64]),
+    "ake_estimate_host_i16": (C.c_int, [_P, _P, _P, C.c_int64, _P, C.c_int, C.c_int64, _P, _P, _P, _P, _P,
                                         C.c_size_t, _P]),
 }
 
@@ -90,7 +95,7 @@ def lib() -> C.CDLL:
             for name, (res, args) in _SIGNATURES.items():
                 fn = getattr(handle, name)  # AttributeError if the library lacks a declared symbol
                 fn.restype, fn.argtypes = res, args
-            if handle.ake_abi_version() != 1:
+            if handle.ake_abi_version() != 2:
                 raise RuntimeError("libake_b200.so ABI version mismatch")
             _lib = handle
     return _lib

@@ -11,7 +11,7 @@ from typing import List, Sequence
 
 import torch
 
-from .cqt import cqt_logmag
+from .cqt import CQTPlan, cqt_logmag
 
 
 def _get(opt, name, default):
@@ -70,20 +70,43 @@ def cache_entry(mel: torch.Tensor, n_frames: int) -> torch.Tensor:
 
 
 def write_cqt_cache(audio_paths: Sequence[str], waveforms: Sequence[torch.Tensor], sr: int, opt, batch: int = 64,
-                    overwrite: bool = False) -> List[str]:
+                    overwrite: bool = False, accept_unpinned_cqt: bool = False) -> List[str]:
     """Compute the log-CQT of ``waveforms`` (mono float32 tensors, CUDA or pinned/pageable host) on the GPU in batches and
     save each as the reference's cache file.  Returns the written file names.  Raises where the B200 front-end does not
-    cover the reference's configuration (``only_semitones``: 12 bins per octave is outside the built filter banks' test matrix
-    only when ``ake_cqt_create`` says so)."""
+    cover the reference's configuration (``ake_cqt_create`` says so).
+
+    ``accept_unpinned_cqt`` must be set: the unmodified ``KeyDataset`` PREFERS these files over calling ``librosa.cqt``
+    (KeyDataset.py:169-185), and the B200 front-end's parity is checked against this repository's restatement of
+    librosa 0.9.2 (oracle/cqt_port.py), not against librosa itself, which is absent from the build environment
+    (DESIGN.md section 2; tests/test_oracle_cqt.py::test_port_matches_librosa_when_importable pins it where librosa
+    exists).  Writing features the reference's training and evaluation will silently consume is therefore an explicit
+    decision of the caller."""
     if len(audio_paths) != len(waveforms):
         raise ValueError("one path per waveform")
-    if int(_get(opt, "frames", 5)) <= 0:
-        raise NotImplementedError("frames == 0 (window-count hop, KeyDataset.py:490) is outside the hot path")
+    if not accept_unpinned_cqt:
+        raise RuntimeError("write_cqt_cache writes files the reference's KeyDataset loads instead of calling librosa.cqt, and CQT "
+                           "parity against librosa itself is unpinned in this build (see the docstring); pass accept_unpinned_cqt=True "
+                           "after running tests/test_oracle_cqt.py::test_port_matches_librosa_when_importable where librosa is installed")
     octaves, frames = int(_get(opt, "octaves", 8)), int(_get(opt, "frames", 5))
     bpo = 12 if bool(_get(opt, "only_semitones", False)) else 36
     names = [cache_name(p, opt) for p in audio_paths]
     written = []
     todo = [i for i, n in enumerate(names) if overwrite or not os.path.exists(n)]
+    if frames <= 0:
+        # opt.frames == 0 (KeyDataset.py:485-503): the hop is per clip, w_length // window_size + 1, and the result is cropped to
+        # window_size frames -- one front-end plan per distinct hop (ValueError where librosa 0.9.2 raises ParameterError:
+        # the hop must be a multiple of 2^(octaves-1))
+        window = int(_get(opt, "window_size", 592))
+        for i in todo:
+            clip = waveforms[i].reshape(-1).to(device="cuda", dtype=torch.float32)
+            plan = CQTPlan.get(sr, int(clip.numel()) // window + 1, bpo * octaves, bpo)
+            mel, seq = plan.run(clip[None])
+            entry = cache_entry(mel[0], min(int(seq[0]), window))
+            if entry.shape[1] != expected_bins(opt):
+                raise RuntimeError(f"{names[i]}: {entry.shape[1]} bins, the reference expects {expected_bins(opt)}")
+            torch.save(entry, names[i])
+            written.append(names[i])
+        return written
     for lo in range(0, len(todo), batch):
         idx = todo[lo: lo + batch]
         clips = [waveforms[i].reshape(-1).to(device="cuda", dtype=torch.float32, non_blocking=True) for i in idx]

@@ -10,6 +10,7 @@ per-clip ``seq_length`` (KeyDataset.py:242-254, 497-509).  Both call libake_b200
 from __future__ import annotations
 
 import ctypes as C
+import threading
 from typing import Optional, Sequence, Tuple, Union
 
 import torch
@@ -37,8 +38,9 @@ class CQTPlan:
 
     @classmethod
     def get(cls, sr, hop_length, n_bins=288, bins_per_octave=36, fmin=None, filter_scale=1.0, sparsity=0.01) -> "CQTPlan":
+        # one plan per host thread: a plan carries per-call staging state and may only be driven by one thread at a time
         key = (float(sr), int(hop_length), int(n_bins), int(bins_per_octave), float(fmin or 0.0), float(filter_scale),
-               float(sparsity), torch.cuda.current_device() if torch.cuda.is_available() else -1)
+               float(sparsity), torch.cuda.current_device() if torch.cuda.is_available() else -1, threading.get_ident())
         plan = cls._cache.get(key)
         if plan is None:
             plan = cls._cache[key] = cls(sr, hop_length, n_bins, bins_per_octave, fmin, filter_scale, sparsity)

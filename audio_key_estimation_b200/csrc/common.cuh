@@ -4,8 +4,11 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <map>
+#include <mutex>
 #include <stdexcept>
 #include <string>
+#include <utility>
 
 #include "../../include/ake_b200.h"
 
@@ -58,15 +61,34 @@ inline int guarded(F&& f) {
   }
 }
 
-// SM count of the current device (persistent kernels launch one CTA, or a fixed few, per SM)
+inline int current_device() {
+  int dev = 0;
+  AKE_CUDA(cudaGetDevice(&dev));
+  return dev;
+}
+
+// SM count of the current device (persistent kernels launch one CTA, or a fixed few, per SM); cached per device
 inline int sm_count() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    AKE_CUDA(cudaGetDevice(&dev));
-    AKE_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+  static int n[64] = {};
+  const int dev = current_device();
+  if (dev < 0 || dev >= 64) fail(AKE_ERR_UNSUPPORTED, "device index %d", dev);
+  if (!n[dev]) AKE_CUDA(cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev));
+  return n[dev];
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE (and per-function) attribute: remember the largest size
+// opted into for (current device, kernel) so a second GPU driven from the same process gets its own opt-in.
+template <class K>
+inline void ensure_dyn_smem(K kern, size_t bytes) {
+  static std::mutex mu;
+  static std::map<std::pair<int, const void*>, size_t> seen;
+  const int dev = current_device();
+  std::lock_guard<std::mutex> lk(mu);
+  size_t& cur = seen[{dev, reinterpret_cast<const void*>(kern)}];
+  if (bytes > cur) {
+    AKE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    cur = bytes;
   }
-  return n;
 }
 
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
@@ -106,6 +128,10 @@ struct ProfScope {
     if (on) profile_record(tag, st, false, (int)(launch_counter() - launches0));
   }
 };
+
+// cqt.cu: the front-end with the per-clip lengths either on the host (validated + staged) or already on the device
+void run_cqt(::ake_cqt* p, const float* audio, long long stride, const int64_t* lengths_host, const long long* lengths_dev, int B,
+             long long n_max, int mode, float* out, int T_max, int* seq_len_out, void* ws, size_t ws_bytes, cudaStream_t st);
 
 constexpr float kLeakySlope = 0.01f;  // nn.LeakyReLU() default (models.py:197,234,315)
 constexpr float kBnEps = 1e-5f;       // nn.BatchNorm2d default

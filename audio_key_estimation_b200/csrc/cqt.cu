@@ -74,6 +74,14 @@ struct ake_cqt {
   __half* d_dec_img = nullptr;   // Toeplitz image of the 63-tap decimator (cascade_umma_kernel)
   float* d_scale_umma = nullptr;
   int npad = 0;  // filters per MMA (2*bpo rounded up to 16), 0: tensor-core path not available for this shape
+  int device = -1;  // device the operand images live on (the one current at the first run)
+  // page-locked staging ring for the per-clip lengths of ake_cqt_run_f32: a pageable source would make the H2D copy
+  // synchronise the stream (no host run-ahead); a slot is reused only after its copy has executed
+  static constexpr int kLenSlots = 4;
+  long long* h_len[kLenSlots] = {};
+  size_t h_len_cap[kLenSlots] = {};
+  cudaEvent_t h_len_done[kLenSlots] = {};
+  int h_len_next = 0;
 };
 
 namespace ake {
@@ -179,9 +187,21 @@ static void build_cqt(ake_cqt* p) {
   kaiser_fast_half(p->dec_half.data());
 }
 
-// Device copies are made lazily so that plan creation (and the bank / tap getters) need no GPU.
+static void free_device_state(ake_cqt* p) {
+  void** ptrs[] = {(void**)&p->d_scale, (void**)&p->d_bank_img, (void**)&p->d_dec_img, (void**)&p->d_scale_umma};
+  for (void** q : ptrs) {
+    if (*q) cudaFree(*q);
+    *q = nullptr;
+  }
+}
+
+// Device copies are made lazily so that plan creation (and the bank / tap getters) need no GPU; they live on the device
+// that is current when the plan first runs, and are rebuilt if the plan is later driven on another device.
 static void ensure_device(ake_cqt* p) {
-  if (p->d_scale) return;
+  const int dev = current_device();
+  if (p->d_scale && p->device == dev) return;
+  free_device_state(p);
+  p->device = dev;
   {
     // Toeplitz operand of the decimator (cascade_umma_kernel): H[n][k] = sqrt(2) h[|k - 2n - 32|], fp16 hi | lo.
     // (sqrt(2): resample(scale=True) divides by sqrt(ratio).)
@@ -928,18 +948,37 @@ static CqtWs carve(const ake_cqt* p, Arena& ar, int B, long long n_max) {
   return w;
 }
 
-static void run_cqt(ake_cqt* p, const float* audio, long long stride, const int64_t* lengths_host, int B, long long n_max,
-                    int mode, float* out, int T_max, int* seq_len_out, void* ws, size_t ws_bytes, cudaStream_t st) {
+// lengths_host -> w.d_len through the plan's page-locked ring (asynchronous: the host never waits for earlier work on `st`)
+static void stage_lengths(ake_cqt* p, const int64_t* lengths_host, int B, long long* d_len, cudaStream_t st) {
+  const int s = p->h_len_next;
+  p->h_len_next = (s + 1) % ake_cqt::kLenSlots;
+  if (!p->h_len_done[s]) AKE_CUDA(cudaEventCreateWithFlags(&p->h_len_done[s], cudaEventDisableTiming));
+  else AKE_CUDA(cudaEventSynchronize(p->h_len_done[s]));  // four calls ago: normally long complete
+  if (p->h_len_cap[s] < (size_t)B) {
+    if (p->h_len[s]) cudaFreeHost(p->h_len[s]);
+    p->h_len[s] = nullptr, p->h_len_cap[s] = 0;
+    AKE_CUDA(cudaMallocHost(&p->h_len[s], sizeof(long long) * (size_t)B));
+    p->h_len_cap[s] = (size_t)B;
+  }
+  for (int b = 0; b < B; ++b) p->h_len[s][b] = lengths_host[b];
+  AKE_CUDA(cudaMemcpyAsync(d_len, p->h_len[s], sizeof(long long) * B, cudaMemcpyHostToDevice, st));
+  AKE_CUDA(cudaEventRecord(p->h_len_done[s], st));
+}
+
+// lengths_host: validated and staged here; lengths_dev: already on the device (the host-buffer pipeline uploads every clip's
+// length once per batch); at most one of the two.
+void run_cqt(ake_cqt* p, const float* audio, long long stride, const int64_t* lengths_host, const long long* lengths_dev, int B,
+             long long n_max, int mode, float* out, int T_max, int* seq_len_out, void* ws, size_t ws_bytes, cudaStream_t st) {
   if (p->n_oct > 15) fail(AKE_ERR_UNSUPPORTED, "too many octaves");
   if (n_max >= (1LL << 31) - 65536) fail(AKE_ERR_UNSUPPORTED, "clips of 2^31 samples or more are not supported (32-bit sample indices in the cascade)");
   ensure_device(p);
   Arena ar(ws, ws_bytes);
   CqtWs w = carve(p, ar, B, n_max);
-  const long long* d_len = nullptr;
+  const long long* d_len = lengths_dev;
   if (lengths_host) {
     for (int b = 0; b < B; ++b)
       if (lengths_host[b] < 0 || lengths_host[b] > n_max) fail(AKE_ERR_INVALID, "lengths_host[%d]=%lld outside [0, n_max]", b, (long long)lengths_host[b]);
-    AKE_CUDA(cudaMemcpyAsync(w.d_len, lengths_host, sizeof(long long) * B, cudaMemcpyHostToDevice, st));
+    stage_lengths(p, lengths_host, B, w.d_len, st);
     d_len = w.d_len;
   }
   w.level[0] = const_cast<float*>(audio);
@@ -947,15 +986,8 @@ static void run_cqt(ake_cqt* p, const float* audio, long long stride, const int6
   if (p->n_oct > 1) {
     // resampling cascade: two octave steps per pass (level p -> p+1, p+2), one persistent warp-specialised CTA per SM
     ProfScope prof("cqt.decimate", st);
-    static bool configured = false;
-    static int n_sm = 0;
-    if (!configured) {
-      AKE_CUDA(cudaFuncSetAttribute(cascade_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCasSmemTotal));
-      int dev = 0;
-      AKE_CUDA(cudaGetDevice(&dev));
-      AKE_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-      configured = true;
-    }
+    ensure_dyn_smem(cascade_umma_kernel, kCasSmemTotal);
+    const int n_sm = sm_count();
     for (int lv = 0; lv < p->n_oct - 1; lv += 2) {
       CascadeArgs ca{};
       ca.in = w.level[lv], ca.in_stride = w.stride[lv];
@@ -990,19 +1022,11 @@ static void run_cqt(ake_cqt* p, const float* audio, long long stride, const int6
     dim3 grid((unsigned)cdiv64(rows, 128 * kBankMB), p->n_oct);
     if (p->npad == 80) {
       constexpr size_t smem = kUStages * bank_stage_bytes(80, kBankMB);
-      static bool configured = false;
-      if (!configured) {
-        AKE_CUDA(cudaFuncSetAttribute(cqt_bank_umma_kernel<80, kBankMB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-      }
+      ensure_dyn_smem(cqt_bank_umma_kernel<80, kBankMB>, smem);
       cqt_bank_umma_kernel<80, kBankMB><<<grid, kBankThreads, smem, st>>>(ba);
     } else {
       constexpr size_t smem = kUStages * bank_stage_bytes(32, kBankMB);
-      static bool configured = false;
-      if (!configured) {
-        AKE_CUDA(cudaFuncSetAttribute(cqt_bank_umma_kernel<32, kBankMB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-      }
+      ensure_dyn_smem(cqt_bank_umma_kernel<32, kBankMB>, smem);
       cqt_bank_umma_kernel<32, kBankMB><<<grid, kBankThreads, smem, st>>>(ba);
     }
     AKE_LAUNCHED();
@@ -1039,10 +1063,11 @@ int ake_cqt_create(double sr, int hop_length, int n_bins, int bins_per_octave, d
 
 void ake_cqt_destroy(ake_cqt* p) {
   if (!p) return;
-  if (p->d_scale) cudaFree(p->d_scale);
-  if (p->d_bank_img) cudaFree(p->d_bank_img);
-  if (p->d_dec_img) cudaFree(p->d_dec_img);
-  if (p->d_scale_umma) cudaFree(p->d_scale_umma);
+  free_device_state(p);
+  for (int s = 0; s < ake_cqt::kLenSlots; ++s) {
+    if (p->h_len[s]) cudaFreeHost(p->h_len[s]);
+    if (p->h_len_done[s]) cudaEventDestroy(p->h_len_done[s]);
+  }
   delete p;
 }
 
@@ -1079,7 +1104,7 @@ int ake_cqt_run_f32(ake_cqt* p, const float* audio_dev, int64_t stride, const in
     if (B <= 0 || n_max <= 0 || stride < n_max || T_max <= 0) fail(AKE_ERR_INVALID, "bad sizes");
     if (mode != AKE_CQT_LOGMAG && mode != AKE_CQT_COMPLEX) fail(AKE_ERR_INVALID, "bad mode");
     ProfScope prof("cqt.total", static_cast<cudaStream_t>(stream));
-    run_cqt(p, audio_dev, stride, lengths_host, B, n_max, mode, out_dev, T_max, seq_len_out_dev, ws_dev, ws_bytes,
+    run_cqt(p, audio_dev, stride, lengths_host, nullptr, B, n_max, mode, out_dev, T_max, seq_len_out_dev, ws_dev, ws_bytes,
             static_cast<cudaStream_t>(stream));
   });
 }

@@ -137,7 +137,10 @@ struct ake_pcn {
   __half* d_wimg_tail = nullptr;    // last conv of the tonic / key / genre heads (head_tail_umma_kernel), 12 KB each
   bool umma_heads = false;
   std::map<std::string, std::pair<const float*, int64_t>> taps;
-  struct ake::TrainTape* tape = nullptr;  // activations kept by the last bn_mode = 2 forward (pcn_train.cuh)
+  // activations kept by the bn_mode = 2 forwards that have not been back-propagated yet, keyed by their workspace
+  // (pcn_train.cuh): several kept forwards may be outstanding (summed losses, siamese use), each with its own workspace
+  std::map<const void*, struct ake::TrainTape*> tapes;
+  int device = -1;  // device the weights / operand images live on (set by the first upload)
 };
 
 namespace ake {
@@ -301,11 +304,7 @@ static void launch_conv_t(ConvArgs a, int B, int max_tg, cudaStream_t st) {
   const int threads = cdiv(RB * a.tgroups, 32) * 32;
   const size_t smem = sizeof(float) * ((size_t)kConvCI * RIN * xp + (size_t)kConvCI * KH * KW * CO_T);
   auto kern = conv_rows_kernel<KH, KW, SR, RB, CO_T, RT>;
-  static size_t configured = 0;
-  if (smem > configured) {
-    AKE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  ensure_dyn_smem(kern, smem);
   dim3 grid(n_tiles, a.n_row_tiles * (a.cout_pad / CO_T), B);
   kern<<<grid, threads, smem, st>>>(a);
   AKE_LAUNCHED();
@@ -357,6 +356,7 @@ struct Fwd {
   bool umma_pc_ready = false;
   bool l0_fast = false;
   __half* l0_planes[3][2] = {};
+  int os_key = 12, os_tonic = 12, os_genre = 11;  // floats between consecutive clips' outputs (35: (B, 35) result rows)
   double* d_stats = nullptr;  // train: per conv channel (sum, sumsq)
   float* d_ss_train = nullptr;
 
@@ -559,14 +559,10 @@ void Fwd::run(const float* mel, float* key_out, float* tonic_out, float* genre_o
           const Conv& c = p->convs[lp.p2p[i]];
           if (!dry) {
             ProfScope prof("pcn.p2p", st);
-            static size_t configured = 0;
-            if (smem > configured) {
-              AKE_CUDA(cudaFuncSetAttribute(p2p_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-              AKE_CUDA(cudaFuncSetAttribute(p2p_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-              AKE_CUDA(cudaFuncSetAttribute((p2p_umma_kernel<false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-              AKE_CUDA(cudaFuncSetAttribute(p2p1_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f1_smem_bytes(TB)));
-              configured = smem;
-            }
+            ensure_dyn_smem(p2p_umma_kernel<false>, smem);
+            ensure_dyn_smem(p2p_umma_kernel<true>, smem);
+            ensure_dyn_smem(p2p_umma_kernel<false, true>, smem);
+            ensure_dyn_smem(p2p1_umma_kernel, f1_smem_bytes(TB));
             const int n_rt = cdiv(P, kP2PRows), n_tiles = B * n_rt * cdiv(Tn, TB);
             check_decode_range((long long)B * n_rt * cdiv(Tn, TB), (long long)n_rt * cdiv(Tn, TB), "Pitch2Pitch");
             P2PArgs a{x[cur][0], x[cur][1], x[cur ^ 1][0], x[cur ^ 1][1],
@@ -611,11 +607,7 @@ void Fwd::run(const float* mel, float* key_out, float* tonic_out, float* genre_o
                             B, P, Tn, Wd, n_oct, TBs, n_tt, B * 12 * n_tt};
             check_decode_range((long long)B * 12 * n_tt, 12LL * n_tt, "pool_semi");
             const size_t smem_s = semi_smem_bytes(n_oct, TBs + 2);
-            static size_t conf_s = 0;
-            if (smem_s > conf_s) {
-              AKE_CUDA(cudaFuncSetAttribute(semi_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
-              conf_s = smem_s;
-            }
+            ensure_dyn_smem(semi_umma_kernel, smem_s);
             semi_umma_kernel<<<std::min(sa.n_items, sm_count()), kSemiThreads, smem_s, st>>>(sa);
           } else {
             SemiArgs sa{x[cur][0], x[cur][1], p->d_params + cs.w_off, scale_of(cs, false), shift_of(cs, false), pc.p,
@@ -636,15 +628,8 @@ void Fwd::run(const float* mel, float* key_out, float* tonic_out, float* genre_o
             for (int j = 0; j < 2; ++j) AKE_CUDA(cudaMemsetAsync(e[i][j], 0, sizeof(__half) * eq_halves, st));
           const int n_tt = cdiv(Tn, 32), TBe = (cdiv(Tn, n_tt) + 1) / 2 * 2;
           const size_t smem_e = pc2pc_smem_bytes(TBe + 6);
-          static size_t conf0 = 0, conf1 = 0;
-          if (smem_e > conf0) {
-            AKE_CUDA(cudaFuncSetAttribute(pc2pc_umma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e));
-            conf0 = smem_e;
-          }
-          if (smem_e > conf1) {
-            AKE_CUDA(cudaFuncSetAttribute(pc2pc_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e));
-            conf1 = smem_e;
-          }
+          ensure_dyn_smem(pc2pc_umma_kernel<0>, smem_e);
+          ensure_dyn_smem(pc2pc_umma_kernel<1>, smem_e);
           int ce = 0;
           for (size_t i = 0; i < lp.pc2pc.size(); ++i) {
             const Conv& c = p->convs[lp.pc2pc[i]];
@@ -725,15 +710,8 @@ void Fwd::run(const float* mel, float* key_out, float* tonic_out, float* genre_o
           for (int j = 0; j < 2; ++j) AKE_CUDA(cudaMemsetAsync(l0_planes[i][j], 0, sizeof(__half) * halves, st));
         const int n_tt = cdiv(Tn, kPc8MaxTB), TB8 = (cdiv(Tn, n_tt) + 1) / 2 * 2;
         const size_t smem8 = pc8_smem_bytes(TB8 + 6);
-        static size_t c0 = 0, c2 = 0;
-        if (smem8 > c0) {
-          AKE_CUDA(cudaFuncSetAttribute(pc8_umma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
-          c0 = smem8;
-        }
-        if (smem8 > c2) {
-          AKE_CUDA(cudaFuncSetAttribute(pc8_umma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
-          c2 = smem8;
-        }
+        ensure_dyn_smem(pc8_umma_kernel<0>, smem8);
+        ensure_dyn_smem(pc8_umma_kernel<2>, smem8);
         for (size_t i = 0; i < lp.pc2pc.size(); ++i) {
           const Conv& c = p->convs[lp.pc2pc[i]];
           const bool last = i + 1 == lp.pc2pc.size();
@@ -828,11 +806,7 @@ void Fwd::run(const float* mel, float* key_out, float* tonic_out, float* genre_o
       ProfScope prof("pcn.equiv", st);
       const int n_tt = cdiv(T1, 32), TBe = (cdiv(T1, n_tt) + 1) / 2 * 2;
       const size_t smem_e = equiv_smem_bytes(TBe + 6);
-      static size_t conf = 0, confg = 0;
-      if (smem_e > conf) {
-        AKE_CUDA(cudaFuncSetAttribute(equiv_umma_kernel<64, 1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e));
-        conf = smem_e;
-      }
+      ensure_dyn_smem(equiv_umma_kernel<64, 1, 3>, smem_e);
       EquivArgs ea{};
       ea.in_hi = umma_pc_hi, ea.in_lo = umma_pc_lo, ea.Wd_in = Tn, ea.T_out = T1, ea.TB = TBe, ea.n_ttiles = cdiv(T1, TBe);
       ea.wimg = p->d_wimg_heads, ea.scale = p->d_ss_heads, ea.shift = p->d_ss_heads + 64;
@@ -840,10 +814,7 @@ void Fwd::run(const float* mel, float* key_out, float* tonic_out, float* genre_o
       equiv_umma_kernel<64, 1, 3><<<dim3(ea.n_ttiles, B), 192, smem_e, st>>>(ea);
       AKE_LAUNCHED();
       if (cfg.genre) {
-        if (smem_e > confg) {
-          AKE_CUDA(cudaFuncSetAttribute(equiv_umma_kernel<32, 1, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e));
-          confg = smem_e;
-        }
+        ensure_dyn_smem(equiv_umma_kernel<32, 1, 3, 1>, smem_e);
         const Conv& cg = p->convs[p->genre_head[0]];
         ea.wimg = p->d_wimg_genre, ea.scale = scale_of(cg, false), ea.shift = shift_of(cg, false);
         ea.out_hi = g_hi, ea.out_lo = g_lo, ea.out_rows = 12;
@@ -871,6 +842,7 @@ void Fwd::run(const float* mel, float* key_out, float* tonic_out, float* genre_o
       int pool_div = 1;
       for (int i = 0; i < cfg.num_layers - 1; ++i) pool_div *= cfg.time_pool_size;
       fa.seq_len = seq_len, fa.T1 = T1, fa.Tf = Tf, fa.pool_div = pool_div, fa.head_shrink = (k - 1) * cfg.head_layers;
+      fa.out_stride[0] = os_tonic, fa.out_stride[1] = os_key, fa.out_stride[2] = os_genre;
       head_fold_kernel<<<dim3(B, nh), 512, 0, st>>>(fa);
       AKE_LAUNCHED();
       heads_folded = true;
@@ -890,11 +862,7 @@ void Fwd::run(const float* mel, float* key_out, float* tonic_out, float* genre_o
       const int n_tt = cdiv(Tf, 20);
       ha.T1 = T1, ha.Tf = Tf, ha.TB = cdiv(Tf, n_tt), ha.n_ttiles = cdiv(Tf, ha.TB);
       const size_t smem_h = head_tail_smem_bytes(ha.TB + 6);
-      static size_t conf_h = 0;
-      if (smem_h > conf_h) {
-        AKE_CUDA(cudaFuncSetAttribute(head_tail_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_h));
-        conf_h = smem_h;
-      }
+      ensure_dyn_smem(head_tail_umma_kernel, smem_h);
       head_tail_umma_kernel<<<dim3(ha.n_ttiles, nh, B), 160, smem_h, st>>>(ha);
       AKE_LAUNCHED();
     }
@@ -913,7 +881,7 @@ void Fwd::run(const float* mel, float* key_out, float* tonic_out, float* genre_o
     const int rows = cfg.genre ? 35 : 24;
     head_reduce_kernel<<<cdiv(B * rows * 32, 256), 256, 0, st>>>(key_f.p, tonic_f.p, cfg.genre ? genre_f.p : nullptr, B,
                                                                 tonic_f.T, seq_len, pool_div, (k - 1) * cfg.head_layers,
-                                                                cfg.max_pool, key_out, tonic_out, genre_out);
+                                                                cfg.max_pool, key_out, tonic_out, genre_out, os_key, os_tonic, os_genre);
     AKE_LAUNCHED();
   }
 }
@@ -922,8 +890,26 @@ void Fwd::run(const float* mel, float* key_out, float* tonic_out, float* genre_o
 #include "pcn_train.cuh"
 namespace ake {
 
+// Everything the plan allocated on its device (weights and operand images).
+static void free_device_state(ake_pcn* p) {
+  void** ptrs[] = {(void**)&p->d_params, (void**)&p->d_packed, (void**)&p->d_ss_eval, (void**)&p->d_ss_raw, (void**)&p->d_wimg,
+                   (void**)&p->d_wimg_f1, (void**)&p->d_wimg_pc, (void**)&p->d_wimg_l0, (void**)&p->d_wimg_semi, (void**)&p->d_wimg_heads,
+                   (void**)&p->d_ss_heads, (void**)&p->d_wimg_genre, (void**)&p->d_wimg_tail};
+  for (void** q : ptrs) {
+    if (*q) cudaFree(*q);
+    *q = nullptr;
+  }
+  p->has_params = false;
+}
+
 static void upload_params(ake_pcn* p, const float* flat_dev, int64_t n, cudaStream_t st) {
   if (n != p->n_params) fail(AKE_ERR_INVALID, "expected %lld parameter floats, got %lld", (long long)p->n_params, (long long)n);
+  // The plan's buffers live on the device that is current at upload time; a module moved to another GPU re-uploads there.
+  const int dev = current_device();
+  if (p->device != dev) {
+    free_device_state(p);
+    p->device = dev;
+  }
   if (!p->d_params) {
     AKE_CUDA(cudaMalloc(&p->d_params, sizeof(float) * p->n_params));
     AKE_CUDA(cudaMalloc(&p->d_packed, sizeof(float) * std::max<int64_t>(p->n_packed, 1)));
@@ -1106,20 +1092,8 @@ int ake_pcn_create(const ake_pcn_config* cfg, ake_pcn** out) {
 
 void ake_pcn_destroy(ake_pcn* p) {
   if (!p) return;
-  cudaFree(p->d_params);
-  cudaFree(p->d_packed);
-  cudaFree(p->d_ss_eval);
-  cudaFree(p->d_ss_raw);
-  cudaFree(p->d_wimg);
-  cudaFree(p->d_wimg_f1);
-  cudaFree(p->d_wimg_pc);
-  cudaFree(p->d_wimg_l0);
-  cudaFree(p->d_wimg_semi);
-  cudaFree(p->d_wimg_heads);
-  cudaFree(p->d_ss_heads);
-  cudaFree(p->d_wimg_genre);
-  cudaFree(p->d_wimg_tail);
-  delete p->tape;
+  free_device_state(p);
+  for (auto& kv : p->tapes) delete kv.second;
   delete p;
 }
 
@@ -1174,16 +1148,49 @@ int ake_pcn_forward_f32(ake_pcn* p, const float* mel_dev, int B, int T, const in
     if (p->cfg.genre && !genre_out_dev) fail(AKE_ERR_INVALID, "genre head enabled but genre_out_dev is NULL");
     if (B <= 0 || T <= 0) fail(AKE_ERR_INVALID, "B and T must be positive (got %d, %d)", B, T);
     if (!p->has_params) fail(AKE_ERR_INVALID, "ake_pcn_set_params_f32 has not been called");
+    if (current_device() != p->device)
+      fail(AKE_ERR_INVALID, "the plan's weights live on device %d but device %d is current: upload the parameters there first", p->device,
+           current_device());
     ProfScope prof("pcn.total", static_cast<cudaStream_t>(stream));
     Fwd f(p, B, T, bn_mode != 0, ws_dev, ws_bytes, static_cast<cudaStream_t>(stream));
     f.seq_len = seq_len_dev, f.bn_stats_out = bn_stats_out_dev;
     if (bn_mode == 2) {
-      if (!p->tape) p->tape = new TrainTape();
-      p->tape->valid = false;
-      f.run_keep(mel_dev, key_out_dev, tonic_out_dev, p->cfg.genre ? genre_out_dev : nullptr, *p->tape);
-      p->tape->ws = ws_dev;
+      if (p->tapes.size() > 64) {  // forwards whose backward never came (dropped graphs): forget the oldest bookkeeping
+        for (auto& kv : p->tapes) delete kv.second;
+        p->tapes.clear();
+      }
+      TrainTape*& tape = p->tapes[ws_dev];
+      if (!tape) tape = new TrainTape();
+      tape->valid = false;
+      f.run_keep(mel_dev, key_out_dev, tonic_out_dev, p->cfg.genre ? genre_out_dev : nullptr, *tape);
+      tape->ws = ws_dev;
     } else {
       f.run(mel_dev, key_out_dev, tonic_out_dev, p->cfg.genre ? genre_out_dev : nullptr);
+    }
+  });
+}
+
+int ake_pcn_forward_rows_f32(ake_pcn* p, const float* mel_dev, int B, int T, const int32_t* seq_len_dev, float* rows_out_dev,
+                             int32_t* ids_out_dev, void* ws_dev, size_t ws_bytes, void* stream) {
+  return guarded([&] {
+    if (!p || !mel_dev || !rows_out_dev || !ws_dev) fail(AKE_ERR_INVALID, "null argument");
+    if (B <= 0 || T <= 0) fail(AKE_ERR_INVALID, "B and T must be positive (got %d, %d)", B, T);
+    if (!p->has_params) fail(AKE_ERR_INVALID, "ake_pcn_set_params_f32 has not been called");
+    if (current_device() != p->device)
+      fail(AKE_ERR_INVALID, "the plan's weights live on device %d but device %d is current: upload the parameters there first", p->device,
+           current_device());
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    ProfScope prof("pcn.total", st);
+    // without a genre head the genre columns stay zero
+    if (!p->cfg.genre) AKE_CUDA(cudaMemsetAsync(rows_out_dev, 0, sizeof(float) * AKE_ROW_FLOATS * (size_t)B, st));
+    Fwd f(p, B, T, false, ws_dev, ws_bytes, st);
+    f.seq_len = seq_len_dev, f.bn_stats_out = nullptr;
+    f.os_key = f.os_tonic = f.os_genre = AKE_ROW_FLOATS;
+    f.run(mel_dev, rows_out_dev, rows_out_dev + 12, p->cfg.genre ? rows_out_dev + 24 : nullptr);
+    if (ids_out_dev) {
+      decode_kernel<<<cdiv(B, 128), 128, 0, st>>>(rows_out_dev, rows_out_dev + 12, p->cfg.genre ? rows_out_dev + 24 : nullptr, B, ids_out_dev,
+                                                  ids_out_dev + B, ids_out_dev + 2 * B, AKE_ROW_FLOATS, AKE_ROW_FLOATS, AKE_ROW_FLOATS);
+      AKE_LAUNCHED();
     }
   });
 }
@@ -1194,14 +1201,17 @@ int ake_pcn_backward_f32(ake_pcn* p, const float* d_key_out_dev, const float* d_
     if (!p || !grads_out_dev || !ws_dev) fail(AKE_ERR_INVALID, "null argument");
     if (!d_key_out_dev && !d_tonic_out_dev && !d_genre_out_dev) fail(AKE_ERR_INVALID, "no output gradient given");
     if (n_floats != p->n_params) fail(AKE_ERR_INVALID, "grads_out_dev must hold %lld floats", (long long)p->n_params);
-    if (!p->tape || !p->tape->valid) fail(AKE_ERR_INVALID, "no kept forward: call ake_pcn_forward_f32 with bn_mode = 2 first");
-    if (p->tape->ws != ws_dev) fail(AKE_ERR_INVALID, "the backward pass needs the workspace of the kept forward");
+    auto it = p->tapes.find(ws_dev);
+    if (it == p->tapes.end() || !it->second->valid)
+      fail(AKE_ERR_INVALID, "no kept forward in this workspace: call ake_pcn_forward_f32 with bn_mode = 2 on it first (one backward per kept forward)");
+    TrainTape* tape = it->second;
     ProfScope prof("pcn.backward", static_cast<cudaStream_t>(stream));
-    Fwd f(p, p->tape->B, p->tape->T, true, ws_dev, ws_bytes, static_cast<cudaStream_t>(stream));
-    f.arena.off = p->tape->ws_off;
-    f.seq_len = p->tape->seq_len, f.bn_stats_out = nullptr;
-    f.backward_keep(*p->tape, d_key_out_dev, d_tonic_out_dev, d_genre_out_dev, grads_out_dev);
-    p->tape->valid = false;  // the backward pass reuses nothing: one backward per kept forward
+    Fwd f(p, tape->B, tape->T, true, ws_dev, ws_bytes, static_cast<cudaStream_t>(stream));
+    f.arena.off = tape->ws_off;
+    f.seq_len = tape->seq_len, f.bn_stats_out = nullptr;
+    f.backward_keep(*tape, d_key_out_dev, d_tonic_out_dev, d_genre_out_dev, grads_out_dev);
+    delete tape;  // the backward pass reuses nothing: one backward per kept forward
+    p->tapes.erase(it);
   });
 }
 
@@ -1249,15 +1259,16 @@ int ake_decode_f32(const float* key_out_dev, const float* tonic_out_dev, const f
 }
 
 int ake_mirex_f32(const float* key_out_dev, const float* tonic_out_dev, const float* key_labels_dev,
-                  const float* tonic_labels_dev, const float* key_signature_id_dev, int B, uint64_t* counters_dev,
+                  const float* tonic_labels_dev, const float* key_signature_id_dev, int sig_width, int B, uint64_t* counters_dev,
                   float* similarity_out_dev, int32_t* category_out_dev, void* stream) {
   return guarded([&] {
     if (B <= 0) fail(AKE_ERR_INVALID, "B must be positive");
+    if (sig_width <= 0) fail(AKE_ERR_INVALID, "sig_width must be positive");
     if (!key_out_dev || !tonic_out_dev || !key_labels_dev || !tonic_labels_dev || !key_signature_id_dev || !counters_dev)
       fail(AKE_ERR_INVALID, "null argument");
     static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "counter width");
     mirex_kernel<<<cdiv(B, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
-        key_out_dev, tonic_out_dev, key_labels_dev, tonic_labels_dev, key_signature_id_dev, B,
+        key_out_dev, tonic_out_dev, key_labels_dev, tonic_labels_dev, key_signature_id_dev, sig_width, B,
         reinterpret_cast<unsigned long long*>(counters_dev), similarity_out_dev, category_out_dev);
     AKE_LAUNCHED();
   });

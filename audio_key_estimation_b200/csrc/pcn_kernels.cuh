@@ -454,13 +454,22 @@ __global__ void timepool_kernel(const float* __restrict__ in, int B, int C, int 
   }
 }
 
+// Frames the masked temporal mean runs over: actual_seq_length = floor(seq / pool^(L-1)) - (k-1) * head_layers, then the
+// Python slice x[..., :actual_seq_length] (models.py:757-770): a positive length clamps to the Th frames that exist, a
+// NEGATIVE one (very short clips) counts from the end -- Th + length frames -- and an empty slice gives torch.mean = nan.
+__device__ __forceinline__ int masked_frames(int seq, int pool_div, int head_shrink, int Th) {
+  const int m = seq / pool_div - head_shrink;
+  return m >= 0 ? min(Th, m) : max(0, Th + m);
+}
+
 // ---- masked temporal mean / max + sigmoid (models.py:754-804) -----------------------------------
 // One warp per output element (clip, head row).  frames: key (B,12,Th), tonic (B,12,Th), genre (B,11,Th).
 // Fixed summation order (lane-strided partial sums, then a shuffle tree) independent of the row index.
 __global__ void head_reduce_kernel(const float* __restrict__ key_f, const float* __restrict__ tonic_f,
                                    const float* __restrict__ genre_f, int B, int Th, const int* __restrict__ seq_len,
                                    int pool_div, int head_shrink, int max_pool, float* __restrict__ key_out,
-                                   float* __restrict__ tonic_out, float* __restrict__ genre_out) {
+                                   float* __restrict__ tonic_out, float* __restrict__ genre_out, int os_key = 12,
+                                   int os_tonic = 12, int os_genre = 11) {  // os_*: floats between consecutive clips' outputs
   const int rows_per_clip = genre_f ? 35 : 24;
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (gw >= B * rows_per_clip) return;
@@ -469,17 +478,17 @@ __global__ void head_reduce_kernel(const float* __restrict__ key_f, const float*
   float* dst;
   int is_key = 0;
   if (rr < 12) {
-    src = key_f + ((long long)b * 12 + rr) * Th, dst = key_out + b * 12 + rr, is_key = 1;
+    src = key_f + ((long long)b * 12 + rr) * Th, dst = key_out + (long long)b * os_key + rr, is_key = 1;
   } else if (rr < 24) {
-    src = tonic_f + ((long long)b * 12 + rr - 12) * Th, dst = tonic_out + b * 12 + rr - 12;
+    src = tonic_f + ((long long)b * 12 + rr - 12) * Th, dst = tonic_out + (long long)b * os_tonic + rr - 12;
   } else {
-    src = genre_f + ((long long)b * 11 + rr - 24) * Th, dst = genre_out + b * 11 + rr - 24;
+    src = genre_f + ((long long)b * 11 + rr - 24) * Th, dst = genre_out + (long long)b * os_genre + rr - 24;
   }
   int n = Th;
   bool use_max = max_pool != 0;
   if (seq_len) {
     // actual_seq_length = floor(seq / pool^(L-1)) - (k-1)*head_layers  (models.py:757-760); slicing clamps to Th
-    n = min(Th, seq_len[b] / pool_div - head_shrink);
+    n = masked_frames(seq_len[b], pool_div, head_shrink, Th);
     use_max = max_pool && b == 0;  // reference quirk: max_pool honoured for sample 0 only (models.py:765-785)
   }
   float v;
@@ -515,6 +524,7 @@ struct HeadFoldArgs {
   int G_total[3], g0[3], R[3], KH[3], rows_out[3], wrap[3], sigmoid[3];
   const int* seq_len;     // or NULL
   int T1, Tf, pool_div, head_shrink;
+  int out_stride[3];      // floats between consecutive clips' outputs (12 / 12 / 11, or 35 when the heads write (B, 35) result rows)
 };
 
 __global__ void __launch_bounds__(512) head_fold_kernel(const HeadFoldArgs a) {
@@ -522,8 +532,8 @@ __global__ void __launch_bounds__(512) head_fold_kernel(const HeadFoldArgs a) {
   __shared__ float edge[4 * 12 * 12 * 8];  // [group][row][j 12 = head 0..5, tail 0..5][8 ch]: y[j] and y[n + j]
   const int h = blockIdx.y, b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int n = a.Tf;
-  if (a.seq_len) n = min(a.Tf, a.seq_len[b] / a.pool_div - a.head_shrink);  // models.py:757-760; slicing clamps
-  float* out = a.out[h] + (long long)b * a.rows_out[h];
+  if (a.seq_len) n = masked_frames(a.seq_len[b], a.pool_div, a.head_shrink, a.Tf);
+  float* out = a.out[h] + (long long)b * a.out_stride[h];
   if (n <= 0) {  // empty slice: torch.mean -> nan
     if (threadIdx.x < a.rows_out[h]) out[threadIdx.x] = __int_as_float(0x7fc00000);
     return;
@@ -612,12 +622,13 @@ __constant__ unsigned short kKeySignatureBits[21] = {
 
 __global__ void decode_kernel(const float* __restrict__ key_out, const float* __restrict__ tonic_out,
                               const float* __restrict__ genre_out, int B, int* __restrict__ key_id,
-                              int* __restrict__ tonic_id, int* __restrict__ genre_id) {
+                              int* __restrict__ tonic_id, int* __restrict__ genre_id, int os_key = 12, int os_tonic = 12,
+                              int os_genre = 11) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   if (key_id) {
     float k[12], nk = 0.f;
-    for (int i = 0; i < 12; ++i) k[i] = key_out[b * 12 + i], nk = fmaf(k[i], k[i], nk);
+    for (int i = 0; i < 12; ++i) k[i] = key_out[(long long)b * os_key + i], nk = fmaf(k[i], k[i], nk);
     const float inv = 1.f / (fmaxf(sqrtf(nk), 1e-8f) * sqrtf(7.f));
     int best = 0;
     float bv = -INFINITY;
@@ -633,7 +644,7 @@ __global__ void decode_kernel(const float* __restrict__ key_out, const float* __
   if (tonic_id) {
     int best = 0;
     for (int i = 1; i < 12; ++i)
-      if (tonic_out[b * 12 + i] > tonic_out[b * 12 + best]) best = i;
+      if (tonic_out[(long long)b * os_tonic + i] > tonic_out[(long long)b * os_tonic + best]) best = i;
     tonic_id[b] = best;
   }
   if (genre_id) {
@@ -641,7 +652,7 @@ __global__ void decode_kernel(const float* __restrict__ key_out, const float* __
     if (genre_out) {
       best = 0;
       for (int i = 1; i < 11; ++i)
-        if (genre_out[b * 11 + i] > genre_out[b * 11 + best]) best = i;
+        if (genre_out[(long long)b * os_genre + i] > genre_out[(long long)b * os_genre + best]) best = i;
     }
     genre_id[b] = best;
   }
@@ -652,7 +663,7 @@ __global__ void decode_kernel(const float* __restrict__ key_out, const float* __
 // correct tonics, key bits right.  One thread per clip; the categories follow the reference's if-chain (first match wins).
 __global__ void __launch_bounds__(128) mirex_kernel(const float* __restrict__ key_out, const float* __restrict__ tonic_out,
                                                     const float* __restrict__ key_labels, const float* __restrict__ tonic_labels,
-                                                    const float* __restrict__ key_sig_id, int B, unsigned long long* __restrict__ counters,
+                                                    const float* __restrict__ key_sig_id, int sig_w, int B, unsigned long long* __restrict__ counters,
                                                     float* __restrict__ sim_out, int* __restrict__ cat_out) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   unsigned int c[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -673,9 +684,10 @@ __global__ void __launch_bounds__(128) mirex_kernel(const float* __restrict__ ke
       d *= inv;
       if (d > bv) bv = d, pred = r;
     }
+    // torch.argmax(key_signature_id[i]) over whatever width the data layer delivers (24-wide one-hot: KeyDataset.py:366, 447)
     int label = 0;
-    for (int r = 1; r < 21; ++r)
-      if (key_sig_id[b * 21 + r] > key_sig_id[b * 21 + label]) label = r;
+    for (int r = 1; r < sig_w; ++r)
+      if (key_sig_id[(long long)b * sig_w + r] > key_sig_id[(long long)b * sig_w + label]) label = r;
     int bits = 0;
     for (int i = 0; i < 12; ++i) bits += (float)((kKeySignatureBits[pred] >> (11 - i)) & 1) == lab[i];
     int tl = 0, tp = 0;

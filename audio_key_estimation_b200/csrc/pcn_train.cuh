@@ -58,11 +58,7 @@ static void launch_wgrad_t(const WgradArgs& a, int B, cudaStream_t st) {
   const size_t smem = sizeof(float) * ((size_t)RIN * XP + (size_t)a.Cout * RB * kWgTB);
   if (a.Cout * KH > 512) fail(AKE_ERR_UNSUPPORTED, "weight-gradient kernel: Cout * KH = %d > 512", a.Cout * KH);
   auto kern = conv_wgrad_kernel<KH, KW, SR, RB>;
-  static size_t configured = 0;
-  if (smem > configured) {
-    AKE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  ensure_dyn_smem(kern, smem);
   kern<<<dim3(cdiv(a.rows_out, RB), a.Cin, B), 256, smem, st>>>(a);
   AKE_LAUNCHED();
 }

@@ -117,6 +117,42 @@ def gather_rows(local_rows: torch.Tensor, n_clips: int, group=None) -> torch.Ten
     return torch.cat([recv[r * cmax: r * cmax + counts[r]] for r in range(world)], dim=0)
 
 
+class RowGather:
+    """The all-gather of one step's (clips, 35) result rows, issued asynchronously: NCCL runs it on the process group's own
+    stream, ordered after the kernels already queued on the current stream, so it overlaps the NEXT step's kernels; ``wait()``
+    makes the current stream wait for it and returns the (n_clips, 35) table in clip order.  (gloo: same API on CPU tensors.)"""
+
+    def __init__(self, local_rows: torch.Tensor, n_clips: int, group=None):
+        self._n, self._group = n_clips, group
+        self._work, self._recv, self._counts = None, None, None
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            if local_rows.shape[0] != n_clips:
+                raise ValueError("single process must hold every clip")
+            self._recv = local_rows
+            return
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        counts = shard_counts(n_clips, world)
+        if local_rows.shape[0] != counts[rank]:
+            raise ValueError(f"rank {rank} holds {local_rows.shape[0]} rows, expected {counts[rank]}")
+        cmax, width = max(counts), local_rows.shape[1]
+        send = local_rows.contiguous()
+        if counts[rank] != cmax:
+            send = torch.zeros((cmax, width), dtype=local_rows.dtype, device=local_rows.device)
+            send[: counts[rank]] = local_rows
+        self._recv = torch.empty((world * cmax, width), dtype=local_rows.dtype, device=local_rows.device)
+        self._counts = counts
+        self._work = dist.all_gather_into_tensor(self._recv, send, group=group, async_op=True)
+
+    def wait(self) -> torch.Tensor:
+        if self._work is not None:
+            self._work.wait()
+            self._work = None
+        if self._counts is None or all(c == max(self._counts) for c in self._counts):
+            return self._recv
+        cmax = max(self._counts)
+        return torch.cat([self._recv[r * cmax: r * cmax + c] for r, c in enumerate(self._counts)], dim=0)
+
+
 def reduce_counters(counters: torch.Tensor, group=None) -> torch.Tensor:
     """Sum a small vector of metric counters over ranks (in place)."""
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:

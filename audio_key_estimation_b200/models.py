@@ -22,6 +22,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import threading
 from typing import Optional, Tuple
 
 import torch
@@ -34,13 +35,24 @@ _UNSUPPORTED_FLAGS = ("resblock", "denseblock", "stay_sixth", "only_semitones", 
 
 
 class _Workspace:
-    """Grow-only device scratch buffer per (device, tag)."""
+    """Grow-only device scratch buffer per (device, CUDA stream, tag).
+
+    Keyed by the stream the work is launched on: calls on one stream are ordered, so they may share scratch; two host
+    threads driving two plans on two streams (include/ake_b200.h: "different plans may be driven from different host
+    threads / streams") get separate buffers."""
 
     _bufs: dict = {}
+    _lock = threading.Lock()
 
     @classmethod
     def get(cls, device: torch.device, nbytes: int, tag: str = "pcn") -> torch.Tensor:
-        key = (device.index if device.index is not None else torch.cuda.current_device(), tag)
+        with cls._lock:
+            return cls._get(device, nbytes, tag)
+
+    @classmethod
+    def _get(cls, device: torch.device, nbytes: int, tag: str) -> torch.Tensor:
+        index = device.index if device.index is not None else torch.cuda.current_device()
+        key = (index, int(torch.cuda.current_stream(device).cuda_stream), tag)
         buf = cls._bufs.get(key)
         if buf is None or buf.numel() < nbytes:
             buf = None
@@ -236,6 +248,9 @@ class PitchClassNet(nn.Module):
                     raise ValueError(f"seq_length has {seq.numel()} entries for a batch of {B}")
                 seq = seq.to(device=device, dtype=torch.int32).contiguous()
             train = bool(self.training)
+            if train and torch.is_grad_enabled() and mel.requires_grad:
+                raise NotImplementedError("gradients with respect to the input spectrogram are not computed by the B200 backward "
+                                          "pass (the reference never asks for them: KeyDataset tensors carry no grad)")
             if train and torch.is_grad_enabled() and any(p.requires_grad for p in self._grad_params()):
                 outs = _KeptForward.apply(self, x, seq, *self._grad_params())
                 return tuple(o.to(out_dtype) for o in outs)
@@ -257,6 +272,44 @@ class PitchClassNet(nn.Module):
                 self._update_running_stats(stats, B, T)
         outs = (key, tonic) + ((genre,) if self._genre else ())
         return tuple(o.to(out_dtype) for o in outs)
+
+    @torch.no_grad()
+    def forward_rows(self, mel: torch.Tensor, seq_length=None, decode: bool = True):
+        """Eval-mode forward with the three outputs side by side: ``rows`` (B, 35) fp32 = [12 key probabilities | 12 tonic
+        logits | 11 genre logits (zeros without a genre head)] and, with ``decode``, ``ids`` (3, B) int32 (key signature,
+        tonic, genre or -1) -- ONE call (``ake_pcn_forward_rows_f32``); ``rows`` is the table a data-parallel job
+        all-gathers.  Same arithmetic as ``forward`` + ``decode``."""
+        if self.training:
+            raise RuntimeError("forward_rows is the eval-mode path (eval.py:116); call .eval() first")
+        if not isinstance(mel, torch.Tensor) or mel.dim() != 4 or mel.shape[1] != 1 or mel.shape[2] != self.pitches:
+            raise ValueError(f"mel must be (B, 1, {self.pitches}, T), got {tuple(getattr(mel, 'shape', ()))}")
+        if not mel.is_cuda:
+            raise RuntimeError("PitchClassNet (B200) runs on CUDA tensors only; there is no CPU fallback")
+        lib = _lib.lib()
+        device = mel.device
+        B, T = int(mel.shape[0]), int(mel.shape[3])
+        with torch.cuda.device(device):
+            stream = torch.cuda.current_stream(device).cuda_stream
+            self._sync_params(device, stream)
+            x = mel.detach().to(torch.float32).contiguous()
+            seq = None
+            if seq_length is not None:
+                seq = torch.as_tensor(seq_length).reshape(-1)
+                if seq.numel() == 1 and B > 1:
+                    seq = seq.expand(B)
+                if seq.numel() != B:
+                    raise ValueError(f"seq_length has {seq.numel()} entries for a batch of {B}")
+                seq = seq.to(device=device, dtype=torch.int32).contiguous()
+            ws_bytes = lib.ake_pcn_workspace_bytes(self._plan, B, T, 0)
+            if ws_bytes == 0:
+                check(_lib.AKE_ERR_INVALID)
+            ws = _Workspace.get(device, ws_bytes)
+            rows = torch.empty((B, _lib.ROW_FLOATS), dtype=torch.float32, device=device)
+            ids = torch.empty((3, B), dtype=torch.int32, device=device) if decode else None
+            check(lib.ake_pcn_forward_rows_f32(
+                self._plan, x.data_ptr(), B, T, seq.data_ptr() if seq is not None else None, rows.data_ptr(),
+                ids.data_ptr() if ids is not None else None, ws.data_ptr(), ws.numel(), stream))
+        return rows, ids
 
     # ------------------------------------------------------------------------------- gradients
     def _grad_params(self):
@@ -362,15 +415,16 @@ def mirex_counters(key_out: torch.Tensor, tonic_out: torch.Tensor, key_labels: t
     B = key_out.shape[0]
     f = lambda x: x.detach().to(device=dev, dtype=torch.float32).contiguous()  # noqa: E731
     k, t, kl, tl, sid = f(key_out), f(tonic_out), f(key_labels), f(tonic_labels), f(key_signature_id)
-    if kl.shape != (B, 12) or tl.shape != (B, 12) or sid.shape != (B, 21) or t.shape != (B, 12) or k.shape != (B, 12):
-        raise ValueError("expected key/tonic outputs and labels of shape (B, 12) and key_signature_id of shape (B, 21)")
+    if kl.shape != (B, 12) or tl.shape != (B, 12) or t.shape != (B, 12) or k.shape != (B, 12) or sid.dim() != 2 or sid.shape[0] != B:
+        raise ValueError("expected key/tonic outputs and labels of shape (B, 12) and key_signature_id of shape (B, W) "
+                         "(W = 24 from the data layer's one-hot, KeyDataset.py:366, 447)")
     if counters is None:
         counters = torch.zeros(len(MIREX_COUNTERS), dtype=torch.int64, device=dev)
     sim = torch.empty(B, dtype=torch.float32, device=dev) if return_details else None
     cat = torch.empty(B, dtype=torch.int32, device=dev) if return_details else None
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream(dev).cuda_stream
-        check(lib.ake_mirex_f32(k.data_ptr(), t.data_ptr(), kl.data_ptr(), tl.data_ptr(), sid.data_ptr(), B, counters.data_ptr(),
+        check(lib.ake_mirex_f32(k.data_ptr(), t.data_ptr(), kl.data_ptr(), tl.data_ptr(), sid.data_ptr(), int(sid.shape[1]), B, counters.data_ptr(),
                                 sim.data_ptr() if sim is not None else None, cat.data_ptr() if cat is not None else None, stream))
     return (counters, sim, cat) if return_details else counters
 

@@ -34,11 +34,14 @@ class KeyEstimator:
         return self.plan.frames(n_samples)
 
     def estimate_host(self, audio: torch.Tensor, lengths: Optional[Sequence[int]] = None, out: Optional[dict] = None) -> dict:
-        """audio: (B, n_max) fp32 HOST tensor (pin it for full PCIe rate).  Returns host tensors
+        """audio: (B, n_max) fp32 HOST tensor (pin it for full PCIe rate), or int16 = 16-bit PCM as the .wav files hold it
+        (normalised on the device exactly as torchaudio.load does, int16 / 32768, KeyDataset.py:478-481: bit-identical results
+        for half the PCIe bytes).  Returns host tensors
         ``key`` (B,12) sigmoid, ``tonic`` (B,12), ``genre`` (B,11)|None and ``ids`` (3,B) int32
         (key-signature id, tonic id, genre id or -1).  Synchronous (the call ends with a stream sync)."""
-        if audio.is_cuda or audio.dtype != torch.float32 or audio.dim() != 2 or audio.stride(1) != 1:
-            raise ValueError("audio must be a (B, n_max) float32 host tensor with unit sample stride")
+        if audio.is_cuda or audio.dtype not in (torch.float32, torch.int16) or audio.dim() != 2 or audio.stride(1) != 1:
+            raise ValueError("audio must be a (B, n_max) float32 or int16 (16-bit PCM) host tensor with unit sample stride")
+        pcm16 = audio.dtype == torch.int16
         lib = _lib.lib()
         B, n_max = int(audio.shape[0]), int(audio.shape[1])
         if out is None:
@@ -54,11 +57,13 @@ class KeyEstimator:
         with torch.cuda.device(self.device):
             stream = torch.cuda.current_stream(self.device).cuda_stream
             self.net._sync_params(self.device, stream)
-            ws_bytes = lib.ake_estimate_workspace_bytes(self.plan._h, self.net._plan, B, n_max)
+            size_fn = lib.ake_estimate_workspace_bytes_i16 if pcm16 else lib.ake_estimate_workspace_bytes
+            ws_bytes = size_fn(self.plan._h, self.net._plan, B, n_max)
             if ws_bytes == 0:
                 check(_lib.AKE_ERR_INVALID)
             ws = _Workspace.get(self.device, ws_bytes, "estimate")
-            check(lib.ake_estimate_host_f32(
+            run = lib.ake_estimate_host_i16 if pcm16 else lib.ake_estimate_host_f32
+            check(run(
                 self.plan._h, self.net._plan, audio.data_ptr(), int(audio.stride(0)), len_arr, B, n_max,
                 out["key"].data_ptr(), out["tonic"].data_ptr(),
                 out["genre"].data_ptr() if self.genre else None, out["ids"].data_ptr(),
@@ -70,3 +75,10 @@ class KeyEstimator:
         """audio already resident on the GPU: (key, tonic[, genre]) device tensors, asynchronous."""
         mel, seq = self.plan.run(audio, lengths=lengths)
         return self.net(mel, seq)
+
+    @torch.no_grad()
+    def estimate_device_rows(self, audio: torch.Tensor, lengths: Optional[Sequence[int]] = None):
+        """audio already resident on the GPU -> ``rows`` (B, 35) = [key | tonic | genre] and ``ids`` (3, B) int32, asynchronous
+        (CQT, then forward + decode in one C-ABI call writing the result rows a multi-GPU job all-gathers)."""
+        mel, seq = self.plan.run(audio, lengths=lengths)
+        return self.net.forward_rows(mel, seq)

@@ -42,6 +42,12 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="--train: launch the step's kernels one by one instead of as a CUDA graph")
+    ap.add_argument("--sweep", action="store_true",
+                    help="BASELINE configs[3]: large-batch sweep (1k/2k/4k/8k/16k long clips of 240 s, global batch sharded over "
+                         "--gpus ranks, processed in resident sub-batches, result rows all-gathered); one JSON line per point")
+    ap.add_argument("--sweep-batches", default="1024,2048,4096,8192,16384")
+    ap.add_argument("--sweep-seconds", type=float, default=240.0)
+    ap.add_argument("--sweep-sub", type=int, default=64, help="--sweep: clips resident per sub-batch (64 x 46 MB = 2.9 GB)")
     ap.add_argument("--train", action="store_true",
                     help="BASELINE configs[4] instead of the headline metric: training step (fwd + loss + bwd, batch 8 per GPU, "
                          "train-mode BN) with ONE flat gradient all-reduce over NCCL; prints its own JSON line")
@@ -143,6 +149,16 @@ def time_cpu_oracle(n_clips, n_samples, steps, warmup, genre):
     return n_clips * steps / dt, dt / steps, cores
 
 
+# ONE protocol for both CPU legs (the in-arm `cpu_baseline` and `--impl reference`): the same function on the same bounded
+# sample -- CPU_CLIPS clips per step (enough to occupy the thread pool), one warm-up step, then timed steps.
+CPU_CLIPS = 8
+
+
+def cpu_sample_text(n_clips, seconds, cores):
+    return (f"{n_clips} clips/step of the b200 arm's workload ({seconds:g} s @ {SR} Hz): oracle CQT (numpy fp32, thread pool of {cores}) "
+            f"+ float64 forward (torch CPU, {cores} threads) + argmax decode")
+
+
 def run_reference(args):
     """--impl reference: the CPU implementation of the path on the host cores.  The reference is pure Python
     (models.py + librosa) and cannot travel to the GPU box, so this times the oracle port (kind "port")."""
@@ -151,20 +167,25 @@ def run_reference(args):
         return
     n_samples = int(round(args.seconds * SR))
     genre = not args.no_genre
-    # calibrate: size the per-step sample so the whole run stays within ~150 s
+    # bounded sample: CPU_CLIPS clips per step, shrunk only if the whole --steps/--warmup run would pass ~150 s
     t0 = time.perf_counter()
     time_cpu_oracle(1, n_samples, 1, 0, genre)
     t_clip = time.perf_counter() - t0
     cores = os.cpu_count() or 1
     budget = 150.0 / max(1, args.steps + args.warmup)
-    n_clips = int(max(1, min(args.batch, 8, budget / max(t_clip / min(cores, 8), 1e-3))))
+    n_clips = int(max(1, min(args.batch, CPU_CLIPS, budget / max(t_clip / min(cores, 8), 1e-3))))
     value, step_s, cores = time_cpu_oracle(n_clips, n_samples, args.steps, args.warmup, genre)
-    sample = f"{n_clips} clips/step of the b200 arm's workload ({args.seconds:g} s @ {SR} Hz), oracle CQT (numpy fp32, thread pool) + float64 forward (torch CPU)"
+    sample = cpu_sample_text(n_clips, args.seconds, cores)
+    cfg = workload_config(args, genre)
+    # what this arm really ran per step (the b200 arm's per-GPU batch is echoed for the driver's config match only)
+    cfg.update({"reference_clips_per_step": n_clips, "reference_ranks": 1,
+                "reference_note": "CPU arm: rank 0 only, all host cores, a bounded sample of the workload per step; it does not scale with --gpus "
+                                  "(ratios against it are meaningful at N = 1)"})
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, genre),
+        "config": cfg,
         "cpu_baseline": {"value": value, "unit": "clips/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -187,8 +208,7 @@ def run_b200(args):
     import torch.distributed as dist
 
     import audio_key_estimation_b200 as ake
-    from audio_key_estimation_b200 import _lib, distributed as akd, synth
-    from oracle import pcn_port  # MAC counting only (bench bookkeeping), never on the timed path
+    from audio_key_estimation_b200 import _lib, distributed as akd, synth, workload
 
     rank, local, world = akd.init_from_env("nccl")
     if world != args.gpus:
@@ -216,12 +236,20 @@ def run_b200(args):
     synth.synth_batch(lo, B, n_samples, SR, device=dev, out=audio)
     torch.cuda.synchronize()
 
+    pending = [None]  # the previous step's all-gather, still in flight
+
     def device_step():
-        out = est.estimate_device(audio)
-        ids = ake.decode(*out)
-        rows = akd.pack_rows(out[0], out[1], out[2] if genre else None)
-        table = akd.gather_rows(rows, B * world) if world > 1 else rows
+        # CQT, then forward + decode in one call that writes the (clips, 35) result rows; their all-gather is asynchronous
+        # (NCCL's own stream) and overlaps the next step's kernels -- the step before's table is waited for here
+        rows, ids = est.estimate_device_rows(audio)
+        table = pending[0].wait() if pending[0] is not None else None
+        pending[0] = akd.RowGather(rows, B * world)
         return table, ids
+
+    def drain():
+        table = pending[0].wait() if pending[0] is not None else None
+        pending[0] = None
+        return table
 
     def barrier():
         if world > 1:
@@ -238,6 +266,7 @@ def run_b200(args):
     # ---- device-resident throughput ("value")
     for _ in range(max(args.warmup, 3)):
         device_step()
+    drain()
     barrier()
     lib = _lib.lib()
     sampler = ClockSampler(local)
@@ -249,9 +278,12 @@ def run_b200(args):
     barrier()
     ev0.record()
     for _ in range(args.steps):
-        table, ids = device_step()
+        _, ids = device_step()
+    table = drain()  # the last step's gather is inside the timed region
     ev1.record()
     barrier()
+    if table.shape != (B * world, akd.ROW):
+        raise SystemExit("gathered result table has the wrong shape")
     ms_total = max_over_ranks(ev0.elapsed_time(ev1))
     launches = int(lib.ake_launch_count(1))
     prof = _lib.profile_collect()
@@ -259,7 +291,7 @@ def run_b200(args):
     value = B * world * args.steps / (ms_total * 1e-3)
 
     # ---- end to end through the C ABI with host buffers ("e2e")
-    e2e = None
+    e2e, e2e_i16 = None, None
     if not args.no_e2e:
         host_audio = torch.empty((B, n_samples), dtype=torch.float32).pin_memory()
         host_audio.copy_(audio)
@@ -283,9 +315,31 @@ def run_b200(args):
                "h2d_bytes_per_step": int(host_audio.numel() * 4), "d2h_bytes_per_step": int(d2h),
                "ms_per_step": ms_e2e / args.steps, "api": "KeyEstimator.estimate_host -> ake_estimate_host_f32 (pinned host audio)"}
         # parity guard: host-buffer path == device-resident path
-        for j, dev_ids in enumerate(ids):
-            if not torch.equal(out_bufs["ids"][j].to(dev), dev_ids):
+        for j in range(3 if genre else 2):
+            if not torch.equal(out_bufs["ids"][j].to(dev), ids[j]):
                 raise SystemExit("e2e ids differ from the device-resident path")
+        # ---- the same call fed with 16-bit PCM (what the reference's .wav files hold; normalised on the device exactly as
+        # torchaudio.load does, KeyDataset.py:478-481): half the PCIe bytes.  Reported beside, not instead of, the fp32 `e2e`.
+        host_pcm = torch.empty((B, n_samples), dtype=torch.int16).pin_memory()
+        host_pcm.copy_((audio.clamp(-1.0, 1.0) * 32767.0).round().to(torch.int16))
+        out16 = None
+        for _ in range(2):
+            out16 = est.estimate_host(host_pcm, out=out16)
+        barrier()
+        t0 = time.perf_counter()
+        ev0.record()
+        for _ in range(args.steps):
+            out16 = est.estimate_host(host_pcm, out=out16)
+            if world > 1:
+                rows = akd.pack_rows(out16["key"], out16["tonic"], out16["genre"]).to(dev)
+                akd.gather_rows(rows, B * world)
+        ev1.record()
+        torch.cuda.synchronize()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        ms16 = max_over_ranks(max(ev0.elapsed_time(ev1), wall_ms))
+        e2e_i16 = {"value": B * world * args.steps / (ms16 * 1e-3), "unit": "clips/s", "h2d_bytes_per_step": int(host_pcm.numel() * 2),
+                   "d2h_bytes_per_step": int(d2h), "ms_per_step": ms16 / args.steps,
+                   "api": "KeyEstimator.estimate_host -> ake_estimate_host_i16 (pinned 16-bit PCM host audio)"}
 
     clocks = sampler.stop() if rank == 0 else None  # sampled across both timed regions (device-resident and end to end)
     if rank != 0:
@@ -295,10 +349,9 @@ def run_b200(args):
         return
 
     # ---- roofline bookkeeping (algorithmic work per step per GPU)
-    sd_f = {k: v for k, v in sd.items() if v.is_floating_point()}
-    macs_clip = pcn_port.count_macs(sd_f, 36 * OCTAVES, T)
-    p2p_macs_clip = 288 * T * 8 * (5 + 8 + 8) * 49
-    cqt_bytes_clip = 4 * n_samples + 4 * 288 * T
+    macs_clip = workload.pcn_macs({k: tuple(v.shape) for k, v in sd.items()}, 36 * OCTAVES, T)
+    p2p_macs_clip = workload.p2p_macs(36 * OCTAVES, T)
+    cqt_bytes_clip = workload.cqt_algorithmic_bytes(n_samples, 36 * OCTAVES, T)
     steps = args.steps
 
     def sec(tag):
@@ -319,6 +372,13 @@ def run_b200(args):
         with open(tpath) as fh:
             tj = json.load(fh)
         traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
+    # The scheme's own ceiling: operands are fp16 hi/lo pairs (22-bit) and the layer has 8 channels, so a row tap of 122
+    # anchors is ONE tcgen05.mma of N = 112 (7 time-tap phases x 8 channels x {W_hi, W_lo}), K = 16 = [x_hi | x_lo], which
+    # one issuing warp retires every ~68 SM cycles (tools/umma_rate.cu).  7 row taps per block, at the SM clock seen.
+    sm_hz = ((clocks or {}).get("sm_mhz") or 1965.0) * 1e6
+    p2p_blocks = B * 3 * 288 * T / 122.0   # output positions of the 3 convs / anchors per MMA block
+    p2p_floor_ms = p2p_blocks * 7 * 68 / (148 * sm_hz) * 1e3
+    scheme_ceiling = (2.0 * p2p_macs_clip * B / (p2p_floor_ms * 1e-3) / 1e12) / peaks["bf16_tflops_sustained"]
     roofline = {
         "kernel": "pcn.p2p: 3 x Conv2d 7x7 circular (pitch,time) + BN + LeakyReLU (64.6% of the reference forward's MACs); "
                   "4 launches: first conv split into its 36-periodic part + mel part (pcn_p2p1.cuh), then 2 x p2p_umma_kernel",
@@ -328,6 +388,11 @@ def run_b200(args):
         "peak_source": f"{peaks['source']} bf16 dense, sustained (kernel timed inside a long step)",
         "launches_per_step": p2p_n, "ms_per_step": p2p_ms,
         "algorithmic_flops_per_step": 2.0 * p2p_macs_clip * B,
+        "scheme_ceiling": scheme_ceiling,
+        "scheme_ceiling_note": "MMA-issue floor of the fp16 hi/lo shift-GEMM at 8 channels (7 x N=112,K=16 MMAs of ~68 cycles per 122 anchors) "
+                               "expressed as a fraction of the dense bf16 peak: frac / scheme_ceiling = share of the achievable",
+        "frac_of_scheme_ceiling": ((p2p_tflops / peaks["bf16_tflops_sustained"]) / scheme_ceiling) if p2p_tflops else None,
+        "dtype_note": "fp16 hi/lo 3-product (x_hi*w_hi + x_lo*w_hi + x_hi*w_lo), 22-bit operands, fp32 accumulate in TMEM",
     }
     stages = {
         "cqt": {"ms_per_step": cqt_ms, "bound": "hbm", "algorithmic_bytes_per_clip": cqt_bytes_clip,
@@ -343,19 +408,93 @@ def run_b200(args):
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
-        n_cpu = 4
-        cv, cstep, cores = time_cpu_oracle(n_cpu, n_samples, 2, 1, genre)
+        cv, cstep, cores = time_cpu_oracle(CPU_CLIPS, n_samples, 12, 1, genre)  # same protocol as --impl reference; ~10 s
         cpu_baseline = {"value": cv, "unit": "clips/s", "cores": cores, "kind": "port",
-                        "sample": f"{n_cpu} clips x 2 steps of the same workload: oracle CQT (numpy fp32, thread pool) + float64 forward (torch CPU, {cores} threads)"}
+                        "sample": cpu_sample_text(CPU_CLIPS, args.seconds, cores) + "; 1 warm-up + 12 timed steps"}
 
     line = {
         "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": workload_config(args, genre),
-        "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "stages": stages,
+        "clocks": clocks, "e2e": e2e, "e2e_i16": e2e_i16, "gpu_launches": launches, "roofline": roofline, "stages": stages,
         "cpu_baseline": cpu_baseline,
     }
     print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_sweep(args):
+    """BASELINE configs[3]: global batches of 1k..16k LONG clips (240 s = 11,520,000 samples, 1201 frames) sharded over the
+    ranks in contiguous clip ranges.  A rank keeps ONE sub-batch of --sweep-sub synthetic clips resident in HBM (64 x 46 MB)
+    and runs it once per sub-batch of its shard -- 2048 clips x 46 MB never sit in HBM at once -- writing each sub-batch's
+    result rows into its shard's (clips, 35) table, which is all-gathered once per step.  One JSON line per batch size."""
+    import torch
+    import torch.distributed as dist
+
+    import audio_key_estimation_b200 as ake
+    from audio_key_estimation_b200 import _lib, distributed as akd, synth
+
+    rank, local, world = akd.init_from_env("nccl")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    genre = not args.no_genre
+    net = ake.PitchClassNet(36 * OCTAVES, 12, 2, 7, opt=ake.default_opt(genre=genre))
+    net.load_state_dict(golden_weights(genre), strict=True)
+    net = net.to(dev).eval()
+    est = ake.KeyEstimator(net, SR, FRAMES)
+    n_samples = int(round(args.sweep_seconds * SR))
+    T = est.frames(n_samples)
+    sub = args.sweep_sub
+    audio = torch.empty((sub, n_samples), dtype=torch.float32, device=dev)
+    synth.synth_batch(rank * sub, sub, n_samples, SR, device=dev, out=audio)
+    torch.cuda.synchronize()
+    lib = _lib.lib()
+    steps, warmup = max(1, min(args.steps, 3)), 1
+    for total in [int(x) for x in args.sweep_batches.split(",")]:
+        lo, hi = akd.shard_range(total, rank, world)
+        n_local = hi - lo
+        shard = torch.empty((n_local, akd.ROW), dtype=torch.float32, device=dev)
+
+        def step():
+            for b0 in range(0, n_local, sub):
+                nb = min(sub, n_local - b0)
+                rows, _ = est.estimate_device_rows(audio[:nb])
+                shard[b0:b0 + nb].copy_(rows)
+            return akd.RowGather(shard, total).wait()
+
+        for _ in range(warmup):
+            step()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        lib.ake_launch_count(1)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(steps):
+            table = step()
+        ev1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        launches = int(lib.ake_launch_count(1))
+        assert table.shape == (total, akd.ROW) and bool(torch.isfinite(table).all())
+        if rank == 0:
+            print(json.dumps({
+                "metric": METRIC + " (configs[3] sweep)", "value": total * steps / (ms * 1e-3), "unit": "clips/s", "n_gpus": world,
+                "steps": steps, "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "strong",
+                "dtype": "f32", "data": "synthetic", "gpu_launches": launches,
+                "audio_seconds_per_s": total * steps * args.sweep_seconds / (ms * 1e-3),
+                "config": {"workload": f"configs[3]: global batch {total} long clips ({args.sweep_seconds:g} s @ {SR} Hz, {n_samples} samples, {T} frames), "
+                                       f"{n_local} per GPU in resident sub-batches of {sub} (one synthetic sub-batch re-used), rows all-gathered per step",
+                           "global_batch": total, "clips_per_gpu": n_local, "sub_batch": sub, "parallelism": f"dp{world} (batch sharded, logit all-gather)"}}),
+                flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -450,7 +589,9 @@ def run_train(args):
 
 def main():
     args = parse_args()
-    if args.train:
+    if args.sweep:
+        run_sweep(args)
+    elif args.train:
         run_train(args)
     elif args.impl == "reference":
         run_reference(args)

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define AKE_ABI_VERSION 1
+#define AKE_ABI_VERSION 2
 
 #define AKE_OK 0
 #define AKE_ERR_INVALID (-1)      /* bad argument / shape (the reference asserts: models.py:43-44,101,356-357) */
@@ -104,6 +104,15 @@ int ake_pcn_forward_f32(ake_pcn* plan, const float* mel_dev, int B, int T, const
                         float* bn_stats_out_dev, void* ws_dev, size_t ws_bytes, void* stream);
 int ake_pcn_bn_channels(const ake_pcn* plan); /* total channels over all BN sites */
 
+/* The eval-mode forward with its three outputs written side by side as result rows, plus the argmax decode:
+ *   rows_out_dev (B, AKE_ROW_FLOATS = 35) fp32 = [12 key probabilities | 12 tonic logits | 11 genre logits (zeros without a
+ *   genre head)] -- the table a data-parallel job all-gathers (one collective) and the one D2H copy of a
+ *   serving loop;  ids_out_dev (optional) int32 (3, B) = key signature ids, tonic ids, genre ids (-1 without genre head),
+ *   the argmax rule of models.py:1083-1085, 1096, 923.  Same arithmetic as ake_pcn_forward_f32(bn_mode 0) + ake_decode_f32. */
+#define AKE_ROW_FLOATS 35
+int ake_pcn_forward_rows_f32(ake_pcn* plan, const float* mel_dev, int B, int T, const int32_t* seq_len_dev,
+                             float* rows_out_dev, int32_t* ids_out_dev, void* ws_dev, size_t ws_bytes, void* stream);
+
 /* Backward pass of the last bn_mode = 2 forward (what loss.backward() runs through models.py:747-817 in the
  * reference).  d_*_out_dev: gradients of the loss w.r.t. key_out (B,12, AFTER the sigmoid), tonic_out (B,12) and
  * genre_out (B,11); NULL = zero.  grads_out_dev receives ake_pcn_param_floats() floats in the layout of
@@ -148,11 +157,12 @@ int ake_adam_step_f32(const float* flat_grads_dev, float* m_flat_dev, float* v_f
  * difference| == 1 -> "fifth") with its per-sample .cuda() upload of the table.  ACCUMULATES into counters_dev[9] =
  * {samples, correct, fifths, relative, parallel, other, all-12-keys-right ("accuracy"), correct tonics, key bits right}
  * (zero them first; sum them over ranks with one all-reduce); mirex = (1.0 correct + 0.5 fifths + 0.3 relative +
- * 0.2 parallel) / samples.  similarity_out_dev (B, cos(key_out, key_label), models.py:1094) and category_out_dev
+ * 0.2 parallel) / samples.  key_signature_id_dev is (B, sig_width): the data layer delivers a 24-wide one-hot
+ * (KeyDataset.py:366, 447) and the reference takes torch.argmax over whatever width arrives.  similarity_out_dev (B, cos(key_out, key_label), models.py:1094) and category_out_dev
  * (B, 0 correct / 1 fifth / 2 relative / 3 parallel / 4 other) may be NULL. */
 int ake_mirex_f32(const float* key_out_dev, const float* tonic_out_dev, const float* key_labels_dev,
-                  const float* tonic_labels_dev, const float* key_signature_id_dev, int B, uint64_t* counters_dev,
-                  float* similarity_out_dev, int32_t* category_out_dev, void* stream);
+                  const float* tonic_labels_dev, const float* key_signature_id_dev, int sig_width, int B,
+                  uint64_t* counters_dev, float* similarity_out_dev, int32_t* category_out_dev, void* stream);
 
 /* ---------------------------------------------------------------- constant-Q front-end */
 
@@ -194,6 +204,15 @@ int ake_estimate_host_f32(ake_cqt* cqt, ake_pcn* pcn, const float* audio_host, i
                           const int64_t* lengths_host, int B, int64_t n_max, float* key_out_host,
                           float* tonic_out_host, float* genre_out_host, int32_t* ids_host, void* ws_dev,
                           size_t ws_bytes, void* stream);
+
+/* The same call for 16-bit PCM host audio (what the reference's .wav files hold): torchaudio.load normalises int16 samples
+ * as int16 / 32768 (KeyDataset.py:478-481), which is exact in fp32, so the device-side conversion makes this entry point
+ * bit-identical to ake_estimate_host_f32 on the normalised samples while moving half the bytes across PCIe (2.88 MB per
+ * standard clip instead of 5.76 MB).  stride / n_max / lengths count samples. */
+size_t ake_estimate_workspace_bytes_i16(const ake_cqt* cqt, const ake_pcn* pcn, int B, int64_t n_max);
+int ake_estimate_host_i16(ake_cqt* cqt, ake_pcn* pcn, const int16_t* pcm_host, int64_t stride, const int64_t* lengths_host,
+                          int B, int64_t n_max, float* key_out_host, float* tonic_out_host, float* genre_out_host,
+                          int32_t* ids_host, void* ws_dev, size_t ws_bytes, void* stream);
 
 #ifdef __cplusplus
 }

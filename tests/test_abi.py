@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     assert set(declared) == set(_lib._SIGNATURES)
-    assert lib.ake_abi_version() == 1
+    assert lib.ake_abi_version() == 2
 
 
 @pytest.mark.parametrize("genre", [False, True])

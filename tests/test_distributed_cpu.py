@@ -33,6 +33,10 @@ def _worker(rank, world, port, n_clips, genre, q):
     tonic = -ids[:, None] + torch.arange(12)[None] / 100
     gen = ids[:, None] * 2 + torch.arange(11)[None] / 100 if genre else None
     table = akd.gather_rows(akd.pack_rows(key, tonic, gen), n_clips)
+    # asynchronous form (bench.py overlaps step i's gather with step i+1's kernels): two gathers in flight, waited in order
+    rows = akd.pack_rows(key, tonic, gen)
+    g1, g2 = akd.RowGather(rows, n_clips), akd.RowGather(rows * 2, n_clips)
+    assert torch.equal(g1.wait(), table) and torch.equal(g2.wait(), table * 2)
     counters = akd.reduce_counters(torch.tensor([hi - lo, 1], dtype=torch.int64))
     out = akd.unpack_rows(table, genre)
     q.put((rank, table.clone(), counters.clone(), len(out)))

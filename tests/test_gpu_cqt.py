@@ -76,6 +76,21 @@ def test_full_size_properties():
     assert np.abs(mel[1, 0].cpu().numpy() - want).max() <= 5e-4
 
 
+def test_long_clip_240s_matches_oracle():
+    """BASELINE configs[3] clip shape: 240 s @ 48 kHz = 11,520,000 samples -> 1201 frames (many cascade tiles per clip,
+    every octave's frames far from the clip edges), next to a shorter clip in the same batch."""
+    n = SR * 240
+    a = synth.synth_clip(77, n, SR)
+    b = synth.synth_clip(78, SR * 100 + 4321, SR)
+    mel, seq = ake.cqt_logmag([a.cuda(), b.cuda()], SR)
+    assert tuple(mel.shape) == (2, 1, 288, 1201) and seq.tolist() == [1201, cp.n_frames(SR * 100 + 4321, HOP, 8)]
+    for i, y in enumerate((a, b)):
+        want = cp.cqt_logmag(y.numpy(), SR)[0]
+        got = mel[i, 0, :, : want.shape[-1]].cpu().numpy()
+        assert np.abs(got - want).max() <= 5e-4
+        assert not mel[i, 0, :, want.shape[-1]:].any()
+
+
 def test_other_bank_shapes_and_errors():
     y = synth.synth_clip(9, 22050 * 3, 22050).cuda()
     got = ake.cqt(y, sr=22050, hop_length=512, n_bins=84, bins_per_octave=12)   # librosa's own defaults
@@ -97,11 +112,25 @@ def test_cache_writer_files_load_like_the_reference_expects(tmp_path):
     lens = [sr * 3, sr * 2 + 1234]
     waves = [synth.synth_clip(40 + i, n, sr, "cpu") for i, n in enumerate(lens)]
     paths = [str(tmp_path / "a.wav"), str(tmp_path / "sub.dir.mp3")]
-    written = ake.write_cqt_cache(paths, waves, sr, opt)
+    with pytest.raises(RuntimeError):
+        ake.write_cqt_cache(paths, waves, sr, opt)   # CQT parity vs librosa itself is unpinned: the caller must say so
+    written = ake.write_cqt_cache(paths, waves, sr, opt, accept_unpinned_cqt=True)
     assert written == [cache.cache_name(p, opt) for p in paths]
     mel, seq = ake.cqt_logmag([w.cuda() for w in waves], sr=sr, frames=5, octaves=8)
     for i, name in enumerate(written):
         t = torch.load(name)
         assert t.dtype == torch.float64 and t.shape == (1, 288, int(seq[i])) and t.shape[1] == cache.expected_bins(opt)
         assert torch.equal(t, mel[i][:, :, : int(seq[i])].double().cpu())
-    assert ake.write_cqt_cache(paths, waves, sr, opt) == []          # existing files are kept, as the reference does
+    assert ake.write_cqt_cache(paths, waves, sr, opt, accept_unpinned_cqt=True) == []   # existing files are kept, as the reference does
+    # opt.frames == 0 (KeyDataset.py:485-503): per-clip hop = w_length // window_size + 1, cropped to window_size frames
+    opt0 = argparse.Namespace(octaves=8, frames=0, only_semitones=False, window_size=100)
+    n0 = 127950                                          # hop = n0 // 100 + 1 = 1280 = 10 * 2^7: accepted by librosa 0.9.2
+    w0 = synth.synth_clip(60, n0, sr, "cpu")
+    p0 = str(tmp_path / "frames0.wav")
+    name0 = ake.write_cqt_cache([p0], [w0], sr, opt0, overwrite=True, accept_unpinned_cqt=True)[0]
+    t0 = torch.load(name0)
+    want0 = np.log(1 + np.abs(cp.cqt(w0.numpy(), sr, 1280, None, 288, 36)))
+    assert t0.shape == (1, 288, 100) and want0.shape[-1] == 100
+    assert np.abs(t0[0].numpy() - want0[:, :100]).max() <= 5e-4
+    with pytest.raises(ValueError):                      # hop 1281: librosa 0.9.2 raises ParameterError
+        ake.write_cqt_cache([str(tmp_path / "bad.wav")], [synth.synth_clip(61, n0 + 100, sr, "cpu")], sr, opt0, accept_unpinned_cqt=True)

@@ -27,6 +27,19 @@ def test_counters_categories_and_ratios_match_reference():
     np.testing.assert_allclose(got, g["ratios"], rtol=0, atol=1e-7)                        # the reference's 7 returned ratios
 
 
+def test_24_wide_signature_ids_match_reference():
+    """key_signature_id as the data layer delivers it: tf.one_hot(id, 24) (KeyDataset.py:366, 447), label ids up to 23."""
+    import audio_key_estimation_b200 as ake
+
+    g = np.load(GOLDEN)
+    dev = [torch.from_numpy(g["w24_" + k]).cuda() for k in ("key_out", "tonic_out", "key_labels", "tonic_labels", "key_signature_id")]
+    assert dev[4].shape == (96, 24)
+    counters, _, cat = ake.mirex_counters(*dev, return_details=True)
+    assert cat.cpu().numpy().tolist() == g["w24_categories"].tolist()
+    got = np.array([float(x) for x in ake.mirex_from_counters(counters)])
+    np.testing.assert_allclose(got, g["w24_ratios"], rtol=0, atol=1e-7)
+
+
 def test_accumulation_over_batches_equals_one_batch():
     import audio_key_estimation_b200 as ake
 

@@ -128,6 +128,13 @@ def test_seq_length_edge_cases():
     # a clip whose masked length is 0 averages an empty slice -> nan, exactly as torch.mean does in the reference
     k, t = net(x, torch.tensor([40, 24]).cuda())
     assert torch.isfinite(k[0]).all() and torch.isnan(t[1]).all()
+    # a NEGATIVE masked length (seq 20 -> floor(20/2) - 12 = -2) is a Python slice [:-2] in the reference
+    # (models.py:770): it keeps Th - 2 frames; the oracle port slices the same way
+    seq = torch.tensor([40, 20])
+    k, t = net(x, seq.cuda())
+    sd64 = {n: v.double() for n, v in golden_state_dict(False).items() if v.is_floating_point()}
+    wk, wt = pcn_port.pcn_forward(sd64, x.double().cpu(), seq)
+    _close(k, wk.numpy()), _close(t, wt.numpy())
 
 
 @pytest.mark.parametrize("inp", ["pattern", "padded_cqt"])

@@ -53,6 +53,105 @@ def test_config1_eight_standard_clips():
         assert torch.equal(d.cpu(), out[name])
 
 
+def _oracle_chain(clips, genre=True):
+    """cqt_port -> pcn_port on the host cores (numpy CQT per clip in a thread pool, then one float64 forward)."""
+    import concurrent.futures as cf
+    import os
+    sd = {k: v.double() for k, v in float_state_dict(golden_state_dict(genre)).items()}
+    with cf.ThreadPoolExecutor(max_workers=os.cpu_count() or 4) as pool:
+        mels = list(pool.map(lambda c: cp.cqt_logmag(c, SR), clips))
+    T = max(m.shape[-1] for m in mels)
+    x = torch.from_numpy(np.stack([np.pad(m, ((0, 0), (0, 0), (0, T - m.shape[-1]))) for m in mels]))
+    with torch.no_grad():
+        return pcn_port.pcn_forward(sd, x, torch.tensor([m.shape[-1] for m in mels]))
+
+
+def test_config2_batch_256_against_oracle():
+    """BASELINE configs[1] as written: batch 256 synthetic standard clips, fused CQT + forward on one GPU vs the reference-side
+    logits (oracle chain on all 256 clips).  Tolerance (north_star): max-abs <= 1e-3 relative to max |logit|; argmax key /
+    tonic / genre identical on every clip whose oracle top-2 margin exceeds 10x the error actually achieved."""
+    est = _estimator(True)
+    B, n = 256, SR * 30
+    audio = synth.synth_batch(0, B, n, SR).pin_memory()
+    out = est.estimate_host(audio)
+    want = _oracle_chain([audio[i].numpy() for i in range(B)])
+    worst = 0.0
+    for name, w in zip(("key", "tonic", "genre"), want):
+        assert out[name].shape == w.shape
+        worst = max(worst, (out[name].double() - w).abs().max().item() / max(1.0, w.abs().max().item()))
+    assert worst <= 1e-3, worst
+    ids = pcn_port.decode(*want)
+    gated = 0
+    for j, w in enumerate(want):
+        scores = w if j else torch.nn.functional.cosine_similarity(w[:, None], pcn_port.key_signature_map(torch.float64)[None], dim=2)
+        top2 = scores.topk(2, dim=1).values
+        safe = (top2[:, 0] - top2[:, 1]) > 10 * max(worst, 1e-6)
+        gated += int((~safe).sum())
+        assert torch.equal(out["ids"][j].long()[safe], ids[j][safe])
+    assert gated <= B // 4, f"{gated} of {3 * B} argmax comparisons gated out by the margin rule"
+    # the device-resident rows path (what bench.py times) gives the same numbers and ids as the host-buffer path
+    rows, dids = est.estimate_device_rows(audio.cuda())
+    assert torch.equal(rows[:, :12].cpu(), out["key"]) and torch.equal(rows[:, 12:24].cpu(), out["tonic"])
+    assert torch.equal(rows[:, 24:].cpu(), out["genre"]) and torch.equal(dids.cpu(), out["ids"])
+
+
+def test_pcm16_entry_point_is_bit_identical_to_fp32_on_normalised_samples():
+    """ake_estimate_host_i16: 16-bit PCM host audio, normalised on the device as torchaudio.load does (int16 / 32768,
+    KeyDataset.py:478-481) == ake_estimate_host_f32 on the normalised samples, bit for bit; ragged lengths included."""
+    est = _estimator(True)
+    B, n = 9, SR * 12 + 5
+    lens = [n, n - 1, SR * 5, n, 9600 * 3 + 1, n, n - 4097, n, SR * 7]
+    f = synth.synth_batch(50, B, n, SR)
+    pcm = (f.clamp(-1, 1) * 32767).round().to(torch.int16)
+    pcm[0, :4] = torch.tensor([-32768, 32767, -1, 1], dtype=torch.int16)
+    normalised = (pcm.to(torch.float32) / 32768.0).pin_memory()
+    a = est.estimate_host(pcm.pin_memory(), lens)
+    b = est.estimate_host(normalised, lens)
+    for k in ("key", "tonic", "genre", "ids"):
+        assert torch.equal(a[k], b[k]), k
+    assert torch.isfinite(a["tonic"]).all()
+    with pytest.raises(ValueError):
+        est.estimate_host(pcm.to(torch.int32))   # only fp32 and 16-bit PCM are accepted
+
+
+def test_rows_path_matches_forward_plus_decode_without_genre_head():
+    est = _estimator(False)
+    audio = synth.synth_batch(7, 3, SR * 6, SR).cuda()
+    rows, ids = est.estimate_device_rows(audio, [SR * 6, SR * 5, SR * 6 - 3])
+    key, tonic = est.estimate_device(audio, [SR * 6, SR * 5, SR * 6 - 3])
+    kid, tid = ake.decode(key, tonic)
+    assert torch.equal(rows[:, :12], key) and torch.equal(rows[:, 12:24], tonic) and not rows[:, 24:].any()
+    assert torch.equal(ids[0], kid) and torch.equal(ids[1], tid) and (ids[2] == -1).all()
+
+
+def test_two_host_threads_two_streams():
+    """include/ake_b200.h: different plans may be driven from different host threads / streams -- scratch is per stream."""
+    import threading
+    results, errors = {}, []
+
+    def work(tag, seed):
+        try:
+            torch.cuda.set_device(0)
+            with torch.cuda.stream(torch.cuda.Stream()):
+                est = _estimator(True)
+                audio = synth.synth_batch(seed, 4, SR * 8, SR).cuda()
+                outs = [est.estimate_device_rows(audio)[0].clone() for _ in range(6)]
+                torch.cuda.current_stream().synchronize()
+                results[tag] = outs
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+
+    th = [threading.Thread(target=work, args=(i, 100 + 10 * i)) for i in range(2)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errors, errors
+    for outs in results.values():
+        for o in outs[1:]:
+            assert torch.equal(o, outs[0])   # a shared scratch buffer would show up as run-to-run differences
+
+
 def test_estimator_requires_eval_and_cuda():
     net = ake.PitchClassNet(288, 12, 2, 7, opt=ake.default_opt())
     with pytest.raises(RuntimeError):

@@ -129,3 +129,15 @@ def test_numa_bind_is_best_effort():
     assert node is None or isinstance(node, int)
     if node is None:
         assert os.sched_getaffinity(0) == before
+
+
+def test_workload_mac_counts_match_the_survey_figures():
+    """SURVEY.md 8d: 551,306,304 MAC per clip at T = 150 (554,584,320 with the genre head), probe-counted on the reference;
+    bench.py's roofline bookkeeping (audio_key_estimation_b200.workload) derives them from the conv shapes alone."""
+    from audio_key_estimation_b200 import workload
+    from conftest import golden_state_dict
+    for genre, want in ((False, 551306304), (True, 554584320)):
+        shapes = {k: tuple(v.shape) for k, v in golden_state_dict(genre).items()}
+        assert workload.pcn_macs(shapes, 288, 150) == want
+    assert workload.p2p_macs(288, 150) == 288 * 150 * 8 * 21 * 49
+    assert workload.cqt_algorithmic_bytes(1440000, 288, 151) == 5933952

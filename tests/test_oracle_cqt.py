@@ -99,3 +99,20 @@ def test_regression_fixture():
     mel = cp.cqt_logmag(y, SR)
     assert mel.shape == (1, 288, 16) and mel.dtype == np.float64
     np.testing.assert_allclose(mel[0], g["logmag"], atol=2e-5)
+
+
+def test_port_matches_librosa_when_importable():
+    """Pins the restatement the moment librosa is importable (it is not in the build container: requirements.txt:250 pins
+    librosa 0.9.2 + resampy 0.3.1, neither vendored).  Same call as KeyDataset.py:490-491."""
+    librosa = pytest.importorskip("librosa")
+    from audio_key_estimation_b200 import synth
+    y = synth.synth_clip(5, SR * 6 + 77, SR).numpy()
+    kwargs = dict(sr=SR, hop_length=HOP, bins_per_octave=36, n_bins=288)
+    major, minor = (int(x) for x in librosa.__version__.split(".")[:2])
+    if (major, minor) >= (0, 10):
+        kwargs["res_type"] = "kaiser_fast"   # the 0.9.2 default this port restates (0.10 switched to soxr_hq)
+    want = librosa.cqt(y, **kwargs)
+    got = cp.cqt(y, SR, HOP, None, 288, 36, dtype=np.float32)
+    assert got.shape == want.shape
+    assert np.abs(got - want).max() <= 2e-5 * np.abs(want).max()
+    np.testing.assert_allclose(cp.cqt_logmag(y, SR)[0], np.log(1 + np.abs(want)), atol=2e-5)

@@ -10,9 +10,9 @@ from oracle import pcn_port, ref_import
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "mirex.npz")
 
 
-def _load():
+def _load(prefix=""):
     g = np.load(GOLDEN)
-    return g, [torch.from_numpy(g[k]) for k in ("key_out", "tonic_out", "key_labels", "tonic_labels", "key_signature_id")]
+    return g, [torch.from_numpy(g[prefix + k]) for k in ("key_out", "tonic_out", "key_labels", "tonic_labels", "key_signature_id")]
 
 
 def test_port_matches_reference_golden():
@@ -24,6 +24,16 @@ def test_port_matches_reference_golden():
     assert [cnt[k] for k in ("correct", "fifths", "relative", "parallel", "other")] == hist.tolist()
     assert min(hist) > 0, "the golden batch must reach every category"
     assert cnt["samples"] == len(g["categories"]) and sim.shape == (len(g["categories"]),)
+
+
+def test_port_matches_reference_golden_24_wide_ids():
+    """The data layer's one-hot is 24 wide (KeyDataset.py:366, 447): label ids 21..23 lie beyond the 21-row table."""
+    g, t = _load("w24_")
+    assert t[4].shape[1] == 24 and int(t[4].argmax(1).max()) >= 21
+    cnt, _ = pcn_port.mirex_counters(*t)
+    np.testing.assert_allclose(np.array(pcn_port.mirex_from_counters(cnt)), g["w24_ratios"], rtol=0, atol=1e-7)
+    hist = np.bincount(g["w24_categories"], minlength=5)
+    assert [cnt[k] for k in ("correct", "fifths", "relative", "parallel", "other")] == hist.tolist()
 
 
 def test_port_matches_live_reference_when_available():
