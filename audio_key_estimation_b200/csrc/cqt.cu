@@ -9,6 +9,7 @@
 // where K is the dense time-domain image of librosa's sparsified FFT basis (identical for every
 // octave because f_k / sr_i does not depend on i).
 #include <cmath>
+#include <cstdlib>
 #include <algorithm>
 #include <complex>
 #include <vector>
@@ -292,6 +293,7 @@ struct CascadeArgs {
   int level_in, n_levels, tiles_per_clip, n_tiles;
   const __half* img;
   int sparse_hop, sparse_nfft;  // > 0: level p+1 is only read by the filter bank (hop, n_fft at that level): store just those rows
+  int stream_in;                // the input is read exactly once (caller's audio): load it with the L2 evict_first policy
 };
 
 // (a, b) -> fp16 pairs hi, lo with a ~= hi + lo
@@ -419,6 +421,7 @@ __global__ void __launch_bounds__(kCasThreads, 1) cascade_umma_kernel(const Casc
       mbar_arrive_expect_tx(&img_bar, kCasImgBytes);
       bulk_g2s(img, a.img, kCasImgBytes, &img_bar);
     }
+    const uint64_t pol = l2_policy_evict_first();
     int i = 0;
     for (int tile = next_tile(blockIdx.x); tile < a.n_tiles; tile = next_tile(tile + gridDim.x), ++i) {
       const int s = i & 1;
@@ -433,7 +436,8 @@ __global__ void __launch_bounds__(kCasThreads, 1) cascade_umma_kernel(const Casc
           for (int q = sp.vlo + n4; q < sp.vhi; ++q) st[q] = __ldg(sp.src + q);
           if (n4 > 0) {
             mbar_arrive_expect_tx(&stage_full[s], (uint32_t)n4 * 4);
-            bulk_g2s(st + sp.vlo, sp.src + sp.vlo, (uint32_t)n4 * 4, &stage_full[s]);
+            if (a.stream_in) bulk_g2s_hint(st + sp.vlo, sp.src + sp.vlo, (uint32_t)n4 * 4, &stage_full[s], pol);
+            else bulk_g2s(st + sp.vlo, sp.src + sp.vlo, (uint32_t)n4 * 4, &stage_full[s]);
           } else {
             mbar_arrive(&stage_full[s]);
           }
@@ -938,12 +942,13 @@ struct CqtWs {
   long long stride[16];
 };
 
-static CqtWs carve(const ake_cqt* p, Arena& ar, int B, long long n_max) {
+// d_len: one length per clip of the batch; level buffers: one group of G clips (reused by every group)
+static CqtWs carve(const ake_cqt* p, Arena& ar, int B, int G, long long n_max) {
   CqtWs w{};
   w.d_len = ar.take<long long>(B);
   for (int i = 1; i < p->n_oct; ++i) {
     w.stride[i] = (long long)align_up((size_t)len_at(n_max, i), 32);  // the cascade kernel stores whole rows of 32 samples
-    w.level[i] = ar.take<float>((size_t)B * w.stride[i]);
+    w.level[i] = ar.take<float>((size_t)G * w.stride[i]);
   }
   return w;
 }
@@ -965,6 +970,19 @@ static void stage_lengths(ake_cqt* p, const int64_t* lengths_host, int B, long l
   AKE_CUDA(cudaEventRecord(p->h_len_done[s], st));
 }
 
+// Clips per group of the front-end.  The level buffers can be reused group by group so that the decimated levels stay resident
+// in L2 (DRAM then sees the audio once and the output once), but on B200 that is SLOWER than one pass over the whole batch
+// (measured, 256 standard clips: 0.90 ms in one group, 1.15 ms in 4 groups of 64, 1.76 ms in 16 groups of 16 -- the persistent
+// kernels' ramp-up and tail are paid per launch, and neither kernel is DRAM-bound), so the default is one group; AKE_CQT_GROUP=n
+// keeps the mechanism available for experiments and for workspaces that must stay small.
+static int cqt_group_clips(int B) {
+  if (const char* e = getenv("AKE_CQT_GROUP")) {
+    const int g = atoi(e);
+    return g <= 0 ? B : std::min(B, g);
+  }
+  return B;
+}
+
 // lengths_host: validated and staged here; lengths_dev: already on the device (the host-buffer pipeline uploads every clip's
 // length once per batch); at most one of the two.
 void run_cqt(ake_cqt* p, const float* audio, long long stride, const int64_t* lengths_host, const long long* lengths_dev, int B,
@@ -972,8 +990,9 @@ void run_cqt(ake_cqt* p, const float* audio, long long stride, const int64_t* le
   if (p->n_oct > 15) fail(AKE_ERR_UNSUPPORTED, "too many octaves");
   if (n_max >= (1LL << 31) - 65536) fail(AKE_ERR_UNSUPPORTED, "clips of 2^31 samples or more are not supported (32-bit sample indices in the cascade)");
   ensure_device(p);
+  const int G = cqt_group_clips(B);
   Arena ar(ws, ws_bytes);
-  CqtWs w = carve(p, ar, B, n_max);
+  CqtWs w = carve(p, ar, B, G, n_max);
   const long long* d_len = lengths_dev;
   if (lengths_host) {
     for (int b = 0; b < B; ++b)
@@ -981,58 +1000,65 @@ void run_cqt(ake_cqt* p, const float* audio, long long stride, const int64_t* le
     stage_lengths(p, lengths_host, B, w.d_len, st);
     d_len = w.d_len;
   }
-  w.level[0] = const_cast<float*>(audio);
-  w.stride[0] = stride;
-  if (p->n_oct > 1) {
-    // resampling cascade: two octave steps per pass (level p -> p+1, p+2), one persistent warp-specialised CTA per SM
-    ProfScope prof("cqt.decimate", st);
-    ensure_dyn_smem(cascade_umma_kernel, kCasSmemTotal);
-    const int n_sm = sm_count();
-    for (int lv = 0; lv < p->n_oct - 1; lv += 2) {
-      CascadeArgs ca{};
-      ca.in = w.level[lv], ca.in_stride = w.stride[lv];
-      ca.out1 = w.level[lv + 1], ca.stride1 = w.stride[lv + 1];
-      ca.n_levels = std::min(2, p->n_oct - 1 - lv);
-      if (ca.n_levels == 2) ca.out2 = w.level[lv + 2], ca.stride2 = w.stride[lv + 2];
-      ca.lengths = d_len, ca.n_uniform = n_max, ca.level_in = lv;
-      ca.tiles_per_clip = (int)cdiv64(len_at(n_max, lv + 1), kCasOwn1);
-      ca.n_tiles = ca.tiles_per_clip * B;
-      // the kernel decodes tile -> clip by multiply-high, exact while n_tiles * tiles_per_clip < 2^32 (very many very long clips
-      // exceed it): refuse instead of decoding wrongly
-      if ((long long)ca.tiles_per_clip * B * ca.tiles_per_clip >= (1LL << 32))
-        fail(AKE_ERR_UNSUPPORTED, "%d clips x %d tiles exceed the cascade's index decode range; split the batch", B, ca.tiles_per_clip);
-      ca.img = p->d_dec_img;
-      // level lv+1 is consumed by the filter bank only (the next pass reads level lv+2): when its frames do not overlap,
-      // the samples between them are never written
-      const int hop1 = p->hop >> (lv + 1);
-      ca.sparse_hop = (ca.n_levels == 2 && hop1 >= p->n_fft + 64) ? hop1 : 0, ca.sparse_nfft = p->n_fft;
-      const int grid = std::min(ca.n_tiles, n_sm);  // persistent: one CTA per SM
-      cascade_umma_kernel<<<grid, kCasThreads, kCasSmemTotal, st>>>(ca);
-      AKE_LAUNCHED();
-    }
-  }
-  const long long rows = (long long)B * T_max;
-  if (p->npad) {
-    // tensor cores: every octave in one launch (grid.y = octave)
-    ProfScope prof("cqt.bank", st);
-    BankArgs ba{};
-    for (int i = 0; i < p->n_oct; ++i) ba.level[i] = w.level[i], ba.stride[i] = w.stride[i];
-    ba.lengths = d_len, ba.n_uniform = n_max, ba.n_oct = p->n_oct, ba.hop0 = p->hop, ba.n_fft = p->n_fft, ba.B = B, ba.T_max = T_max;
-    ba.n_bins = p->n_bins, ba.bpo = p->bpo, ba.mode = mode, ba.bank_img = p->d_bank_img, ba.scale = p->d_scale_umma, ba.out = out;
-    dim3 grid((unsigned)cdiv64(rows, 128 * kBankMB), p->n_oct);
-    if (p->npad == 80) {
-      constexpr size_t smem = kUStages * bank_stage_bytes(80, kBankMB);
-      ensure_dyn_smem(cqt_bank_umma_kernel<80, kBankMB>, smem);
-      cqt_bank_umma_kernel<80, kBankMB><<<grid, kBankThreads, smem, st>>>(ba);
-    } else {
-      constexpr size_t smem = kUStages * bank_stage_bytes(32, kBankMB);
-      ensure_dyn_smem(cqt_bank_umma_kernel<32, kBankMB>, smem);
-      cqt_bank_umma_kernel<32, kBankMB><<<grid, kBankThreads, smem, st>>>(ba);
-    }
-    AKE_LAUNCHED();
-  } else {
+  if (!p->npad)
     fail(AKE_ERR_UNSUPPORTED, "bins_per_octave %d / n_fft %d: the filter-bank kernel is built for 36 and 12 bins per octave, n_fft %% 64 == 0",
          p->bpo, p->n_fft);
+  w.stride[0] = stride;
+  const int n_sm = sm_count();
+  const bool grouped = G < B;
+  for (int g0 = 0; g0 < B; g0 += G) {
+    const int nb = std::min(G, B - g0);
+    const long long* g_len = d_len ? d_len + g0 : nullptr;
+    w.level[0] = const_cast<float*>(audio) + (size_t)g0 * stride;
+    if (p->n_oct > 1) {
+      // resampling cascade: two octave steps per pass (level p -> p+1, p+2), one persistent warp-specialised CTA per SM
+      ProfScope prof("cqt.decimate", st);
+      ensure_dyn_smem(cascade_umma_kernel, kCasSmemTotal);
+      for (int lv = 0; lv < p->n_oct - 1; lv += 2) {
+        CascadeArgs ca{};
+        ca.in = w.level[lv], ca.in_stride = w.stride[lv];
+        ca.out1 = w.level[lv + 1], ca.stride1 = w.stride[lv + 1];
+        ca.n_levels = std::min(2, p->n_oct - 1 - lv);
+        if (ca.n_levels == 2) ca.out2 = w.level[lv + 2], ca.stride2 = w.stride[lv + 2];
+        ca.lengths = g_len, ca.n_uniform = n_max, ca.level_in = lv;
+        ca.tiles_per_clip = (int)cdiv64(len_at(n_max, lv + 1), kCasOwn1);
+        ca.n_tiles = ca.tiles_per_clip * nb;
+        // the kernel decodes tile -> clip by multiply-high, exact while n_tiles * tiles_per_clip < 2^32 (very many very long clips
+        // exceed it): refuse instead of decoding wrongly
+        if ((long long)ca.tiles_per_clip * nb * ca.tiles_per_clip >= (1LL << 32))
+          fail(AKE_ERR_UNSUPPORTED, "%d clips x %d tiles exceed the cascade's index decode range; split the batch", nb, ca.tiles_per_clip);
+        ca.img = p->d_dec_img;
+        // level lv+1 is consumed by the filter bank only (the next pass reads level lv+2): when its frames do not overlap,
+        // the samples between them are never written
+        const int hop1 = p->hop >> (lv + 1);
+        ca.sparse_hop = (ca.n_levels == 2 && hop1 >= p->n_fft + 64) ? hop1 : 0, ca.sparse_nfft = p->n_fft;
+        ca.stream_in = (grouped && lv == 0) ? 1 : 0;  // the audio is read once: do not let it displace the resident levels
+        const int grid = std::min(ca.n_tiles, n_sm);  // persistent: one CTA per SM
+        cascade_umma_kernel<<<grid, kCasThreads, kCasSmemTotal, st>>>(ca);
+        AKE_LAUNCHED();
+      }
+    }
+    {
+      // tensor cores: every octave in one launch (grid.y = octave)
+      ProfScope prof("cqt.bank", st);
+      const long long rows = (long long)nb * T_max;
+      BankArgs ba{};
+      for (int i = 0; i < p->n_oct; ++i) ba.level[i] = w.level[i], ba.stride[i] = w.stride[i];
+      ba.lengths = g_len, ba.n_uniform = n_max, ba.n_oct = p->n_oct, ba.hop0 = p->hop, ba.n_fft = p->n_fft, ba.B = nb, ba.T_max = T_max;
+      ba.n_bins = p->n_bins, ba.bpo = p->bpo, ba.mode = mode, ba.bank_img = p->d_bank_img, ba.scale = p->d_scale_umma;
+      ba.out = out + (size_t)g0 * p->n_bins * T_max * (mode == AKE_CQT_COMPLEX ? 2 : 1);
+      dim3 grid((unsigned)cdiv64(rows, 128 * kBankMB), p->n_oct);
+      if (p->npad == 80) {
+        constexpr size_t smem = kUStages * bank_stage_bytes(80, kBankMB);
+        ensure_dyn_smem(cqt_bank_umma_kernel<80, kBankMB>, smem);
+        cqt_bank_umma_kernel<80, kBankMB><<<grid, kBankThreads, smem, st>>>(ba);
+      } else {
+        constexpr size_t smem = kUStages * bank_stage_bytes(32, kBankMB);
+        ensure_dyn_smem(cqt_bank_umma_kernel<32, kBankMB>, smem);
+        cqt_bank_umma_kernel<32, kBankMB><<<grid, kBankThreads, smem, st>>>(ba);
+      }
+      AKE_LAUNCHED();
+    }
   }
   if (seq_len_out) {
     cqt_seqlen_kernel<<<cdiv(B, 128), 128, 0, st>>>(d_len, n_max, B, p->n_oct, p->hop, T_max, seq_len_out);
@@ -1091,8 +1117,10 @@ int ake_cqt_get_decimator(const ake_cqt* p, float* taps_host, int cap) {
 
 size_t ake_cqt_workspace_bytes(const ake_cqt* p, int B, int64_t n_max) {
   if (!p || B <= 0 || n_max <= 0) return 0;
+  // sized for the whole batch in one group, so that the grouping policy (L2 size of the device that runs the plan, experiments)
+  // never has to be known when the caller allocates
   Arena ar(nullptr, 0);
-  carve(p, ar, B, n_max);
+  carve(p, ar, B, B, n_max);
   return ar.off + 256;
 }
 

@@ -82,13 +82,22 @@ def test_config2_batch_256_against_oracle():
     assert worst <= 1e-3, worst
     ids = pcn_port.decode(*want)
     gated = 0
+    # The 21-row signature table holds enharmonic duplicates (e.g. rows 0 and 12 are the same pitch-class set), whose cosines
+    # tie exactly: the margin that matters is between DISTINCT pitch-class sets, and ids are compared through their set.
+    table = pcn_port.key_signature_map(torch.float64)
+    uniq, inverse = torch.unique(table, dim=0, return_inverse=True)
     for j, w in enumerate(want):
-        scores = w if j else torch.nn.functional.cosine_similarity(w[:, None], pcn_port.key_signature_map(torch.float64)[None], dim=2)
+        scores = w if j else torch.nn.functional.cosine_similarity(w[:, None], uniq[None], dim=2)
         top2 = scores.topk(2, dim=1).values
         safe = (top2[:, 0] - top2[:, 1]) > 10 * max(worst, 1e-6)
         gated += int((~safe).sum())
-        assert torch.equal(out["ids"][j].long()[safe], ids[j][safe])
-    assert gated <= B // 4, f"{gated} of {3 * B} argmax comparisons gated out by the margin rule"
+        got_ids, want_ids = out["ids"][j].long(), ids[j]
+        if j == 0:
+            got_ids, want_ids = inverse[got_ids], inverse[want_ids]
+        assert torch.equal(got_ids[safe], want_ids[safe])
+    assert gated <= B // 4, f"{gated} of {3 * B} argmax comparisons gated out by the margin rule (achieved error {worst:.2e})"
+    # ties between enharmonic duplicates resolve to the first row on both sides (torch.argmax): raw ids agree as well
+    assert (out["ids"][0].long() == ids[0]).float().mean() > 0.95
     # the device-resident rows path (what bench.py times) gives the same numbers and ids as the host-buffer path
     rows, dids = est.estimate_device_rows(audio.cuda())
     assert torch.equal(rows[:, :12].cpu(), out["key"]) and torch.equal(rows[:, 12:24].cpu(), out["tonic"])
