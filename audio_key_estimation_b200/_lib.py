@@ -17,6 +17,7 @@ AKE_OK = 0
 AKE_ERR_INVALID, AKE_ERR_UNSUPPORTED, AKE_ERR_CUDA, AKE_ERR_WORKSPACE = -1, -2, -3, -4
 ROW_FLOATS = 35  # AKE_ROW_FLOATS: 12 key + 12 tonic + 11 genre
 CQT_LOGMAG, CQT_COMPLEX = 0, 1
+CQT_RECURSION_092, CQT_RECURSION_HALVE_WHILE_EVEN = 0, 1
 
 
 class PcnConfig(C.Structure):
@@ -55,6 +56,9 @@ _SIGNATURES = {
                                     C.c_float, C.c_int, _P]),
     "ake_cqt_create": (C.c_int, [C.c_double, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double,
                                  C.POINTER(_P)]),
+    "ake_cqt_create_ex": (C.c_int, [C.c_double, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int,
+                                    C.POINTER(_P)]),
+    "ake_cqt_set_peak": (C.c_int, [_P, C.c_float]),
     "ake_cqt_destroy": (None, [_P]),
     "ake_cqt_n_fft": (C.c_int, [_P]),
     "ake_cqt_n_bins": (C.c_int, [_P]),

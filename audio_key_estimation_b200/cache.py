@@ -70,7 +70,7 @@ def cache_entry(mel: torch.Tensor, n_frames: int) -> torch.Tensor:
 
 
 def write_cqt_cache(audio_paths: Sequence[str], waveforms: Sequence[torch.Tensor], sr: int, opt, batch: int = 64,
-                    overwrite: bool = False, accept_unpinned_cqt: bool = False) -> List[str]:
+                    overwrite: bool = False, accept_unpinned_cqt: bool = False, recursion: str = "librosa-0.9.2") -> List[str]:
     """Compute the log-CQT of ``waveforms`` (mono float32 tensors, CUDA or pinned/pageable host) on the GPU in batches and
     save each as the reference's cache file.  Returns the written file names.  Raises where the B200 front-end does not
     cover the reference's configuration (``ake_cqt_create`` says so).
@@ -80,7 +80,11 @@ def write_cqt_cache(audio_paths: Sequence[str], waveforms: Sequence[torch.Tensor
     librosa 0.9.2 (oracle/cqt_port.py), not against librosa itself, which is absent from the build environment
     (DESIGN.md section 2; tests/test_oracle_cqt.py::test_port_matches_librosa_when_importable pins it where librosa
     exists).  Writing features the reference's training and evaluation will silently consume is therefore an explicit
-    decision of the caller."""
+    decision of the caller.
+
+    ``recursion="halve-while-even"`` is needed for 44.1 kHz / 22.05 kHz material (hop = round(rate / frames) is then not a
+    multiple of 2^(octaves-1), which librosa 0.9.2 rejects); see ``CQTPlan``.  Clips of any amplitude are exact (their peak is
+    measured on the device)."""
     if len(audio_paths) != len(waveforms):
         raise ValueError("one path per waveform")
     if not accept_unpinned_cqt:
@@ -99,7 +103,7 @@ def write_cqt_cache(audio_paths: Sequence[str], waveforms: Sequence[torch.Tensor
         window = int(_get(opt, "window_size", 592))
         for i in todo:
             clip = waveforms[i].reshape(-1).to(device="cuda", dtype=torch.float32)
-            plan = CQTPlan.get(sr, int(clip.numel()) // window + 1, bpo * octaves, bpo)
+            plan = CQTPlan.get(sr, int(clip.numel()) // window + 1, bpo * octaves, bpo, recursion=recursion)
             mel, seq = plan.run(clip[None])
             entry = cache_entry(mel[0], min(int(seq[0]), window))
             if entry.shape[1] != expected_bins(opt):
@@ -110,7 +114,7 @@ def write_cqt_cache(audio_paths: Sequence[str], waveforms: Sequence[torch.Tensor
     for lo in range(0, len(todo), batch):
         idx = todo[lo: lo + batch]
         clips = [waveforms[i].reshape(-1).to(device="cuda", dtype=torch.float32, non_blocking=True) for i in idx]
-        mel, seq = cqt_logmag(clips, sr=sr, frames=frames, octaves=octaves, bins_per_octave=bpo)
+        mel, seq = cqt_logmag(clips, sr=sr, frames=frames, octaves=octaves, bins_per_octave=bpo, recursion=recursion)
         seq = seq.tolist()
         for j, i in enumerate(idx):
             entry = cache_entry(mel[j], seq[j])

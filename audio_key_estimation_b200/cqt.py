@@ -26,24 +26,37 @@ class CQTPlan:
     _cache: dict = {}
 
     def __init__(self, sr: float, hop_length: int, n_bins: int = 288, bins_per_octave: int = 36,
-                 fmin: Optional[float] = None, filter_scale: float = 1.0, sparsity: float = 0.01):
+                 fmin: Optional[float] = None, filter_scale: float = 1.0, sparsity: float = 0.01,
+                 recursion: str = "librosa-0.9.2", peak: Optional[float] = None):
+        """``recursion``: "librosa-0.9.2" (the release the reference pins: the hop must be a multiple of 2^(octaves-1)) or
+        "halve-while-even" (the octave loop of later librosa releases on the 0.9.2 filter design; include/ake_b200.h) -- the
+        latter lets hop = round(rate / 5) (KeyDataset.py:485) run at 44.1 kHz and 22.05 kHz.
+        ``peak``: the largest |sample| the caller guarantees (1.0 for torchaudio-normalised audio, KeyDataset.py:478-481);
+        None = unknown, measured per clip by one extra pass (any amplitude is then exact, as with librosa)."""
         lib = _lib.lib()
         h = C.c_void_p()
+        modes = {"librosa-0.9.2": _lib.CQT_RECURSION_092, "halve-while-even": _lib.CQT_RECURSION_HALVE_WHILE_EVEN}
+        if recursion not in modes:
+            raise ValueError(f"recursion must be one of {sorted(modes)}")
         # ValueError where librosa raises ParameterError, NotImplementedError for un-built branches
-        check(lib.ake_cqt_create(float(sr), int(hop_length), int(n_bins), int(bins_per_octave),
-                                 float(fmin) if fmin else 0.0, float(filter_scale), float(sparsity), C.byref(h)))
+        check(lib.ake_cqt_create_ex(float(sr), int(hop_length), int(n_bins), int(bins_per_octave),
+                                    float(fmin) if fmin else 0.0, float(filter_scale), float(sparsity), modes[recursion], C.byref(h)))
         self._h = h
+        check(lib.ake_cqt_set_peak(h, 0.0 if peak is None else float(peak)))
         self.sr, self.hop_length, self.n_bins, self.bins_per_octave = float(sr), int(hop_length), int(n_bins), int(bins_per_octave)
+        self.recursion, self.peak = recursion, peak
         self.n_fft = lib.ake_cqt_n_fft(h)
 
     @classmethod
-    def get(cls, sr, hop_length, n_bins=288, bins_per_octave=36, fmin=None, filter_scale=1.0, sparsity=0.01) -> "CQTPlan":
+    def get(cls, sr, hop_length, n_bins=288, bins_per_octave=36, fmin=None, filter_scale=1.0, sparsity=0.01,
+            recursion="librosa-0.9.2", peak=None) -> "CQTPlan":
         # one plan per host thread: a plan carries per-call staging state and may only be driven by one thread at a time
         key = (float(sr), int(hop_length), int(n_bins), int(bins_per_octave), float(fmin or 0.0), float(filter_scale),
-               float(sparsity), torch.cuda.current_device() if torch.cuda.is_available() else -1, threading.get_ident())
+               float(sparsity), recursion, peak, torch.cuda.current_device() if torch.cuda.is_available() else -1,
+               threading.get_ident())
         plan = cls._cache.get(key)
         if plan is None:
-            plan = cls._cache[key] = cls(sr, hop_length, n_bins, bins_per_octave, fmin, filter_scale, sparsity)
+            plan = cls._cache[key] = cls(sr, hop_length, n_bins, bins_per_octave, fmin, filter_scale, sparsity, recursion, peak)
         return plan
 
     def frames(self, n_samples: int) -> int:
@@ -94,17 +107,20 @@ class CQTPlan:
 
 
 def cqt(y: torch.Tensor, sr: float = 22050, hop_length: int = 512, fmin: Optional[float] = None, n_bins: int = 84,
-        bins_per_octave: int = 12, filter_scale: float = 1.0, sparsity: float = 0.01) -> torch.Tensor:
-    """``librosa.cqt`` for a mono CUDA signal: complex64 (n_bins, T) (batched input (B, N) -> (B, n_bins, T))."""
+        bins_per_octave: int = 12, filter_scale: float = 1.0, sparsity: float = 0.01, recursion: str = "librosa-0.9.2",
+        peak: Optional[float] = None) -> torch.Tensor:
+    """``librosa.cqt`` for a mono CUDA signal: complex64 (n_bins, T) (batched input (B, N) -> (B, n_bins, T)).
+    Any amplitude is accepted, as librosa does (``peak=None``: each clip's peak is measured); see ``CQTPlan``."""
     single = y.dim() == 1
-    plan = CQTPlan.get(sr, hop_length, n_bins, bins_per_octave, fmin, filter_scale, sparsity)
+    plan = CQTPlan.get(sr, hop_length, n_bins, bins_per_octave, fmin, filter_scale, sparsity, recursion, peak)
     out, _ = plan.run(y[None] if single else y, mode=_lib.CQT_COMPLEX)
     c = torch.view_as_complex(out)
     return c[0] if single else c
 
 
 def cqt_logmag(audio: Union[torch.Tensor, Sequence[torch.Tensor]], sr: float, frames: int = 5, octaves: int = 8,
-               lengths: Optional[Sequence[int]] = None, bins_per_octave: int = 36) -> Tuple[torch.Tensor, torch.Tensor]:
+               lengths: Optional[Sequence[int]] = None, bins_per_octave: int = 36, recursion: str = "librosa-0.9.2",
+               peak: Optional[float] = None) -> Tuple[torch.Tensor, torch.Tensor]:
     """The network input of KeyDataset.py:485-509 for a batch of clips, computed on the GPU.
 
     Returns ``mel`` (B, 1, 36*octaves, T_max) fp32, zero-padded beyond each clip's frames
@@ -118,5 +134,5 @@ def cqt_logmag(audio: Union[torch.Tensor, Sequence[torch.Tensor]], sr: float, fr
             batch[i, : a.numel()] = a.reshape(-1)
         audio = batch
     hop = round(sr / frames)
-    plan = CQTPlan.get(sr, hop, bins_per_octave * octaves, bins_per_octave)  # 12 per octave: opt.only_semitones (KeyDataset.py:493)
+    plan = CQTPlan.get(sr, hop, bins_per_octave * octaves, bins_per_octave, recursion=recursion, peak=peak)  # 12 per octave: opt.only_semitones (KeyDataset.py:493)
     return plan.run(audio, lengths=lengths, mode=_lib.CQT_LOGMAG)

@@ -65,17 +65,28 @@ using namespace ake;
 
 struct ake_cqt {
   double sr, fmin, filter_scale, sparsity;
-  int hop, n_bins, bpo, n_oct, n_fft;
+  int hop, n_bins, bpo, n_oct, n_fft;  // n_fft: of the top octave
+  int recursion = AKE_CQT_RECURSION_092;
+  // Per octave (0 = top): which decimated level it reads, its hop and frame length there, and which filter bank it uses.
+  // librosa 0.9.2 recursion: octave i reads level i with ONE shared bank (f_k / sr_i does not depend on i).  "halve while the hop
+  // is even" recursion: once the hop is odd the level stays and the filters double in length octave by octave.
+  int oct_level[16] = {}, oct_hop[16] = {}, oct_nfft[16] = {}, oct_bank[16] = {};
+  int n_levels = 1;                // decimated levels the cascade produces, plus the input (level 0)
   std::vector<double> dec_half;    // kaiser_fast half filter (without the sqrt(2) gain)
-  std::vector<float> bank;         // (2*bpo, n_fft): row 2k = Re K_k, 2k+1 = Im K_k
-  std::vector<float> out_scale;    // (n_oct, bpo): sqrt(2^i) / sqrt(length of the full-rate bin)
+  std::vector<std::vector<float>> banks;  // distinct banks: (2*bpo, n_fft_b), row 2k = Re K_k, 2k+1 = Im K_k
+  std::vector<int> bank_nfft;
+  std::vector<float> out_scale;    // (n_oct, bpo): sqrt(sr / sr_i) / sqrt(length of the full-rate bin)
   float* d_scale = nullptr;
-  // tensor-core path: fp16 (hi | lo) image of the bank in the shared-memory operand layout, one block per 64 samples of K
-  __half* d_bank_img = nullptr;
+  // tensor-core path: fp16 (hi | lo) image of each bank in the shared-memory operand layout, one block per 64 samples of K
+  std::vector<__half*> d_bank_img;
   __half* d_dec_img = nullptr;   // Toeplitz image of the 63-tap decimator (cascade_umma_kernel)
   float* d_scale_umma = nullptr;
   int npad = 0;  // filters per MMA (2*bpo rounded up to 16), 0: tensor-core path not available for this shape
   int device = -1;  // device the operand images live on (the one current at the first run)
+  // Amplitude contract (ake_cqt_set_peak): peak > 0 -- the caller guarantees |sample| <= peak and the kernels pre-scale by the
+  // exact power of two 2^-ceil(log2 peak); peak == 0 -- unknown: one extra pass measures max |sample| per clip and scales each
+  // clip by its own power of two.  Either way the fp16 hi/lo operands see |x| <= 1 and the results carry no scaling error.
+  float peak = 1.f;
   // page-locked staging ring for the per-clip lengths of ake_cqt_run_f32: a pageable source would make the H2D copy
   // synchronise the stream (no host run-ahead); a slot is reused only after its copy has executed
   static constexpr int kLenSlots = 4;
@@ -93,13 +104,87 @@ static int two_factors(int x) {
   return n;
 }
 
+// In-place radix-2 FFT (forward, e^{-2 pi i fn/N}); n is a power of two.
+static void fft_pow2(std::vector<std::complex<double>>& x) {
+  const size_t n = x.size();
+  for (size_t i = 1, j = 0; i < n; ++i) {
+    size_t bit = n >> 1;
+    for (; j & bit; bit >>= 1) j ^= bit;
+    j ^= bit;
+    if (i < j) std::swap(x[i], x[j]);
+  }
+  for (size_t len = 2; len <= n; len <<= 1) {
+    const double ang = -2.0 * kPi / (double)len;
+    std::vector<std::complex<double>> w(len / 2);
+    for (size_t k = 0; k < len / 2; ++k) w[k] = std::polar(1.0, ang * (double)k);
+    for (size_t i = 0; i < n; i += len)
+      for (size_t k = 0; k < len / 2; ++k) {
+        const std::complex<double> u = x[i + k], v = x[i + k + len / 2] * w[k];
+        x[i + k] = u + v, x[i + k + len / 2] = u - v;
+      }
+  }
+}
+
+// One octave's filter bank: librosa.filters.constant_q(sr_oct, fmin_oct, bpo filters) -> __cqt_filter_fft (complex64 basis times
+// lengths / n_fft, FFT, sparsify_rows at `sparsity`) -> its dense real time-domain image K[k][n] = sum_f B[k][f] e^{-2 pi i fn / N}
+// (the response basis . rFFT(frame) is linear in the frame, so it equals frame . K^T).  Returns n_fft.
+static int make_bank(double sr_oct, double fmin_oct, int bpo, double Q, double sparsity, std::vector<float>& bank) {
+  std::vector<double> lengths(bpo);
+  double max_len = 0;
+  for (int k = 0; k < bpo; ++k) lengths[k] = Q * sr_oct / (fmin_oct * std::pow(2.0, (double)k / bpo)), max_len = std::max(max_len, lengths[k]);
+  const int N = 1 << (int)std::ceil(std::log2(max_len)), NF = N / 2 + 1;
+  bank.assign((size_t)2 * bpo * N, 0.f);
+  std::vector<std::complex<double>> buf(N);
+  std::vector<double> mags(NF), sorted(NF);
+  for (int k = 0; k < bpo; ++k) {
+    const double ilen = lengths[k], freq = fmin_oct * std::pow(2.0, (double)k / bpo);
+    const double start = std::floor(-ilen / 2.0), stop = std::floor(ilen / 2.0);  // np.arange(-ilen//2, ilen//2)
+    const int len = (int)std::ceil(stop - start);
+    const int lpad = (N - len) / 2;  // util.pad_center
+    std::fill(buf.begin(), buf.end(), std::complex<double>(0.0, 0.0));
+    double wsum = 0;
+    for (int m = 0; m < len; ++m) {
+      const double w = 0.5 - 0.5 * std::cos(2.0 * kPi * m / len);  // periodic hann
+      buf[lpad + m] = std::polar(1.0, (start + m) * 2.0 * kPi * freq / sr_oct) * w;
+      wsum += std::abs(buf[lpad + m]);
+    }
+    const double gain = (ilen / N) / wsum;  // L1 normalisation, then basis *= lengths / n_fft
+    fft_pow2(buf);
+    double norm = 0;
+    for (int f = 0; f < NF; ++f) buf[f] *= gain, mags[f] = std::abs(buf[f]), norm += mags[f];
+    // util.sparsify_rows(quantile=sparsity): drop the smallest bins holding < quantile of the L1 mass
+    sorted = mags;
+    std::sort(sorted.begin(), sorted.end());
+    double cum = 0, thresh = sorted[0];
+    for (int f = 0; f < NF; ++f) {
+      cum += sorted[f] / norm;
+      if (!(cum < sparsity)) {
+        thresh = sorted[f];
+        break;
+      }
+    }
+    for (int f = 0; f < N; ++f) {
+      if (f < NF && mags[f] >= thresh) buf[f] = std::complex<double>((float)buf[f].real(), (float)buf[f].imag());  // complex64 basis
+      else buf[f] = 0;
+    }
+    fft_pow2(buf);  // dense time-domain image of the kept bins
+    for (int n = 0; n < N; ++n) {
+      bank[(size_t)(2 * k) * N + n] = (float)buf[n].real();
+      bank[(size_t)(2 * k + 1) * N + n] = (float)buf[n].imag();
+    }
+  }
+  return N;
+}
+
 static void build_cqt(ake_cqt* p) {
   const int bpo = p->bpo, n_bins = p->n_bins;
   if (p->sr <= 0 || p->hop <= 0 || n_bins <= 0 || bpo <= 0) fail(AKE_ERR_INVALID, "sr, hop_length, n_bins, bins_per_octave must be positive");
   if (n_bins % bpo) fail(AKE_ERR_UNSUPPORTED, "n_bins must be a multiple of bins_per_octave");
   if (!(p->sparsity >= 0.0 && p->sparsity < 1.0)) fail(AKE_ERR_INVALID, "sparsity must be in [0, 1)");
+  if (p->recursion != AKE_CQT_RECURSION_092 && p->recursion != AKE_CQT_RECURSION_HALVE_WHILE_EVEN) fail(AKE_ERR_INVALID, "unknown recursion mode %d", p->recursion);
   if (p->fmin <= 0) p->fmin = 32.70319566257483;  // note_to_hz('C1')
   p->n_oct = n_bins / bpo;
+  if (p->n_oct > 15) fail(AKE_ERR_UNSUPPORTED, "too many octaves");
   const double alpha = std::pow(2.0, 1.0 / bpo) - 1.0;
   const double Q = p->filter_scale / alpha;
   std::vector<double> freqs(n_bins);
@@ -117,83 +202,50 @@ static void build_cqt(ake_cqt* p) {
   const int num_twos = two_factors(p->hop);
   const int c2 = std::max(0, num_twos - p->n_oct + 1);
   if (std::min(c1, c2) > 0) fail(AKE_ERR_UNSUPPORTED, "this sr/hop would early-downsample in librosa; not built");
-  if (num_twos < p->n_oct - 1)
-    fail(AKE_ERR_INVALID, "hop_length must be a positive integer multiple of 2^%d for %d-octave CQT", p->n_oct - 1, p->n_oct);
+  if (p->recursion == AKE_CQT_RECURSION_092 && num_twos < p->n_oct - 1)
+    fail(AKE_ERR_INVALID, "hop_length must be a positive integer multiple of 2^%d for %d-octave CQT (librosa 0.9.2; "
+         "AKE_CQT_RECURSION_HALVE_WHILE_EVEN lifts this)", p->n_oct - 1, p->n_oct);
 
-  // ---- filters.constant_q for the top octave (lengths are identical for every octave)
-  std::vector<double> lengths(bpo);
-  double max_len = 0;
-  for (int k = 0; k < bpo; ++k) lengths[k] = Q * p->sr / (fmin_t * std::pow(2.0, (double)k / bpo)), max_len = std::max(max_len, lengths[k]);
-  p->n_fft = 1 << (int)std::ceil(std::log2(max_len));
-  const int N = p->n_fft, NF = N / 2 + 1;
-  std::vector<std::complex<double>> tw(N);
-  for (int m = 0; m < N; ++m) tw[m] = std::polar(1.0, -2.0 * kPi * m / N);
-  p->bank.assign((size_t)2 * bpo * N, 0.f);
-  std::vector<std::complex<double>> sig, spec(NF);
-  std::vector<double> mags(NF), sorted(NF);
-  for (int k = 0; k < bpo; ++k) {
-    const double ilen = lengths[k], freq = fmin_t * std::pow(2.0, (double)k / bpo);
-    const double start = std::floor(-ilen / 2.0), stop = std::floor(ilen / 2.0);  // np.arange(-ilen//2, ilen//2)
-    const int len = (int)std::ceil(stop - start);
-    sig.assign(len, 0.0);
-    double wsum = 0;
-    for (int m = 0; m < len; ++m) {
-      const double w = 0.5 - 0.5 * std::cos(2.0 * kPi * m / len);  // periodic hann
-      sig[m] = std::polar(1.0, (start + m) * 2.0 * kPi * freq / p->sr) * w;
-      wsum += std::abs(sig[m]);
+  // ---- the recursion: which level / hop / filters every octave uses
+  p->banks.clear(), p->bank_nfft.clear();
+  int level = 0, hop = p->hop;
+  for (int i = 0; i < p->n_oct; ++i) {
+    p->oct_level[i] = level, p->oct_hop[i] = hop;
+    if (level == i && i > 0) {
+      p->oct_bank[i] = 0;  // f_k / sr_i as in the top octave: the same bank
+    } else {
+      std::vector<float> bank;
+      const int nfft = make_bank(p->sr / std::pow(2.0, level), fmin_t / std::pow(2.0, i), bpo, Q, p->sparsity, bank);
+      p->oct_bank[i] = (int)p->banks.size();
+      p->banks.push_back(std::move(bank)), p->bank_nfft.push_back(nfft);
     }
-    const int lpad = (N - len) / 2;  // util.pad_center
-    const double gain = (ilen / N) / wsum;  // L1 normalisation, then basis *= lengths / n_fft
-    for (int f = 0; f < NF; ++f) {
-      std::complex<double> acc = 0;
-      for (int m = 0; m < len; ++m) acc += sig[m] * tw[(int)(((long long)f * (lpad + m)) % N)];
-      spec[f] = acc * gain;
-      mags[f] = std::abs(spec[f]);
-    }
-    // util.sparsify_rows(quantile=sparsity): drop the smallest bins holding < quantile of the L1 mass
-    sorted = mags;
-    std::sort(sorted.begin(), sorted.end());
-    double norm = 0;
-    for (double m : mags) norm += m;
-    double cum = 0, thresh = sorted[0];
-    for (int f = 0; f < NF; ++f) {
-      cum += sorted[f] / norm;
-      if (!(cum < p->sparsity)) {
-        thresh = sorted[f];
-        break;
-      }
-    }
-    for (int f = 0; f < NF; ++f) {
-      if (mags[f] >= thresh) spec[f] = std::complex<double>((float)spec[f].real(), (float)spec[f].imag());  // complex64 basis
-      else spec[f] = 0;
-    }
-    // dense time-domain image: K[n] = sum_f B[f] * exp(-2 pi i f n / N)
-    for (int n = 0; n < N; ++n) {
-      std::complex<double> acc = 0;
-      for (int f = 0; f < NF; ++f)
-        if (spec[f] != 0.0) acc += spec[f] * tw[(int)(((long long)f * n) % N)];
-      p->bank[(size_t)(2 * k) * N + n] = (float)acc.real();
-      p->bank[(size_t)(2 * k + 1) * N + n] = (float)acc.imag();
-    }
+    p->oct_nfft[i] = p->bank_nfft[p->oct_bank[i]];
+    // 0.9.2 halves before every further octave (the hop was checked above); the other rule halves while the hop stays even
+    if (i + 1 < p->n_oct && (p->recursion == AKE_CQT_RECURSION_092 || hop % 2 == 0)) ++level, hop /= 2;
   }
-  // fft_basis *= sqrt(2^i); V /= sqrt(constant_q_lengths at the full rate)
+  p->n_levels = p->oct_level[p->n_oct - 1] + 1;
+  p->n_fft = p->oct_nfft[0];
+  // fft_basis *= sqrt(sr / sr_i); V /= sqrt(constant_q_lengths at the full rate)
   p->out_scale.resize((size_t)p->n_oct * bpo);
   for (int i = 0; i < p->n_oct; ++i)
     for (int k = 0; k < bpo; ++k) {
       const int bin = n_bins - bpo * (i + 1) + k;
       const double full_len = Q * p->sr / freqs[bin];
-      p->out_scale[(size_t)i * bpo + k] = (float)(std::sqrt(std::pow(2.0, i)) / std::sqrt(full_len));
+      p->out_scale[(size_t)i * bpo + k] = (float)(std::sqrt(std::pow(2.0, p->oct_level[i])) / std::sqrt(full_len));
     }
   p->dec_half.resize(kHalfTaps);
   kaiser_fast_half(p->dec_half.data());
 }
 
 static void free_device_state(ake_cqt* p) {
-  void** ptrs[] = {(void**)&p->d_scale, (void**)&p->d_bank_img, (void**)&p->d_dec_img, (void**)&p->d_scale_umma};
+  void** ptrs[] = {(void**)&p->d_scale, (void**)&p->d_dec_img, (void**)&p->d_scale_umma};
   for (void** q : ptrs) {
     if (*q) cudaFree(*q);
     *q = nullptr;
   }
+  for (__half* q : p->d_bank_img)
+    if (q) cudaFree(q);
+  p->d_bank_img.clear();
 }
 
 // Device copies are made lazily so that plan creation (and the bank / tap getters) need no GPU; they live on the device
@@ -226,21 +278,28 @@ static void ensure_device(ake_cqt* p) {
   // tensor-core operand image: per 64-sample block of K, 8 chunks x (2*npad) rows x 8 halves; rows [0,npad) = hi, [npad,2npad) = lo
   const int nf = 2 * p->bpo;
   const int npad = (nf + 15) / 16 * 16;
-  if ((npad == 80 || npad == 32) && p->n_fft % kUKB == 0) {
+  bool ok = npad == 80 || npad == 32;
+  for (int nfft : p->bank_nfft) ok = ok && nfft % kUKB == 0;
+  if (ok) {
     p->npad = npad;
-    const int n_kb = p->n_fft / kUKB;
-    std::vector<__half> img((size_t)n_kb * 8 * 2 * npad * 8, __float2half(0.f));
-    for (int f = 0; f < nf; ++f)
-      for (int k = 0; k < p->n_fft; ++k) {
-        const float v = p->bank[(size_t)f * p->n_fft + k] * kBankScale;
-        const __half hi = __float2half_rn(v);
-        const __half lo = __float2half_rn(v - __half2float(hi));
-        const size_t blk = (size_t)(k / kUKB) * 8 * 2 * npad * 8, c = (k % kUKB) / 8, e = k % 8;
-        img[blk + (c * 2 * npad + f) * 8 + e] = hi;
-        img[blk + (c * 2 * npad + npad + f) * 8 + e] = lo;
-      }
-    AKE_CUDA(cudaMalloc(&p->d_bank_img, sizeof(__half) * img.size()));
-    AKE_CUDA(cudaMemcpy(p->d_bank_img, img.data(), sizeof(__half) * img.size(), cudaMemcpyHostToDevice));
+    for (size_t bi = 0; bi < p->banks.size(); ++bi) {
+      const int nfft = p->bank_nfft[bi], n_kb = nfft / kUKB;
+      const std::vector<float>& bank = p->banks[bi];
+      std::vector<__half> img((size_t)n_kb * 8 * 2 * npad * 8, __float2half(0.f));
+      for (int f = 0; f < nf; ++f)
+        for (int k = 0; k < nfft; ++k) {
+          const float v = bank[(size_t)f * nfft + k] * kBankScale;
+          const __half hi = __float2half_rn(v);
+          const __half lo = __float2half_rn(v - __half2float(hi));
+          const size_t blk = (size_t)(k / kUKB) * 8 * 2 * npad * 8, c = (k % kUKB) / 8, e = k % 8;
+          img[blk + (c * 2 * npad + f) * 8 + e] = hi;
+          img[blk + (c * 2 * npad + npad + f) * 8 + e] = lo;
+        }
+      __half* d = nullptr;
+      AKE_CUDA(cudaMalloc(&d, sizeof(__half) * img.size()));
+      AKE_CUDA(cudaMemcpy(d, img.data(), sizeof(__half) * img.size(), cudaMemcpyHostToDevice));
+      p->d_bank_img.push_back(d);
+    }
     std::vector<float> sc(p->out_scale);
     for (float& v : sc) v /= (kXScale * kBankScale);
     AKE_CUDA(cudaMalloc(&p->d_scale_umma, sizeof(float) * sc.size()));
@@ -253,7 +312,7 @@ static inline long long len_at(long long n0, int i) { return (n0 + (1LL << i) - 
 static int frames_for(const ake_cqt* p, long long n) {
   long long T = -1;
   for (int i = 0; i < p->n_oct; ++i) {
-    const long long t = 1 + len_at(n, i) / (p->hop >> i);
+    const long long t = 1 + len_at(n, p->oct_level[i]) / p->oct_hop[i];
     T = (T < 0 || t < T) ? t : T;
   }
   return (int)T;
@@ -294,6 +353,11 @@ struct CascadeArgs {
   const __half* img;
   int sparse_hop, sparse_nfft;  // > 0: level p+1 is only read by the filter bank (hop, n_fft at that level): store just those rows
   int stream_in;                // the input is read exactly once (caller's audio): load it with the L2 evict_first policy
+  // Amplitude pre-scale of the FIRST pass (level 0 = the caller's audio): clip b is multiplied by the exact power of two xs[b]
+  // (xs == NULL: xs_uniform for every clip) on its way into the fp16 hi/lo operands; the decimated levels are stored scaled and
+  // the filter bank's epilogue divides it out again.  Later passes run with xs == NULL, xs_uniform == 1.
+  const float* xs;
+  float xs_uniform;
 };
 
 // (a, b) -> fp16 pairs hi, lo with a ~= hi + lo
@@ -500,12 +564,13 @@ __global__ void __launch_bounds__(kCasThreads, 1) cascade_umma_kernel(const Casc
   } else if (warp >= 10) {
     // ------------------------------------------------------------------ converter: stage -> level-p operand planes
     const int ct = tid - 10 * 32;
-    const uint64_t ss = f2_pack(kXScale, kXScale);
     int i = 0;
     for (int tile = next_tile(blockIdx.x); tile < a.n_tiles; tile = next_tile(tile + gridDim.x), ++i) {
       const int bf = i & 1;
       const uint32_t ph = (i >> 1) & 1;
       const Span sp = span_of(tile);
+      const float xsc = kXScale * (a.xs ? __ldg(a.xs + clip_of(tile)) : a.xs_uniform);  // issued before the waits below
+      const uint64_t ss = f2_pack(xsc, xsc);
       const float* st = stage + (size_t)bf * kCasSpan;
       uint8_t* p0h = p0 + (size_t)bf * 2 * kCasP0Bytes;
       uint8_t* p0l = p0h + kCasP0Bytes;
@@ -727,14 +792,19 @@ __global__ void __launch_bounds__(kCasThreads, 1) cascade_umma_kernel(const Casc
 // multiplies MB blocks of 128 frame rows by every bank block it fetches, so the image is read once per 128 * MB rows.
 
 struct BankArgs {
+  // per octave (0 = top): the decimated level it reads (pointer, clip stride, decimation count), its hop and frame length there,
+  // and its filter-bank image
   const float* level[16];
   long long stride[16];
+  const __half* bank_img[16];
+  int shift[16], hop[16], nfft[16];
   const long long* lengths;
   long long n_uniform;
-  int n_oct, hop0, n_fft, B, T_max, n_bins, bpo, mode;
-  const __half* bank_img;
+  int n_oct, B, T_max, n_bins, bpo, mode;
   const float* scale;
   float* out;
+  const float* xs;   // per-clip amplitude pre-scale (exact powers of two) or NULL = xs_uniform; see CascadeArgs
+  float xs_uniform;
 };
 
 constexpr uint32_t kBankLBO = 129 * 16;                  // chunk pitch of the frame operand: odd multiple of 16 B (conflict-free 8-byte scatter)
@@ -759,11 +829,13 @@ __global__ void __launch_bounds__(32 * (8 * MB + 1), 1) cqt_bank_umma_kernel(con
   __shared__ uint32_t tmem_slot;
   __shared__ long long s_g0[128 * MB];   // index (into the octave's level array) of the first sample of frame row r
   __shared__ int2 s_valid[128 * MB];     // samples [x, y) of that frame exist (the rest is the zero padding of centred frames)
+  __shared__ float s_xs[128 * MB];       // operand scale of the row: kXScale, times the clip's amplitude pre-scale where the row is raw audio
 
   const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
   const int octave = blockIdx.y;
   const long long m0 = (long long)blockIdx.x * (128 * MB);
-  const int n_kb = a.n_fft / kUKB;
+  const int n_fft = a.nfft[octave];
+  const int n_kb = n_fft / kUKB;
   const int mb = warp >> 3;                                   // row block of this producer warp
   const int row_e = 128 * mb + 32 * (warp & 3) + lane;        // epilogue warps (warp & 7) < 4: TMEM lane 32 (warp & 3) + lane of accumulator mb
 
@@ -776,6 +848,7 @@ __global__ void __launch_bounds__(32 * (8 * MB + 1), 1) cqt_bank_umma_kernel(con
   // ---- frame row `row_e`: which clip / frame, where its samples live
   bool in_range = false, real_frame = false;
   int b = 0, t = 0;
+  float inv_xs = 1.f;
   if (warp < ISSUER && (warp & 7) < 4) {
     const long long m = m0 + row_e;
     in_range = m < (long long)a.B * a.T_max;
@@ -783,14 +856,19 @@ __global__ void __launch_bounds__(32 * (8 * MB + 1), 1) cqt_bank_umma_kernel(con
     const long long n0 = a.lengths ? a.lengths[b] : a.n_uniform;
     long long T = -1;
     for (int i = 0; i < a.n_oct; ++i) {
-      const long long ti = 1 + ((n0 + (1LL << i) - 1) >> i) / (a.hop0 >> i);
+      const long long ti = 1 + ((n0 + (1LL << a.shift[i]) - 1) >> a.shift[i]) / a.hop[i];
       T = (T < 0 || ti < T) ? ti : T;
     }
     real_frame = in_range && t < T;
-    const long long len = (n0 + (1LL << octave) - 1) >> octave;
-    const long long first = (long long)t * (a.hop0 >> octave) - a.n_fft / 2;  // centred frame, zero padded (pad_mode='constant')
+    const int sh = a.shift[octave];
+    const long long len = (n0 + (1LL << sh) - 1) >> sh;
+    const long long first = (long long)t * a.hop[octave] - n_fft / 2;  // centred frame, zero padded (pad_mode='constant')
     s_g0[row_e] = (long long)b * a.stride[octave] + first;
-    s_valid[row_e] = real_frame ? make_int2((int)max(0LL, -first), (int)max(0LL, min((long long)a.n_fft, len - first))) : make_int2(0, 0);
+    s_valid[row_e] = real_frame ? make_int2((int)max(0LL, -first), (int)max(0LL, min((long long)n_fft, len - first))) : make_int2(0, 0);
+    // the clip's amplitude pre-scale: applied here when the octave reads the raw audio (level 0), already in the data otherwise
+    const float xs = a.xs ? __ldg(a.xs + b) : a.xs_uniform;
+    s_xs[row_e] = kXScale * (sh == 0 ? xs : 1.f);
+    inv_xs = 1.f / xs;  // exact: xs is a power of two
   }
   fence_before_sync();
   __syncthreads();
@@ -807,19 +885,20 @@ __global__ void __launch_bounds__(32 * (8 * MB + 1), 1) cqt_bank_umma_kernel(con
     const uint32_t a_off = (uint32_t)mb * 2 * A_HALF;
     const float* level = a.level[octave];
     const int f = lane & 15;
-    const uint64_t ss = f2_pack(kXScale, kXScale);
     // The 16 rows this thread feeds are the same for every block of K: their sample pointers (frame-local index 4 f of the
     // first block) and a 2-bit class live in registers.  Class 0: the whole frame exists and the pointer is 16-byte aligned
     // (one vector load); 1: the whole frame exists (four scalar loads); 2: centred-frame zero padding or the clip's end
     // cuts the frame (per-sample predicates).
     const float* rowp[8];
+    float rowsc[8];
     uint32_t cls = 0;
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
       const int r = rb + pw * 32 + 2 * (it0 + it) + (lane >> 4);
       const int2 v = s_valid[r];
       rowp[it] = level + s_g0[r] + 4 * f;
-      const uint32_t c = (v.x == 0 && v.y == a.n_fft) ? (((reinterpret_cast<uintptr_t>(rowp[it]) & 15) == 0) ? 0u : 1u) : 2u;
+      rowsc[it] = s_xs[r];
+      const uint32_t c = (v.x == 0 && v.y == n_fft) ? (((reinterpret_cast<uintptr_t>(rowp[it]) & 15) == 0) ? 0u : 1u) : 2u;
       cls |= c << (2 * it);
     }
     for (int kb = 0; kb < n_kb; ++kb) {
@@ -829,7 +908,7 @@ __global__ void __launch_bounds__(32 * (8 * MB + 1), 1) cqt_bank_umma_kernel(con
       uint8_t* stage = smem + (size_t)s * STAGE;
       if (tid == 0) {
         mbar_arrive_expect_tx(&full_bar[s], B_BYTES);
-        bulk_g2s(stage + B_OFF, reinterpret_cast<const uint8_t*>(a.bank_img) + (size_t)kb * B_BYTES, B_BYTES, &full_bar[s]);
+        bulk_g2s(stage + B_OFF, reinterpret_cast<const uint8_t*>(a.bank_img[octave]) + (size_t)kb * B_BYTES, B_BYTES, &full_bar[s]);
       }
       const int i0 = kb * kUKB + 4 * f;  // frame-local index of this lane's first sample
       // all 16 loads are issued before the first conversion consumes one
@@ -854,6 +933,7 @@ __global__ void __launch_bounds__(32 * (8 * MB + 1), 1) cqt_bank_umma_kernel(con
 #pragma unroll
       for (int it = 0; it < 8; ++it) {
         uint32_t h0, l0, h1, l1;
+        const uint64_t ss = f2_pack(rowsc[it], rowsc[it]);
         cas_split2(f2_mul(f2_pack(x[it].x, x[it].y), ss), h0, l0);
         cas_split2(f2_mul(f2_pack(x[it].z, x[it].w), ss), h1, l1);
         const uint32_t off = off0 + 32u * it;  // row r = pw * 32 + 2 (it0 + it) + (lane >> 4)
@@ -880,7 +960,7 @@ __global__ void __launch_bounds__(32 * (8 * MB + 1), 1) cqt_bank_umma_kernel(con
         const int k = c0 / 2 + j;
         if (k >= bpo) break;
         const int bin = a.n_bins - bpo * (octave + 1) + k;
-        const float sc = a.scale[octave * bpo + k];
+        const float sc = a.scale[octave * bpo + k] * inv_xs;
         float re = (u[2 * j] + w[2 * j]) * sc, im = (u[2 * j + 1] + w[2 * j + 1]) * sc;
         if (!real_frame) re = 0.f, im = 0.f;  // beyond the clip's frames: batch padding is zero (KeyDataset.py:242-254)
         if (a.mode == AKE_CQT_LOGMAG) {
@@ -923,30 +1003,75 @@ __global__ void __launch_bounds__(32 * (8 * MB + 1), 1) cqt_bank_umma_kernel(con
   if (warp == ISSUER) tmem_dealloc(tmem, TMEM_COLS);
 }
 
-__global__ void cqt_seqlen_kernel(const long long* __restrict__ lengths, long long n_uniform, int B, int n_oct, int hop0,
-                                  int T_max, int* __restrict__ seq_len) {
+struct OctTable {
+  int n_oct, shift[16], hop[16];
+};
+
+__global__ void cqt_seqlen_kernel(const long long* __restrict__ lengths, long long n_uniform, int B, const OctTable oc, int T_max,
+                                  int* __restrict__ seq_len) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   const long long n0 = lengths ? lengths[b] : n_uniform;
   long long T = -1;
-  for (int i = 0; i < n_oct; ++i) {
-    const long long ti = 1 + ((n0 + (1LL << i) - 1) >> i) / (hop0 >> i);
+  for (int i = 0; i < oc.n_oct; ++i) {
+    const long long ti = 1 + ((n0 + (1LL << oc.shift[i]) - 1) >> oc.shift[i]) / oc.hop[i];
     T = (T < 0 || ti < T) ? ti : T;
   }
   seq_len[b] = (int)(T < T_max ? T : T_max);
 }
 
+// ---- amplitude pre-scale (ake_cqt_set_peak(plan, 0): "measure") ------------------------------------------------------------
+// max |x| per clip (bit pattern of a non-negative float orders like the float), then the exact power of two 2^-ceil(log2 max).
+__global__ void __launch_bounds__(256) peak_max_kernel(const float* __restrict__ audio, long long stride, const long long* __restrict__ lengths,
+                                                       long long n_uniform, unsigned int* __restrict__ peak_bits) {
+  const int b = blockIdx.y;
+  const long long n = lengths ? lengths[b] : n_uniform;
+  const float* x = audio + (long long)b * stride;
+  float m = 0.f;
+  // vector loads over the 16-byte aligned middle, scalar head / tail
+  const long long head = min(n, (long long)((4 - ((reinterpret_cast<uintptr_t>(x) >> 2) & 3)) & 3));
+  const long long n4 = (n - head) >> 2;
+  const float4* x4 = reinterpret_cast<const float4*>(x + head);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(x4 + i);
+    m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+  }
+  if (blockIdx.x == 0) {
+    for (long long i = threadIdx.x; i < head; i += blockDim.x) m = fmaxf(m, fabsf(__ldg(x + i)));
+    for (long long i = head + 4 * n4 + threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, fabsf(__ldg(x + i)));
+  }
+  for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(peak_bits + b, __float_as_uint(m));  // NaN samples are ignored by fmaxf
+}
+__global__ void peak_scale_kernel(const unsigned int* __restrict__ peak_bits, int B, float* __restrict__ xs) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const float m = __uint_as_float(peak_bits[b]);
+  float sc = 1.f;
+  if (m > 0.f && m < INFINITY) {
+    int e;
+    frexpf(m, &e);                        // m = f * 2^e, f in [0.5, 1)  ->  m * 2^-e in [0.5, 1)
+    e = max(-100, min(100, e));           // keep 2^-e and its inverse finite normal floats
+    sc = ldexpf(1.f, -e);
+  }
+  xs[b] = sc;
+}
+
 struct CqtWs {
   long long* d_len;
+  float* d_xs;              // per-clip amplitude pre-scale (measure mode)
+  unsigned int* d_peak;
   float* level[16];
   long long stride[16];
 };
 
-// d_len: one length per clip of the batch; level buffers: one group of G clips (reused by every group)
+// d_len / d_xs: one entry per clip of the batch; level buffers: one group of G clips (reused by every group)
 static CqtWs carve(const ake_cqt* p, Arena& ar, int B, int G, long long n_max) {
   CqtWs w{};
   w.d_len = ar.take<long long>(B);
-  for (int i = 1; i < p->n_oct; ++i) {
+  w.d_xs = ar.take<float>(B);
+  w.d_peak = ar.take<unsigned int>(B);
+  for (int i = 1; i < p->n_levels; ++i) {
     w.stride[i] = (long long)align_up((size_t)len_at(n_max, i), 32);  // the cascade kernel stores whole rows of 32 samples
     w.level[i] = ar.take<float>((size_t)G * w.stride[i]);
   }
@@ -987,7 +1112,6 @@ static int cqt_group_clips(int B) {
 // length once per batch); at most one of the two.
 void run_cqt(ake_cqt* p, const float* audio, long long stride, const int64_t* lengths_host, const long long* lengths_dev, int B,
              long long n_max, int mode, float* out, int T_max, int* seq_len_out, void* ws, size_t ws_bytes, cudaStream_t st) {
-  if (p->n_oct > 15) fail(AKE_ERR_UNSUPPORTED, "too many octaves");
   if (n_max >= (1LL << 31) - 65536) fail(AKE_ERR_UNSUPPORTED, "clips of 2^31 samples or more are not supported (32-bit sample indices in the cascade)");
   ensure_device(p);
   const int G = cqt_group_clips(B);
@@ -1003,22 +1127,42 @@ void run_cqt(ake_cqt* p, const float* audio, long long stride, const int64_t* le
   if (!p->npad)
     fail(AKE_ERR_UNSUPPORTED, "bins_per_octave %d / n_fft %d: the filter-bank kernel is built for 36 and 12 bins per octave, n_fft %% 64 == 0",
          p->bpo, p->n_fft);
+  // ---- amplitude pre-scale: one exact power of two per clip
+  const float* d_xs = nullptr;
+  float xs_uniform = 1.f;
+  if (p->peak > 0.f) {
+    int e;
+    frexpf(p->peak, &e);  // peak = f * 2^e, f in [0.5, 1): |x| <= peak  ->  |x * 2^-e| <= 1
+    if (std::ldexp(0.5f, e) == p->peak) --e;  // peak itself a power of two
+    xs_uniform = std::ldexp(1.f, -std::max(-100, std::min(100, e)));
+  } else {
+    ProfScope prof("cqt.peak", st);
+    AKE_CUDA(cudaMemsetAsync(w.d_peak, 0, sizeof(unsigned int) * B, st));
+    const int bx = (int)std::max<long long>(1, std::min<long long>(cdiv64(n_max, 256 * 4 * 8), std::max(1, 4 * sm_count() / B)));
+    peak_max_kernel<<<dim3(bx, B), 256, 0, st>>>(audio, stride, d_len, n_max, w.d_peak);
+    AKE_LAUNCHED();
+    peak_scale_kernel<<<cdiv(B, 128), 128, 0, st>>>(w.d_peak, B, w.d_xs);
+    AKE_LAUNCHED();
+    d_xs = w.d_xs;
+  }
   w.stride[0] = stride;
   const int n_sm = sm_count();
   const bool grouped = G < B;
+  const int d_max = p->n_levels - 1;  // deepest decimated level
   for (int g0 = 0; g0 < B; g0 += G) {
     const int nb = std::min(G, B - g0);
     const long long* g_len = d_len ? d_len + g0 : nullptr;
+    const float* g_xs = d_xs ? d_xs + g0 : nullptr;
     w.level[0] = const_cast<float*>(audio) + (size_t)g0 * stride;
-    if (p->n_oct > 1) {
+    if (d_max > 0) {
       // resampling cascade: two octave steps per pass (level p -> p+1, p+2), one persistent warp-specialised CTA per SM
       ProfScope prof("cqt.decimate", st);
       ensure_dyn_smem(cascade_umma_kernel, kCasSmemTotal);
-      for (int lv = 0; lv < p->n_oct - 1; lv += 2) {
+      for (int lv = 0; lv < d_max; lv += 2) {
         CascadeArgs ca{};
         ca.in = w.level[lv], ca.in_stride = w.stride[lv];
         ca.out1 = w.level[lv + 1], ca.stride1 = w.stride[lv + 1];
-        ca.n_levels = std::min(2, p->n_oct - 1 - lv);
+        ca.n_levels = std::min(2, d_max - lv);
         if (ca.n_levels == 2) ca.out2 = w.level[lv + 2], ca.stride2 = w.stride[lv + 2];
         ca.lengths = g_len, ca.n_uniform = n_max, ca.level_in = lv;
         ca.tiles_per_clip = (int)cdiv64(len_at(n_max, lv + 1), kCasOwn1);
@@ -1028,11 +1172,12 @@ void run_cqt(ake_cqt* p, const float* audio, long long stride, const int64_t* le
         if ((long long)ca.tiles_per_clip * nb * ca.tiles_per_clip >= (1LL << 32))
           fail(AKE_ERR_UNSUPPORTED, "%d clips x %d tiles exceed the cascade's index decode range; split the batch", nb, ca.tiles_per_clip);
         ca.img = p->d_dec_img;
-        // level lv+1 is consumed by the filter bank only (the next pass reads level lv+2): when its frames do not overlap,
-        // the samples between them are never written
-        const int hop1 = p->hop >> (lv + 1);
-        ca.sparse_hop = (ca.n_levels == 2 && hop1 >= p->n_fft + 64) ? hop1 : 0, ca.sparse_nfft = p->n_fft;
+        // level lv+1 < d_max is consumed by octave lv+1's filter bank only (the next pass reads level lv+2): when its frames do
+        // not overlap, the samples between them are never written
+        const int hop1 = p->oct_hop[lv + 1], nfft1 = p->oct_nfft[lv + 1];
+        ca.sparse_hop = (ca.n_levels == 2 && hop1 >= nfft1 + 64) ? hop1 : 0, ca.sparse_nfft = nfft1;
         ca.stream_in = (grouped && lv == 0) ? 1 : 0;  // the audio is read once: do not let it displace the resident levels
+        ca.xs = lv == 0 ? g_xs : nullptr, ca.xs_uniform = lv == 0 ? xs_uniform : 1.f;
         const int grid = std::min(ca.n_tiles, n_sm);  // persistent: one CTA per SM
         cascade_umma_kernel<<<grid, kCasThreads, kCasSmemTotal, st>>>(ca);
         AKE_LAUNCHED();
@@ -1043,10 +1188,15 @@ void run_cqt(ake_cqt* p, const float* audio, long long stride, const int64_t* le
       ProfScope prof("cqt.bank", st);
       const long long rows = (long long)nb * T_max;
       BankArgs ba{};
-      for (int i = 0; i < p->n_oct; ++i) ba.level[i] = w.level[i], ba.stride[i] = w.stride[i];
-      ba.lengths = g_len, ba.n_uniform = n_max, ba.n_oct = p->n_oct, ba.hop0 = p->hop, ba.n_fft = p->n_fft, ba.B = nb, ba.T_max = T_max;
-      ba.n_bins = p->n_bins, ba.bpo = p->bpo, ba.mode = mode, ba.bank_img = p->d_bank_img, ba.scale = p->d_scale_umma;
+      for (int i = 0; i < p->n_oct; ++i) {
+        const int lv = p->oct_level[i];
+        ba.level[i] = w.level[lv], ba.stride[i] = w.stride[lv], ba.shift[i] = lv, ba.hop[i] = p->oct_hop[i], ba.nfft[i] = p->oct_nfft[i];
+        ba.bank_img[i] = p->d_bank_img[p->oct_bank[i]];
+      }
+      ba.lengths = g_len, ba.n_uniform = n_max, ba.n_oct = p->n_oct, ba.B = nb, ba.T_max = T_max;
+      ba.n_bins = p->n_bins, ba.bpo = p->bpo, ba.mode = mode, ba.scale = p->d_scale_umma;
       ba.out = out + (size_t)g0 * p->n_bins * T_max * (mode == AKE_CQT_COMPLEX ? 2 : 1);
+      ba.xs = g_xs, ba.xs_uniform = xs_uniform;
       dim3 grid((unsigned)cdiv64(rows, 128 * kBankMB), p->n_oct);
       if (p->npad == 80) {
         constexpr size_t smem = kUStages * bank_stage_bytes(80, kBankMB);
@@ -1061,7 +1211,10 @@ void run_cqt(ake_cqt* p, const float* audio, long long stride, const int64_t* le
     }
   }
   if (seq_len_out) {
-    cqt_seqlen_kernel<<<cdiv(B, 128), 128, 0, st>>>(d_len, n_max, B, p->n_oct, p->hop, T_max, seq_len_out);
+    OctTable oc{};
+    oc.n_oct = p->n_oct;
+    for (int i = 0; i < p->n_oct; ++i) oc.shift[i] = p->oct_level[i], oc.hop[i] = p->oct_hop[i];
+    cqt_seqlen_kernel<<<cdiv(B, 128), 128, 0, st>>>(d_len, n_max, B, oc, T_max, seq_len_out);
     AKE_LAUNCHED();
   }
 }
@@ -1072,11 +1225,24 @@ extern "C" {
 
 int ake_cqt_create(double sr, int hop_length, int n_bins, int bins_per_octave, double fmin, double filter_scale,
                    double sparsity, ake_cqt** out) {
+  return ake_cqt_create_ex(sr, hop_length, n_bins, bins_per_octave, fmin, filter_scale, sparsity, AKE_CQT_RECURSION_092, out);
+}
+
+int ake_cqt_set_peak(ake_cqt* p, float peak) {
+  return guarded([&] {
+    if (!p) fail(AKE_ERR_INVALID, "null argument");
+    if (!(peak >= 0.f) || std::isinf(peak)) fail(AKE_ERR_INVALID, "peak must be a finite non-negative number (0 = measure per clip)");
+    p->peak = peak;
+  });
+}
+
+int ake_cqt_create_ex(double sr, int hop_length, int n_bins, int bins_per_octave, double fmin, double filter_scale,
+                      double sparsity, int recursion, ake_cqt** out) {
   return guarded([&] {
     if (!out) fail(AKE_ERR_INVALID, "null argument");
     ake_cqt* p = new ake_cqt();
     p->sr = sr, p->hop = hop_length, p->n_bins = n_bins, p->bpo = bins_per_octave, p->fmin = fmin;
-    p->filter_scale = filter_scale, p->sparsity = sparsity;
+    p->filter_scale = filter_scale, p->sparsity = sparsity, p->recursion = recursion;
     try {
       build_cqt(p);
     } catch (...) {
@@ -1104,8 +1270,9 @@ int ake_cqt_frames(const ake_cqt* p, int64_t n) { return (p && n >= 0) ? frames_
 int ake_cqt_get_bank(const ake_cqt* p, float* bank_host, int64_t cap) {
   return guarded([&] {
     if (!p || !bank_host) fail(AKE_ERR_INVALID, "null argument");
-    if (cap < (int64_t)p->bank.size()) fail(AKE_ERR_INVALID, "bank needs %zu floats", p->bank.size());
-    std::copy(p->bank.begin(), p->bank.end(), bank_host);
+    const std::vector<float>& bank = p->banks[0];  // the top octave's bank
+    if (cap < (int64_t)bank.size()) fail(AKE_ERR_INVALID, "bank needs %zu floats", bank.size());
+    std::copy(bank.begin(), bank.end(), bank_host);
   });
 }
 

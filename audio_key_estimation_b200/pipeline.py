@@ -19,7 +19,11 @@ from .models import PitchClassNet, _Workspace
 
 
 class KeyEstimator:
-    def __init__(self, net: PitchClassNet, sr: float, frames: int = 5, device: Optional[torch.device] = None):
+    def __init__(self, net: PitchClassNet, sr: float, frames: int = 5, device: Optional[torch.device] = None,
+                 recursion: str = "librosa-0.9.2", peak: Optional[float] = 1.0):
+        """``peak``: largest |sample| of the audio this estimator will see -- 1.0 for what ``torchaudio.load`` delivers
+        (KeyDataset.py:478-481) and for 16-bit PCM input; None measures every clip (one extra pass over the audio).
+        ``recursion``: see ``CQTPlan`` ("halve-while-even" for 44.1 kHz / 22.05 kHz material)."""
         if net.training:
             raise RuntimeError("KeyEstimator runs the eval-mode forward (eval.py:116); call net.eval() first")
         self.net = net
@@ -27,7 +31,7 @@ class KeyEstimator:
         if self.device.type != "cuda":
             raise RuntimeError("KeyEstimator needs the network on a CUDA device; there is no CPU fallback")
         self.sr = float(sr)
-        self.plan = CQTPlan.get(sr, round(sr / frames), net.pitches, 36)
+        self.plan = CQTPlan.get(sr, round(sr / frames), net.pitches, 36, recursion=recursion, peak=peak)
         self.genre = bool(net._genre)
 
     def frames(self, n_samples: int) -> int:

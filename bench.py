@@ -288,6 +288,8 @@ def run_b200(args):
     value = B * world * args.steps / (ms_total * 1e-3)
     # ---- the same K steps once more with the library's per-section CUDA events on (roofline / stage breakdown); kept out of
     # the timed region above: ~30 event records per step between the kernels are not part of the product path
+    time.sleep(0.25)  # let the board's power budget recover: a back-to-back second pass runs ~7 % slower under sw_power_cap
+    device_step()
     _lib.profile_enable(True)
     barrier()
     for _ in range(args.steps):

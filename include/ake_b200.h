@@ -173,6 +173,27 @@ int ake_mirex_f32(const float* key_out_dev, const float* tonic_out_dev, const fl
  * (AKE_ERR_UNSUPPORTED) where its recursion would early-downsample or switch resampler. */
 int ake_cqt_create(double sr, int hop_length, int n_bins, int bins_per_octave, double fmin, double filter_scale,
                    double sparsity, ake_cqt** out);
+/* The same with the octave recursion selectable:
+ *   AKE_CQT_RECURSION_092              librosa 0.9.2 (the release the reference pins, requirements.txt:250): every octave halves
+ *                                      the rate, so hop_length must be a multiple of 2^(n_octaves-1) -- the reference's own
+ *                                      hop = round(rate / 5) (KeyDataset.py:485) passes at 48 kHz (9600) and raises at 44.1 kHz
+ *                                      (8820) and 22.05 kHz (4410);
+ *   AKE_CQT_RECURSION_HALVE_WHILE_EVEN the rule later librosa releases use (vqt: `if my_hop % 2 == 0` halve): once the hop is
+ *                                      odd the rate stays and the filters of the lower octaves double in length.  Built on the
+ *                                      0.9.2 filter design and the kaiser_fast resampler, so it is a restated VARIANT (checked
+ *                                      against oracle/cqt_port.py's restatement of the same rule), not a bit-level statement of
+ *                                      any librosa release: those releases also changed the filter bandwidth and the default
+ *                                      resampler (soxr_hq). */
+#define AKE_CQT_RECURSION_092 0
+#define AKE_CQT_RECURSION_HALVE_WHILE_EVEN 1
+int ake_cqt_create_ex(double sr, int hop_length, int n_bins, int bins_per_octave, double fmin, double filter_scale,
+                      double sparsity, int recursion, ake_cqt** out);
+/* Amplitude contract of the plan.  The kernels carry samples as fp16 (hi, lo) pairs and pre-scale each clip by an exact power
+ * of two so that they see |x| <= 1 (results carry no scaling error; librosa.cqt accepts any amplitude).
+ *   peak > 0: the caller guarantees |sample| <= peak (default 1: torchaudio.load normalises, KeyDataset.py:478-481);
+ *             samples beyond ~256 x peak overflow the fp16 operands (inf / NaN in the result);
+ *   peak = 0: unknown -- one extra pass over the audio measures max |sample| per clip (costs ~25 % of the front-end's time). */
+int ake_cqt_set_peak(ake_cqt* plan, float peak);
 void ake_cqt_destroy(ake_cqt* plan);
 int ake_cqt_n_fft(const ake_cqt* plan);
 int ake_cqt_n_bins(const ake_cqt* plan);

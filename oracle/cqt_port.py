@@ -168,14 +168,36 @@ def early_downsample_count(nyquist, filter_cutoff, hop_length, n_octaves) -> int
     return min(downsample_count1, downsample_count2)
 
 
+RECURSION_092 = "librosa-0.9.2"
+RECURSION_HALVE_WHILE_EVEN = "halve-while-even"
+
+
+def octave_plan(hop_length: int, n_octaves: int, recursion: str = RECURSION_092):
+    """[(decimation count, hop at that rate)] per octave, top first.  0.9.2: octave i sits i halvings down.
+    halve-while-even (the rule of later librosa releases' vqt loop, ``if my_hop % 2 == 0``): halve after an octave only
+    while the hop is even; afterwards the rate stays and the filters grow."""
+    plan, level, hop = [], 0, int(hop_length)
+    for i in range(n_octaves):
+        plan.append((level, hop))
+        if i + 1 < n_octaves and (recursion == RECURSION_092 or hop % 2 == 0):
+            level, hop = level + 1, hop // 2
+    return plan
+
+
 def cqt(y: np.ndarray, sr: float = 22050, hop_length: int = 512, fmin: Optional[float] = None, n_bins: int = 84,
         bins_per_octave: int = 12, filter_scale: float = 1.0, sparsity: float = 0.01,
-        dtype=np.float64) -> np.ndarray:
+        dtype=np.float64, recursion: str = RECURSION_092) -> np.ndarray:
     """librosa.cqt == vqt(gamma=0) with tuning=0, norm=1, hann, scale=True, pad_mode='constant', res_type=None.
 
     ``dtype`` is the real working precision: np.float32 mirrors librosa (which keeps the input's
     precision, complex64 output); np.float64 (default) is the higher-precision yardstick the CUDA
-    path is compared with."""
+    path is compared with.
+
+    ``recursion``: RECURSION_092 is librosa 0.9.2 (the release the reference pins).  RECURSION_HALVE_WHILE_EVEN
+    restates the octave loop of later releases -- filter response first, then ``if my_hop % 2 == 0`` halve hop, rate and
+    signal -- ON TOP OF the 0.9.2 filter design and the kaiser_fast resampler (those releases also changed the filter
+    bandwidth and default to soxr_hq): a variant that lets the reference's own hop = round(rate / 5) run at 44.1 kHz and
+    22.05 kHz (KeyDataset.py:485), not a statement of any particular librosa release."""
     y = np.asarray(y, dtype=dtype)
     cdtype = np.complex64 if dtype == np.float32 else np.complex128
     n_octaves = int(np.ceil(float(n_bins) / bins_per_octave))
@@ -192,21 +214,23 @@ def cqt(y: np.ndarray, sr: float = 22050, hop_length: int = 512, fmin: Optional[
         raise NotImplementedError("top octave would use kaiser_best resampling; only the kaiser_fast recursion is restated")
     if early_downsample_count(nyquist, filter_cutoff, hop_length, n_octaves) > 0:
         raise NotImplementedError("early down-sampling branch of librosa is not restated")
-    if _num_two_factors(hop_length) < n_octaves - 1:
+    if recursion not in (RECURSION_092, RECURSION_HALVE_WHILE_EVEN):
+        raise ParameterError("unknown recursion")
+    if recursion == RECURSION_092 and _num_two_factors(hop_length) < n_octaves - 1:
         raise ParameterError("hop_length must be a positive integer multiple of 2^{0:d} for {1:d}-octave CQT/VQT"
                              .format(n_octaves - 1, n_octaves))
     resp = []
-    my_y, my_sr, my_hop = y, float(sr), int(hop_length)
-    for i in range(n_octaves):
-        if i > 0:
+    my_y, level = y, 0
+    for i, (lv, my_hop) in enumerate(octave_plan(hop_length, n_octaves, recursion)):
+        if lv > level:  # the previous octave halved the rate
             if len(my_y) < 2:
                 raise ParameterError("Input signal length={} is too short for {:d}-octave CQT/VQT".format(len(y), n_octaves))
             my_y = resample_half(my_y)
-            my_sr /= 2.0
-            my_hop //= 2
+            level = lv
+        my_sr = float(sr) / 2 ** lv
         fft_basis, n_fft = cqt_filter_fft(my_sr, float(fmin_t * 2.0 ** -i), n_filters, bins_per_octave, float(filter_scale),
                                           float(sparsity))
-        fft_basis = fft_basis * np.float32(np.sqrt(2 ** i))
+        fft_basis = fft_basis * np.float32(np.sqrt(2 ** lv))  # fft_basis *= sqrt(sr / my_sr)
         resp.append(cqt_response(my_y, n_fft, my_hop, fft_basis, cdtype))
     # __trim_stack
     max_col = min(c.shape[-1] for c in resp)
@@ -224,14 +248,15 @@ def cqt(y: np.ndarray, sr: float = 22050, hop_length: int = 512, fmin: Optional[
     return out
 
 
-def cqt_logmag(y: np.ndarray, sr: float, frames: int = 5, octaves: int = 8, dtype=np.float64) -> np.ndarray:
+def cqt_logmag(y: np.ndarray, sr: float, frames: int = 5, octaves: int = 8, dtype=np.float64,
+               recursion: str = RECURSION_092) -> np.ndarray:
     """DatasetLoader.get_all's feature (KeyDataset.py:485-509): (1, 36*octaves, T) float64."""
     hop = round(sr / frames)
-    C = cqt(y, sr=sr, hop_length=hop, bins_per_octave=36, n_bins=36 * octaves, dtype=dtype)
+    C = cqt(y, sr=sr, hop_length=hop, bins_per_octave=36, n_bins=36 * octaves, dtype=dtype, recursion=recursion)
     mel = np.log(1 + np.abs(C))
     return mel.reshape(1, mel.shape[0], mel.shape[1]).astype(np.float64)
 
 
-def n_frames(n_samples: int, hop_length: int, n_octaves: int) -> int:
-    """Frames librosa returns: the minimum over octaves of 1 + ceil(n / 2^i) // (hop / 2^i)."""
-    return min(1 + int(math.ceil(n_samples / 2 ** i)) // (hop_length >> i) for i in range(n_octaves))
+def n_frames(n_samples: int, hop_length: int, n_octaves: int, recursion: str = RECURSION_092) -> int:
+    """Frames librosa returns: the minimum over octaves of 1 + ceil(n / 2^level) // hop at that level."""
+    return min(1 + int(math.ceil(n_samples / 2 ** lv)) // hop for lv, hop in octave_plan(hop_length, n_octaves, recursion))

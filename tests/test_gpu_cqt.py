@@ -91,6 +91,49 @@ def test_long_clip_240s_matches_oracle():
         assert not mel[i, 0, :, want.shape[-1]:].any()
 
 
+@pytest.mark.parametrize("sr,hop", [(44100, 8820), (22050, 4410)])
+def test_reference_sample_rates_with_halve_while_even_recursion(sr, hop):
+    """hop = round(rate / 5) (KeyDataset.py:485) at the sample rates of the reference's datasets (GiantSteps 44.1 kHz, GTZAN
+    22.05 kHz): rejected by the pinned librosa 0.9.2 recursion, run by the halve-while-even variant against its oracle
+    restatement (octaves below the last even hop keep their rate: filters of up to 32768 samples)."""
+    with pytest.raises(ValueError):
+        ake.cqt(torch.zeros(sr).cuda(), sr=sr, hop_length=hop, n_bins=288, bins_per_octave=36)
+    lens = [sr * 7 + 13, sr * 4]
+    clips = [synth.synth_clip(30 + i, n, sr) for i, n in enumerate(lens)]
+    mel, seq = ake.cqt_logmag([c.cuda() for c in clips], sr, recursion="halve-while-even")
+    T = [cp.n_frames(n, hop, 8, cp.RECURSION_HALVE_WHILE_EVEN) for n in lens]
+    assert seq.tolist() == T and tuple(mel.shape) == (2, 1, 288, max(T))
+    for i, c in enumerate(clips):
+        want = cp.cqt_logmag(c.numpy(), sr, recursion=cp.RECURSION_HALVE_WHILE_EVEN)[0]
+        got = mel[i, 0].cpu().numpy()
+        assert np.abs(got[:, : T[i]] - want).max() <= 5e-4
+        assert not got[:, T[i]:].any()
+    Cc = ake.cqt(clips[0].cuda(), sr=sr, hop_length=hop, n_bins=288, bins_per_octave=36, recursion="halve-while-even")
+    wantc = cp.cqt(clips[0].numpy(), sr, hop, None, 288, 36, recursion=cp.RECURSION_HALVE_WHILE_EVEN)
+    assert np.abs(Cc.cpu().numpy() - wantc).max() <= 2e-4 * np.abs(wantc).max()
+
+
+@pytest.mark.parametrize("gain", [1e-3, 1e2, 32768.0])
+def test_any_amplitude_matches_oracle(gain):
+    """librosa.cqt accepts any amplitude.  The fp16 hi/lo operands do not: each clip is pre-scaled by an exact power of two
+    (measured per clip when the plan's peak is unknown, or given by the caller), so quiet clips keep their 22 bits and
+    int16-scale clips do not overflow.  Tolerance relative to each clip's own max |C|, as everywhere."""
+    y = synth.synth_clip(3, SR * 5 + 123, SR)
+    batch = torch.stack([y * gain, y * (gain * 0.01)]).cuda()     # two clips of different loudness in one batch
+    got = ake.cqt(batch, sr=SR, hop_length=HOP, n_bins=288, bins_per_octave=36)       # peak unknown: measured per clip
+    for i, g in enumerate((gain, gain * 0.01)):
+        want = cp.cqt((y * g).numpy().astype(np.float64), SR, HOP, None, 288, 36)
+        err = np.abs(got[i].cpu().numpy() - want).max()
+        assert np.isfinite(got[i].abs().max().item()) and err <= 2e-4 * np.abs(want).max(), (g, err)
+    # the caller states the peak instead: same result without the measuring pass (exact powers of two either way)
+    hinted = ake.cqt(batch[0], sr=SR, hop_length=HOP, n_bins=288, bins_per_octave=36, peak=float(gain))
+    want = cp.cqt((y * gain).numpy().astype(np.float64), SR, HOP, None, 288, 36)
+    assert np.abs(hinted.cpu().numpy() - want).max() <= 2e-4 * np.abs(want).max()
+    # log-magnitude of the loud clip (what the network would see)
+    mel, _ = ake.cqt_logmag(batch[:1], SR)
+    assert np.abs(mel[0, 0].cpu().numpy() - np.log1p(np.abs(want))).max() <= 5e-4 * max(1.0, np.log1p(np.abs(want)).max())
+
+
 def test_other_bank_shapes_and_errors():
     y = synth.synth_clip(9, 22050 * 3, 22050).cuda()
     got = ake.cqt(y, sr=22050, hop_length=512, n_bins=84, bins_per_octave=12)   # librosa's own defaults

@@ -101,6 +101,50 @@ def test_regression_fixture():
     np.testing.assert_allclose(mel[0], g["logmag"], atol=2e-5)
 
 
+def test_halve_while_even_recursion_runs_the_reference_sample_rates():
+    """KeyDataset.py:485 sets hop = round(rate / 5): 8820 at 44.1 kHz (GiantSteps) and 4410 at 22.05 kHz (GTZAN), which the
+    pinned librosa 0.9.2 rejects (not multiples of 2^7).  The halve-while-even variant (see cqt_port.cqt) decimates while the
+    hop is even and then lengthens the filters; anchors: octave plan, frame count, and the pure-tone known answer in octaves
+    that are computed WITHOUT further decimation (their filters are 2..32 times longer)."""
+    R = cp.RECURSION_HALVE_WHILE_EVEN
+    assert cp.octave_plan(9600, 8, R) == cp.octave_plan(9600, 8) == [(i, 9600 >> i) for i in range(8)]
+    assert cp.octave_plan(8820, 8, R) == [(0, 8820), (1, 4410)] + [(2, 2205)] * 6
+    assert cp.octave_plan(4410, 8, R) == [(0, 4410)] + [(1, 2205)] * 7
+    for sr, hop in ((44100, 8820), (22050, 4410)):
+        n = sr * 5
+        assert cp.n_frames(n, hop, 8, R) == 1 + n // hop
+        t = np.arange(n) / sr
+        for bin_ in (20, 130, 260):
+            f0 = cp.C1_HZ * 2 ** (bin_ / 36)
+            Cq = np.abs(cp.cqt(0.3 * np.sin(2 * np.pi * f0 * t), sr, hop, None, 288, 36, recursion=R))
+            col = Cq[:, Cq.shape[1] // 2]
+            assert col.argmax() == bin_
+            expect = 0.5 * 0.3 * np.sqrt(cp.constant_q_lengths(sr, cp.C1_HZ, 288, 36)[bin_])
+            assert abs(col.max() / expect - 1) < 3e-3
+    # at a hop that IS a multiple of 2^7 the two recursions are the same computation
+    y = np.random.default_rng(1).standard_normal(SR)
+    np.testing.assert_array_equal(cp.cqt(y, SR, HOP, None, 288, 36, recursion=R), cp.cqt(y, SR, HOP, None, 288, 36))
+
+
+def test_extended_plan_tables_and_long_filter_banks():
+    """ake_cqt_create_ex(HALVE_WHILE_EVEN): frame counts follow the extended oracle; the default mode still raises."""
+    from audio_key_estimation_b200 import _lib
+    L = _lib.lib()
+    for sr, hop in ((44100, 8820), (22050, 4410)):
+        h = C.c_void_p()
+        assert L.ake_cqt_create(float(sr), hop, 288, 36, 0.0, 1.0, 0.01, C.byref(h)) == _lib.AKE_ERR_INVALID
+        assert L.ake_cqt_create_ex(float(sr), hop, 288, 36, 0.0, 1.0, 0.01, _lib.CQT_RECURSION_HALVE_WHILE_EVEN, C.byref(h)) == 0
+        try:
+            for n_samp in (0, 1, hop - 1, hop, sr * 30, sr * 30 + 1):
+                assert L.ake_cqt_frames(h, n_samp) == cp.n_frames(n_samp, hop, 8, cp.RECURSION_HALVE_WHILE_EVEN)
+            assert L.ake_cqt_set_peak(h, 0.0) == 0 and L.ake_cqt_set_peak(h, 32768.0) == 0
+            assert L.ake_cqt_set_peak(h, -1.0) == _lib.AKE_ERR_INVALID
+        finally:
+            L.ake_cqt_destroy(h)
+    h = C.c_void_p()
+    assert L.ake_cqt_create_ex(48000.0, 9600, 288, 36, 0.0, 1.0, 0.01, 7, C.byref(h)) == _lib.AKE_ERR_INVALID
+
+
 def test_port_matches_librosa_when_importable():
     """Pins the restatement the moment librosa is importable (it is not in the build container: requirements.txt:250 pins
     librosa 0.9.2 + resampy 0.3.1, neither vendored).  Same call as KeyDataset.py:490-491."""
