@@ -25,7 +25,7 @@ class PcnConfig(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "pitches", "pitch_classes", "num_layers", "kernel_size", "conv_layers", "n_filters", "head_layers",
         "time_pool_size", "genre", "max_pool", "resblock", "denseblock", "stay_sixth", "only_semitones",
-        "p2pc_conv", "pc2p_mem", "local")]
+        "p2pc_conv", "pc2p_mem", "local", "frames", "loc_window_size")]
 
 
 _P = C.c_void_p
@@ -45,6 +45,8 @@ _SIGNATURES = {
     "ake_pcn_workspace_bytes": (C.c_size_t, [_P, C.c_int, C.c_int, C.c_int]),
     "ake_pcn_forward_f32": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, C.c_int, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "ake_pcn_bn_channels": (C.c_int, [_P]),
+    "ake_pcn_bn_counts": (C.c_int, [_P, _P, C.c_int]),
+    "ake_pcn_local_frames": (C.c_int, [_P, C.c_int, C.POINTER(C.c_int)]),
     "ake_pcn_forward_rows_f32": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P, _P, _P, C.c_size_t, _P]),
     "ake_pcn_backward_f32": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, _P, C.c_size_t, _P]),
     "ake_loss_f32": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_float, C.c_float, C.c_float, _P, _P, _P, _P, _P]),

@@ -89,7 +89,9 @@ struct BnSite {
 struct Conv {
   int Cout, Cin, KH, KW;
   bool transposed = false;  // ConvTranspose2d weight layout (Cin, Cout, KH, KW)
-  int64_t w_off, b_off;
+  bool has_bias = true;     // dense layers: nn.Conv2d(..., bias=False) (models.py:463, 467)
+  bool norm_only = false;   // a BatchNorm with no convolution in front (dense layers' norm1): KH = KW = 0, no weights
+  int64_t w_off = 0, b_off = 0;
   int bn = -1;              // index into bn sites, -1: none
   int cout_pad = 0;
   int64_t packed_off = 0;   // into packed weights
@@ -98,10 +100,21 @@ struct Conv {
 
 struct TrainTape;
 
+struct ResPair {  // ResBlock / ResBlockEquivariant (models.py:402-454): conv1 (C -> 2C) + BN + act, conv2 (2C -> C) + BN, + x, act
+  int c1, c2;
+};
+
+struct DenseLayer {  // _DenseLayer / _DenseLayerEquivariant (models.py:456-580): norm1 + LeakyReLU + conv1 (1 wide) + norm2 + ReLU + conv2
+  int norm1, conv1, conv2;
+};
+
 struct LayerPlan {
   int prev_p = 0, prev_pc = 0, out_p = 0, out_pc = 0;
   int sem = -1, up = -1;
-  std::vector<int> p2p, pc2pc;
+  int pool_conv = -1;                  // opt.p2pc_conv: Pitch2PitchClassConv instead of the octave max pool
+  std::vector<int> p2p, pc2pc;         // the plain conv stacks; with opt.resblock only their first conv ...
+  std::vector<ResPair> p2p_res, pc2pc_res;  // ... followed by conv_layers residual blocks
+  std::vector<DenseLayer> p2p_dense, pc2pc_dense;  // opt.denseblock: DenseBlock / DenseBlockEquivariant instead of the stacks
 };
 
 }  // namespace ake
@@ -141,6 +154,7 @@ struct ake_pcn {
   // (pcn_train.cuh): several kept forwards may be outstanding (summed losses, siamese use), each with its own workspace
   std::map<const void*, struct ake::TrainTape*> tapes;
   int device = -1;  // device the weights / operand images live on (set by the first upload)
+  std::vector<int64_t> bn_count;  // per BatchNorm site: elements per channel it normalised over in the last train-mode forward
 };
 
 namespace ake {
@@ -173,14 +187,14 @@ static int add_bn(ake_pcn* p, const std::string& prefix, int C) {
 }
 
 static int add_conv(ake_pcn* p, const std::string& wname, int Cout, int Cin, int KH, int KW, int co_tile,
-                    bool transposed = false) {
+                    bool transposed = false, bool has_bias = true) {
   Conv c;
-  c.Cout = Cout, c.Cin = Cin, c.KH = KH, c.KW = KW, c.transposed = transposed;
+  c.Cout = Cout, c.Cin = Cin, c.KH = KH, c.KW = KW, c.transposed = transposed, c.has_bias = has_bias;
   if (transposed)
     c.w_off = add_tensor(p, wname + ".weight", {Cin, Cout, KH, KW});
   else
     c.w_off = add_tensor(p, wname + ".weight", {Cout, Cin, KH, KW});
-  c.b_off = add_tensor(p, wname + ".bias", {Cout});
+  if (has_bias) c.b_off = add_tensor(p, wname + ".bias", {Cout});
   c.cout_pad = cdiv(Cout, co_tile) * co_tile;
   c.packed_off = p->n_packed;
   if (!transposed) p->n_packed += (int64_t)Cin * KH * KW * c.cout_pad;
@@ -190,13 +204,29 @@ static int add_conv(ake_pcn* p, const std::string& wname, int Cout, int Cin, int
   return (int)p->convs.size() - 1;
 }
 
+// A BatchNorm site with no convolution in front of it (its scale / shift tables still live in a Conv slot).
+static int add_norm(ake_pcn* p, const std::string& prefix, int C) {
+  Conv c;
+  c.Cout = C, c.Cin = C, c.KH = 0, c.KW = 0, c.norm_only = true, c.has_bias = false;
+  c.ss_off = p->n_ss;
+  p->n_ss += C;
+  c.bn = add_bn(p, prefix, C);
+  p->convs.push_back(c);
+  return (int)p->convs.size() - 1;
+}
+
 static int co_tile_for(int Cout) { return Cout >= 8 ? 8 : (Cout >= 4 ? 4 : 1); }
 
 static void build_plan(ake_pcn* p) {
   const ake_pcn_config& c = p->cfg;
-  if (c.resblock || c.denseblock || c.stay_sixth || c.only_semitones || c.p2pc_conv || c.pc2p_mem || c.local)
-    fail(AKE_ERR_UNSUPPORTED,
-         "resblock/denseblock/stay_sixth/only_semitones/p2pc_conv/pc2p_mem/local are outside the B200 hot path");
+  if (c.denseblock && (c.resblock || c.pc2p_mem || c.stay_sixth))
+    fail(AKE_ERR_UNSUPPORTED, "denseblock together with resblock / pc2p_mem / stay_sixth is not built (the reference's own channel plan "
+         "does not cover those combinations, models.py:266-283, 331-335)");
+  if (c.only_semitones) fail(AKE_ERR_UNSUPPORTED, "only_semitones is not built (the reference itself cannot run it: models.py:366-367)");
+  if (c.stay_sixth && c.pc2p_mem) fail(AKE_ERR_UNSUPPORTED, "stay_sixth together with pc2p_mem is not built");
+  if (c.p2pc_conv && (c.pitches / 3) % 12) fail(AKE_ERR_UNSUPPORTED, "p2pc_conv needs pitches / 3 to be a multiple of 12 (the reference pads with -inf otherwise)");
+  const bool variant = c.resblock || c.stay_sixth || c.p2pc_conv || c.pc2p_mem || c.local || c.denseblock;
+  if (c.local && (c.frames <= 0 || c.loc_window_size <= 0)) fail(AKE_ERR_INVALID, "opt.local needs opt.frames > 0 and opt.loc_window_size > 0");
   if (c.pitch_classes != 12) fail(AKE_ERR_INVALID, "pitch_classes must be 12 (models.py:171)");
   if (c.pitches <= 0 || c.pitches % 36) fail(AKE_ERR_INVALID, "pitches must be a positive multiple of 36");
   if (c.kernel_size != 7) fail(AKE_ERR_UNSUPPORTED, "kernel_size %d: only 7 is built", c.kernel_size);
@@ -205,6 +235,50 @@ static void build_plan(ake_pcn* p) {
   if (c.conv_layers < 1 || c.n_filters < 1 || c.head_layers < 1) fail(AKE_ERR_INVALID, "bad layer counts");
   const int k = c.kernel_size, nf = c.n_filters;
 
+  // Pitch2Pitch / PitchClass2PitchClass stack (models.py:168-243): conv_layers x (conv + BN + LeakyReLU), or with opt.resblock
+  // conv + BN + LeakyReLU followed by conv_layers residual blocks ("<stack>.layer.{3 + j}.conv1 / b1 / conv2 / b2")
+  auto build_stack = [&](const std::string& stack, bool equivariant, int Cin, int Cout, std::vector<int>& ids, std::vector<ResPair>& res) {
+    const int KH = equivariant ? 12 : k;
+    const std::string leaf = equivariant ? ".conv2d" : "";
+    for (int i = 0; i < (c.resblock ? 1 : c.conv_layers); ++i) {
+      int id = add_conv(p, stack + ".layer." + std::to_string(3 * i) + leaf, Cout, i == 0 ? Cin : Cout, KH, k, co_tile_for(Cout));
+      p->convs[id].bn = add_bn(p, stack + ".layer." + std::to_string(3 * i + 1), Cout);
+      ids.push_back(id);
+    }
+    if (c.resblock)
+      for (int j = 0; j < c.conv_layers; ++j) {
+        const std::string rb = stack + ".layer." + std::to_string(3 + j);
+        ResPair rp;
+        rp.c1 = add_conv(p, rb + ".conv1" + leaf, 2 * Cout, Cout, KH, k, co_tile_for(2 * Cout));
+        p->convs[rp.c1].bn = add_bn(p, rb + ".b1", 2 * Cout);
+        rp.c2 = add_conv(p, rb + ".conv2" + leaf, Cout, 2 * Cout, KH, k, co_tile_for(Cout));
+        p->convs[rp.c2].bn = add_bn(p, rb + ".b2", Cout);
+        res.push_back(rp);
+      }
+  };
+  // DenseBlock / DenseBlockEquivariant(num_layers = conv_layers, num_input_features = Cin, bn_size = Cin // 2 (1 for Cin = 1),
+  // growth_rate = n_filters, multi_path off): "<stack>.layer.0.denselayer{i+1}.norm1 / conv1 / norm2 / conv2" (models.py:186, 224, 582-648)
+  auto build_dense = [&](const std::string& stack, bool equivariant, int Cin, std::vector<DenseLayer>& dl) {
+    const int bn_size = Cin > 1 ? Cin / 2 : 1, g = nf;
+    const std::string leaf = equivariant ? ".conv2d" : "";
+    for (int i = 0; i < c.conv_layers; ++i) {
+      const std::string d = stack + ".layer.0.denselayer" + std::to_string(i + 1);
+      const int Cn = Cin + i * g;
+      DenseLayer L;
+      L.norm1 = add_norm(p, d + ".norm1", Cn);
+      L.conv1 = add_conv(p, d + ".conv1" + leaf, bn_size * g, Cn, equivariant ? 12 : 1, 1, co_tile_for(bn_size * g), false, equivariant);
+      p->convs[L.conv1].bn = add_bn(p, d + ".norm2", bn_size * g);
+      L.conv2 = add_conv(p, d + ".conv2" + leaf, g, bn_size * g, equivariant ? 12 : k, k, co_tile_for(g), false, equivariant);
+      dl.push_back(L);
+    }
+    return Cin + c.conv_layers * g;
+  };
+  auto build_pool = [&](const std::string& pre, int C, LayerPlan& lp) {
+    if (!c.p2pc_conv) return;
+    const int KS = cdiv(c.pitches / 3, 12);  // Pitch2PitchClassConv.kernel_size (models.py:115)
+    lp.pool_conv = add_conv(p, pre + "pool.conv", C, C, KS, 1, 1);
+    p->convs[lp.pool_conv].bn = add_bn(p, pre + "pool.bn", C);
+  };
   for (int L = 0; L < c.num_layers; ++L) {
     LayerPlan lp;
     const std::string pre = "model." + std::to_string(L) + ".";
@@ -212,12 +286,19 @@ static void build_plan(ake_pcn* p) {
       lp.out_p = 1, lp.out_pc = nf;  // models.py:298-300 (pc2pc built with num_filters, :320)
       lp.sem = add_conv(p, pre + "pool_semi", 1, 1, 3, 3, 1);
       p->convs[lp.sem].bn = add_bn(p, pre + "pool_semi_b", 1);
-      for (int i = 0; i < c.conv_layers; ++i) {
-        const std::string s = pre + "pc2pc.layer." + std::to_string(3 * i);
-        int id = add_conv(p, s + ".conv2d", nf, i == 0 ? 1 : nf, 12, k, co_tile_for(nf));
-        p->convs[id].bn = add_bn(p, pre + "pc2pc.layer." + std::to_string(3 * i + 1), nf);
-        lp.pc2pc.push_back(id);
-      }
+      build_pool(pre, 1, lp);
+      if (c.denseblock) lp.out_pc = build_dense(pre + "pc2pc", true, 1, lp.pc2pc_dense);
+      else build_stack(pre + "pc2pc", true, 1, nf, lp.pc2pc, lp.pc2pc_res);
+    } else if (c.denseblock) {
+      // models.py:266-283: every layer passes all of its input features on (DenseNet concatenation)
+      lp.prev_p = p->layers[L - 1].out_p, lp.prev_pc = p->layers[L - 1].out_pc;
+      lp.up = add_conv(p, pre + "up_sixth", lp.prev_pc, lp.prev_pc, 3, 1, 1, /*transposed=*/true);
+      p->convs[lp.up].bn = add_bn(p, pre + "up_sixth_b", lp.prev_pc);
+      lp.out_p = build_dense(pre + "p2p", false, lp.prev_p + lp.prev_pc, lp.p2p_dense);
+      lp.sem = add_conv(p, pre + "pool_semi", lp.out_p, lp.out_p, 3, 3, 8);
+      p->convs[lp.sem].bn = add_bn(p, pre + "pool_semi_b", lp.out_p);
+      build_pool(pre, lp.out_p, lp);
+      lp.out_pc = build_dense(pre + "pc2pc", true, lp.out_p + lp.prev_pc, lp.pc2pc_dense);
     } else {
       // models.py:285-308
       if (L == 1) lp.prev_p = 1, lp.prev_pc = nf, lp.out_p = 2 * nf, lp.out_pc = 2 * lp.out_p;
@@ -226,22 +307,18 @@ static void build_plan(ake_pcn* p) {
         lp.prev_pc = 2 * lp.prev_p;
         lp.out_p = 4 * lp.prev_p, lp.out_pc = 4 * lp.prev_pc;
       }
-      lp.up = add_conv(p, pre + "up_sixth", lp.prev_pc, lp.prev_pc, 3, 1, 1, /*transposed=*/true);
-      p->convs[lp.up].bn = add_bn(p, pre + "up_sixth_b", lp.prev_pc);
-      for (int i = 0; i < c.conv_layers; ++i) {
-        const std::string s = pre + "p2p.layer." + std::to_string(3 * i);
-        int id = add_conv(p, s, lp.out_p, i == 0 ? lp.prev_p + lp.prev_pc : lp.out_p, k, k, 8);
-        p->convs[id].bn = add_bn(p, pre + "p2p.layer." + std::to_string(3 * i + 1), lp.out_p);
-        lp.p2p.push_back(id);
+      if (!c.stay_sixth) {  // opt.stay_sixth: the pitch-class rows are tiled straight over the semitones (models.py:322-323)
+        lp.up = add_conv(p, pre + "up_sixth", lp.prev_pc, lp.prev_pc, 3, 1, 1, /*transposed=*/true);
+        p->convs[lp.up].bn = add_bn(p, pre + "up_sixth_b", lp.prev_pc);
       }
-      lp.sem = add_conv(p, pre + "pool_semi", lp.out_p, lp.out_p, 3, 3, 8);
-      p->convs[lp.sem].bn = add_bn(p, pre + "pool_semi_b", lp.out_p);
-      for (int i = 0; i < c.conv_layers; ++i) {
-        const std::string s = pre + "pc2pc.layer." + std::to_string(3 * i);
-        int id = add_conv(p, s + ".conv2d", lp.out_pc, i == 0 ? lp.out_p + lp.prev_pc : lp.out_pc, 12, k, 8);
-        p->convs[id].bn = add_bn(p, pre + "pc2pc.layer." + std::to_string(3 * i + 1), lp.out_pc);
-        lp.pc2pc.push_back(id);
+      // opt.pc2p_mem: the up-sampled features are added to p instead of concatenated (models.py:335)
+      build_stack(pre + "p2p", false, c.pc2p_mem ? lp.prev_p : lp.prev_p + lp.prev_pc, lp.out_p, lp.p2p, lp.p2p_res);
+      if (!c.stay_sixth) {
+        lp.sem = add_conv(p, pre + "pool_semi", lp.out_p, lp.out_p, 3, 3, 8);
+        p->convs[lp.sem].bn = add_bn(p, pre + "pool_semi_b", lp.out_p);
       }
+      build_pool(pre, lp.out_p, lp);
+      build_stack(pre + "pc2pc", true, lp.out_p + lp.prev_pc, lp.out_pc, lp.pc2pc, lp.pc2pc_res);
     }
     p->layers.push_back(lp);
   }
@@ -265,7 +342,7 @@ static void build_plan(ake_pcn* p) {
   {
     // Tensor-core path: the Pitch2Pitch stack of layer 1 at the train_model.py channel plan (1 + 4 -> 8 -> 8 channels).
     const char* off = getenv("AKE_DISABLE_UMMA");
-    p->umma = !(off && off[0] == '1') && c.num_layers == 2 && nf == 4 && k == 7;
+    p->umma = !(off && off[0] == '1') && c.num_layers == 2 && nf == 4 && k == 7 && !variant;
     if (p->umma) p->umma_convs = p->layers[1].p2p;
   }
   build_head("tonic_classifier", true, p->tonic_head);
@@ -327,6 +404,14 @@ static void launch_conv(const ConvArgs& a, const ConvGeom& g, int co_tile, int B
     if (co_tile == 8) return launch_conv_t<1, 7, 1, 12, 8, 4>(a, B, 8, st);
     if (co_tile == 4) return launch_conv_t<1, 7, 1, 12, 4, 4>(a, B, 8, st);
     if (co_tile == 1) return launch_conv_t<1, 7, 1, 12, 1, 4>(a, B, 8, st);
+  } else if (g.KH == 1 && g.KW == 1 && g.SR == 1) {  // dense layers: 1 x 1 bottleneck on the pitch rows
+    if (co_tile == 8) return launch_conv_t<1, 1, 1, 32, 8, 8>(a, B, 4, st);
+    if (co_tile == 4) return launch_conv_t<1, 1, 1, 32, 4, 8>(a, B, 4, st);
+    if (co_tile == 1) return launch_conv_t<1, 1, 1, 32, 1, 8>(a, B, 4, st);
+  } else if (g.KH == 12 && g.KW == 1 && g.SR == 1) {  // dense layers: equivariant bottleneck (kernel_depth 1)
+    if (co_tile == 8) return launch_conv_t<12, 1, 1, 12, 8, 4>(a, B, 8, st);
+    if (co_tile == 4) return launch_conv_t<12, 1, 1, 12, 4, 4>(a, B, 8, st);
+    if (co_tile == 1) return launch_conv_t<12, 1, 1, 12, 1, 4>(a, B, 8, st);
   } else if (g.KH == 2 && g.KW == 7 && g.SR == 1) {
     if (co_tile == 1) return launch_conv_t<2, 7, 1, 12, 1, 4>(a, B, 8, st);
     if (co_tile == 8) return launch_conv_t<2, 7, 1, 12, 8, 4>(a, B, 8, st);
@@ -387,6 +472,8 @@ struct Fwd {
     double* stats = d_stats + 2 * c.ss_off;
     if (dry) return;
     const int rt = v.R * v.T;
+    if (p->bn_count.size() != p->bns.size()) p->bn_count.assign(p->bns.size(), 0);
+    p->bn_count[c.bn] = (int64_t)B * rt;
     dim3 grid(std::max(1, std::min(64, (int)cdiv64((long long)B * rt, 4096))), c.Cout);
     bn_stats_kernel<<<grid, 256, 0, st>>>(v.p, B, v.C, coff, rt, stats);
     AKE_LAUNCHED();
@@ -398,7 +485,7 @@ struct Fwd {
   }
 
   // One row convolution + BatchNorm + LeakyReLU (+ fused time pool).  Returns nothing; writes `out`.
-  void conv(int id, const View& in0, const View* in1, const ConvGeom& g, View& out, int out_coff, bool act) {
+  void conv(int id, const View& in0, const View* in1, const ConvGeom& g, View& out, int out_coff, int act) {  // act: 0 none, 1 LeakyReLU, 2 ReLU
     const Conv& c = p->convs[id];
     const bool has_bn = c.bn >= 0;
     const bool raw = train && has_bn;
@@ -415,7 +502,7 @@ struct Fwd {
     if (a.c0 + a.c1 != c.Cin) fail(AKE_ERR_INVALID, "internal: conv %d channel mismatch %d+%d vs %d", id, a.c0, a.c1, c.Cin);
     a.w = p->d_packed + c.packed_off, a.cout_pad = c.cout_pad;
     a.scale = scale_of(c, raw), a.shift = shift_of(c, raw);
-    a.act = raw ? 0 : (act ? 1 : 0);
+    a.act = raw ? 0 : act;
     a.out = out.p, a.obs = out.bstride(), a.ocs = (long long)out.R * out.T, a.out_coff = out_coff;
     a.pool_t = raw ? 0 : g.pool_t;
     a.T_store = out.T;
@@ -423,11 +510,11 @@ struct Fwd {
     launch_conv(a, g, co_tile, B, st);
   }
 
-  void affine_act(const Conv& c, View& v, int coff) {
+  void affine_act(const Conv& c, View& v, int coff, int act = 1) {
     if (dry) return;
     const long long n = (long long)B * c.Cout * v.R * v.T;
     affine_act_kernel<<<ew_blocks(n), 256, 0, st>>>(v.p, B, v.C, coff, c.Cout, v.R * v.T, d_ss_train + c.ss_off,
-                                                   d_ss_train + p->n_ss + c.ss_off, 1);
+                                                   d_ss_train + p->n_ss + c.ss_off, act);
     AKE_LAUNCHED();
   }
 
@@ -438,6 +525,76 @@ struct Fwd {
       train_bn(p->convs[id], out, coff);
       affine_act(p->convs[id], out, coff);
     }
+  }
+
+  // A Pitch2Pitch / PitchClass2PitchClass stack on the generic path: conv + BN + LeakyReLU repeated, or (opt.resblock) one such
+  // conv followed by residual blocks x -> LeakyReLU(x + bn2(conv2(LeakyReLU(bn1(conv1(x)))))) (models.py:402-454).
+  View conv_stack(const std::vector<int>& ids, const std::vector<ResPair>& res, const View& in0, const View* in1, const ConvGeom& g,
+                  const std::string& tapbase) {
+    const int Cout = p->convs[ids[0]].Cout;
+    View a = alloc(Cout, g.rows_out, g.T_out), b2 = alloc(Cout, g.rows_out, g.T_out);
+    View cur = a;
+    conv_bn_act(ids[0], in0, in1, g, a, 0);
+    tap(tapbase + "0", a);
+    for (size_t i = 1; i < ids.size(); ++i) {
+      View dst = cur.p == a.p ? b2 : a;
+      conv_bn_act(ids[i], cur, nullptr, g, dst, 0);
+      tap(tapbase + std::to_string(i), dst);
+      cur = dst;
+    }
+    if (!res.empty()) {
+      View mid = alloc(2 * Cout, g.rows_out, g.T_out), z = alloc(Cout, g.rows_out, g.T_out);
+      for (size_t j = 0; j < res.size(); ++j) {
+        const Conv& c2 = p->convs[res[j].c2];
+        conv_bn_act(res[j].c1, cur, nullptr, g, mid, 0);
+        conv(res[j].c2, mid, nullptr, g, z, 0, false);  // eval: BatchNorm folded into the epilogue; train: raw, statistics below
+        if (train) train_bn(c2, z, 0);
+        View dst = cur.p == a.p ? b2 : a;
+        if (!dry) {
+          residual_act_kernel<<<ew_blocks(z.numel(B)), 256, 0, st>>>(z.p, cur.p, B, Cout, z.R * z.T, train ? d_ss_train + c2.ss_off : nullptr,
+                                                                    train ? d_ss_train + p->n_ss + c2.ss_off : nullptr, dst.p);
+          AKE_LAUNCHED();
+        }
+        tap(tapbase + "res" + std::to_string(j), dst);
+        cur = dst;
+      }
+    }
+    return cur;
+  }
+
+  // DenseBlock / DenseBlockEquivariant (models.py:582-648): every layer reads the concatenation of the block's input and all
+  // earlier layers' outputs -- norm1 + LeakyReLU on that concatenation, a 1-wide bottleneck conv, norm2 + ReLU, a k-wide conv
+  // (zero padded on the pitch rows / circular over the pitch classes, zero padded in time) -- and appends `growth` channels.
+  // `init`: the block's input, materialised (C_in, R, T).  Returns the (C_in + layers * growth, R, T) concatenation.
+  View dense_stack(const std::vector<DenseLayer>& dl, const View& init, bool equivariant, const std::string& tapbase) {
+    const int k = p->cfg.kernel_size, g = p->convs[dl[0].conv2].Cout, Tn = init.T, R = init.R;
+    View feat = alloc(init.C + (int)dl.size() * g, R, Tn);
+    if (!dry) {
+      tile_rows_kernel<<<ew_blocks(init.numel(B)), 256, 0, st>>>(init.p, B, init.C, R, R, Tn, feat.p, feat.C, 0);
+      AKE_LAUNCHED();
+    }
+    const ConvGeom g1 = equivariant ? ConvGeom{12, 1, 1, 12, 1, 0, 0, 0, 12, Tn} : ConvGeom{1, 1, 1, R, 0, 0, 0, 0, R, Tn};
+    const ConvGeom g2 = equivariant ? ConvGeom{12, k, 1, 12, 1, 0, k / 2, 0, 12, Tn} : ConvGeom{k, k, 1, R, 0, -(k / 2), k / 2, 0, R, Tn};
+    for (size_t i = 0; i < dl.size(); ++i) {
+      const Conv& n1 = p->convs[dl[i].norm1];
+      const Conv& c1 = p->convs[dl[i].conv1];
+      const int Cn = n1.Cout;
+      View nb = alloc(Cn, R, Tn), mid = alloc(c1.Cout, R, Tn);
+      if (train) train_bn(n1, feat, 0);  // statistics of the first Cn channels of the concatenation
+      if (!dry) {
+        bn_act_copy_kernel<<<ew_blocks(nb.numel(B)), 256, 0, st>>>(feat.p, B, feat.C, Cn, R * Tn, train ? d_ss_train + n1.ss_off : scale_of(n1, false),
+                                                                  train ? d_ss_train + p->n_ss + n1.ss_off : shift_of(n1, false), 1, nb.p);
+        AKE_LAUNCHED();
+      }
+      conv(dl[i].conv1, nb, nullptr, g1, mid, 0, 2);  // eval: norm2 folded into the epilogue, ReLU
+      if (train) {
+        train_bn(c1, mid, 0);
+        affine_act(c1, mid, 0, 2);
+      }
+      conv(dl[i].conv2, mid, nullptr, g2, feat, Cn, 0);  // new features appended behind the concatenation
+    }
+    tap(tapbase, feat);
+    return feat;
   }
 
   void run(const float* mel, float* key_out, float* tonic_out, float* genre_out);
@@ -463,23 +620,52 @@ void Fwd::run(const float* mel, float* key_out, float* tonic_out, float* genre_o
   View pc;    // current pitch-class features
   int Tn = T;
 
-  auto semitone_pool = [&](int L, const View& src, View& dst_cat, int coff) {
-    // pool_semi conv + BN + act (models.py:361-363 / 386-388), then Pitch2PitchClassPool (:368 / :389)
+  const bool v_stay = cfg.stay_sixth != 0, v_mem = cfg.pc2p_mem != 0, v_local = cfg.local != 0;
+  const bool variant = v_stay || v_mem || v_local || cfg.resblock || cfg.p2pc_conv || cfg.denseblock;
+  // Pitch2PitchClass on semitone rows (C, S, Tn): the octave max pool (models.py:82-106) or, with opt.p2pc_conv, the dilated
+  // convolution + BN + LeakyReLU of models.py:108-133.  `raw_of`: train mode, the BN + act of that conv are still to be applied.
+  auto pitch_class_pool = [&](int L, View& semi, const Conv* raw_of, View& dst_cat, int coff) {
+    const LayerPlan& lp = p->layers[L];
+    if (lp.pool_conv < 0) {
+      if (!dry) {
+        octmax_kernel<<<ew_blocks((long long)B * semi.C * 12 * Tn), 256, 0, st>>>(
+            semi.p, B, semi.C, semi.R, Tn, raw_of ? d_ss_train + raw_of->ss_off : nullptr,
+            raw_of ? d_ss_train + p->n_ss + raw_of->ss_off : nullptr, raw_of ? 1 : 0, dst_cat.p, dst_cat.C, coff);
+        AKE_LAUNCHED();
+      }
+      return;
+    }
+    if (raw_of) affine_act(*raw_of, semi, 0);  // the convolution needs the activated map
+    const Conv& cp = p->convs[lp.pool_conv];
+    if (!dry) {
+      p2pc_conv_kernel<<<ew_blocks((long long)B * semi.C * 12 * Tn), 256, 0, st>>>(semi.p, p->d_params + cp.w_off, B, semi.C, semi.R, cp.KH, Tn,
+                                                                                 scale_of(cp, train), shift_of(cp, train), train ? 0 : 1,
+                                                                                 dst_cat.p, dst_cat.C, coff);
+      AKE_LAUNCHED();
+    }
+    if (train) {
+      train_bn(cp, dst_cat, coff);
+      affine_act(cp, dst_cat, coff);
+    }
+  };
+  // pool_semi conv + BN + act (models.py:361-363 / 386-388), then Pitch2PitchClass (:368 / :389).  Returns the semitone map
+  // (activated when `need_act`, e.g. opt.stay_sixth keeps it as the next layer's pitch-wise input).
+  auto semitone_pool = [&](int L, const View& src, View& dst_cat, int coff, bool need_act = false) {
     const LayerPlan& lp = p->layers[L];
     const Conv& c = p->convs[lp.sem];
     View semi = alloc(c.Cout, S, Tn);
     ConvGeom g = g_sem;
     g.T_out = Tn;
     conv(lp.sem, src, nullptr, g, semi, 0, true);
-    const long long n = (long long)B * c.Cout * 12 * Tn;
-    if (train) train_bn(c, semi, 0);
-    if (!dry) {
-      octmax_kernel<<<ew_blocks(n), 256, 0, st>>>(semi.p, B, c.Cout, S, Tn, train ? d_ss_train + c.ss_off : nullptr,
-                                                 train ? d_ss_train + p->n_ss + c.ss_off : nullptr, train ? 1 : 0,
-                                                 dst_cat.p, dst_cat.C, coff);
-      AKE_LAUNCHED();
+    const Conv* raw_of = nullptr;
+    if (train) {
+      train_bn(c, semi, 0);
+      raw_of = &c;
+      if (need_act) affine_act(c, semi, 0), raw_of = nullptr;
     }
-    tap("l" + std::to_string(L) + (train ? ".semi_raw" : ".semi"), semi);
+    pitch_class_pool(L, semi, raw_of, dst_cat, coff);
+    tap("l" + std::to_string(L) + (raw_of ? ".semi_raw" : ".semi"), semi);
+    return semi;
   };
 
   for (int L = 0; L < cfg.num_layers; ++L) {
@@ -488,7 +674,7 @@ void Fwd::run(const float* mel, float* key_out, float* tonic_out, float* genre_o
     View cat;  // input of the pc2pc stack
     if (L == 0) {
       cat = alloc(1, 12, Tn);
-      if (!train && p->convs[lp.sem].Cout == 1) {
+      if (!train && p->convs[lp.sem].Cout == 1 && lp.pool_conv < 0) {
         // eval mode: conv + BN + act + octave pool in one pass over the log-CQT
         const Conv& c = p->convs[lp.sem];
         View semi = alloc(1, S, Tn);
@@ -507,8 +693,10 @@ void Fwd::run(const float* mel, float* key_out, float* tonic_out, float* genre_o
           AKE_LAUNCHED();
         }
         tap("l0.semi", semi);
+        if (v_stay) p_in = semi;  // opt.stay_sixth: the semitone map is the pitch-wise feature from here on (models.py:366-367)
       } else {
-        semitone_pool(0, p_in, cat, 0);
+        View semi = semitone_pool(0, p_in, cat, 0, v_stay);
+        if (v_stay) p_in = semi;
       }
       tap("l0.pool", cat);
     } else {
@@ -657,45 +845,85 @@ void Fwd::run(const float* mel, float* key_out, float* tonic_out, float* genre_o
         Tn = Th;
         umma_pc_ready = true;
       } else {
-      // up_sixth ConvTranspose + BN + act (models.py:372-374); tiled to all pitches by the conv loader (:378)
-      const Conv& cu = p->convs[lp.up];
-      View up = alloc(lp.prev_pc, 36, Tn);
-      if (!dry) {
-        const bool raw = train;
-        const long long n = up.numel(B);
-        upsixth_kernel<<<ew_blocks(n), 256, 0, st>>>(pc.p, p->d_params + cu.w_off, scale_of(cu, raw), shift_of(cu, raw),
-                                                    raw ? 0 : 1, up.p, B, lp.prev_pc, Tn);
-        AKE_LAUNCHED();
+      const int Pl = v_stay ? S : P;  // rows of the pitch-wise features (opt.stay_sixth: semitones)
+      View up;                         // second input of the first conv: rows tiled over the pitches (models.py:135-143)
+      View p_first = p_in;
+      const View* in1 = nullptr;
+      if (!v_stay) {
+        // up_sixth ConvTranspose + BN + act (models.py:372-374); tiled to all pitches by the conv loader (:378)
+        const Conv& cu = p->convs[lp.up];
+        up = alloc(lp.prev_pc, 36, Tn);
+        if (!dry) {
+          const bool raw = train;
+          const long long n = up.numel(B);
+          upsixth_kernel<<<ew_blocks(n), 256, 0, st>>>(pc.p, p->d_params + cu.w_off, scale_of(cu, raw), shift_of(cu, raw),
+                                                      raw ? 0 : 1, up.p, B, lp.prev_pc, Tn);
+          AKE_LAUNCHED();
+        }
+        if (train) {
+          train_bn(cu, up, 0);
+          affine_act(cu, up, 0);
+        }
+        tap(ln + ".up", up);
+        if (v_mem) {
+          // opt.pc2p_mem (models.py:145-166, 376): p += channel-group sums of the up-sampled features; nothing is concatenated
+          if (P % 36 || lp.prev_pc % lp.prev_p) fail(AKE_ERR_UNSUPPORTED, "pc2p_mem needs pitches %% 36 == 0 and %d %% %d == 0", lp.prev_pc, lp.prev_p);
+          View pm = alloc(lp.prev_p, P, Tn);
+          if (!dry) {
+            pc2p_mem_add_kernel<<<ew_blocks(pm.numel(B)), 256, 0, st>>>(p_in.p, up.p, B, lp.prev_p, lp.prev_pc, P, Tn, pm.p);
+            AKE_LAUNCHED();
+          }
+          tap(ln + ".mem", pm);
+          p_first = pm;
+        } else {
+          in1 = &up;
+        }
+      } else {
+        in1 = &pc;  // PitchClass2Pitch(pitches // 3): the 12 pitch-class rows tiled over the semitones (models.py:323, 380)
       }
-      if (train) {
-        train_bn(cu, up, 0);
-        affine_act(cu, up, 0);
-      }
-      tap(ln + ".up", up);
       // Pitch2Pitch stack (models.py:384): circular in pitch and time
-      ConvGeom gp{k, k, 1, P, 1, -(k / 2), k / 2, 1, P, Tn};
-      View a = alloc(lp.out_p, P, Tn), b2 = alloc(lp.out_p, P, Tn);
-      View* src = nullptr;
-      View* dst = &a;
-      for (size_t i = 0; i < lp.p2p.size(); ++i) {
-        if (i == 0) conv_bn_act(lp.p2p[i], p_in, &up, gp, *dst, 0);
-        else conv_bn_act(lp.p2p[i], *src, nullptr, gp, *dst, 0);
-        tap(ln + ".p2p" + std::to_string(i), *dst);
-        src = dst;
-        dst = (dst == &a) ? &b2 : &a;
+      ConvGeom gp{k, k, 1, Pl, 1, -(k / 2), k / 2, 1, Pl, Tn};
+      if (!lp.p2p_dense.empty()) {
+        // opt.denseblock: the block normalises its whole input, so cat[p, tile(up_sixth(pc))] (models.py:378-383) is materialised
+        View p_cat = alloc(lp.prev_p + lp.prev_pc, P, Tn);
+        if (!dry) {
+          tile_rows_kernel<<<ew_blocks((long long)B * lp.prev_p * P * Tn), 256, 0, st>>>(p_in.p, B, lp.prev_p, P, P, Tn, p_cat.p, p_cat.C, 0);
+          AKE_LAUNCHED();
+          tile_rows_kernel<<<ew_blocks((long long)B * lp.prev_pc * P * Tn), 256, 0, st>>>(up.p, B, lp.prev_pc, 36, P, Tn, p_cat.p, p_cat.C, lp.prev_p);
+          AKE_LAUNCHED();
+        }
+        p_feat = dense_stack(lp.p2p_dense, p_cat, false, ln + ".p2p_dense");
+      } else if (variant) {
+        p_feat = conv_stack(lp.p2p, lp.p2p_res, p_first, in1, gp, ln + ".p2p");
+      } else {
+        View a = alloc(lp.out_p, P, Tn), b2 = alloc(lp.out_p, P, Tn);
+        View* src = nullptr;
+        View* dst = &a;
+        for (size_t i = 0; i < lp.p2p.size(); ++i) {
+          if (i == 0) conv_bn_act(lp.p2p[i], p_in, &up, gp, *dst, 0);
+          else conv_bn_act(lp.p2p[i], *src, nullptr, gp, *dst, 0);
+          tap(ln + ".p2p" + std::to_string(i), *dst);
+          src = dst;
+          dst = (dst == &a) ? &b2 : &a;
+        }
+        p_feat = *src;
       }
-      p_feat = *src;
-      semitone_pool(L, p_feat, cat, lp.prev_pc);
+      if (v_stay) pitch_class_pool(L, p_feat, nullptr, cat, lp.prev_pc);  // no pool_semi: p already sits on semitones (models.py:390-391)
+      else semitone_pool(L, p_feat, cat, lp.prev_pc);
       tap(ln + ".cat", cat);
       }
       // time pooling of the pitch-wise features is only needed if another layer follows (models.py:395)
       if (L + 1 < cfg.num_layers) {
-        View pp = alloc(lp.out_p, P, Tn / 2);
-        if (!dry) {
-          timepool_kernel<<<ew_blocks(pp.numel(B)), 256, 0, st>>>(p_feat.p, B, lp.out_p, P, Tn, nullptr, nullptr, 0, pp.p);
-          AKE_LAUNCHED();
+        if (v_local) {
+          p_in = p_feat;  // opt.local: no time pooling (models.py:349, 394)
+        } else {
+          View pp = alloc(lp.out_p, p_feat.R, Tn / 2);
+          if (!dry) {
+            timepool_kernel<<<ew_blocks(pp.numel(B)), 256, 0, st>>>(p_feat.p, B, lp.out_p, p_feat.R, Tn, nullptr, nullptr, 0, pp.p);
+            AKE_LAUNCHED();
+          }
+          p_in = pp;
         }
-        p_in = pp;
       }
     }
     if (umma_pc_ready && L == 1) continue;
@@ -734,6 +962,22 @@ void Fwd::run(const float* mel, float* key_out, float* tonic_out, float* genre_o
         }
       }
       pc = out;
+      continue;
+    }
+    if (variant) {
+      // PitchClass2PitchClass stack (models.py:369 / 393) of the non-default architectures, then MaxPool2d((1, 2)) (:396)
+      View y = !lp.pc2pc_dense.empty() ? dense_stack(lp.pc2pc_dense, cat, true, ln + ".pc2pc_dense")
+                                       : conv_stack(lp.pc2pc, lp.pc2pc_res, cat, nullptr, g_equiv(Tn, true), ln + ".pc2pc");
+      if (L > 0 && !v_local) {
+        View pooled = alloc(lp.out_pc, 12, Tn / 2);
+        if (!dry) {
+          timepool_kernel<<<ew_blocks(pooled.numel(B)), 256, 0, st>>>(y.p, B, lp.out_pc, 12, Tn, nullptr, nullptr, 0, pooled.p);
+          AKE_LAUNCHED();
+        }
+        y = pooled;
+        Tn /= 2;
+      }
+      pc = y;
       continue;
     }
     // PitchClass2PitchClass stack (models.py:369 / 393), zero padding in time
@@ -875,6 +1119,25 @@ void Fwd::run(const float* mel, float* key_out, float* tonic_out, float* genre_o
   if (cfg.genre && !heads_done) genre_f = head(p->genre_head, false, "genre_frames");
   if (tonic_f.T <= 0) fail(AKE_ERR_INVALID, "T=%d is too short: the heads need more than %d frames after pooling", T,
                            (k - 1) * cfg.head_layers);
+  if (v_local) {
+    // opt.local (models.py:720-722, 804-810): MaxPool2d((1, W), stride 1) behind the last conv of the key and tonic heads, no
+    // temporal mean; the outputs stay (B, 1, rows, T') and the reference merely REINTERPRETS them as (B, T', rows)
+    const int W = cfg.frames * cfg.loc_window_size - cfg.head_layers * (k - 1);
+    if (W < 1 || tonic_f.T - W + 1 < 1)
+      fail(AKE_ERR_INVALID, "opt.local: pooling window %d does not fit the %d head frames", W, tonic_f.T);
+    if (!dry) {
+      const int To = tonic_f.T - W + 1;
+      slide_max_kernel<<<ew_blocks((long long)B * 12 * To), 256, 0, st>>>(key_f.p, B, 12, key_f.T, W, 1, key_out);
+      AKE_LAUNCHED();
+      slide_max_kernel<<<ew_blocks((long long)B * 12 * To), 256, 0, st>>>(tonic_f.p, B, 12, tonic_f.T, W, 0, tonic_out);
+      AKE_LAUNCHED();
+      if (cfg.genre) {
+        slide_max_kernel<<<ew_blocks((long long)B * 11 * genre_f.T), 256, 0, st>>>(genre_f.p, B, 11, genre_f.T, 1, 0, genre_out);
+        AKE_LAUNCHED();
+      }
+    }
+    return;
+  }
   if (!dry && !heads_folded) {
     int pool_div = 1;
     for (int i = 0; i < cfg.num_layers - 1; ++i) pool_div *= cfg.time_pool_size;
@@ -918,7 +1181,7 @@ static void upload_params(ake_pcn* p, const float* flat_dev, int64_t n, cudaStre
   }
   AKE_CUDA(cudaMemcpyAsync(p->d_params, flat_dev, sizeof(float) * n, cudaMemcpyDeviceToDevice, st));
   for (const Conv& c : p->convs) {
-    if (!c.transposed) {
+    if (!c.transposed && !c.norm_only) {
       const int nn = c.Cin * c.KH * c.KW * c.cout_pad;
       pack_conv_kernel<<<cdiv(nn, 256), 256, 0, st>>>(p->d_params + c.w_off, c.Cout, c.Cin, c.KH * c.KW, c.cout_pad,
                                                      p->d_packed + c.packed_off);
@@ -926,7 +1189,7 @@ static void upload_params(ake_pcn* p, const float* flat_dev, int64_t n, cudaStre
     }
     const BnSite* bn = c.bn >= 0 ? &p->bns[c.bn] : nullptr;
     fold_bn_kernel<<<cdiv(c.Cout, 64), 64, 0, st>>>(
-        p->d_params + c.b_off, bn ? p->d_params + bn->gamma : nullptr, bn ? p->d_params + bn->beta : nullptr,
+        c.has_bias ? p->d_params + c.b_off : nullptr, bn ? p->d_params + bn->gamma : nullptr, bn ? p->d_params + bn->beta : nullptr,
         bn ? p->d_params + bn->mean : nullptr, bn ? p->d_params + bn->var : nullptr, c.Cout, p->d_ss_eval + c.ss_off,
         p->d_ss_eval + p->n_ss + c.ss_off, p->d_ss_raw + c.ss_off, p->d_ss_raw + p->n_ss + c.ss_off);
     AKE_LAUNCHED();
@@ -1108,6 +1371,19 @@ int ake_pcn_tensor_shape(const ake_pcn* p, int i, int64_t shape4[4]) {
 }
 int64_t ake_pcn_param_floats(const ake_pcn* p) { return p ? p->n_params : AKE_ERR_INVALID; }
 int ake_pcn_bn_channels(const ake_pcn* p) { return p ? p->n_bn_ch : AKE_ERR_INVALID; }
+int ake_pcn_bn_counts(const ake_pcn* p, int64_t* counts_out, int cap) {
+  if (!p || !counts_out || cap < (int)p->bns.size()) return AKE_ERR_INVALID;
+  for (size_t i = 0; i < p->bns.size(); ++i) counts_out[i] = i < p->bn_count.size() ? p->bn_count[i] : 0;
+  return (int)p->bns.size();
+}
+int ake_pcn_local_frames(const ake_pcn* p, int T, int* genre_frames_out) {
+  if (!p || !p->cfg.local || T <= 0) return AKE_ERR_INVALID;
+  const int k = p->cfg.kernel_size;
+  const int Tf = T - p->cfg.head_layers * (k - 1);  // no time pooling with opt.local
+  const int W = p->cfg.frames * p->cfg.loc_window_size - p->cfg.head_layers * (k - 1);
+  if (genre_frames_out) *genre_frames_out = Tf;
+  return (W >= 1 && Tf - W + 1 >= 1) ? Tf - W + 1 : AKE_ERR_INVALID;
+}
 int ake_pcn_get_config(const ake_pcn* p, ake_pcn_config* out) {
   if (!p || !out) return AKE_ERR_INVALID;
   *out = p->cfg;
@@ -1174,6 +1450,7 @@ int ake_pcn_forward_rows_f32(ake_pcn* p, const float* mel_dev, int B, int T, con
                              int32_t* ids_out_dev, void* ws_dev, size_t ws_bytes, void* stream) {
   return guarded([&] {
     if (!p || !mel_dev || !rows_out_dev || !ws_dev) fail(AKE_ERR_INVALID, "null argument");
+    if (p->cfg.local) fail(AKE_ERR_UNSUPPORTED, "opt.local produces per-window outputs: use ake_pcn_forward_f32");
     if (B <= 0 || T <= 0) fail(AKE_ERR_INVALID, "B and T must be positive (got %d, %d)", B, T);
     if (!p->has_params) fail(AKE_ERR_INVALID, "ake_pcn_set_params_f32 has not been called");
     if (current_device() != p->device)

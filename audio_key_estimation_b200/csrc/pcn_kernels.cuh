@@ -51,6 +51,8 @@ struct ConvArgs {
 constexpr int kConvCI = 8;  // input channels staged per shared-memory pass
 
 __device__ __forceinline__ float leaky(float v) { return v > 0.f ? v : kLeakySlope * v; }
+// activation codes of the conv / affine epilogues: 0 none, 1 nn.LeakyReLU(), 2 nn.ReLU() (dense layers, models.py:461-466)
+__device__ __forceinline__ float apply_act(float v, int act) { return act == 1 ? leaky(v) : (act == 2 ? fmaxf(v, 0.f) : v); }
 
 template <int KH, int KW, int SR, int RB, int CO_T, int RT>
 __global__ void __launch_bounds__(256) conv_rows_kernel(const ConvArgs a) {
@@ -179,8 +181,7 @@ __global__ void __launch_bounds__(256) conv_rows_kernel(const ConvArgs a) {
       for (int j = 0; j < RT; ++j) {
         const int t = t0 + tg * RT + j;
         if (t < a.T_out) {
-          float v = fmaf(acc[c][j], s, h);
-          v = a.act ? leaky(v) : v;
+          float v = apply_act(fmaf(acc[c][j], s, h), a.act);
           op[t] = a.accum ? op[t] + v : v;
         }
       }
@@ -190,7 +191,7 @@ __global__ void __launch_bounds__(256) conv_rows_kernel(const ConvArgs a) {
         const int u = (t0 + tg * RT) / 2 + j;
         if (2 * u + 1 < a.T_out) {
           float v0 = fmaf(acc[c][2 * j], s, h), v1 = fmaf(acc[c][2 * j + 1], s, h);
-          if (a.act) v0 = leaky(v0), v1 = leaky(v1);
+          v0 = apply_act(v0, a.act), v1 = apply_act(v1, a.act);
           op[u] = fmaxf(v0, v1);
         }
       }
@@ -431,8 +432,7 @@ __global__ void affine_act_kernel(float* __restrict__ x, int B, int C_total, int
     const int c = q % C;
     const long long b = q / C;
     float* p = x + ((b * C_total + coff + c) * (long long)RT_elems) + e;
-    float v = fmaf(*p, scale[c], shift[c]);
-    *p = act ? leaky(v) : v;
+    *p = apply_act(fmaf(*p, scale[c], shift[c]), act);
   }
 }
 
@@ -451,6 +451,112 @@ __global__ void timepool_kernel(const float* __restrict__ in, int B, int C, int 
       v1 = leaky(fmaf(v1, scale[c], shift[c]));
     }
     out[i] = fmaxf(v0, v1);
+  }
+}
+
+// ---- non-default architecture pieces -----------------------------------------------------------
+// Pitch2PitchClassConv (opt.p2pc_conv, models.py:108-133): Conv2d(C, C, (KS, 1), dilation (12, 1)) over the semitone rows --
+// out[co, c, t] = sum_{ci, o < KS} W[co, ci, o] * x[ci, c + 12 o, t] -- the learned replacement of the octave max pool.  The
+// epilogue y = act(acc * scale + shift) carries the conv bias and eval-mode BatchNorm (train mode: scale 1, shift = bias, no
+// act; BatchNorm follows from the batch statistics).  Writes channels [coff, coff + C) of a (B, C_total, 12, T) tensor.
+__global__ void p2pc_conv_kernel(const float* __restrict__ in, const float* __restrict__ w, int B, int C, int R, int KS, int T,
+                                 const float* __restrict__ scale, const float* __restrict__ shift, int act, float* __restrict__ out,
+                                 int C_total, int coff) {
+  const long long n = (long long)B * C * 12 * T;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int t = i % T;
+    long long q = i / T;
+    const int pc = q % 12;
+    q /= 12;
+    const int co = q % C;
+    const int b = q / C;
+    float acc = 0.f;
+    for (int ci = 0; ci < C; ++ci) {
+      const float* src = in + (((long long)b * C + ci) * R + pc) * T + t;
+      const float* wr = w + ((long long)co * C + ci) * KS;
+      for (int o = 0; o < KS; ++o) acc = fmaf(__ldg(wr + o), __ldg(src + (long long)(12 * o) * T), acc);
+    }
+    const float v = fmaf(acc, scale[co], shift[co]);
+    out[(((long long)b * C_total + coff + co) * 12 + pc) * T + t] = act ? leaky(v) : v;
+  }
+}
+
+// PitchClass2Pitch_MemoryVariant (opt.pc2p_mem, models.py:145-166): the up-sampled pitch-class features (B, Cpc, 36, T) are summed
+// over groups of Cpc / Cp channels and ADDED to the pitch-wise features instead of being concatenated:
+//   out[b, c, p, t] = x[b, c, p, t] + sum_{g < Cpc/Cp} six[b, c * (Cpc/Cp) + g, p / (P/36), t]
+// (the reference reshapes the pitch axis as (36, P/36): row p pairs with table row p / (P/36), NOT p % 36).
+__global__ void pc2p_mem_add_kernel(const float* __restrict__ x, const float* __restrict__ six, int B, int Cp, int Cpc, int P, int T,
+                                    float* __restrict__ out) {
+  const long long n = (long long)B * Cp * P * T;
+  const int G = Cpc / Cp, per = P / 36;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int t = i % T;
+    long long q = i / T;
+    const int pr = q % P;
+    q /= P;
+    const int c = q % Cp;
+    const int b = q / Cp;
+    float acc = 0.f;
+    for (int g = 0; g < G; ++g) acc += __ldg(six + (((long long)b * Cpc + c * G + g) * 36 + pr / per) * T + t);
+    out[i] = __ldg(x + i) + acc;
+  }
+}
+
+// Tail of ResBlock / ResBlockEquivariant (models.py:402-454): out = LeakyReLU(x + bn2(conv2(..))).  `z` holds conv2's output:
+// already normalised (eval: BatchNorm folded into the conv epilogue, scale == NULL) or raw (train: scale / shift from the batch).
+__global__ void residual_act_kernel(const float* __restrict__ z, const float* __restrict__ x, int B, int C, int RT_elems,
+                                    const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ out) {
+  const long long n = (long long)B * C * RT_elems;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (i / RT_elems) % C;
+    float v = __ldg(z + i);
+    if (scale) v = fmaf(v, scale[c], shift[c]);
+    out[i] = leaky(__ldg(x + i) + v);
+  }
+}
+
+// opt.local heads (models.py:720-722): MaxPool2d((1, W), stride 1) along time behind the last head conv, (optionally) the
+// sigmoid of the key head.  in (B, R, Tf) -> out (B, R, Tf - W + 1).  (W = 1: plain copy, the genre head has no pool.)
+__global__ void slide_max_kernel(const float* __restrict__ in, int B, int R, int Tf, int W, int sigmoid, float* __restrict__ out) {
+  const int To = Tf - W + 1;
+  const long long n = (long long)B * R * To;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int t = i % To;
+    const long long line = i / To;
+    const float* src = in + line * Tf + t;
+    float m = -INFINITY;
+    for (int j = 0; j < W; ++j) m = fmaxf(m, __ldg(src + j));
+    out[i] = sigmoid ? 1.f / (1.f + expf(-m)) : m;
+  }
+}
+
+// Dense layers (opt.denseblock, models.py:456-648) normalise the CONCATENATION of everything before them: the first C channels
+// of a (B, C_total_in, RT) tensor -> act(x * scale + shift) as a dense (B, C, RT) tensor (the raw features stay for later layers).
+__global__ void bn_act_copy_kernel(const float* __restrict__ x, int B, int C_total_in, int C, int RT_elems, const float* __restrict__ scale,
+                                   const float* __restrict__ shift, int act, float* __restrict__ out) {
+  const long long n = (long long)B * C * RT_elems;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long e = i % RT_elems;
+    long long q = i / RT_elems;
+    const int c = q % C;
+    const long long b = q / C;
+    out[i] = apply_act(fmaf(__ldg(x + ((b * C_total_in + c) * (long long)RT_elems) + e), scale[c], shift[c]), act);
+  }
+}
+
+// PitchClass2Pitch (models.py:135-143) materialised: rows r of the destination take row r % R_src of the source; written into
+// channels [coff, coff + C) of a (B, C_total, R_dst, T) tensor (R_src == R_dst: a plain channel-slice copy).
+__global__ void tile_rows_kernel(const float* __restrict__ src, int B, int C, int R_src, int R_dst, int T, float* __restrict__ dst,
+                                 int C_total, int coff) {
+  const long long n = (long long)B * C * R_dst * T;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int t = i % T;
+    long long q = i / T;
+    const int r = q % R_dst;
+    q /= R_dst;
+    const int c = q % C;
+    const long long b = q / C;
+    dst[(((b * C_total + coff + c) * R_dst) + r) * (long long)T + t] = __ldg(src + (((b * C + c) * R_src) + r % R_src) * (long long)T + t);
   }
 }
 

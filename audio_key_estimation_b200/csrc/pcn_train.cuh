@@ -78,6 +78,8 @@ void Fwd::run_keep(const float* mel, float* key_out, float* tonic_out, float* ge
   if (cfg.num_layers != 2 || cfg.head_layers != 2)
     fail(AKE_ERR_UNSUPPORTED, "the training step is built for num_layers = 2, head_layers = 2 (train_model.py defaults)");
   if (cfg.max_pool) fail(AKE_ERR_UNSUPPORTED, "the training step does not cover opt.max_pool");
+  if (cfg.resblock || cfg.denseblock || cfg.stay_sixth || cfg.p2pc_conv || cfg.pc2p_mem || cfg.local)
+    fail(AKE_ERR_UNSUPPORTED, "the training step (backward pass) is built for the default architecture; the non-default switches run forward only");
   const int P = cfg.pitches, S = P / 3, k = cfg.kernel_size;
   if (!dry) p->taps.clear();
   d_stats = arena.take<double>(2 * (size_t)p->n_ss);

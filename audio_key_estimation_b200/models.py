@@ -31,7 +31,8 @@ from torch import nn
 from . import _lib
 from ._lib import PcnConfig, check
 
-_UNSUPPORTED_FLAGS = ("resblock", "denseblock", "stay_sixth", "only_semitones", "p2pc_conv", "pc2p_mem", "local")
+# architecture switches of the reference's opt (models.py:260-350, 720-722): all but denseblock / only_semitones are built
+_ARCH_FLAGS = ("resblock", "denseblock", "stay_sixth", "only_semitones", "p2pc_conv", "pc2p_mem", "local")
 
 
 class _Workspace:
@@ -135,9 +136,12 @@ class PitchClassNet(nn.Module):
             kernel_size=self.kernel_size, conv_layers=self.conv_layers, n_filters=self.n_filters,
             head_layers=int(_opt_get(opt, "head_layers", 2)), time_pool_size=int(_opt_get(opt, "time_pool_size", 2)),
             genre=int(bool(_opt_get(opt, "genre", False))), max_pool=int(bool(_opt_get(opt, "max_pool", False))),
-            **{f: int(bool(_opt_get(opt, f, False))) for f in _UNSUPPORTED_FLAGS})
+            frames=int(_opt_get(opt, "frames", 5)), loc_window_size=int(_opt_get(opt, "loc_window_size", 10)),
+            **{f: int(bool(_opt_get(opt, f, False))) for f in _ARCH_FLAGS})
         self._cfg = cfg
         self._genre = bool(cfg.genre)
+        self._local = bool(cfg.local)
+        self._default_arch = not any(getattr(cfg, f) for f in _ARCH_FLAGS)
         lib = _lib.lib()
         handle = C.c_void_p()
         check(lib.ake_pcn_create(C.byref(cfg), C.byref(handle)))  # NotImplementedError for unsupported switches
@@ -224,8 +228,6 @@ class PitchClassNet(nn.Module):
     # ---------------------------------------------------------------------------------- forward
     def forward(self, mel: torch.Tensor, seq_length=None) -> Tuple[torch.Tensor, ...]:
         """models.py:747-817.  mel (B,1,pitches,T); seq_length None | int tensor (B,) | (1,1)."""
-        if _opt_get(self.opt, "local", False):
-            raise NotImplementedError("opt.local sliding-window heads are outside the B200 hot path")
         if not isinstance(mel, torch.Tensor) or mel.dim() != 4 or mel.shape[1] != 1 or mel.shape[2] != self.pitches:
             raise ValueError(f"mel must be (B, 1, {self.pitches}, T), got {tuple(getattr(mel, 'shape', ()))}")
         if not mel.is_cuda:
@@ -258,9 +260,20 @@ class PitchClassNet(nn.Module):
             if ws_bytes == 0:
                 check(_lib.AKE_ERR_INVALID)
             ws = _Workspace.get(device, ws_bytes)
-            key = torch.empty((B, 12), dtype=torch.float32, device=device)
-            tonic = torch.empty((B, 12), dtype=torch.float32, device=device)
-            genre = torch.empty((B, 11), dtype=torch.float32, device=device) if self._genre else None
+            if self._local:
+                # opt.local (models.py:804-810): one value per pitch class and window; the reference hands the (B, 1, rows, T')
+                # maps out RESHAPED (not permuted) to (B, T', rows) -- the same memory, viewed the same way here
+                g_frames = C.c_int(0)
+                Tl = lib.ake_pcn_local_frames(self._plan, T, C.byref(g_frames))
+                if Tl < 0:
+                    raise ValueError(f"T={T} is too short for the sliding-window heads of opt.local")
+                key = torch.empty((B, Tl, 12), dtype=torch.float32, device=device)
+                tonic = torch.empty((B, Tl, 12), dtype=torch.float32, device=device)
+                genre = torch.empty((B, g_frames.value, 11), dtype=torch.float32, device=device) if self._genre else None
+            else:
+                key = torch.empty((B, 12), dtype=torch.float32, device=device)
+                tonic = torch.empty((B, 12), dtype=torch.float32, device=device)
+                genre = torch.empty((B, 11), dtype=torch.float32, device=device) if self._genre else None
             stats = None
             if train:
                 stats = torch.empty(2 * sum(self._bn_channels), dtype=torch.float32, device=device)
@@ -350,11 +363,22 @@ class PitchClassNet(nn.Module):
                 counts.append(B * 12 * (Tn - (k - 1) * (i + 1)))
         return counts
 
+    def _bn_counts_of_last_forward(self):
+        """Elements per channel each BN site normalised over in the last train-mode forward (from the library: the non-default
+        architectures move the sites around)."""
+        n = len(self._bn_sites)
+        arr = (C.c_int64 * n)()
+        got = _lib.lib().ake_pcn_bn_counts(self._plan, arr, n)
+        if got != n:
+            raise RuntimeError("BatchNorm site table mismatch")
+        return [int(v) for v in arr]
+
     @torch.no_grad()
     def _update_running_stats(self, stats: torch.Tensor, B: int, T: int) -> None:
         """nn.BatchNorm2d train-mode buffer update (momentum 0.1, unbiased variance)."""
         off = 0
-        for site, Cn, n in zip(self._bn_sites, self._bn_channels, self._bn_counts(B, T)):
+        counts = self._bn_counts(B, T) if self._default_arch else self._bn_counts_of_last_forward()
+        for site, Cn, n in zip(self._bn_sites, self._bn_channels, counts):
             mean, var = stats[off: off + Cn], stats[off + Cn: off + 2 * Cn]
             off += 2 * Cn
             rm, rv = self._lookup(site + ".running_mean"), self._lookup(site + ".running_var")
@@ -378,6 +402,48 @@ class PitchClassNet(nn.Module):
         if n2 < 0:
             check(int(n2))
         return out
+
+
+class PitchClassNet_Multi(nn.Module):
+    """Drop-in for the reference's ``PitchClassNet_Multi`` (models.py:1118-1189; call sites train_model.py:100-103, eval.py:93-96):
+    two ``PitchClassNet`` (``model1`` on ``mel1``, ``model2`` on ``mel2``, both running the B200 kernels) whose outputs are
+    averaged, or -- with ``opt.linear_reg_multi`` -- combined by the reference's per-class linear regression.  As in the
+    reference the regression coefficients are plain random tensors (``torch.randn``), not parameters: they are not part of the
+    ``state_dict``, whose keys are ``model1.*`` / ``model2.*``.  The 24-value combination is host-side glue on device tensors."""
+
+    def __init__(self, pitches1, pitches2, pitch_classes, num_layers, kernel_size, opt=None, window_size=23, batch_size=4,
+                 train_set=None, val_set=None):
+        super().__init__()
+        if opt is None:
+            raise AttributeError("'NoneType' object has no attribute 'conv_layers'")
+        self.pitches1, self.pitches2, self.pitch_classes = pitches1, pitches2, pitch_classes
+        self.num_layers, self.kernel_size, self.opt = num_layers, kernel_size, opt
+        self.batch_size, self.window_size = batch_size, window_size
+        self.conv_layers, self.n_filters = opt.conv_layers, opt.n_filters
+        self.data = {"train": train_set, "val": val_set}
+        kw = dict(opt=opt, window_size=window_size, batch_size=batch_size, train_set=train_set, val_set=val_set)
+        self.model1 = PitchClassNet(pitches1, pitch_classes, num_layers, kernel_size, **kw)
+        self.model2 = PitchClassNet(pitches2, pitch_classes, num_layers, kernel_size, **kw)
+        self._genre = bool(_opt_get(opt, "genre", False))
+        self._linear = bool(_opt_get(opt, "linear_reg_multi", False))
+        if self._linear:
+            dev = "cuda" if torch.cuda.is_available() else "cpu"
+            self.wk, self.wt = torch.randn(2, 12, device=dev), torch.randn(2, 12, device=dev)
+            self.bk, self.bt = torch.randn(12, device=dev), torch.randn(12, device=dev)
+            if self._genre:
+                self.wg, self.bg = torch.randn(2, 12, device=dev), torch.randn(12, device=dev)
+
+    def forward(self, mel1, mel2, seq_length):
+        x1 = self.model1(mel1, seq_length)
+        x2 = self.model2(mel2, seq_length)
+        if self._linear:
+            # models.py:1169-1175 (note: the key outputs are sigmoid probabilities already and go through another sigmoid)
+            f = lambda w, b, a1, a2: w[0].to(a1) * a1 + w[1].to(a1) * a2 + b.to(a1)  # noqa: E731
+            out = (torch.sigmoid(f(self.wk, self.bk, x1[0], x2[0])), f(self.wt, self.bt, x1[1], x2[1]))
+            if self._genre:
+                out = out + (f(self.wg, self.bg, x1[2], x2[2]),)
+            return out
+        return tuple((a + b) / 2 for a, b in zip(x1, x2))
 
 
 def decode(key_out: torch.Tensor, tonic_out: torch.Tensor, genre_out: Optional[torch.Tensor] = None):

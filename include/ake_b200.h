@@ -71,8 +71,20 @@ typedef struct ake_pcn_config {
   int32_t time_pool_size; /* opt.time_pool_size, default 2 */
   int32_t genre;          /* opt.genre */
   int32_t max_pool;       /* opt.max_pool */
-  /* architecture switches that are NOT on the hot path: any non-zero -> AKE_ERR_UNSUPPORTED */
+  /* non-default architectures, all on the generic fp32 CUDA-core path:
+   *   resblock    Pitch2Pitch / PitchClass2PitchClass stacks = conv + conv_layers residual blocks (models.py:402-454)
+   *   stay_sixth  layers >= 1 work on the semitone rows: no up_sixth / pool_semi (models.py:322-323, 366-367)
+   *   p2pc_conv   Pitch2PitchClassConv (dilated conv + BN + LeakyReLU) instead of the octave max pool (models.py:108-133)
+   *   pc2p_mem    PitchClass2Pitch_MemoryVariant: up-sampled features added to p, not concatenated (models.py:145-166)
+   *   local       sliding-window heads: MaxPool2d((1, frames * loc_window_size - head_layers * (kernel_size - 1)), stride 1)
+   *               behind the key / tonic heads, no time pooling, no temporal mean (models.py:349, 720-722, 804-810);
+   *               outputs per clip are then 12 x T' (11 x T'' for genre) values, see ake_pcn_local_frames
+   *   denseblock  DenseBlock / DenseBlockEquivariant stacks with DenseNet concatenation (models.py:456-648, 266-283); not
+   *               together with resblock / pc2p_mem / stay_sixth (the reference's channel plan does not cover those)
+   *   only_semitones: AKE_ERR_UNSUPPORTED (the reference cannot run it either: models.py:366-367 feeds 96 rows to pools built
+   *               for 32) */
   int32_t resblock, denseblock, stay_sixth, only_semitones, p2pc_conv, pc2p_mem, local;
+  int32_t frames, loc_window_size; /* opt.frames (default 5), opt.loc_window_size (default 10): read by `local` only */
 } ake_pcn_config;
 
 int ake_pcn_create(const ake_pcn_config* cfg, ake_pcn** out);
@@ -103,6 +115,13 @@ int ake_pcn_forward_f32(ake_pcn* plan, const float* mel_dev, int B, int T, const
                         int bn_mode, float* key_out_dev, float* tonic_out_dev, float* genre_out_dev,
                         float* bn_stats_out_dev, void* ws_dev, size_t ws_bytes, void* stream);
 int ake_pcn_bn_channels(const ake_pcn* plan); /* total channels over all BN sites */
+/* Elements per channel every BatchNorm site normalised over in the LAST train-mode forward (state_dict order of the sites):
+ * what the caller needs for the unbiased running-variance update.  Returns the number of sites (negative error). */
+int ake_pcn_bn_counts(const ake_pcn* plan, int64_t* counts_out, int cap);
+/* opt.local: frames per clip of the key / tonic outputs (T') and of the genre output (T'') for an input of T frames; the
+ * forward then writes key_out (B, 12 * T'), tonic_out (B, 12 * T'), genre_out (B, 11 * T''), which the reference views as
+ * (B, T', 12) / (B, T'', 11) by a plain reshape (models.py:806-810).  Negative error code if the plan is not `local`. */
+int ake_pcn_local_frames(const ake_pcn* plan, int T, int* genre_frames_out);
 
 /* The eval-mode forward with its three outputs written side by side as result rows, plus the argmax decode:
  *   rows_out_dev (B, AKE_ROW_FLOATS = 35) fp32 = [12 key probabilities | 12 tonic logits | 11 genre logits (zeros without a

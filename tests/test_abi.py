@@ -4,6 +4,7 @@ import ctypes as C
 
 import pytest
 
+import audio_key_estimation_b200 as ake
 from audio_key_estimation_b200 import _lib
 from audio_key_estimation_b200._lib import PcnConfig
 from conftest import golden_state_dict
@@ -11,7 +12,7 @@ from conftest import golden_state_dict
 
 def _cfg(**kw):
     d = dict(pitches=288, pitch_classes=12, num_layers=2, kernel_size=7, conv_layers=3, n_filters=4, head_layers=2,
-             time_pool_size=2, genre=0, max_pool=0)
+             time_pool_size=2, genre=0, max_pool=0, frames=5, loc_window_size=10)
     d.update(kw)
     return PcnConfig(**d)
 
@@ -52,7 +53,36 @@ def test_plan_tensor_table_matches_reference_state_dict(genre):
         lib.ake_pcn_destroy(h)
 
 
-@pytest.mark.parametrize("flag", ["resblock", "denseblock", "stay_sixth", "only_semitones", "p2pc_conv", "pc2p_mem", "local"])
+def test_non_default_architecture_tensor_tables_match_the_reference():
+    """with every built architecture switch the plan's tensor table == the state_dict of the unmodified reference
+    (names, order, shapes; tests/golden/variants.npz from oracle/make_golden_variants.py), so strict loading works."""
+    import json
+    from conftest import load_golden
+    meta = json.loads(bytes(load_golden("variants.npz")["meta"]).decode())
+    lib = _lib.lib()
+    for group in ("variants", "tables"):
+        for name, entry in meta[group].items():
+            opt = dict(entry["opt"])
+            cfg = _cfg(**{k: int(v) for k, v in opt.items()})
+            h = C.c_void_p()
+            assert lib.ake_pcn_create(C.byref(cfg), C.byref(h)) == 0, (name, lib.ake_last_error())
+            try:
+                want = [(k, tuple(shape)) for k, shape in entry["tensors"] if not k.endswith("num_batches_tracked")]
+                shape4 = (C.c_int64 * 4)()
+                got = []
+                for i in range(lib.ake_pcn_num_tensors(h)):
+                    nd = lib.ake_pcn_tensor_shape(h, i, C.byref(shape4))
+                    got.append((lib.ake_pcn_tensor_name(h, i).decode(), tuple(shape4[:nd])))
+                assert got == want, name
+                assert lib.ake_pcn_workspace_bytes(h, 2, 70, 0) > 0 and lib.ake_pcn_workspace_bytes(h, 2, 70, 1) > 0
+                assert lib.ake_pcn_workspace_bytes(h, 2, 70, 2) == 0   # the backward pass covers the default architecture only
+            finally:
+                lib.ake_pcn_destroy(h)
+            net = ake.PitchClassNet(288, 12, int(opt.get("num_layers", 2)), 7, opt=ake.default_opt(**opt))
+            assert [k for k in net.state_dict()] == [k for k, _ in entry["tensors"]]
+
+
+@pytest.mark.parametrize("flag", ["only_semitones"])
 def test_unsupported_architecture_switches_fail_loudly(flag):
     lib = _lib.lib()
     h = C.c_void_p()

@@ -44,18 +44,36 @@ def _worker(rank, world, port, n_clips, genre, q):
     dist.destroy_process_group()
 
 
+def _run_world2(target, args):
+    """Spawn two ranks; a rendezvous that loses the race for its TCP port (another process grabbed it between _free_port()
+    and the store's bind) is retried on a fresh port."""
+    import queue as _queue
+    ctx = mp.get_context("spawn")
+    last = None
+    for _ in range(3):
+        q = ctx.Queue()
+        port = _free_port()
+        procs = [ctx.Process(target=target, args=(r, 2, port) + tuple(args) + (q,)) for r in range(2)]
+        for p in procs:
+            p.start()
+        results = []
+        try:
+            results = [q.get(timeout=120) for _ in procs]
+        except _queue.Empty as e:
+            last = e
+        for p in procs:
+            p.join(timeout=60)
+            if p.is_alive():
+                p.kill()
+        if len(results) == 2 and all(p.exitcode == 0 for p in procs):
+            return results
+        last = last or RuntimeError(f"exit codes {[p.exitcode for p in procs]}")
+    raise AssertionError(f"world-size-2 run failed three times: {last}")
+
+
 @pytest.mark.parametrize("n_clips,genre", [(8, True), (7, False), (1, True)])
 def test_shard_gather_world2(n_clips, genre):
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, n_clips, genre, q)) for r in range(2)]
-    for p in procs:
-        p.start()
-    results = [q.get(timeout=120) for _ in procs]
-    for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
+    results = _run_world2(_worker, (n_clips, genre))
     ids = torch.arange(n_clips, dtype=torch.float32)
     for rank, table, counters, n_out in results:
         assert table.shape == (n_clips, 35)
@@ -81,15 +99,6 @@ def _grad_worker(rank, world, port, q):
 
 def test_gradient_bucket_allreduce_world2():
     """Config 5's only collective: ONE averaged all-reduce of the flat gradient buffer."""
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    port = _free_port()
-    procs = [ctx.Process(target=_grad_worker, args=(r, 2, port, q)) for r in range(2)]
-    for p in procs:
-        p.start()
-    results = [q.get(timeout=120) for _ in procs]
-    for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
+    results = _run_world2(_grad_worker, ())
     for rank, head, mid in results:
         assert head.tolist() == [6.0, 5.5, 1.5] and mid == 1.5

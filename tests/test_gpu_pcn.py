@@ -218,3 +218,68 @@ def test_tensor_core_and_cuda_core_paths_agree(monkeypatch, fwd_golden):
         sq = torch.randint(max(26, T - 9), T + 1, (B,)).cuda()
         for a, b in zip(fast(xs, sq), slow(xs, sq)):
             assert torch.isfinite(a).all() and (a - b).abs().max().item() <= 2e-5 * max(1.0, b.abs().max().item()), (B, T)
+
+
+VARIANT_NAMES = ("stay_sixth", "p2pc_conv", "pc2p_mem", "resblock", "local", "local_genre", "res_mem_pconv_l3", "stay_sixth_genre_l3",
+                 "denseblock", "dense_l3", "dense_pconv_local_genre")
+
+
+@pytest.mark.parametrize("name", VARIANT_NAMES)
+def test_non_default_architectures_match_reference_golden(name):
+    """opt.stay_sixth / p2pc_conv / pc2p_mem / resblock / local (alone and combined, 2 and 3 layers, with and
+    without the genre head) against the unmodified reference's float64 outputs (oracle/make_golden_variants.py): eval mode with
+    ragged seq_length, train mode with batch statistics, and the BatchNorm running buffers that train-mode forward leaves."""
+    import json
+    from conftest import load_golden
+    g = load_golden("variants.npz")
+    meta = json.loads(bytes(g["meta"]).decode())["variants"][name]
+    opt = ake.default_opt(**meta["opt"])
+    net = ake.PitchClassNet(288, 12, int(meta["opt"].get("num_layers", 2)), 7, opt=opt)
+    # the golden run's weights, regenerated from the tensor table (seed 3); the stored checksum guards the random stream
+    template = {k: torch.zeros(shape, dtype=torch.int64 if k.endswith("num_batches_tracked") else torch.float32) for k, shape in meta["tensors"]}
+    sd = synth.randomise_state_dict(template, seed=3, dtype=torch.float32)
+    chk = np.array([sum(float(v.double().sum()) for v in sd.values() if v.is_floating_point()),
+                    sum(float((v.double() ** 2).sum()) for v in sd.values() if v.is_floating_point())])
+    np.testing.assert_allclose(chk, g[f"{name}.sd_checksum"], rtol=1e-12, err_msg="numpy's random stream differs from the golden run")
+    net.load_state_dict(sd, strict=True)
+    net = net.cuda().eval()
+    x = torch.from_numpy(g["mel"])[:, None].cuda()
+    seq = torch.from_numpy(g["seq_length"]).cuda()
+    names = ("key", "tonic", "genre")[: 3 if meta["opt"].get("genre") else 2]
+    res = net(x, seq)
+    assert len(res) == len(names)
+    for nm, r in zip(names, res):
+        _close(r, g[f"{name}.eval.{nm}"])
+    net.train()
+    with torch.no_grad():
+        res = net(x, seq)
+    for nm, r in zip(names, res):
+        _close(r, g[f"{name}.train.{nm}"], 5e-5)
+    new_sd = net.state_dict()
+    for k in new_sd:
+        if k.endswith("running_mean") or k.endswith("running_var"):
+            _close(new_sd[k], g[f"{name}.buf.{k}"], 5e-5)
+    if not meta["opt"].get("local"):
+        with pytest.raises(NotImplementedError):      # the backward pass is built for the default architecture only
+            net(x, seq)                                # train mode + grad enabled -> kept forward
+
+
+def test_multi_scale_wrapper_matches_reference_golden():
+    """PitchClassNet_Multi (models.py:1118-1189): model1(mel1), model2(mel2), outputs averaged."""
+    import json
+    from conftest import load_golden
+    g = load_golden("variants.npz")
+    meta = json.loads(bytes(g["meta"]).decode())["multi"]
+    net = ake.PitchClassNet_Multi(288, 288, 12, 2, 7, opt=ake.default_opt(**meta["opt"]))
+    assert list(net.state_dict()) == [k for k, _ in meta["tensors"]]
+    template = {k: torch.zeros(shape, dtype=torch.int64 if k.endswith("num_batches_tracked") else torch.float32) for k, shape in meta["tensors"]}
+    sd = synth.randomise_state_dict(template, seed=3, dtype=torch.float32)
+    chk = np.array([sum(float(v.double().sum()) for v in sd.values() if v.is_floating_point()),
+                    sum(float((v.double() ** 2).sum()) for v in sd.values() if v.is_floating_point())])
+    np.testing.assert_allclose(chk, g["multi.sd_checksum"], rtol=1e-12)
+    net.load_state_dict(sd, strict=True)
+    net = net.cuda().eval()
+    res = net(torch.from_numpy(g["mel"])[:, None].cuda(), torch.from_numpy(g["mel2"])[:, None].cuda(), torch.from_numpy(g["seq_length"]).cuda())
+    assert len(res) == 3
+    for nm, r in zip(("key", "tonic", "genre"), res):
+        _close(r, g[f"multi.eval.{nm}"])
