@@ -389,13 +389,16 @@ __device__ __forceinline__ void cas_store_split8(uint8_t* hi_dst, uint8_t* lo_ds
 //   warps 0-7   epilogue 1, two groups of four warps taking alternate tiles: level p+1 accumulators -> fp16 hi/lo planes
 //               (operand of the level p+2 MMAs) and, through a transposition buffer, row-contiguous fp32 stores (only the
 //               rows the filter bank reads when `sparse_hop` > 0)
-//   warps 8-9   epilogue 2: level p+2 accumulators (63 rows) -> fp32 stores
-//   warps 10-21 converter: landed fp32 span -> fp16 hi/lo transposed chunk planes (level-p operand), double buffered
-//   warp 22     loader: one bulk async copy per tile span into a two-stage ring
-//   warps 23-24 MMA issuers (converged, elect.sync), one per level: MMA1(i+2) is issued as soon as epilogue 1 has drained
+//   warps 8-11  epilogue 2: level p+2 accumulators (63 rows) -> fp32 stores.  The level p+2 MMAs run with M = 64 (half the
+//               operand bytes out of shared memory), whose accumulator rows 16 q .. 16 q + 15 sit in lanes 0..15 of TMEM
+//               quadrant q (tools/m64_probe.cu): one warp per quadrant, its upper half-warp idles through the drain
+//   warps 12-23 converter: landed fp32 span -> fp16 hi/lo transposed chunk planes (level-p operand), double buffered
+//   warp 24     loader: one bulk async copy per tile span into a two-stage ring
+//   warps 25-26 MMA issuers (converged, elect.sync), one per level: MMA1(i+2) is issued as soon as epilogue 1 has drained
 //               accumulator i, MMA2(i) as soon as its operand planes exist; two warps because one cannot issue MMAs of
 //               N <= 64 as fast as the tensor pipe executes them
-constexpr int kCasThreads = 800;
+constexpr int kCasThreads = 864;
+constexpr int kCasEpi2Warp = 8, kCasConvWarp = 12, kCasLoadWarp = 24, kCasIssueWarp = 25;
 constexpr int kCasConvThreads = 384;
 constexpr int kCasChunks = kCasP0Rows * 8;                 // 1032 chunks of 8 samples per tile span
 constexpr int kCasSpan = kCasChunks * 8;                   // 8256 input samples per tile
@@ -411,8 +414,6 @@ __global__ void __launch_bounds__(kCasThreads, 1) cascade_umma_kernel(const Casc
   __shared__ __align__(8) uint64_t img_bar, stage_full[2], stage_empty[2], p0_full[2], p0_empty[2], p1_full[2], p1_empty[2], acc1_full[2],
       acc1_empty[2], acc2_full[2], acc2_empty[2];
   __shared__ uint32_t tmem_slot;
-  // Order matters: the level p+2 MMA runs M = 128 over 63 useful rows; its surplus rows read on into the following buffers,
-  // which must hold finite fp16 data (their products only reach accumulator rows that are never read back).
   uint8_t* p1 = smem;                                  // [buf 2][hi | lo][kCasP1Bytes]
   uint8_t* p0 = smem + 4 * kCasP1Bytes;                // [buf 2][hi | lo][kCasP0Bytes]
   uint8_t* img = p0 + 4 * kCasP0Bytes;
@@ -422,7 +423,7 @@ __global__ void __launch_bounds__(kCasThreads, 1) cascade_umma_kernel(const Casc
   const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
   const bool two = a.n_levels == 2;
 
-  if (warp == 23) tmem_alloc(&tmem_slot, 256);
+  if (warp == kCasIssueWarp) tmem_alloc(&tmem_slot, 256);
   if (tid == 0) {
     mbar_init(&img_bar, 1);
     for (int i = 0; i < 2; ++i) {
@@ -430,7 +431,7 @@ __global__ void __launch_bounds__(kCasThreads, 1) cascade_umma_kernel(const Casc
       mbar_init(&p0_full[i], kCasConvThreads), mbar_init(&p0_empty[i], 1);
       mbar_init(&p1_full[i], 128), mbar_init(&p1_empty[i], 1);
       mbar_init(&acc1_full[i], 1), mbar_init(&acc1_empty[i], 128);
-      mbar_init(&acc2_full[i], 1), mbar_init(&acc2_empty[i], 64);
+      mbar_init(&acc2_full[i], 1), mbar_init(&acc2_empty[i], 128);
     }
     mbar_init_fence();
   }
@@ -479,7 +480,7 @@ __global__ void __launch_bounds__(kCasThreads, 1) cascade_umma_kernel(const Casc
     return s;
   };
 
-  if (warp == 22) {
+  if (warp == kCasLoadWarp) {
     // ------------------------------------------------------------------ loader
     if (lane == 0) {
       mbar_arrive_expect_tx(&img_bar, kCasImgBytes);
@@ -513,22 +514,22 @@ __global__ void __launch_bounds__(kCasThreads, 1) cascade_umma_kernel(const Casc
       }
       __syncwarp();
     }
-  } else if (warp >= 23) {
-    // ------------------------------------------------------------------ MMA issuers (warp 23: level p+1, warp 24: level p+2)
+  } else if (warp >= kCasIssueWarp) {
+    // ------------------------------------------------------------------ MMA issuers (first warp: level p+1, second: level p+2)
     int n_my = 0;
     for (int tile = next_tile(blockIdx.x); tile < a.n_tiles; tile = next_tile(tile + gridDim.x)) ++n_my;
     mbar_wait(&img_bar, 0);
     const uint32_t w0 = smem_u32(img);
-    auto issue_level = [&](uint32_t d, uint32_t hi0, uint32_t lo0, uint32_t lbo, uint64_t* bar_acc, uint64_t* bar_planes) {
+    auto issue_level = [&](uint32_t d, uint32_t hi0, uint32_t lo0, uint32_t lbo, uint64_t* bar_acc, uint64_t* bar_planes, uint32_t idesc64,
+                           uint32_t idesc32) {
       const uint64_t a_desc = desc_hi(lbo);
       constexpr uint64_t B_DESC = desc_hi(64 * 16);
-      constexpr uint32_t IDESC64 = idesc_f16(64), IDESC32 = idesc_f16(32);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const uint32_t off = (uint32_t)((2 * j) & 7) * lbo + (j >= 4 ? 16u : 0u);  // chunks 8..15 = planes 0..7, one row on
         const uint64_t bd = make_desc(B_DESC, w0 + (uint32_t)j * 2048);
-        mma_f16(d, make_desc(a_desc, hi0 + off), bd, IDESC64, j ? 1u : 0u);
-        mma_f16(d, make_desc(a_desc, lo0 + off), bd, IDESC32, 1u);
+        mma_f16(d, make_desc(a_desc, hi0 + off), bd, idesc64, j ? 1u : 0u);
+        mma_f16(d, make_desc(a_desc, lo0 + off), bd, idesc32, 1u);
       }
       commit(bar_acc);
       commit(bar_planes);
@@ -540,7 +541,7 @@ __global__ void __launch_bounds__(kCasThreads, 1) cascade_umma_kernel(const Casc
       mbar_wait(&acc1_empty[bf], ph ^ 1);
       fence_after_sync();
       const uint32_t hi0 = smem_u32(p0 + (size_t)bf * 2 * kCasP0Bytes);
-      if (elect_one()) issue_level(tmem + bf * 64, hi0, hi0 + kCasP0Bytes, kCasLBO0, &acc1_full[bf], &p0_empty[bf]);
+      if (elect_one()) issue_level(tmem + bf * 64, hi0, hi0 + kCasP0Bytes, kCasLBO0, &acc1_full[bf], &p0_empty[bf], idesc_f16(64), idesc_f16(32));
       __syncwarp();
     };
     auto issue2 = [&](int i) {
@@ -550,20 +551,22 @@ __global__ void __launch_bounds__(kCasThreads, 1) cascade_umma_kernel(const Casc
       mbar_wait(&acc2_empty[bf], ph ^ 1);
       fence_after_sync();
       const uint32_t hi0 = smem_u32(p1 + (size_t)bf * 2 * kCasP1Bytes);
-      if (elect_one()) issue_level(tmem + 128 + bf * 64, hi0, hi0 + kCasP1Bytes, kCasLBO1, &acc2_full[bf], &p1_empty[bf]);
+      // 63 rows of level p+2 per tile: M = 64 (the operand read is what an MMA of this N costs; M = 128 would read 128 rows)
+      if (elect_one())
+        issue_level(tmem + 128 + bf * 64, hi0, hi0 + kCasP1Bytes, kCasLBO1, &acc2_full[bf], &p1_empty[bf], idesc_f16(64, 64), idesc_f16(32, 64));
       __syncwarp();
     };
     // One warp issues at most one MMA per ~65 cycles (tools/umma_rate.cu: 7 x N=64 MMAs per block take 65 cycles each from
     // one warp, 48 -- the shared-memory operand rate -- from two), so the two levels are issued by two warps: independent
     // streams that only meet through the plane / accumulator barriers.
-    if (warp == 23) {
+    if (warp == kCasIssueWarp) {
       for (int i = 0; i < n_my; ++i) issue1(i);
     } else if (two) {
       for (int i = 0; i < n_my; ++i) issue2(i);
     }
-  } else if (warp >= 10) {
+  } else if (warp >= kCasConvWarp) {
     // ------------------------------------------------------------------ converter: stage -> level-p operand planes
-    const int ct = tid - 10 * 32;
+    const int ct = tid - kCasConvWarp * 32;
     int i = 0;
     for (int tile = next_tile(blockIdx.x); tile < a.n_tiles; tile = next_tile(tile + gridDim.x), ++i) {
       const int bf = i & 1;
@@ -715,9 +718,12 @@ __global__ void __launch_bounds__(kCasThreads, 1) cascade_umma_kernel(const Casc
       asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");  // the transposition buffer is reused by the group's next tile
     }
   } else if (two) {
-    // ------------------------------------------------------------------ epilogue 2 (warps 8, 9): rows 0..62 of level p+2
-    const int row = tid - 256;  // accumulator lane (warp 8: lanes 0..31, warp 9: 32..63)
-    const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16) + 128;
+    // ------------------------------------------------------------------ epilogue 2 (warps 8-11): rows 0..62 of level p+2
+    const int quad = warp - kCasEpi2Warp;       // TMEM quadrant; rows 16 quad .. + 15 of the M = 64 accumulator in its lanes 0..15
+    const int row = 16 * quad + (lane & 15);
+    const bool has_row = lane < 16;
+    const int tid2 = tid - kCasEpi2Warp * 32;   // 0..127
+    const uint32_t lane_base = tmem + ((uint32_t)(quad * 32) << 16) + 128;
     const uint64_t inv2 = f2_pack(kInv2, kInv2);
     int i = 0;
     for (int tile = next_tile(blockIdx.x); tile < a.n_tiles; tile = next_tile(tile + gridDim.x), ++i) {
@@ -755,7 +761,7 @@ __global__ void __launch_bounds__(kCasThreads, 1) cascade_umma_kernel(const Casc
           o[n] = f2_pack(2 * n < zhi ? x0 : 0.f, 2 * n + 1 < zhi ? x1 : 0.f);
         }
       }
-      if (row < kCasRows2) {
+      if (has_row && row < kCasRows2) {
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           float4 v;
@@ -764,22 +770,22 @@ __global__ void __launch_bounds__(kCasThreads, 1) cascade_umma_kernel(const Casc
           *reinterpret_cast<float4*>(tbuf2 + row * kCasTPitch + 4 * q) = v;
         }
       }
-      asm volatile("bar.sync 3, 64;" ::: "memory");
+      asm volatile("bar.sync 3, 128;" ::: "memory");
       {
-        // 63 rows x 8 float4s; thread `row` stores float4 (row & 7) of the rows (row >> 3) + 8 k
-        float* dst = a.out2 + ((long long)b * a.stride2 + (o_lo2 + 32 * (row >> 3) + 4 * (row & 7)));
-        const float* src = tbuf2 + (row >> 3) * kCasTPitch + 4 * (row & 7);
+        // 63 rows x 8 float4s; thread tid2 stores float4 (tid2 & 7) of the rows (tid2 >> 3) + 16 k
+        float* dst = a.out2 + ((long long)b * a.stride2 + (o_lo2 + 32 * (tid2 >> 3) + 4 * (tid2 & 7)));
+        const float* src = tbuf2 + (tid2 >> 3) * kCasTPitch + 4 * (tid2 & 7);
         const int r_lim = min(kCasRows2, max(0, (n2 - o_lo2 + 31) >> 5));  // rows with 32 r < n2 - o_lo2 exist
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-          if ((row >> 3) + 8 * k < r_lim) *reinterpret_cast<float4*>(dst + 256 * k) = *reinterpret_cast<const float4*>(src + 8 * k * kCasTPitch);
+        for (int k = 0; k < 4; ++k)
+          if ((tid2 >> 3) + 16 * k < r_lim) *reinterpret_cast<float4*>(dst + 512 * k) = *reinterpret_cast<const float4*>(src + 16 * k * kCasTPitch);
       }
-      asm volatile("bar.sync 3, 64;" ::: "memory");  // the transposition buffer is reused by the next tile
+      asm volatile("bar.sync 3, 128;" ::: "memory");  // the transposition buffer is reused by the next tile
     }
   }
   fence_before_sync();
   __syncthreads();
-  if (warp == 23) tmem_dealloc(tmem, 256);
+  if (warp == kCasIssueWarp) tmem_dealloc(tmem, 256);
 }
 
 // ---- tensor-core filter bank (tcgen05): one CTA = 128 frames of one octave x all filters x all of K ----------------

@@ -789,7 +789,10 @@ void Fwd::run(const float* mel, float* key_out, float* tonic_out, float* genre_o
           if (p->d_wimg_semi && P % 36 == 0 && n_oct <= kSemiMaxOct) {
             // tensor cores: all octaves of a (clip, pitch class, time tile) accumulate side by side in TMEM
             // tile width: TB + 2 <= 128 anchors, and kSemiBufs tiles of 3 n_oct rows (hi + lo) must fit in shared memory
-            const int tb_cap = std::min(kSemiMaxTB, (6400 / kSemiBufs) / (3 * n_oct) - 2);
+            // 227 KB of shared memory: kSemiBufs tile buffers of 3 n_oct (TB + 2) + 136 positions (hi + lo), the weights and the
+            // hand-over buffers (semi_smem_bytes), ~1 KB of static shared memory
+            const int pos_cap = (int)((232448 - 1280 - (long long)semi_smem_bytes(n_oct, 0) + (long long)kSemiBufs * 2 * 136 * 16) / (kSemiBufs * 32)) - 136;
+            const int tb_cap = std::min(kSemiMaxTB, pos_cap / (3 * n_oct) - 2);
             const int n_tt = cdiv(Tn, tb_cap), TBs = cdiv(Tn, n_tt);
             SemiUmmaArgs sa{x[cur][0], x[cur][1], p->d_wimg_semi, scale_of(cs, false), shift_of(cs, false), pc.p, e[0][0], e[0][1],
                             B, P, Tn, Wd, n_oct, TBs, n_tt, B * 12 * n_tt};

@@ -516,10 +516,14 @@ __global__ void __launch_bounds__(128) semitone_pool_chunks_kernel(const SemiArg
 // {W_hi 8, W_lo 8}; the accumulators of ALL octaves of a work item (b, c, time tile) sit side by side in TMEM (48 columns
 // each), and the epilogue re-aligns the phases, applies BN + LeakyReLU and takes the octave max in registers.  The kernel
 // streams the last Pitch2Pitch output once (HBM-bound) instead of spending 4608 FFMAs per output on it.
-// Persistent CTA per SM: warps 0-3 epilogue (thread = anchor = frame), warp 4 loader (double-buffered tiles), warp 5 issuer.
+// Persistent CTA per SM: 4 epilogue groups of 4 warps (thread = anchor = frame; group g drains the octaves g, g + 4, ... of
+// every item, so the ~1400-instruction drain of an item is four independent chains instead of one; the groups' octave maxima
+// meet in shared memory), then the loader warp (triple-buffered tiles) and the MMA-issuer warp.
 constexpr int kSemiMaxTB = 126;     // frames per tile: TB + 2 <= 128 anchors
 constexpr int kSemiMaxOct = 10;     // 48 TMEM columns per octave
-constexpr int kSemiThreads = 192;
+constexpr int kSemiGroups = 4;      // epilogue groups
+constexpr int kSemiOctPerGroup = (kSemiMaxOct + kSemiGroups - 1) / kSemiGroups;
+constexpr int kSemiThreads = 32 * (4 * kSemiGroups + 2);
 constexpr int kSemiBufs = 3;        // tile buffers: two loads in flight while one tile is multiplied (a single 64 KB load in flight per SM
                                     // runs at its ~3 us loaded latency, far below the HBM rate)
 constexpr uint32_t kSemiWBytes = 3 * 2 * 48 * 16;
@@ -552,7 +556,8 @@ struct SemiUmmaArgs {
 
 __host__ __device__ inline uint32_t semi_plane_positions(int n_oct, int Wt) { return (uint32_t)(3 * n_oct * Wt + 136); }
 __host__ __device__ inline size_t semi_smem_bytes(int n_oct, int Wt) {
-  return (size_t)kSemiBufs * 2 * semi_plane_positions(n_oct, Wt) * 16 + kSemiWBytes + (size_t)kSemiMaxOct * 3 * 3 * 32;
+  return (size_t)kSemiBufs * 2 * semi_plane_positions(n_oct, Wt) * 16 + kSemiWBytes + (size_t)kSemiMaxOct * 3 * 3 * 32 +
+         (size_t)kSemiGroups * 128 * 32;  // + the octave maxima the groups exchange
 }
 
 __global__ void __launch_bounds__(kSemiThreads, 1) semi_umma_kernel(const SemiUmmaArgs a) {
@@ -567,6 +572,8 @@ __global__ void __launch_bounds__(kSemiThreads, 1) semi_umma_kernel(const SemiUm
   const uint32_t plane = semi_plane_positions(n_oct, Wt) * 16;  // a tile buffer holds [hi][lo]
   uint8_t* s_w = smem + 2 * kSemiBufs * plane;
   float4* pub = reinterpret_cast<float4*>(s_w + kSemiWBytes);    // [octave][warp 1..3][slot 3 = (f 1: lane 0), (f 2: lanes 0, 1)][8 floats]
+  float4* s_best = pub + kSemiMaxOct * 3 * 3 * 2;                // [group][thread 128][8 floats]
+  constexpr int G = kSemiGroups, LOADER = 4 * G, ISSUER = 4 * G + 1;
   const int per_clip = 12 * a.n_ttiles;
   const uint32_t pc_magic = 0xFFFFFFFFu / (uint32_t)per_clip + 1, tt_magic = 0xFFFFFFFFu / (uint32_t)a.n_ttiles + 1;
   auto decode = [&](int item, int& b, int& c, int& t0) {
@@ -576,11 +583,11 @@ __global__ void __launch_bounds__(kSemiThreads, 1) semi_umma_kernel(const SemiUm
     t0 = (r - c * a.n_ttiles) * a.TB;
   };
 
-  if (warp == 5) tmem_alloc(&tmem_slot, 512);
+  if (warp == ISSUER) tmem_alloc(&tmem_slot, 512);
   if (threadIdx.x == 0) {
     mbar_init(&w_bar, 1);
     for (int i = 0; i < kSemiBufs; ++i) mbar_init(&full_bar[i], 1), mbar_init(&empty_bar[i], 1);
-    mbar_init(&acc_full, 1), mbar_init(&acc_empty, 128);
+    mbar_init(&acc_full, 1), mbar_init(&acc_empty, 128 * G);
     mbar_init_fence();
   }
   if (threadIdx.x < 8) s_scale[threadIdx.x] = a.scale[threadIdx.x] * (1.f / kWScale), s_shift[threadIdx.x] = a.shift[threadIdx.x];
@@ -591,7 +598,7 @@ __global__ void __launch_bounds__(kSemiThreads, 1) semi_umma_kernel(const SemiUm
   fence_after_sync();
   const uint32_t tmem = tmem_slot;
 
-  if (warp == 4) {
+  if (warp == LOADER) {
     // ------------------------------------------------------------ loader: rows 3 (c + 12 o) + dp of the halo'd planes
     if (lane == 0) {
       mbar_arrive_expect_tx(&w_bar, kSemiWBytes);
@@ -615,7 +622,7 @@ __global__ void __launch_bounds__(kSemiThreads, 1) semi_umma_kernel(const SemiUm
         bulk_g2s(dst + plane + (size_t)r * Wt * 16, a.in_lo + src, row_bytes, &full_bar[s]);
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == ISSUER) {
     // ------------------------------------------------------------ MMA issuer (converged warp, one elected lane issues)
     const uint64_t A_DESC = desc_hi(plane);        // chunk 1 = the x_lo plane at the same position
     constexpr uint64_t B_DESC = desc_hi(48 * 16);  // chunk stride: 48 rows x 16 B
@@ -642,20 +649,30 @@ __global__ void __launch_bounds__(kSemiThreads, 1) semi_umma_kernel(const SemiUm
       __syncwarp();
     }
   } else {
-    // ------------------------------------------------------------ epilogue: thread = TMEM lane = frame t0 + tid
-    const int tid = threadIdx.x, wq = warp;
+    // ------------------------------------------------------------ epilogue: thread = TMEM lane = frame t0 + tid; group grp owns
+    // the octaves grp, grp + G, ...
+    const int grp = warp >> 2, wq = warp & 3, tid = threadIdx.x & 127;
     const uint32_t acc = tmem + ((uint32_t)(wq * 32) << 16);
     int k = 0;
     for (int item = blockIdx.x; item < a.n_items; item += gridDim.x, ++k) {
       int b, c, t0;
       decode(item, b, c, t0);
+      // the previous layer's pitch-class features of this frame (channels 0..3 of the output): loaded before the wait so that
+      // their latency hides behind the MMAs
+      const int t = t0 + tid;
+      float pcv[4] = {0.f, 0.f, 0.f, 0.f};
+      if ((grp & 1) == 0 && tid < a.TB && t < a.T) {
+#pragma unroll
+        for (int ci = 0; ci < 4; ++ci) pcv[ci] = __ldg(a.pc_prev + (((long long)b * 4 + ci) * 12 + c) * a.T + t);
+      }
       mbar_wait_relaxed(&acc_full, k & 1);
       fence_after_sync();
       // pass 1: per octave, D_dt = columns [16 dt, 16 dt + 8) + [16 dt + 8, 16 dt + 16); s = D_0[a] + D_1[a + 1] + D_2[a + 2] with
       // the in-warp part by shuffles; lanes 0, 1 of warps 1..3 publish what lanes 30, 31 of the previous warp still need
-      uint64_t sacc[kSemiMaxOct][4];
+      uint64_t sacc[kSemiOctPerGroup][4];
 #pragma unroll
-      for (int o = 0; o < kSemiMaxOct; ++o) {
+      for (int oi = 0; oi < kSemiOctPerGroup; ++oi) {
+        const int o = grp + G * oi;
         if (o < n_oct) {
           uint32_t v0[16], v1[16], v2[16];
           tmem_ld16_issue(acc + o * 48, v0);
@@ -664,8 +681,8 @@ __global__ void __launch_bounds__(kSemiThreads, 1) semi_umma_kernel(const SemiUm
           tmem_ld_wait16(v0), tmem_ld_wait16(v1), tmem_ld_wait16(v2);
 #pragma unroll
           for (int e = 0; e < 4; ++e)
-            sacc[o][e] = f2_add(f2_pack(__uint_as_float(v0[2 * e]), __uint_as_float(v0[2 * e + 1])),
-                                f2_pack(__uint_as_float(v0[8 + 2 * e]), __uint_as_float(v0[9 + 2 * e])));
+            sacc[oi][e] = f2_add(f2_pack(__uint_as_float(v0[2 * e]), __uint_as_float(v0[2 * e + 1])),
+                                 f2_pack(__uint_as_float(v0[8 + 2 * e]), __uint_as_float(v0[9 + 2 * e])));
 #pragma unroll
           for (int f = 1; f < 3; ++f) {
             const uint32_t(&v)[16] = f == 1 ? v1 : v2;
@@ -681,19 +698,20 @@ __global__ void __launch_bounds__(kSemiThreads, 1) semi_umma_kernel(const SemiUm
             const float mk = (lane + f < 32) ? 1.f : 0.f;  // masked FMA = predicated add (see p2p_umma_kernel)
             const uint64_t mk2 = f2_pack(mk, mk);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) sacc[o][e] = f2_fma(f2_pack(x[2 * e], x[2 * e + 1]), mk2, sacc[o][e]);
+            for (int e = 0; e < 4; ++e) sacc[oi][e] = f2_fma(f2_pack(x[2 * e], x[2 * e + 1]), mk2, sacc[oi][e]);
           }
         }
       }
       fence_before_sync();
-      mbar_arrive(&acc_empty);  // accumulators drained: the issuer may start the next item
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_arrive(&acc_empty);  // this group's accumulators drained: the issuer may start the next item once every group has
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
       // pass 2: the cross-warp contributions (ascending tap order on every lane), BN + LeakyReLU, octave max
       float best[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) best[e] = -INFINITY;
 #pragma unroll
-      for (int o = 0; o < kSemiMaxOct; ++o) {
+      for (int oi = 0; oi < kSemiOctPerGroup; ++oi) {
+        const int o = grp + G * oi;
         if (o < n_oct) {
           if (wq < 3 && lane >= 30) {
 #pragma unroll
@@ -703,36 +721,48 @@ __global__ void __launch_bounds__(kSemiThreads, 1) semi_umma_kernel(const SemiUm
               const float4 x0 = src[0], x1 = src[1];
               const float mk = take ? 1.f : 0.f;
               const uint64_t mk2 = f2_pack(mk, mk);
-              sacc[o][0] = f2_fma(f2_pack(x0.x, x0.y), mk2, sacc[o][0]), sacc[o][1] = f2_fma(f2_pack(x0.z, x0.w), mk2, sacc[o][1]);
-              sacc[o][2] = f2_fma(f2_pack(x1.x, x1.y), mk2, sacc[o][2]), sacc[o][3] = f2_fma(f2_pack(x1.z, x1.w), mk2, sacc[o][3]);
+              sacc[oi][0] = f2_fma(f2_pack(x0.x, x0.y), mk2, sacc[oi][0]), sacc[oi][1] = f2_fma(f2_pack(x0.z, x0.w), mk2, sacc[oi][1]);
+              sacc[oi][2] = f2_fma(f2_pack(x1.x, x1.y), mk2, sacc[oi][2]), sacc[oi][3] = f2_fma(f2_pack(x1.z, x1.w), mk2, sacc[oi][3]);
             }
           }
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             float y0, y1;
-            f2_unpack(f2_fma(sacc[o][e], f2_pack(s_scale[2 * e], s_scale[2 * e + 1]), f2_pack(s_shift[2 * e], s_shift[2 * e + 1])), y0, y1);
+            f2_unpack(f2_fma(sacc[oi][e], f2_pack(s_scale[2 * e], s_scale[2 * e + 1]), f2_pack(s_shift[2 * e], s_shift[2 * e + 1])), y0, y1);
             best[2 * e] = fmaxf(best[2 * e], fmaxf(y0, kLeakySlope * y0)), best[2 * e + 1] = fmaxf(best[2 * e + 1], fmaxf(y1, kLeakySlope * y1));
           }
         }
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");  // the hand-over buffer is reused by the next item
-      const int t = t0 + tid;
+      // every group publishes the maxima of its octaves and reads the others' (max is exact and order-free), then stores one
+      // quarter of the item: group 0 / 1 the two channel groups of the home row, groups 2 / 3 their wrap-row copies
+      {
+        float4* d = s_best + (grp * 128 + tid) * 2;
+        d[0] = make_float4(best[0], best[1], best[2], best[3]), d[1] = make_float4(best[4], best[5], best[6], best[7]);
+      }
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + G), "r"(128 * G) : "memory");
+#pragma unroll
+      for (int g2 = 1; g2 < G; ++g2) {
+        const int og = (grp + g2) & (G - 1);
+        const float4 b0 = s_best[(og * 128 + tid) * 2], b1 = s_best[(og * 128 + tid) * 2 + 1];
+        best[0] = fmaxf(best[0], b0.x), best[1] = fmaxf(best[1], b0.y), best[2] = fmaxf(best[2], b0.z), best[3] = fmaxf(best[3], b0.w);
+        best[4] = fmaxf(best[4], b1.x), best[5] = fmaxf(best[5], b1.y), best[6] = fmaxf(best[6], b1.z), best[7] = fmaxf(best[7], b1.w);
+      }
+      asm volatile("bar.sync %0, %1;" ::"r"(2 + G), "r"(128 * G) : "memory");  // s_best read: the next item may overwrite it
       const long long row0 = (((long long)b * 2 + 0) * 23 + c) * a.Wd, row1 = (((long long)b * 2 + 1) * 23 + c) * a.Wd;
       const long long wr = (long long)12 * a.Wd * 8;
-      if (tid < a.TB && t < a.T) {
-        float g0[8], g1[8];
+      if (tid < a.TB && t < a.T && (grp < 2 || c < 11)) {  // wrap rows 12..22 = rows 0..10 (models.py:27-28)
+        float gv[8];
+        if ((grp & 1) == 0) {
 #pragma unroll
-        for (int ci = 0; ci < 4; ++ci) g0[ci] = __ldg(a.pc_prev + (((long long)b * 4 + ci) * 12 + c) * a.T + t);
+          for (int e = 0; e < 4; ++e) gv[e] = pcv[e], gv[4 + e] = best[e];
+        } else {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) g0[4 + e] = best[e], g1[e] = best[4 + e], g1[4 + e] = 0.f;
-        const long long q0 = (row0 + t + 3) * 8, q1 = (row1 + t + 3) * 8;
-        store_split8(a.out_hi + q0, a.out_lo + q0, g0);
-        store_split8(a.out_hi + q1, a.out_lo + q1, g1);
-        if (c < 11) {  // wrap rows 12..22 = rows 0..10 (models.py:27-28)
-          store_split8(a.out_hi + q0 + wr, a.out_lo + q0 + wr, g0);
-          store_split8(a.out_hi + q1 + wr, a.out_lo + q1 + wr, g1);
+          for (int e = 0; e < 4; ++e) gv[e] = best[4 + e], gv[4 + e] = 0.f;
         }
+        const long long q = (((grp & 1) ? row1 : row0) + t + 3) * 8 + (grp >= 2 ? wr : 0);
+        store_split8(a.out_hi + q, a.out_lo + q, gv);
       }
+      if (grp > 0) continue;
       if (t0 == 0 && tid < 6) {
         // zero halo columns 0..2 and T + 3..T + 5 (the "same" padding of the equivariant convs, models.py:45-47)
         const int col = tid < 3 ? tid : a.T + tid;
@@ -747,7 +777,7 @@ __global__ void __launch_bounds__(kSemiThreads, 1) semi_umma_kernel(const SemiUm
   }
   fence_before_sync();
   __syncthreads();
-  if (warp == 5) tmem_dealloc(tmem, 512);
+  if (warp == ISSUER) tmem_dealloc(tmem, 512);
 }
 
 // ---- equivariant pitch-class convolution (models.py:22-51) on tensor cores -----------------------------------------
