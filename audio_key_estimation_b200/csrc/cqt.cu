@@ -392,8 +392,11 @@ __device__ __forceinline__ void cas_store_split8(uint8_t* hi_dst, uint8_t* lo_ds
 //   warps 8-11  epilogue 2: level p+2 accumulators (63 rows) -> fp32 stores.  The level p+2 MMAs run with M = 64 (half the
 //               operand bytes out of shared memory), whose accumulator rows 16 q .. 16 q + 15 sit in lanes 0..15 of TMEM
 //               quadrant q (tools/m64_probe.cu): one warp per quadrant, its upper half-warp idles through the drain
-//   warps 12-23 converter: landed fp32 span -> fp16 hi/lo transposed chunk planes (level-p operand), double buffered
-//   warp 24     loader: one bulk async copy per tile span into a two-stage ring
+//   warps 12-23 converter: landed fp32 span -> fp16 hi/lo transposed chunk planes (level-p operand) IN PLACE: a span of 8256 fp32
+//               samples and its hi + lo planes are both 33,024 bytes, so a ring buffer is landing area first and MMA operand
+//               afterwards (every converter thread holds its samples in registers across a barrier before the first write)
+//   warp 24     loader: one bulk async copy per tile span into the ring (kCasRing buffers: all but the one being multiplied can
+//               be in flight)
 //   warps 25-26 MMA issuers (converged, elect.sync), one per level: MMA1(i+2) is issued as soon as epilogue 1 has drained
 //               accumulator i, MMA2(i) as soon as its operand planes exist; two warps because one cannot issue MMAs of
 //               N <= 64 as fast as the tensor pipe executes them
@@ -406,36 +409,36 @@ constexpr uint32_t kCasStageBytes = kCasSpan * 4;          // fp32 landing buffe
 constexpr int kCasTPitch = 36;                             // floats per row of the store-transposition buffers (144 B: conflict-free)
 constexpr uint32_t kCasT1Bytes = 128 * kCasTPitch * 4;     // level p+1 outputs on their way to coalesced global stores
 constexpr uint32_t kCasT2Bytes = 64 * kCasTPitch * 4;      // level p+2
-constexpr uint32_t kCasSmemTotal = 2 * 2 * kCasP1Bytes + 2 * 2 * kCasP0Bytes + kCasImgBytes + 2 * kCasStageBytes + 2 * kCasT1Bytes + kCasT2Bytes;
+constexpr int kCasRing = 4;                                // ring buffers: landing area, then level-p operand planes (same bytes)
+static_assert(kCasStageBytes == 2 * kCasP0Bytes, "a landed span and its hi + lo planes must be the same size (in-place conversion)");
+constexpr uint32_t kCasSmemTotal = 2 * 2 * kCasP1Bytes + kCasRing * kCasStageBytes + kCasImgBytes + 2 * kCasT1Bytes + kCasT2Bytes;
 
 __global__ void __launch_bounds__(kCasThreads, 1) cascade_umma_kernel(const CascadeArgs a) {
   using namespace umma;
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ __align__(8) uint64_t img_bar, stage_full[2], stage_empty[2], p0_full[2], p0_empty[2], p1_full[2], p1_empty[2], acc1_full[2],
+  __shared__ __align__(8) uint64_t img_bar, stage_full[kCasRing], p0_full[kCasRing], p0_empty[kCasRing], p1_full[2], p1_empty[2], acc1_full[2],
       acc1_empty[2], acc2_full[2], acc2_empty[2];
   __shared__ uint32_t tmem_slot;
   uint8_t* p1 = smem;                                  // [buf 2][hi | lo][kCasP1Bytes]
-  uint8_t* p0 = smem + 4 * kCasP1Bytes;                // [buf 2][hi | lo][kCasP0Bytes]
-  uint8_t* img = p0 + 4 * kCasP0Bytes;
-  float* stage = reinterpret_cast<float*>(img + kCasImgBytes);  // [2][kCasSpan]
-  float* tbuf1 = reinterpret_cast<float*>(img + kCasImgBytes + 2 * kCasStageBytes);  // [group 2]
-  float* tbuf2 = reinterpret_cast<float*>(img + kCasImgBytes + 2 * kCasStageBytes + 2 * kCasT1Bytes);
+  uint8_t* ring = smem + 4 * kCasP1Bytes;              // [kCasRing][kCasStageBytes]: fp32 span, then [hi | lo][kCasP0Bytes] in place
+  uint8_t* img = ring + kCasRing * kCasStageBytes;
+  float* tbuf1 = reinterpret_cast<float*>(img + kCasImgBytes);  // [group 2]
+  float* tbuf2 = reinterpret_cast<float*>(img + kCasImgBytes + 2 * kCasT1Bytes);
   const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
   const bool two = a.n_levels == 2;
 
   if (warp == kCasIssueWarp) tmem_alloc(&tmem_slot, 256);
   if (tid == 0) {
     mbar_init(&img_bar, 1);
+    for (int i = 0; i < kCasRing; ++i) mbar_init(&stage_full[i], 1), mbar_init(&p0_full[i], kCasConvThreads), mbar_init(&p0_empty[i], 1);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&stage_full[i], 1), mbar_init(&stage_empty[i], kCasConvThreads);
-      mbar_init(&p0_full[i], kCasConvThreads), mbar_init(&p0_empty[i], 1);
       mbar_init(&p1_full[i], 128), mbar_init(&p1_empty[i], 1);
       mbar_init(&acc1_full[i], 1), mbar_init(&acc1_empty[i], 128);
       mbar_init(&acc2_full[i], 1), mbar_init(&acc2_empty[i], 128);
     }
     mbar_init_fence();
   }
-  for (uint32_t i = tid; i < (4 * kCasP1Bytes + 4 * kCasP0Bytes) / 16; i += kCasThreads) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  for (uint32_t i = tid; i < (4 * kCasP1Bytes + kCasRing * kCasStageBytes) / 16; i += kCasThreads) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
   fence_proxy_async();
   fence_before_sync();
   __syncthreads();
@@ -489,10 +492,10 @@ __global__ void __launch_bounds__(kCasThreads, 1) cascade_umma_kernel(const Casc
     const uint64_t pol = l2_policy_evict_first();
     int i = 0;
     for (int tile = next_tile(blockIdx.x); tile < a.n_tiles; tile = next_tile(tile + gridDim.x), ++i) {
-      const int s = i & 1;
-      float* st = stage + (size_t)s * kCasSpan;
+      const int s = i % kCasRing;
+      float* st = reinterpret_cast<float*>(ring + (size_t)s * kCasStageBytes);
       const Span sp = span_of(tile);
-      mbar_wait_relaxed(&stage_empty[s], ((i >> 1) & 1) ^ 1);
+      mbar_wait_relaxed(&p0_empty[s], ((i / kCasRing) & 1) ^ 1);  // free once the level p+1 MMAs of the tile it held have read it
       if (sp.bulk) {
         // one bulk copy of the existing samples (whole float4s); lane 0 patches the <= 3 tail samples.  Samples outside
         // [vlo, vhi) are masked at conversion time, not written here.
@@ -535,13 +538,13 @@ __global__ void __launch_bounds__(kCasThreads, 1) cascade_umma_kernel(const Casc
       commit(bar_planes);
     };
     auto issue1 = [&](int i) {
-      const int bf = i & 1;
+      const int bf = i & 1, s = i % kCasRing;
       const uint32_t ph = (i >> 1) & 1;
-      mbar_wait(&p0_full[bf], ph);
+      mbar_wait(&p0_full[s], (i / kCasRing) & 1);
       mbar_wait(&acc1_empty[bf], ph ^ 1);
       fence_after_sync();
-      const uint32_t hi0 = smem_u32(p0 + (size_t)bf * 2 * kCasP0Bytes);
-      if (elect_one()) issue_level(tmem + bf * 64, hi0, hi0 + kCasP0Bytes, kCasLBO0, &acc1_full[bf], &p0_empty[bf], idesc_f16(64), idesc_f16(32));
+      const uint32_t hi0 = smem_u32(ring + (size_t)s * kCasStageBytes);
+      if (elect_one()) issue_level(tmem + bf * 64, hi0, hi0 + kCasP0Bytes, kCasLBO0, &acc1_full[bf], &p0_empty[s], idesc_f16(64), idesc_f16(32));
       __syncwarp();
     };
     auto issue2 = [&](int i) {
@@ -569,16 +572,14 @@ __global__ void __launch_bounds__(kCasThreads, 1) cascade_umma_kernel(const Casc
     const int ct = tid - kCasConvWarp * 32;
     int i = 0;
     for (int tile = next_tile(blockIdx.x); tile < a.n_tiles; tile = next_tile(tile + gridDim.x), ++i) {
-      const int bf = i & 1;
-      const uint32_t ph = (i >> 1) & 1;
+      const int s = i % kCasRing;
       const Span sp = span_of(tile);
-      const float xsc = kXScale * (a.xs ? __ldg(a.xs + clip_of(tile)) : a.xs_uniform);  // issued before the waits below
+      const float xsc = kXScale * (a.xs ? __ldg(a.xs + clip_of(tile)) : a.xs_uniform);  // issued before the wait below
       const uint64_t ss = f2_pack(xsc, xsc);
-      const float* st = stage + (size_t)bf * kCasSpan;
-      uint8_t* p0h = p0 + (size_t)bf * 2 * kCasP0Bytes;
+      const float* st = reinterpret_cast<const float*>(ring + (size_t)s * kCasStageBytes);
+      uint8_t* p0h = ring + (size_t)s * kCasStageBytes;  // the planes overwrite the span they are made from
       uint8_t* p0l = p0h + kCasP0Bytes;
-      mbar_wait_relaxed(&stage_full[bf], ph);
-      mbar_wait_relaxed(&p0_empty[bf], ph ^ 1);
+      mbar_wait_relaxed(&stage_full[s], (i / kCasRing) & 1);
       const bool interior = sp.vlo == 0 && sp.vhi == kCasSpan;
       // one float4 per thread and round: consecutive lanes read consecutive 16 B of the stage and write 8-byte halves of the
       // operand chunks (both conflict-free).  float4 f = ct + kCasConvThreads r is half (f & 1) of chunk q = f / 2, which lives
@@ -608,6 +609,8 @@ __global__ void __launch_bounds__(kCasThreads, 1) cascade_umma_kernel(const Casc
 #pragma unroll
       for (int u = 0; u < kFull; ++u) v[u] = st4[kCasConvThreads * u];
       v[kFull] = ct < kRest ? st4[kCasConvThreads * kFull] : make_float4(0.f, 0.f, 0.f, 0.f);
+      // in-place conversion: every converter thread must hold its samples before any plane byte is written
+      asm volatile("bar.sync 4, %0;" ::"n"(kCasConvThreads) : "memory");
       if (interior) {  // all but the first and last tiles of a clip: no per-sample predicates
 #pragma unroll
         for (int u = 0; u < kFull; ++u) convert4(u, v[u], false);
@@ -617,8 +620,7 @@ __global__ void __launch_bounds__(kCasThreads, 1) cascade_umma_kernel(const Casc
       }
       if (ct < kRest) convert4(kFull, v[kFull], !interior);
       fence_proxy_async();
-      mbar_arrive(&p0_full[bf]);
-      mbar_arrive(&stage_empty[bf]);
+      mbar_arrive(&p0_full[s]);
     }
   } else if (warp < 8) {
     // ------------------------------------------------------------------ epilogue 1: accumulator lane = row of 32 level p+1 outputs
