@@ -41,6 +41,9 @@ def parse_args():
     ap.add_argument("--no-genre", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--gather-every", type=int, default=4,
+                    help="multi-GPU: all-gather the (clips, 35) result rows once per this many steps (rows of the steps in between wait "
+                         "in a device buffer); 1 = after every step")
     ap.add_argument("--no-graph", action="store_true", help="--train: launch the step's kernels one by one instead of as a CUDA graph")
     ap.add_argument("--sweep", action="store_true",
                     help="BASELINE configs[3]: large-batch sweep (1k/2k/4k/8k/16k long clips of 240 s, global batch sharded over "
@@ -199,7 +202,7 @@ def workload_config(args, genre):
                         f"({n_samples} samples, hop {SR // FRAMES}, {1 + n_samples // (SR // FRAMES)} frames x {36 * OCTAVES} bins), "
                         f"CQT + PitchClassNet(288,12,2,7) train_model.py defaults{' + genre head' if genre else ''} + decode, eval-mode BN",
             "clips_per_gpu": args.batch, "global_batch": args.batch * args.gpus, "clip_seconds": args.seconds, "sr": SR,
-            "l2_policy": "inputs larger than L2 (audio batch >> 126 MB), no flush", "parallelism": f"dp{args.gpus} (batch sharded, logit all-gather)"}
+            "l2_policy": "inputs larger than L2 (audio batch >> 126 MB), no flush", "parallelism": f"dp{args.gpus} (batch sharded, logit all-gather" + (f" every {max(1, args.gather_every)} steps)" if args.gpus > 1 else ")")}
 
 
 # ------------------------------------------------------------------------------------ B200 arm
@@ -236,20 +239,38 @@ def run_b200(args):
     synth.synth_batch(lo, B, n_samples, SR, device=dev, out=audio)
     torch.cuda.synchronize()
 
-    pending = [None]  # the previous step's all-gather, still in flight
+    # Result rows of up to `gather_every` steps wait in a device buffer and cross NVLink in ONE all-gather (the collective is
+    # latency-bound: 36 KB per rank and step).  Measured on 8 GPUs: a gather after every step costs ~60 us
+    # per 2.4 ms step on the compute stream; issued asynchronously on NCCL's own stream it costs MORE (~120 us: its CTAs take
+    # SMs from the one-CTA-per-SM persistent kernels while they wait for the slowest rank); one gather per 4 steps ~15 us per step.
+    K_g = max(1, args.gather_every) if world > 1 else 1
+    acc = torch.empty((K_g, B, akd.ROW), dtype=torch.float32, device=dev) if world > 1 else None
+    n_acc = [0]
+    last_table = [None]
+
+    def flush():
+        if world > 1 and n_acc[0]:
+            k = n_acc[0]
+            # (k * B) rows per rank -> (world, k, B, 35); the table of the latest step is [:, k - 1]
+            got = akd.gather_rows(acc[:k].reshape(k * B, akd.ROW), k * B * world).reshape(world, k, B, akd.ROW)
+            last_table[0] = got[:, k - 1].reshape(B * world, akd.ROW)
+            n_acc[0] = 0
 
     def device_step():
-        # CQT, then forward + decode in one call that writes the (clips, 35) result rows; their all-gather is asynchronous
-        # (NCCL's own stream) and overlaps the next step's kernels -- the step before's table is waited for here
+        # CQT, then forward + decode in one call that writes the (clips, 35) result rows
         rows, ids = est.estimate_device_rows(audio)
-        table = pending[0].wait() if pending[0] is not None else None
-        pending[0] = akd.RowGather(rows, B * world)
-        return table, ids
+        if world == 1:
+            last_table[0] = rows
+        else:
+            acc[n_acc[0]].copy_(rows)
+            n_acc[0] += 1
+            if n_acc[0] == K_g:
+                flush()
+        return last_table[0], ids
 
     def drain():
-        table = pending[0].wait() if pending[0] is not None else None
-        pending[0] = None
-        return table
+        flush()
+        return last_table[0]
 
     def barrier():
         if world > 1:
