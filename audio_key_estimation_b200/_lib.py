@@ -94,8 +94,8 @@ def lib() -> C.CDLL:
     global _lib
     with _lock:
         if _lib is None:
-            path = _build.LIB_PATH
-            if not os.path.exists(path) or os.environ.get("AKE_REBUILD"):
+            path = os.environ.get("AKE_LIB_PATH") or _build.LIB_PATH  # AKE_LIB_PATH: a build variant under test (tools/)
+            if path == _build.LIB_PATH and (not os.path.exists(path) or os.environ.get("AKE_REBUILD")):
                 path = _build.build()
             handle = C.CDLL(path)
             for name, (res, args) in _SIGNATURES.items():

@@ -54,13 +54,7 @@ __global__ void p2p_pack_weights_sub_kernel(const float* __restrict__ w, int Cou
     const int f = fc / 8, co = fc % 8;
     float v = 0.f;
     if (ci < n_ci && co < Cout) v = w[(((long long)co * Cin + ci0 + ci) * 7 + dp) * 7 + f] * kWScale;
-    const __half hi = __float2half_rn(v);
-    const __half lo = __float2half_rn(v - __half2float(hi));
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      img[((dp * 2 + c) * 112 + 16 * f + co) * 8 + ci] = hi;
-      img[((dp * 2 + c) * 112 + 16 * f + 8 + co) * 8 + ci] = lo;
-    }
+    p2p_img_store(img, dp, f, co, ci, v);
   }
 }
 

@@ -27,10 +27,18 @@ constexpr int kP2PStride = 122;     // anchors produced per 128-row MMA block (6
 constexpr int kP2PRows = 8;         // pitch rows per CTA tile
 constexpr int kP2PBufs = 2;         // tile buffers of the load ring
 constexpr int kP2PMaxTB = 160;      // frames per CTA tile (upper bound)
-constexpr int kP2PGroups = 4;       // epilogue groups of 4 warps = accumulator buffers of 128 TMEM columns
+#ifndef AKE_P2P_GROUPS
+#define AKE_P2P_GROUPS 5
+#endif
+#ifndef AKE_P2P_ISSUERS
+#define AKE_P2P_ISSUERS 2
+#endif
+constexpr int kP2PGroups = AKE_P2P_GROUPS;  // epilogue groups of 4 warps = accumulator buffers of 64 TMEM columns (56 used)
+constexpr int kP2PGroupsGen = AKE_P2P_GROUPS < 4 ? AKE_P2P_GROUPS : 4;    // ... of the tile-generating variant (eight more warps: the register file allows four groups)
 constexpr int kP2PGenWarps = 8;      // tile-generator warps of the first conv (instead of the one loader warp)
-constexpr int kP2PThreads = 32 * (4 * kP2PGroups + 2);                    // + the loader warp and the MMA-issuer warp
-constexpr int kP2PThreadsGen = 32 * (4 * kP2PGroups + kP2PGenWarps + 1);  // + the generator warps and the MMA-issuer warp
+constexpr int kP2PThreads = 32 * (4 * kP2PGroups + 1 + AKE_P2P_ISSUERS);        // + the loader warp and the MMA-issuer warps
+constexpr int kP2PThreadsGen = 32 * (4 * kP2PGroupsGen + kP2PGenWarps + 1);  // + the generator warps and one MMA-issuer warp
+constexpr int kP2PMmas = 11;        // MMAs per block: 7 row taps (x_hi + x_lo) . W_hi, then x_hi . W_lo of the row taps in pairs
 
 __device__ __forceinline__ float leaky_f(float v) { return v > 0.f ? v : kLeakySlope * v; }
 
@@ -67,9 +75,20 @@ __global__ void __launch_bounds__(128) upsixth_table_kernel(const float* __restr
   up[((long long)b * 36 + p36) * T + t] = make_float4(y[0], y[1], y[2], y[3]);
 }
 
-// ---- weight image for the 7x7 convolution: [dp 7][chunk 2][n 112][ci 8] fp16 ------------------------------------------
-// n = 16 f + j: time tap f; j < 8: W_hi of output channel j, j >= 8: W_lo of output channel j - 8 (so one 16-column TMEM
-// load fetches both halves of a phase).  Both chunks (x_hi, x_lo) hold the same weights.
+// ---- weight image for the 7x7 convolution: [mma 11][chunk 2][n 56][ci 8] fp16 -------------------------------------------
+// n = 8 f + co (time tap f, output channel co).  The three products x_hi W_hi + x_lo W_hi + x_hi W_lo all accumulate into ONE
+// 56-column accumulator (no hi / lo halves to add in the epilogue, half the TMEM columns per block: more blocks in flight):
+//   MMA dp < 7   : A chunks = (x_hi, x_lo) of one position (LBO = plane distance), B chunks = (W_hi[dp], W_hi[dp])
+//   MMA 7 + j    : A chunks = x_hi of row taps 2 j and 2 j + 1 (LBO = row pitch),  B chunks = (W_lo[2 j], W_lo[2 j + 1] or 0)
+__device__ __forceinline__ void p2p_img_store(__half* __restrict__ img, int dp, int f, int co, int ci, float v) {
+  const __half hi = __float2half_rn(v);
+  const __half lo = __float2half_rn(v - __half2float(hi));
+  const int n = 8 * f + co;
+  img[((dp * 2 + 0) * 56 + n) * 8 + ci] = hi;
+  img[((dp * 2 + 1) * 56 + n) * 8 + ci] = hi;
+  img[(((7 + dp / 2) * 2 + (dp & 1)) * 56 + n) * 8 + ci] = lo;
+  if (dp == 6) img[((10 * 2 + 1) * 56 + n) * 8 + ci] = __float2half_rn(0.f);  // row tap 7 does not exist
+}
 __global__ void p2p_pack_weights_kernel(const float* __restrict__ w, int Cout, int Cin, __half* __restrict__ img) {
   const int n_items = 7 * 56 * 8;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_items; i += gridDim.x * blockDim.x) {
@@ -77,13 +96,7 @@ __global__ void p2p_pack_weights_kernel(const float* __restrict__ w, int Cout, i
     const int f = fc / 8, co = fc % 8;
     float v = 0.f;
     if (ci < Cin && co < Cout) v = w[(((long long)co * Cin + ci) * 7 + dp) * 7 + f] * kWScale;
-    const __half hi = __float2half_rn(v);
-    const __half lo = __float2half_rn(v - __half2float(hi));
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      img[((dp * 2 + c) * 112 + 16 * f + co) * 8 + ci] = hi;
-      img[((dp * 2 + c) * 112 + 16 * f + 8 + co) * 8 + ci] = lo;
-    }
+    p2p_img_store(img, dp, f, co, ci, v);
   }
 }
 
@@ -106,7 +119,7 @@ struct P2PArgs {
   float* raw_out;
 };
 
-constexpr uint32_t kP2PWBytes = 7 * 2 * 112 * 16;
+constexpr uint32_t kP2PWBytes = kP2PMmas * 2 * 56 * 16;
 constexpr uint32_t kP2PPubBytes = 2 * 3 * 21 * 32;  // per epilogue group: [parity 2][warp 1..3][phase f = 1..6: f lanes][co 8] floats
 
 __host__ __device__ inline uint32_t p2p_plane_positions(int Wt) { return (uint32_t)((kP2PRows + 6) * Wt + 136); }
@@ -124,10 +137,16 @@ __host__ __device__ inline size_t p2p_smem_bytes(int Wt) {
 template <bool GEN, bool RAW = false>
 __global__ void __launch_bounds__(GEN ? kP2PThreadsGen : kP2PThreads, 1) p2p_umma_kernel(const P2PArgs a) {
   using namespace umma;
-  constexpr int G = kP2PGroups;
+  constexpr int G = GEN ? kP2PGroupsGen : kP2PGroups;
+  // MMA-issuer warps, taking alternate blocks: one warp issues an MMA of N <= 64 every ~61 cycles, the tensor pipe executes one
+  // every ~46 (tools/umma_rate.cu).  The accumulator buffers are shared between the issuers (G is odd), so a buffer's "drained"
+  // hand-over alternates between TWO mbarriers: a waiter two uses ahead of a single barrier would pass on a stale parity.
+  constexpr int NI = GEN ? 1 : AKE_P2P_ISSUERS;
+  constexpr uint32_t TMEM_COLS = 64 * G <= 256 ? 256 : 512;
   constexpr int NLOAD = GEN ? kP2PGenWarps : 1, ISSUER = 4 * G + NLOAD;  // warp roles: [0, 4G) epilogue, [4G, 4G + NLOAD) tile producers, ISSUER
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ __align__(8) uint64_t w_bar, full_bar[kP2PBufs], empty_bar[kP2PBufs], acc_full[G], acc_empty[G];
+  __shared__ __align__(8) uint64_t w_bar, full_bar[kP2PBufs], empty_bar[kP2PBufs], acc_full[G], acc_empty[G][2];
+  static_assert(G <= kP2PGroups, "shared-memory sizing assumes at most kP2PGroups hand-over buffers");
   __shared__ uint32_t tmem_slot;
   __shared__ float s_scale[8], s_shift[8];
 
@@ -158,11 +177,11 @@ __global__ void __launch_bounds__(GEN ? kP2PThreadsGen : kP2PThreads, 1) p2p_umm
     return g;
   };
 
-  if (warp == ISSUER) tmem_alloc(&tmem_slot, 128 * G);
+  if (warp == ISSUER) tmem_alloc(&tmem_slot, TMEM_COLS);
   if (threadIdx.x == 0) {
     mbar_init(&w_bar, 1);
-    for (int i = 0; i < kP2PBufs; ++i) mbar_init(&full_bar[i], GEN ? 32 * NLOAD : 1), mbar_init(&empty_bar[i], 1);
-    for (int i = 0; i < G; ++i) mbar_init(&acc_full[i], 1), mbar_init(&acc_empty[i], 128);
+    for (int i = 0; i < kP2PBufs; ++i) mbar_init(&full_bar[i], GEN ? 32 * NLOAD : 1), mbar_init(&empty_bar[i], NI);
+    for (int i = 0; i < G; ++i) mbar_init(&acc_full[i], 1), mbar_init(&acc_empty[i][0], 128), mbar_init(&acc_empty[i][1], 128);
     mbar_init_fence();
   }
   if (threadIdx.x < 8) s_scale[threadIdx.x] = a.scale[threadIdx.x] * (1.f / kWScale), s_shift[threadIdx.x] = a.shift[threadIdx.x];
@@ -278,11 +297,14 @@ __global__ void __launch_bounds__(GEN ? kP2PThreadsGen : kP2PThreads, 1) p2p_umm
         }
       }
     }
-  } else if (warp == ISSUER) {
-    // ------------------------------------------------------------ MMA issuer (converged warp, one elected lane issues)
-    const uint64_t A_DESC = desc_hi(plane);         // chunk 1 = the x_lo plane at the same position
-    constexpr uint64_t B_DESC = desc_hi(112 * 16);  // chunk stride: 112 rows x 16 B
-    constexpr uint32_t IDESC = idesc_f16(112);
+  } else if (warp >= ISSUER) {
+    // ------------------------------------------------------------ MMA issuers (converged warps, one elected lane issues)
+    const uint32_t my = (uint32_t)(warp - ISSUER);  // this warp issues the blocks j with j % NI == my
+    const uint64_t A_DESC = desc_hi(plane);                     // chunk 1 = the x_lo plane at the same position
+    const uint64_t A_DESC_ROW = desc_hi((uint32_t)Wt * 16);     // chunk 1 = the x_hi plane one pitch row further (the next row tap)
+    constexpr uint64_t B_DESC = desc_hi(56 * 16);               // chunk stride: 56 rows x 16 B
+    constexpr uint32_t IDESC = idesc_f16(56);
+    constexpr uint32_t W_MMA = 2 * 56 * 16;                     // bytes of one MMA's weight block
     const uint32_t w0 = smem_u32(s_w);
     mbar_wait(&w_bar, 0);
     int k = 0;
@@ -293,25 +315,30 @@ __global__ void __launch_bounds__(GEN ? kP2PThreadsGen : kP2PThreads, 1) p2p_umm
       const uint32_t hi0 = smem_u32(smem + (size_t)s * 2 * plane);
       mbar_wait(&full_bar[s], (k / kP2PBufs) & 1);
       for (int m = 0; m < g.n_mb; ++m, ++j) {
-        const uint32_t buf = j % G;
-        mbar_wait(&acc_empty[buf], ((j / G) & 1) ^ 1);
+        if (NI > 1 && j % NI != my) continue;
+        const uint32_t buf = j % G, use = j / G;  // the buffer's previous use (use - 1) must have been drained
+        if (use > 0) mbar_wait(&acc_empty[buf][(use - 1) & 1], ((use - 1) >> 1) & 1);
         fence_after_sync();
-        const uint32_t d = tmem + buf * 128;
+        const uint32_t d = tmem + buf * 64;
         const uint32_t a_off = hi0 + (uint32_t)(m * kP2PStride) * 16;
         if (elect_one()) {
 #pragma unroll
-          for (int dp = 0; dp < 7; ++dp)
-            mma_f16(d, make_desc(A_DESC, a_off + (uint32_t)(dp * Wt) * 16), make_desc(B_DESC, w0 + dp * (2 * 112 * 16)), IDESC, dp ? 1u : 0u);
+          for (int dp = 0; dp < 7; ++dp)  // (x_hi + x_lo) . W_hi of row tap dp
+            mma_f16(d, make_desc(A_DESC, a_off + (uint32_t)(dp * Wt) * 16), make_desc(B_DESC, w0 + dp * W_MMA), IDESC, dp ? 1u : 0u);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)     // x_hi . W_lo of the row taps 2 j, 2 j + 1 (tap 7: zero weights on whatever follows the tile)
+            mma_f16(d, make_desc(A_DESC_ROW, a_off + (uint32_t)(2 * j * Wt) * 16), make_desc(B_DESC, w0 + (7 + j) * W_MMA), IDESC, 1u);
           commit(&acc_full[buf]);
-          if (m == g.n_mb - 1) commit(&empty_bar[s]);  // the tile buffer is free once these MMAs have read it
         }
         __syncwarp();
       }
+      if (elect_one()) commit(&empty_bar[s]);  // the tile buffer is free once every issuer's MMAs of this tile have read it
+      __syncwarp();
     }
   } else {
     // ------------------------------------------------------------ epilogue: thread = TMEM lane = anchor row
     const int grp = warp >> 2, wq = warp & 3, tid = threadIdx.x & 127;
-    const uint32_t acc = tmem + ((uint32_t)(wq * 32) << 16) + grp * 128;
+    const uint32_t acc = tmem + ((uint32_t)(wq * 32) << 16) + grp * 64;
     float4* pub = reinterpret_cast<float4*>(s_pub + grp * kP2PPubBytes);
     const uint32_t wt_magic = 0xFFFFFFFFu / (uint32_t)Wt + 1;  // anchor / Wt == umulhi(anchor, magic) for anchor * Wt < 2^32
     uint64_t sc2[4], sh2[4];
@@ -326,23 +353,21 @@ __global__ void __launch_bounds__(GEN ? kP2PThreadsGen : kP2PThreads, 1) p2p_umm
         const int m = (int)(j - j0);
         mbar_wait_relaxed(&acc_full[grp], n_done & 1);
         fence_after_sync();
-        // phase f = time tap f: out[a] = sum_f D_f[a + f], D_f of this thread's row = columns [16 f, 16 f + 8) (W_hi) +
-        // [16 f + 8, 16 f + 16) (W_lo).  Rows a + f live f lanes further on: warp shuffles for lane + f < 32, the first
-        // lanes of the next warp (through shared memory) otherwise -- ascending f for every anchor either way.
+        // phase f = time tap f: out[a] = sum_f D_f[a + f], D_f of this thread's row = columns [8 f, 8 f + 8).  Rows a + f live f
+        // lanes further on: warp shuffles for lane + f < 32, the first lanes of the next warp (through shared memory)
+        // otherwise -- ascending f for every anchor either way.
         float4* pub_w = pub + (n_done & 1) * (3 * 21 * 2);
         uint64_t o[4];
-        uint32_t r[2][16];
-        tmem_ld16_issue(acc, r[0]);
+        uint32_t r[2][8];
+        tmem_ld8_issue(acc, r[0]);
 #pragma unroll
         for (int f = 0; f < 7; ++f) {
-          uint32_t(&v)[16] = r[f & 1];
-          tmem_ld_wait16(v);
-          if (f < 6) tmem_ld16_issue(acc + 16 * (f + 1), r[(f + 1) & 1]);
+          uint32_t(&v)[8] = r[f & 1];
+          tmem_ld_wait8(v);
+          if (f < 6) tmem_ld8_issue(acc + 8 * (f + 1), r[(f + 1) & 1]);
           uint64_t u[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e)
-            u[e] = f2_add(f2_pack(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1])),
-                          f2_pack(__uint_as_float(v[8 + 2 * e]), __uint_as_float(v[9 + 2 * e])));
+          for (int e = 0; e < 4; ++e) u[e] = f2_pack(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1]));
           if (f == 0) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) o[e] = u[e];
@@ -365,7 +390,7 @@ __global__ void __launch_bounds__(GEN ? kP2PThreadsGen : kP2PThreads, 1) p2p_umm
           }
         }
         fence_before_sync();
-        mbar_arrive(&acc_empty[grp]);  // accumulator drained: the issuer may start block j + G
+        mbar_arrive(&acc_empty[grp][n_done & 1]);  // accumulator drained: block j + G may be issued
         asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
         if (wq < 3 && lane >= 26) {
 #pragma unroll
@@ -424,7 +449,7 @@ __global__ void __launch_bounds__(GEN ? kP2PThreadsGen : kP2PThreads, 1) p2p_umm
   }
   fence_before_sync();
   __syncthreads();
-  if (warp == ISSUER) tmem_dealloc(tmem, 128 * G);
+  if (warp == ISSUER) tmem_dealloc(tmem, TMEM_COLS);
 }
 
 // ---- pool_semi conv (3x3, stride (3,1), time-circular) + BN + LeakyReLU + octave max pool, from chunk planes ------

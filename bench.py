@@ -402,12 +402,12 @@ def run_b200(args):
         with open(tpath) as fh:
             tj = json.load(fh)
         traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
-    # The scheme's own ceiling: operands are fp16 hi/lo pairs (22-bit) and the layer has 8 channels, so a row tap of 122
-    # anchors is ONE tcgen05.mma of N = 112 (7 time-tap phases x 8 channels x {W_hi, W_lo}), K = 16 = [x_hi | x_lo], which
-    # one issuing warp retires every ~68 SM cycles (tools/umma_rate.cu).  7 row taps per block, at the SM clock seen.
-    sm_hz = ((clocks or {}).get("sm_mhz") or 1965.0) * 1e6
+    # The scheme's own ceiling: operands are fp16 hi/lo pairs (22-bit) and the layer has 8 channels, so a block of 122 anchors is
+    # 11 tcgen05.mma of N = 56 (7 time-tap phases x 8 channels), K = 16: seven (x_hi | x_lo) . W_hi row taps and four x_hi . W_lo
+    # row-tap pairs, each bound by its 4 KB operand read out of shared memory (32 + N/4 = 46 SM cycles; tools/umma_rate.cu).
+    sm_hz = ((clocks or {}).get("sm_max_mhz") or 1965.0) * 1e6
     p2p_blocks = B * 3 * 288 * T / 122.0   # output positions of the 3 convs / anchors per MMA block
-    p2p_floor_ms = p2p_blocks * 7 * 68 / (148 * sm_hz) * 1e3
+    p2p_floor_ms = p2p_blocks * 11 * 46 / (148 * sm_hz) * 1e3
     scheme_ceiling = (2.0 * p2p_macs_clip * B / (p2p_floor_ms * 1e-3) / 1e12) / peaks["bf16_tflops_sustained"]
     roofline = {
         "kernel": "pcn.p2p: 3 x Conv2d 7x7 circular (pitch,time) + BN + LeakyReLU (64.6% of the reference forward's MACs); "
@@ -419,7 +419,7 @@ def run_b200(args):
         "launches_per_step": p2p_n, "ms_per_step": p2p_ms,
         "algorithmic_flops_per_step": 2.0 * p2p_macs_clip * B,
         "scheme_ceiling": scheme_ceiling,
-        "scheme_ceiling_note": "MMA-issue floor of the fp16 hi/lo shift-GEMM at 8 channels (7 x N=112,K=16 MMAs of ~68 cycles per 122 anchors) "
+        "scheme_ceiling_note": "operand-read floor of the fp16 hi/lo shift-GEMM at 8 channels (11 x N=56,K=16 MMAs of 46 cycles per 122 anchors) "
                                "expressed as a fraction of the dense bf16 peak: frac / scheme_ceiling = share of the achievable",
         "frac_of_scheme_ceiling": ((p2p_tflops / peaks["bf16_tflops_sustained"]) / scheme_ceiling) if p2p_tflops else None,
         "dtype_note": "fp16 hi/lo 3-product (x_hi*w_hi + x_lo*w_hi + x_hi*w_lo), 22-bit operands, fp32 accumulate in TMEM",
