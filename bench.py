@@ -397,7 +397,7 @@ def run_b200(args):
     # DRAM bytes per launch of the dominant kernel come from the committed ncu capture (profiles/), valid for the default
     # workload only; never measured live (a number taken under a profiler is not a bench value)
     traffic, traffic_src = None, None
-    tpath = os.path.join(ROOT, "profiles", "r01_roofline_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r02_roofline_traffic.json")
     if os.path.exists(tpath) and B == 256 and abs(args.seconds - SECONDS_STD) < 1e-9 and genre:
         with open(tpath) as fh:
             tj = json.load(fh)
