@@ -370,6 +370,8 @@ template <int KH, int KW, int SR, int RB, int CO_T, int RT>
 static void launch_conv_t(ConvArgs a, int B, int max_tg, cudaStream_t st) {
   constexpr int RIN = (RB - 1) * SR + KH;
   const int groups = cdiv(a.T_out, RT);
+  // (Narrower time tiles for small batches were measured and dropped: 5.40 -> 7.92 ms for the 8-clip training step -- every block
+  // re-stages its weight slice and input halo.)
   const int n_tiles = cdiv(groups, max_tg);
   a.tgroups = cdiv(groups, n_tiles);
   const int TBW = a.tgroups * RT + KW - 1;
@@ -390,6 +392,9 @@ static void launch_conv_t(ConvArgs a, int B, int max_tg, cudaStream_t st) {
 static void launch_conv(const ConvArgs& a, const ConvGeom& g, int co_tile, int B, cudaStream_t st) {
   // (KH, KW, SR) families: equivariant 12x7, pitch 7x7, semitone 3x3/3, genre 1x7 and 2x7
   if (g.KH == 12 && g.KW == 7 && g.SR == 1) {
+    // few blocks (small batch: the 8-clip training step): four output channels per thread instead of eight doubles the blocks of
+    // the equivariant convs (5.40 -> 5.21 ms per step); the accumulation order of an output does not depend on the tiling
+    if (co_tile == 8 && (long long)cdiv(cdiv(a.T_out, 4), 8) * (a.cout_pad / 8) * B < 2LL * sm_count()) co_tile = 4;
     if (co_tile == 8) return launch_conv_t<12, 7, 1, 12, 8, 4>(a, B, 8, st);
     if (co_tile == 4) return launch_conv_t<12, 7, 1, 12, 4, 4>(a, B, 8, st);
     if (co_tile == 1) return launch_conv_t<12, 7, 1, 12, 1, 4>(a, B, 8, st);

@@ -214,6 +214,27 @@ void Fwd::run_keep(const float* mel, float* key_out, float* tonic_out, float* ge
 }
 
 // ------------------------------------------------------------------------------------------------ backward
+// One side stream per host thread and device for the weight-gradient kernels of the backward pass.
+struct SideStream {
+  int device = -1;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+  bool used = false;
+};
+static SideStream& side_stream() {
+  thread_local SideStream s;
+  const int dev = current_device();
+  if (s.device != dev) {
+    s = SideStream();
+    s.device = dev;
+    AKE_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    AKE_CUDA(cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming));
+    AKE_CUDA(cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming));
+  }
+  s.used = false;
+  return s;
+}
+
 void Fwd::backward_keep(const TrainTape& tp, const float* d_key, const float* d_tonic, const float* d_genre, float* grads) {
   const ake_pcn_config& cfg = p->cfg;
   const int P = cfg.pitches, k = cfg.kernel_size;
@@ -255,10 +276,26 @@ void Fwd::backward_keep(const TrainTape& tp, const float* d_key, const float* d_
     channel_sum_kernel<<<grid, 256, 0, st>>>(dz.p, B, c.Cout, dz.R * dz.T, grads + c.b_off);
     AKE_LAUNCHED();
   };
+  // Weight and bias gradients only feed the gradient buffer: they run on a side stream, forked behind the kernel that produced dz
+  // and joined at the end of the backward pass, so that they overlap the data-gradient chain (at batch 8 neither fills the GPU).
+  SideStream& side = side_stream();
   auto wgrad = [&](const ConvSite& s, const View& dz) {
     const Conv& c = p->convs[s.id];
-    bias_grad(c, dz);
     if (dry) return;
+    const cudaStream_t main_st = st;
+    static const bool use_side = [] { const char* e = getenv("AKE_WGRAD_SIDE"); return e ? atoi(e) != 0 : true; }();  // 5.40 -> 4.63 ms per step
+    if (use_side) {
+      AKE_CUDA(cudaEventRecord(side.fork, main_st));
+      AKE_CUDA(cudaStreamWaitEvent(side.stream, side.fork, 0));
+      st = side.stream;  // bias_grad and launch_wgrad below launch on `st`
+      side.used = true;
+    }
+    struct Restore {
+      cudaStream_t& s;
+      cudaStream_t v;
+      ~Restore() { s = v; }
+    } restore{st, main_st};
+    bias_grad(c, dz);
     WgradArgs a{};
     a.in0 = s.in0.p, a.c0 = s.in0.C, a.rows0 = s.in0.R, a.bs0 = s.in0.bstride();
     if (s.in1.p) a.in1 = s.in1.p, a.c1 = s.in1.C, a.rows1 = s.in1.R, a.bs1 = s.in1.bstride();
@@ -400,6 +437,10 @@ void Fwd::backward_keep(const TrainTape& tp, const float* d_key, const float* d_
     }
     View dz = bn_bwd(s.id, s.z, da);
     wgrad(s, dz);
+  }
+  if (!dry && side.used) {  // join: the gradient buffer is complete only once the side stream's kernels are done
+    AKE_CUDA(cudaEventRecord(side.join, side.stream));
+    AKE_CUDA(cudaStreamWaitEvent(st, side.join, 0));
   }
 }
 

@@ -536,7 +536,7 @@ def run_train(args):
     --impl reference: the oracle port (float64 torch-CPU autograd, the reference's dtype) on the host cores."""
     import numpy as np
     import torch
-    B, T = 8, 1 + SECONDS_STD * SR // (SR // FRAMES)
+    B, T = (args.batch if args.batch != 256 else 8), 1 + SECONDS_STD * SR // (SR // FRAMES)  # --batch N: clips per GPU (default 8, train_model.py)
     rng = np.random.default_rng(0)
     mel = torch.from_numpy(np.log1p(rng.gamma(1.0, 1.0, (B, 1, 36 * OCTAVES, T))).astype(np.float32))
     key_labels = torch.from_numpy((rng.random((B, 12)) < 0.6).astype(np.float32))
