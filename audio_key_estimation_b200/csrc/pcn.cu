@@ -380,11 +380,14 @@ static void launch_conv_t(ConvArgs a, int B, int max_tg, cudaStream_t st) {
   while (xp % 32 != 12 && xp % 32 != 4 && xp % 32 != 20 && xp % 32 != 28) xp += 4;  // odd multiple of 4: conflict-free float4 rows
   a.xp = xp;
   a.n_row_tiles = cdiv(a.rows_out, RB);
-  const int threads = cdiv(RB * a.tgroups, 32) * 32;
+  int threads = cdiv(RB * a.tgroups, 32) * 32;
   const size_t smem = sizeof(float) * ((size_t)kConvCI * RIN * xp + (size_t)kConvCI * KH * KW * CO_T);
   auto kern = conv_rows_kernel<KH, KW, SR, RB, CO_T, RT>;
   ensure_dyn_smem(kern, smem);
   dim3 grid(n_tiles, a.n_row_tiles * (a.cout_pad / CO_T), B);
+  // few blocks (the 8-clip training step): a block is alone on its SM and its staging phase is latency-bound with 3-4 warps;
+  // extra warps only stage (the kernel's `active` guard keeps them out of the arithmetic)
+  if ((long long)grid.x * grid.y * grid.z <= 2LL * sm_count()) threads = 256;
   kern<<<grid, threads, smem, st>>>(a);
   AKE_LAUNCHED();
 }

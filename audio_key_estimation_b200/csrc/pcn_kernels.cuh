@@ -101,23 +101,37 @@ __global__ void __launch_bounds__(256) conv_rows_kernel(const ConvArgs a) {
     const int nci = min(kConvCI, a.Cin - cbase);
     __syncthreads();
     // ---- stage the input tile: one warp per (channel, row) line
-    for (int line = warp; line < nci * RIN; line += nwarps) {
-      const int ci = line / RIN, row = line - ci * RIN;
-      int v = out_row0 * SR + a.row_off + row;
-      const float* src = nullptr;
-      if (a.row_circ) {
-        v %= a.rows_v;
-        if (v < 0) v += a.rows_v;
-      }
-      if (v >= 0 && v < a.rows_v) {
-        const int ch = cbase + ci;
-        src = (ch < a.c0) ? a.in0 + b * a.bs0 + (long long)(ch * a.rows0 + v) * a.T_in
-                          : a.in1 + b * a.bs1 + (long long)((ch - a.c0) * a.rows1 + v % a.rows1) * a.T_in;
-      }
-      float* dst = xs + (ci * RIN + row) * XP;
+    // (four lines per round: their loads are all in flight before the first store -- with few warps per block the staging
+    // is latency-bound otherwise)
+    const int n_lines = nci * RIN;
+    for (int line0 = warp; line0 < n_lines; line0 += 4 * nwarps) {
+      float xv[4][3];
 #pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        if (tm[k] != -2) dst[lane + 32 * k] = (src != nullptr && tm[k] >= 0) ? __ldg(src + tm[k]) : 0.f;
+      for (int u = 0; u < 4; ++u) {
+        const int line = line0 + u * nwarps;
+        const int ci = line / RIN, row = line - ci * RIN;
+        int v = out_row0 * SR + a.row_off + row;
+        const float* src = nullptr;
+        if (a.row_circ) {
+          v %= a.rows_v;
+          if (v < 0) v += a.rows_v;
+        }
+        if (line < n_lines && v >= 0 && v < a.rows_v) {
+          const int ch = cbase + ci;
+          src = (ch < a.c0) ? a.in0 + b * a.bs0 + (long long)(ch * a.rows0 + v) * a.T_in
+                            : a.in1 + b * a.bs1 + (long long)((ch - a.c0) * a.rows1 + v % a.rows1) * a.T_in;
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) xv[u][k] = (src != nullptr && tm[k] >= 0) ? __ldg(src + tm[k]) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int line = line0 + u * nwarps;
+        if (line >= n_lines) break;
+        float* dst = xs + line * XP;  // line = ci * RIN + row
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+          if (tm[k] != -2) dst[lane + 32 * k] = xv[u][k];
       }
     }
     // ---- stage the weight slice [nci][KH][KW][CO_T]
