@@ -52,23 +52,27 @@ __global__ void bn_mean_invstd_kernel(const double* __restrict__ stats, double c
   invstd[c] = (float)(1.0 / sqrt(var + (double)kBnEps));
 }
 
-template <int KH, int KW, int SR, int RB>
-static void launch_wgrad_t(const WgradArgs& a, int B, cudaStream_t st) {
-  constexpr int RIN = (RB - 1) * SR + KH, XP = (kWgTB + KW - 1 + 3) / 4 * 4;
-  const size_t smem = sizeof(float) * ((size_t)RIN * XP + (size_t)a.Cout * RB * kWgTB);
-  if (a.Cout * KH > 512) fail(AKE_ERR_UNSUPPORTED, "weight-gradient kernel: Cout * KH = %d > 512", a.Cout * KH);
-  auto kern = conv_wgrad_kernel<KH, KW, SR, RB>;
+template <int KH, int KW, int SR, int RB, int RS>
+static void launch_wgrad_t(WgradArgs a, int B, cudaStream_t st) {
+  constexpr int RIN = (RB - 1) * SR + KH;
+  const size_t smem = sizeof(float) * ((size_t)kWgCI * RIN * wg_xp(KW) + (size_t)RB * kWgGP);
+  auto kern = conv_wgrad_kernel<KH, KW, SR, RB, RS>;
   ensure_dyn_smem(kern, smem);
-  kern<<<dim3(cdiv(a.rows_out, RB), a.Cin, B), 256, smem, st>>>(a);
+  a.n_cob = cdiv(a.Cout, kWgCO);
+  const int row_tiles = cdiv(a.rows_out, RB), y = cdiv(a.Cin, kWgCI) * a.n_cob;
+  // enough blocks for two per SM, at least one 16-frame tile each
+  const long long base = (long long)row_tiles * y * B;
+  a.t_splits = (int)std::max<long long>(1, std::min<long long>(cdiv(a.T_out, kWgTB), cdiv64(2LL * sm_count(), base)));
+  kern<<<dim3(row_tiles * a.t_splits, y, B), kWgCI * KH * RS, smem, st>>>(a);
   AKE_LAUNCHED();
 }
 
 static void launch_wgrad(const WgradArgs& a, const ConvGeom& g, int B, cudaStream_t st) {
-  if (g.KH == 12 && g.KW == 7 && g.SR == 1) return launch_wgrad_t<12, 7, 1, 12>(a, B, st);
-  if (g.KH == 7 && g.KW == 7 && g.SR == 1) return launch_wgrad_t<7, 7, 1, 8>(a, B, st);
-  if (g.KH == 3 && g.KW == 3 && g.SR == 3) return launch_wgrad_t<3, 3, 3, 8>(a, B, st);
-  if (g.KH == 1 && g.KW == 7 && g.SR == 1) return launch_wgrad_t<1, 7, 1, 12>(a, B, st);
-  if (g.KH == 2 && g.KW == 7 && g.SR == 1) return launch_wgrad_t<2, 7, 1, 12>(a, B, st);
+  if (g.KH == 12 && g.KW == 7 && g.SR == 1) return launch_wgrad_t<12, 7, 1, 12, 2>(a, B, st);
+  if (g.KH == 7 && g.KW == 7 && g.SR == 1) return launch_wgrad_t<7, 7, 1, 8, 4>(a, B, st);
+  if (g.KH == 3 && g.KW == 3 && g.SR == 3) return launch_wgrad_t<3, 3, 3, 8, 8>(a, B, st);
+  if (g.KH == 1 && g.KW == 7 && g.SR == 1) return launch_wgrad_t<1, 7, 1, 12, 4>(a, B, st);
+  if (g.KH == 2 && g.KW == 7 && g.SR == 1) return launch_wgrad_t<2, 7, 1, 12, 4>(a, B, st);
   fail(AKE_ERR_UNSUPPORTED, "no weight-gradient kernel for KH=%d KW=%d SR=%d", g.KH, g.KW, g.SR);
 }
 

@@ -39,8 +39,10 @@ __global__ void pack_conv_dgrad_kernel(const float* __restrict__ w, int Cout, in
 
 // ---- weight gradient of a row convolution ---------------------------------------------------------------------------
 //   dW[co, ci, dr, dt] = sum_{b, r, t} dZ[b, co, r, t] * x[b, ci, rowmap(r*SR + off + dr), tmap(t - pad + dt)]
-// grid (row tiles, Cin, B); a block walks the frames of its (clip, input channel, row tile) in tiles of 16, keeps
-// KW accumulators per (co, dr) pair in registers and adds them to the gradient buffer once at the end.
+// A block owns (clip, row tile, 8 input channels, 8 output channels, a range of 16-frame tiles).  A thread owns one (ci, dr) and
+// every RS-th output row of the tile; it keeps the 8 x KW accumulators of its 8 output channels in registers over all its frames
+// (per row and tile: 22 input frames and 16 x 8 gradients from shared memory feed 16 x 8 x KW FMAs), the RS row shares are summed
+// with warp shuffles and added to the gradient buffer once per block.
 struct WgradArgs {
   const float* in0;
   const float* in1;
@@ -50,92 +52,130 @@ struct WgradArgs {
   int rows_out, T_out, Cin, Cout;
   const float* dz;  // (B, Cout, rows_out, T_out)
   float* dw;        // (Cout, Cin, KH, KW), accumulated
+  int t_splits;     // blocks along the frames of a (clip, row tile)
+  int n_cob;        // blocks of 8 output channels
 };
 
-constexpr int kWgTB = 16;
+constexpr int kWgTB = 16;             // frames per tile
+constexpr int kWgCI = 8, kWgCO = 8;   // input / output channels per block
+constexpr int kWgGP = kWgTB * kWgCO + 4;  // gradient row pitch (floats): rows land in different banks
+__host__ __device__ constexpr int wg_xp(int kw) {  // input row pitch: a multiple of 4 floats with an odd quotient (conflict-free float4 rows)
+  int xp = (kWgTB + kw - 1 + 3) / 4 * 4;
+  return (xp / 4) % 2 ? xp : xp + 4;
+}
 
-template <int KH, int KW, int SR, int RB>
-__global__ void __launch_bounds__(256) conv_wgrad_kernel(const WgradArgs a) {
+template <int KH, int KW, int SR, int RB, int RS>
+__global__ void __launch_bounds__(kWgCI* KH* RS) conv_wgrad_kernel(const WgradArgs a) {
   constexpr int RIN = (RB - 1) * SR + KH;
   constexpr int XW = kWgTB + KW - 1;
-  constexpr int XP = (XW + 3) / 4 * 4;
+  constexpr int XP = wg_xp(KW);
+  constexpr int NT = kWgCI * KH * RS;
+  static_assert(RB % RS == 0 && (RS & (RS - 1)) == 0 && RS <= 32 && NT % 32 == 0 && XW <= 32, "thread layout");
   extern __shared__ float4 smem4[];
-  float* xs = reinterpret_cast<float*>(smem4);  // [RIN][XP]
-  float* gs = xs + RIN * XP;                    // [Cout][RB][kWgTB]
-  const int tid = threadIdx.x;
-  const int row_tile = blockIdx.x, ci = blockIdx.y, b = blockIdx.z;
+  float* xs = reinterpret_cast<float*>(smem4);  // [kWgCI][RIN][XP]
+  float* gs = xs + kWgCI * RIN * XP;            // [RB][kWgTB][kWgCO] (+ 4 floats per row)
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NW = NT / 32;
+  const int rs = tid % RS, dr = (tid / RS) % KH, cil = tid / (RS * KH);
+  const int row_tile = blockIdx.x / a.t_splits, tsp = blockIdx.x - row_tile * a.t_splits;
+  const int cib = blockIdx.y / a.n_cob, cob = blockIdx.y - cib * a.n_cob;
+  const int b = blockIdx.z;
   const int out_row0 = row_tile * RB;
-  const int n_pairs = a.Cout * KH;
-  float acc[2][KW];
-#pragma unroll
-  for (int p = 0; p < 2; ++p)
-#pragma unroll
-    for (int d = 0; d < KW; ++d) acc[p][d] = 0.f;
+  const int n_tiles = (a.T_out + kWgTB - 1) / kWgTB, per = (n_tiles + a.t_splits - 1) / a.t_splits;
+  const int tile_lo = tsp * per, tile_hi = min(n_tiles, tile_lo + per);
 
-  for (int t0 = 0; t0 < a.T_out; t0 += kWgTB) {
+  float acc[kWgCO][KW];
+#pragma unroll
+  for (int c = 0; c < kWgCO; ++c)
+#pragma unroll
+    for (int d = 0; d < KW; ++d) acc[c][d] = 0.f;
+
+  for (int tile = tile_lo; tile < tile_hi; ++tile) {
+    const int t0 = tile * kWgTB;
     __syncthreads();
-    for (int i = tid; i < RIN * XP; i += blockDim.x) {
-      const int row = i / XP, j = i - row * XP;
-      int v = out_row0 * SR + a.row_off + row;
-      if (a.row_circ) {
-        v %= a.rows_v;
-        if (v < 0) v += a.rows_v;
-      }
-      int t = t0 - a.pad_t + j;
+    // ---- inputs: one warp per (channel, row) line, four lines of loads in flight
+    {
+      int t = t0 - a.pad_t + lane;
       if (a.time_circ) {
         t %= a.T_in;
         if (t < 0) t += a.T_in;
+      } else if (t < 0 || t >= a.T_in) {
+        t = -1;
       }
-      float val = 0.f;
-      if (j < XW && v >= 0 && v < a.rows_v && t >= 0 && t < a.T_in) {
-        const float* src = (ci < a.c0) ? a.in0 + b * a.bs0 + (long long)(ci * a.rows0 + v) * a.T_in
-                                       : a.in1 + b * a.bs1 + (long long)((ci - a.c0) * a.rows1 + v % a.rows1) * a.T_in;
-        val = __ldg(src + t);
-      }
-      xs[i] = val;
-    }
-    for (int i = tid; i < a.Cout * RB * kWgTB; i += blockDim.x) {
-      const int j = i % kWgTB, r = (i / kWgTB) % RB, co = i / (kWgTB * RB);
-      const int orow = out_row0 + r, t = t0 + j;
-      gs[i] = (orow < a.rows_out && t < a.T_out) ? __ldg(a.dz + (((long long)b * a.Cout + co) * a.rows_out + orow) * a.T_out + t) : 0.f;
-    }
-    __syncthreads();
+      if (lane >= XW) t = -1;
+      for (int line0 = warp; line0 < kWgCI * RIN; line0 += 4 * NW) {
+        float xv[4];
 #pragma unroll
-    for (int pp = 0; pp < 2; ++pp) {
-      const int p = tid + 256 * pp;
-      if (p < n_pairs) {
-        const int co = p / KH, dr = p - co * KH;
-#pragma unroll 1
-        for (int r = 0; r < RB; ++r) {
-          const float* xr = xs + (r * SR + dr) * XP;
-          const float* gr = gs + (co * RB + r) * kWgTB;
-          float x[XP], g[kWgTB];
-#pragma unroll
-          for (int q = 0; q < XP / 4; ++q) {
-            const float4 v4 = *reinterpret_cast<const float4*>(xr + 4 * q);
-            x[4 * q] = v4.x, x[4 * q + 1] = v4.y, x[4 * q + 2] = v4.z, x[4 * q + 3] = v4.w;
+        for (int u = 0; u < 4; ++u) {
+          const int line = line0 + u * NW;
+          const int ci = line / RIN, row = line - ci * RIN, ch = cib * kWgCI + ci;
+          int v = out_row0 * SR + a.row_off + row;
+          if (a.row_circ) {
+            v %= a.rows_v;
+            if (v < 0) v += a.rows_v;
           }
-#pragma unroll
-          for (int q = 0; q < kWgTB / 4; ++q) {
-            const float4 v4 = *reinterpret_cast<const float4*>(gr + 4 * q);
-            g[4 * q] = v4.x, g[4 * q + 1] = v4.y, g[4 * q + 2] = v4.z, g[4 * q + 3] = v4.w;
+          xv[u] = 0.f;
+          if (line < kWgCI * RIN && ch < a.Cin && v >= 0 && v < a.rows_v && t >= 0) {
+            const float* src = (ch < a.c0) ? a.in0 + b * a.bs0 + (long long)(ch * a.rows0 + v) * a.T_in
+                                           : a.in1 + b * a.bs1 + (long long)((ch - a.c0) * a.rows1 + v % a.rows1) * a.T_in;
+            xv[u] = __ldg(src + t);
           }
+        }
 #pragma unroll
-          for (int j = 0; j < kWgTB; ++j)
-#pragma unroll
-            for (int d = 0; d < KW; ++d) acc[pp][d] = fmaf(g[j], x[j + d], acc[pp][d]);
+        for (int u = 0; u < 4; ++u) {
+          const int line = line0 + u * NW;
+          if (line < kWgCI * RIN && lane < XP) xs[line * XP + lane] = xv[u];
         }
       }
     }
+    // ---- output gradients, transposed to [row][frame][co]
+    for (int i = tid; i < kWgCO * RB * kWgTB; i += NT) {
+      const int j = i % kWgTB, r = (i / kWgTB) % RB, co = i / (kWgTB * RB);
+      const int orow = out_row0 + r, t = t0 + j, cg = cob * kWgCO + co;
+      gs[r * kWgGP + j * kWgCO + co] =
+          (cg < a.Cout && orow < a.rows_out && t < a.T_out) ? __ldg(a.dz + (((long long)b * a.Cout + cg) * a.rows_out + orow) * a.T_out + t) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int r = rs; r < RB; r += RS) {
+      const float* xr = xs + (cil * RIN + r * SR + dr) * XP;
+      const float* gr = gs + r * kWgGP;
+      float x[XP];
+#pragma unroll
+      for (int q = 0; q < XP / 4; ++q) {
+        const float4 v4 = *reinterpret_cast<const float4*>(xr + 4 * q);
+        x[4 * q] = v4.x, x[4 * q + 1] = v4.y, x[4 * q + 2] = v4.z, x[4 * q + 3] = v4.w;
+      }
+#pragma unroll
+      for (int j = 0; j < kWgTB; ++j) {
+        const float4 g0 = *reinterpret_cast<const float4*>(gr + j * kWgCO), g1 = *reinterpret_cast<const float4*>(gr + j * kWgCO + 4);
+        const float g[kWgCO] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+        for (int c = 0; c < kWgCO; ++c)
+#pragma unroll
+          for (int d = 0; d < KW; ++d) acc[c][d] = fmaf(g[c], x[j + d], acc[c][d]);
+      }
+    }
   }
+  // ---- sum the RS row shares (consecutive lanes), one atomic per weight and block
 #pragma unroll
-  for (int pp = 0; pp < 2; ++pp) {
-    const int p = tid + 256 * pp;
-    if (p < n_pairs) {
-      const int co = p / KH, dr = p - co * KH;
-      float* dst = a.dw + (((long long)co * a.Cin + ci) * KH + dr) * KW;
+  for (int c = 0; c < kWgCO; ++c)
 #pragma unroll
-      for (int d = 0; d < KW; ++d) atomicAdd(dst + d, acc[pp][d]);
+    for (int d = 0; d < KW; ++d) {
+      float v = acc[c][d];
+#pragma unroll
+      for (int o = RS / 2; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      acc[c][d] = v;
+    }
+  const int ch = cib * kWgCI + cil;
+  if (rs == 0 && ch < a.Cin && tile_lo < tile_hi) {
+#pragma unroll
+    for (int c = 0; c < kWgCO; ++c) {
+      const int cg = cob * kWgCO + c;
+      if (cg >= a.Cout) break;
+      float* dst = a.dw + (((long long)cg * a.Cin + ch) * KH + dr) * KW;
+#pragma unroll
+      for (int d = 0; d < KW; ++d) atomicAdd(dst + d, acc[c][d]);
     }
   }
 }
