@@ -19,6 +19,7 @@
 #include "pcn_train_kernels.cuh"
 #include "pcn_umma.cuh"
 #include "pcn_p2p1.cuh"
+#include "pcn_train_tc.cuh"
 
 namespace ake {
 
@@ -149,6 +150,7 @@ struct ake_pcn {
   __half* d_wimg_genre = nullptr;   // first conv of the genre head (1 x 7, 16 -> 32): one 16 KB stage
   __half* d_wimg_tail = nullptr;    // last conv of the tonic / key / genre heads (head_tail_umma_kernel), 12 KB each
   bool umma_heads = false;
+  bool umma_dirty = false;  // parameters uploaded since the operand images were last built (built lazily by the next eval-mode forward)
   std::map<std::string, std::pair<const float*, int64_t>> taps;
   // activations kept by the bn_mode = 2 forwards that have not been back-propagated yet, keyed by their workspace
   // (pcn_train.cuh): several kept forwards may be outstanding (summed losses, siamese use), each with its own workspace
@@ -387,7 +389,7 @@ static void launch_conv_t(ConvArgs a, int B, int max_tg, cudaStream_t st) {
   dim3 grid(n_tiles, a.n_row_tiles * (a.cout_pad / CO_T), B);
   // few blocks (the 8-clip training step): a block is alone on its SM and its staging phase is latency-bound with 3-4 warps;
   // extra warps only stage (the kernel's `active` guard keeps them out of the arithmetic)
-  if ((long long)grid.x * grid.y * grid.z <= 2LL * sm_count()) threads = 256;
+  if ((long long)grid.x * grid.y * grid.z <= 4LL * sm_count()) threads = 256;
   kern<<<grid, threads, smem, st>>>(a);
   AKE_LAUNCHED();
 }
@@ -398,8 +400,13 @@ static void launch_conv(const ConvArgs& a, const ConvGeom& g, int co_tile, int B
     // few blocks (small batch: the 8-clip training step): four output channels per thread instead of eight doubles the blocks of
     // the equivariant convs (5.40 -> 5.21 ms per step); the accumulation order of an output does not depend on the tiling
     if (co_tile == 8 && (long long)cdiv(cdiv(a.T_out, 4), 8) * (a.cout_pad / 8) * B < 2LL * sm_count()) co_tile = 4;
+    // ... and two per thread once more when even that leaves the GPU with fewer than two blocks per SM (a thread's serial FMA chain
+    // -- Cin x 84 taps x co_tile x 4 frames -- is what the launch waits for)
+    static const int min_tile = [] { const char* e = getenv("AKE_EQUIV_MIN_TILE"); return e ? atoi(e) : 2; }();
+    if (co_tile == 4 && min_tile <= 2 && (long long)cdiv(cdiv(a.T_out, 4), 8) * (a.cout_pad / 4) * B < 2LL * sm_count()) co_tile = 2;
     if (co_tile == 8) return launch_conv_t<12, 7, 1, 12, 8, 4>(a, B, 8, st);
     if (co_tile == 4) return launch_conv_t<12, 7, 1, 12, 4, 4>(a, B, 8, st);
+    if (co_tile == 2) return launch_conv_t<12, 7, 1, 12, 2, 4>(a, B, 8, st);
     if (co_tile == 1) return launch_conv_t<12, 7, 1, 12, 1, 4>(a, B, 8, st);
   } else if (g.KH == 7 && g.KW == 7 && g.SR == 1) {
     if (co_tile == 8) return launch_conv_t<7, 7, 1, 32, 8, 8>(a, B, 4, st);
@@ -452,6 +459,13 @@ struct Fwd {
   int os_key = 12, os_tonic = 12, os_genre = 11;  // floats between consecutive clips' outputs (35: (B, 35) result rows)
   double* d_stats = nullptr;  // train: per conv channel (sum, sumsq)
   float* d_ss_train = nullptr;
+  float* d_mi_train = nullptr;  // kept forward: [mean | invstd] per conv channel for the BatchNorm backward
+  // kept forward / backward: 7x7 convolutions on the tensor cores (pcn_train_tc.cuh); scratch shared by every site of the pass
+  bool tc_ready = false;
+  __half* tc_hi = nullptr;
+  __half* tc_lo = nullptr;
+  float* tc_raw = nullptr;
+  __half* tc_wimg = nullptr;
 
   Fwd(ake_pcn* p_, int B_, int T_, bool train_, void* ws, size_t ws_bytes, cudaStream_t st_)
       : p(p_), B(B_), T(T_), train(train_), dry(ws == nullptr), st(st_), arena(ws, ws_bytes) {}
@@ -476,19 +490,69 @@ struct Fwd {
 
   // Batch statistics of channels [coff, coff+C) of `v`, then scale/shift for the train-mode epilogue.
   void train_bn(const Conv& c, const View& v, int coff) {
+    if (dry) return;
+    const int rt = v.R * v.T;
+    dim3 grid(std::max(1, std::min(64, (int)cdiv64((long long)B * rt, 4096))), c.Cout);
+    bn_stats_kernel<<<grid, 256, 0, st>>>(v.p, B, v.C, coff, rt, d_stats + 2 * c.ss_off);
+    AKE_LAUNCHED();
+    train_bn_finalize(c, rt);
+  }
+  // ... the second half: (sum, sumsq) of conv `c` over B * rt elements per channel -> scale / shift (+ mean / invstd, running-stat inputs)
+  void train_bn_finalize(const Conv& c, int rt) {
     const BnSite& bn = p->bns[c.bn];
     double* stats = d_stats + 2 * c.ss_off;
     if (dry) return;
-    const int rt = v.R * v.T;
     if (p->bn_count.size() != p->bns.size()) p->bn_count.assign(p->bns.size(), 0);
     p->bn_count[c.bn] = (int64_t)B * rt;
-    dim3 grid(std::max(1, std::min(64, (int)cdiv64((long long)B * rt, 4096))), c.Cout);
-    bn_stats_kernel<<<grid, 256, 0, st>>>(v.p, B, v.C, coff, rt, stats);
-    AKE_LAUNCHED();
     bn_finalize_kernel<<<cdiv(c.Cout, 64), 64, 0, st>>>(stats, (double)B * rt, p->d_params + bn.gamma,
                                                          p->d_params + bn.beta, c.Cout, d_ss_train + c.ss_off,
                                                          d_ss_train + p->n_ss + c.ss_off,
-                                                         bn_stats_out ? bn_stats_out + 2 * bn.stat_off : nullptr);
+                                                         bn_stats_out ? bn_stats_out + 2 * bn.stat_off : nullptr,
+                                                         d_mi_train ? d_mi_train + c.ss_off : nullptr,
+                                                         d_mi_train ? d_mi_train + p->n_ss + c.ss_off : nullptr);
+    AKE_LAUNCHED();
+  }
+
+  // ---- train mode: a 7x7 circular convolution (or its data gradient) on the tensor cores (pcn_train_tc.cuh)
+  bool tc_conv_ok(const Conv& c, const ConvGeom& g, int Tn) const {
+    static const bool on = [] { const char* e = getenv("AKE_TRAIN_TC"); return e ? atoi(e) != 0 : true; }();
+    return on && p->umma && g.KH == 7 && g.KW == 7 && g.SR == 1 && g.row_circ && g.time_circ && g.row_off == -3 && g.pad_t == 3 &&
+           g.rows_v == g.rows_out && c.Cin <= 8 && c.Cout <= 8 && Tn >= 7;
+  }
+  // out = conv(cat[in0, tile(in1)], W) + bias   (dgrad = false; `stats` += the BatchNorm sums of the result), or
+  // out = the data gradient of that conv for the output gradient in0 (dgrad = true; maxbits: largest |in0| as float bits)
+  void tc_conv(const View& in0, const View* in1, const Conv& c, bool dgrad, const unsigned* maxbits, View& out, double* stats) {
+    const int P = in0.R, Tn = in0.T, Wd = Tn + 6;
+    if (!tc_ready) {
+      const size_t halves = (size_t)B * (P + 6) * Wd * 8;
+      tc_hi = arena.take<__half>(halves), tc_lo = arena.take<__half>(halves);
+      tc_raw = arena.take<float>((size_t)B * P * Tn * 8);
+      tc_wimg = arena.take<__half>(kP2PWBytes / 2);
+      tc_ready = true;
+    }
+    if (dry) return;
+    ProfScope prof("pcn.p2p", st);
+    if (dgrad) p2p_pack_weights_flip_kernel<<<14, 256, 0, st>>>(p->d_params + c.w_off, c.Cout, c.Cin, tc_wimg);
+    else p2p_pack_weights_kernel<<<14, 256, 0, st>>>(p->d_params + c.w_off, c.Cout, c.Cin, tc_wimg);
+    AKE_LAUNCHED();
+    TcPackArgs pa{};
+    pa.in0 = in0.p, pa.bs0 = in0.bstride(), pa.c0 = in0.C;
+    pa.in1 = in1 ? in1->p : in0.p, pa.bs1 = in1 ? in1->bstride() : 0, pa.c1 = in1 ? in1->C : 0, pa.rows1 = in1 ? in1->R : 1;
+    pa.B = B, pa.P = P, pa.T = Tn, pa.Wd = Wd, pa.maxbits = maxbits, pa.hi = tc_hi, pa.lo = tc_lo;
+    tc_pack_planes_kernel<<<ew_blocks((long long)B * (P + 6) * Wd), 256, 0, st>>>(pa);
+    AKE_LAUNCHED();
+    const int n_tt = cdiv(Tn, kP2PMaxTB), TB = cdiv(Tn, n_tt), n_rt = cdiv(P, kP2PRows), n_tiles = B * n_rt * n_tt;
+    const size_t smem = p2p_smem_bytes(TB + 6);
+    ensure_dyn_smem(p2p_umma_kernel<false, true>, smem);
+    check_decode_range((long long)n_tiles, (long long)n_rt * n_tt, "Pitch2Pitch (training)");
+    P2PArgs a{tc_hi, tc_lo, nullptr, nullptr, tc_wimg, p->d_ss_raw, p->d_ss_raw, P, Tn, Wd, TB, n_tt, n_rt, n_tiles, nullptr, nullptr, tc_raw};
+    p2p_umma_kernel<false, true><<<std::min(n_tiles, sm_count()), kP2PThreads, smem, st>>>(a);
+    AKE_LAUNCHED();
+    TcUnpackArgs ua{};
+    ua.raw = tc_raw, ua.out = out.p, ua.maxbits = maxbits, ua.B = B, ua.P = P, ua.T = Tn, ua.stats = stats;
+    ua.C = dgrad ? c.Cin : c.Cout;
+    ua.bias = (!dgrad && c.has_bias) ? p->d_params + c.b_off : nullptr;
+    tc_unpack_kernel<<<std::min<int>((int)cdiv64((long long)B * P * Tn, 256), 4 * sm_count()), 256, 0, st>>>(ua);
     AKE_LAUNCHED();
   }
 
@@ -1176,6 +1240,8 @@ static void free_device_state(ake_pcn* p) {
   p->has_params = false;
 }
 
+static void pack_umma_images(ake_pcn* p, cudaStream_t st);
+
 static void upload_params(ake_pcn* p, const float* flat_dev, int64_t n, cudaStream_t st) {
   if (n != p->n_params) fail(AKE_ERR_INVALID, "expected %lld parameter floats, got %lld", (long long)p->n_params, (long long)n);
   // The plan's buffers live on the device that is current at upload time; a module moved to another GPU re-uploads there.
@@ -1205,7 +1271,17 @@ static void upload_params(ake_pcn* p, const float* flat_dev, int64_t n, cudaStre
         p->d_ss_eval + p->n_ss + c.ss_off, p->d_ss_raw + c.ss_off, p->d_ss_raw + p->n_ss + c.ss_off);
     AKE_LAUNCHED();
   }
+  // The fp16 hi/lo operand images of the tensor-core path only serve eval-mode forwards: a training loop uploads new
+  // parameters every step and never reads them, so after the first build they are rebuilt lazily (ensure_umma_images).
   if (p->umma) {
+    if (!p->d_wimg_pc) pack_umma_images(p, st);
+    else p->umma_dirty = true;
+  }
+  p->has_params = true;
+}
+
+static void pack_umma_images(ake_pcn* p, cudaStream_t st) {
+  {
     if (!p->d_wimg) AKE_CUDA(cudaMalloc(&p->d_wimg, (size_t)kP2PWBytes * p->umma_convs.size()));
     for (size_t i = 0; i < p->umma_convs.size(); ++i) {
       const Conv& c = p->convs[p->umma_convs[i]];
@@ -1287,7 +1363,11 @@ static void upload_params(ake_pcn* p, const float* flat_dev, int64_t n, cudaStre
       }
     }
   }
-  p->has_params = true;
+  p->umma_dirty = false;
+}
+
+static inline void ensure_umma_images(ake_pcn* p, cudaStream_t st) {
+  if (p->umma && p->umma_dirty) pack_umma_images(p, st);
 }
 
 }  // namespace ake
@@ -1438,6 +1518,7 @@ int ake_pcn_forward_f32(ake_pcn* p, const float* mel_dev, int B, int T, const in
     if (current_device() != p->device)
       fail(AKE_ERR_INVALID, "the plan's weights live on device %d but device %d is current: upload the parameters there first", p->device,
            current_device());
+    if (bn_mode == 0) ensure_umma_images(p, static_cast<cudaStream_t>(stream));
     ProfScope prof("pcn.total", static_cast<cudaStream_t>(stream));
     Fwd f(p, B, T, bn_mode != 0, ws_dev, ws_bytes, static_cast<cudaStream_t>(stream));
     f.seq_len = seq_len_dev, f.bn_stats_out = bn_stats_out_dev;
@@ -1468,6 +1549,7 @@ int ake_pcn_forward_rows_f32(ake_pcn* p, const float* mel_dev, int B, int T, con
       fail(AKE_ERR_INVALID, "the plan's weights live on device %d but device %d is current: upload the parameters there first", p->device,
            current_device());
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    ensure_umma_images(p, st);
     ProfScope prof("pcn.total", st);
     // without a genre head the genre columns stay zero
     if (!p->cfg.genre) AKE_CUDA(cudaMemsetAsync(rows_out_dev, 0, sizeof(float) * AKE_ROW_FLOATS * (size_t)B, st));

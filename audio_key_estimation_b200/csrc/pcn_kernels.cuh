@@ -424,16 +424,19 @@ __global__ void bn_stats_kernel(const float* __restrict__ in, int B, int C_total
 // scale = gamma / sqrt(var + eps), shift = beta - mean * scale (the conv bias is already inside the raw values)
 __global__ void bn_finalize_kernel(const double* __restrict__ stats, double count, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, int C, float* __restrict__ scale,
-                                   float* __restrict__ shift, float* __restrict__ stats_out) {
+                                   float* __restrict__ shift, float* __restrict__ stats_out, float* __restrict__ mean_out = nullptr,
+                                   float* __restrict__ invstd_out = nullptr) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const double mean = stats[2 * c] / count;
   double var = stats[2 * c + 1] / count - mean * mean;
   if (var < 0.0) var = 0.0;
-  const double s = (double)gamma[c] / sqrt(var + (double)kBnEps);
+  const double is = 1.0 / sqrt(var + (double)kBnEps);
+  const double s = (double)gamma[c] * is;
   scale[c] = (float)s;
   shift[c] = (float)((double)beta[c] - mean * s);
   if (stats_out) stats_out[c] = (float)mean, stats_out[C + c] = (float)var;
+  if (mean_out) mean_out[c] = (float)mean, invstd_out[c] = (float)is;  // kept for the BatchNorm backward (pcn_train.cuh)
 }
 
 // in-place y = act(x*scale[c] + shift[c]) over channels [coff, coff+C) of a (B, C_total, R*T) tensor

@@ -34,22 +34,17 @@ struct TrainTape {
   bool genre = false;
   float* d_ss = nullptr;  // [scale | shift] of every BN site of this forward (batch statistics), n_ss each
   float* d_mi = nullptr;  // [mean | invstd], n_ss each
+  // scratch of the tensor-core 7x7 convolutions (pcn_train_tc.cuh), carved by the forward and reused by the backward
+  bool tc_ready = false;
+  __half* tc_hi = nullptr;
+  __half* tc_lo = nullptr;
+  float* tc_raw = nullptr;
+  __half* tc_wimg = nullptr;
 };
 
 __global__ void fill_kernel(float* __restrict__ x, int n, float v) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) x[i] = v;
-}
-
-__global__ void bn_mean_invstd_kernel(const double* __restrict__ stats, double count, int C, float* __restrict__ mean,
-                                      float* __restrict__ invstd) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  const double m = stats[2 * c] / count;
-  double var = stats[2 * c + 1] / count - m * m;
-  if (var < 0.0) var = 0.0;
-  mean[c] = (float)m;
-  invstd[c] = (float)(1.0 / sqrt(var + (double)kBnEps));
 }
 
 template <int KH, int KW, int SR, int RB, int RS>
@@ -95,14 +90,8 @@ void Fwd::run_keep(const float* mel, float* key_out, float* tonic_out, float* ge
   tp.d_ss = d_ss_train, tp.d_mi = d_mi;
   tp.mel.p = const_cast<float*>(mel), tp.mel.C = 1, tp.mel.R = P, tp.mel.T = T;
 
-  auto stats_of = [&](const Conv& c, const View& z) {
-    train_bn(c, z, 0);
-    if (!dry) {
-      bn_mean_invstd_kernel<<<cdiv(c.Cout, 64), 64, 0, st>>>(d_stats + 2 * c.ss_off, (double)B * z.R * z.T, c.Cout, d_mi + c.ss_off,
-                                                             d_mi + p->n_ss + c.ss_off);
-      AKE_LAUNCHED();
-    }
-  };
+  d_mi_train = d_mi;  // bn_finalize_kernel also writes the mean / inverse standard deviation the backward pass needs
+  auto stats_of = [&](const Conv& c, const View& z) { train_bn(c, z, 0); };
   auto bn_act = [&](const Conv& c, const View& z) {
     View a = alloc(z.C, z.R, z.T);
     if (!dry) {
@@ -119,6 +108,16 @@ void Fwd::run_keep(const float* mel, float* key_out, float* tonic_out, float* ge
     s.id = id, s.in0 = in0, s.g = g, s.has_bn = c.bn >= 0;
     if (in1) s.in1 = *in1;
     s.z = alloc(c.Cout, g.rows_out, g.T_out);
+    if (tc_conv_ok(c, g, in0.T)) {
+      // 7x7 circular conv on the tensor cores; the BatchNorm sums of z come out of the same pass
+      tc_conv(in0, in1, c, false, nullptr, s.z, s.has_bn ? d_stats + 2 * c.ss_off : nullptr);
+      s.a = s.z;
+      if (s.has_bn) {
+        train_bn_finalize(c, s.z.R * s.z.T);
+        if (act_now) s.a = bn_act(c, s.z);
+      }
+      return s;
+    }
     conv(id, in0, in1, g, s.z, 0, false);
     s.a = s.z;
     if (s.has_bn) {
@@ -213,6 +212,7 @@ void Fwd::run_keep(const float* mel, float* key_out, float* tonic_out, float* ge
                                                                                tonic_out, genre_out);
     AKE_LAUNCHED();
   }
+  tp.tc_ready = tc_ready, tp.tc_hi = tc_hi, tp.tc_lo = tc_lo, tp.tc_raw = tc_raw, tp.tc_wimg = tc_wimg;
   tp.ws_off = arena.off;
   tp.valid = !dry;
 }
@@ -243,10 +243,14 @@ void Fwd::backward_keep(const TrainTape& tp, const float* d_key, const float* d_
   const ake_pcn_config& cfg = p->cfg;
   const int P = cfg.pitches, k = cfg.kernel_size;
   const int n_ss = p->n_ss;
+  tc_ready = tp.tc_ready, tc_hi = tp.tc_hi, tc_lo = tp.tc_lo, tc_raw = tp.tc_raw, tc_wimg = tp.tc_wimg;
   float* ones = arena.take<float>(64);
   float* zeros = arena.take<float>(64);
   double* bsums = arena.take<double>(2 * (size_t)n_ss);
+  unsigned* d_maxbits = arena.take<unsigned>(64);  // largest |dz| per tensor-core data gradient (its operand scale)
+  int n_maxbits = 0;
   if (!dry) {
+    AKE_CUDA(cudaMemsetAsync(d_maxbits, 0, sizeof(unsigned) * 64, st));
     AKE_CUDA(cudaMemsetAsync(grads, 0, sizeof(float) * p->n_params, st));
     AKE_CUDA(cudaMemsetAsync(zeros, 0, sizeof(float) * 64, st));
     AKE_CUDA(cudaMemsetAsync(bsums, 0, sizeof(double) * 2 * n_ss, st));
@@ -256,7 +260,7 @@ void Fwd::backward_keep(const TrainTape& tp, const float* d_key, const float* d_
   auto zalloc = [&](const View& like) { return alloc(like.C, like.R, like.T); };
 
   // BatchNorm + LeakyReLU backward of conv `id`: da (grad w.r.t. the activation) -> dz; writes dgamma / dbeta
-  auto bn_bwd = [&](int id, const View& z, const View& da) {
+  auto bn_bwd = [&](int id, const View& z, const View& da, unsigned* maxbits = nullptr) {
     const Conv& c = p->convs[id];
     const BnSite& bn = p->bns[c.bn];
     View dz = zalloc(z);
@@ -270,7 +274,7 @@ void Fwd::backward_keep(const TrainTape& tp, const float* d_key, const float* d_
     bn_bwd_reduce_kernel<<<grid, 256, 0, st>>>(z.p, da.p, B, c.Cout, RT, sc, sh, mu, is, bsums + 2 * c.ss_off);
     AKE_LAUNCHED();
     bn_bwd_apply_kernel<<<ew_blocks(z.numel(B)), 256, 0, st>>>(z.p, da.p, dz.p, B, c.Cout, RT, sc, sh, mu, is, bsums + 2 * c.ss_off,
-                                                              (double)B * RT, grads + bn.gamma, grads + bn.beta);
+                                                              (double)B * RT, grads + bn.gamma, grads + bn.beta, maxbits);
     AKE_LAUNCHED();
     return dz;
   };
@@ -299,7 +303,9 @@ void Fwd::backward_keep(const TrainTape& tp, const float* d_key, const float* d_
       cudaStream_t v;
       ~Restore() { s = v; }
     } restore{st, main_st};
-    bias_grad(c, dz);
+    // a conv bias in front of a train-mode BatchNorm has an exactly-zero gradient (dz sums to zero per channel; the reference
+    // leaves ~1e-15 of rounding there): the zeroed gradient buffer already holds it
+    if (!s.has_bn) bias_grad(c, dz);
     WgradArgs a{};
     a.in0 = s.in0.p, a.c0 = s.in0.C, a.rows0 = s.in0.R, a.bs0 = s.in0.bstride();
     if (s.in1.p) a.in1 = s.in1.p, a.c1 = s.in1.C, a.rows1 = s.in1.R, a.bs1 = s.in1.bstride();
@@ -311,8 +317,13 @@ void Fwd::backward_keep(const TrainTape& tp, const float* d_key, const float* d_
     launch_wgrad(a, s.g, B, st);
   };
   // data gradient of a stride-1 convolution: the forward kernel on dz with flipped / transposed weights
-  auto dgrad = [&](const ConvSite& s, const View& dz, View& dx, bool accumulate) {
+  auto dgrad = [&](const ConvSite& s, const View& dz, View& dx, bool accumulate, const unsigned* maxbits = nullptr) {
     const Conv& c = p->convs[s.id];
+    if (maxbits) {  // tensor-core data gradient (the caller checked tc_conv_ok and had bn_bwd record the largest |dz|)
+      if (accumulate || dx.C != c.Cin) fail(AKE_ERR_INVALID, "internal: tensor-core dgrad overwrites a (B, Cin, P, T) tensor");
+      tc_conv(dz, nullptr, c, true, maxbits, dx, nullptr);
+      return;
+    }
     const int tile = co_tile_for(c.Cin), cin_pad = cdiv(c.Cin, tile) * tile;
     float* wd = arena.take<float>((size_t)c.Cout * c.KH * c.KW * cin_pad);
     if (dry) return;
@@ -339,11 +350,13 @@ void Fwd::backward_keep(const TrainTape& tp, const float* d_key, const float* d_
   auto stack_bwd = [&](const std::vector<ConvSite>& sites, View d_a, int first) {
     for (int i = (int)sites.size() - 1; i >= first; --i) {
       const ConvSite& s = sites[i];
-      View dz = bn_bwd(s.id, s.z, d_a);
-      wgrad(s, dz);
       const Conv& c = p->convs[s.id];
+      unsigned* mb = nullptr;
+      if (tc_conv_ok(c, s.g, s.in0.T) && n_maxbits < 64) mb = d_maxbits + n_maxbits++;
+      View dz = bn_bwd(s.id, s.z, d_a, mb);
+      wgrad(s, dz);
       View dx = alloc(c.Cin, s.in0.R, s.in0.T);
-      dgrad(s, dz, dx, false);
+      dgrad(s, dz, dx, false, mb);
       d_a = dx;
     }
     return d_a;
@@ -418,8 +431,7 @@ void Fwd::backward_keep(const TrainTape& tp, const float* d_key, const float* d_
       tile_sum_kernel<<<ew_blocks(d_up.numel(B)), 256, 0, st>>>(dX0.p, B, dX0.C, 1, d_up.C, P, dX0.T, d_up.p);
       AKE_LAUNCHED();
     }
-    View dz_up = bn_bwd(p->layers[1].up, tp.up_z, d_up);
-    bias_grad(cu, dz_up);
+    View dz_up = bn_bwd(p->layers[1].up, tp.up_z, d_up);  // (the ConvTranspose bias sits in front of a BatchNorm: zero gradient)
     if (!dry) {
       if (cu.Cin > 8) fail(AKE_ERR_UNSUPPORTED, "up_sixth backward: more than 8 channels");
       const long long n = (long long)B * 12 * pc0.T;

@@ -247,7 +247,8 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ z, const float* __
                                     int C, int RT, const float* __restrict__ scale, const float* __restrict__ shift,
                                     const float* __restrict__ mean, const float* __restrict__ invstd,
                                     const double* __restrict__ sums, double count, float* __restrict__ dgamma,
-                                    float* __restrict__ dbeta) {
+                                    float* __restrict__ dbeta, unsigned* __restrict__ maxbits = nullptr) {
+  unsigned mx = 0;  // largest |dz| as a float bit pattern (max is order-free): the scale of the tensor-core data gradient (pcn_train_tc.cuh)
   if (blockIdx.x == 0 && threadIdx.x < C) {
     dbeta[threadIdx.x] = (float)sums[2 * threadIdx.x];
     dgamma[threadIdx.x] = (float)sums[2 * threadIdx.x + 1];
@@ -261,7 +262,13 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ z, const float* __
     const float g = da[i] * (y > 0.f ? 1.f : kLeakySlope);
     const float xh = (zz - mu) * is;
     const float m1 = (float)(sums[2 * c] / count), m2 = (float)(sums[2 * c + 1] / count);
-    dz[i] = sc * (g - m1 - xh * m2);
+    const float d = sc * (g - m1 - xh * m2);
+    dz[i] = d;
+    mx = max(mx, __float_as_uint(fabsf(d)));
+  }
+  if (maxbits) {
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    if ((threadIdx.x & 31) == 0 && mx) atomicMax(maxbits, mx);
   }
 }
 

@@ -1,7 +1,8 @@
 """GPU parity of the training step (BASELINE config 5) against the reference's own
 general_step + loss.backward() frozen in tests/golden/train_step.npz.
-Tolerance: loss 1e-5 relative; every parameter gradient max-abs <= 2e-3 of that tensor's max |grad| (+1e-6):
-fp32 arithmetic with atomically accumulated weight gradients against a float64 reference."""
+Tolerance: loss 1e-5 relative; every parameter gradient max-abs <= 5e-4 of that tensor's max |grad| (+ a floor for the
+tensors whose gradient is exactly zero): fp32 arithmetic (7x7 convolutions: fp16 hi/lo three-product tensor-core operands,
+22 bits) with atomically accumulated weight gradients against a float64 reference; measured worst case 6e-5."""
 import numpy as np
 import pytest
 import torch
@@ -29,7 +30,7 @@ def _setup(genre, fwd_golden):
     return g, net, mel, seq, key_labels, tonic_1h, genre_1h.cuda()
 
 
-def _check_grads(net, g, tag, tol=2e-3):
+def _check_grads(net, g, tag, tol=5e-4):
     worst = 0.0
     n = 0
     # conv biases in front of a train-mode BatchNorm have an exactly-zero gradient (reference: ~1e-15): the floor is set by
@@ -42,7 +43,8 @@ def _check_grads(net, g, tag, tol=2e-3):
         err = np.abs(got - ref).max()
         scale = np.abs(ref).max()
         assert err <= tol * scale + floor, f"{name}: max-abs error {err:.3e} vs max |grad| {scale:.3e}"
-        worst = max(worst, err / (scale + 1e-12))
+        if scale > 100 * floor:  # (tensors whose gradient is exactly zero have no relative error)
+            worst = max(worst, err / scale)
         n += 1
     return n, worst
 
@@ -56,6 +58,7 @@ def test_fused_train_step_matches_reference(tag, fwd_golden):
     want = float(g[f"{tag}.loss"])
     assert abs(res["loss"].item() - want) <= 1e-5 * abs(want)
     n, worst = _check_grads(net, g, tag)
+    print(f"[{tag}] worst gradient error / max |grad| over {n} tensors: {worst:.3e}")
     assert n == (66 if genre else 60)
     # the flat buffer is what a data-parallel job all-reduces; world size 1 leaves it untouched
     before = step.flat_grads.clone()
