@@ -401,7 +401,7 @@ static void launch_conv(const ConvArgs& a, const ConvGeom& g, int co_tile, int B
     // the equivariant convs (5.40 -> 5.21 ms per step); the accumulation order of an output does not depend on the tiling
     if (co_tile == 8 && (long long)cdiv(cdiv(a.T_out, 4), 8) * (a.cout_pad / 8) * B < 2LL * sm_count()) co_tile = 4;
     // ... and two per thread once more when even that leaves the GPU with fewer than two blocks per SM (a thread's serial FMA chain
-    // -- Cin x 84 taps x co_tile x 4 frames -- is what the launch waits for)
+    // -- Cin x 84 taps x co_tile x 4 frames -- is what the launch waits for; one channel per thread was measured slower: 2.60 -> 2.81 ms)
     static const int min_tile = [] { const char* e = getenv("AKE_EQUIV_MIN_TILE"); return e ? atoi(e) : 2; }();
     if (co_tile == 4 && min_tile <= 2 && (long long)cdiv(cdiv(a.T_out, 4), 8) * (a.cout_pad / 4) * B < 2LL * sm_count()) co_tile = 2;
     if (co_tile == 8) return launch_conv_t<12, 7, 1, 12, 8, 4>(a, B, 8, st);
@@ -1257,18 +1257,22 @@ static void upload_params(ake_pcn* p, const float* flat_dev, int64_t n, cudaStre
     AKE_CUDA(cudaMalloc(&p->d_ss_raw, sizeof(float) * 2 * p->n_ss));
   }
   AKE_CUDA(cudaMemcpyAsync(p->d_params, flat_dev, sizeof(float) * n, cudaMemcpyDeviceToDevice, st));
-  for (const Conv& c : p->convs) {
-    if (!c.transposed && !c.norm_only) {
-      const int nn = c.Cin * c.KH * c.KW * c.cout_pad;
-      pack_conv_kernel<<<cdiv(nn, 256), 256, 0, st>>>(p->d_params + c.w_off, c.Cout, c.Cin, c.KH * c.KW, c.cout_pad,
-                                                     p->d_packed + c.packed_off);
-      AKE_LAUNCHED();
+  // repacked weights + folded epilogues of every convolution: one launch per kPackTableMax convolutions (pack_all_kernel)
+  for (size_t c0 = 0; c0 < p->convs.size(); c0 += kPackTableMax) {
+    PackTable t{};
+    t.n = (int)std::min<size_t>(kPackTableMax, p->convs.size() - c0), t.n_ss = p->n_ss;
+    int max_n = 1;
+    for (int i = 0; i < t.n; ++i) {
+      const Conv& c = p->convs[c0 + i];
+      const BnSite* bn = c.bn >= 0 ? &p->bns[c.bn] : nullptr;
+      PackEntry& e = t.e[i];
+      e.w_off = c.w_off, e.packed_off = c.packed_off, e.b_off = c.b_off;
+      e.gamma = bn ? bn->gamma : 0, e.beta = bn ? bn->beta : 0, e.mean = bn ? bn->mean : 0, e.var = bn ? bn->var : 0;
+      e.Cout = c.Cout, e.Cin = c.Cin, e.KHW = c.KH * c.KW, e.cout_pad = c.cout_pad, e.ss_off = c.ss_off;
+      e.pack = (!c.transposed && !c.norm_only) ? 1 : 0, e.has_bias = c.has_bias ? 1 : 0, e.has_bn = bn ? 1 : 0;
+      if (e.pack) max_n = std::max(max_n, c.Cin * c.KH * c.KW * c.cout_pad);
     }
-    const BnSite* bn = c.bn >= 0 ? &p->bns[c.bn] : nullptr;
-    fold_bn_kernel<<<cdiv(c.Cout, 64), 64, 0, st>>>(
-        c.has_bias ? p->d_params + c.b_off : nullptr, bn ? p->d_params + bn->gamma : nullptr, bn ? p->d_params + bn->beta : nullptr,
-        bn ? p->d_params + bn->mean : nullptr, bn ? p->d_params + bn->var : nullptr, c.Cout, p->d_ss_eval + c.ss_off,
-        p->d_ss_eval + p->n_ss + c.ss_off, p->d_ss_raw + c.ss_off, p->d_ss_raw + p->n_ss + c.ss_off);
+    pack_all_kernel<<<dim3(std::min(32, cdiv(max_n, 256)), t.n), 256, 0, st>>>(t, p->d_params, p->d_packed, p->d_ss_eval, p->d_ss_raw);
     AKE_LAUNCHED();
   }
   // The fp16 hi/lo operand images of the tensor-core path only serve eval-mode forwards: a training loop uploads new

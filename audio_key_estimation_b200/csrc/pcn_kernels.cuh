@@ -838,35 +838,47 @@ __global__ void __launch_bounds__(128) mirex_kernel(const float* __restrict__ ke
   }
 }
 
-// ---- parameter preparation ---------------------------------------------------------------------
-// Repack a (Cout,Cin,KH,KW) conv weight to [Cin][KH][KW][cout_pad] (zero padded output channels).
-__global__ void pack_conv_kernel(const float* __restrict__ w, int Cout, int Cin, int KHW, int cout_pad,
-                                 float* __restrict__ dst) {
-  const int n = Cin * KHW * cout_pad;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const int co = i % cout_pad, k = i / cout_pad;  // k = ci*KHW + tap
-    dst[i] = co < Cout ? w[(long long)co * Cin * KHW + k] : 0.f;
+// Conv weights (Cout, Cin, KH, KW) -> [Cin][KH*KW][cout_pad] (zero padded output channels), the eval-mode epilogue (BatchNorm folded on
+// the running statistics) and the raw epilogue (bias only):
+// ---- every convolution's repacked weights and folded epilogues in ONE launch (a training loop uploads new parameters each step:
+// ~35 separate 3 us launches otherwise).  The table travels as a kernel argument; blockIdx.y = table entry.
+struct PackEntry {
+  long long w_off, packed_off, b_off, gamma, beta, mean, var;  // float offsets into the flat parameter / packed buffers
+  int Cout, Cin, KHW, cout_pad, ss_off;
+  int pack;             // 1: repack the weights (false for transposed convs and norm-only sites)
+  int has_bias, has_bn;
+};
+constexpr int kPackTableMax = 32;
+struct PackTable {
+  int n, n_ss;
+  PackEntry e[kPackTableMax];
+};
+__global__ void __launch_bounds__(256) pack_all_kernel(const PackTable t, const float* __restrict__ params, float* __restrict__ packed,
+                                                       float* __restrict__ ss_eval, float* __restrict__ ss_raw) {
+  const PackEntry& e = t.e[blockIdx.y];
+  if (e.pack) {
+    const float* w = params + e.w_off;
+    float* dst = packed + e.packed_off;
+    const int n = e.Cin * e.KHW * e.cout_pad;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+      const int co = i % e.cout_pad, k = i / e.cout_pad;  // k = ci*KHW + tap
+      dst[i] = co < e.Cout ? w[(long long)co * e.Cin * e.KHW + k] : 0.f;
+    }
   }
-}
-
-// Eval-mode epilogue (BatchNorm folded on running statistics) and the raw epilogue (bias only).
-__global__ void fold_bn_kernel(const float* __restrict__ bias, const float* __restrict__ gamma,
-                               const float* __restrict__ beta, const float* __restrict__ mean,
-                               const float* __restrict__ var, int C, float* __restrict__ scale_eval,
-                               float* __restrict__ shift_eval, float* __restrict__ scale_raw,
-                               float* __restrict__ shift_raw) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  const double bb = bias ? (double)bias[c] : 0.0;
-  scale_raw[c] = 1.f;
-  shift_raw[c] = (float)bb;
-  if (gamma) {
-    const double s = (double)gamma[c] / sqrt((double)var[c] + (double)kBnEps);
-    scale_eval[c] = (float)s;
-    shift_eval[c] = (float)((bb - (double)mean[c]) * s + (double)beta[c]);
-  } else {
-    scale_eval[c] = 1.f;
-    shift_eval[c] = (float)bb;
+  if (blockIdx.x == 0) {
+    for (int c = threadIdx.x; c < e.Cout; c += blockDim.x) {
+      const double bb = e.has_bias ? (double)params[e.b_off + c] : 0.0;
+      ss_raw[e.ss_off + c] = 1.f;
+      ss_raw[t.n_ss + e.ss_off + c] = (float)bb;
+      if (e.has_bn) {
+        const double sc = (double)params[e.gamma + c] / sqrt((double)params[e.var + c] + (double)kBnEps);
+        ss_eval[e.ss_off + c] = (float)sc;
+        ss_eval[t.n_ss + e.ss_off + c] = (float)((bb - (double)params[e.mean + c]) * sc + (double)params[e.beta + c]);
+      } else {
+        ss_eval[e.ss_off + c] = 1.f;
+        ss_eval[t.n_ss + e.ss_off + c] = (float)bb;
+      }
+    }
   }
 }
 

@@ -249,6 +249,7 @@ void Fwd::backward_keep(const TrainTape& tp, const float* d_key, const float* d_
   double* bsums = arena.take<double>(2 * (size_t)n_ss);
   unsigned* d_maxbits = arena.take<unsigned>(64);  // largest |dz| per tensor-core data gradient (its operand scale)
   int n_maxbits = 0;
+  std::map<int, const float*> wd_of;  // conv id -> flipped / transposed weights of its FFMA data gradient
   if (!dry) {
     AKE_CUDA(cudaMemsetAsync(d_maxbits, 0, sizeof(unsigned) * 64, st));
     AKE_CUDA(cudaMemsetAsync(grads, 0, sizeof(float) * p->n_params, st));
@@ -325,12 +326,11 @@ void Fwd::backward_keep(const TrainTape& tp, const float* d_key, const float* d_
       return;
     }
     const int tile = co_tile_for(c.Cin), cin_pad = cdiv(c.Cin, tile) * tile;
-    float* wd = arena.take<float>((size_t)c.Cout * c.KH * c.KW * cin_pad);
     if (dry) return;
     if (dx.C != c.Cin) fail(AKE_ERR_INVALID, "internal: dgrad channel mismatch");
-    const int nn = c.Cout * c.KH * c.KW * cin_pad;
-    pack_conv_dgrad_kernel<<<cdiv(nn, 256), 256, 0, st>>>(p->d_params + c.w_off, c.Cout, c.Cin, c.KH, c.KW, cin_pad, wd);
-    AKE_LAUNCHED();
+    const auto wit = wd_of.find(s.id);
+    if (wit == wd_of.end()) fail(AKE_ERR_INVALID, "internal: no data-gradient weights were packed for conv %d", s.id);
+    const float* wd = wit->second;
     ConvArgs a{};
     a.in0 = dz.p, a.c0 = dz.C, a.rows0 = dz.R, a.bs0 = dz.bstride();
     a.in1 = dz.p, a.c1 = 0, a.rows1 = 1, a.bs1 = 0;
@@ -362,6 +362,35 @@ void Fwd::backward_keep(const TrainTape& tp, const float* d_key, const float* d_
     return d_a;
   };
 
+  // ---- flipped / transposed weights of every FFMA data-gradient convolution of this pass, packed by one launch
+  {
+    std::vector<const ConvSite*> sites = {&tp.ht[1], &tp.ht[0], &tp.hk[1], &tp.hk[0]};
+    if (tp.genre) sites.push_back(&tp.hg[1]), sites.push_back(&tp.hg[0]);
+    for (const ConvSite& s : tp.e1) sites.push_back(&s);
+    for (const ConvSite& s : tp.p)
+      if (!tc_conv_ok(p->convs[s.id], s.g, s.in0.T)) sites.push_back(&s);
+    for (const ConvSite& s : tp.e0) sites.push_back(&s);
+    std::vector<DgradPackEntry> ents;
+    size_t total = 0;
+    int max_n = 1;
+    for (const ConvSite* s : sites) {
+      const Conv& c = p->convs[s->id];
+      const int tile = co_tile_for(c.Cin), cin_pad = cdiv(c.Cin, tile) * tile;
+      const size_t n = (size_t)c.Cout * c.KH * c.KW * cin_pad;
+      ents.push_back(DgradPackEntry{c.w_off, (long long)total, c.Cout, c.Cin, c.KH, c.KW, cin_pad});
+      total += align_up(n, 64);
+      max_n = std::max(max_n, (int)n);
+    }
+    float* block = arena.take<float>(total);
+    for (size_t i = 0; i < sites.size(); ++i) wd_of[sites[i]->id] = block + ents[i].dst_off;
+    for (size_t i0 = 0; !dry && i0 < ents.size(); i0 += kDgradPackMax) {
+      DgradPackTable t{};
+      t.n = (int)std::min<size_t>(kDgradPackMax, ents.size() - i0);
+      for (int i = 0; i < t.n; ++i) t.e[i] = ents[i0 + i];
+      pack_dgrad_all_kernel<<<dim3(std::min(32, cdiv(max_n, 256)), t.n), 256, 0, st>>>(t, p->d_params, block);
+      AKE_LAUNCHED();
+    }
+  }
   // ---- masked means (+ sigmoid)
   const View& tf = tp.ht[1].z;
   View d_tf = zalloc(tf), d_kf = zalloc(tp.hk[1].z), d_gf;

@@ -22,18 +22,30 @@ __global__ void bn_act_out_kernel(const float* __restrict__ z, float* __restrict
   }
 }
 
-// Weights of the data-gradient convolution: dst[co][KH-1-dr][KW-1-dt][ci (padded)] = w[co][ci][dr][dt]
-// (the forward packing [Cin'][KH][KW][cout_pad'] with Cin' = Cout, Cout' = Cin, taps flipped).
-__global__ void pack_conv_dgrad_kernel(const float* __restrict__ w, int Cout, int Cin, int KH, int KW, int cin_pad,
-                                       float* __restrict__ dst) {
-  const int n = Cout * KH * KW * cin_pad;
+// Weights of the data-gradient convolutions: dst[co][KH-1-dr][KW-1-dt][ci (padded)] = w[co][ci][dr][dt]
+// (the forward packing [Cin'][KH][KW][cout_pad'] with Cin' = Cout, Cout' = Cin, taps flipped), every site of a backward pass in one
+// launch: the table travels as a kernel argument, blockIdx.y = table entry.
+struct DgradPackEntry {
+  long long w_off, dst_off;  // float offsets into the flat parameters / the pass's scratch block
+  int Cout, Cin, KH, KW, cin_pad;
+};
+constexpr int kDgradPackMax = 32;
+struct DgradPackTable {
+  int n;
+  DgradPackEntry e[kDgradPackMax];
+};
+__global__ void __launch_bounds__(256) pack_dgrad_all_kernel(const DgradPackTable t, const float* __restrict__ params, float* __restrict__ scratch) {
+  const DgradPackEntry& e = t.e[blockIdx.y];
+  const float* w = params + e.w_off;
+  float* dst = scratch + e.dst_off;
+  const int n = e.Cout * e.KH * e.KW * e.cin_pad;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const int ci = i % cin_pad;
-    int q = i / cin_pad;
-    const int dt = q % KW;
-    q /= KW;
-    const int dr = q % KH, co = q / KH;
-    dst[i] = ci < Cin ? w[(((long long)co * Cin + ci) * KH + (KH - 1 - dr)) * KW + (KW - 1 - dt)] : 0.f;
+    const int ci = i % e.cin_pad;
+    int q = i / e.cin_pad;
+    const int dt = q % e.KW;
+    q /= e.KW;
+    const int dr = q % e.KH, co = q / e.KH;
+    dst[i] = ci < e.Cin ? w[(((long long)co * e.Cin + ci) * e.KH + (e.KH - 1 - dr)) * e.KW + (e.KW - 1 - dt)] : 0.f;
   }
 }
 
