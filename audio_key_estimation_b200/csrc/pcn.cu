@@ -557,7 +557,8 @@ struct Fwd {
   }
 
   // One row convolution + BatchNorm + LeakyReLU (+ fused time pool).  Returns nothing; writes `out`.
-  void conv(int id, const View& in0, const View* in1, const ConvGeom& g, View& out, int out_coff, int act) {  // act: 0 none, 1 LeakyReLU, 2 ReLU
+  void conv(int id, const View& in0, const View* in1, const ConvGeom& g, View& out, int out_coff, int act,  // act: 0 none, 1 LeakyReLU, 2 ReLU
+            double* stats = nullptr) {  // train mode with a BatchNorm behind: also accumulate the batch sums of the raw outputs
     const Conv& c = p->convs[id];
     const bool has_bn = c.bn >= 0;
     const bool raw = train && has_bn;
@@ -578,6 +579,7 @@ struct Fwd {
     a.out = out.p, a.obs = out.bstride(), a.ocs = (long long)out.R * out.T, a.out_coff = out_coff;
     a.pool_t = raw ? 0 : g.pool_t;
     a.T_store = out.T;
+    a.stats = raw ? stats : nullptr;
     const int co_tile = c.cout_pad % 8 == 0 ? 8 : (c.cout_pad % 4 == 0 ? 4 : 1);
     launch_conv(a, g, co_tile, B, st);
   }

@@ -46,6 +46,8 @@ struct ConvArgs {
   int tgroups;  // time groups per block: block covers tgroups*RT output frames
   int xp;       // shared-memory row pitch (floats, multiple of 4, >= tgroups*RT + KW - 1)
   int accum;    // add to the stored values instead of overwriting them (data gradients with several consumers)
+  double* stats;  // train mode (raw outputs, no pool): stats[2 ch] += sum, stats[2 ch + 1] += sum of squares of the stored values
+                  // (bn_stats_kernel's contract, out of the conv's own epilogue); NULL otherwise
 };
 
 constexpr int kConvCI = 8;  // input channels staged per shared-memory pass
@@ -183,6 +185,36 @@ __global__ void __launch_bounds__(256) conv_rows_kernel(const ConvArgs a) {
   }
 
   const int out_row = out_row0 + r;
+  if (a.stats != nullptr) {
+    // raw outputs + their BatchNorm sums: every lane of every warp takes part in the shuffles, stores are predicated
+    const bool store = active && out_row < a.rows_out;
+#pragma unroll
+    for (int c = 0; c < CO_T; ++c) {
+      const int ch = cob * CO_T + c;  // (warp-uniform)
+      if (ch >= a.Cout) break;
+      const float s = a.scale[ch], h = a.shift[ch];
+      float* op = a.out + b * a.obs + (a.out_coff + ch) * a.ocs + (long long)out_row * a.T_store;
+      double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+      for (int j = 0; j < RT; ++j) {
+        const int t = t0 + tg * RT + j;
+        if (store && t < a.T_out) {
+          const float v = fmaf(acc[c][j], s, h);
+          op[t] = v;
+          s1 += (double)v, s2 += (double)v * (double)v;
+        }
+      }
+      for (int o = 16; o; o >>= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+      }
+      if (lane == 0 && tid < RB * a.tgroups) {
+        atomicAdd(a.stats + 2 * ch, s1);
+        atomicAdd(a.stats + 2 * ch + 1, s2);
+      }
+    }
+    return;
+  }
   if (!active || out_row >= a.rows_out) return;
 #pragma unroll
   for (int c = 0; c < CO_T; ++c) {

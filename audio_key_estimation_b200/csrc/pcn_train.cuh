@@ -118,10 +118,10 @@ void Fwd::run_keep(const float* mel, float* key_out, float* tonic_out, float* ge
       }
       return s;
     }
-    conv(id, in0, in1, g, s.z, 0, false);
+    conv(id, in0, in1, g, s.z, 0, false, s.has_bn ? d_stats + 2 * c.ss_off : nullptr);  // the BatchNorm sums come out of the conv's epilogue
     s.a = s.z;
     if (s.has_bn) {
-      stats_of(c, s.z);
+      train_bn_finalize(c, s.z.R * s.z.T);
       if (act_now) s.a = bn_act(c, s.z);
     }
     return s;
