@@ -160,3 +160,24 @@ def test_port_matches_librosa_when_importable():
     assert got.shape == want.shape
     assert np.abs(got - want).max() <= 2e-5 * np.abs(want).max()
     np.testing.assert_allclose(cp.cqt_logmag(y, SR)[0], np.log(1 + np.abs(want)), atol=2e-5)
+
+
+def test_decimator_agrees_with_torchaudio_kaiser_resampler():
+    """An EXTERNAL anchor for the decimation stage while librosa / resampy are absent: torchaudio's windowed-sinc resampler with the
+    parameters its documentation gives as the equivalent of resampy's ``kaiser_fast`` (lowpass_filter_width 16, rolloff 0.85,
+    beta 8.555504641634386) is an independent implementation of the same published filter family.  Its taper is stretched by
+    1 / rolloff, so the two agree in the passband rather than tap by tap: on a band-limited signal the port's ``resample_half`` must
+    equal torchaudio's output times sqrt(2) (librosa's ``scale=True`` energy normalisation, audio.py resample) -- that pins the
+    port's passband gain, its zero-phase alignment / output sample positions and the sqrt(2) per level.  Measured 2.3e-5."""
+    torchaudio = pytest.importorskip("torchaudio")
+    import torch
+    n = SR
+    t = np.arange(n) / SR
+    y = sum(a * np.sin(2 * np.pi * f * t + ph) for a, f, ph in [(0.5, 440.0, 0.1), (0.3, 1234.5, 1.0), (0.2, 3100.0, 2.0), (0.1, 55.0, 0.3)])
+    got = cp.resample_half(y.astype(np.float64))
+    want = torchaudio.functional.resample(torch.from_numpy(y)[None].double(), 2, 1, lowpass_filter_width=16, rolloff=0.85,
+                                          resampling_method="sinc_interp_kaiser", beta=8.555504641634386)[0].numpy() * np.sqrt(2.0)
+    assert got.shape == want.shape
+    edge = 64  # the two implementations pad the clip's ends differently
+    err = np.abs(got[edge:-edge] - want[edge:-edge]).max()
+    assert err <= 1e-4 * np.abs(want).max(), err
