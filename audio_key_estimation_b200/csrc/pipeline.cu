@@ -155,7 +155,21 @@ void estimate_host(ake_cqt* cqt, ake_pcn* pcn, const Sample* audio_host, int64_t
     if (T_batch <= 0) fail(AKE_ERR_INVALID, "clips too short");
   }
   const int dev = current_device();
-  const int n_chunks = cdiv(B, l.chunk);
+  // chunk boundaries: full chunks, then the last one cut into a half and two quarters (>= 8 clips each) -- the only compute the
+  // PCIe transfer cannot hide is that of the final chunk, so it is kept short
+  std::vector<int> cuts = {0};
+  while (cuts.back() < B) {
+    const int left = B - cuts.back();
+    if (left > l.chunk) {
+      cuts.push_back(cuts.back() + l.chunk);
+    } else if (left >= 32 && cuts.size() > 1) {
+      const int q = left / 4;
+      cuts.push_back(cuts.back() + left - 2 * q), cuts.push_back(cuts.back() + q), cuts.push_back(B);
+    } else {
+      cuts.push_back(B);
+    }
+  }
+  const int n_chunks = (int)cuts.size() - 1;
   g_lane.ensure(dev, (size_t)n_chunks);
   // the copy stream must not overwrite the audio buffer while earlier work on `st` still reads it
   AKE_CUDA(cudaEventRecord(g_lane.entry, st));
@@ -169,13 +183,13 @@ void estimate_host(ake_cqt* cqt, ake_pcn* pcn, const Sample* audio_host, int64_t
   }
   Sample* stage = kPcm16 ? reinterpret_cast<Sample*>(l.audio16) : reinterpret_cast<Sample*>(l.audio);
   for (int c = 0; c < n_chunks; ++c) {
-    const int b0 = c * l.chunk, nb = std::min(l.chunk, B - b0);
+    const int b0 = cuts[c], nb = cuts[c + 1] - b0;
     AKE_CUDA(cudaMemcpy2DAsync(stage + (size_t)b0 * l.stride, sizeof(Sample) * l.stride, audio_host + (size_t)b0 * stride,
                                sizeof(Sample) * stride, sizeof(Sample) * n_max, nb, cudaMemcpyHostToDevice, g_lane.stream));
     AKE_CUDA(cudaEventRecord(g_lane.landed[c], g_lane.stream));
   }
   for (int c = 0; c < n_chunks; ++c) {
-    const int b0 = c * l.chunk, nb = std::min(l.chunk, B - b0);
+    const int b0 = cuts[c], nb = cuts[c + 1] - b0;
     AKE_CUDA(cudaStreamWaitEvent(st, g_lane.landed[c], 0));
     const float* clips = l.audio + (size_t)b0 * l.stride;
     if (kPcm16) {
