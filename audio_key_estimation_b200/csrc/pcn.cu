@@ -466,6 +466,11 @@ struct Fwd {
   __half* tc_lo = nullptr;
   float* tc_raw = nullptr;
   __half* tc_wimg = nullptr;
+  // backward: scratch of the tensor-core weight gradient (side stream: its own planes)
+  bool wg_ready = false;
+  __half* wg_x[2] = {};
+  __half* wg_g[2] = {};
+  float* wg_partial = nullptr;
 
   Fwd(ake_pcn* p_, int B_, int T_, bool train_, void* ws, size_t ws_bytes, cudaStream_t st_)
       : p(p_), B(B_), T(T_), train(train_), dry(ws == nullptr), st(st_), arena(ws, ws_bytes) {}
@@ -538,7 +543,7 @@ struct Fwd {
     TcPackArgs pa{};
     pa.in0 = in0.p, pa.bs0 = in0.bstride(), pa.c0 = in0.C;
     pa.in1 = in1 ? in1->p : in0.p, pa.bs1 = in1 ? in1->bstride() : 0, pa.c1 = in1 ? in1->C : 0, pa.rows1 = in1 ? in1->R : 1;
-    pa.B = B, pa.P = P, pa.T = Tn, pa.Wd = Wd, pa.maxbits = maxbits, pa.hi = tc_hi, pa.lo = tc_lo;
+    pa.B = B, pa.P = P, pa.T = Tn, pa.Wd = Wd, pa.col_shift = 3, pa.wrap_cols = 1, pa.maxbits = maxbits, pa.hi = tc_hi, pa.lo = tc_lo;
     tc_pack_planes_kernel<<<ew_blocks((long long)B * (P + 6) * Wd), 256, 0, st>>>(pa);
     AKE_LAUNCHED();
     const int n_tt = cdiv(Tn, kP2PMaxTB), TB = cdiv(Tn, n_tt), n_rt = cdiv(P, kP2PRows), n_tiles = B * n_rt * n_tt;
@@ -554,6 +559,44 @@ struct Fwd {
     ua.bias = (!dgrad && c.has_bias) ? p->d_params + c.b_off : nullptr;
     tc_unpack_kernel<<<std::min<int>((int)cdiv64((long long)B * P * Tn, 256), 4 * sm_count()), 256, 0, st>>>(ua);
     AKE_LAUNCHED();
+  }
+
+  // dW of a 7x7 circular conv (input cat[in0, tile(in1)], output gradient dz with largest |dz| = maxbits) on the tensor cores,
+  // on stream `ws` (the backward's side stream); overwrites dw (Cout, Cin, 7, 7).  pcn_train_tc.cuh: p2p_wgrad_umma_kernel.
+  void tc_wgrad(const View& in0, const View* in1, const Conv& c, const View& dz, const unsigned* maxbits, float* dw, cudaStream_t ws) {
+    const int P = in0.R, Tn = in0.T, Wd = Tn + 6, Wg = cdiv(Tn, 16) * 16;
+    if (!wg_ready) {
+      for (int i = 0; i < 2; ++i) {
+        wg_x[i] = arena.take<__half>((size_t)B * (P + 6) * Wd * 8 + 64 * 8);
+        wg_g[i] = arena.take<__half>((size_t)B * (P + 6) * Wg * 8 + 64 * 8);
+      }
+      wg_partial = arena.take<float>((size_t)sm_count() * 64 * 56);
+      wg_ready = true;
+    }
+    if (dry) return;
+    TcPackArgs px{};
+    px.in0 = in0.p, px.bs0 = in0.bstride(), px.c0 = in0.C;
+    px.in1 = in1 ? in1->p : in0.p, px.bs1 = in1 ? in1->bstride() : 0, px.c1 = in1 ? in1->C : 0, px.rows1 = in1 ? in1->R : 1;
+    px.B = B, px.P = P, px.T = Tn, px.Wd = Wd, px.col_shift = 3, px.wrap_cols = 1, px.maxbits = nullptr, px.hi = wg_x[0], px.lo = wg_x[1];
+    tc_pack_planes_kernel<<<ew_blocks((long long)B * (P + 6) * Wd), 256, 0, ws>>>(px);
+    AKE_LAUNCHED();
+    TcPackArgs pg{};
+    pg.in0 = dz.p, pg.bs0 = dz.bstride(), pg.c0 = dz.C, pg.in1 = dz.p, pg.bs1 = 0, pg.c1 = 0, pg.rows1 = 1;
+    pg.B = B, pg.P = P, pg.T = Tn, pg.Wd = Wg, pg.col_shift = 0, pg.wrap_cols = 0, pg.maxbits = maxbits, pg.hi = wg_g[0], pg.lo = wg_g[1];
+    tc_pack_planes_kernel<<<ew_blocks((long long)B * (P + 6) * Wg), 256, 0, ws>>>(pg);
+    AKE_LAUNCHED();
+    WgradTcArgs wa{wg_x[0], wg_x[1], wg_g[0], wg_g[1], wg_partial, B, P, Tn, Wd, Wg, cdiv(P, kWgR), B * cdiv(P, kWgR)};
+    const size_t smem = wgrad_tc_smem_bytes(Wd, Wg);
+    ensure_dyn_smem(p2p_wgrad_umma_kernel, smem);
+    const int grid = std::min(wa.n_tiles, sm_count());
+    p2p_wgrad_umma_kernel<<<grid, kWgThreads, smem, ws>>>(wa);
+    AKE_LAUNCHED();
+    wgrad_tc_reduce_kernel<<<cdiv(c.Cout * c.Cin * 49, 128), 128, 0, ws>>>(wg_partial, grid, maxbits, c.Cout, c.Cin, dw);
+    AKE_LAUNCHED();
+  }
+  bool tc_wgrad_ok(const Conv& c, const ConvGeom& g, int Tn) const {
+    static const bool on = [] { const char* e = getenv("AKE_TRAIN_TC_WGRAD"); return e ? atoi(e) != 0 : true; }();
+    return on && tc_conv_ok(c, g, Tn) && wgrad_tc_smem_bytes(Tn + 6, cdiv(Tn, 16) * 16) <= 227 * 1024;
   }
 
   // One row convolution + BatchNorm + LeakyReLU (+ fused time pool).  Returns nothing; writes `out`.

@@ -288,9 +288,13 @@ void Fwd::backward_keep(const TrainTape& tp, const float* d_key, const float* d_
   // Weight and bias gradients only feed the gradient buffer: they run on a side stream, forked behind the kernel that produced dz
   // and joined at the end of the backward pass, so that they overlap the data-gradient chain (at batch 8 neither fills the GPU).
   SideStream& side = side_stream();
-  auto wgrad = [&](const ConvSite& s, const View& dz) {
+  auto wgrad = [&](const ConvSite& s, const View& dz, const unsigned* maxbits = nullptr) {
     const Conv& c = p->convs[s.id];
-    if (dry) return;
+    const bool tc = maxbits != nullptr && tc_wgrad_ok(c, s.g, s.in0.T);
+    if (dry) {
+      if (tc) tc_wgrad(s.in0, s.in1.p ? &s.in1 : nullptr, c, dz, maxbits, nullptr, st);  // (carves the scratch)
+      return;
+    }
     const cudaStream_t main_st = st;
     static const bool use_side = [] { const char* e = getenv("AKE_WGRAD_SIDE"); return e ? atoi(e) != 0 : true; }();  // 5.40 -> 4.63 ms per step
     if (use_side) {
@@ -307,6 +311,10 @@ void Fwd::backward_keep(const TrainTape& tp, const float* d_key, const float* d_
     // a conv bias in front of a train-mode BatchNorm has an exactly-zero gradient (dz sums to zero per channel; the reference
     // leaves ~1e-15 of rounding there): the zeroed gradient buffer already holds it
     if (!s.has_bn) bias_grad(c, dz);
+    if (tc) {  // 7x7 conv: one tensor-core GEMM over positions, deterministic reduction (pcn_train_tc.cuh)
+      tc_wgrad(s.in0, s.in1.p ? &s.in1 : nullptr, c, dz, maxbits, grads + c.w_off, st);
+      return;
+    }
     WgradArgs a{};
     a.in0 = s.in0.p, a.c0 = s.in0.C, a.rows0 = s.in0.R, a.bs0 = s.in0.bstride();
     if (s.in1.p) a.in1 = s.in1.p, a.c1 = s.in1.C, a.rows1 = s.in1.R, a.bs1 = s.in1.bstride();
@@ -354,7 +362,7 @@ void Fwd::backward_keep(const TrainTape& tp, const float* d_key, const float* d_
       unsigned* mb = nullptr;
       if (tc_conv_ok(c, s.g, s.in0.T) && n_maxbits < 64) mb = d_maxbits + n_maxbits++;
       View dz = bn_bwd(s.id, s.z, d_a, mb);
-      wgrad(s, dz);
+      wgrad(s, dz, mb);
       View dx = alloc(c.Cin, s.in0.R, s.in0.T);
       dgrad(s, dz, dx, false, mb);
       d_a = dx;

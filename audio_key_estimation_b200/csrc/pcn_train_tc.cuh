@@ -30,6 +30,8 @@ struct TcPackArgs {
   long long bs0, bs1;
   int c0, c1, rows1;
   int B, P, T, Wd;
+  int col_shift;      // plane column of frame 0: 3 (circular halo columns, the conv operand) or 0
+  int wrap_cols;      // 1: columns outside [0, T) hold the circular copies; 0: they hold zeros (the weight-gradient operand)
   const unsigned* maxbits;  // NULL: scale 1
   __half* hi;
   __half* lo;
@@ -42,13 +44,16 @@ __global__ void __launch_bounds__(256) tc_pack_planes_kernel(const TcPackArgs a)
     const int col = (int)(i % a.Wd);
     const long long q = i / a.Wd;
     const int row = (int)(q % (a.P + 6)), b = (int)(q / (a.P + 6));
-    int p = (row - 3) % a.P, t = (col - 3) % a.T;
+    int p = (row - 3) % a.P, t = col - a.col_shift;
+    const bool live = a.wrap_cols || (t >= 0 && t < a.T);
+    t %= a.T;
     p += p < 0 ? a.P : 0, t += t < 0 ? a.T : 0;
     float v[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
       float x = 0.f;
-      if (c < a.c0) x = __ldg(a.in0 + b * a.bs0 + ((long long)c * a.P + p) * a.T + t);
+      if (!live) x = 0.f;
+      else if (c < a.c0) x = __ldg(a.in0 + b * a.bs0 + ((long long)c * a.P + p) * a.T + t);
       else if (c < a.c0 + a.c1) x = __ldg(a.in1 + b * a.bs1 + ((long long)(c - a.c0) * a.rows1 + p % a.rows1) * a.T + t);
       v[c] = x * mul;
     }
@@ -116,6 +121,135 @@ __global__ void p2p_pack_weights_flip_kernel(const float* __restrict__ w, int Co
     if (ci < Cout && co < Cin) v = w[(((long long)ci * Cin + co) * 7 + (6 - dp)) * 7 + (6 - f)] * kWScale;
     p2p_img_store(img, dp, f, co, ci, v);
   }
+}
+
+// ---- weight gradient of the 7x7 circular conv as ONE tensor-core GEMM over positions ---------------------------------------------------
+//   dW[co, ci, dp, dt] = sum_{b, r, t} dZ[b, co, r, t] * x~[b, ci, r + dp, t + dt]        (x~ = the halo'd input, circular)
+// Both tensors are position-major chunk planes ([position][8 channels] fp16), i.e. MN-MAJOR tcgen05 operands whose K index is the
+// position -- no transposition pass.  With s = r + dp - 3 (the un-halo'd input row, taken modulo P) the sum over (r, dp) becomes a sum
+// over s in [0, P) and the seven gradient rows s - 3 ... s + 3 (halo rows above / below are the circular copies):
+//   A (M = 64): rows (g = dt, ci), K = 16 consecutive frames of input row s: x~[s + 3][t0 + k + g]  -- eight core matrices 16 B apart
+//               (OVERLAPPING: SBO = 16 B; verified by tools/mn_probe.cu), the eighth (g = 7) is discarded
+//   B (N = 56): columns (j = 6 - dp, co): dZ plane row s + j, frames t0 + k                           -- SBO = the plane's row pitch
+//   D[(dt, ci), (6 - dp, co)] += A . B, three hi/lo products per 16 frames, accumulated in TMEM over every tile of the CTA.
+// The gradient planes carry zeros beyond frame T - 1 (tc_pack_planes_kernel, wrap_cols = 0), so partial 16-frame blocks add nothing.
+// Persistent CTA per SM: warps 0-3 drain the accumulator once at the end (M = 64: rows 16 q ... 16 q + 15 in lanes 0-15 of TMEM quadrant
+// q) into a per-CTA partial; warp 4 loads the tiles (R input rows + R + 6 gradient rows, two buffers), warp 5 issues the MMAs.
+// wgrad_tc_reduce_kernel sums the partials in CTA order (deterministic, no atomics) and writes dW.
+constexpr int kWgR = 6;                 // input rows per tile
+constexpr int kWgThreads = 32 * 6;
+struct WgradTcArgs {
+  const __half* x_hi;
+  const __half* x_lo;   // [B][P+6][Wd][8]: the conv's input operand planes (circular halos, scale 1)
+  const __half* g_hi;
+  const __half* g_lo;   // [B][P+6][Wg][8]: output gradient, halo ROWS circular, column = frame, zeros beyond T, scaled by tc_scale_of(maxbits)
+  float* partial;       // [gridDim.x][64][56]
+  int B, P, T, Wd, Wg;
+  int n_rtiles, n_tiles;
+};
+__host__ __device__ inline uint32_t wgrad_tc_x_bytes(int Wd) { return (uint32_t)(kWgR * Wd + 32) * 16; }      // + slack: the last block reads past the row
+__host__ __device__ inline uint32_t wgrad_tc_g_bytes(int Wg) { return (uint32_t)((kWgR + 6) * Wg + 16) * 16; }
+__host__ __device__ inline size_t wgrad_tc_smem_bytes(int Wd, int Wg) { return (size_t)2 * 2 * (wgrad_tc_x_bytes(Wd) + wgrad_tc_g_bytes(Wg)); }
+
+__global__ void __launch_bounds__(kWgThreads, 1) p2p_wgrad_umma_kernel(const WgradTcArgs a) {
+  using namespace umma;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t full_bar[2], empty_bar[2], done_bar;
+  __shared__ uint32_t tmem_slot;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
+  const uint32_t XB = wgrad_tc_x_bytes(a.Wd), GB = wgrad_tc_g_bytes(a.Wg), BUF = 2 * (XB + GB);  // buffer: [x_hi][x_lo][g_hi][g_lo]
+  if (warp == 5) tmem_alloc(&tmem_slot, 64);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) mbar_init(&full_bar[i], 1), mbar_init(&empty_bar[i], 1);
+    mbar_init(&done_bar, 1);
+    mbar_init_fence();
+  }
+  // the slack behind the rows is read (by blocks whose gradient frames are zero) but never written by the copies: keep it finite
+  for (uint32_t i = threadIdx.x; i < 2 * BUF / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  const int n_blk = (a.T + 15) / 16;
+
+  if (warp == 4) {
+    // ------------------------------------------------------------ loader: rows are contiguous in the planes, one copy per plane
+    int k = 0;
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++k) {
+      const int s = k & 1;
+      const int b = tile / a.n_rtiles, s0 = (tile - b * a.n_rtiles) * kWgR, R = min(kWgR, a.P - s0);
+      mbar_wait_relaxed(&empty_bar[s], ((k >> 1) & 1) ^ 1);
+      if (lane == 0) {
+        const uint32_t xb = (uint32_t)(R * a.Wd) * 16, gb = (uint32_t)((R + 6) * a.Wg) * 16;
+        mbar_arrive_expect_tx(&full_bar[s], 2 * (xb + gb));
+        uint8_t* dst = smem + (size_t)s * BUF;
+        const long long xo = (((long long)b * (a.P + 6) + s0 + 3) * a.Wd) * 8, go = (((long long)b * (a.P + 6) + s0) * a.Wg) * 8;
+        bulk_g2s(dst, a.x_hi + xo, xb, &full_bar[s]);
+        bulk_g2s(dst + XB, a.x_lo + xo, xb, &full_bar[s]);
+        bulk_g2s(dst + 2 * XB, a.g_hi + go, gb, &full_bar[s]);
+        bulk_g2s(dst + 2 * XB + GB, a.g_lo + go, gb, &full_bar[s]);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 5) {
+    // ------------------------------------------------------------ MMA issuer (converged warp, one elected lane issues)
+    constexpr uint64_t A_DESC = desc_hi(128, 16);                      // MN-major: K groups of 8 frames 128 B apart, M groups (time taps) 16 B apart
+    const uint64_t B_DESC = desc_hi(128, (uint32_t)a.Wg * 16);          // N groups (row taps) one plane row apart
+    constexpr uint32_t IDESC = idesc_f16(56, 64) | (1u << 15) | (1u << 16);  // A and B MN-major
+    int k = 0;
+    uint32_t first = 0;  // the CTA's very first MMA overwrites the accumulator
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++k) {
+      const int s = k & 1;
+      const int b = tile / a.n_rtiles, s0 = (tile - b * a.n_rtiles) * kWgR, R = min(kWgR, a.P - s0);
+      const uint32_t x0 = smem_u32(smem + (size_t)s * BUF), g0 = x0 + 2 * XB;
+      mbar_wait(&full_bar[s], (k >> 1) & 1);
+      fence_after_sync();
+      if (elect_one()) {
+        for (int i = 0; i < R; ++i) {
+          for (int c = 0; c < n_blk; ++c) {
+            const uint32_t xa = x0 + (uint32_t)(i * a.Wd + 16 * c) * 16, ga = g0 + (uint32_t)(i * a.Wg + 16 * c) * 16;
+            mma_f16(tmem, make_desc(A_DESC, xa), make_desc(B_DESC, ga), IDESC, first);            // x_hi . g_hi
+            first = 1u;
+            mma_f16(tmem, make_desc(A_DESC, xa + XB), make_desc(B_DESC, ga), IDESC, 1u);          // x_lo . g_hi
+            mma_f16(tmem, make_desc(A_DESC, xa), make_desc(B_DESC, ga + GB), IDESC, 1u);          // x_hi . g_lo
+          }
+        }
+        commit(&empty_bar[s]);
+      }
+      __syncwarp();
+    }
+    if (elect_one()) commit(&done_bar);
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------ final drain: partial[cta][m][n], m = 8 dt + ci, n = 8 (6 - dp) + co
+    mbar_wait_relaxed(&done_bar, 0);
+    fence_after_sync();
+    float* dst = a.partial + (size_t)blockIdx.x * 64 * 56;
+    for (int c0 = 0; c0 < 56; c0 += 8) {
+      float v[8];
+      tmem_ld8(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
+      if (lane < 16) {
+        float4* d4 = reinterpret_cast<float4*>(dst + (16 * warp + lane) * 56 + c0);
+        d4[0] = make_float4(v[0], v[1], v[2], v[3]), d4[1] = make_float4(v[4], v[5], v[6], v[7]);
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc(tmem, 64);
+}
+
+// dW[co][ci][dp][dt] = (sum over the CTAs' partials, in CTA order) / the gradient planes' scale.  One thread per weight.
+__global__ void wgrad_tc_reduce_kernel(const float* __restrict__ partial, int n_cta, const unsigned* __restrict__ maxbits, int Cout, int Cin,
+                                       float* __restrict__ dw) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Cout * Cin * 49) return;
+  const int dt = i % 7, dp = (i / 7) % 7, ci = (i / 49) % Cin, co = i / (49 * Cin);
+  const int m = 8 * dt + ci, n = 8 * (6 - dp) + co;
+  float s = 0.f;
+  for (int c = 0; c < n_cta; ++c) s += __ldg(partial + ((size_t)c * 64 + m) * 56 + n);
+  dw[i] = s / (maxbits ? tc_scale_of(__ldg(maxbits)) : 1.f);
 }
 
 }  // namespace ake
