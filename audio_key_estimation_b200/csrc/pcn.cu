@@ -466,6 +466,11 @@ struct Fwd {
   __half* tc_lo = nullptr;
   float* tc_raw = nullptr;
   __half* tc_wimg = nullptr;
+  // ... and the equivariant 12 x 7 convolutions of the PitchClass2PitchClass stacks (pc2pc_umma_kernel<3>, pc8_umma_kernel<2> raw)
+  bool eq_ready = false;
+  __half* eq_hi = nullptr;
+  __half* eq_lo = nullptr;
+  __half* eq_wimg = nullptr;
   // backward: scratch of the tensor-core weight gradient (side stream: its own planes)
   bool wg_ready = false;
   __half* wg_x[2] = {};
@@ -558,6 +563,64 @@ struct Fwd {
     ua.C = dgrad ? c.Cin : c.Cout;
     ua.bias = (!dgrad && c.has_bias) ? p->d_params + c.b_off : nullptr;
     tc_unpack_kernel<<<std::min<int>((int)cdiv64((long long)B * P * Tn, 256), 4 * sm_count()), 256, 0, st>>>(ua);
+    AKE_LAUNCHED();
+  }
+
+  // ---- train mode: an equivariant 12 x 7 convolution ("same" zero padding in time) or its data gradient on the tensor cores
+  bool eq_conv_ok(const Conv& c, const ConvGeom& g, int Tn) const {
+    static const bool on = [] { const char* e = getenv("AKE_TRAIN_TC_EQUIV"); return e ? atoi(e) != 0 : true; }();
+    return on && p->umma && g.KH == 12 && g.KW == 7 && g.SR == 1 && g.row_circ && !g.time_circ && g.row_off == 0 && g.pad_t == 3 &&
+           g.rows_v == 12 && g.rows_out == 12 && g.T_out == Tn && c.Cin <= 16 && c.Cout <= 16 && Tn >= 7;
+  }
+  // out = conv(in, W) + bias (dgrad = false), or the data gradient for the output gradient `in` (dgrad = true; maxbits: largest |in|);
+  // ones / zeros: 16 floats each on the device (the data gradient's epilogue)
+  void eq_conv(const View& in, const Conv& c, bool dgrad, const unsigned* maxbits, const float* ones, const float* zeros, View& out) {
+    const int Tn = in.T, Wd = Tn + 6;
+    if (!eq_ready) {
+      const size_t halves = (size_t)B * 2 * 23 * Wd * 8;
+      eq_hi = arena.take<__half>(halves), eq_lo = arena.take<__half>(halves);
+      eq_wimg = arena.take<__half>(kPcWBytes / 2);
+      eq_ready = true;
+    }
+    if (dry) return;
+    ProfScope prof("pcn.equiv", st);
+    const int Cin = dgrad ? c.Cout : c.Cin, Cout = dgrad ? c.Cin : c.Cout;  // of the convolution that runs
+    const bool wide = Cin > 8 || Cout > 8;
+    const float* w = p->d_params + c.w_off;
+    if (wide) {
+      if (dgrad) pc2pc_pack_weights_flip_kernel<<<84, 256, 0, st>>>(w, c.Cout, c.Cin, eq_wimg);
+      else pc2pc_pack_weights_kernel<<<84, 256, 0, st>>>(w, c.Cout, c.Cin, eq_wimg);
+    } else {
+      if (dgrad) pc8_pack_weights_flip_kernel<<<21, 256, 0, st>>>(w, c.Cout, c.Cin, eq_wimg);
+      else pc8_pack_weights_kernel<<<21, 256, 0, st>>>(w, c.Cout, c.Cin, eq_wimg);
+    }
+    AKE_LAUNCHED();
+    EqPackArgs pa{in.p, B, in.C, wide ? 2 : 1, Tn, Wd, maxbits, eq_hi, eq_lo};
+    eq_pack_planes_kernel<<<ew_blocks((long long)B * pa.G * 23 * Wd), 256, 0, st>>>(pa);
+    AKE_LAUNCHED();
+    const float* scale = dgrad ? ones : scale_of(c, true);
+    const float* shift = dgrad ? zeros : shift_of(c, true);
+    if (wide) {
+      const int n_tt = cdiv(Tn, 32), TBe = (cdiv(Tn, n_tt) + 1) / 2 * 2;
+      const size_t smem_e = pc2pc_smem_bytes(TBe + 6);
+      ensure_dyn_smem(pc2pc_umma_kernel<3>, smem_e);
+      Pc2PcArgs ea{};
+      ea.in_hi = eq_hi, ea.in_lo = eq_lo, ea.Wd_in = Wd, ea.T_out = Tn, ea.TB = TBe, ea.n_ttiles = cdiv(Tn, TBe);
+      ea.n_tiles = ea.n_ttiles * B;
+      check_decode_range((long long)ea.n_tiles, ea.n_ttiles, "PitchClass2PitchClass (training)");
+      ea.wimg = eq_wimg, ea.scale = scale, ea.shift = shift, ea.out_f32 = out.p, ea.Cout_store = Cout, ea.maxbits = maxbits;
+      pc2pc_umma_kernel<3><<<std::min(ea.n_tiles, sm_count()), kPcThreads, smem_e, st>>>(ea);
+    } else {
+      const int n_tt = cdiv(Tn, kPc8MaxTB), TB8 = (cdiv(Tn, n_tt) + 1) / 2 * 2;
+      const size_t smem8 = pc8_smem_bytes(TB8 + 6);
+      ensure_dyn_smem(pc8_umma_kernel<2>, smem8);
+      Pc8Args a8{};
+      a8.in_hi = eq_hi, a8.in_lo = eq_lo, a8.Wd_in = Wd, a8.T_out = Tn, a8.TB = TB8, a8.n_ttiles = cdiv(Tn, TB8);
+      a8.n_tiles = a8.n_ttiles * B;
+      check_decode_range((long long)a8.n_tiles, a8.n_ttiles, "layer-0 PitchClass2PitchClass (training)");
+      a8.wimg = eq_wimg, a8.scale = scale, a8.shift = shift, a8.Cout = Cout, a8.out_f32 = out.p, a8.raw = 1, a8.maxbits = maxbits;
+      pc8_umma_kernel<2><<<std::min(a8.n_tiles, sm_count()), kPc8Threads, smem8, st>>>(a8);
+    }
     AKE_LAUNCHED();
   }
 

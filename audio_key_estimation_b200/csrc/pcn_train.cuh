@@ -40,6 +40,10 @@ struct TrainTape {
   __half* tc_lo = nullptr;
   float* tc_raw = nullptr;
   __half* tc_wimg = nullptr;
+  bool eq_ready = false;
+  __half* eq_hi = nullptr;
+  __half* eq_lo = nullptr;
+  __half* eq_wimg = nullptr;
 };
 
 __global__ void fill_kernel(float* __restrict__ x, int n, float v) {
@@ -114,6 +118,16 @@ void Fwd::run_keep(const float* mel, float* key_out, float* tonic_out, float* ge
       s.a = s.z;
       if (s.has_bn) {
         train_bn_finalize(c, s.z.R * s.z.T);
+        if (act_now) s.a = bn_act(c, s.z);
+      }
+      return s;
+    }
+    if (!in1 && eq_conv_ok(c, g, in0.T)) {
+      // equivariant 12 x 7 conv on the tensor cores (raw planar output), then its batch statistics
+      eq_conv(in0, c, false, nullptr, nullptr, nullptr, s.z);
+      s.a = s.z;
+      if (s.has_bn) {
+        stats_of(c, s.z);
         if (act_now) s.a = bn_act(c, s.z);
       }
       return s;
@@ -213,6 +227,7 @@ void Fwd::run_keep(const float* mel, float* key_out, float* tonic_out, float* ge
     AKE_LAUNCHED();
   }
   tp.tc_ready = tc_ready, tp.tc_hi = tc_hi, tp.tc_lo = tc_lo, tp.tc_raw = tc_raw, tp.tc_wimg = tc_wimg;
+  tp.eq_ready = eq_ready, tp.eq_hi = eq_hi, tp.eq_lo = eq_lo, tp.eq_wimg = eq_wimg;
   tp.ws_off = arena.off;
   tp.valid = !dry;
 }
@@ -244,6 +259,7 @@ void Fwd::backward_keep(const TrainTape& tp, const float* d_key, const float* d_
   const int P = cfg.pitches, k = cfg.kernel_size;
   const int n_ss = p->n_ss;
   tc_ready = tp.tc_ready, tc_hi = tp.tc_hi, tc_lo = tp.tc_lo, tc_raw = tp.tc_raw, tc_wimg = tp.tc_wimg;
+  eq_ready = tp.eq_ready, eq_hi = tp.eq_hi, eq_lo = tp.eq_lo, eq_wimg = tp.eq_wimg;
   float* ones = arena.take<float>(64);
   float* zeros = arena.take<float>(64);
   double* bsums = arena.take<double>(2 * (size_t)n_ss);
@@ -328,9 +344,10 @@ void Fwd::backward_keep(const TrainTape& tp, const float* d_key, const float* d_
   // data gradient of a stride-1 convolution: the forward kernel on dz with flipped / transposed weights
   auto dgrad = [&](const ConvSite& s, const View& dz, View& dx, bool accumulate, const unsigned* maxbits = nullptr) {
     const Conv& c = p->convs[s.id];
-    if (maxbits) {  // tensor-core data gradient (the caller checked tc_conv_ok and had bn_bwd record the largest |dz|)
-      if (accumulate || dx.C != c.Cin) fail(AKE_ERR_INVALID, "internal: tensor-core dgrad overwrites a (B, Cin, P, T) tensor");
-      tc_conv(dz, nullptr, c, true, maxbits, dx, nullptr);
+    if (maxbits) {  // tensor-core data gradient (the caller checked tc_conv_ok / eq_conv_ok and had bn_bwd record the largest |dz|)
+      if (accumulate || dx.C != c.Cin) fail(AKE_ERR_INVALID, "internal: tensor-core dgrad overwrites a (B, Cin, rows, T) tensor");
+      if (s.g.KH == 12) eq_conv(dz, c, true, maxbits, ones, zeros, dx);
+      else tc_conv(dz, nullptr, c, true, maxbits, dx, nullptr);
       return;
     }
     const int tile = co_tile_for(c.Cin), cin_pad = cdiv(c.Cin, tile) * tile;
@@ -360,7 +377,7 @@ void Fwd::backward_keep(const TrainTape& tp, const float* d_key, const float* d_
       const ConvSite& s = sites[i];
       const Conv& c = p->convs[s.id];
       unsigned* mb = nullptr;
-      if (tc_conv_ok(c, s.g, s.in0.T) && n_maxbits < 64) mb = d_maxbits + n_maxbits++;
+      if ((tc_conv_ok(c, s.g, s.in0.T) || (!s.in1.p && eq_conv_ok(c, s.g, s.in0.T))) && n_maxbits < 64) mb = d_maxbits + n_maxbits++;
       View dz = bn_bwd(s.id, s.z, d_a, mb);
       wgrad(s, dz, mb);
       View dx = alloc(c.Cin, s.in0.R, s.in0.T);
@@ -374,10 +391,12 @@ void Fwd::backward_keep(const TrainTape& tp, const float* d_key, const float* d_
   {
     std::vector<const ConvSite*> sites = {&tp.ht[1], &tp.ht[0], &tp.hk[1], &tp.hk[0]};
     if (tp.genre) sites.push_back(&tp.hg[1]), sites.push_back(&tp.hg[0]);
-    for (const ConvSite& s : tp.e1) sites.push_back(&s);
+    for (const ConvSite& s : tp.e1)
+      if (!eq_conv_ok(p->convs[s.id], s.g, s.in0.T)) sites.push_back(&s);
     for (const ConvSite& s : tp.p)
       if (!tc_conv_ok(p->convs[s.id], s.g, s.in0.T)) sites.push_back(&s);
-    for (const ConvSite& s : tp.e0) sites.push_back(&s);
+    for (const ConvSite& s : tp.e0)
+      if (!eq_conv_ok(p->convs[s.id], s.g, s.in0.T)) sites.push_back(&s);
     std::vector<DgradPackEntry> ents;
     size_t total = 0;
     int max_n = 1;

@@ -17,13 +17,6 @@
 
 namespace ake {
 
-// power of two that brings a tensor whose largest |x| has the bit pattern `maxbits` into [8, 16)
-__device__ __forceinline__ float tc_scale_of(unsigned maxbits) {
-  const int e = (int)((maxbits >> 23) & 0xffu);
-  if (e < 3 || e == 255) return 1.f;  // zero / denormal / non-finite: leave the tensor alone
-  return __uint_as_float((unsigned)(257 - e) << 23);  // 2^(3 - (e - 127))
-}
-
 struct TcPackArgs {
   const float* in0;   // (B, c0, P, T)
   const float* in1;   // (B, c1, rows1, T), row p of the conv input = row p % rows1 (PitchClass2Pitch tiling), or unused (c1 = 0)
@@ -250,6 +243,67 @@ __global__ void wgrad_tc_reduce_kernel(const float* __restrict__ partial, int n_
   float s = 0.f;
   for (int c = 0; c < n_cta; ++c) s += __ldg(partial + ((size_t)c * 64 + m) * 56 + n);
   dw[i] = s / (maxbits ? tc_scale_of(__ldg(maxbits)) : 1.f);
+}
+
+// ---- equivariant 12 x 7 convolutions of the PitchClass2PitchClass stacks in train mode ------------------------------------------------
+// pc2pc_umma_kernel<3> (<= 16 -> <= 16 channels) and pc8_umma_kernel<2> with raw = 1 (<= 8 -> <= 8) write raw planar fp32; their operand
+// planes [B][G][23][T + 6][8] (zero halo columns = the "same" padding in time, rows 12..22 = rows 0..10) come from the planar activations:
+struct EqPackArgs {
+  const float* in;  // (B, C, 12, T)
+  int B, C, G, T, Wd;
+  const unsigned* maxbits;  // NULL: scale 1
+  __half* hi;
+  __half* lo;
+};
+__global__ void __launch_bounds__(256) eq_pack_planes_kernel(const EqPackArgs a) {
+  const float mul = a.maxbits ? tc_scale_of(__ldg(a.maxbits)) : 1.f;
+  const long long n = (long long)a.B * a.G * 23 * a.Wd;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int col = (int)(i % a.Wd);
+    long long q = i / a.Wd;
+    const int row = (int)(q % 23);
+    q /= 23;
+    const int g = (int)(q % a.G), b = (int)(q / a.G);
+    const int c = row >= 12 ? row - 12 : row, t = col - 3;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int ch = g * 8 + e;
+      v[e] = (ch < a.C && t >= 0 && t < a.T) ? __ldg(a.in + (((long long)b * a.C + ch) * 12 + c) * a.T + t) * mul : 0.f;
+    }
+    store_split8(a.hi + i * 8, a.lo + i * 8, v);
+  }
+}
+// data-gradient weight images: the equivariant conv (Cout' = Cin, Cin' = Cout) with w'[co'][ci'][dp][f] = w[ci'][co'][(12 - dp) % 12][6 - f]
+//   dX[ci, c, t] = sum_{co, dp, dt} W[co, ci, dp, dt] dZ[co, (c - dp) mod 12, t - dt + 3]
+__global__ void pc2pc_pack_weights_flip_kernel(const float* __restrict__ w, int Cout, int Cin, __half* __restrict__ img) {
+  const int n_items = 12 * 2 * 112 * 8;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_items; i += gridDim.x * blockDim.x) {
+    const int e = i % 8, n = (i / 8) % 112, g = (i / (8 * 112)) % 2, dp = i / (16 * 112);
+    const int f = n / 16, co = n % 16, ci = g * 8 + e;  // ci: channel of dZ (< Cout), co: channel of dX (< Cin)
+    float v = 0.f;
+    if (ci < Cout && co < Cin) v = w[(((long long)ci * Cin + co) * 12 + (12 - dp) % 12) * 7 + (6 - f)] * kWScale;
+    const __half hi = __float2half_rn(v);
+    const __half lo = __float2half_rn(v - __half2float(hi));
+    img[((dp * 2 + g) * 224 + n) * 8 + e] = hi;
+    img[((dp * 2 + g) * 224 + 112 + n) * 8 + e] = lo;
+  }
+}
+__global__ void pc8_pack_weights_flip_kernel(const float* __restrict__ w, int Cout, int Cin, __half* __restrict__ img) {
+  const int n_items = 12 * 56 * 8;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_items; i += gridDim.x * blockDim.x) {
+    const int ci = i % 8, fc = (i / 8) % 56, dp = i / 448;
+    const int f = fc / 8, co = fc % 8;
+    float v = 0.f;
+    if (ci < Cout && co < Cin) v = w[(((long long)ci * Cin + co) * 12 + (12 - dp) % 12) * 7 + (6 - f)] * kWScale;
+    const __half hi = __float2half_rn(v);
+    const __half lo = __float2half_rn(v - __half2float(hi));
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      img[((dp * 2 + c) * 112 + 16 * f + co) * 8 + ci] = hi;
+      img[((dp * 2 + c) * 112 + 16 * f + 8 + co) * 8 + ci] = lo;
+    }
+  }
 }
 
 }  // namespace ake

@@ -42,6 +42,14 @@ constexpr int kP2PMmas = 11;        // MMAs per block: 7 row taps (x_hi + x_lo) 
 
 __device__ __forceinline__ float leaky_f(float v) { return v > 0.f ? v : kLeakySlope * v; }
 
+// Training step (pcn_train_tc.cuh): operand planes of gradients carry an exact power of two that brings the tensor's largest |x|
+// (given as its float bit pattern) into [8, 16); the kernels divide it out again.
+__device__ __forceinline__ float tc_scale_of(unsigned maxbits) {
+  const int e = (int)((maxbits >> 23) & 0xffu);
+  if (e < 3 || e == 255) return 1.f;  // zero / denormal / non-finite: leave the tensor alone
+  return __uint_as_float((unsigned)(257 - e) << 23);  // 2^(3 - (e - 127))
+}
+
 __device__ __forceinline__ void store_split8(__half* hi_dst, __half* lo_dst, const float (&v)[8]) {
   uint32_t h[4], l[4];
 #pragma unroll
@@ -1158,7 +1166,10 @@ struct Pc2PcArgs {
   __half* out_hi;
   __half* out_lo;        // EPI 0: [B][2][23][Wd_out][8] written at column t + col_off; EPI 1: same with t / 2
   int Wd_out, col_off;
-  float* out_f32;        // EPI 1: (B,16,12,T_out/2)
+  float* out_f32;        // EPI 1: (B,16,12,T_out/2);  EPI 3: (B, Cout_store, 12, T_out)
+  // EPI 3 (training step): y = acc * scale / kWScale / tc_scale_of(*maxbits) + shift, NO activation, planar fp32
+  int Cout_store;
+  const unsigned* maxbits;
 };
 
 __host__ __device__ inline uint32_t pc2pc_plane_positions(int Wt) { return (uint32_t)(23 * Wt + 136); }
@@ -1190,7 +1201,10 @@ __global__ void __launch_bounds__(kPcThreads, 1) pc2pc_umma_kernel(const Pc2PcAr
     for (int i = 0; i < G; ++i) mbar_init(&acc_full[i], 1), mbar_init(&acc_empty[i], 128);
     mbar_init_fence();
   }
-  if (threadIdx.x < 16) s_scale[threadIdx.x] = a.scale[threadIdx.x] * (1.f / kWScale), s_shift[threadIdx.x] = a.shift[threadIdx.x];
+  if (threadIdx.x < 16) {
+    const float inv = (EPI == 3 && a.maxbits) ? 1.f / tc_scale_of(__ldg(a.maxbits)) : 1.f;  // exact: a power of two
+    s_scale[threadIdx.x] = a.scale[threadIdx.x] * (1.f / kWScale) * inv, s_shift[threadIdx.x] = a.shift[threadIdx.x];
+  }
   // positions the bulk copies never write only feed discarded anchors; give them finite values once
   for (uint32_t i = threadIdx.x; i < 8 * plane / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
   fence_proxy_async();
@@ -1326,13 +1340,21 @@ __global__ void __launch_bounds__(kPcThreads, 1) pc2pc_umma_kernel(const Pc2PcAr
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           f2_unpack(f2_fma(o[e], f2_pack(s_scale[2 * e], s_scale[2 * e + 1]), f2_pack(s_shift[2 * e], s_shift[2 * e + 1])), y[2 * e], y[2 * e + 1]);
-          y[2 * e] = fmaxf(y[2 * e], kLeakySlope * y[2 * e]), y[2 * e + 1] = fmaxf(y[2 * e + 1], kLeakySlope * y[2 * e + 1]);
+          if constexpr (EPI != 3) y[2 * e] = fmaxf(y[2 * e], kLeakySlope * y[2 * e]), y[2 * e + 1] = fmaxf(y[2 * e + 1], kLeakySlope * y[2 * e + 1]);
         }
         const int anchor = m * kPcStride + tid;
         const int c = (int)__umulhi((uint32_t)anchor, wt_magic), tl = anchor - c * Wt;
         const int t = t0 + tl;
         bool valid = tid < kPcStride && anchor < n_anchor && tl < TBv;
         int col = t + a.col_off;
+        if constexpr (EPI == 3) {  // raw planar fp32 (the training step's conv / data gradient)
+          if (valid) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (i < a.Cout_store) a.out_f32[(((long long)b * a.Cout_store + i) * 12 + c) * a.T_out + t] = y[i];
+          }
+          valid = false;
+        }
         if constexpr (EPI == 1) {
           // fused MaxPool2d((1,2)): frames (2u, 2u+1) are neighbouring anchors of one warp (t0, TB, Wt and the block stride are even)
 #pragma unroll
@@ -1408,6 +1430,8 @@ struct Pc8Args {
   __half* out_lo;        // EPI 0: [B][23][Wd_out][8] written at column t + 3
   int Wd_out;
   float* out_f32;        // EPI 2: (B, Cout, 12, T_out)
+  int raw;               // EPI 2, training step: no activation, scale additionally divided by tc_scale_of(*maxbits)
+  const unsigned* maxbits;
 };
 
 __host__ __device__ inline uint32_t pc8_plane_positions(int Wt) { return (uint32_t)(23 * Wt + 136); }
@@ -1443,7 +1467,8 @@ __global__ void __launch_bounds__(kPc8Threads, 1) pc8_umma_kernel(const Pc8Args 
   }
   if (threadIdx.x < 8) {
     const bool on = (int)threadIdx.x < a.Cout;
-    s_scale[threadIdx.x] = on ? a.scale[threadIdx.x] * (1.f / kWScale) : 0.f, s_shift[threadIdx.x] = on ? a.shift[threadIdx.x] : 0.f;
+    const float inv = (a.raw && a.maxbits) ? 1.f / tc_scale_of(__ldg(a.maxbits)) : 1.f;  // exact: a power of two
+    s_scale[threadIdx.x] = on ? a.scale[threadIdx.x] * (1.f / kWScale) * inv : 0.f, s_shift[threadIdx.x] = on ? a.shift[threadIdx.x] : 0.f;
   }
   // positions the bulk copies never write only feed discarded anchors; give them finite values once
   for (uint32_t i = threadIdx.x; i < 4 * plane / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
@@ -1578,7 +1603,7 @@ __global__ void __launch_bounds__(kPc8Threads, 1) pc8_umma_kernel(const Pc8Args 
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               f2_unpack(f2_fma(o[e], sc2[e], sh2[e]), y[2 * e], y[2 * e + 1]);
-              y[2 * e] = fmaxf(y[2 * e], kLeakySlope * y[2 * e]), y[2 * e + 1] = fmaxf(y[2 * e + 1], kLeakySlope * y[2 * e + 1]);
+              if (!a.raw) y[2 * e] = fmaxf(y[2 * e], kLeakySlope * y[2 * e]), y[2 * e + 1] = fmaxf(y[2 * e + 1], kLeakySlope * y[2 * e + 1]);
             }
             const int t = t0 + tl;
             if constexpr (EPI == 0) {
