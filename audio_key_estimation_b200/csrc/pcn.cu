@@ -465,12 +465,12 @@ struct Fwd {
   __half* tc_hi = nullptr;
   __half* tc_lo = nullptr;
   float* tc_raw = nullptr;
-  __half* tc_wimg = nullptr;
+  __half* tcw_block = nullptr;                 // every operand image of the step (tc_pack_all_weights_kernel)
+  std::map<int, long long> tcw_fwd, tcw_bwd;  // conv id -> offset (halves) of its forward / data-gradient image in the block
   // ... and the equivariant 12 x 7 convolutions of the PitchClass2PitchClass stacks (pc2pc_umma_kernel<3>, pc8_umma_kernel<2> raw)
   bool eq_ready = false;
   __half* eq_hi = nullptr;
   __half* eq_lo = nullptr;
-  __half* eq_wimg = nullptr;
   // backward: scratch of the tensor-core weight gradient (side stream: its own planes)
   bool wg_ready = false;
   __half* wg_x[2] = {};
@@ -502,7 +502,7 @@ struct Fwd {
   void train_bn(const Conv& c, const View& v, int coff) {
     if (dry) return;
     const int rt = v.R * v.T;
-    dim3 grid(std::max(1, std::min(64, (int)cdiv64((long long)B * rt, 4096))), c.Cout);
+    dim3 grid(std::max(1, std::min(64, (int)cdiv64((long long)B * rt, 1024))), c.Cout);
     bn_stats_kernel<<<grid, 256, 0, st>>>(v.p, B, v.C, coff, rt, d_stats + 2 * c.ss_off);
     AKE_LAUNCHED();
     train_bn_finalize(c, rt);
@@ -523,6 +523,47 @@ struct Fwd {
     AKE_LAUNCHED();
   }
 
+  // ---- train mode: operand images of every tensor-core convolution of the step, packed by ONE launch at the start of the kept forward
+  // (the parameters changed since the last step); `sites`: (conv id, geometry, input frames) of the candidate convolutions
+  struct TcSite {
+    int id;
+    ConvGeom g;
+    int Tn;
+    bool two_inputs;
+  };
+  void tc_pack_images(const std::vector<TcSite>& sites) {
+    std::vector<TcWeightEntry> ents;
+    long long total = 0;
+    for (const TcSite& s : sites) {
+      const Conv& c = p->convs[s.id];
+      int kind = -1;
+      if (tc_conv_ok(c, s.g, s.Tn)) kind = 0;
+      else if (!s.two_inputs && eq_conv_ok(c, s.g, s.Tn)) kind = (c.Cin > 8 || c.Cout > 8) ? 2 : 1;
+      if (kind < 0) continue;
+      const long long halves = (kind == 0 ? kP2PWBytes : (kind == 1 ? kPc8WBytes : kPcWBytes)) / 2;
+      for (int flip = 0; flip < 2; ++flip) {
+        ents.push_back(TcWeightEntry{c.w_off, total, c.Cout, c.Cin, kind, flip});
+        (flip ? tcw_bwd : tcw_fwd)[s.id] = total;
+        total += (halves + 127) / 128 * 128;
+      }
+    }
+    tcw_block = arena.take<__half>((size_t)std::max<long long>(total, 128));
+    for (size_t i0 = 0; !dry && i0 < ents.size(); i0 += kTcWeightMax) {
+      TcWeightTable t{};
+      t.n = (int)std::min<size_t>(kTcWeightMax, ents.size() - i0);
+      for (int i = 0; i < t.n; ++i) t.e[i] = ents[i0 + i];
+      tc_pack_all_weights_kernel<<<dim3(21, t.n), 256, 0, st>>>(t, p->d_params, tcw_block);
+      AKE_LAUNCHED();
+    }
+  }
+  const __half* tc_image(const Conv& c, bool dgrad) const {
+    const int id = (int)(&c - p->convs.data());
+    const auto& m = dgrad ? tcw_bwd : tcw_fwd;
+    const auto it = m.find(id);
+    if (it == m.end()) fail(AKE_ERR_INVALID, "internal: no tensor-core operand image was packed for conv %d", id);
+    return tcw_block ? tcw_block + it->second : nullptr;
+  }
+
   // ---- train mode: a 7x7 circular convolution (or its data gradient) on the tensor cores (pcn_train_tc.cuh)
   bool tc_conv_ok(const Conv& c, const ConvGeom& g, int Tn) const {
     static const bool on = [] { const char* e = getenv("AKE_TRAIN_TC"); return e ? atoi(e) != 0 : true; }();
@@ -537,14 +578,11 @@ struct Fwd {
       const size_t halves = (size_t)B * (P + 6) * Wd * 8;
       tc_hi = arena.take<__half>(halves), tc_lo = arena.take<__half>(halves);
       tc_raw = arena.take<float>((size_t)B * P * Tn * 8);
-      tc_wimg = arena.take<__half>(kP2PWBytes / 2);
       tc_ready = true;
     }
     if (dry) return;
     ProfScope prof("pcn.p2p", st);
-    if (dgrad) p2p_pack_weights_flip_kernel<<<14, 256, 0, st>>>(p->d_params + c.w_off, c.Cout, c.Cin, tc_wimg);
-    else p2p_pack_weights_kernel<<<14, 256, 0, st>>>(p->d_params + c.w_off, c.Cout, c.Cin, tc_wimg);
-    AKE_LAUNCHED();
+    const __half* wimg = tc_image(c, dgrad);
     TcPackArgs pa{};
     pa.in0 = in0.p, pa.bs0 = in0.bstride(), pa.c0 = in0.C;
     pa.in1 = in1 ? in1->p : in0.p, pa.bs1 = in1 ? in1->bstride() : 0, pa.c1 = in1 ? in1->C : 0, pa.rows1 = in1 ? in1->R : 1;
@@ -555,7 +593,7 @@ struct Fwd {
     const size_t smem = p2p_smem_bytes(TB + 6);
     ensure_dyn_smem(p2p_umma_kernel<false, true>, smem);
     check_decode_range((long long)n_tiles, (long long)n_rt * n_tt, "Pitch2Pitch (training)");
-    P2PArgs a{tc_hi, tc_lo, nullptr, nullptr, tc_wimg, p->d_ss_raw, p->d_ss_raw, P, Tn, Wd, TB, n_tt, n_rt, n_tiles, nullptr, nullptr, tc_raw};
+    P2PArgs a{tc_hi, tc_lo, nullptr, nullptr, wimg, p->d_ss_raw, p->d_ss_raw, P, Tn, Wd, TB, n_tt, n_rt, n_tiles, nullptr, nullptr, tc_raw};
     p2p_umma_kernel<false, true><<<std::min(n_tiles, sm_count()), kP2PThreads, smem, st>>>(a);
     AKE_LAUNCHED();
     TcUnpackArgs ua{};
@@ -579,22 +617,13 @@ struct Fwd {
     if (!eq_ready) {
       const size_t halves = (size_t)B * 2 * 23 * Wd * 8;
       eq_hi = arena.take<__half>(halves), eq_lo = arena.take<__half>(halves);
-      eq_wimg = arena.take<__half>(kPcWBytes / 2);
       eq_ready = true;
     }
     if (dry) return;
     ProfScope prof("pcn.equiv", st);
     const int Cin = dgrad ? c.Cout : c.Cin, Cout = dgrad ? c.Cin : c.Cout;  // of the convolution that runs
     const bool wide = Cin > 8 || Cout > 8;
-    const float* w = p->d_params + c.w_off;
-    if (wide) {
-      if (dgrad) pc2pc_pack_weights_flip_kernel<<<84, 256, 0, st>>>(w, c.Cout, c.Cin, eq_wimg);
-      else pc2pc_pack_weights_kernel<<<84, 256, 0, st>>>(w, c.Cout, c.Cin, eq_wimg);
-    } else {
-      if (dgrad) pc8_pack_weights_flip_kernel<<<21, 256, 0, st>>>(w, c.Cout, c.Cin, eq_wimg);
-      else pc8_pack_weights_kernel<<<21, 256, 0, st>>>(w, c.Cout, c.Cin, eq_wimg);
-    }
-    AKE_LAUNCHED();
+    const __half* wimg = tc_image(c, dgrad);
     EqPackArgs pa{in.p, B, in.C, wide ? 2 : 1, Tn, Wd, maxbits, eq_hi, eq_lo};
     eq_pack_planes_kernel<<<ew_blocks((long long)B * pa.G * 23 * Wd), 256, 0, st>>>(pa);
     AKE_LAUNCHED();
@@ -608,7 +637,7 @@ struct Fwd {
       ea.in_hi = eq_hi, ea.in_lo = eq_lo, ea.Wd_in = Wd, ea.T_out = Tn, ea.TB = TBe, ea.n_ttiles = cdiv(Tn, TBe);
       ea.n_tiles = ea.n_ttiles * B;
       check_decode_range((long long)ea.n_tiles, ea.n_ttiles, "PitchClass2PitchClass (training)");
-      ea.wimg = eq_wimg, ea.scale = scale, ea.shift = shift, ea.out_f32 = out.p, ea.Cout_store = Cout, ea.maxbits = maxbits;
+      ea.wimg = wimg, ea.scale = scale, ea.shift = shift, ea.out_f32 = out.p, ea.Cout_store = Cout, ea.maxbits = maxbits;
       pc2pc_umma_kernel<3><<<std::min(ea.n_tiles, sm_count()), kPcThreads, smem_e, st>>>(ea);
     } else {
       const int n_tt = cdiv(Tn, kPc8MaxTB), TB8 = (cdiv(Tn, n_tt) + 1) / 2 * 2;
@@ -618,7 +647,7 @@ struct Fwd {
       a8.in_hi = eq_hi, a8.in_lo = eq_lo, a8.Wd_in = Wd, a8.T_out = Tn, a8.TB = TB8, a8.n_ttiles = cdiv(Tn, TB8);
       a8.n_tiles = a8.n_ttiles * B;
       check_decode_range((long long)a8.n_tiles, a8.n_ttiles, "layer-0 PitchClass2PitchClass (training)");
-      a8.wimg = eq_wimg, a8.scale = scale, a8.shift = shift, a8.Cout = Cout, a8.out_f32 = out.p, a8.raw = 1, a8.maxbits = maxbits;
+      a8.wimg = wimg, a8.scale = scale, a8.shift = shift, a8.Cout = Cout, a8.out_f32 = out.p, a8.raw = 1, a8.maxbits = maxbits;
       pc8_umma_kernel<2><<<std::min(a8.n_tiles, sm_count()), kPc8Threads, smem8, st>>>(a8);
     }
     AKE_LAUNCHED();

@@ -39,11 +39,11 @@ struct TrainTape {
   __half* tc_hi = nullptr;
   __half* tc_lo = nullptr;
   float* tc_raw = nullptr;
-  __half* tc_wimg = nullptr;
   bool eq_ready = false;
   __half* eq_hi = nullptr;
   __half* eq_lo = nullptr;
-  __half* eq_wimg = nullptr;
+  __half* tcw_block = nullptr;
+  std::map<int, long long> tcw_fwd, tcw_bwd;
 };
 
 __global__ void fill_kernel(float* __restrict__ x, int n, float v) {
@@ -152,6 +152,15 @@ void Fwd::run_keep(const float* mel, float* key_out, float* tonic_out, float* ge
   const LayerPlan& l0 = p->layers[0];
   const LayerPlan& l1 = p->layers[1];
 
+  {
+    // operand images of the step's tensor-core convolutions (7x7 stack, both equivariant stacks), one launch
+    std::vector<TcSite> cand;
+    const ConvGeom gp0{k, k, 1, P, 1, -(k / 2), k / 2, 1, P, T};
+    for (int id : l0.pc2pc) cand.push_back(TcSite{id, g_equiv(T, true), T, false});
+    for (int id : l1.p2p) cand.push_back(TcSite{id, gp0, T, false});
+    for (int id : l1.pc2pc) cand.push_back(TcSite{id, g_equiv(T, true), T, false});
+    tc_pack_images(cand);
+  }
   // ---- layer 0 (models.py:359-369)
   tp.s0 = site(l0.sem, tp.mel, nullptr, g_sem, false);
   tp.q0 = alloc(1, 12, T);
@@ -226,8 +235,9 @@ void Fwd::run_keep(const float* mel, float* key_out, float* tonic_out, float* ge
                                                                                tonic_out, genre_out);
     AKE_LAUNCHED();
   }
-  tp.tc_ready = tc_ready, tp.tc_hi = tc_hi, tp.tc_lo = tc_lo, tp.tc_raw = tc_raw, tp.tc_wimg = tc_wimg;
-  tp.eq_ready = eq_ready, tp.eq_hi = eq_hi, tp.eq_lo = eq_lo, tp.eq_wimg = eq_wimg;
+  tp.tc_ready = tc_ready, tp.tc_hi = tc_hi, tp.tc_lo = tc_lo, tp.tc_raw = tc_raw;
+  tp.eq_ready = eq_ready, tp.eq_hi = eq_hi, tp.eq_lo = eq_lo;
+  tp.tcw_block = tcw_block, tp.tcw_fwd = tcw_fwd, tp.tcw_bwd = tcw_bwd;
   tp.ws_off = arena.off;
   tp.valid = !dry;
 }
@@ -258,8 +268,9 @@ void Fwd::backward_keep(const TrainTape& tp, const float* d_key, const float* d_
   const ake_pcn_config& cfg = p->cfg;
   const int P = cfg.pitches, k = cfg.kernel_size;
   const int n_ss = p->n_ss;
-  tc_ready = tp.tc_ready, tc_hi = tp.tc_hi, tc_lo = tp.tc_lo, tc_raw = tp.tc_raw, tc_wimg = tp.tc_wimg;
-  eq_ready = tp.eq_ready, eq_hi = tp.eq_hi, eq_lo = tp.eq_lo, eq_wimg = tp.eq_wimg;
+  tc_ready = tp.tc_ready, tc_hi = tp.tc_hi, tc_lo = tp.tc_lo, tc_raw = tp.tc_raw;
+  eq_ready = tp.eq_ready, eq_hi = tp.eq_hi, eq_lo = tp.eq_lo;
+  tcw_block = tp.tcw_block, tcw_fwd = tp.tcw_fwd, tcw_bwd = tp.tcw_bwd;
   float* ones = arena.take<float>(64);
   float* zeros = arena.take<float>(64);
   double* bsums = arena.take<double>(2 * (size_t)n_ss);
@@ -287,7 +298,7 @@ void Fwd::backward_keep(const TrainTape& tp, const float* d_key, const float* d_
     const float* sh = tp.d_ss + n_ss + c.ss_off;
     const float* mu = tp.d_mi + c.ss_off;
     const float* is = tp.d_mi + n_ss + c.ss_off;
-    dim3 grid(std::max(1, std::min(64, (int)cdiv64((long long)B * RT, 4096))), c.Cout);
+    dim3 grid(std::max(1, std::min(64, (int)cdiv64((long long)B * RT, 1024))), c.Cout);
     bn_bwd_reduce_kernel<<<grid, 256, 0, st>>>(z.p, da.p, B, c.Cout, RT, sc, sh, mu, is, bsums + 2 * c.ss_off);
     AKE_LAUNCHED();
     bn_bwd_apply_kernel<<<ew_blocks(z.numel(B)), 256, 0, st>>>(z.p, da.p, dz.p, B, c.Cout, RT, sc, sh, mu, is, bsums + 2 * c.ss_off,
@@ -297,7 +308,7 @@ void Fwd::backward_keep(const TrainTape& tp, const float* d_key, const float* d_
   };
   auto bias_grad = [&](const Conv& c, const View& dz) {
     if (dry) return;
-    dim3 grid(std::max(1, std::min(32, (int)cdiv64((long long)B * dz.R * dz.T, 4096))), c.Cout);
+    dim3 grid(std::max(1, std::min(32, (int)cdiv64((long long)B * dz.R * dz.T, 1024))), c.Cout);
     channel_sum_kernel<<<grid, 256, 0, st>>>(dz.p, B, c.Cout, dz.R * dz.T, grads + c.b_off);
     AKE_LAUNCHED();
   };

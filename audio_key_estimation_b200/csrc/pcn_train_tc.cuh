@@ -10,7 +10,7 @@
 //   p2p_umma_kernel<0, 1> : raw accumulators (B, P, T, 8)
 //   tc_unpack_kernel      : -> planar z (+ bias, scales divided out) and, for the forward, the BatchNorm batch statistics of z in the
 //                           same pass (replaces bn_stats_kernel's extra read)
-// The data gradient is the same conv with the weights transposed and both taps flipped (p2p_pack_weights_flip_kernel):
+// The data gradient is the same conv with the weights transposed and both taps flipped (tc_pack_all_weights_kernel, flip = 1):
 //   dX[ci, p, t] = sum_{co, dp, dt} W[co, ci, 6 - dp, 6 - dt] dZ[co, p + dp - 3, t + dt - 3]   (indices circular).
 #pragma once
 #include "pcn_umma.cuh"
@@ -101,18 +101,6 @@ __global__ void __launch_bounds__(256) tc_unpack_kernel(const TcUnpackArgs a) {
     double v = 0.0;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += sh[w][threadIdx.x];
     atomicAdd(a.stats + threadIdx.x, v);
-  }
-}
-
-// weight image of the data-gradient conv: the conv (Cout' = Cin, Cin' = Cout) with w'[co'][ci'][dp][f] = w[ci'][co'][6 - dp][6 - f]
-__global__ void p2p_pack_weights_flip_kernel(const float* __restrict__ w, int Cout, int Cin, __half* __restrict__ img) {
-  const int n_items = 7 * 56 * 8;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_items; i += gridDim.x * blockDim.x) {
-    const int ci = i % 8, fc = (i / 8) % 56, dp = i / 448;  // ci: channel of dZ (< Cout), co: channel of dX (< Cin)
-    const int f = fc / 8, co = fc % 8;
-    float v = 0.f;
-    if (ci < Cout && co < Cin) v = w[(((long long)ci * Cin + co) * 7 + (6 - dp)) * 7 + (6 - f)] * kWScale;
-    p2p_img_store(img, dp, f, co, ci, v);
   }
 }
 
@@ -274,34 +262,67 @@ __global__ void __launch_bounds__(256) eq_pack_planes_kernel(const EqPackArgs a)
     store_split8(a.hi + i * 8, a.lo + i * 8, v);
   }
 }
-// data-gradient weight images: the equivariant conv (Cout' = Cin, Cin' = Cout) with w'[co'][ci'][dp][f] = w[ci'][co'][(12 - dp) % 12][6 - f]
-//   dX[ci, c, t] = sum_{co, dp, dt} W[co, ci, dp, dt] dZ[co, (c - dp) mod 12, t - dt + 3]
-__global__ void pc2pc_pack_weights_flip_kernel(const float* __restrict__ w, int Cout, int Cin, __half* __restrict__ img) {
-  const int n_items = 12 * 2 * 112 * 8;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_items; i += gridDim.x * blockDim.x) {
-    const int e = i % 8, n = (i / 8) % 112, g = (i / (8 * 112)) % 2, dp = i / (16 * 112);
-    const int f = n / 16, co = n % 16, ci = g * 8 + e;  // ci: channel of dZ (< Cout), co: channel of dX (< Cin)
-    float v = 0.f;
-    if (ci < Cout && co < Cin) v = w[(((long long)ci * Cin + co) * 12 + (12 - dp) % 12) * 7 + (6 - f)] * kWScale;
-    const __half hi = __float2half_rn(v);
-    const __half lo = __float2half_rn(v - __half2float(hi));
-    img[((dp * 2 + g) * 224 + n) * 8 + e] = hi;
-    img[((dp * 2 + g) * 224 + 112 + n) * 8 + e] = lo;
-  }
-}
-__global__ void pc8_pack_weights_flip_kernel(const float* __restrict__ w, int Cout, int Cin, __half* __restrict__ img) {
-  const int n_items = 12 * 56 * 8;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_items; i += gridDim.x * blockDim.x) {
-    const int ci = i % 8, fc = (i / 8) % 56, dp = i / 448;
-    const int f = fc / 8, co = fc % 8;
-    float v = 0.f;
-    if (ci < Cout && co < Cin) v = w[(((long long)ci * Cin + co) * 12 + (12 - dp) % 12) * 7 + (6 - f)] * kWScale;
-    const __half hi = __float2half_rn(v);
-    const __half lo = __float2half_rn(v - __half2float(hi));
+// ---- every operand image of a training step's tensor-core convolutions (forward + tap-flipped data-gradient images of the 7x7, the
+// <= 8-channel and the 16-channel equivariant convs) in ONE launch: the table travels as a kernel argument, blockIdx.y = entry.
+struct TcWeightEntry {
+  long long w_off;   // floats into the flat parameters
+  long long img_off; // halves into the step's image block
+  int Cout, Cin;     // of the convolution as stored (Cout, Cin, KH, 7)
+  int kind;          // 0: 7x7 (p2p_umma_kernel), 1: <= 8 channels equivariant (pc8_umma_kernel), 2: 16 channels equivariant (pc2pc_umma_kernel)
+  int flip;          // 1: the data-gradient image
+};
+constexpr int kTcWeightMax = 24;
+struct TcWeightTable {
+  int n;
+  TcWeightEntry e[kTcWeightMax];
+};
+__global__ void __launch_bounds__(256) tc_pack_all_weights_kernel(const TcWeightTable t, const float* __restrict__ params, __half* __restrict__ images) {
+  const TcWeightEntry& en = t.e[blockIdx.y];
+  const float* w = params + en.w_off;
+  __half* img = images + en.img_off;
+  const int Cout = en.Cout, Cin = en.Cin;
+  if (en.kind == 0) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 7 * 56 * 8; i += gridDim.x * blockDim.x) {
+      const int ci = i % 8, fc = (i / 8) % 56, dp = i / 448, f = fc / 8, co = fc % 8;
+      float v = 0.f;
+      if (!en.flip) {
+        if (ci < Cin && co < Cout) v = w[(((long long)co * Cin + ci) * 7 + dp) * 7 + f] * kWScale;
+      } else if (ci < Cout && co < Cin) {
+        v = w[(((long long)ci * Cin + co) * 7 + (6 - dp)) * 7 + (6 - f)] * kWScale;
+      }
+      p2p_img_store(img, dp, f, co, ci, v);
+    }
+  } else if (en.kind == 1) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 12 * 56 * 8; i += gridDim.x * blockDim.x) {
+      const int ci = i % 8, fc = (i / 8) % 56, dp = i / 448, f = fc / 8, co = fc % 8;
+      float v = 0.f;
+      if (!en.flip) {
+        if (ci < Cin && co < Cout) v = w[(((long long)co * Cin + ci) * 12 + dp) * 7 + f] * kWScale;
+      } else if (ci < Cout && co < Cin) {
+        v = w[(((long long)ci * Cin + co) * 12 + (12 - dp) % 12) * 7 + (6 - f)] * kWScale;
+      }
+      const __half hi = __float2half_rn(v);
+      const __half lo = __float2half_rn(v - __half2float(hi));
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      img[((dp * 2 + c) * 112 + 16 * f + co) * 8 + ci] = hi;
-      img[((dp * 2 + c) * 112 + 16 * f + 8 + co) * 8 + ci] = lo;
+      for (int c = 0; c < 2; ++c) {
+        img[((dp * 2 + c) * 112 + 16 * f + co) * 8 + ci] = hi;
+        img[((dp * 2 + c) * 112 + 16 * f + 8 + co) * 8 + ci] = lo;
+      }
+    }
+  } else {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 12 * 2 * 112 * 8; i += gridDim.x * blockDim.x) {
+      const int e = i % 8, n = (i / 8) % 112, g = (i / (8 * 112)) % 2, dp = i / (16 * 112);
+      const int f = n / 16, co = n % 16, ci = g * 8 + e;
+      float v = 0.f;
+      if (!en.flip) {
+        if (ci < Cin && co < Cout) v = w[(((long long)co * Cin + ci) * 12 + dp) * 7 + f] * kWScale;
+      } else if (ci < Cout && co < Cin) {
+        v = w[(((long long)ci * Cin + co) * 12 + (12 - dp) % 12) * 7 + (6 - f)] * kWScale;
+      }
+      const __half hi = __float2half_rn(v);
+      const __half lo = __float2half_rn(v - __half2float(hi));
+      img[((dp * 2 + g) * 224 + n) * 8 + e] = hi;
+      img[((dp * 2 + g) * 224 + 112 + n) * 8 + e] = lo;
     }
   }
 }
