@@ -105,6 +105,9 @@ void Fwd::run_keep(const float* mel, float* key_out, float* tonic_out, float* ge
     }
     return a;
   };
+  auto tail_conv_ok = [&](const Conv& c, const ConvGeom& g) {
+    return c.Cout == 1 && g.KW == 7 && g.KH == c.KH && (c.KH == 12 || c.KH == 2) && g.SR == 1 && g.pad_t == 0 && !g.time_circ && g.row_off == 0 && c.Cin * c.KH * 7 <= 8192;
+  };
   // conv (+ batch statistics) (+ BN + LReLU into a separate buffer)
   auto site = [&](int id, const View& in0, const View* in1, const ConvGeom& g, bool act_now) {
     const Conv& c = p->convs[id];
@@ -120,6 +123,18 @@ void Fwd::run_keep(const float* mel, float* key_out, float* tonic_out, float* ge
         train_bn_finalize(c, s.z.R * s.z.T);
         if (act_now) s.a = bn_act(c, s.z);
       }
+      return s;
+    }
+    if (!in1 && tail_conv_ok(c, g) && !s.has_bn) {
+      // last conv of a classifier head (Cin -> 1 channel): a dedicated latency-sized kernel
+      if (!dry) {
+        const size_t smem = sizeof(float) * ((size_t)c.Cin * c.KH * 7 + 256);
+        auto kern = c.KH == 12 ? tail_conv_fwd_kernel<12> : tail_conv_fwd_kernel<2>;
+        kern<<<dim3(g.rows_out, B), 256, smem, st>>>(in0.p, p->d_params + c.w_off, c.has_bias ? p->d_params + c.b_off : nullptr, s.z.p, c.Cin,
+                                                     in0.R, g.rows_out, in0.T, g.T_out, g.row_circ);
+        AKE_LAUNCHED();
+      }
+      s.a = s.z;
       return s;
     }
     if (!in1 && eq_conv_ok(c, g, in0.T)) {

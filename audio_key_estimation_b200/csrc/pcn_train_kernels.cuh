@@ -550,4 +550,52 @@ __global__ void __launch_bounds__(256) adam_step_kernel(const AdamArgs a) {
   }
 }
 
+// ---- last convolution of a classifier head (Cin -> 1 channel, KH x 7, valid in time; models.py:716-742) in train mode --------------------
+// 16 MMAC per step at batch 8: the generic row-tiled conv spends ~50 us of pure latency on it (one output channel per block pass, four
+// staged input-channel passes); here one thread owns one output frame of one row and a quarter of the input channels.  (A matching
+// dedicated data-gradient kernel was measured too: 8.7 us against the generic kernel's 6.5 us for the single input channel -- dropped.)
+//   out[b, 0, r, t] = bias + sum_{ci, dp, dt} W[0, ci, dp, dt] x[b, ci, row(r + dp), t + dt]      row() wraps modulo R_in when `wrap`
+// grid (R_out, B), 256 threads = 4 channel quarters x 64 frames (T_out <= 64 per pass, looped otherwise)
+template <int KH>
+__global__ void __launch_bounds__(256) tail_conv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                                                            float* __restrict__ out, int Cin, int R_in, int R_out, int T_in, int T_out,
+                                                            int wrap) {
+  extern __shared__ float tail_smem[];
+  float* ws = tail_smem;                 // [Cin][KH][7]
+  float* red = ws + Cin * KH * 7;        // [4][64]
+  const int r = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, q = tid >> 6, tl = tid & 63;
+  for (int i = tid; i < Cin * KH * 7; i += 256) ws[i] = __ldg(w + i);
+  __syncthreads();
+  const int cq = (Cin + 3) / 4;
+  for (int t0 = 0; t0 < T_out; t0 += 64) {
+    const int t = t0 + tl;
+    float acc = 0.f;
+    if (t < T_out) {
+      for (int ci = q * cq; ci < min(Cin, (q + 1) * cq); ++ci) {
+        // all KH x 7 loads of a channel are in flight before the first FMA: every (channel, row) line is a first touch for this
+        // block, i.e. an L2 round trip -- one per channel instead of one per row tap
+        float xv[KH][7];
+        const float* xc = x + ((long long)b * Cin + ci) * R_in * T_in + t;
+#pragma unroll
+        for (int dp = 0; dp < KH; ++dp) {
+          int row = r + dp;
+          if (wrap) row -= row >= R_in ? R_in : 0;
+#pragma unroll
+          for (int dt = 0; dt < 7; ++dt) xv[dp][dt] = __ldg(xc + row * T_in + dt);
+        }
+        const float* wc = ws + ci * KH * 7;
+#pragma unroll
+        for (int dp = 0; dp < KH; ++dp)
+#pragma unroll
+          for (int dt = 0; dt < 7; ++dt) acc = fmaf(wc[dp * 7 + dt], xv[dp][dt], acc);
+      }
+    }
+    red[q * 64 + tl] = acc;
+    __syncthreads();
+    if (q == 0 && t < T_out)
+      out[((long long)b * R_out + r) * T_out + t] = ((red[tl] + red[64 + tl]) + (red[128 + tl] + red[192 + tl])) + (bias ? __ldg(bias) : 0.f);
+    __syncthreads();
+  }
+}
+
 }  // namespace ake
