@@ -624,7 +624,7 @@ struct Fwd {
     const int Cin = dgrad ? c.Cout : c.Cin, Cout = dgrad ? c.Cin : c.Cout;  // of the convolution that runs
     const bool wide = Cin > 8 || Cout > 8;
     const __half* wimg = tc_image(c, dgrad);
-    EqPackArgs pa{in.p, B, in.C, wide ? 2 : 1, Tn, Wd, maxbits, eq_hi, eq_lo};
+    EqPackArgs pa{in.p, B, in.C, wide ? 2 : 1, Tn, Wd, 3, maxbits, eq_hi, eq_lo};
     eq_pack_planes_kernel<<<ew_blocks((long long)B * pa.G * 23 * Wd), 256, 0, st>>>(pa);
     AKE_LAUNCHED();
     const float* scale = dgrad ? ones : scale_of(c, true);
@@ -650,6 +650,45 @@ struct Fwd {
       a8.wimg = wimg, a8.scale = scale, a8.shift = shift, a8.Cout = Cout, a8.out_f32 = out.p, a8.raw = 1, a8.maxbits = maxbits;
       pc8_umma_kernel<2><<<std::min(a8.n_tiles, sm_count()), kPc8Threads, smem8, st>>>(a8);
     }
+    AKE_LAUNCHED();
+  }
+
+  // ---- train mode: the first conv of the tonic AND the key head (16 -> 32 | 32 channels, valid in time) in one tensor-core pass
+  // (equiv_umma_kernel<64, 1, 2> raw: the eval-mode kernel without BatchNorm / activation), raw planar outputs with their biases
+  bool heads_tc_ready = false;
+  __half* hd_hi = nullptr;
+  __half* hd_lo = nullptr;
+  __half* hd_wimg = nullptr;
+  float* hd_ss = nullptr;
+  bool heads_tc_ok(const Conv& ct, const Conv& ck, int T2) const {
+    static const bool on = [] { const char* e = getenv("AKE_TRAIN_TC_HEADS"); return e ? atoi(e) != 0 : true; }();
+    return on && p->umma && p->umma_heads && ct.Cin == 16 && ck.Cin == 16 && ct.Cout == 32 && ck.Cout == 32 && ct.KH == 12 && ck.KH == 12 && T2 >= 13;
+  }
+  void heads_tc(const View& pcp, const Conv& ct, const Conv& ck, View& zt, View& zk) {
+    const int T2 = pcp.T, T1 = T2 - 6;
+    if (!heads_tc_ready) {
+      const size_t halves = (size_t)B * 2 * 23 * T2 * 8 + 64 * 8;
+      hd_hi = arena.take<__half>(halves), hd_lo = arena.take<__half>(halves);
+      hd_wimg = arena.take<__half>((size_t)84 * 4096 / 2);
+      hd_ss = arena.take<float>(128);
+      heads_tc_ready = true;
+    }
+    if (dry) return;
+    ProfScope prof("pcn.equiv", st);
+    EqPackArgs pa{pcp.p, B, pcp.C, 2, T2, T2, 0, nullptr, hd_hi, hd_lo};
+    eq_pack_planes_kernel<<<ew_blocks((long long)B * 2 * 23 * T2), 256, 0, st>>>(pa);
+    AKE_LAUNCHED();
+    equiv_pack_weights_kernel<<<168, 256, 0, st>>>(p->d_params + ct.w_off, p->d_params + ck.w_off, 32, 64, 16, 1, hd_wimg);
+    AKE_LAUNCHED();
+    heads_raw_ss_kernel<<<1, 64, 0, st>>>(ct.has_bias ? p->d_params + ct.b_off : nullptr, ck.has_bias ? p->d_params + ck.b_off : nullptr, hd_ss);
+    AKE_LAUNCHED();
+    const int n_tt = cdiv(T1, 32), TBe = (cdiv(T1, n_tt) + 1) / 2 * 2;
+    const size_t smem_e = equiv_smem_bytes(TBe + 6);
+    ensure_dyn_smem(equiv_umma_kernel<64, 1, 2>, smem_e);
+    EquivArgs ea{};
+    ea.in_hi = hd_hi, ea.in_lo = hd_lo, ea.Wd_in = T2, ea.T_out = T1, ea.TB = TBe, ea.n_ttiles = cdiv(T1, TBe);
+    ea.wimg = hd_wimg, ea.scale = hd_ss, ea.shift = hd_ss + 64, ea.out_f32 = zt.p, ea.out_f32_b = zk.p, ea.raw = 1;
+    equiv_umma_kernel<64, 1, 2><<<dim3(ea.n_ttiles, B), 192, smem_e, st>>>(ea);
     AKE_LAUNCHED();
   }
 

@@ -236,9 +236,31 @@ void Fwd::run_keep(const float* mel, float* key_out, float* tonic_out, float* ge
   // ---- heads (models.py:713-742, 750-753)
   const int T1 = T2 - (k - 1), Tf = T1 - (k - 1);
   if (Tf <= 0) fail(AKE_ERR_INVALID, "T=%d is too short: the heads need more than %d frames after pooling", T, (k - 1) * cfg.head_layers);
-  tp.ht[0] = site(p->tonic_head[0], tp.pcp, nullptr, g_equiv(T2, false), true);
+  {
+    const Conv& ct = p->convs[p->tonic_head[0]];
+    const Conv& ck = p->convs[p->key_head[0]];
+    if (heads_tc_ok(ct, ck, T2) && ct.bn >= 0 && ck.bn >= 0) {
+      // first conv of both heads in ONE tensor-core pass (they read the same input), then each head's BatchNorm + LeakyReLU
+      const Conv* hc[2] = {&ct, &ck};
+      ConvSite* hs[2] = {&tp.ht[0], &tp.hk[0]};
+      const int ids[2] = {p->tonic_head[0], p->key_head[0]};
+      for (int h = 0; h < 2; ++h) {
+        ConvSite s;
+        s.id = ids[h], s.in0 = tp.pcp, s.g = g_equiv(T2, false), s.has_bn = true;
+        s.z = alloc(hc[h]->Cout, 12, T1);
+        *hs[h] = s;
+      }
+      heads_tc(tp.pcp, ct, ck, tp.ht[0].z, tp.hk[0].z);
+      for (int h = 0; h < 2; ++h) {
+        stats_of(*hc[h], hs[h]->z);
+        hs[h]->a = bn_act(*hc[h], hs[h]->z);
+      }
+    } else {
+      tp.ht[0] = site(p->tonic_head[0], tp.pcp, nullptr, g_equiv(T2, false), true);
+      tp.hk[0] = site(p->key_head[0], tp.pcp, nullptr, g_equiv(T2, false), true);
+    }
+  }
   tp.ht[1] = site(p->tonic_head[1], tp.ht[0].a, nullptr, g_equiv(T1, false), false);
-  tp.hk[0] = site(p->key_head[0], tp.pcp, nullptr, g_equiv(T2, false), true);
   tp.hk[1] = site(p->key_head[1], tp.hk[0].a, nullptr, g_equiv(T1, false), false);
   if (cfg.genre) {
     tp.hg[0] = site(p->genre_head[0], tp.pcp, nullptr, ConvGeom{1, k, 1, 12, 0, 0, 0, 0, 12, T1}, true);

@@ -5,7 +5,7 @@
 // operands, raw fp32 accumulators out"; the training step keeps planar fp32 activations (B, C, R, T) for its BatchNorm / weight-gradient
 // kernels, so the conv is wrapped by two streaming kernels:
 //   tc_pack_planes_kernel : planar fp32 [+ a second, row-tiled tensor: cat[mel, tile(up)]] -> hi / lo chunk planes [B][P+6][T+6][8] with
-//                           circular halos, times an exact power of two that brings the tensor's max |x| to [8, 16) (gradients are
+//                           circular halos, times an exact power of two that brings the tensor's max |x| to [2^13, 2^14) (gradients are
 //                           ~1e-5: the lo halves would fall into fp16's subnormals otherwise)
 //   p2p_umma_kernel<0, 1> : raw accumulators (B, P, T, 8)
 //   tc_unpack_kernel      : -> planar z (+ bias, scales divided out) and, for the forward, the BatchNorm batch statistics of z in the
@@ -239,6 +239,7 @@ __global__ void wgrad_tc_reduce_kernel(const float* __restrict__ partial, int n_
 struct EqPackArgs {
   const float* in;  // (B, C, 12, T)
   int B, C, G, T, Wd;
+  int col_shift;            // plane column of frame 0: 3 ("same" convs: zero halo columns) or 0 (valid convs: Wd = T)
   const unsigned* maxbits;  // NULL: scale 1
   __half* hi;
   __half* lo;
@@ -252,7 +253,7 @@ __global__ void __launch_bounds__(256) eq_pack_planes_kernel(const EqPackArgs a)
     const int row = (int)(q % 23);
     q /= 23;
     const int g = (int)(q % a.G), b = (int)(q / a.G);
-    const int c = row >= 12 ? row - 12 : row, t = col - 3;
+    const int c = row >= 12 ? row - 12 : row, t = col - a.col_shift;
     float v[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
@@ -262,6 +263,12 @@ __global__ void __launch_bounds__(256) eq_pack_planes_kernel(const EqPackArgs a)
     store_split8(a.hi + i * 8, a.lo + i * 8, v);
   }
 }
+// epilogue table of the heads' fused first conv in train mode: scale 1, shift = [tonic bias | key bias]
+__global__ void heads_raw_ss_kernel(const float* __restrict__ bias_t, const float* __restrict__ bias_k, float* __restrict__ ss) {
+  const int i = threadIdx.x;
+  if (i < 64) ss[i] = 1.f, ss[64 + i] = i < 32 ? (bias_t ? bias_t[i] : 0.f) : (bias_k ? bias_k[i - 32] : 0.f);
+}
+
 // ---- every operand image of a training step's tensor-core convolutions (forward + tap-flipped data-gradient images of the 7x7, the
 // <= 8-channel and the 16-channel equivariant convs) in ONE launch: the table travels as a kernel argument, blockIdx.y = entry.
 struct TcWeightEntry {

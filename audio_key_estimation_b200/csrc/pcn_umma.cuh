@@ -43,11 +43,12 @@ constexpr int kP2PMmas = 11;        // MMAs per block: 7 row taps (x_hi + x_lo) 
 __device__ __forceinline__ float leaky_f(float v) { return v > 0.f ? v : kLeakySlope * v; }
 
 // Training step (pcn_train_tc.cuh): operand planes of gradients carry an exact power of two that brings the tensor's largest |x|
-// (given as its float bit pattern) into [8, 16); the kernels divide it out again.
+// (given as its float bit pattern) into [2^13, 2^14) -- the top of fp16's range, so that elements down to 2^-16 of the largest keep
+// both halves of the hi/lo split in fp16's normal range; the kernels divide it out again.
 __device__ __forceinline__ float tc_scale_of(unsigned maxbits) {
   const int e = (int)((maxbits >> 23) & 0xffu);
-  if (e < 3 || e == 255) return 1.f;  // zero / denormal / non-finite: leave the tensor alone
-  return __uint_as_float((unsigned)(257 - e) << 23);  // 2^(3 - (e - 127))
+  if (e < 14 || e == 255) return 1.f;  // zero / denormal / non-finite: leave the tensor alone
+  return __uint_as_float((unsigned)(267 - e) << 23);  // 2^(13 - (e - 127))
 }
 
 __device__ __forceinline__ void store_split8(__half* hi_dst, __half* lo_dst, const float (&v)[8]) {
@@ -835,6 +836,7 @@ struct EquivArgs {
   float* out_f32;
   float* out_f32_b;
   int out_rows;   // EPI 3: rows per group of the output planes (23: wrapped pitch classes, 12: plain rows)
+  int raw;        // EPI 2, training step: no activation (y = acc * scale / kWScale + shift)
 };
 
 constexpr uint32_t kEqStageBytes = 16384;
@@ -1109,7 +1111,8 @@ __global__ void __launch_bounds__(192) equiv_umma_kernel(const EquivArgs a) {
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
                 const int co = h * 16 + j;
-                const float y = leaky_f(fmaf(u[j] + w[j], s_scale[co], s_shift[co]));
+                const float yl = fmaf(u[j] + w[j], s_scale[co], s_shift[co]);
+                const float y = a.raw ? yl : leaky_f(yl);
                 float* dst = co < 32 ? a.out_f32 : a.out_f32_b;
                 dst[(((long long)b * 32 + (co & 31)) * 12 + c) * a.T_out + t] = y;
               }

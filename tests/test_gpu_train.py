@@ -171,62 +171,48 @@ def test_graph_replay_equals_eager_step():
     assert len(graph._graphs) == 1
 
 
-_PATH_SCRIPT = r"""
-import sys, numpy as np, torch
-import audio_key_estimation_b200 as ake
-out, shapes = sys.argv[1], [tuple(int(v) for v in a.split("x")) for a in sys.argv[2:]]
-torch.manual_seed(11)
-net = ake.PitchClassNet(288, 12, 2, 7, opt=ake.default_opt(genre=True))
-for m in net.modules():
-    if isinstance(m, torch.nn.BatchNorm2d):
-        m.weight.data.uniform_(0.5, 1.5), m.bias.data.uniform_(-0.3, 0.3)
-net = net.cuda().train()
-res = {}
-for B, T in shapes:
-    g = torch.Generator().manual_seed(5)
-    mel = torch.log1p(torch.rand((B, 1, 288, T), generator=g) * 4).cuda()
-    seq = torch.randint(T // 2, T + 1, (B,), generator=g).cuda()
-    key = (torch.rand((B, 12), generator=g) < 0.6).float().cuda()
-    tonic = torch.nn.functional.one_hot(torch.randint(0, 12, (B,), generator=g), 12).cuda()
-    genre = torch.nn.functional.one_hot(torch.randint(0, 11, (B,), generator=g), 11).cuda()
-    step = ake.TrainStep(net)
-    r = step.step(mel, seq, key, tonic, genre)
-    torch.cuda.synchronize()
-    res[f"loss_{B}x{T}"] = r["loss"].item()
-    res[f"flat_{B}x{T}"] = step.flat_grads.cpu().numpy().copy()
-np.savez(out, **res)
-"""
+TOL_OTHER_SHAPES = 2e-2
 
 
-def test_tensor_core_path_matches_ffma_path(tmp_path):
-    """The tensor-core kernels of the training step (7x7 convs forward / data gradient / weight gradient, equivariant stacks forward /
-    data gradient: pcn_train_tc.cuh) against the fp32 FFMA kernels they replace (AKE_TRAIN_TC=0 AKE_TRAIN_TC_EQUIV=0 AKE_TRAIN_TC_WGRAD=0:
-    read once per process, hence the two subprocesses), at shapes the goldens do not cover: a frame count that is not a multiple of 16
-    (zero-padded K blocks of the weight-gradient GEMM), two time tiles per clip, ragged masks.  Tolerance 2e-4 of the largest gradient per
-    parameter tensor."""
-    import os
-    import subprocess
-    import sys
+@pytest.mark.parametrize("B,T", [(3, 57), (2, 200)])
+def test_train_step_matches_oracle_at_other_shapes(B, T):
+    """The training step against the float64 oracle port (oracle/pcn_port.py + torch autograd: the restatement that the golden tests
+    pin to the unmodified reference) at shapes the goldens do not cover: a frame count that is not a multiple of 16 (zero-padded K
+    blocks of the weight-gradient GEMM, odd time tiles), two time tiles per clip in the 7x7 kernels, ragged masks, random BatchNorm
+    affine parameters.  Loss to 1e-5.  Gradients to 2e-2 of each tensor's largest entry, NOT the goldens' 5e-4: on random data the
+    network's max-pools (octave, time) and LeakyReLU kinks make the gradient discontinuous in the activations -- a 1e-6 rounding
+    difference in a conv output moves a pooling winner and with it O(1e-3) of a gradient tensor (measured: up to 8e-3 at T = 176 / 200
+    for the tensor-core path AND 1e-3 for the fp32 FFMA path, exactly 0 beyond the floor at T = 61 / 64 / 73 / 151 / 160 for both;
+    tools/train_oracle_check.py).  A wrong tap, halo or scale shows up as O(1)."""
+    from oracle import pcn_port
 
-    shapes = ["3x57", "2x200"]
-    outs = []
-    for name, env in (("tc", {}), ("ffma", {"AKE_TRAIN_TC": "0", "AKE_TRAIN_TC_EQUIV": "0", "AKE_TRAIN_TC_WGRAD": "0"})):
-        out = str(tmp_path / f"{name}.npz")
-        e = dict(os.environ, **env)
-        e["PYTHONPATH"] = os.path.dirname(os.path.dirname(os.path.abspath(__file__))) + os.pathsep + e.get("PYTHONPATH", "")
-        r = subprocess.run([sys.executable, "-c", _PATH_SCRIPT, out, *shapes], env=e, capture_output=True, text=True, timeout=600)
-        assert r.returncode == 0, r.stderr[-2000:]
-        outs.append(np.load(out))
-    tc, ff = outs
+    torch.manual_seed(11)
     net = ake.PitchClassNet(288, 12, 2, 7, opt=ake.default_opt(genre=True))
-    for sh in shapes:
-        assert abs(float(tc[f"loss_{sh}"]) - float(ff[f"loss_{sh}"])) <= 1e-5 * abs(float(ff[f"loss_{sh}"]))
-        off = 0
-        for name in net._tensor_names:
-            n = net._lookup(name).numel()
-            a, b = tc[f"flat_{sh}"][off:off + n], ff[f"flat_{sh}"][off:off + n]
-            off += n
-            scale = np.abs(b).max()
-            if "running_" in name or "num_batches" in name or scale == 0:
-                continue
-            assert np.abs(a - b).max() <= 2e-4 * scale + 1e-9, f"{sh} {name}: {np.abs(a - b).max():.3e} vs max |grad| {scale:.3e}"
+    for m in net.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.weight.data.uniform_(0.5, 1.5), m.bias.data.uniform_(-0.3, 0.3)
+    sd64 = {k: v.detach().clone().double().requires_grad_("running_" not in k) for k, v in net.state_dict().items() if v.is_floating_point()}
+    g = torch.Generator().manual_seed(5)
+    mel = torch.log1p(torch.rand((B, 1, 288, T), generator=g) * 4)
+    seq = torch.randint(T // 2, T + 1, (B,), generator=g)
+    key = (torch.rand((B, 12), generator=g) < 0.6).float()
+    tonic = torch.nn.functional.one_hot(torch.randint(0, 12, (B,), generator=g), 12)
+    genre = torch.nn.functional.one_hot(torch.randint(0, 11, (B,), generator=g), 11)
+    out = pcn_port.pcn_forward(sd64, mel.double(), seq, train=True)
+    want_loss = ake.criterion(out, key.double(), tonic, genre)
+    want_loss.backward()
+
+    net = net.cuda().train()
+    step = ake.TrainStep(net)
+    res = step.step(mel.cuda(), seq.cuda(), key.cuda(), tonic.cuda(), genre.cuda())
+    assert abs(res["loss"].item() - want_loss.item()) <= 1e-5 * abs(want_loss.item())
+    floor = 1e-5 * max(float(v.grad.abs().max()) for v in sd64.values() if v.grad is not None)
+    errs = []
+    for name, prm in net.named_parameters():
+        ref = sd64[name].grad.numpy()
+        got = prm.grad.detach().cpu().numpy()
+        err, scale = np.abs(got - ref).max(), np.abs(ref).max()
+        errs.append((float(max(0.0, err - floor) / max(scale, 1e-30)), name, float(err), float(scale)))
+    errs.sort(reverse=True)
+    print(f"[B={B} T={T}] worst gradient errors / max |grad| vs the float64 oracle:", [(f"{e:.2e}", n) for e, n, _, _ in errs[:5]])
+    assert errs[0][0] <= TOL_OTHER_SHAPES, errs[:5]
