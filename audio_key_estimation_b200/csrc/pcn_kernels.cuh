@@ -748,17 +748,21 @@ __global__ void __launch_bounds__(512) head_fold_kernel(const HeadFoldArgs a) {
     }
   }
   __syncthreads();
-  // ---- out[c] = b + (1/n) sum W[ci][dp][dt] S[ci][row][dt]: one warp per output row, lanes over the (ci, dp, dt) triples
-  const int KH = a.KH[h], n_w = 32 * KH * 7;
+  // ---- out[c] = b + (1/n) sum W[ci][dp][dt] S[ci][row][dt]: one warp per output row, lanes over the (ci, dp) pairs, the seven time
+  // taps of a pair in sequence (one index decode per seven MACs: decoding every (ci, dp, dt) triple cost ~50 integer instructions per MAC
+  // and was most of the kernel's instruction count)
+  const int KH = a.KH[h], n_pairs = 32 * KH;
   const float* w = a.w[h];
   for (int c = warp; c < a.rows_out[h]; c += kWarps) {
     float acc = 0.f;
-#pragma unroll 4
-    for (int i = lane; i < n_w; i += 32) {
-      const int dt = i % 7, q = i / 7, dp = q % KH, ci = q / KH;
+    for (int q = lane; q < n_pairs; q += 32) {
+      const int ci = KH == 12 ? q / 12 : q / KH, dp = q - ci * KH;
       int row = c + dp;
       if (a.wrap[h]) row -= row >= 12 ? 12 : 0;
-      acc = fmaf(__ldg(w + i), S[(ci * 12 + row) * 7 + dt], acc);
+      const float* wq = w + q * 7;
+      const float* sq = S + (ci * 12 + row) * 7;
+#pragma unroll
+      for (int dt = 0; dt < 7; ++dt) acc = fmaf(__ldg(wq + dt), sq[dt], acc);
     }
     for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if (lane == 0) {
