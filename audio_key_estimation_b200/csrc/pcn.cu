@@ -934,7 +934,7 @@ void Fwd::run(const float* mel, float* key_out, float* tonic_out, float* genre_o
             for (int j = 0; j < 2; ++j) l0_planes[i][j] = arena.take<__half>((size_t)B * 23 * (Tn + 6) * 8);
         if (!dry) {
           ProfScope prof("pcn.semitone", st);
-          l0_semitone_pool_kernel<<<dim3(cdiv(Tn, 128), 12, B), 128, 0, st>>>(p_in.p, p->d_params + c.w_off, scale_of(c, false),
+          l0_semitone_pool_kernel<<<dim3(cdiv(12 * Tn, 128), 1, B), 128, 0, st>>>(p_in.p, p->d_params + c.w_off, scale_of(c, false),
                                                                             shift_of(c, false), semi.p, cat.p, P, Tn, 1, 0,
                                                                             l0_fast ? l0_planes[0][0] : nullptr,
                                                                             l0_fast ? l0_planes[0][1] : nullptr);
@@ -981,7 +981,7 @@ void Fwd::run(const float* mel, float* key_out, float* tonic_out, float* genre_o
         if (!dry) {
           ProfScope prof("pcn.prep", st);
           if (split1)
-            upsixth_planes_kernel<<<dim3(cdiv(Tn, 128), 36, B), 128, 0, st>>>(pc.p, p->d_params + cu.w_off, scale_of(cu, false),
+            upsixth_planes_kernel<<<dim3(cdiv(36 * Tn, 128), 1, B), 128, 0, st>>>(pc.p, p->d_params + cu.w_off, scale_of(cu, false),
                                                                               shift_of(cu, false), up_hi, up_lo, Tn, Wd);
           else
             upsixth_table_kernel<<<dim3(cdiv(Tn, 128), 36, B), 128, 0, st>>>(pc.p, p->d_params + cu.w_off, scale_of(cu, false),
@@ -1738,7 +1738,7 @@ int ake_pcn_forward_rows_f32(ake_pcn* p, const float* mel_dev, int B, int T, con
     f.os_key = f.os_tonic = f.os_genre = AKE_ROW_FLOATS;
     f.run(mel_dev, rows_out_dev, rows_out_dev + 12, p->cfg.genre ? rows_out_dev + 24 : nullptr);
     if (ids_out_dev) {
-      decode_kernel<<<cdiv(B, 128), 128, 0, st>>>(rows_out_dev, rows_out_dev + 12, p->cfg.genre ? rows_out_dev + 24 : nullptr, B, ids_out_dev,
+      decode_kernel<<<cdiv(B, 4), 128, 0, st>>>(rows_out_dev, rows_out_dev + 12, p->cfg.genre ? rows_out_dev + 24 : nullptr, B, ids_out_dev,
                                                   ids_out_dev + B, ids_out_dev + 2 * B, AKE_ROW_FLOATS, AKE_ROW_FLOATS, AKE_ROW_FLOATS);
       AKE_LAUNCHED();
     }
@@ -1802,7 +1802,7 @@ int ake_decode_f32(const float* key_out_dev, const float* tonic_out_dev, const f
   return guarded([&] {
     if (B <= 0) fail(AKE_ERR_INVALID, "B must be positive");
     if ((key_id_dev && !key_out_dev) || (tonic_id_dev && !tonic_out_dev)) fail(AKE_ERR_INVALID, "null argument");
-    decode_kernel<<<cdiv(B, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(key_out_dev, tonic_out_dev, genre_out_dev, B,
+    decode_kernel<<<cdiv(B, 4), 128, 0, static_cast<cudaStream_t>(stream)>>>(key_out_dev, tonic_out_dev, genre_out_dev, B,
                                                                             key_id_dev, tonic_id_dev, genre_id_dev);
     AKE_LAUNCHED();
   });

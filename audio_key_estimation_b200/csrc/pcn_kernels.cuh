@@ -370,14 +370,16 @@ __global__ void octmax_kernel(const float* __restrict__ in, int B, int C, int R,
 // ---- layer 0 in one pass (eval mode): pool_semi Conv2d(1,1,3,stride (3,1),time-circular) + BN + LeakyReLU (models.py:313-315,
 // 361-363) and Pitch2PitchClassPool (models.py:368) straight from the log-CQT.  One thread per (pitch class, frame): it walks
 // the octaves, so every semitone is accumulated by the same instruction sequence (transposition equivariance stays bit exact).
-// grid (frames / 128, 12, B).  `semi` (B,1,S,T) keeps the pre-pool map for the parity taps.
+// grid (12 * frames / 128, 1, B): the (pitch class, frame) pairs of a clip flattened over the blocks (151 frames in blocks of 128 would
+// leave 41 % of the second block's threads idle).  `semi` (B,1,S,T) keeps the pre-pool map for the parity taps.
 __global__ void __launch_bounds__(128) l0_semitone_pool_kernel(const float* __restrict__ mel, const float* __restrict__ w,
                                                                 const float* __restrict__ scale, const float* __restrict__ shift,
                                                                 float* __restrict__ semi, float* __restrict__ pc, int P, int T,
                                                                 int C_total, int coff, __half* __restrict__ pl_hi = nullptr,
                                                                 __half* __restrict__ pl_lo = nullptr) {
-  const int t = blockIdx.x * 128 + threadIdx.x, c = blockIdx.y, b = blockIdx.z;
-  if (t >= T) return;
+  const int idx = blockIdx.x * 128 + threadIdx.x, b = blockIdx.z;
+  if (idx >= 12 * T) return;
+  const int c = idx / T, t = idx - c * T;
   const int tm = t == 0 ? T - 1 : t - 1, tp = t == T - 1 ? 0 : t + 1;
   float k[9];
 #pragma unroll
@@ -779,41 +781,53 @@ __constant__ unsigned short kKeySignatureBits[21] = {
     0x5AB, 0x56B, 0xD6A, 0xD5A, 0xB5A, 0xB56, 0xAD6, 0xAD5, 0xAB5, 0x6B5, 0x6AD,
     0x5AD, 0x5AB, 0x56B, 0xD6A, 0x6B5, 0x5AD, 0x6AD, 0xB5A, 0xD5A, 0xB56};
 
-__global__ void decode_kernel(const float* __restrict__ key_out, const float* __restrict__ tonic_out,
-                              const float* __restrict__ genre_out, int B, int* __restrict__ key_id,
-                              int* __restrict__ tonic_id, int* __restrict__ genre_id, int os_key = 12, int os_tonic = 12,
-                              int os_genre = 11) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+// first maximum of (v, i) over the lanes of a warp (torch.argmax's tie rule); lanes that do not take part pass v = -inf
+__device__ __forceinline__ int warp_argmax_first(float v, int i) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, i, o);
+    if (ov > v || (ov == v && oi < i)) v = ov, i = oi;
+  }
+  return i;
+}
+
+// One WARP per clip: lane r < 21 scores key signature r (the same twelve conditional adds in the same order as a serial loop would do),
+// lanes < 12 / < 11 hold the tonic / genre logits; first-maximum reductions by shuffles.  (One thread per clip walked 21 x 12 table bits
+// serially: 8 us for 256 clips.)
+__global__ void __launch_bounds__(128) decode_kernel(const float* __restrict__ key_out, const float* __restrict__ tonic_out,
+                                                     const float* __restrict__ genre_out, int B, int* __restrict__ key_id,
+                                                     int* __restrict__ tonic_id, int* __restrict__ genre_id, int os_key = 12, int os_tonic = 12,
+                                                     int os_genre = 11) {
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (b >= B) return;
   if (key_id) {
     float k[12], nk = 0.f;
     for (int i = 0; i < 12; ++i) k[i] = key_out[(long long)b * os_key + i], nk = fmaf(k[i], k[i], nk);
     const float inv = 1.f / (fmaxf(sqrtf(nk), 1e-8f) * sqrtf(7.f));
-    int best = 0;
-    float bv = -INFINITY;
-    for (int r = 0; r < 21; ++r) {
-      float d = 0.f;
+    float d = -INFINITY;
+    if (lane < 21) {
+      d = 0.f;
+      const unsigned bits = kKeySignatureBits[lane];
       for (int i = 0; i < 12; ++i)
-        if ((kKeySignatureBits[r] >> (11 - i)) & 1) d += k[i];
+        if ((bits >> (11 - i)) & 1) d += k[i];
       d *= inv;
-      if (d > bv) bv = d, best = r;  // strict '>' keeps the first maximum, as torch.argmax does
     }
-    key_id[b] = best;
+    const int best = warp_argmax_first(d, lane);
+    if (lane == 0) key_id[b] = best;
   }
   if (tonic_id) {
-    int best = 0;
-    for (int i = 1; i < 12; ++i)
-      if (tonic_out[(long long)b * os_tonic + i] > tonic_out[(long long)b * os_tonic + best]) best = i;
-    tonic_id[b] = best;
+    const float v = lane < 12 ? tonic_out[(long long)b * os_tonic + lane] : -INFINITY;
+    const int best = warp_argmax_first(v, lane);
+    if (lane == 0) tonic_id[b] = best;
   }
   if (genre_id) {
     int best = -1;
     if (genre_out) {
-      best = 0;
-      for (int i = 1; i < 11; ++i)
-        if (genre_out[(long long)b * os_genre + i] > genre_out[(long long)b * os_genre + best]) best = i;
+      const float v = lane < 11 ? genre_out[(long long)b * os_genre + lane] : -INFINITY;
+      best = warp_argmax_first(v, lane);
     }
-    genre_id[b] = best;
+    if (lane == 0) genre_id[b] = best;
   }
 }
 

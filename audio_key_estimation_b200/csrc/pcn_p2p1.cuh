@@ -59,12 +59,13 @@ __global__ void p2p_pack_weights_sub_kernel(const float* __restrict__ w, int Cou
 }
 
 // up_sixth (models.py:372-374) as chunk planes of a 36-row image with circular halos: [B][36 + 6][Wd][8] (channels 4..7 zero).
-// grid (ceil(T / 128), 36, B)
+// grid (ceil(36 T / 128), 1, B)
 __global__ void __launch_bounds__(128) upsixth_planes_kernel(const float* __restrict__ pc, const float* __restrict__ w_up,
                                                              const float* __restrict__ scale, const float* __restrict__ shift,
                                                              __half* __restrict__ out_hi, __half* __restrict__ out_lo, int T, int Wd) {
-  const int t = blockIdx.x * 128 + threadIdx.x, p36 = blockIdx.y, b = blockIdx.z;
-  if (t >= T) return;
+  const int idx = blockIdx.x * 128 + threadIdx.x, b = blockIdx.z;  // (row, frame) pairs flattened over the blocks: no idle tail threads
+  if (idx >= 36 * T) return;
+  const int p36 = idx / T, t = idx - p36 * T;
   const int c = p36 / 3, r = p36 - 3 * c;
   float x[4], y[8];
 #pragma unroll
