@@ -1,5 +1,11 @@
-// pcn_train_tc.cuh -- the 7x7 circular convolutions of the TRAINING step on the tensor cores (BASELINE config 5; models.py:228-234 in
-// train mode and its data gradient).  They are 64.6 % of the network's MACs, forward and backward.
+// pcn_train_tc.cuh -- the TRAINING step's convolutions on the tensor cores (BASELINE config 5):
+//   * the 7x7 circular convolutions (models.py:228-234; 64.6 % of the network's MACs): forward, data gradient (this comment) and
+//     weight gradient (p2p_wgrad_umma_kernel below: one MN-major GEMM over positions);
+//   * the equivariant 12x7 convolutions of both PitchClass2PitchClass stacks (models.py:22-51, 191-197): forward and data gradient through
+//     raw-output variants of the eval-mode kernels (eq_pack_planes_kernel below feeds them);
+//   * the first conv of the tonic and key heads, forward (heads_raw_ss_kernel below builds its epilogue table);
+//   * every operand image of the step in one launch (tc_pack_all_weights_kernel).
+// Host side: Fwd::tc_conv / tc_wgrad / eq_conv / heads_tc in pcn.cu, wired into the kept forward / backward in pcn_train.cuh.
 //
 // The eval-mode kernel p2p_umma_kernel<false, RAW = true> (pcn_umma.cuh) already is "7x7 circular conv, fp16 hi/lo three-product
 // operands, raw fp32 accumulators out"; the training step keeps planar fp32 activations (B, C, R, T) for its BatchNorm / weight-gradient
