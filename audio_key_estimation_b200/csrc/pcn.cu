@@ -467,6 +467,7 @@ struct Fwd {
   float* tc_raw = nullptr;
   __half* tcw_block = nullptr;                 // every operand image of the step (tc_pack_all_weights_kernel)
   std::map<int, long long> tcw_fwd, tcw_bwd;  // conv id -> offset (halves) of its forward / data-gradient image in the block
+  std::map<int, long long> tcw_head;          // 2 * conv id + part -> data-gradient image of gradient channels [16 part, 16 part + 16) of a head's first conv
   // ... and the equivariant 12 x 7 convolutions of the PitchClass2PitchClass stacks (pc2pc_umma_kernel<3>, pc8_umma_kernel<2> raw)
   bool eq_ready = false;
   __half* eq_hi = nullptr;
@@ -531,7 +532,7 @@ struct Fwd {
     int Tn;
     bool two_inputs;
   };
-  void tc_pack_images(const std::vector<TcSite>& sites) {
+  void tc_pack_images(const std::vector<TcSite>& sites, const std::vector<int>& head_first = {}) {
     std::vector<TcWeightEntry> ents;
     long long total = 0;
     for (const TcSite& s : sites) {
@@ -542,9 +543,18 @@ struct Fwd {
       if (kind < 0) continue;
       const long long halves = (kind == 0 ? kP2PWBytes : (kind == 1 ? kPc8WBytes : kPcWBytes)) / 2;
       for (int flip = 0; flip < 2; ++flip) {
-        ents.push_back(TcWeightEntry{c.w_off, total, c.Cout, c.Cin, kind, flip});
+        ents.push_back(TcWeightEntry{c.w_off, total, c.Cout, c.Cin, kind, flip, 0});
         (flip ? tcw_bwd : tcw_fwd)[s.id] = total;
         total += (halves + 127) / 128 * 128;
+      }
+    }
+    // data gradient of the heads' first convs (32 gradient channels each -> 16): two 16-channel images per head
+    for (int id : head_first) {
+      const Conv& c = p->convs[id];
+      for (int part = 0; part < 2; ++part) {
+        ents.push_back(TcWeightEntry{c.w_off, total, c.Cout, c.Cin, 2, 1, 16 * part});
+        tcw_head[id * 2 + part] = total;
+        total += (kPcWBytes / 2 + 127) / 128 * 128;
       }
     }
     tcw_block = arena.take<__half>((size_t)std::max<long long>(total, 128));
@@ -624,7 +634,7 @@ struct Fwd {
     const int Cin = dgrad ? c.Cout : c.Cin, Cout = dgrad ? c.Cin : c.Cout;  // of the convolution that runs
     const bool wide = Cin > 8 || Cout > 8;
     const __half* wimg = tc_image(c, dgrad);
-    EqPackArgs pa{in.p, B, in.C, wide ? 2 : 1, Tn, Wd, 3, maxbits, eq_hi, eq_lo};
+    EqPackArgs pa{in.p, B, in.C, wide ? 2 : 1, Tn, Wd, 3, 0, maxbits, eq_hi, eq_lo};
     eq_pack_planes_kernel<<<ew_blocks((long long)B * pa.G * 23 * Wd), 256, 0, st>>>(pa);
     AKE_LAUNCHED();
     const float* scale = dgrad ? ones : scale_of(c, true);
@@ -675,7 +685,7 @@ struct Fwd {
     }
     if (dry) return;
     ProfScope prof("pcn.equiv", st);
-    EqPackArgs pa{pcp.p, B, pcp.C, 2, T2, T2, 0, nullptr, hd_hi, hd_lo};
+    EqPackArgs pa{pcp.p, B, pcp.C, 2, T2, T2, 0, 0, nullptr, hd_hi, hd_lo};
     eq_pack_planes_kernel<<<ew_blocks((long long)B * 2 * 23 * T2), 256, 0, st>>>(pa);
     AKE_LAUNCHED();
     equiv_pack_weights_kernel<<<168, 256, 0, st>>>(p->d_params + ct.w_off, p->d_params + ck.w_off, 32, 64, 16, 1, hd_wimg);
@@ -690,6 +700,31 @@ struct Fwd {
     ea.wimg = hd_wimg, ea.scale = hd_ss, ea.shift = hd_ss + 64, ea.out_f32 = zt.p, ea.out_f32_b = zk.p, ea.raw = 1;
     equiv_umma_kernel<64, 1, 2><<<dim3(ea.n_ttiles, B), 192, smem_e, st>>>(ea);
     AKE_LAUNCHED();
+  }
+
+  // data gradient of a head's first conv (16 -> 32 channels, valid in time): d_in (B, 16, 12, T2) (+)= the "full" conv of dz (B, 32, 12, T2 - 6)
+  // with the tap-flipped weights = pc2pc_umma_kernel<3> on planes with six zero halo columns, once per 16 gradient channels (the second
+  // launch, and a second head, accumulate)
+  void heads_dgrad_tc(int id, const View& dz, const unsigned* maxbits, const float* ones, const float* zeros, View& d_in, bool accumulate) {
+    const Conv& c = p->convs[id];
+    const int T1 = dz.T, T2 = d_in.T, Wd = T2 + 6;
+    if (dry) return;
+    ProfScope prof("pcn.equiv", st);
+    const int n_tt = cdiv(T2, 32), TBe = (cdiv(T2, n_tt) + 1) / 2 * 2;
+    const size_t smem_e = pc2pc_smem_bytes(TBe + 6);
+    ensure_dyn_smem(pc2pc_umma_kernel<3>, smem_e);
+    for (int part = 0; part < 2; ++part) {
+      EqPackArgs pa{dz.p, B, dz.C, 2, T1, Wd, 6, 16 * part, maxbits, eq_hi, eq_lo};
+      eq_pack_planes_kernel<<<ew_blocks((long long)B * 2 * 23 * Wd), 256, 0, st>>>(pa);
+      AKE_LAUNCHED();
+      Pc2PcArgs ea{};
+      ea.in_hi = eq_hi, ea.in_lo = eq_lo, ea.Wd_in = Wd, ea.T_out = T2, ea.TB = TBe, ea.n_ttiles = cdiv(T2, TBe);
+      ea.n_tiles = ea.n_ttiles * B;
+      ea.wimg = tcw_block + tcw_head.at(id * 2 + part), ea.scale = ones, ea.shift = zeros, ea.out_f32 = d_in.p, ea.Cout_store = c.Cin;
+      ea.maxbits = maxbits, ea.accumulate = (accumulate || part > 0) ? 1 : 0;
+      pc2pc_umma_kernel<3><<<std::min(ea.n_tiles, sm_count()), kPcThreads, smem_e, st>>>(ea);
+      AKE_LAUNCHED();
+    }
   }
 
   // dW of a 7x7 circular conv (input cat[in0, tile(in1)], output gradient dz with largest |dz| = maxbits) on the tensor cores,

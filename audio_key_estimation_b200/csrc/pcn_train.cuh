@@ -43,7 +43,8 @@ struct TrainTape {
   __half* eq_hi = nullptr;
   __half* eq_lo = nullptr;
   __half* tcw_block = nullptr;
-  std::map<int, long long> tcw_fwd, tcw_bwd;
+  std::map<int, long long> tcw_fwd, tcw_bwd, tcw_head;
+  bool heads_tc = false;  // the heads' first convs ran on the tensor cores (their data gradients do too)
 };
 
 __global__ void fill_kernel(float* __restrict__ x, int n, float v) {
@@ -174,7 +175,15 @@ void Fwd::run_keep(const float* mel, float* key_out, float* tonic_out, float* ge
     for (int id : l0.pc2pc) cand.push_back(TcSite{id, g_equiv(T, true), T, false});
     for (int id : l1.p2p) cand.push_back(TcSite{id, gp0, T, false});
     for (int id : l1.pc2pc) cand.push_back(TcSite{id, g_equiv(T, true), T, false});
-    tc_pack_images(cand);
+    std::vector<int> head_first;
+    {
+      const Conv& ct = p->convs[p->tonic_head[0]];
+      const Conv& ck = p->convs[p->key_head[0]];
+      if (heads_tc_ok(ct, ck, T / 2) && ct.bn >= 0 && ck.bn >= 0 && eq_conv_ok(p->convs[l1.pc2pc.back()], g_equiv(T, true), T))
+        head_first = {p->tonic_head[0], p->key_head[0]};
+    }
+    tp.heads_tc = !head_first.empty();
+    tc_pack_images(cand, head_first);
   }
   // ---- layer 0 (models.py:359-369)
   tp.s0 = site(l0.sem, tp.mel, nullptr, g_sem, false);
@@ -274,7 +283,7 @@ void Fwd::run_keep(const float* mel, float* key_out, float* tonic_out, float* ge
   }
   tp.tc_ready = tc_ready, tp.tc_hi = tc_hi, tp.tc_lo = tc_lo, tp.tc_raw = tc_raw;
   tp.eq_ready = eq_ready, tp.eq_hi = eq_hi, tp.eq_lo = eq_lo;
-  tp.tcw_block = tcw_block, tp.tcw_fwd = tcw_fwd, tp.tcw_bwd = tcw_bwd;
+  tp.tcw_block = tcw_block, tp.tcw_fwd = tcw_fwd, tp.tcw_bwd = tcw_bwd, tp.tcw_head = tcw_head;
   tp.ws_off = arena.off;
   tp.valid = !dry;
 }
@@ -307,7 +316,7 @@ void Fwd::backward_keep(const TrainTape& tp, const float* d_key, const float* d_
   const int n_ss = p->n_ss;
   tc_ready = tp.tc_ready, tc_hi = tp.tc_hi, tc_lo = tp.tc_lo, tc_raw = tp.tc_raw;
   eq_ready = tp.eq_ready, eq_hi = tp.eq_hi, eq_lo = tp.eq_lo;
-  tcw_block = tp.tcw_block, tcw_fwd = tp.tcw_fwd, tcw_bwd = tp.tcw_bwd;
+  tcw_block = tp.tcw_block, tcw_fwd = tp.tcw_fwd, tcw_bwd = tp.tcw_bwd, tcw_head = tp.tcw_head;
   float* ones = arena.take<float>(64);
   float* zeros = arena.take<float>(64);
   double* bsums = arena.take<double>(2 * (size_t)n_ss);
@@ -483,9 +492,12 @@ void Fwd::backward_keep(const TrainTape& tp, const float* d_key, const float* d_
     wgrad(h[1], d_frames);
     View d_a0 = zalloc(h[0].a);
     dgrad(h[1], d_frames, d_a0, false);
-    View dz0 = bn_bwd(h[0].id, h[0].z, d_a0);
+    const bool tc = tp.heads_tc && &h != &tp.hg && n_maxbits < 64 && eq_ready;
+    unsigned* mb = tc ? d_maxbits + n_maxbits++ : nullptr;
+    View dz0 = bn_bwd(h[0].id, h[0].z, d_a0, mb);
     wgrad(h[0], dz0);
-    dgrad(h[0], dz0, d_pcp, accumulate);
+    if (tc) heads_dgrad_tc(h[0].id, dz0, mb, ones, zeros, d_pcp, accumulate);
+    else dgrad(h[0], dz0, d_pcp, accumulate);
   };
   head_bwd(tp.ht, d_tf, false);
   head_bwd(tp.hk, d_kf, true);

@@ -243,9 +243,10 @@ __global__ void wgrad_tc_reduce_kernel(const float* __restrict__ partial, int n_
 // pc2pc_umma_kernel<3> (<= 16 -> <= 16 channels) and pc8_umma_kernel<2> with raw = 1 (<= 8 -> <= 8) write raw planar fp32; their operand
 // planes [B][G][23][T + 6][8] (zero halo columns = the "same" padding in time, rows 12..22 = rows 0..10) come from the planar activations:
 struct EqPackArgs {
-  const float* in;  // (B, C, 12, T)
+  const float* in;  // (B, C, 12, T); the planes hold its channels [c0, c0 + 8 G)
   int B, C, G, T, Wd;
-  int col_shift;            // plane column of frame 0: 3 ("same" convs: zero halo columns) or 0 (valid convs: Wd = T)
+  int col_shift;            // plane column of frame 0: 3 ("same" convs), 0 (valid convs: Wd = T) or 6 (the data gradient of a valid conv)
+  int c0;
   const unsigned* maxbits;  // NULL: scale 1
   __half* hi;
   __half* lo;
@@ -263,7 +264,7 @@ __global__ void __launch_bounds__(256) eq_pack_planes_kernel(const EqPackArgs a)
     float v[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const int ch = g * 8 + e;
+      const int ch = a.c0 + g * 8 + e;
       v[e] = (ch < a.C && t >= 0 && t < a.T) ? __ldg(a.in + (((long long)b * a.C + ch) * 12 + c) * a.T + t) * mul : 0.f;
     }
     store_split8(a.hi + i * 8, a.lo + i * 8, v);
@@ -283,6 +284,7 @@ struct TcWeightEntry {
   int Cout, Cin;     // of the convolution as stored (Cout, Cin, KH, 7)
   int kind;          // 0: 7x7 (p2p_umma_kernel), 1: <= 8 channels equivariant (pc8_umma_kernel), 2: 16 channels equivariant (pc2pc_umma_kernel)
   int flip;          // 1: the data-gradient image
+  int ci0;           // kind 2, flip: first gradient channel of this image (a data gradient over > 16 channels is summed over several images)
 };
 constexpr int kTcWeightMax = 24;
 struct TcWeightTable {
@@ -329,8 +331,8 @@ __global__ void __launch_bounds__(256) tc_pack_all_weights_kernel(const TcWeight
       float v = 0.f;
       if (!en.flip) {
         if (ci < Cin && co < Cout) v = w[(((long long)co * Cin + ci) * 12 + dp) * 7 + f] * kWScale;
-      } else if (ci < Cout && co < Cin) {
-        v = w[(((long long)ci * Cin + co) * 12 + (12 - dp) % 12) * 7 + (6 - f)] * kWScale;
+      } else if (en.ci0 + ci < Cout && co < Cin) {
+        v = w[(((long long)(en.ci0 + ci) * Cin + co) * 12 + (12 - dp) % 12) * 7 + (6 - f)] * kWScale;
       }
       const __half hi = __float2half_rn(v);
       const __half lo = __float2half_rn(v - __half2float(hi));

@@ -1173,6 +1173,7 @@ struct Pc2PcArgs {
   // EPI 3 (training step): y = acc * scale / kWScale / tc_scale_of(*maxbits) + shift, NO activation, planar fp32
   int Cout_store;
   const unsigned* maxbits;
+  int accumulate;        // EPI 3: add to the stored values (a data gradient summed over several launches: > 16 input channels, several consumers)
 };
 
 __host__ __device__ inline uint32_t pc2pc_plane_positions(int Wt) { return (uint32_t)(23 * Wt + 136); }
@@ -1354,7 +1355,10 @@ __global__ void __launch_bounds__(kPcThreads, 1) pc2pc_umma_kernel(const Pc2PcAr
           if (valid) {
 #pragma unroll
             for (int i = 0; i < 16; ++i)
-              if (i < a.Cout_store) a.out_f32[(((long long)b * a.Cout_store + i) * 12 + c) * a.T_out + t] = y[i];
+              if (i < a.Cout_store) {
+                float* dst = a.out_f32 + (((long long)b * a.Cout_store + i) * 12 + c) * a.T_out + t;
+                *dst = a.accumulate ? *dst + y[i] : y[i];
+              }
           }
           valid = false;
         }
