@@ -634,7 +634,7 @@ struct Fwd {
     const int Cin = dgrad ? c.Cout : c.Cin, Cout = dgrad ? c.Cin : c.Cout;  // of the convolution that runs
     const bool wide = Cin > 8 || Cout > 8;
     const __half* wimg = tc_image(c, dgrad);
-    EqPackArgs pa{in.p, B, in.C, wide ? 2 : 1, Tn, Wd, 3, 0, maxbits, eq_hi, eq_lo};
+    EqPackArgs pa{in.p, B, in.C, wide ? 2 : 1, Tn, Wd, 3, 0, 0, maxbits, eq_hi, eq_lo};
     eq_pack_planes_kernel<<<ew_blocks((long long)B * pa.G * 23 * Wd), 256, 0, st>>>(pa);
     AKE_LAUNCHED();
     const float* scale = dgrad ? ones : scale_of(c, true);
@@ -685,7 +685,7 @@ struct Fwd {
     }
     if (dry) return;
     ProfScope prof("pcn.equiv", st);
-    EqPackArgs pa{pcp.p, B, pcp.C, 2, T2, T2, 0, 0, nullptr, hd_hi, hd_lo};
+    EqPackArgs pa{pcp.p, B, pcp.C, 2, T2, T2, 0, 0, 0, nullptr, hd_hi, hd_lo};
     eq_pack_planes_kernel<<<ew_blocks((long long)B * 2 * 23 * T2), 256, 0, st>>>(pa);
     AKE_LAUNCHED();
     equiv_pack_weights_kernel<<<168, 256, 0, st>>>(p->d_params + ct.w_off, p->d_params + ck.w_off, 32, 64, 16, 1, hd_wimg);
@@ -714,7 +714,7 @@ struct Fwd {
     const size_t smem_e = pc2pc_smem_bytes(TBe + 6);
     ensure_dyn_smem(pc2pc_umma_kernel<3>, smem_e);
     for (int part = 0; part < 2; ++part) {
-      EqPackArgs pa{dz.p, B, dz.C, 2, T1, Wd, 6, 16 * part, maxbits, eq_hi, eq_lo};
+      EqPackArgs pa{dz.p, B, dz.C, 2, T1, Wd, 6, 16 * part, 0, maxbits, eq_hi, eq_lo};
       eq_pack_planes_kernel<<<ew_blocks((long long)B * 2 * 23 * Wd), 256, 0, st>>>(pa);
       AKE_LAUNCHED();
       Pc2PcArgs ea{};
@@ -758,6 +758,41 @@ struct Fwd {
     p2p_wgrad_umma_kernel<<<grid, kWgThreads, smem, ws>>>(wa);
     AKE_LAUNCHED();
     wgrad_tc_reduce_kernel<<<cdiv(c.Cout * c.Cin * 49, 128), 128, 0, ws>>>(wg_partial, grid, maxbits, c.Cout, c.Cin, dw);
+    AKE_LAUNCHED();
+  }
+  // dW of a 16-channel equivariant conv on the tensor cores, on stream `ws` (eq_wgrad_umma_kernel); overwrites dw (Cout, Cin, 12, 7)
+  bool eqw_ready = false;
+  __half* eqw_x[2] = {};
+  __half* eqw_g[2] = {};
+  float* eqw_partial = nullptr;
+  bool eq_wgrad_ok(const Conv& c, const ConvGeom& g, int Tn) const {
+    static const bool on = [] { const char* e = getenv("AKE_TRAIN_TC_EQ_WGRAD"); return e ? atoi(e) != 0 : true; }();
+    return on && eq_conv_ok(c, g, Tn) && (c.Cin > 8 || c.Cout > 8) && eq_wgrad_smem_bytes(Tn + 6, cdiv(Tn, 16) * 16) <= 227 * 1024 - 256;
+  }
+  void eq_wgrad(const View& in, const Conv& c, const View& dz, const unsigned* maxbits, float* dw, cudaStream_t ws) {
+    const int Tn = in.T, Wx = Tn + 6, Wg = cdiv(Tn, 16) * 16;
+    if (!eqw_ready) {
+      for (int i = 0; i < 2; ++i) {
+        eqw_x[i] = arena.take<__half>((size_t)B * 2 * 23 * Wx * 8 + 64 * 8);
+        eqw_g[i] = arena.take<__half>((size_t)B * 2 * 23 * Wg * 8 + 64 * 8);
+      }
+      eqw_partial = arena.take<float>((size_t)sm_count() * 64 * 96);
+      eqw_ready = true;
+    }
+    if (dry) return;
+    EqPackArgs px{in.p, B, in.C, 2, Tn, Wx, 3, 0, 0, nullptr, eqw_x[0], eqw_x[1]};
+    eq_pack_planes_kernel<<<ew_blocks((long long)B * 2 * 23 * Wx), 256, 0, ws>>>(px);
+    AKE_LAUNCHED();
+    EqPackArgs pg{dz.p, B, dz.C, 2, Tn, Wg, 0, 0, 1, maxbits, eqw_g[0], eqw_g[1]};
+    eq_pack_planes_kernel<<<ew_blocks((long long)B * 2 * 23 * Wg), 256, 0, ws>>>(pg);
+    AKE_LAUNCHED();
+    EqWgradArgs wa{eqw_x[0], eqw_x[1], eqw_g[0], eqw_g[1], eqw_partial, B, Tn, Wx, Wg};
+    const size_t smem = eq_wgrad_smem_bytes(Wx, Wg);
+    ensure_dyn_smem(eq_wgrad_umma_kernel, smem);
+    const int grid = std::min(4 * B, sm_count() / 4 * 4);
+    eq_wgrad_umma_kernel<<<grid, kEqWgThreads, smem, ws>>>(wa);
+    AKE_LAUNCHED();
+    eq_wgrad_reduce_kernel<<<cdiv(c.Cout * c.Cin * 84, 128), 128, 0, ws>>>(eqw_partial, grid, maxbits, c.Cout, c.Cin, dw);
     AKE_LAUNCHED();
   }
   bool tc_wgrad_ok(const Conv& c, const ConvGeom& g, int Tn) const {

@@ -364,8 +364,10 @@ void Fwd::backward_keep(const TrainTape& tp, const float* d_key, const float* d_
   auto wgrad = [&](const ConvSite& s, const View& dz, const unsigned* maxbits = nullptr) {
     const Conv& c = p->convs[s.id];
     const bool tc = maxbits != nullptr && tc_wgrad_ok(c, s.g, s.in0.T);
+    const bool eqw = maxbits != nullptr && !s.in1.p && eq_wgrad_ok(c, s.g, s.in0.T);
     if (dry) {
       if (tc) tc_wgrad(s.in0, s.in1.p ? &s.in1 : nullptr, c, dz, maxbits, nullptr, st);  // (carves the scratch)
+      if (eqw) eq_wgrad(s.in0, c, dz, maxbits, nullptr, st);
       return;
     }
     const cudaStream_t main_st = st;
@@ -386,6 +388,10 @@ void Fwd::backward_keep(const TrainTape& tp, const float* d_key, const float* d_
     if (!s.has_bn) bias_grad(c, dz);
     if (tc) {  // 7x7 conv: one tensor-core GEMM over positions, deterministic reduction (pcn_train_tc.cuh)
       tc_wgrad(s.in0, s.in1.p ? &s.in1 : nullptr, c, dz, maxbits, grads + c.w_off, st);
+      return;
+    }
+    if (eqw) {  // 16-channel equivariant conv: likewise (eq_wgrad_umma_kernel)
+      eq_wgrad(s.in0, c, dz, maxbits, grads + c.w_off, st);
       return;
     }
     WgradArgs a{};

@@ -247,6 +247,7 @@ struct EqPackArgs {
   int B, C, G, T, Wd;
   int col_shift;            // plane column of frame 0: 3 ("same" convs), 0 (valid convs: Wd = T) or 6 (the data gradient of a valid conv)
   int c0;
+  int row_shift;            // plane row i holds pitch class (i + row_shift) % 12: 0 (operand of the conv), 1 (gradient operand of eq_wgrad_umma_kernel)
   const unsigned* maxbits;  // NULL: scale 1
   __half* hi;
   __half* lo;
@@ -260,7 +261,7 @@ __global__ void __launch_bounds__(256) eq_pack_planes_kernel(const EqPackArgs a)
     const int row = (int)(q % 23);
     q /= 23;
     const int g = (int)(q % a.G), b = (int)(q / a.G);
-    const int c = row >= 12 ? row - 12 : row, t = col - a.col_shift;
+    const int c = (row + a.row_shift) % 12, t = col - a.col_shift;
     float v[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
@@ -270,6 +271,123 @@ __global__ void __launch_bounds__(256) eq_pack_planes_kernel(const EqPackArgs a)
     store_split8(a.hi + i * 8, a.lo + i * 8, v);
   }
 }
+// ---- weight gradient of a 16-channel equivariant 12 x 7 conv ("same" in time) as a tensor-core GEMM over positions -----------------------
+//   dW[co, ci, dp, dt] = sum_{b, c, t} dZ[b, co, c, t] * x~[b, ci, (c + dp) mod 12, t + dt]       (x~: the operand planes, three zero halo columns)
+// The scheme of p2p_wgrad_umma_kernel with twelve row taps: for input row rho the gradient rows (rho - dp) mod 12, dp = 11 ... 0, are the
+// CONSECUTIVE rows rho ... rho + 11 of a 23-row gradient plane whose row i holds pitch class (i + 1) mod 12 (eq_pack_planes_kernel, row_shift 1):
+//   A (M = 64): rows (dt, ci) of one channel group, K = 16 frames of x~ row rho (time taps 16 B apart: overlapping core matrices)
+//   B (N = 96): columns (j = 11 - dp, co) of one gradient channel group, rows rho + j (SBO = the plane's row pitch)
+// A work item is (clip, input channel group, output channel group); a CTA keeps its (group, group) pair over all its items (the grid is a
+// multiple of four), so its accumulator stays in TMEM; eq_wgrad_reduce_kernel sums the partials of each pair in CTA order.
+constexpr int kEqWgThreads = 32 * 6;
+struct EqWgradArgs {
+  const __half* x_hi;
+  const __half* x_lo;   // [B][2][23][Wx][8]
+  const __half* g_hi;
+  const __half* g_lo;   // [B][2][23][Wg][8]: zeros beyond T, scaled by tc_scale_of(maxbits)
+  float* partial;       // [gridDim.x][64][96]
+  int B, T, Wx, Wg;
+};
+__host__ __device__ inline uint32_t eq_wgrad_x_bytes(int Wx) { return (uint32_t)(12 * Wx + 32) * 16; }
+__host__ __device__ inline uint32_t eq_wgrad_g_bytes(int Wg) { return (uint32_t)(23 * Wg + 16) * 16; }
+__host__ __device__ inline size_t eq_wgrad_smem_bytes(int Wx, int Wg) { return (size_t)2 * (eq_wgrad_x_bytes(Wx) + eq_wgrad_g_bytes(Wg)); }
+
+__global__ void __launch_bounds__(kEqWgThreads, 1) eq_wgrad_umma_kernel(const EqWgradArgs a) {
+  using namespace umma;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t full_bar, empty_bar, done_bar;
+  __shared__ uint32_t tmem_slot;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
+  const uint32_t XB = eq_wgrad_x_bytes(a.Wx), GB = eq_wgrad_g_bytes(a.Wg);  // [x_hi][x_lo][g_hi][g_lo]
+  if (warp == 5) tmem_alloc(&tmem_slot, 128);
+  if (threadIdx.x == 0) {
+    mbar_init(&full_bar, 1), mbar_init(&empty_bar, 1), mbar_init(&done_bar, 1);
+    mbar_init_fence();
+  }
+  for (uint32_t i = threadIdx.x; i < 2 * (XB + GB) / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  const int n_items = 4 * a.B, n_blk = (a.T + 15) / 16;
+  const int gi = ((int)blockIdx.x & 3) >> 1, go = (int)blockIdx.x & 1;  // fixed per CTA: gridDim.x is a multiple of 4
+
+  if (warp == 4) {
+    // ------------------------------------------------------------ loader: 12 input rows and 23 gradient rows, contiguous in their planes
+    int k = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++k) {
+      const int b = item >> 2;
+      mbar_wait_relaxed(&empty_bar, (k & 1) ^ 1);
+      if (lane == 0) {
+        const uint32_t xb = (uint32_t)(12 * a.Wx) * 16, gb = (uint32_t)(23 * a.Wg) * 16;
+        mbar_arrive_expect_tx(&full_bar, 2 * (xb + gb));
+        const long long xo = (((long long)b * 2 + gi) * 23) * a.Wx * 8, gof = (((long long)b * 2 + go) * 23) * a.Wg * 8;
+        bulk_g2s(smem, a.x_hi + xo, xb, &full_bar);
+        bulk_g2s(smem + XB, a.x_lo + xo, xb, &full_bar);
+        bulk_g2s(smem + 2 * XB, a.g_hi + gof, gb, &full_bar);
+        bulk_g2s(smem + 2 * XB + GB, a.g_lo + gof, gb, &full_bar);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 5) {
+    // ------------------------------------------------------------ MMA issuer (converged warp, one elected lane issues)
+    constexpr uint64_t A_DESC = desc_hi(128, 16);
+    const uint64_t B_DESC = desc_hi(128, (uint32_t)a.Wg * 16);
+    constexpr uint32_t IDESC = idesc_f16(96, 64) | (1u << 15) | (1u << 16);  // A and B MN-major
+    const uint32_t x0 = smem_u32(smem), g0 = x0 + 2 * XB;
+    int k = 0;
+    uint32_t first = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++k) {
+      mbar_wait(&full_bar, k & 1);
+      fence_after_sync();
+      if (elect_one()) {
+        for (int rho = 0; rho < 12; ++rho) {
+          for (int c = 0; c < n_blk; ++c) {
+            const uint32_t xa = x0 + (uint32_t)(rho * a.Wx + 16 * c) * 16, ga = g0 + (uint32_t)(rho * a.Wg + 16 * c) * 16;
+            mma_f16(tmem, make_desc(A_DESC, xa), make_desc(B_DESC, ga), IDESC, first);
+            first = 1u;
+            mma_f16(tmem, make_desc(A_DESC, xa + XB), make_desc(B_DESC, ga), IDESC, 1u);
+            mma_f16(tmem, make_desc(A_DESC, xa), make_desc(B_DESC, ga + GB), IDESC, 1u);
+          }
+        }
+        commit(&empty_bar);
+      }
+      __syncwarp();
+    }
+    if (elect_one()) commit(&done_bar);
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------ final drain (M = 64: rows 16 q ... 16 q + 15 in lanes 0-15 of quadrant q)
+    mbar_wait_relaxed(&done_bar, 0);
+    fence_after_sync();
+    float* dst = a.partial + (size_t)blockIdx.x * 64 * 96;
+    for (int c0 = 0; c0 < 96; c0 += 8) {
+      float v[8];
+      tmem_ld8(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
+      if (lane < 16) {
+        float4* d4 = reinterpret_cast<float4*>(dst + (16 * warp + lane) * 96 + c0);
+        d4[0] = make_float4(v[0], v[1], v[2], v[3]), d4[1] = make_float4(v[4], v[5], v[6], v[7]);
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc(tmem, 128);
+}
+
+// dW[co][ci][dp][dt] = (sum over the partials of the CTAs that own (ci / 8, co / 8), in CTA order) / the gradient planes' scale
+__global__ void eq_wgrad_reduce_kernel(const float* __restrict__ partial, int n_cta, const unsigned* __restrict__ maxbits, int Cout, int Cin,
+                                       float* __restrict__ dw) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Cout * Cin * 84) return;
+  const int dt = i % 7, dp = (i / 7) % 12, ci = (i / 84) % Cin, co = i / (84 * Cin);
+  const int pair = (ci >> 3) * 2 + (co >> 3), m = 8 * dt + (ci & 7), n = 8 * (11 - dp) + (co & 7);
+  float s = 0.f;
+  for (int c = pair; c < n_cta; c += 4) s += __ldg(partial + ((size_t)c * 64 + m) * 96 + n);
+  dw[i] = s / (maxbits ? tc_scale_of(__ldg(maxbits)) : 1.f);
+}
+
 // epilogue table of the heads' fused first conv in train mode: scale 1, shift = [tonic bias | key bias]
 __global__ void heads_raw_ss_kernel(const float* __restrict__ bias_t, const float* __restrict__ bias_k, float* __restrict__ ss) {
   const int i = threadIdx.x;
