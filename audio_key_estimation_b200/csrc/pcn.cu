@@ -762,37 +762,44 @@ struct Fwd {
   }
   // dW of a 16-channel equivariant conv on the tensor cores, on stream `ws` (eq_wgrad_umma_kernel); overwrites dw (Cout, Cin, 12, 7)
   bool eqw_ready = false;
+  size_t eqw_x_halves = 0, eqw_g_halves = 0;
   __half* eqw_x[2] = {};
   __half* eqw_g[2] = {};
   float* eqw_partial = nullptr;
+  // equivariant 12 x 7 convs: the "same" convs of both stacks (operand planes with three zero halo columns) and the heads' valid first convs
   bool eq_wgrad_ok(const Conv& c, const ConvGeom& g, int Tn) const {
     static const bool on = [] { const char* e = getenv("AKE_TRAIN_TC_EQ_WGRAD"); return e ? atoi(e) != 0 : true; }();
-    return on && eq_conv_ok(c, g, Tn) && (c.Cin > 8 || c.Cout > 8) && eq_wgrad_smem_bytes(Tn + 6, cdiv(Tn, 16) * 16) <= 227 * 1024 - 256;
+    const bool same = g.pad_t == 3 && g.T_out == Tn, valid = g.pad_t == 0 && g.T_out == Tn - 6;
+    const int n_pairs = cdiv(c.Cin, 8) * cdiv(c.Cout, 8);
+    return on && p->umma && g.KH == 12 && c.KH == 12 && g.KW == 7 && g.SR == 1 && g.row_circ && !g.time_circ && g.row_off == 0 && (same || valid) &&
+           g.rows_v == 12 && g.rows_out == 12 && Tn >= 13 && c.Cin <= 32 && c.Cout <= 32 && n_pairs <= 16 &&
+           eq_wgrad_smem_bytes(Tn + (same ? 6 : 0), cdiv(g.T_out, 16) * 16) <= 227 * 1024 - 256;
   }
-  void eq_wgrad(const View& in, const Conv& c, const View& dz, const unsigned* maxbits, float* dw, cudaStream_t ws) {
-    const int Tn = in.T, Wx = Tn + 6, Wg = cdiv(Tn, 16) * 16;
-    if (!eqw_ready) {
-      for (int i = 0; i < 2; ++i) {
-        eqw_x[i] = arena.take<__half>((size_t)B * 2 * 23 * Wx * 8 + 64 * 8);
-        eqw_g[i] = arena.take<__half>((size_t)B * 2 * 23 * Wg * 8 + 64 * 8);
-      }
-      eqw_partial = arena.take<float>((size_t)sm_count() * 64 * 96);
+  void eq_wgrad(const View& in, const Conv& c, const ConvGeom& g, const View& dz, const unsigned* maxbits, float* dw, cudaStream_t ws) {
+    const bool same = g.pad_t == 3;
+    const int Tn = in.T, To = dz.T, Wx = Tn + (same ? 6 : 0), Wg = cdiv(To, 16) * 16;
+    const int n_gi = cdiv(c.Cin, 8), n_go = cdiv(c.Cout, 8), n_pairs = n_gi * n_go;
+    const size_t xh = (size_t)B * n_gi * 23 * Wx * 8 + 64 * 8, gh = (size_t)B * n_go * 23 * Wg * 8 + 64 * 8;
+    if (!eqw_ready || xh > eqw_x_halves || gh > eqw_g_halves) {  // the heads come first in a backward pass, the larger stack tensors later: regrow
+      eqw_x_halves = std::max(eqw_x_halves, xh), eqw_g_halves = std::max(eqw_g_halves, gh);
+      for (int i = 0; i < 2; ++i) eqw_x[i] = arena.take<__half>(eqw_x_halves), eqw_g[i] = arena.take<__half>(eqw_g_halves);
+      if (!eqw_ready) eqw_partial = arena.take<float>((size_t)sm_count() * 64 * 96);
       eqw_ready = true;
     }
     if (dry) return;
-    EqPackArgs px{in.p, B, in.C, 2, Tn, Wx, 3, 0, 0, nullptr, eqw_x[0], eqw_x[1]};
-    eq_pack_planes_kernel<<<ew_blocks((long long)B * 2 * 23 * Wx), 256, 0, ws>>>(px);
+    EqPackArgs px{in.p, B, in.C, n_gi, Tn, Wx, same ? 3 : 0, 0, 0, nullptr, eqw_x[0], eqw_x[1]};
+    eq_pack_planes_kernel<<<ew_blocks((long long)B * n_gi * 23 * Wx), 256, 0, ws>>>(px);
     AKE_LAUNCHED();
-    EqPackArgs pg{dz.p, B, dz.C, 2, Tn, Wg, 0, 0, 1, maxbits, eqw_g[0], eqw_g[1]};
-    eq_pack_planes_kernel<<<ew_blocks((long long)B * 2 * 23 * Wg), 256, 0, ws>>>(pg);
+    EqPackArgs pg{dz.p, B, dz.C, n_go, To, Wg, 0, 0, 1, maxbits, eqw_g[0], eqw_g[1]};
+    eq_pack_planes_kernel<<<ew_blocks((long long)B * n_go * 23 * Wg), 256, 0, ws>>>(pg);
     AKE_LAUNCHED();
-    EqWgradArgs wa{eqw_x[0], eqw_x[1], eqw_g[0], eqw_g[1], eqw_partial, B, Tn, Wx, Wg};
+    EqWgradArgs wa{eqw_x[0], eqw_x[1], eqw_g[0], eqw_g[1], eqw_partial, B, To, Wx, Wg, n_gi, n_go};
     const size_t smem = eq_wgrad_smem_bytes(Wx, Wg);
     ensure_dyn_smem(eq_wgrad_umma_kernel, smem);
-    const int grid = std::min(4 * B, sm_count() / 4 * 4);
+    const int grid = std::min(n_pairs * B, sm_count() / n_pairs * n_pairs);
     eq_wgrad_umma_kernel<<<grid, kEqWgThreads, smem, ws>>>(wa);
     AKE_LAUNCHED();
-    eq_wgrad_reduce_kernel<<<cdiv(c.Cout * c.Cin * 84, 128), 128, 0, ws>>>(eqw_partial, grid, maxbits, c.Cout, c.Cin, dw);
+    eq_wgrad_reduce_kernel<<<cdiv(c.Cout * c.Cin * 84, 128), 128, 0, ws>>>(eqw_partial, grid, maxbits, c.Cout, c.Cin, n_gi, n_go, dw);
     AKE_LAUNCHED();
   }
   bool tc_wgrad_ok(const Conv& c, const ConvGeom& g, int Tn) const {

@@ -367,7 +367,7 @@ void Fwd::backward_keep(const TrainTape& tp, const float* d_key, const float* d_
     const bool eqw = maxbits != nullptr && !s.in1.p && eq_wgrad_ok(c, s.g, s.in0.T);
     if (dry) {
       if (tc) tc_wgrad(s.in0, s.in1.p ? &s.in1 : nullptr, c, dz, maxbits, nullptr, st);  // (carves the scratch)
-      if (eqw) eq_wgrad(s.in0, c, dz, maxbits, nullptr, st);
+      if (eqw) eq_wgrad(s.in0, c, s.g, dz, maxbits, nullptr, st);
       return;
     }
     const cudaStream_t main_st = st;
@@ -391,7 +391,7 @@ void Fwd::backward_keep(const TrainTape& tp, const float* d_key, const float* d_
       return;
     }
     if (eqw) {  // 16-channel equivariant conv: likewise (eq_wgrad_umma_kernel)
-      eq_wgrad(s.in0, c, dz, maxbits, grads + c.w_off, st);
+      eq_wgrad(s.in0, c, s.g, dz, maxbits, grads + c.w_off, st);
       return;
     }
     WgradArgs a{};
@@ -501,7 +501,7 @@ void Fwd::backward_keep(const TrainTape& tp, const float* d_key, const float* d_
     const bool tc = tp.heads_tc && &h != &tp.hg && n_maxbits < 64 && eq_ready;
     unsigned* mb = tc ? d_maxbits + n_maxbits++ : nullptr;
     View dz0 = bn_bwd(h[0].id, h[0].z, d_a0, mb);
-    wgrad(h[0], dz0);
+    wgrad(h[0], dz0, mb);
     if (tc) heads_dgrad_tc(h[0].id, dz0, mb, ones, zeros, d_pcp, accumulate);
     else dgrad(h[0], dz0, d_pcp, accumulate);
   };

@@ -271,14 +271,15 @@ __global__ void __launch_bounds__(256) eq_pack_planes_kernel(const EqPackArgs a)
     store_split8(a.hi + i * 8, a.lo + i * 8, v);
   }
 }
-// ---- weight gradient of a 16-channel equivariant 12 x 7 conv ("same" in time) as a tensor-core GEMM over positions -----------------------
-//   dW[co, ci, dp, dt] = sum_{b, c, t} dZ[b, co, c, t] * x~[b, ci, (c + dp) mod 12, t + dt]       (x~: the operand planes, three zero halo columns)
+// ---- weight gradient of an equivariant 12 x 7 conv as a tensor-core GEMM over positions -------------------------------------------------------
+//   dW[co, ci, dp, dt] = sum_{b, c, t} dZ[b, co, c, t] * x~[b, ci, (c + dp) mod 12, t + dt]
+// (x~: the conv's operand planes -- three zero halo columns for the "same" convs of the stacks, none for the heads' valid convs)
 // The scheme of p2p_wgrad_umma_kernel with twelve row taps: for input row rho the gradient rows (rho - dp) mod 12, dp = 11 ... 0, are the
 // CONSECUTIVE rows rho ... rho + 11 of a 23-row gradient plane whose row i holds pitch class (i + 1) mod 12 (eq_pack_planes_kernel, row_shift 1):
 //   A (M = 64): rows (dt, ci) of one channel group, K = 16 frames of x~ row rho (time taps 16 B apart: overlapping core matrices)
 //   B (N = 96): columns (j = 11 - dp, co) of one gradient channel group, rows rho + j (SBO = the plane's row pitch)
 // A work item is (clip, input channel group, output channel group); a CTA keeps its (group, group) pair over all its items (the grid is a
-// multiple of four), so its accumulator stays in TMEM; eq_wgrad_reduce_kernel sums the partials of each pair in CTA order.
+// multiple of the number of pairs), so its accumulator stays in TMEM; eq_wgrad_reduce_kernel sums the partials of each pair in CTA order.
 constexpr int kEqWgThreads = 32 * 6;
 struct EqWgradArgs {
   const __half* x_hi;
@@ -287,6 +288,7 @@ struct EqWgradArgs {
   const __half* g_lo;   // [B][2][23][Wg][8]: zeros beyond T, scaled by tc_scale_of(maxbits)
   float* partial;       // [gridDim.x][64][96]
   int B, T, Wx, Wg;
+  int n_gi, n_go;       // channel groups of the input / of the gradient (planes per clip); gridDim.x is a multiple of n_gi * n_go
 };
 __host__ __device__ inline uint32_t eq_wgrad_x_bytes(int Wx) { return (uint32_t)(12 * Wx + 32) * 16; }
 __host__ __device__ inline uint32_t eq_wgrad_g_bytes(int Wg) { return (uint32_t)(23 * Wg + 16) * 16; }
@@ -310,19 +312,19 @@ __global__ void __launch_bounds__(kEqWgThreads, 1) eq_wgrad_umma_kernel(const Eq
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem = tmem_slot;
-  const int n_items = 4 * a.B, n_blk = (a.T + 15) / 16;
-  const int gi = ((int)blockIdx.x & 3) >> 1, go = (int)blockIdx.x & 1;  // fixed per CTA: gridDim.x is a multiple of 4
+  const int n_pairs = a.n_gi * a.n_go, n_items = n_pairs * a.B, n_blk = (a.T + 15) / 16;
+  const int pair = (int)blockIdx.x % n_pairs, gi = pair / a.n_go, go = pair - gi * a.n_go;  // fixed per CTA: gridDim.x is a multiple of n_pairs
 
   if (warp == 4) {
     // ------------------------------------------------------------ loader: 12 input rows and 23 gradient rows, contiguous in their planes
     int k = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++k) {
-      const int b = item >> 2;
+      const int b = item / n_pairs;
       mbar_wait_relaxed(&empty_bar, (k & 1) ^ 1);
       if (lane == 0) {
         const uint32_t xb = (uint32_t)(12 * a.Wx) * 16, gb = (uint32_t)(23 * a.Wg) * 16;
         mbar_arrive_expect_tx(&full_bar, 2 * (xb + gb));
-        const long long xo = (((long long)b * 2 + gi) * 23) * a.Wx * 8, gof = (((long long)b * 2 + go) * 23) * a.Wg * 8;
+        const long long xo = (((long long)b * a.n_gi + gi) * 23) * a.Wx * 8, gof = (((long long)b * a.n_go + go) * 23) * a.Wg * 8;
         bulk_g2s(smem, a.x_hi + xo, xb, &full_bar);
         bulk_g2s(smem + XB, a.x_lo + xo, xb, &full_bar);
         bulk_g2s(smem + 2 * XB, a.g_hi + gof, gb, &full_bar);
@@ -378,13 +380,13 @@ __global__ void __launch_bounds__(kEqWgThreads, 1) eq_wgrad_umma_kernel(const Eq
 
 // dW[co][ci][dp][dt] = (sum over the partials of the CTAs that own (ci / 8, co / 8), in CTA order) / the gradient planes' scale
 __global__ void eq_wgrad_reduce_kernel(const float* __restrict__ partial, int n_cta, const unsigned* __restrict__ maxbits, int Cout, int Cin,
-                                       float* __restrict__ dw) {
+                                       int n_gi, int n_go, float* __restrict__ dw) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= Cout * Cin * 84) return;
   const int dt = i % 7, dp = (i / 7) % 12, ci = (i / 84) % Cin, co = i / (84 * Cin);
-  const int pair = (ci >> 3) * 2 + (co >> 3), m = 8 * dt + (ci & 7), n = 8 * (11 - dp) + (co & 7);
+  const int pair = (ci >> 3) * n_go + (co >> 3), m = 8 * dt + (ci & 7), n = 8 * (11 - dp) + (co & 7);
   float s = 0.f;
-  for (int c = pair; c < n_cta; c += 4) s += __ldg(partial + ((size_t)c * 64 + m) * 96 + n);
+  for (int c = pair; c < n_cta; c += n_gi * n_go) s += __ldg(partial + ((size_t)c * 64 + m) * 96 + n);
   dw[i] = s / (maxbits ? tc_scale_of(__ldg(maxbits)) : 1.f);
 }
 
